@@ -1,0 +1,178 @@
+/*
+ * unreal_b200.h -- C ABI of libunreal_b200.so, the B200-native (sm_100a) implementation of
+ * the UNREAL rollout-and-target hot path of kvas7andy/unreal.
+ *
+ * The reference is pure Python and has no FFI of its own; its boundary is the Python class
+ * API of Environment / Experience / Trainer / RMSPropApplier.  Each entry
+ * point below names the reference function (path:line under /root/reference) whose
+ * arithmetic it replaces; unreal_b200/_lib.py is the ctypes binding and INTEGRATION.md shows
+ * the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - every function returns UNREAL_OK (0) or a negative UNREAL_E* code and never throws;
+ *     unreal_last_error() returns a thread-local message for the last failure.
+ *   - all array arguments are caller-owned DEVICE pointers (e.g. torch.Tensor.data_ptr())
+ *     unless the name ends in _host; "nullable" arguments may be NULL.
+ *   - functions only enqueue work on `stream` (a cudaStream_t passed as void*, NULL = the
+ *     legacy default stream); they do not synchronise, allocate, or keep caller pointers.
+ *     The only library-owned memory is what *_create() returns handles to.
+ *   - layouts are C-contiguous; [T, N] means time-major (one row per rollout step).
+ *   - a handle must not be used from two host threads at once; distinct handles are independent.
+ */
+#ifndef UNREAL_B200_H_
+#define UNREAL_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UNREAL_OK 0
+#define UNREAL_EINVAL (-1) /* bad argument (null, size, dtype, alignment) */
+#define UNREAL_ECUDA (-2)  /* a CUDA runtime call or launch failed */
+#define UNREAL_ESTATE (-3) /* call not valid in the handle's current state */
+#define UNREAL_ENOMEM (-4)
+
+/* element type tags for observation / frame buffers */
+#define UNREAL_F32 0
+#define UNREAL_U8 1 /* 1.0 is stored as 255; loaders divide by 255 (lab/indoor/gym convention) */
+
+#define UNREAL_MAZE_GRID 7
+#define UNREAL_FRAME_HW 84
+#define UNREAL_PC_CELLS 20
+#define UNREAL_MT_WORDS 624
+
+/* ---- library ------------------------------------------------------------------------ */
+const char* unreal_last_error(void);
+int unreal_abi_version(void);
+/* sm count, compute capability of the current device; fails if it is not sm_100. */
+int unreal_device_info(int* sm_count, int* cc_major, int* cc_minor);
+/* tunables used by the benchmarks to A/B kernel variants: "maze_render_variant" (0 direct
+ * 128-bit stores, 1 TMA bulk store from a shared-memory frame template), ... */
+int unreal_set_tunable(const char* name, int value);
+int unreal_get_tunable(const char* name, int* value);
+
+/* ---- maze: environment/maze_environment.py --------------------------------------------
+ * map49_host: the 49-character map of maze_environment.py:18-25 ('+' wall, 'S', 'G'); it is
+ * parsed like _setup (:30-48) and copied to __constant__ memory.  NULL selects the
+ * reference map.  Must be called before any other unreal_maze_* call. */
+int unreal_maze_set_map(const char* map49_host);
+/* start / goal cell of the current map (host ints). */
+int unreal_maze_get_layout(int* start_x, int* start_y, int* goal_x, int* goal_y, uint8_t* walls49_host);
+
+/* reset() (:50-55) for every env with mask[i] != 0 (all when mask is NULL):
+ * pos <- start, last_action <- 0, last_reward <- 0. */
+int unreal_maze_reset(int32_t* pos /*[N,2] x,y*/, int32_t* last_action /*[N]*/, float* last_reward /*[N]*/,
+                      const uint8_t* mask /*[N] nullable*/, int n, void* stream);
+
+/* K1: process(action) (:98-128) for N mazes in one launch: _move/_clamp/_is_wall (:66-91),
+ * reward/terminal (:114-122), render (_get_current_image :93-96, _put_pixel :57-60) and the
+ * pixel change against the previous frame (environment.py:88-99, evaluated in closed form
+ * from the old and new cell).  Updates pos / last_action / last_reward in
+ * place like :125-127.
+ *   active     [N] u8, nullable: envs with 0 are skipped (their rollout already ended);
+ *              they get reward 0, terminal 0, an invalid frame record, obs/pc untouched.
+ *   obs        [N,84,84,3] of obs_dtype, nullable: env.last_state['image'] AFTER the call,
+ *              i.e. the new frame, or the start frame if auto_reset reset the env.
+ *   pc         [N,20,20] f32, nullable.
+ *   frame_rec  [N] u64, nullable: packed ExperienceFrame (experience.py:10-18) of this step
+ *              for unreal_replay_add; layout in DESIGN.md ("frame record").
+ *   auto_reset != 0: an env that reached the goal is reset inside the call, which is what
+ *              the caller does at trainer.py:201-204, :279-296. */
+int unreal_maze_step(int32_t* pos, const int32_t* action /*[N]*/, const uint8_t* active,
+                     float* reward /*[N]*/, uint8_t* terminal /*[N]*/, int32_t* last_action,
+                     float* last_reward, void* obs, int obs_dtype, float* pc, uint64_t* frame_rec,
+                     int n, int auto_reset, void* stream);
+
+/* _get_current_image (:93-96) for M cells: pos [M,2] -> obs [M,84,84,3]. Used to
+ * re-materialise frames sampled from the compact replay ring. */
+int unreal_maze_render(const int32_t* pos, void* obs, int obs_dtype, int m, void* stream);
+
+/* closed-form pixel change between two cells: pos0, pos1 [M,2] -> pc [M,20,20]. */
+int unreal_maze_pixel_change(const int32_t* pos0, const int32_t* pos1, float* pc, int m, void* stream);
+
+/* ---- K2: Environment._calc_pixel_change + _subsample (environment.py:88-99) ------------
+ * literal |cur-prev| over the 2-pixel-cropped frame, mean over channels, 4x4 mean.
+ * cur, prev: [M,H,W,C] of dtype (u8 values are divided by 255); pc: [M,(H-4)/4,(W-4)/4] f32. */
+int unreal_pixel_change(const void* cur, const void* prev, int dtype, float* pc, int m, int h, int w,
+                        int c, void* stream);
+/* stream form: frames [S, L+1, H,W,C]; pc [S, L, ph, pw] with pc[s,i] = change(frames[s,i+1],
+ * frames[s,i]).  Every frame is read from HBM once. */
+int unreal_pixel_change_stream(const void* frames, int dtype, float* pc, int s, int l, int h, int w,
+                               int c, void* stream);
+
+/* ---- K3: n-step returns and advantages, Trainer._process_base (trainer.py:298-324) -----
+ * R_t = r_t + gamma * (term_t ? 0 : R_{t+1}), R_T = boot; adv_t = R_t - v_t.
+ * r, v, out_R, out_adv: [T,N] f32; term [T,N] u8; boot [N] f32 (ignored where the last
+ * step is terminal).  out_adv / v nullable together (that is Trainer._process_vr's scan,
+ * trainer.py:394-403, on time-major data). */
+int unreal_nstep_returns(const float* r, const float* v, const uint8_t* term, const float* boot,
+                         float gamma, float* out_R, float* out_adv, int t, int n, void* stream);
+/* env-major form for sequences gathered from the replay ring: r [N,L] f32, len [N] i32
+ * (number of target steps, <= L), boot [N]; one warp per sequence, shuffle scan. */
+int unreal_sequence_returns(const float* r, const int32_t* len, const float* boot, float gamma,
+                            float* out_R /*[N,L]*/, int n, int l, void* stream);
+
+/* ---- K4: pixel-control Q targets, Trainer._process_pc (trainer.py:352-372) ------------
+ * tgt_t = pc_t + gamma_pc * (term_t ? 0 : tgt_{t+1}); tgt_{len} = boot.
+ * pc, tgt [T,N,20,20] f32; term [T,N] u8 nullable; len [N] i32 nullable (steps >= len are
+ * written as 0); boot [N,20,20]. */
+int unreal_pc_targets(const float* pc, const uint8_t* term, const int32_t* len, const float* boot,
+                      float gamma_pc, float* tgt, int t, int n, void* stream);
+
+/* ---- RNG: numpy legacy RandomState streams, one per env --------------------------------
+ * mt [624,N] u32 (word-major), mt_pos [N] i32.  seed_host: N seeds (RandomState(seed)). */
+int unreal_mt_seed(uint32_t* mt, int32_t* mt_pos, const uint32_t* seeds /*[N] device*/, int n, void* stream);
+/* Trainer.choose_action (trainer.py:147-148) = RandomState.choice(A, p=pi): pi [N,A] f32 ->
+ * action [N] i32; consumes two words per active env. */
+int unreal_choose_action(uint32_t* mt, int32_t* mt_pos, const float* pi, const uint8_t* active,
+                         int32_t* action, int n, int a, void* stream);
+/* raw draws for tests: out [N,K] = randint(0, high) K times per env. */
+int unreal_mt_randint(uint32_t* mt, int32_t* mt_pos, uint32_t high, int32_t* out, int n, int k, void* stream);
+
+/* ---- K5: replay ring, train/experience.py ----------------------------------------------
+ * Device-resident ring of packed frame records, H slots per env (experience.py:48-60). */
+typedef struct unreal_replay unreal_replay_t;
+int unreal_replay_create(unreal_replay_t** out, int n_envs, int history_size);
+int unreal_replay_destroy(unreal_replay_t* r);
+int unreal_replay_reset(unreal_replay_t* r, void* stream);
+/* add_frame (:63-93) for every env whose record is valid. */
+int unreal_replay_add(unreal_replay_t* r, const uint64_t* frame_rec /*[N]*/, void* stream);
+/* is_full (:96-97) per env -> full [N] u8; count/top for tests (nullable). */
+int unreal_replay_state(unreal_replay_t* r, uint8_t* full, int32_t* count, int64_t* top,
+                        int32_t* n_pos, int32_t* n_neg, void* stream);
+/* sample_sequence(L) (:100-118) with the env's own MT stream: start [N], len [N] i32 and
+ * the gathered records rec [N,L] u64 (entries >= len are 0). */
+int unreal_replay_sample_sequence(unreal_replay_t* r, uint32_t* mt, int32_t* mt_pos, int seq_len,
+                                  int32_t* start, int32_t* len, uint64_t* rec, void* stream);
+/* sample_rp_sequence() (:121-153): start [N] i32 (raw position of the first of 4 frames)
+ * and rec [N,4] u64. */
+int unreal_replay_sample_rp(unreal_replay_t* r, uint32_t* mt, int32_t* mt_pos, int32_t* start,
+                            uint64_t* rec, void* stream);
+/* unpack records (any shape, M entries) into SoA fields; every output nullable.
+ * pos0 [M,2] i32 state cell, pos1 [M,2] i32 cell after the move, action/last_action [M] i32,
+ * reward/last_reward [M] f32, terminal/valid [M] u8. */
+int unreal_frame_unpack(const uint64_t* rec, int m, int32_t* pos0, int32_t* pos1, int32_t* action,
+                        float* reward, uint8_t* terminal, int32_t* last_action, float* last_reward,
+                        uint8_t* valid, void* stream);
+
+/* ---- K6: shared RMSProp with global-norm clip, train/rmsprop_applier.py ---------------
+ * _apply_gradients (:109-132): g <- grad * clip / max(||grad||, clip)  (tf.clip_by_global_norm :121)
+ * _apply_dense (:83-93) = TF ApplyRMSProp:  ms += (g*g - ms)*(1-decay);
+ *                         mom = momentum*mom + lr*g/sqrt(ms+eps);  var -= mom.
+ * All of var/rms/mom/grad are flat [P] f32 (the 20 variables concatenated).
+ *   unreal_grad_sumsq   : sumsq[0] += sum(grad^2)  (caller zeroes it; fp32 tree + fp64 atomics)
+ *   unreal_rmsprop_update: mom nullable iff momentum == 0; sumsq is the (all-reduced) sum of
+ *                         squares on device; clip_norm <= 0 disables clipping; grad_scale
+ *                         multiplies grad first (1/world for an averaged all-reduce);
+ *                         writes grad_norm[0] (nullable). */
+int unreal_grad_sumsq(const float* grad, int64_t p, double* sumsq, void* stream);
+int unreal_rmsprop_update(float* var, float* rms, float* mom, const float* grad, int64_t p,
+                          const double* sumsq, float grad_scale, float lr, float decay, float momentum,
+                          float eps, float clip_norm, float* grad_norm, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UNREAL_B200_H_ */

@@ -1,0 +1,486 @@
+// K1: fused maze step + render + pixel-change for thousands of 7x7 mazes (sm_100a).
+//
+// Replaces, per env and per step, MazeEnvironment.process (environment/maze_environment.py:98-128):
+// _move/_clamp/_is_wall (:66-91), reward/terminal (:114-122), _get_current_image (:93-96) and
+// Environment._calc_pixel_change (environment/environment.py:88-99).
+//
+// The kernel is a pure HBM writer: 84 672 B (f32) or 21 168 B (u8) of frame + 1 600 B of
+// pixel-change map per env-step against ~30 B of state read.  Two render variants:
+//   variant 0 (default): one CTA per env in env order; every thread builds its 128-bit words
+//     from per-lane bit masks and stores them directly, 512 contiguous aligned bytes per warp.
+//   variant 1: each persistent CTA keeps wall-only frame templates in shared memory, patches
+//     the 12x12 agent block (144 elements) and hands the whole frame to the TMA engine with
+//     cp.async.bulk (shared -> global), multi-buffered so patching overlaps the store.
+//   variant 2: one warp per env, same mask-built words, no shared memory or barriers.
+// The default is whichever measured fastest on B200 (profiles/).
+#include "common.cuh"
+#include "maze_core.cuh"
+
+namespace unreal {
+
+__constant__ MazeLayout c_maze;
+static MazeLayout h_maze;
+static bool h_maze_ready = false;
+
+static const char kReferenceMap[] =
+    "--+---G"
+    "--+-+++"
+    "S-+---+"
+    "--+++--"
+    "--+-+--"
+    "--+----"
+    "-----++";  // maze_environment.py:18-25
+
+constexpr int kFrameElems = UNREAL_FRAME_HW * UNREAL_FRAME_HW * 3;  // 21168
+constexpr int kRowElems = UNREAL_FRAME_HW * 3;                      // 252
+constexpr int kPcElems = UNREAL_PC_CELLS * UNREAL_PC_CELLS;         // 400
+constexpr int kThreads = 256;
+
+struct StepArgs {
+  int32_t* pos;
+  const int32_t* action;
+  const uint8_t* active;
+  float* reward;
+  uint8_t* terminal;
+  int32_t* last_action;
+  float* last_reward;
+  void* obs;
+  float* pc;
+  uint64_t* rec;
+  int n;
+  int auto_reset;
+};
+
+struct EnvInfo {
+  int rx, ry;          // cell drawn into obs
+  int x0, y0, x1, y1;  // cells defining the pixel change
+  int live;            // 0: env skipped, nothing large is written
+};
+
+// One thread per env: everything of process() except the two big outputs.
+template <bool kStep>
+__device__ __forceinline__ EnvInfo env_logic(const StepArgs& a, int e) {
+  EnvInfo o;
+  int x = a.pos[2 * e], y = a.pos[2 * e + 1];
+  o.rx = x; o.ry = y; o.x0 = x; o.y0 = y; o.x1 = x; o.y1 = y; o.live = 1;
+  if (!kStep) return o;
+  if (a.active != nullptr && a.active[e] == 0) {
+    o.live = 0;
+    a.reward[e] = 0.f;
+    a.terminal[e] = 0;
+    if (a.rec) a.rec[e] = 0ull;
+    return o;
+  }
+  int act = a.action[e];
+  MazeStep s = maze_step_core(c_maze, x, y, act);
+  int la = a.last_action[e];
+  float lr = a.last_reward[e];
+  if (a.rec) a.rec[e] = frame_pack(x, y, s.x1, s.y1, act, s.reward, s.terminal, la, (int)lr);
+  a.reward[e] = (float)s.reward;
+  a.terminal[e] = (uint8_t)s.terminal;
+  o.x1 = s.x1; o.y1 = s.y1;
+  if (s.terminal && a.auto_reset) {  // caller-side reset of trainer.py:201-204,:279-296 + reset() :50-55
+    o.rx = c_maze.start_x; o.ry = c_maze.start_y;
+    a.last_action[e] = 0;
+    a.last_reward[e] = 0.f;
+  } else {
+    o.rx = s.x1; o.ry = s.y1;
+    a.last_action[e] = act;             // :126
+    a.last_reward[e] = (float)s.reward; // :127
+  }
+  a.pos[2 * e] = o.rx;
+  a.pos[2 * e + 1] = o.ry;
+  return o;
+}
+
+// 100 threads write the 20x20 map of one env as float4: k/48 with
+// k = ov(i,y0)*ov(j,x0) + ov(i,y1)*ov(j,x1), 0 when the agent did not move.
+__device__ __forceinline__ void write_pc(float* pc, const EnvInfo& f, int q) {
+  int i = q / 5, j0 = (q - i * 5) * 4;
+  bool moved = (f.x0 != f.x1) || (f.y0 != f.y1);
+  int wy0 = pc_overlap(i, f.y0), wy1 = pc_overlap(i, f.y1);
+  float v[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    int k = moved ? wy0 * pc_overlap(j0 + u, f.x0) + wy1 * pc_overlap(j0 + u, f.x1) : 0;
+    v[u] = (float)k / 48.0f;  // IEEE division: equals float32 of the reference's float64 means
+  }
+  reinterpret_cast<float4*>(pc)[q] = make_float4(v[0], v[1], v[2], v[3]);
+}
+
+template <typename T> struct One;
+template <> struct One<float> { static __device__ __forceinline__ float v() { return 1.0f; } };
+template <> struct One<uint8_t> { static __device__ __forceinline__ uint8_t v() { return 255; } };
+
+// ------------------------------------------------------------------------------------
+// variant 1: shared-memory frame templates + TMA bulk stores.
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, uint32_t bytes) {
+  uint32_t s = (uint32_t)__cvta_generic_to_shared(ssrc);
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(s), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int kPending>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kPending) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+template <typename T>
+__device__ __forceinline__ void set_agent(T* buf, int x, int y, int t, T val) {
+  // t in [0,144): pixel (12x + t%12, 12y + t/12), channel 1   (_put_pixel :57-60)
+  int j = t / 12, i = t - j * 12;
+  buf[((12 * y + j) * UNREAL_FRAME_HW + 12 * x + i) * 3 + 1] = val;
+}
+
+template <typename T, int kBufs, bool kStep>
+__global__ void __launch_bounds__(kThreads) maze_tma_kernel(StepArgs a) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  __shared__ EnvInfo s_info[2];
+  T* bufs = reinterpret_cast<T*>(smem_raw);
+  const int tid = threadIdx.x;
+  constexpr uint32_t kFrameBytes = kFrameElems * sizeof(T);
+
+  // prologue: wall-only template (channel 0) in every buffer   (_setup :30-41)
+  for (int i = tid; i < kFrameElems; i += kThreads) {
+    int row = i / kRowElems;
+    int f = i - row * kRowElems;
+    int px = f / 3;
+    int chn = f - px * 3;
+    bool on = (chn == 0) && ((c_maze.wall_rows[row / 12] >> (px / 12)) & 1u);
+    T v = on ? One<T>::v() : (T)0;
+#pragma unroll
+    for (int b = 0; b < kBufs; ++b) bufs[(size_t)b * kFrameElems + i] = v;
+  }
+  int drawn[kBufs];  // agent cell currently patched into buffer b (x | y<<4), -1 none
+#pragma unroll
+  for (int b = 0; b < kBufs; ++b) drawn[b] = -1;
+  fence_async_smem();  // template writes must be visible to the TMA engine too
+  __syncthreads();
+
+  int it = 0;
+  for (int e = blockIdx.x; e < a.n; e += gridDim.x, ++it) {
+    const int b = it % kBufs;
+    if (tid == 0) {
+      s_info[it & 1] = env_logic<kStep>(a, e);
+      bulk_wait_read<kBufs - 1>();  // the store issued kBufs iterations ago has drained buffer b
+    }
+    __syncthreads();
+    const EnvInfo f = s_info[it & 1];
+    const bool store = f.live && a.obs != nullptr;
+    if (f.live && a.pc != nullptr && tid < kPcElems / 4) write_pc(a.pc + (size_t)e * kPcElems, f, tid);
+    if (store) {
+      T* buf = bufs + (size_t)b * kFrameElems;
+      int want = f.rx | (f.ry << 4);
+      int have = -1;
+#pragma unroll
+      for (int k = 0; k < kBufs; ++k) have = (k == b) ? drawn[k] : have;
+      if (have != want && tid < 144) {
+        if (have >= 0) set_agent<T>(buf, have & 15, have >> 4, tid, (T)0);
+        set_agent<T>(buf, f.rx, f.ry, tid, One<T>::v());
+        fence_async_smem();  // generic-proxy writes -> visible to the async (TMA) proxy
+      }
+#pragma unroll
+      for (int k = 0; k < kBufs; ++k) drawn[k] = (k == b) ? want : drawn[k];
+    }
+    __syncthreads();
+    if (tid == 0) {
+      if (store) bulk_store(reinterpret_cast<T*>(a.obs) + (size_t)e * kFrameElems,
+                            bufs + (size_t)b * kFrameElems, kFrameBytes);
+      bulk_commit();  // one group per iteration (possibly empty) keeps the wait arithmetic uniform
+    }
+  }
+  if (tid == 0) bulk_wait_all();
+}
+
+// ------------------------------------------------------------------------------------
+// variant 2: one warp per env, no shared memory, no barriers.
+// A frame is a sequence of identical-size "groups" of 63 x 16 B = 1008 B: one pixel row for
+// f32 (252 floats), four pixel rows for u8 (4 x 252 B).  All groups of one maze-cell row
+// ("band", 12 pixel rows) are identical, so a lane computes the two 16-byte chunks it owns
+// (lane, lane+32) once per band from per-lane bit masks and stores them to every group of
+// the band: 512 contiguous bytes per warp store instruction.
+// A 16-byte chunk covers < 6 pixels, hence at most two maze-cell columns (A and B).
+// ------------------------------------------------------------------------------------
+template <typename T> struct Chunk;
+template <> struct Chunk<float> { static constexpr int kElems = 4, kGroupsPerBand = 12; };
+template <> struct Chunk<uint8_t> { static constexpr int kElems = 16, kGroupsPerBand = 3; };
+
+struct ChunkMasks {
+  uint32_t wallA[4], wallB[4], agentA[4], agentB[4];  // all-ones element patterns
+  int cxA, cxB;
+};
+
+template <typename T>
+__device__ __forceinline__ ChunkMasks make_masks(int chunk) {
+  ChunkMasks m;
+#pragma unroll
+  for (int w = 0; w < 4; ++w) m.wallA[w] = m.wallB[w] = m.agentA[w] = m.agentB[w] = 0u;
+  constexpr int E = Chunk<T>::kElems;
+  const int first = (chunk * E) % kRowElems;
+  m.cxA = (first / 3) / 12;
+  m.cxB = m.cxA;
+#pragma unroll
+  for (int i = 0; i < E; ++i) {
+    int col = (chunk * E + i) % kRowElems;
+    int px = col / 3, ch = col - px * 3, cx = px / 12;
+    uint32_t bits = (sizeof(T) == 4) ? 0x3f800000u : (0xffu << (8 * (i & 3)));
+    int w = (sizeof(T) == 4) ? i : (i >> 2);
+    bool isA = (cx == m.cxA);
+    if (!isA) m.cxB = cx;
+    if (ch == 0) { if (isA) m.wallA[w] |= bits; else m.wallB[w] |= bits; }
+    if (ch == 1) { if (isA) m.agentA[w] |= bits; else m.agentB[w] |= bits; }
+  }
+  return m;
+}
+
+__device__ __forceinline__ uint4 band_value(const ChunkMasks& m, uint32_t walls, bool agent_band, int ax) {
+  uint32_t wa = ((walls >> m.cxA) & 1u) ? 0xffffffffu : 0u;
+  uint32_t wb = ((walls >> m.cxB) & 1u) ? 0xffffffffu : 0u;
+  uint32_t aa = (agent_band && m.cxA == ax) ? 0xffffffffu : 0u;
+  uint32_t ab = (agent_band && m.cxB == ax) ? 0xffffffffu : 0u;
+  uint4 v;
+  v.x = (m.wallA[0] & wa) | (m.wallB[0] & wb) | (m.agentA[0] & aa) | (m.agentB[0] & ab);
+  v.y = (m.wallA[1] & wa) | (m.wallB[1] & wb) | (m.agentA[1] & aa) | (m.agentB[1] & ab);
+  v.z = (m.wallA[2] & wa) | (m.wallB[2] & wb) | (m.agentA[2] & aa) | (m.agentB[2] & ab);
+  v.w = (m.wallA[3] & wa) | (m.wallB[3] & wb) | (m.agentA[3] & aa) | (m.agentB[3] & ab);
+  return v;
+}
+
+template <typename T, bool kStep, int kWarps>
+__global__ void __launch_bounds__(kWarps * 32) maze_warp_kernel(StepArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int e = blockIdx.x * kWarps + (threadIdx.x >> 5);
+  if (e >= a.n) return;
+  int packed = 0;
+  if (lane == 0) {
+    EnvInfo f = env_logic<kStep>(a, e);
+    packed = f.rx | (f.ry << 3) | (f.x0 << 6) | (f.y0 << 9) | (f.x1 << 12) | (f.y1 << 15) | (f.live << 18);
+  }
+  packed = __shfl_sync(0xffffffffu, packed, 0);
+  EnvInfo f;
+  f.rx = packed & 7; f.ry = (packed >> 3) & 7; f.x0 = (packed >> 6) & 7; f.y0 = (packed >> 9) & 7;
+  f.x1 = (packed >> 12) & 7; f.y1 = (packed >> 15) & 7; f.live = (packed >> 18) & 1;
+  if (!f.live) return;
+  if (a.pc != nullptr) {
+    float* pc = a.pc + (size_t)e * kPcElems;
+#pragma unroll
+    for (int q = lane; q < kPcElems / 4; q += 32) write_pc(pc, f, q);
+  }
+  if (a.obs == nullptr) return;
+  constexpr int G = Chunk<T>::kGroupsPerBand;
+  constexpr int kChunksPerGroup = 63;
+  const ChunkMasks m0 = make_masks<T>(lane);
+  const ChunkMasks m1 = make_masks<T>(lane + 32);
+  const bool has1 = lane + 32 < kChunksPerGroup;
+  uint4* out = reinterpret_cast<uint4*>(reinterpret_cast<T*>(a.obs) + (size_t)e * kFrameElems) + lane;
+#pragma unroll
+  for (int cy = 0; cy < UNREAL_MAZE_GRID; ++cy) {
+    const uint32_t walls = c_maze.wall_rows[cy];
+    const uint4 v0 = band_value(m0, walls, cy == f.ry, f.rx);
+    const uint4 v1 = band_value(m1, walls, cy == f.ry, f.rx);
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      uint4* p = out + (size_t)(cy * G + g) * kChunksPerGroup;
+      __stcs(p, v0);
+      if (has1) __stcs(p + 32, v1);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// variant 0 (default): one CTA per env, launched non-persistently in env order.
+// Thread t owns chunk column t % 63 of groups t / 63 + R*j (R = kThreads / 63), so one pass
+// of the CTA writes R whole groups = R*1008 contiguous bytes and every warp store is 512
+// contiguous, sector-aligned bytes.  Measured on B200 (profiles/store_patterns_r1.md):
+// in-order one-CTA-per-env beats persistent/strided and warp-per-env write patterns.
+// ------------------------------------------------------------------------------------
+template <typename T, bool kStep, int kThreads>
+__global__ void __launch_bounds__(kThreads) maze_cta_kernel(StepArgs a) {
+  __shared__ EnvInfo s_info;
+  constexpr int kChunksPerGroup = 63;
+  constexpr int R = kThreads / kChunksPerGroup;
+  constexpr int G = Chunk<T>::kGroupsPerBand;
+  constexpr int kGroups = G * UNREAL_MAZE_GRID;
+  const int tid = threadIdx.x;
+  const int e = blockIdx.x;
+  if (tid == 0) s_info = env_logic<kStep>(a, e);
+  const int gsub = tid / kChunksPerGroup;
+  const int c = tid - gsub * kChunksPerGroup;
+  const ChunkMasks m = make_masks<T>(c);   // overlaps the logic thread's global loads
+  __syncthreads();
+  const EnvInfo f = s_info;
+  if (!f.live) return;
+  if (a.pc != nullptr && tid >= kThreads - kPcElems / 4) write_pc(a.pc + (size_t)e * kPcElems, f, tid - (kThreads - kPcElems / 4));
+  if (a.obs == nullptr || gsub >= R) return;
+  uint4* out = reinterpret_cast<uint4*>(reinterpret_cast<T*>(a.obs) + (size_t)e * kFrameElems) + c;
+#pragma unroll
+  for (int j = 0; j < (kGroups + R - 1) / R; ++j) {
+    const int g = gsub + R * j;
+    if (g < kGroups) {
+      const int cy = g / G;
+      __stcs(out + (size_t)g * kChunksPerGroup, band_value(m, c_maze.wall_rows[cy], cy == f.ry, f.rx));
+    }
+  }
+}
+
+// pixel change between arbitrary cell pairs (re-materialising maps of replayed frames)
+__global__ void __launch_bounds__(128) maze_pc_pairs_kernel(const int32_t* __restrict__ p0,
+                                                            const int32_t* __restrict__ p1, float* pc, int m) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  int e = idx / (kPcElems / 4), q = idx - e * (kPcElems / 4);
+  if (e >= m) return;
+  EnvInfo f;
+  f.x0 = p0[2 * e]; f.y0 = p0[2 * e + 1]; f.x1 = p1[2 * e]; f.y1 = p1[2 * e + 1];
+  f.rx = f.ry = 0; f.live = 1;
+  write_pc(pc + (size_t)e * kPcElems, f, q);
+}
+
+__global__ void maze_reset_kernel(int32_t* pos, int32_t* last_action, float* last_reward, const uint8_t* mask,
+                                  int n) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n || (mask != nullptr && mask[e] == 0)) return;
+  pos[2 * e] = c_maze.start_x;
+  pos[2 * e + 1] = c_maze.start_y;
+  if (last_action) last_action[e] = 0;
+  if (last_reward) last_reward[e] = 0.f;
+}
+
+static int ensure_map() {
+  if (h_maze_ready) return UNREAL_OK;
+  return unreal_maze_set_map(nullptr);
+}
+
+template <bool kStep>
+static int launch_render(const StepArgs& a, int obs_dtype, cudaStream_t st) {
+  if (a.n == 0) return UNREAL_OK;
+  const int sms = sm_count();
+  if (sms <= 0) return UNREAL_ECUDA;
+  // defaults = fastest measured on B200 (profiles/microbench_r1.md): f32 -> CTA per env with
+  // 256 threads (99% of measured HBM peak), u8 -> warp per env.
+  int variant = get_tunable("maze_render_variant", -1);
+  if (variant < 0) variant = (obs_dtype == UNREAL_U8 && a.obs != nullptr) ? 2 : 0;
+  if (a.obs == nullptr && variant == 1) variant = 0;  // nothing to stage through shared memory
+  if (variant == 2) {
+    constexpr int kWarps = 4;
+    int grid = (a.n + kWarps - 1) / kWarps;
+    if (obs_dtype == UNREAL_F32) maze_warp_kernel<float, kStep, kWarps><<<grid, kWarps * 32, 0, st>>>(a);
+    else maze_warp_kernel<uint8_t, kStep, kWarps><<<grid, kWarps * 32, 0, st>>>(a);
+    UNREAL_LAUNCH_CHECK("maze_warp_kernel");
+    return UNREAL_OK;
+  }
+  if (variant == 0) {
+    if (obs_dtype == UNREAL_F32) {
+      if (get_tunable("maze_cta_threads", 256) == 512) maze_cta_kernel<float, kStep, 512><<<a.n, 512, 0, st>>>(a);
+      else maze_cta_kernel<float, kStep, 256><<<a.n, 256, 0, st>>>(a);
+    } else {
+      if (get_tunable("maze_cta_threads", 256) == 512) maze_cta_kernel<uint8_t, kStep, 512><<<a.n, 512, 0, st>>>(a);
+      else maze_cta_kernel<uint8_t, kStep, 256><<<a.n, 256, 0, st>>>(a);
+    }
+    UNREAL_LAUNCH_CHECK("maze_cta_kernel");
+    return UNREAL_OK;
+  }
+  if (obs_dtype == UNREAL_F32) {
+    constexpr int kBufs = 2;
+    size_t smem = (size_t)kBufs * kFrameElems * sizeof(float);
+    auto k = maze_tma_kernel<float, kBufs, kStep>;
+    UNREAL_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int grid = a.n < sms ? a.n : sms;
+    k<<<grid, kThreads, smem, st>>>(a);
+    UNREAL_LAUNCH_CHECK("maze_tma_kernel<f32>");
+  } else {
+    constexpr int kBufs = 4;
+    size_t smem = (size_t)kBufs * kFrameElems * sizeof(uint8_t);
+    auto k = maze_tma_kernel<uint8_t, kBufs, kStep>;
+    UNREAL_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = get_tunable("maze_u8_ctas_per_sm", 2);
+    int grid = a.n < sms * per_sm ? a.n : sms * per_sm;
+    k<<<grid, kThreads, smem, st>>>(a);
+    UNREAL_LAUNCH_CHECK("maze_tma_kernel<u8>");
+  }
+  return UNREAL_OK;
+}
+
+}  // namespace unreal
+
+using namespace unreal;
+
+extern "C" int unreal_maze_set_map(const char* map49_host) {
+  const char* m = map49_host ? map49_host : kReferenceMap;
+  MazeLayout L;
+  for (int y = 0; y < UNREAL_MAZE_GRID; ++y) L.wall_rows[y] = 0;
+  L.start_x = L.start_y = L.goal_x = L.goal_y = -1;
+  for (int i = 0; i < UNREAL_MAZE_GRID * UNREAL_MAZE_GRID; ++i) {
+    char c = m[i];
+    UNREAL_REQUIRE(c != 0, "maze map shorter than 49 characters");
+    int x = i % UNREAL_MAZE_GRID, y = i / UNREAL_MAZE_GRID;
+    if (c == '+') L.wall_rows[y] |= 1u << x;
+    else if (c == 'S') { L.start_x = x; L.start_y = y; }
+    else if (c == 'G') { L.goal_x = x; L.goal_y = y; }
+  }
+  UNREAL_REQUIRE(L.start_x >= 0, "maze map has no 'S' cell");
+  UNREAL_CUDA(cudaMemcpyToSymbol(c_maze, &L, sizeof(L)));
+  h_maze = L;
+  h_maze_ready = true;
+  return UNREAL_OK;
+}
+
+extern "C" int unreal_maze_get_layout(int* sx, int* sy, int* gx, int* gy, uint8_t* walls49_host) {
+  int rc = ensure_map();
+  if (rc) return rc;
+  if (sx) *sx = h_maze.start_x;
+  if (sy) *sy = h_maze.start_y;
+  if (gx) *gx = h_maze.goal_x;
+  if (gy) *gy = h_maze.goal_y;
+  if (walls49_host)
+    for (int i = 0; i < 49; ++i) walls49_host[i] = (h_maze.wall_rows[i / 7] >> (i % 7)) & 1u;
+  return UNREAL_OK;
+}
+
+extern "C" int unreal_maze_reset(int32_t* pos, int32_t* last_action, float* last_reward, const uint8_t* mask,
+                                 int n, void* stream) {
+  UNREAL_REQUIRE(pos != nullptr && n >= 0, "unreal_maze_reset: pos is null or n < 0");
+  int rc = ensure_map();
+  if (rc) return rc;
+  if (n == 0) return UNREAL_OK;
+  maze_reset_kernel<<<(n + 255) / 256, 256, 0, as_stream(stream)>>>(pos, last_action, last_reward, mask, n);
+  UNREAL_LAUNCH_CHECK("maze_reset_kernel");
+  return UNREAL_OK;
+}
+
+extern "C" int unreal_maze_step(int32_t* pos, const int32_t* action, const uint8_t* active, float* reward,
+                                uint8_t* terminal, int32_t* last_action, float* last_reward, void* obs,
+                                int obs_dtype, float* pc, uint64_t* frame_rec, int n, int auto_reset,
+                                void* stream) {
+  UNREAL_REQUIRE(n >= 0, "unreal_maze_step: n < 0");
+  UNREAL_REQUIRE(pos && action && reward && terminal && last_action && last_reward,
+                 "unreal_maze_step: pos/action/reward/terminal/last_action/last_reward must be non-null");
+  UNREAL_REQUIRE(obs_dtype == UNREAL_F32 || obs_dtype == UNREAL_U8, "unreal_maze_step: bad obs_dtype %d", obs_dtype);
+  UNREAL_REQUIRE(aligned16(obs) && aligned16(pc), "unreal_maze_step: obs and pc must be 16-byte aligned");
+  int rc = ensure_map();
+  if (rc) return rc;
+  StepArgs a{pos, action, active, reward, terminal, last_action, last_reward, obs, pc, frame_rec, n, auto_reset};
+  return launch_render<true>(a, obs_dtype, as_stream(stream));
+}
+
+extern "C" int unreal_maze_render(const int32_t* pos, void* obs, int obs_dtype, int m, void* stream) {
+  UNREAL_REQUIRE(pos && obs && m >= 0, "unreal_maze_render: null argument or m < 0");
+  UNREAL_REQUIRE(obs_dtype == UNREAL_F32 || obs_dtype == UNREAL_U8, "unreal_maze_render: bad obs_dtype %d", obs_dtype);
+  UNREAL_REQUIRE(aligned16(obs), "unreal_maze_render: obs must be 16-byte aligned");
+  int rc = ensure_map();
+  if (rc) return rc;
+  StepArgs a{const_cast<int32_t*>(pos), nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, obs, nullptr, nullptr, m, 0};
+  return launch_render<false>(a, obs_dtype, as_stream(stream));
+}
+
+extern "C" int unreal_maze_pixel_change(const int32_t* pos0, const int32_t* pos1, float* pc, int m, void* stream) {
+  UNREAL_REQUIRE(pos0 && pos1 && pc && m >= 0, "unreal_maze_pixel_change: null argument or m < 0");
+  UNREAL_REQUIRE(aligned16(pc), "unreal_maze_pixel_change: pc must be 16-byte aligned");
+  if (m == 0) return UNREAL_OK;
+  long long threads = (long long)m * (kPcElems / 4);
+  maze_pc_pairs_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, as_stream(stream)>>>(pos0, pos1, pc, m);
+  UNREAL_LAUNCH_CHECK("maze_pc_pairs_kernel");
+  return UNREAL_OK;
+}

@@ -1,0 +1,166 @@
+"""Thin tensor-level wrappers over the C ABI (one function per entry point family).
+
+All tensors are CUDA tensors owned by the caller; the wrappers allocate outputs when they
+are not passed in, enqueue on torch's current stream and never synchronise.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import call, ptr, stream_ptr
+
+FRAME = 84
+PC = 20
+MT_WORDS = 624
+
+
+# ---------------------------------------------------------------------------- maze
+def maze_set_map(map49=None):
+  call("unreal_maze_set_map", None if map49 is None else map49.encode())
+
+
+def maze_layout():
+  v = [ctypes.c_int() for _ in range(4)]
+  walls = (ctypes.c_uint8 * 49)()
+  call("unreal_maze_get_layout", *[ctypes.byref(x) for x in v], walls)
+  return (v[0].value, v[1].value), (v[2].value, v[3].value), bytes(walls)
+
+
+class MazeState(object):
+  """SoA device state of N mazes: what MazeEnvironment keeps in self.x/self.y/last_action/
+  last_reward (maze_environment.py:50-55, :125-127)."""
+
+  def __init__(self, n, device):
+    self.n = n
+    self.device = torch.device(device)
+    self.pos = torch.zeros(n, 2, dtype=torch.int32, device=device)
+    self.last_action = torch.zeros(n, dtype=torch.int32, device=device)
+    self.last_reward = torch.zeros(n, dtype=torch.float32, device=device)
+    maze_reset(self)
+
+
+def maze_reset(state, mask=None):
+  call("unreal_maze_reset", ptr(state.pos, torch.int32), ptr(state.last_action, torch.int32),
+       ptr(state.last_reward, torch.float32), ptr(mask, torch.uint8), state.n, stream_ptr())
+
+
+def maze_step(state, action, obs=None, pc=None, reward=None, terminal=None, frame_rec=None, active=None,
+              auto_reset=False):
+  """One process() for every env.  Returns (reward, terminal); obs/pc/frame_rec are filled
+  when given (pass None to skip that output)."""
+  n = state.n
+  dev = state.device
+  if reward is None:
+    reward = torch.empty(n, dtype=torch.float32, device=dev)
+  if terminal is None:
+    terminal = torch.empty(n, dtype=torch.uint8, device=dev)
+  if obs is not None and obs.numel() != n * FRAME * FRAME * 3:
+    raise _lib.UnrealError("obs must hold [N,84,84,3]")
+  if pc is not None and (pc.numel() != n * PC * PC or pc.dtype != torch.float32):
+    raise _lib.UnrealError("pc must be float32 [N,20,20]")
+  call("unreal_maze_step", ptr(state.pos, torch.int32), ptr(action, torch.int32, "action"),
+       ptr(active, torch.uint8, "active"), ptr(reward, torch.float32), ptr(terminal, torch.uint8),
+       ptr(state.last_action, torch.int32), ptr(state.last_reward, torch.float32),
+       ptr(obs), _lib.dtype_tag(obs) if obs is not None else _lib.F32, ptr(pc),
+       ptr(frame_rec, torch.int64, "frame_rec"), n, 1 if auto_reset else 0, stream_ptr())
+  return reward, terminal
+
+
+def maze_render(pos, out=None, dtype=torch.float32):
+  m = pos.shape[0]
+  if out is None:
+    out = torch.empty(m, FRAME, FRAME, 3, dtype=dtype, device=pos.device)
+  call("unreal_maze_render", ptr(pos, torch.int32, "pos"), ptr(out), _lib.dtype_tag(out), m, stream_ptr())
+  return out
+
+
+def maze_pixel_change(pos0, pos1, out=None):
+  m = pos0.shape[0]
+  if out is None:
+    out = torch.empty(m, PC, PC, dtype=torch.float32, device=pos0.device)
+  call("unreal_maze_pixel_change", ptr(pos0, torch.int32), ptr(pos1, torch.int32), ptr(out, torch.float32), m,
+       stream_ptr())
+  return out
+
+
+# ---------------------------------------------------------------------------- pixel change (generic)
+def pixel_change(cur, prev, out=None):
+  """cur, prev [M,H,W,C] float32 or uint8 -> [M,(H-4)//4,(W-4)//4] float32."""
+  m, h, w, c = cur.shape
+  if out is None:
+    out = torch.empty(m, (h - 4) // 4, (w - 4) // 4, dtype=torch.float32, device=cur.device)
+  if prev.shape != cur.shape or prev.dtype != cur.dtype:
+    raise _lib.UnrealError("cur and prev must have the same shape and dtype")
+  call("unreal_pixel_change", ptr(cur), ptr(prev), _lib.dtype_tag(cur), ptr(out, torch.float32), m, h, w, c,
+       stream_ptr())
+  return out
+
+
+def pixel_change_stream(frames, out=None):
+  """frames [S,L+1,H,W,C] -> [S,L,ph,pw]; each frame is read once."""
+  s, l1, h, w, c = frames.shape
+  if out is None:
+    out = torch.empty(s, l1 - 1, (h - 4) // 4, (w - 4) // 4, dtype=torch.float32, device=frames.device)
+  call("unreal_pixel_change_stream", ptr(frames), _lib.dtype_tag(frames), ptr(out, torch.float32), s, l1 - 1, h, w,
+       c, stream_ptr())
+  return out
+
+
+# ---------------------------------------------------------------------------- targets
+def nstep_returns(r, v, term, boot, gamma, out_R=None, out_adv=None):
+  t, n = r.shape
+  if out_R is None:
+    out_R = torch.empty_like(r)
+  if v is not None and out_adv is None:
+    out_adv = torch.empty_like(r)
+  call("unreal_nstep_returns", ptr(r, torch.float32), ptr(v, torch.float32), ptr(term, torch.uint8),
+       ptr(boot, torch.float32), float(gamma), ptr(out_R, torch.float32), ptr(out_adv, torch.float32), t, n,
+       stream_ptr())
+  return out_R, out_adv
+
+
+def sequence_returns(r, length, boot, gamma, out=None):
+  n, l = r.shape
+  if out is None:
+    out = torch.empty_like(r)
+  call("unreal_sequence_returns", ptr(r, torch.float32), ptr(length, torch.int32), ptr(boot, torch.float32),
+       float(gamma), ptr(out, torch.float32), n, l, stream_ptr())
+  return out
+
+
+def pc_targets(pc, term, length, boot, gamma_pc, out=None):
+  t, n = pc.shape[0], pc.shape[1]
+  if out is None:
+    out = torch.empty_like(pc)
+  call("unreal_pc_targets", ptr(pc, torch.float32), ptr(term, torch.uint8), ptr(length, torch.int32),
+       ptr(boot, torch.float32), float(gamma_pc), ptr(out, torch.float32), t, n, stream_ptr())
+  return out
+
+
+# ---------------------------------------------------------------------------- RNG
+class MtStreams(object):
+  """One numpy-legacy RandomState stream per env, resident on the device."""
+
+  def __init__(self, seeds, device):
+    seeds = torch.as_tensor(seeds, dtype=torch.int64).to(device)
+    self.n = seeds.numel()
+    self.device = torch.device(device)
+    self.mt = torch.empty(MT_WORDS, self.n, dtype=torch.int32, device=device)
+    self.pos = torch.empty(self.n, dtype=torch.int32, device=device)
+    s32 = (seeds & 0xFFFFFFFF).to(torch.int64)
+    s32 = torch.where(s32 >= 2 ** 31, s32 - 2 ** 32, s32).to(torch.int32)  # same 32 bits
+    call("unreal_mt_seed", ptr(self.mt), ptr(self.pos), ptr(s32), self.n, stream_ptr())
+
+  def randint(self, high, k=1):
+    out = torch.empty(self.n, k, dtype=torch.int32, device=self.device)
+    call("unreal_mt_randint", ptr(self.mt), ptr(self.pos), int(high), ptr(out), self.n, k, stream_ptr())
+    return out
+
+  def choose_action(self, pi, active=None, out=None):
+    n, a = pi.shape
+    if out is None:
+      out = torch.zeros(n, dtype=torch.int32, device=self.device)
+    call("unreal_choose_action", ptr(self.mt), ptr(self.pos), ptr(pi, torch.float32, "pi"),
+         ptr(active, torch.uint8), ptr(out, torch.int32), n, a, stream_ptr())
+    return out
