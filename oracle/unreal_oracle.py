@@ -347,10 +347,12 @@ def global_norm(grads, dtype=np.float32):
 
 
 def clip_by_global_norm(grads, clip_norm, dtype=np.float32):
-  """``tf.clip_by_global_norm`` as called at rmsprop_applier.py:121:
-  ``g * clip / max(norm, clip)``.  -> (clipped list, norm)."""
+  """``tf.clip_by_global_norm`` as called at rmsprop_applier.py:121.  TensorFlow documents
+  ``g * clip / max(norm, clip)`` and evaluates it as ``g * (clip * min(1/norm, 1/clip))``
+  (tensorflow/python/ops/clip_ops.py); the latter is restated.  -> (clipped list, norm)."""
   norm = global_norm(grads, dtype)
-  scale = dtype(clip_norm) / max(norm, dtype(clip_norm))
+  one = dtype(1.0)
+  scale = dtype(clip_norm) * min(one / norm, one / dtype(clip_norm)) if norm > 0 else one
   return [np.asarray(g, dtype=dtype) * scale for g in grads], norm
 
 

@@ -164,3 +164,98 @@ class MtStreams(object):
     call("unreal_choose_action", ptr(self.mt), ptr(self.pos), ptr(pi, torch.float32, "pi"),
          ptr(active, torch.uint8), ptr(out, torch.int32), n, a, stream_ptr())
     return out
+
+
+# ---------------------------------------------------------------------------- replay ring
+class ReplayRing(object):
+  """Device ring of packed frame records, H slots for each of N envs (library-owned)."""
+
+  def __init__(self, n_envs, history_size, device):
+    self.n = int(n_envs)
+    self.h = int(history_size)
+    self.device = torch.device(device)
+    h = ctypes.c_void_p()
+    with torch.cuda.device(self.device):
+      _lib.check(_lib.lib.unreal_replay_create(ctypes.byref(h), self.n, self.h), "unreal_replay_create")
+    self._h = h
+
+  def close(self):
+    if self._h is not None:
+      _lib.lib.unreal_replay_destroy(self._h)
+      self._h = None
+
+  def __del__(self):
+    try:
+      self.close()
+    except Exception:
+      pass
+
+  def reset(self):
+    call("unreal_replay_reset", self._h, stream_ptr())
+
+  def add(self, frame_rec):
+    if frame_rec.numel() != self.n:
+      raise _lib.UnrealError("frame_rec must hold one record per env")
+    call("unreal_replay_add", self._h, ptr(frame_rec, torch.int64, "frame_rec"), stream_ptr())
+
+  def state(self):
+    """-> dict(full u8, count i32, top i64, n_pos i32, n_neg i32), each [N]."""
+    d = self.device
+    out = dict(full=torch.empty(self.n, dtype=torch.uint8, device=d),
+               count=torch.empty(self.n, dtype=torch.int32, device=d),
+               top=torch.empty(self.n, dtype=torch.int64, device=d),
+               n_pos=torch.empty(self.n, dtype=torch.int32, device=d),
+               n_neg=torch.empty(self.n, dtype=torch.int32, device=d))
+    call("unreal_replay_state", self._h, ptr(out["full"]), ptr(out["count"]), ptr(out["top"]), ptr(out["n_pos"]),
+         ptr(out["n_neg"]), stream_ptr())
+    return out
+
+  def sample_sequence(self, streams, seq_len):
+    """-> start [N] i32, len [N] i32, rec [N, seq_len] i64 (zero past len)."""
+    d = self.device
+    start = torch.empty(self.n, dtype=torch.int32, device=d)
+    length = torch.empty(self.n, dtype=torch.int32, device=d)
+    rec = torch.empty(self.n, seq_len, dtype=torch.int64, device=d)
+    call("unreal_replay_sample_sequence", self._h, ptr(streams.mt), ptr(streams.pos), int(seq_len), ptr(start),
+         ptr(length), ptr(rec), stream_ptr())
+    return start, length, rec
+
+  def sample_rp(self, streams):
+    """-> start [N] i32 (raw position of the first of four frames), rec [N, 4] i64."""
+    d = self.device
+    start = torch.empty(self.n, dtype=torch.int32, device=d)
+    rec = torch.empty(self.n, 4, dtype=torch.int64, device=d)
+    call("unreal_replay_sample_rp", self._h, ptr(streams.mt), ptr(streams.pos), ptr(start), ptr(rec), stream_ptr())
+    return start, rec
+
+
+def frame_unpack(rec, fields=("pos0", "pos1", "action", "reward", "terminal", "last_action", "last_reward", "valid")):
+  """Packed records (any shape) -> dict of SoA tensors with that shape (+[2] for positions)."""
+  m = rec.numel()
+  d = rec.device
+  shape = tuple(rec.shape)
+  spec = dict(pos0=(torch.int32, shape + (2,)), pos1=(torch.int32, shape + (2,)), action=(torch.int32, shape),
+              reward=(torch.float32, shape), terminal=(torch.uint8, shape), last_action=(torch.int32, shape),
+              last_reward=(torch.float32, shape), valid=(torch.uint8, shape))
+  out = {k: torch.empty(spec[k][1], dtype=spec[k][0], device=d) for k in fields}
+  g = lambda k: ptr(out[k]) if k in out else None  # noqa: E731
+  call("unreal_frame_unpack", ptr(rec, torch.int64, "rec"), m, g("pos0"), g("pos1"), g("action"), g("reward"),
+       g("terminal"), g("last_action"), g("last_reward"), g("valid"), stream_ptr())
+  return out
+
+
+# ---------------------------------------------------------------------------- optimiser
+def grad_sumsq(grad, out=None):
+  """sum(grad^2) as a device double; `out` (1-element float64) is accumulated into."""
+  if out is None:
+    out = torch.zeros(1, dtype=torch.float64, device=grad.device)
+  call("unreal_grad_sumsq", ptr(grad, torch.float32, "grad"), grad.numel(), ptr(out, torch.float64), stream_ptr())
+  return out
+
+
+def rmsprop_update(var, rms, mom, grad, sumsq, lr, decay, momentum, eps, clip_norm, grad_scale=1.0, grad_norm=None):
+  call("unreal_rmsprop_update", ptr(var, torch.float32, "var"), ptr(rms, torch.float32, "rms"),
+       ptr(mom, torch.float32, "mom"), ptr(grad, torch.float32, "grad"), var.numel(),
+       ptr(sumsq, torch.float64, "sumsq"), float(grad_scale), float(lr), float(decay), float(momentum), float(eps),
+       float(clip_norm), ptr(grad_norm, torch.float32, "grad_norm"), stream_ptr())
+  return grad_norm
