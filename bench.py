@@ -1,0 +1,310 @@
+#!/usr/bin/env python
+"""Headline benchmark: maze env-steps/s including pixel-change + returns (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--obs-dtype f32|u8]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1], per GPU): 4096 batched maze envs; one *step* = one pass of
+the hot path over that batch = 20 rollout steps of K1 (fused maze step + 84x84x3 render +
+20x20 pixel-change) + K3 (20-step n-step returns and advantages) + K4 (pixel-control Q
+targets) = 81 920 env-steps.  Envs shard across GPUs with no data-path collective (weak
+scaling).  Prints ONE JSON line (rank 0).
+
+`value`     device-resident throughput (inputs already in HBM), CUDA events, max over ranks.
+`e2e`       the same pass through the host-buffer entry point RolloutTargets.run_host():
+            pinned host inputs copied H2D and rewards/terminals/returns/advantages copied
+            D2H inside the timed region every step.
+`roofline`  K1 (the dominant kernel): algorithmic bytes per launch / its average launch
+            duration, measured with CUDA events inside the timed region.
+`cpu_baseline` the numpy oracle port of the reference path on this box's host cores.
+
+--impl reference  times the reference's CPU implementation of the path (the oracle port: the
+reference is Python and /root/reference does not exist on the GPU box) on all host cores.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "maze env-steps/s incl. pixel-change+returns"
+UNIT = "env-steps/s"
+ENVS_PER_GPU = 4096
+ROLLOUT = 20
+# SURVEY.md 8(d) / DESIGN.md: algorithmic bytes per env-step of K1
+K1_BYTES = {"f32": 86313, "u8": 22809}
+K3_BYTES_PER_ENV_STEP = 17.2
+K4_BYTES_PER_ENV_STEP = 3280
+
+
+def parse():
+  p = argparse.ArgumentParser()
+  p.add_argument("--gpus", type=int, default=1)
+  p.add_argument("--steps", type=int, default=300)
+  p.add_argument("--warmup", type=int, default=10)
+  p.add_argument("--impl", default="b200", choices=["b200", "reference"])
+  p.add_argument("--obs-dtype", default="f32", choices=["f32", "u8"])
+  p.add_argument("--envs-per-gpu", type=int, default=ENVS_PER_GPU)
+  p.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
+  p.add_argument("--no-cpu-baseline", action="store_true")
+  return p.parse_args()
+
+
+def workload_config(args):
+  return {
+      "workload": "configs[1]: %d batched maze envs per GPU, fused step/render/pixel-change (K1) x %d + "
+                  "20-step n-step returns/advantages (K3) + PC Q-targets (K4)" % (args.envs_per_gpu, ROLLOUT),
+      "envs_per_gpu": args.envs_per_gpu, "rollout_len": ROLLOUT, "obs_dtype": args.obs_dtype,
+      "gamma": 0.99, "gamma_pc": 0.9,
+      "l2": "every pass writes a %.1f GB rollout buffer (obs+pc+targets), far larger than the 126 MB L2" % (
+          args.envs_per_gpu * ROLLOUT * (K1_BYTES[args.obs_dtype] + 1600) / 1e9),
+  }
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler(object):
+  """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+  def __init__(self, index):
+    self.samples = []
+    self.reasons = set()
+    self.max_mhz = None
+    self._stop = threading.Event()
+    self._thr = None
+    try:
+      import pynvml
+      pynvml.nvmlInit()
+      self.nv = pynvml
+      self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+      self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+    except Exception as e:  # NVML missing: report that, do not fail the run
+      self.nv = None
+      self.err = repr(e)
+
+  def _loop(self):
+    nv = self.nv
+    names = {}
+    for k in dir(nv):
+      if k.startswith("nvmlClocksThrottleReason") or k.startswith("nvmlClocksEventReason"):
+        v = getattr(nv, k)
+        if isinstance(v, int) and v:
+          names[v] = k.replace("nvmlClocksThrottleReason", "").replace("nvmlClocksEventReason", "")
+    while not self._stop.is_set():
+      try:
+        self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+        try:
+          mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+        except Exception:
+          mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        for bit, name in names.items():
+          if mask & bit and bit & (bit - 1) == 0:
+            self.reasons.add(name)
+      except Exception:
+        pass
+      time.sleep(0.02)
+
+  def start(self):
+    if self.nv is not None:
+      self._thr = threading.Thread(target=self._loop, daemon=True)
+      self._thr.start()
+
+  def stop(self):
+    self._stop.set()
+    if self._thr is not None:
+      self._thr.join()
+    s = sorted(self.samples)
+    reasons = sorted(r for r in self.reasons if r not in ("None", "GpuIdle", "ApplicationsClocksSetting"))
+    return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": reasons,
+            "samples": len(s)} if self.nv is not None else {"sm_mhz": None, "sm_max_mhz": None, "reasons": [],
+                                                            "error": self.err}
+
+
+# --------------------------------------------------------------------------- CPU arm
+def cpu_throughput(seconds, procs):
+  """Bounded sample of the same workload on host cores -> (env-steps/s, env-steps, description)."""
+  from oracle import cpu_path
+  steps0, wall0 = cpu_path.run_parallel(1, 1, ROLLOUT, 10)          # calibrate one core
+  rate = steps0 / wall0
+  passes = max(1, int(seconds * rate / (2 * ROLLOUT)))               # 2 envs per process
+  steps, wall = cpu_path.run_parallel(procs, 2, ROLLOUT, passes)
+  return steps / wall, steps, "%d processes x 2 envs x %d passes x %d steps = %d env-steps in %.1f s" % (
+      procs, passes, ROLLOUT, steps, wall)
+
+
+def run_reference(args):
+  """The reference's CPU implementation of the path (oracle port), all host cores."""
+  rank = int(os.environ.get("RANK", "0"))
+  if rank != 0:
+    return 0
+  from oracle import cpu_path
+  import multiprocessing as mp
+  procs = cpu_path.host_cores()
+  steps0, wall0 = cpu_path.run_parallel(1, 1, ROLLOUT, 10)
+  rate = steps0 / wall0
+  # size each step so that warmup + steps finish in about two minutes
+  budget = 120.0
+  envs = max(1, min(64, int(budget * rate / (ROLLOUT * (args.steps + args.warmup)))))
+  pool = mp.get_context("fork").Pool(procs) if procs > 1 else None
+  for _ in range(args.warmup):
+    cpu_path.run_parallel(procs, envs, ROLLOUT, 1, pool)
+  t0 = time.perf_counter()
+  total = 0
+  for _ in range(args.steps):
+    s, _w = cpu_path.run_parallel(procs, envs, ROLLOUT, 1, pool)
+    total += s
+  wall = time.perf_counter() - t0
+  if pool is not None:
+    pool.close(); pool.join()
+  value = total / wall
+  sample = "each step = %d processes x %d envs x %d rollout steps of the numpy oracle port (bounded sample)" % (
+      procs, envs, ROLLOUT)
+  line = {
+      "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+      "warmup": args.warmup, "ms_per_step": wall / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+      "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args),
+      "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample},
+      "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+      "gpu_launches": 0,
+  }
+  print(json.dumps(line), flush=True)
+  return 0
+
+
+# --------------------------------------------------------------------------- B200 arm
+def run_b200(args):
+  import torch
+  import torch.distributed as dist
+  rank = int(os.environ.get("RANK", "0"))
+  world = int(os.environ.get("WORLD_SIZE", "1"))
+  local = int(os.environ.get("LOCAL_RANK", "0"))
+  if world != args.gpus and world > 1:
+    raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
+  if not torch.cuda.is_available():
+    raise SystemExit("bench.py needs a CUDA device (B200); there is no CPU fallback. "
+                     "Use --impl reference for the CPU arm.")
+  torch.cuda.set_device(local)
+  dev = torch.device("cuda", local)
+  if world > 1:
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    dist.init_process_group("nccl", device_id=dev)
+
+  from unreal_b200 import _lib
+  from unreal_b200.train.rollout import RolloutTargets
+  _lib.require_device()
+  n, t = args.envs_per_gpu, ROLLOUT
+  obs_dtype = torch.float32 if args.obs_dtype == "f32" else torch.uint8
+  eng = RolloutTargets(n, t, 0.99, 0.9, obs_dtype, dev, auto_reset=True, use_graphs=True)
+  g = torch.Generator(device=dev).manual_seed(1234 + rank)
+  eng.actions.copy_(torch.randint(0, 4, (t, n), device=dev, dtype=torch.int32, generator=g))
+  eng.values.copy_(torch.randn(t, n, device=dev, generator=torch.Generator(device=dev).manual_seed(rank)))
+  eng.boot_value.copy_(torch.randn(n, device=dev, generator=g))
+  eng.boot_q.copy_(torch.rand(n, 20, 20, device=dev, generator=g))
+
+  def barrier():
+    if world > 1:
+      dist.barrier()
+    torch.cuda.synchronize(dev)
+
+  # ---- device-resident arm ----
+  for _ in range(max(args.warmup, 3)):
+    eng.run_device()
+  K = args.steps
+  evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(K)]
+  sampler = ClockSampler(local)
+  barrier()
+  sampler.start()
+  for k in range(K):
+    eng.run_device(evs[k])
+  barrier()
+  clocks = sampler.stop()
+  total_ms = evs[0][0].elapsed_time(evs[-1][3])
+  k1_ms = sum(e[0].elapsed_time(e[1]) for e in evs) / (K * t)
+  k3_ms = sum(e[1].elapsed_time(e[2]) for e in evs) / K
+  k4_ms = sum(e[2].elapsed_time(e[3]) for e in evs) / K
+
+  # ---- host-buffer (e2e) arm: same pass through run_host() ----
+  h_act = eng.actions.cpu().numpy(); h_val = eng.values.cpu().numpy()
+  h_bv = eng.boot_value.cpu().numpy(); h_bq = eng.boot_q.cpu().numpy()
+  for _ in range(3):
+    out = eng.run_host(h_act, h_val, h_bv, h_bq)
+  ke = max(3, min(K, 200))
+  e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+  barrier()
+  e0.record()
+  for _ in range(ke):
+    out = eng.run_host(h_act, h_val, h_bv, h_bq)
+  e1.record()
+  barrier()
+  e2e_ms = e0.elapsed_time(e1)
+  checksum = float(out["R"].sum())
+
+  times = torch.tensor([total_ms, e2e_ms], device=dev, dtype=torch.float64)
+  if world > 1:
+    dist.all_reduce(times, op=dist.ReduceOp.MAX)
+  total_ms, e2e_ms = times.tolist()
+
+  if rank == 0:
+    steps_per_pass = n * t
+    value = world * steps_per_pass * K / (total_ms * 1e-3)
+    e2e = world * steps_per_pass * ke / (e2e_ms * 1e-3)
+    peaks = {}
+    try:
+      with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+        peaks = json.load(f)
+    except Exception:
+      pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    k1_bytes = n * K1_BYTES[args.obs_dtype]
+    achieved = k1_bytes / (k1_ms * 1e-3) / 1e9
+    path_bytes = steps_per_pass * (K1_BYTES[args.obs_dtype] + K3_BYTES_PER_ENV_STEP + K4_BYTES_PER_ENV_STEP)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(args.warmup, 3),
+        "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": args.obs_dtype, "data": "synthetic", "config": workload_config(args), "clocks": clocks,
+        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": eng.h2d_bytes_per_pass,
+                "d2h_bytes_per_step": eng.d2h_bytes_per_pass, "steps": ke, "ms_per_step": e2e_ms / ke,
+                "api": "unreal_b200.train.rollout.RolloutTargets.run_host (pinned host in/out; frames, "
+                       "pixel-change maps and PC targets stay in HBM for the learner)", "checksum_R": checksum},
+        "gpu_launches": K * eng.launches_per_pass,
+        "roofline": {"bound": "hbm", "kernel": "maze_cta_kernel (K1)" if args.obs_dtype == "f32" else "maze_warp_kernel (K1)",
+                     "achieved": achieved, "peak": peak,
+                     "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650",
+                     "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "algorithmic_bytes_per_launch": k1_bytes, "us_per_launch": k1_ms * 1e3,
+                     "whole_pass_gbs": path_bytes / (total_ms / K * 1e-3) / 1e9,
+                     "whole_pass_frac": path_bytes / (total_ms / K * 1e-3) / 1e9 / peak,
+                     "k3_us": k3_ms * 1e3, "k4_us": k4_ms * 1e3,
+                     "k4_gbs": n * 65600 / (k4_ms * 1e-3) / 1e9},
+    }
+    traffic_file = os.path.join(ROOT, "profiles", "k1_traffic.json")
+    if os.path.exists(traffic_file):
+      try:
+        with open(traffic_file) as f:
+          line["roofline"]["traffic"] = json.load(f).get(args.obs_dtype)
+      except Exception:
+        pass
+    if not args.no_cpu_baseline and world == 1:
+      from oracle import cpu_path
+      procs = cpu_path.host_cores()
+      v, steps, sample = cpu_throughput(args.cpu_seconds, procs)
+      line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample}
+    print(json.dumps(line), flush=True)
+  if world > 1:
+    dist.barrier()
+    dist.destroy_process_group()
+  return 0
+
+
+def main():
+  args = parse()
+  if args.impl == "reference":
+    return run_reference(args)
+  return run_b200(args)
+
+
+if __name__ == "__main__":
+  sys.exit(main())
