@@ -22,18 +22,32 @@ UNREAL_HD void mt_seed_core(MtStream s, uint32_t seed) {
   *s.pos = UNREAL_MT_WORDS;
 }
 
-// One tempered word.  The twist is applied lazily, in place, one word per draw; identical to
-// block regeneration because word i of the next block reads old mt[i], old mt[i+1] and
-// mt[(i+397)%624], which is already new exactly when the block algorithm would see it new.
+// One tempered word.  The state is kept in numpy's own representation -- a block of 624 words
+// regenerated all at once when pos reaches 624 -- so a stream can be imported from / exported
+// to np.random.RandomState.get_state()/set_state() at any point (the scalar drop-in classes
+// share one RandomState with their caller, main.py:213,:270).
+UNREAL_HD uint32_t mt_twist(uint32_t u, uint32_t v, uint32_t m) {
+  uint32_t y = (u & 0x80000000u) | (v & 0x7fffffffu);
+  return m ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+}
+
+UNREAL_HD void mt_regenerate(MtStream s) {
+  const int64_t st = s.stride;
+  int kk = 0;
+  for (; kk < UNREAL_MT_WORDS - 397; ++kk)
+    s.mt[kk * st] = mt_twist(s.mt[kk * st], s.mt[(kk + 1) * st], s.mt[(kk + 397) * st]);
+  for (; kk < UNREAL_MT_WORDS - 1; ++kk)
+    s.mt[kk * st] = mt_twist(s.mt[kk * st], s.mt[(kk + 1) * st], s.mt[(kk + 397 - UNREAL_MT_WORDS) * st]);
+  s.mt[(UNREAL_MT_WORDS - 1) * st] = mt_twist(s.mt[(UNREAL_MT_WORDS - 1) * st], s.mt[0], s.mt[396 * st]);
+}
+
 UNREAL_HD uint32_t mt_next(MtStream s) {
   int i = *s.pos;
-  if (i >= UNREAL_MT_WORDS) i = 0;
-  int i1 = (i + 1 == UNREAL_MT_WORDS) ? 0 : i + 1;
-  int im = i + 397;
-  if (im >= UNREAL_MT_WORDS) im -= UNREAL_MT_WORDS;
-  uint32_t y = (s.mt[(int64_t)i * s.stride] & 0x80000000u) | (s.mt[(int64_t)i1 * s.stride] & 0x7fffffffu);
-  uint32_t v = s.mt[(int64_t)im * s.stride] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
-  s.mt[(int64_t)i * s.stride] = v;
+  if (i >= UNREAL_MT_WORDS) {
+    mt_regenerate(s);
+    i = 0;
+  }
+  uint32_t v = s.mt[(int64_t)i * s.stride];
   *s.pos = i + 1;
   v ^= v >> 11;
   v ^= (v << 7) & 0x9d2c5680u;

@@ -152,6 +152,25 @@ class MtStreams(object):
     s32 = torch.where(s32 >= 2 ** 31, s32 - 2 ** 32, s32).to(torch.int32)  # same 32 bits
     call("unreal_mt_seed", ptr(self.mt), ptr(self.pos), ptr(s32), self.n, stream_ptr())
 
+  # The device keeps numpy's own (key[624], pos) representation, so a stream can be exchanged
+  # with an np.random.RandomState at any time.
+  def load_numpy_state(self, random_state, env=0):
+    """Copy `random_state`'s MT19937 state into env `env`'s stream."""
+    name, key, pos, _, _ = random_state.get_state()
+    if name != 'MT19937':
+      raise _lib.UnrealError("RandomState must be MT19937")
+    import numpy as np
+    self.mt[:, env].copy_(torch.from_numpy(np.ascontiguousarray(key, dtype=np.uint32).view(np.int32).copy()))
+    self.pos[env] = int(pos)
+
+  def store_numpy_state(self, random_state, env=0):
+    """Write env `env`'s stream back into `random_state` (draws made on the device become
+    visible to every other user of that RandomState)."""
+    import numpy as np
+    key = self.mt[:, env].cpu().numpy().view(np.uint32).copy()
+    st = random_state.get_state()
+    random_state.set_state((st[0], key, int(self.pos[env]), st[3], st[4]))
+
   def randint(self, high, k=1):
     out = torch.empty(self.n, k, dtype=torch.int32, device=self.device)
     call("unreal_mt_randint", ptr(self.mt), ptr(self.pos), int(high), ptr(out), self.n, k, stream_ptr())

@@ -1,0 +1,313 @@
+"""Trainer: drop-in for train/trainer.py of the reference, batched over num_envs mazes.
+
+Constructor and method signatures are the reference's (trainer.py:31-59, :132-148, :176, :218,
+:339, :383, :415, :438).  One Trainer drives `num_envs` environments in lock step, each of
+them behaving exactly like one reference Trainer thread with its own RandomState stream:
+
+  * rollouts stop at a terminal step and the env is reset (trainer.py:279-296) -- the env
+    simply goes inactive for the rest of the window, so targets equal the reference's;
+  * the per-env draw order is the reference's: T x choice (trainer.py:147-148) ->
+    randint for the PC sequence -> randint for the VR sequence -> randint(2), randint(len) for
+    RP (experience.py:103, :125, :137-141);
+  * with num_envs == 1 the caller's RandomState object itself is advanced (its state is moved
+    to the device and back around each call), so sharing it between objects keeps working.
+
+All tensors stay on the device.  The network is any object with the batched call surface of
+UnrealModel's run_* helpers (model/model.py:630-728):
+    run_base_policy_and_value(sess, state, last_action_reward, active) -> pi [N,A] f32, v [N] f32, _
+    run_base_value(sess, state, last_action_reward) -> v [N]
+    run_pc_q_max(sess, state, last_action_reward)  -> q [N,20,20]
+    run_vr_value(sess, state, last_action_reward)  -> v [N]
+    reset_state(mask)          base_lstm_state_out
+and optionally `update(feed, learning_rate) -> dict(losses..., grad_norm)`.
+
+Summary writers / tf.summary plumbing of the reference (trainer.py:151-169, :577-632) is
+observability only and is not reproduced; the arguments are accepted and ignored.
+"""
+import time
+from collections import deque
+
+import numpy as np
+import torch
+
+from .. import _lib
+from .. import kernels as K
+from ..environment.environment import Environment
+from .experience import BatchedExperience
+
+LOG_INTERVAL = 1000
+PERFORMANCE_LOG_INTERVAL = 2000
+LOSS_AND_EVAL_LOG_INTERVAL = 5000
+
+
+class Trainer(object):
+  def __init__(self, thread_index, global_network, initial_learning_rate, learning_rate_input, grad_applier,
+               env_type, env_name, use_lstm, use_pixel_change, use_value_replay, use_reward_prediction,
+               pixel_change_lambda, entropy_beta, local_t_max, n_step_TD, gamma, gamma_pc,
+               experience_history_size, max_global_time_step, device, segnet_param_dict, image_shape,
+               is_training, n_classes, random_state, termination_time, segnet_lambda, dropout,
+               num_envs=1, seeds=None, verbose=False):
+    _lib.require_device()
+    self.thread_index = thread_index
+    self.learning_rate_input = learning_rate_input
+    self.env_type = env_type
+    self.env_name = env_name
+    self.use_lstm = use_lstm
+    self.use_pixel_change = use_pixel_change
+    self.use_value_replay = use_value_replay
+    self.use_reward_prediction = use_reward_prediction
+    self.pixel_change_lambda = pixel_change_lambda
+    self.entropy_beta = entropy_beta
+    self.local_t_max = local_t_max
+    self.n_step_TD = n_step_TD
+    self.gamma = gamma
+    self.gamma_pc = gamma_pc
+    self.experience_history_size = experience_history_size
+    self.max_global_time_step = max_global_time_step
+    self.action_size = Environment.get_action_size(env_type, env_name)
+    self.objective_size = Environment.get_objective_size(env_type, env_name)
+    self.segnet_param_dict = segnet_param_dict or {}
+    self.segnet_mode = self.segnet_param_dict.get("segnet_mode", 0)
+    if self.segnet_mode:
+      raise _lib.UnrealError("segnet_mode != 0 (ErfNet encoder/decoder) is outside the B200 hot path")
+    if env_type != 'maze':
+      raise _lib.UnrealError("the batched Trainer drives env_type 'maze'")
+    self.is_training = is_training
+    self.n_classes = n_classes
+    self.segnet_lambda = segnet_lambda
+    self.random_state = random_state
+    self.termination_time = termination_time
+    self.dropout = dropout
+    self.verbose = verbose
+    self.num_envs = int(num_envs)
+    self.device = torch.device(device if str(device).startswith("cuda") else "cuda:0")
+    if seeds is None and self.num_envs > 1:
+      seeds = random_state.randint(0, 2 ** 31 - 1, size=self.num_envs)
+    self._seeds = seeds
+
+    # the reference builds a thread-local copy of the network and syncs it from the global one
+    # every iteration (trainer.py:93-116, :457); the batched learner is synchronous, so the
+    # global network is used directly.
+    self.local_network = global_network
+    self.grad_applier = grad_applier
+    n, d = self.num_envs, self.device
+    with torch.cuda.device(d):
+      streams = K.MtStreams([0] * n if seeds is None else seeds, d)
+    self.experience = BatchedExperience(n, experience_history_size, None, d, streams=streams)
+    self.streams = streams
+    self.local_t = 0
+    self.initial_learning_rate = initial_learning_rate
+    self.episode_reward = torch.zeros(n, dtype=torch.float32, device=d)
+    self.prev_local_t = -1
+    self.prev_local_t_loss = 0
+    self.sr_size = 50
+    self.success_rates = deque(maxlen=self.sr_size)
+    self.environment = None
+    self.last_feed = None
+
+  # -- RandomState hand-over for the single-env drop-in case ---------------------------------
+  def _rng_in(self):
+    if self.num_envs == 1 and self._seeds is None:
+      self.streams.load_numpy_state(self.random_state)
+
+  def _rng_out(self):
+    if self.num_envs == 1 and self._seeds is None:
+      self.streams.store_numpy_state(self.random_state)
+
+  # -- reference surface ---------------------------------------------------------------------
+  def prepare(self, termination_time=50.0, termination_dist_value=-10.0):
+    """trainer.py:132-135."""
+    self.environment = Environment.create_environment(
+        self.env_type, self.env_name, self.termination_time,
+        env_args={'num_envs': self.num_envs, 'device': self.device, 'auto_reset': True},
+        thread_index=self.thread_index)
+    n, d, T = self.num_envs, self.device, self.n_step_TD
+    A = self.action_size
+    # rollout buffers: obs has T+1 slots (state before each action + the bootstrap state)
+    self._obs = torch.empty(T + 1, n, 84, 84, 3, dtype=torch.float32, device=d)
+    self._pos = torch.zeros(T + 1, n, 2, dtype=torch.int32, device=d)
+    self._lar = torch.zeros(T, n, A + 1, dtype=torch.float32, device=d)
+    self._act = torch.zeros(T, n, dtype=torch.int32, device=d)
+    self._val = torch.zeros(T, n, dtype=torch.float32, device=d)
+    self._rew = torch.zeros(T, n, dtype=torch.float32, device=d)
+    self._term = torch.zeros(T, n, dtype=torch.uint8, device=d)
+    self._active = torch.zeros(T, n, dtype=torch.uint8, device=d)
+    self._pc = torch.zeros(T, n, 20, 20, dtype=torch.float32, device=d)
+
+  def stop(self):
+    if self.environment is not None:
+      self.environment.stop()
+
+  def _anneal_learning_rate(self, global_time_step):
+    """trainer.py:140-144."""
+    learning_rate = self.initial_learning_rate * (self.max_global_time_step - global_time_step) / \
+        self.max_global_time_step
+    if learning_rate < 0.0:
+      learning_rate = 0.0
+    return learning_rate
+
+  def choose_action(self, pi_values, active=None):
+    """trainer.py:147-148, per env on its own device RandomState stream.  A 1-D numpy/torch
+    vector is accepted for the scalar case and returns a python int."""
+    scalar = not isinstance(pi_values, torch.Tensor) or pi_values.dim() == 1
+    pi = torch.as_tensor(np.asarray(pi_values, dtype=np.float32) if scalar else pi_values)
+    pi = pi.to(self.device, torch.float32).reshape(-1, pi.shape[-1]).contiguous()
+    a = self.streams.choose_action(pi, active)
+    return int(a[0]) if scalar else a
+
+  def set_start_time(self, start_time):
+    self.start_time = start_time
+
+  def _last_action_reward(self, last_action, last_reward):
+    """ExperienceFrame.concat_action_and_reward (experience.py:34-46), batched: [N, A+1]."""
+    n = last_action.shape[0]
+    out = torch.zeros(n, self.action_size + 1, dtype=torch.float32, device=self.device)
+    out.scatter_(1, last_action.to(torch.int64).clamp_(0, self.action_size - 1).unsqueeze(1), 1.0)
+    out[:, -1] = last_reward
+    return out
+
+  def _fill_experience(self, sess):
+    """trainer.py:176-205: one policy forward, one env step, one add_frame, for every env."""
+    env = self.environment
+    lar = self._last_action_reward(env.last_action, env.last_reward)
+    pi, _, _ = self.local_network.run_base_policy_and_value(sess, env.last_state, lar, None)
+    action = self.choose_action(pi)
+    env.process(action)                       # auto-reset covers `if terminal: reset()` (:201-202)
+    self.experience.add_frames(env.frame_rec)
+    full = self.experience.ring.state()["full"]
+    if bool(full.any()):
+      env.reset(full)                         # :203-205
+      if self.verbose:
+        print("Replay buffer filled")
+
+  def _print_log(self, global_t):
+    if (self.thread_index == 0) and (self.local_t - self.prev_local_t >= PERFORMANCE_LOG_INTERVAL):
+      self.prev_local_t += PERFORMANCE_LOG_INTERVAL
+      elapsed_time = time.time() - self.start_time
+      steps_per_sec = global_t / elapsed_time
+      print("### Performance : {} STEPS in {:.0f} sec. {:.0f} STEPS/sec. {:.2f}M STEPS/hour".format(
+          global_t, elapsed_time, steps_per_sec, steps_per_sec * 3600 / 1000000.))
+
+  # -- [Base A3C]  trainer.py:218-336 ----------------------------------------------------------
+  def _process_base(self, sess, global_t, summary_writer, summary_op_dict, summary_dict):
+    env, net = self.environment, self.local_network
+    n, T, d = self.num_envs, self.n_step_TD, self.device
+    start_lstm_state = net.base_lstm_state_out if self.use_lstm else None
+    active = torch.ones(n, dtype=torch.uint8, device=d)
+    ended = torch.zeros(n, dtype=torch.uint8, device=d)
+    self._obs[0].copy_(env.last_state['image'])
+    self._pos[0].copy_(env.state.pos)
+    self._active.zero_(); self._rew.zero_(); self._term.zero_()
+    last_rec = torch.zeros(n, dtype=torch.int64, device=d)
+    for t in range(T):
+      lar = self._last_action_reward(env.last_action, env.last_reward)
+      pi, v, _ = net.run_base_policy_and_value(sess, {'image': self._obs[t]}, lar, active)
+      action = self.choose_action(pi, active)
+      self._lar[t].copy_(lar); self._val[t].copy_(v); self._act[t].copy_(action); self._active[t].copy_(active)
+      # the new frame lands in obs[t+1]; envs whose rollout already ended are skipped by the kernel
+      env.process(action, active=active, out_obs=self._obs[t + 1], out_pc=self._pc[t],
+                  out_reward=self._rew[t], out_terminal=self._term[t])
+      self._pos[t + 1].copy_(env.state.pos)
+      self.experience.add_frames(env.frame_rec)
+      last_rec = torch.where(active.bool(), env.frame_rec, last_rec)
+      self.episode_reward += self._rew[t]
+      term_now = self._term[t] & active
+      if bool(term_now.any()):
+        ended |= term_now
+        net.reset_state(term_now)              # :293
+        self.episode_reward.mul_(1 - term_now.to(torch.float32))
+      active = active & (1 - term_now)
+      if not bool(active.any()):
+        break
+    lengths = self._active.sum(0).to(torch.int32)
+    self.local_t += int(lengths.max())
+    # bootstrap: V(new_state) with frame.get_action_reward for envs that did not end (:298-300)
+    rec = K.frame_unpack(last_rec, fields=("action", "reward"))
+    boot_lar = self._last_action_reward(rec["action"], rec["reward"])
+    boot_obs = self._obs[1:].gather(
+        0, (lengths.to(torch.int64) - 1).clamp_(min=0).view(1, n, 1, 1, 1).expand(1, n, 84, 84, 3))[0]
+    env.last_state = {'image': boot_obs}   # every env's current frame (the reset frame for ended envs)
+    boot = net.run_base_value(sess, {'image': boot_obs}, boot_lar)
+    boot = torch.where(ended.bool(), torch.zeros_like(boot), boot).contiguous()
+    R, adv = K.nstep_returns(self._rew, self._val, self._term, boot, self.gamma)
+    batch_a = torch.nn.functional.one_hot(self._act.to(torch.int64), self.action_size).to(torch.float32)
+    return dict(si=self._obs[:T], pos=self._pos[:T], last_action_rewards=self._lar, a=batch_a, adv=adv, R=R,
+                start_lstm_state=start_lstm_state, length=lengths, active=self._active, terminal_end=ended)
+
+  # -- replayed sequences, shared by PC and VR -----------------------------------------------
+  def _sample_sequence(self):
+    L = self.local_t_max + 1
+    start, length, f = self.experience.sample_sequence(L)
+    n_batch = (length - 1).to(torch.int32)                  # the last frame is only the bootstrap state
+    idx_last = (length.to(torch.int64) - 1).clamp_(min=0)
+    take = lambda x: x.gather(1, idx_last.view(-1, *([1] * (x.dim() - 1))).expand(-1, 1, *x.shape[2:]))[:, 0]  # noqa: E731
+    boot_pos = take(f["pos0"]).contiguous()
+    boot_lar = self._last_action_reward(take(f["last_action"]), take(f["last_reward"]))
+    boot_state = {'image': K.maze_render(boot_pos), 'pos': boot_pos}
+    lar = self._last_action_reward(f["last_action"].reshape(-1), f["last_reward"].reshape(-1))
+    lar = lar.view(self.num_envs, L, -1)
+    return start, length, n_batch, f, boot_state, boot_lar, lar
+
+  # -- [Pixel change]  trainer.py:339-380 ------------------------------------------------------
+  def _process_pc(self, sess):
+    n, L = self.num_envs, self.local_t_max + 1
+    start, length, n_batch, f, boot_state, boot_lar, lar = self._sample_sequence()
+    # the `frames[1].terminal` guard (:352) can never fire (only the last sampled frame can be
+    # terminal), so the bootstrap is always taken -- as in the reference
+    pc_boot = self.local_network.run_pc_q_max(sess, boot_state, boot_lar).contiguous()
+    pos0 = f["pos0"][:, :L - 1].transpose(0, 1).contiguous()      # [L-1, N, 2] time-major
+    pos1 = f["pos1"][:, :L - 1].transpose(0, 1).contiguous()
+    pc = K.maze_pixel_change(pos0.view(-1, 2), pos1.view(-1, 2)).view(L - 1, n, 20, 20)
+    pc_R = K.pc_targets(pc, None, n_batch, pc_boot, self.gamma_pc)
+    a = torch.nn.functional.one_hot(f["action"][:, :L - 1].to(torch.int64), self.action_size).to(torch.float32)
+    return dict(pos=f["pos0"][:, :L - 1], last_action_reward=lar[:, :L - 1], a=a, R=pc_R.transpose(0, 1),
+                length=n_batch, start=start)
+
+  # -- [Value replay]  trainer.py:383-412 ------------------------------------------------------
+  def _process_vr(self, sess):
+    L = self.local_t_max + 1
+    start, length, n_batch, f, boot_state, boot_lar, lar = self._sample_sequence()
+    vr_boot = self.local_network.run_vr_value(sess, boot_state, boot_lar).contiguous()
+    vr_R = K.sequence_returns(f["reward"].contiguous(), n_batch, vr_boot, self.gamma)
+    return dict(pos=f["pos0"][:, :L - 1], last_action_reward=lar[:, :L - 1], R=vr_R[:, :L - 1], length=n_batch,
+                start=start)
+
+  # -- [Reward prediction]  trainer.py:415-436 -------------------------------------------------
+  def _process_rp(self):
+    start, f = self.experience.sample_rp_sequence()
+    r = f["reward"][:, 3]
+    c = torch.zeros(self.num_envs, 3, dtype=torch.float32, device=self.device)
+    zero = r.abs() < 1e-10
+    c[:, 0] = zero.float(); c[:, 1] = (~zero & (r > 0)).float(); c[:, 2] = (~zero & (r < 0)).float()
+    return dict(pos=f["pos0"][:, :3], c=c, start=start)
+
+  # -- one iteration  trainer.py:438-636 -------------------------------------------------------
+  def process(self, sess=None, global_t=0, summary_writer=None, summary_op_dict=None, score_input=None,
+              sr_input=None, eval_input=None, entropy_input=None, term_global_t=None, losses_input=None):
+    with torch.cuda.device(self.device):
+      self._rng_in()
+      try:
+        if not self.experience.is_full():
+          self._fill_experience(sess)
+          return 0, None
+        start_local_t = self.local_t
+        cur_learning_rate = self._anneal_learning_rate(global_t)
+        feed = {'base': self._process_base(sess, global_t, summary_writer, summary_op_dict,
+                                           {'placeholders': {}, 'values': {}}),
+                'learning_rate': cur_learning_rate}
+        if self.use_pixel_change:
+          feed['pc'] = self._process_pc(sess)
+        if self.use_value_replay:
+          feed['vr'] = self._process_vr(sess)
+        if self.use_reward_prediction:
+          feed['rp'] = self._process_rp()
+      finally:
+        self._rng_out()
+      self.last_feed = feed
+      if hasattr(self.local_network, 'update'):
+        self.last_losses = self.local_network.update(feed, cur_learning_rate, self.grad_applier)
+      if hasattr(self, 'start_time'):
+        self._print_log(global_t)
+      ended = feed['base']['terminal_end']
+      episode_score = None   # per-env scores are device side; see self.episode_reward
+      return self.local_t - start_local_t, episode_score
