@@ -172,6 +172,21 @@ int unreal_rmsprop_update(float* var, float* rms, float* mom, const float* grad,
                           const double* sumsq, float grad_scale, float lr, float decay, float momentum,
                           float eps, float clip_norm, float* grad_norm, void* stream);
 
+/* ---- K7: dense layers of UnrealModel (model/model.py:281-598) on the tcgen05 tensor path ------
+ * C[M,N] (=|+=) act(A*B + bias + add), bf16 operands, fp32 accumulation in TMEM.
+ *   a_mn_major 0: A is row-major [M,K] (lda >= K);  1: A is row-major [K,M] (lda >= M)
+ *   b_mn_major 0: B is row-major [N,K] (ldb >= K);  1: B is row-major [K,N] (ldb >= N) -- TF's
+ *              [in,out] weight layout (model.py:752-783) is b_mn_major = 1 for tf.matmul(x, W).
+ *   c_dtype    UNREAL_GEMM_OUT_F32 / UNREAL_GEMM_OUT_BF16; ldc in elements.
+ *   bias [N] f32 nullable; add [M,N] f32 (ld = ldc) nullable; relu != 0 applies max(.,0).
+ *   accumulate != 0 or split_k > 1: C (f32) += result with red.global.add (caller zeroes C).
+ * lda / ldb must be multiples of 8 elements and all pointers 16-byte aligned (TMA). */
+#define UNREAL_GEMM_OUT_F32 0
+#define UNREAL_GEMM_OUT_BF16 1
+int unreal_gemm_bf16(const void* a, int64_t lda, int a_mn_major, const void* b, int64_t ldb, int b_mn_major,
+                     void* c, int64_t ldc, int c_dtype, const float* bias, const float* add, int relu,
+                     int accumulate, int split_k, int m, int n, int k, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,376 @@
+// K7: bf16 x bf16 -> fp32 GEMM on the sm_100a tensor path (tcgen05.mma, TMEM accumulators, TMA).
+//
+// The dense layers of UnrealModel (model/model.py:281-598) are tf.matmul / tf.nn.conv2d calls in
+// the reference; batched over envs x time they become the GEMMs
+//     fc1      [S, 2592] x [2592, 256]      (model.py:337-340)
+//     LSTM     [S, 256+A+1+G] x [., 1024] and per step [N, 256] x [256, 1024]   (:110, :346-351)
+//     pc_fc1   [S, 256] x [256, 2592]       (:424)
+//     conv1/2  im2col [S*400, 192] x [192, 16], [S*81, 256] x [256, 32]          (:283-289)
+//     deconv   [S*81, 32] x [32, 16*(1+A)]  (:425-430)
+// plus their dgrad / wgrad transposes.  One kernel serves all of them:
+//
+//     C[M,N] (=|+=) act( A * B + bias ),   fp32 accumulation in TMEM
+//
+//   A: "K-major"  = row-major [M,K] (K contiguous)   or "MN-major" = row-major [K,M] (M contiguous)
+//   B: "K-major"  = row-major [N,K] (K contiguous)   or "MN-major" = row-major [K,N] (N contiguous)
+// so forward (X * W, W stored [in,out] like TF), dgrad (dY * W^T) and wgrad (X^T * dY) all read
+// the operands where they lie, with no transposed copies.
+//
+// Structure (one persistent CTA per SM, 192 threads):
+//   warp 0   TMA producer: cp.async.bulk.tensor.2d with 128-byte swizzle into a ring of kStages
+//            shared-memory stages, one mbarrier pair (full/empty) per stage;
+//   warp 1   MMA issuer: ONE thread issues tcgen05.mma.cta_group::1.kind::f16 (UMMA 128 x BN x 16),
+//            tcgen05.commit releases the stage / publishes the accumulator;
+//   warps 2-5 epilogue: tcgen05.ld (32 lanes x 32 columns) -> bias / ReLU / convert -> global.
+//            Two TMEM accumulator buffers, so the epilogue of tile i overlaps the MMAs of tile i+1.
+// Split-K (wgrad: K = samples is the long dimension) adds the partial tiles with red.global.add.f32.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include <mutex>
+
+#include "common.cuh"
+#include "tc05.cuh"
+
+namespace unreal {
+using namespace tc05;
+
+constexpr int kBM = 128;        // UMMA M (cta_group::1): accumulator row i lives in TMEM lane i
+constexpr int kBK = 64;         // bf16 elements per stage along K = one 128-byte swizzle row
+constexpr int kUmmaK = 16;      // K per tcgen05.mma for 16-bit operands
+constexpr int kGemmThreads = 192;
+
+struct GemmArgs {
+  void* c;
+  const float* bias;
+  const void* add;  // optional [M,N] f32 addend read by the epilogue (ld = ldc)
+  int64_t ldc;
+  int m, n, k;
+  int split_k;
+  int c_bf16;       // 1: C is bf16, 0: f32
+  int relu;
+  int accumulate;   // 1: C += result (red.global.add.f32); implied by split_k > 1
+};
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int kABytes = kBM * kBK * 2;
+  static constexpr int kBBytes = BN * kBK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (BN >= 256) ? 4 : (BN >= 128 ? 6 : 8);
+  static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
+};
+
+// ---- epilogue stores -------------------------------------------------------------------
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                    const GemmArgs g) {
+  using Cfg = GemmCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  // 128-byte swizzle atoms are 1024 bytes: every operand tile starts on a 1024-byte boundary
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + Cfg::kStages * Cfg::kStageBytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::kStages + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::kStages + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::kStages + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::kStages + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_m = (g.m + kBM - 1) / kBM, num_n = (g.n + BN - 1) / BN;
+  const int kb_total = (g.k + kBK - 1) / kBK;
+  const int kb_per = (kb_total + g.split_k - 1) / g.split_k;
+  const int work_total = num_m * num_n * g.split_k;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&tma_a);
+    prefetch_tensormap(&tma_b);
+    for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    fence_mbar_init();
+  } else if (warp == 2) {
+    tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      int stage = 0; uint32_t phase = 0;
+      for (int w = blockIdx.x; w < work_total; w += gridDim.x) {
+        const int n_blk = w % num_n, m_blk = (w / num_n) % num_m, sp = w / (num_n * num_m);
+        const int kb0 = sp * kb_per, kb1 = min(kb0 + kb_per, kb_total);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t sa = smem_base + stage * Cfg::kStageBytes, sb = sa + Cfg::kABytes;
+          mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes);
+          if (A_MN) {
+#pragma unroll
+            for (int b = 0; b < kBM / 64; ++b)
+              tma_load_2d(sa + b * (kBK * 128), &tma_a, full_bar(stage), m_blk * kBM + b * 64, kb * kBK);
+          } else {
+            tma_load_2d(sa, &tma_a, full_bar(stage), kb * kBK, m_blk * kBM);
+          }
+          if (B_MN) {
+#pragma unroll
+            for (int b = 0; b < BN / 64; ++b)
+              tma_load_2d(sb + b * (kBK * 128), &tma_b, full_bar(stage), n_blk * BN + b * 64, kb * kBK);
+          } else {
+            tma_load_2d(sb, &tma_b, full_bar(stage), kb * kBK, n_blk * BN);
+          }
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      constexpr uint32_t idesc = idesc_bf16_f32(kBM, BN, A_MN, B_MN);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int w = blockIdx.x; w < work_total; w += gridDim.x) {
+        const int sp = w / (num_n * num_m);
+        const int kb0 = sp * kb_per, kb1 = min(kb0 + kb_per, kb_total);
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);   // epilogue has drained this accumulator
+        fence_after_sync();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          fence_after_sync();
+          const uint32_t sa = smem_base + stage * Cfg::kStageBytes, sb = sa + Cfg::kABytes;
+#pragma unroll
+          for (int k = 0; k < kBK / kUmmaK; ++k) {
+            // K-major: 16 elements = 32 bytes further inside the swizzle row; 8-row groups 1024 B apart.
+            // MN-major: 16 k-rows = two 8-row groups = 2048 bytes; 64-element MN chunks kBK*128 B apart.
+            const uint64_t ad = A_MN ? smem_desc_sw128(sa + k * 2048, kBK * 128, 1024)
+                                     : smem_desc_sw128(sa + k * 32, 16, 1024);
+            const uint64_t bd = B_MN ? smem_desc_sw128(sb + k * 2048, kBK * 128, 1024)
+                                     : smem_desc_sw128(sb + k * 32, 16, 1024);
+            mma_f16(tmem_d, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          mma_commit(empty_bar(stage));               // stage is free once these MMAs have read it
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
+        }
+        mma_commit(tfull_bar(acc));                   // accumulator complete
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else {
+    // ===== epilogue (warps 2..5): warp w may touch TMEM lanes 32*(w%4) .. +31 =====
+    const int quarter = warp & 3;
+    const int row_in_tile = quarter * 32 + lane;
+    int acc = 0; uint32_t acc_phase = 0;
+    const bool atomic = g.accumulate || g.split_k > 1;
+    for (int w = blockIdx.x; w < work_total; w += gridDim.x) {
+      const int n_blk = w % num_n, m_blk = (w / num_n) % num_m, sp = w / (num_n * num_m);
+      mbar_wait(tfull_bar(acc), acc_phase);
+      fence_after_sync();
+      const int row = m_blk * kBM + row_in_tile;
+      const bool row_ok = row < g.m;
+      const bool lead = (sp == 0);  // bias / addend are applied by the first K split only
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + c0), r);
+        tmem_ld_wait();
+        const int col0 = n_blk * BN + c0;
+        if (row_ok && col0 < g.n) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          const bool full = (col0 + 32 <= g.n);
+          if (g.bias != nullptr && lead) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (full || col0 + j < g.n) v[j] += __ldg(g.bias + col0 + j);
+          }
+          if (g.add != nullptr && lead) {
+            const float* ap = reinterpret_cast<const float*>(g.add) + (size_t)row * g.ldc + col0;
+            if (full && ((g.ldc & 3) == 0)) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                float4 t = *reinterpret_cast<const float4*>(ap + j);
+                v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) if (col0 + j < g.n) v[j] += ap[j];
+            }
+          }
+          if (g.relu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+          }
+          if (g.c_bf16) {
+            __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(g.c) + (size_t)row * g.ldc + col0;
+            if (full && ((g.ldc & 7) == 0)) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                __nv_bfloat162 p0 = __floats2bfloat162_rn(v[j], v[j + 1]);
+                __nv_bfloat162 p1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
+                __nv_bfloat162 p2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]);
+                __nv_bfloat162 p3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
+                uint4 u;
+                u.x = *reinterpret_cast<uint32_t*>(&p0); u.y = *reinterpret_cast<uint32_t*>(&p1);
+                u.z = *reinterpret_cast<uint32_t*>(&p2); u.w = *reinterpret_cast<uint32_t*>(&p3);
+                *reinterpret_cast<uint4*>(cp + j) = u;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) if (col0 + j < g.n) cp[j] = __float2bfloat16_rn(v[j]);
+            }
+          } else {
+            float* cp = reinterpret_cast<float*>(g.c) + (size_t)row * g.ldc + col0;
+            const bool vec = full && ((g.ldc & 3) == 0);
+            if (atomic) {
+              if (vec) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) red_add_v4(cp + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) if (col0 + j < g.n) atomicAdd(cp + j, v[j]);
+              }
+            } else if (vec) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(cp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) if (col0 + j < g.n) cp[j] = v[j];
+            }
+          }
+        }
+      }
+      fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+  __syncwarp();
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 2) {
+    fence_after_sync();
+    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+// ---- host side -------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+// row-major bf16 [rows, cols] with leading dimension ld; box = [box_rows, 64 cols], 128-byte swizzle
+int make_tma_2d_bf16(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+  EncodeTiledFn fn = encode_tiled();
+  if (fn == nullptr) {
+    set_error("cuTensorMapEncodeTiled is not available from the CUDA driver");
+    return UNREAL_ECUDA;
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d) for a [%lld x %lld] bf16 matrix, ld %lld", (int)r, (long long)rows,
+              (long long)cols, (long long)ld);
+    return UNREAL_ECUDA;
+  }
+  return UNREAL_OK;
+}
+
+template <int BN, bool A_MN, bool B_MN>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& g, cudaStream_t st) {
+  using Cfg = GemmCfg<BN>;
+  static bool configured = false;
+  auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN>;
+  if (!configured) {
+    UNREAL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    configured = true;
+  }
+  const int num_m = (g.m + kBM - 1) / kBM, num_n = (g.n + BN - 1) / BN;
+  const int64_t work = (int64_t)num_m * num_n * g.split_k;
+  const int sms = sm_count();
+  if (sms <= 0) return UNREAL_ECUDA;
+  const int grid = (int)(work < sms ? work : sms);
+  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(ta, tb, g);
+  UNREAL_LAUNCH_CHECK("gemm_tcgen05_kernel");
+  return UNREAL_OK;
+}
+
+}  // namespace unreal
+
+using namespace unreal;
+
+extern "C" int unreal_gemm_bf16(const void* a, int64_t lda, int a_mn_major, const void* b, int64_t ldb,
+                                int b_mn_major, void* c, int64_t ldc, int c_dtype, const float* bias,
+                                const float* add, int relu, int accumulate, int split_k, int m, int n, int k,
+                                void* stream) {
+  UNREAL_REQUIRE(a && b && c, "unreal_gemm_bf16: null operand");
+  UNREAL_REQUIRE(m > 0 && n > 0 && k > 0, "unreal_gemm_bf16: empty problem %d x %d x %d", m, n, k);
+  UNREAL_REQUIRE(aligned16(a) && aligned16(b) && aligned16(c), "unreal_gemm_bf16: operands must be 16-byte aligned");
+  UNREAL_REQUIRE((lda & 7) == 0 && (ldb & 7) == 0, "unreal_gemm_bf16: lda/ldb must be multiples of 8 elements (TMA)");
+  UNREAL_REQUIRE(lda >= (a_mn_major ? m : k) && ldb >= (b_mn_major ? n : k) && ldc >= n,
+                 "unreal_gemm_bf16: leading dimension smaller than the row length");
+  UNREAL_REQUIRE(c_dtype == UNREAL_GEMM_OUT_F32 || c_dtype == UNREAL_GEMM_OUT_BF16, "unreal_gemm_bf16: bad c_dtype");
+  if (split_k < 1) split_k = 1;
+  const int kb_total = (k + kBK - 1) / kBK;
+  if (split_k > kb_total) split_k = kb_total;
+  // every split must own at least one K block
+  while (split_k > 1 && (int64_t)((kb_total + split_k - 1) / split_k) * (split_k - 1) >= kb_total) --split_k;
+  UNREAL_REQUIRE(!(c_dtype == UNREAL_GEMM_OUT_BF16 && (accumulate || split_k > 1)),
+                 "unreal_gemm_bf16: accumulate / split-K need an f32 output");
+  UNREAL_REQUIRE(!(relu && (accumulate || split_k > 1)), "unreal_gemm_bf16: ReLU cannot be fused with accumulation");
+  // tile width: wide tiles for wide outputs; MN-major B needs whole 64-column boxes
+  int bn = (n > 64) ? 128 : (n > 32 ? 64 : 32);
+  if (b_mn_major && bn < 64) bn = 64;
+  CUtensorMap ta, tb;
+  int rc;
+  if (a_mn_major) rc = make_tma_2d_bf16(&ta, a, k, m, lda, kBK); else rc = make_tma_2d_bf16(&ta, a, m, k, lda, kBM);
+  if (rc != UNREAL_OK) return rc;
+  if (b_mn_major) rc = make_tma_2d_bf16(&tb, b, k, n, ldb, kBK); else rc = make_tma_2d_bf16(&tb, b, n, k, ldb, bn);
+  if (rc != UNREAL_OK) return rc;
+  GemmArgs g{c, bias, add, ldc, m, n, k, split_k, c_dtype == UNREAL_GEMM_OUT_BF16 ? 1 : 0, relu ? 1 : 0,
+             accumulate ? 1 : 0};
+  cudaStream_t st = as_stream(stream);
+#define UNREAL_GEMM_CASE(BN_, AMN_, BMN_) \
+  if (bn == BN_ && (a_mn_major != 0) == AMN_ && (b_mn_major != 0) == BMN_) return launch_gemm<BN_, AMN_, BMN_>(ta, tb, g, st);
+  UNREAL_GEMM_CASE(32, false, false)
+  UNREAL_GEMM_CASE(64, false, false)
+  UNREAL_GEMM_CASE(128, false, false)
+  UNREAL_GEMM_CASE(64, false, true)
+  UNREAL_GEMM_CASE(128, false, true)
+  UNREAL_GEMM_CASE(32, true, false)
+  UNREAL_GEMM_CASE(64, true, false)
+  UNREAL_GEMM_CASE(128, true, false)
+  UNREAL_GEMM_CASE(64, true, true)
+  UNREAL_GEMM_CASE(128, true, true)
+#undef UNREAL_GEMM_CASE
+  set_error("unreal_gemm_bf16: no kernel for tile %d, a_mn %d, b_mn %d", bn, a_mn_major, b_mn_major);
+  return UNREAL_EINVAL;
+}

@@ -278,3 +278,46 @@ def rmsprop_update(var, rms, mom, grad, sumsq, lr, decay, momentum, eps, clip_no
        ptr(sumsq, torch.float64, "sumsq"), float(grad_scale), float(lr), float(decay), float(momentum), float(eps),
        float(clip_norm), ptr(grad_norm, torch.float32, "grad_norm"), stream_ptr())
   return grad_norm
+
+
+# ---------------------------------------------------------------------------- K7: tcgen05 GEMM
+def _mat(t, name):
+  """(data_ptr, leading dimension) of a 2-D bf16 CUDA tensor whose rows are contiguous."""
+  if not isinstance(t, torch.Tensor) or not t.is_cuda or t.dim() != 2 or t.dtype != torch.bfloat16:
+    raise _lib.UnrealError("%s must be a 2-D bfloat16 CUDA tensor" % name)
+  if t.stride(1) != 1 and t.shape[1] != 1:
+    raise _lib.UnrealError("%s must have contiguous rows" % name)
+  return t.data_ptr(), t.stride(0)
+
+
+def gemm_bf16(a, b, out=None, a_mn_major=False, b_mn_major=False, bias=None, add=None, relu=False,
+              accumulate=False, split_k=1, out_dtype=torch.float32):
+  """C[M,N] = act(A @ B + bias + add) on the tcgen05 tensor path, fp32 accumulation.
+
+  a: [M,K] bf16 (or [K,M] when a_mn_major), b: [N,K] bf16 (or [K,N] when b_mn_major -- TF's
+  [in,out] weight layout).  out: f32 or bf16 [M,N] with contiguous rows (allocated if None)."""
+  if a_mn_major:
+    k, m = a.shape
+  else:
+    m, k = a.shape
+  if b_mn_major:
+    kb, n = b.shape
+  else:
+    n, kb = b.shape
+  if kb != k:
+    raise _lib.UnrealError("gemm_bf16: inner dimensions differ (%d vs %d)" % (k, kb))
+  if out is None:
+    out = (torch.zeros if (accumulate or split_k > 1) else torch.empty)(m, n, dtype=out_dtype, device=a.device)
+  if out.dim() != 2 or tuple(out.shape) != (m, n) or (out.stride(1) != 1 and n != 1):
+    raise _lib.UnrealError("gemm_bf16: out must be [%d,%d] with contiguous rows" % (m, n))
+  if out.dtype not in (torch.float32, torch.bfloat16):
+    raise _lib.UnrealError("gemm_bf16: out must be float32 or bfloat16")
+  if add is not None and (add.dtype != torch.float32 or tuple(add.shape) != (m, n) or add.stride(0) != out.stride(0)):
+    raise _lib.UnrealError("gemm_bf16: add must be f32 [M,N] with the same row stride as out")
+  pa, lda = _mat(a, "a")
+  pb, ldb = _mat(b, "b")
+  call("unreal_gemm_bf16", pa, lda, 1 if a_mn_major else 0, pb, ldb, 1 if b_mn_major else 0, out.data_ptr(),
+       out.stride(0), 1 if out.dtype == torch.bfloat16 else 0, ptr(bias, torch.float32, "bias"),
+       None if add is None else add.data_ptr(), 1 if relu else 0, 1 if accumulate else 0, int(split_k), m, n, k,
+       stream_ptr())
+  return out
