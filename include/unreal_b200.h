@@ -37,6 +37,7 @@ extern "C" {
 /* element type tags for observation / frame buffers */
 #define UNREAL_F32 0
 #define UNREAL_U8 1 /* 1.0 is stored as 255; loaders divide by 255 (lab/indoor/gym convention) */
+#define UNREAL_BF16 2 /* activations between the dense layers (K7) */
 
 #define UNREAL_MAZE_GRID 7
 #define UNREAL_FRAME_HW 84
@@ -186,6 +187,26 @@ int unreal_rmsprop_update(float* var, float* rms, float* mom, const float* grad,
 int unreal_gemm_bf16(const void* a, int64_t lda, int a_mn_major, const void* b, int64_t ldb, int b_mn_major,
                      void* c, int64_t ldc, int c_dtype, const float* bias, const float* add, int relu,
                      int accumulate, int split_k, int m, int n, int k, void* stream);
+
+/* tf.nn.conv2d / conv2d_transpose with VALID padding around the GEMM (model.py:786-787, :803-820).
+ * in [S,H,W,C] of in_dtype (UNREAL_F32 / UNREAL_U8 (/255) / UNREAL_BF16) ->
+ * out bf16 [S*OH*OW, KH*KW*C], column (ky*KW + kx)*C + c, i.e. the row-major order of an HWIO
+ * filter.  (H-KH) and (W-KW) must be multiples of the stride. */
+int unreal_im2col(const void* in, int in_dtype, void* out_bf16, int s, int h, int w, int c, int kh, int kw,
+                  int stride, void* stream);
+/* inverse scatter as a gather: out[s,y,x,c] = act(bias[c] + sum of the taps that cover (y,x)).
+ * cols [S*OH*OW, KH*KW*C] f32/bf16, out [S,H,W,C] f32/bf16, bias [C] nullable, relu flag. */
+int unreal_col2im(const void* cols, int cols_dtype, void* out, int out_dtype, const float* bias, int relu, int s,
+                  int h, int w, int c, int kh, int kw, int stride, void* stream);
+/* contrib.rnn.BasicLSTMCell(256) pointwise part (model.py:110): gates [N,1024] f32 hold the
+ * pre-activations i|j|f|o on entry and their activations on return (forget_bias 1.0);
+ * c = c_prev*f + i*j, h = tanh(c)*o; h16 is the bf16 copy fed to the next step's GEMM. */
+int unreal_lstm_cell_fwd(float* gates, const float* c_prev, float* c_out, float* h_out, void* h16_out, int n,
+                         void* stream);
+/* backward of the above: dh [N,256] total gradient wrt h_t; dc [N,256] in: wrt c_t, out: wrt
+ * c_{t-1}; dgates bf16 [N,1024] wrt the pre-activations. */
+int unreal_lstm_cell_bwd(const float* gates_act, const float* c_prev, const float* c, const float* dh, float* dc,
+                         void* dgates_bf16, int n, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,182 @@
+"""UnrealModel on the tcgen05 path against oracle/model_oracle.py (PyTorch-CPU fp32 restatement of
+model/model.py; TF parity itself is unpinned, see the oracle's header).
+
+Two comparisons, tolerances stated where they are used:
+  * against the oracle with `emulate_bf16=True` (it rounds exactly the tensors the CUDA path keeps
+    in bf16): forward values differ only by fp32 accumulation order -> 2e-3 relative;
+  * against the plain fp32 oracle: bf16 operand rounding (2^-9 per element) -> 3e-2 relative.
+Gradients additionally round dY to bf16 at each layer; they are compared per variable with
+max|diff| <= 3e-2 * max|ref| against the emulating oracle, and in
+relative L2 norm (<= 1e-1) against the plain fp32 one, whose forward pass itself differs.
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+A = 4
+
+
+def _feed(T, N, L, seed, maze_frames=False):
+  rs = np.random.RandomState(seed)
+
+  def images(*lead):
+    if maze_frames:
+      from oracle import unreal_oracle as O
+      cells = [(x, y) for y in range(7) for x in range(7) if not O.WALLS[y, x]]
+      out = np.zeros(lead + (84, 84, 3), np.float32)
+      flat = out.reshape(-1, 84, 84, 3)
+      for i in range(flat.shape[0]):
+        x, y = cells[rs.randint(len(cells))]
+        flat[i] = O.maze_render(x, y).astype(np.float32)
+      return torch.from_numpy(out)
+    return torch.from_numpy(rs.rand(*lead, 84, 84, 3).astype(np.float32)).to(torch.bfloat16).float()
+
+  def lar(*lead):
+    a = rs.randint(0, A, size=lead)
+    out = np.zeros(lead + (A + 1,), np.float32)
+    np.put_along_axis(out, a[..., None], 1.0, axis=-1)
+    out[..., A] = rs.randint(-1, 2, size=lead)
+    return torch.from_numpy(out)
+
+  def onehot(*lead):
+    a = rs.randint(0, A, size=lead)
+    out = np.zeros(lead + (A,), np.float32)
+    np.put_along_axis(out, a[..., None], 1.0, axis=-1)
+    return torch.from_numpy(out)
+
+  def mask(t, n):
+    m = np.ones((t, n), np.float32)
+    m[t - 2:, 0] = 0          # env 0 ended two steps early
+    return torch.from_numpy(m)
+
+  f32 = lambda *s: torch.from_numpy(rs.randn(*s).astype(np.float32))  # noqa: E731
+  rp_c = np.zeros((N, 3), np.float32); rp_c[np.arange(N), rs.randint(0, 3, N)] = 1
+  return {
+      "base": dict(images=images(T, N), lar=lar(T, N), a=onehot(T, N), adv=f32(T, N), R=f32(T, N), mask=mask(T, N),
+                   c0=f32(N, 256) * 0.1, h0=f32(N, 256) * 0.1),
+      "pc": dict(images=images(L, N), lar=lar(L, N), a=onehot(L, N),
+                 R=torch.from_numpy(rs.rand(L, N, 20, 20).astype(np.float32)), mask=mask(L, N)),
+      "vr": dict(images=images(L, N), lar=lar(L, N), R=f32(L, N), mask=mask(L, N)),
+      "rp": dict(images=images(N, 3), c=torch.from_numpy(rp_c)),
+  }
+
+
+def _to(feed, dev):
+  return {k: {kk: vv.to(dev) for kk, vv in v.items()} for k, v in feed.items()}
+
+
+def _model(dev, seed=0, n=3):
+  from unreal_b200.model.model import UnrealModel
+  return UnrealModel(A, 0, -1, True, True, True, True, 0.05, 0.001, dev, {'segnet_mode': 0}, (84, 84), True, 0,
+                     0.0, 0.0, num_envs=n, seed=seed)
+
+
+def _oracle(model, emulate):
+  from oracle import model_oracle as M
+  params = {k: v.detach().cpu().clone() for k, v in model.named_vars().items()}
+  return M.ModelOracle(params, A, 0, 0.05, 0.001, emulate_bf16=emulate)
+
+
+def test_parameter_layout():
+  dev = torch.device("cuda", 0)
+  m = _model(dev)
+  assert m.num_parameters == 1898877 and len(m.get_vars()) == 20
+  shapes = [tuple(v.shape) for v in m.get_vars()]
+  assert shapes[0] == (8, 8, 3, 16) and shapes[6] == (517, 1024) and shapes[-2] == (7776, 3)
+
+
+def test_im2col_col2im_match_unfold_fold():
+  from unreal_b200 import kernels as K
+  dev = torch.device("cuda", 0)
+  g = torch.Generator(device=dev).manual_seed(0)
+  for (s, h, w, c, kh, kw, st, dt) in [(3, 84, 84, 3, 8, 8, 4, torch.float32), (3, 84, 84, 3, 8, 8, 4, torch.uint8),
+                                       (2, 20, 20, 16, 4, 4, 2, torch.bfloat16), (2, 20, 20, 5, 4, 4, 2, torch.float32)]:
+    if dt == torch.uint8:
+      x = torch.randint(0, 256, (s, h, w, c), device=dev, dtype=torch.uint8, generator=g)
+      xf = (x.float() / 255.0)
+    else:
+      x = torch.rand(s, h, w, c, device=dev, generator=g).to(dt)
+      xf = x.float()
+    cols = K.im2col(x, kh, kw, st)
+    oh, ow = (h - kh) // st + 1, (w - kw) // st + 1
+    ref = torch.nn.functional.unfold(xf.permute(0, 3, 1, 2), (kh, kw), stride=st)       # [S, C*KH*KW, L]
+    ref = ref.view(s, c, kh, kw, oh * ow).permute(0, 4, 2, 3, 1).reshape(s * oh * ow, kh * kw * c)
+    assert torch.equal(cols.float(), ref.to(torch.bfloat16).float())
+    back = K.col2im(cols, s, h, w, c, kh, kw, st)
+    folded = torch.nn.functional.fold(
+        cols.float().view(s, oh * ow, kh, kw, c).permute(0, 4, 2, 3, 1).reshape(s, c * kh * kw, oh * ow),
+        (h, w), (kh, kw), stride=st).permute(0, 2, 3, 1)
+    assert torch.allclose(back, folded, rtol=1e-5, atol=1e-5)
+
+
+def test_acting_helpers_match_oracle():
+  dev = torch.device("cuda", 0)
+  m = _model(dev, seed=3, n=3)
+  o = _oracle(m, True)
+  feed = _feed(2, 3, 2, seed=5)
+  img, lar = feed["base"]["images"], feed["base"]["lar"]
+  c = torch.zeros(3, 256); h = torch.zeros(3, 256)
+  for t in range(2):
+    pi, v, _ = m.run_base_policy_and_value(None, {'image': img[t].to(dev)}, lar[t].to(dev))
+    rpi, rv, (c, h) = o.base_forward(img[t:t + 1], lar[t:t + 1], c, h)
+    assert torch.allclose(pi.cpu(), rpi[0], rtol=2e-3, atol=2e-4)
+    assert torch.allclose(v.cpu(), rv[0], rtol=2e-3, atol=2e-3)
+  # bootstrap value does not advance the state (model.py:687-704)
+  before = [s.clone() for s in m.base_lstm_state_out]
+  bv = m.run_base_value(None, {'image': img[0].to(dev)}, lar[0].to(dev))
+  assert all(torch.equal(a, b) for a, b in zip(before, m.base_lstm_state_out))
+  rbv = o.base_forward(img[0:1], lar[0:1], c, h)[1][0]
+  assert torch.allclose(bv.cpu(), rbv, rtol=2e-3, atol=2e-3)
+  qmax = m.run_pc_q_max(None, {'image': img[1].to(dev)}, lar[1].to(dev))
+  rq = o.pc_forward(img[1:2], lar[1:2])[1][0]
+  assert torch.allclose(qmax.cpu(), rq, rtol=2e-3, atol=2e-3)
+  vr = m.run_vr_value(None, {'image': img[1].to(dev)}, lar[1].to(dev))
+  assert torch.allclose(vr.cpu(), o.vr_forward(img[1:2], lar[1:2])[0], rtol=2e-3, atol=2e-3)
+  # masked state reset / masked advance
+  m.reset_state(torch.tensor([1, 0, 0], device=dev, dtype=torch.uint8))
+  assert float(m.base_lstm_state_out[0][0].abs().max()) == 0 and float(m.base_lstm_state_out[0][1].abs().max()) > 0
+
+
+@pytest.mark.parametrize("maze", [False, True])
+def test_loss_and_gradients_match_oracle(maze):
+  dev = torch.device("cuda", 0)
+  m = _model(dev, seed=1, n=3)
+  feed = _feed(5, 3, 4, seed=2, maze_frames=maze)
+  total, parts, grad = m.loss_and_grads(_to(feed, dev))
+  got = {k: v.cpu() for k, v in m._views(grad).items()}
+  for emulate, ftol, gtol in ((True, 2e-3, 3e-2), (False, 3e-2, 1e-1)):
+    o = _oracle(m, emulate)
+    rtotal, rparts, rgrads = o.loss_and_grads(feed)
+    for k in ("policy", "value", "pc", "vr", "rp"):
+      assert abs(float(parts[k]) - float(rparts[k])) <= ftol * max(1.0, abs(float(rparts[k]))), (k, emulate)
+    for k, rg in rgrads.items():
+      if emulate:     # element-wise: worst element against the variable's largest gradient
+        err = float((got[k] - rg).abs().max())
+        assert err <= gtol * float(rg.abs().max()) + 1e-6, (k, emulate, err, float(rg.abs().max()))
+      else:           # against pure fp32 the forward itself differs (bf16 operands): L2-relative
+        err = float((got[k] - rg).norm() / rg.norm().clamp_min(1e-12))
+        assert err <= gtol, (k, emulate, err)
+
+
+def test_update_applies_rmsprop_like_the_oracle():
+  """One learner step = K6 on the flat gradient: compare with the numpy RMSProp restatement."""
+  from oracle import unreal_oracle as O
+  from unreal_b200.train.rmsprop_applier import RMSPropApplier
+  dev = torch.device("cuda", 0)
+  m = _model(dev, seed=4, n=3)
+  feed = _to(_feed(4, 3, 3, seed=6), dev)
+  before = m.flat.detach().cpu().numpy().copy()
+  _, _, grad = m.loss_and_grads(feed, 1.0 / 3)
+  g = grad.detach().cpu().numpy().copy()
+  applier = RMSPropApplier(7e-4, decay=0.99, momentum=0.0, epsilon=0.1, clip_norm=40.0)
+  out = m.update(feed, 7e-4, applier)
+  norm = np.sqrt((g.astype(np.float64) ** 2).sum())
+  gc = g * (40.0 / max(norm, 40.0))
+  ms = 1.0 + (gc * gc - 1.0) * (1 - 0.99)
+  want = before - 7e-4 * gc / np.sqrt(ms + 0.1)
+  after = m.flat.detach().cpu().numpy()
+  assert np.allclose(after, want, rtol=1e-5, atol=1e-7)
+  assert abs(float(out["grad_norm"]) - norm) <= 1e-4 * norm
+  assert torch.equal(m.flat16.float(), m.flat.detach().to(torch.bfloat16).float())

@@ -65,6 +65,10 @@ SIGNATURES = {
                                       c_float, P, P]),
     "unreal_gemm_bf16": (c_int, [P, c_int64, c_int, P, c_int64, c_int, P, c_int64, c_int, P, P, c_int, c_int, c_int,
                                  c_int, c_int, c_int, P]),
+    "unreal_im2col": (c_int, [P, c_int, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
+    "unreal_col2im": (c_int, [P, c_int, P, c_int, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
+    "unreal_lstm_cell_fwd": (c_int, [P, P, P, P, P, c_int, P]),
+    "unreal_lstm_cell_bwd": (c_int, [P, P, P, P, P, P, c_int, P]),
 }
 
 MISSING = []
@@ -100,7 +104,8 @@ def require_device():
   return sm.value, maj.value, mnr.value
 
 
-_DTYPE_TAG = {torch.float32: F32, torch.uint8: U8}
+BF16 = 2
+_DTYPE_TAG = {torch.float32: F32, torch.uint8: U8, torch.bfloat16: BF16}
 
 
 def dtype_tag(t):

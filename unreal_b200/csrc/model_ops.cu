@@ -1,0 +1,245 @@
+// K7 support kernels around the tcgen05 GEMM: the non-GEMM pieces of UnrealModel's dense layers
+// (model/model.py:281-443).  All are HBM-bound data movement / pointwise work.
+//
+//   im2col / col2im   tf.nn.conv2d (:786-787) and tf.nn.conv2d_transpose (:803-820) with VALID
+//                     padding on NHWC tensors, expressed around a GEMM: patches are rows of a
+//                     [S*OH*OW, KH*KW*C] matrix whose column index is (ky*KW + kx)*C + c -- the
+//                     row-major order of TF's HWIO filter, so weights are used where they lie.
+//   lstm cell         contrib.rnn.BasicLSTMCell (:110): gates i, j, f, o, forget_bias 1.0.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace unreal {
+
+struct ConvGeom {
+  int s, h, w, c, kh, kw, stride, oh, ow;
+};
+
+template <typename T> struct In;
+template <> struct In<float> { static __device__ __forceinline__ float ld(const float* p) { return *p; } };
+template <> struct In<uint8_t> {
+  // frames stored as uint8 are scaled by 1/255 on load (lab_environment.py:99-102)
+  static __device__ __forceinline__ float ld(const uint8_t* p) { return __fdiv_rn((float)*p, 255.0f); }
+};
+template <> struct In<__nv_bfloat16> {
+  static __device__ __forceinline__ float ld(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+};
+
+// One thread per chunk of V consecutive elements inside one patch-row segment (KW*C contiguous
+// input elements).  Consecutive threads walk one output row, so stores are fully coalesced.
+template <typename T, int V>
+__global__ void __launch_bounds__(256) im2col_kernel(const T* __restrict__ in, __nv_bfloat16* __restrict__ out,
+                                                     ConvGeom g, int64_t total_chunks) {
+  const int seg = g.kw * g.c;            // contiguous input run
+  const int chunks_per_seg = seg / V;
+  const int k = g.kh * seg;              // output row length
+  for (int64_t id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; id < total_chunks;
+       id += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = id;
+    const int ch = (int)(r % chunks_per_seg); r /= chunks_per_seg;
+    const int ky = (int)(r % g.kh); r /= g.kh;
+    const int ox = (int)(r % g.ow); r /= g.ow;
+    const int oy = (int)(r % g.oh); r /= g.oh;
+    const int64_t s = r;
+    const T* src = in + (((s * g.h + (oy * g.stride + ky)) * g.w + ox * g.stride) * (int64_t)g.c) + ch * V;
+    __nv_bfloat16* dst = out + (((s * g.oh + oy) * g.ow + ox) * (int64_t)k) + ky * seg + ch * V;
+    if (V == 8) {
+      float v[8];
+      if (sizeof(T) == 4) {
+        const float4 a = *reinterpret_cast<const float4*>(src);
+        const float4 b = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(src) + 4);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+      } else if (sizeof(T) == 2) {
+        const uint4 u = *reinterpret_cast<const uint4*>(src);
+        *reinterpret_cast<uint4*>(dst) = u;  // bf16 -> bf16: plain 16-byte move
+        continue;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = In<T>::ld(src + j);
+      }
+      __nv_bfloat162 p0 = __floats2bfloat162_rn(v[0], v[1]), p1 = __floats2bfloat162_rn(v[2], v[3]);
+      __nv_bfloat162 p2 = __floats2bfloat162_rn(v[4], v[5]), p3 = __floats2bfloat162_rn(v[6], v[7]);
+      uint4 u;
+      u.x = *reinterpret_cast<uint32_t*>(&p0); u.y = *reinterpret_cast<uint32_t*>(&p1);
+      u.z = *reinterpret_cast<uint32_t*>(&p2); u.w = *reinterpret_cast<uint32_t*>(&p3);
+      *reinterpret_cast<uint4*>(dst) = u;
+    } else {
+      dst[0] = __float2bfloat16_rn(In<T>::ld(src));
+    }
+  }
+}
+
+// Gather form of col2im: out[s,y,x,c] = act(bias[c] + sum over taps (ky,kx) with
+// y = oy*stride + ky, x = ox*stride + kx of cols[(s,oy,ox), (ky*KW+kx)*C + c]).
+template <typename TC, typename TO>
+__global__ void __launch_bounds__(256) col2im_kernel(const TC* __restrict__ cols, TO* __restrict__ out,
+                                                     const float* __restrict__ bias, int relu, ConvGeom g,
+                                                     int64_t total) {
+  const int k = g.kh * g.kw * g.c;
+  for (int64_t id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; id < total; id += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = id;
+    const int c = (int)(r % g.c); r /= g.c;
+    const int x = (int)(r % g.w); r /= g.w;
+    const int y = (int)(r % g.h); r /= g.h;
+    const int64_t s = r;
+    float acc = bias ? bias[c] : 0.f;
+    for (int ky = y % g.stride; ky < g.kh; ky += g.stride) {
+      const int oy = (y - ky) / g.stride;
+      if (y - ky < 0 || oy >= g.oh) continue;
+      for (int kx = x % g.stride; kx < g.kw; kx += g.stride) {
+        const int ox = (x - kx) / g.stride;
+        if (x - kx < 0 || ox >= g.ow) continue;
+        acc += In<TC>::ld(cols + ((s * g.oh + oy) * g.ow + ox) * (int64_t)k + (ky * g.kw + kx) * g.c + c);
+      }
+    }
+    if (relu) acc = fmaxf(acc, 0.f);
+    if (sizeof(TO) == 2) reinterpret_cast<__nv_bfloat16*>(out)[id] = __float2bfloat16_rn(acc);
+    else reinterpret_cast<float*>(out)[id] = acc;
+  }
+}
+
+// ---- BasicLSTMCell pointwise -----------------------------------------------------------
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
+
+// gates [N,1024] pre-activations (i | j | f | o blocks of 256) are replaced by their activations
+__global__ void __launch_bounds__(256) lstm_cell_fwd_kernel(float* __restrict__ gates, const float* __restrict__ c_prev,
+                                                            float* __restrict__ c_out, float* __restrict__ h_out,
+                                                            __nv_bfloat16* __restrict__ h16_out, int n) {
+  const int id = blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= n * 256) return;
+  const int e = id >> 8, u = id & 255;
+  float* gr = gates + (size_t)e * 1024;
+  const float i = sigmoidf_(gr[u]);
+  const float j = tanhf(gr[256 + u]);
+  const float f = sigmoidf_(gr[512 + u] + 1.0f);   // forget_bias = 1.0
+  const float o = sigmoidf_(gr[768 + u]);
+  const float c = c_prev[id] * f + i * j;
+  const float h = tanhf(c) * o;
+  gr[u] = i; gr[256 + u] = j; gr[512 + u] = f; gr[768 + u] = o;
+  c_out[id] = c;
+  h_out[id] = h;
+  h16_out[id] = __float2bfloat16_rn(h);
+}
+
+// dh: total gradient wrt h_t (heads + recurrent); dc: in = gradient wrt c_t from step t+1,
+// out = gradient wrt c_{t-1}.  dgates are the gradients wrt the PRE-activations, as bf16 (the
+// operand dtype of the dgrad / wgrad GEMMs that consume them).
+__global__ void __launch_bounds__(256) lstm_cell_bwd_kernel(const float* __restrict__ gates_act,
+                                                            const float* __restrict__ c_prev, const float* __restrict__ c,
+                                                            const float* __restrict__ dh, float* __restrict__ dc,
+                                                            __nv_bfloat16* __restrict__ dgates, int n) {
+  const int id = blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= n * 256) return;
+  const int e = id >> 8, u = id & 255;
+  const float* gr = gates_act + (size_t)e * 1024;
+  const float i = gr[u], j = gr[256 + u], f = gr[512 + u], o = gr[768 + u];
+  const float tc = tanhf(c[id]);
+  const float dhv = dh[id];
+  const float d_o = dhv * tc;
+  const float dcv = dc[id] + dhv * o * (1.0f - tc * tc);
+  __nv_bfloat16* dg = dgates + (size_t)e * 1024;
+  dg[u] = __float2bfloat16_rn(dcv * j * i * (1.0f - i));
+  dg[256 + u] = __float2bfloat16_rn(dcv * i * (1.0f - j * j));
+  dg[512 + u] = __float2bfloat16_rn(dcv * c_prev[id] * f * (1.0f - f));
+  dg[768 + u] = __float2bfloat16_rn(d_o * o * (1.0f - o));
+  dc[id] = dcv * f;
+}
+
+static int grid_for_elems(int64_t total, int per_block = 256) {
+  int sms = sm_count();
+  if (sms <= 0) return 0;
+  int64_t want = (total + per_block - 1) / per_block;
+  int64_t cap = (int64_t)sms * 16;
+  if (want < 1) want = 1;
+  return (int)(want < cap ? want : cap);
+}
+
+static int check_geom(const char* fn, ConvGeom& g) {
+  UNREAL_REQUIRE(g.s > 0 && g.h > 0 && g.w > 0 && g.c > 0 && g.kh > 0 && g.kw > 0 && g.stride > 0,
+                 "%s: non-positive geometry", fn);
+  UNREAL_REQUIRE(g.h >= g.kh && g.w >= g.kw, "%s: kernel larger than the image", fn);
+  UNREAL_REQUIRE((g.h - g.kh) % g.stride == 0 && (g.w - g.kw) % g.stride == 0,
+                 "%s: VALID windows must tile the image exactly (H-KH and W-KW multiples of the stride)", fn);
+  g.oh = (g.h - g.kh) / g.stride + 1;
+  g.ow = (g.w - g.kw) / g.stride + 1;
+  return UNREAL_OK;
+}
+
+}  // namespace unreal
+
+using namespace unreal;
+
+extern "C" int unreal_im2col(const void* in, int in_dtype, void* out_bf16, int s, int h, int w, int c, int kh, int kw,
+                             int stride, void* stream) {
+  UNREAL_REQUIRE(in && out_bf16, "unreal_im2col: null buffer");
+  ConvGeom g{s, h, w, c, kh, kw, stride, 0, 0};
+  int rc = check_geom("unreal_im2col", g);
+  if (rc != UNREAL_OK) return rc;
+  const int seg = kw * c;
+  const int esz = in_dtype == UNREAL_F32 ? 4 : (in_dtype == UNREAL_U8 ? 1 : 2);
+  UNREAL_REQUIRE(in_dtype == UNREAL_F32 || in_dtype == UNREAL_U8 || in_dtype == UNREAL_BF16, "unreal_im2col: bad dtype");
+  // the 8-wide path needs every chunk 16-byte aligned on both sides (f32: 32 B reads)
+  const bool v8 = (seg % 8 == 0) && ((stride * c * esz) % 16 == 0) && ((w * c * esz) % 16 == 0) && aligned16(in) &&
+                  aligned16(out_bf16) && in_dtype != UNREAL_U8;
+  const int64_t rows = (int64_t)s * g.oh * g.ow;
+  const int64_t chunks = rows * kh * (v8 ? seg / 8 : seg);
+  const int grid = grid_for_elems(chunks);
+  if (grid <= 0) return UNREAL_ECUDA;
+  cudaStream_t st = as_stream(stream);
+  __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out_bf16);
+  if (in_dtype == UNREAL_F32) {
+    if (v8) im2col_kernel<float, 8><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(in), o, g, chunks);
+    else im2col_kernel<float, 1><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(in), o, g, chunks);
+  } else if (in_dtype == UNREAL_U8) {
+    im2col_kernel<uint8_t, 1><<<grid, 256, 0, st>>>(reinterpret_cast<const uint8_t*>(in), o, g, chunks);
+  } else {
+    if (v8) im2col_kernel<__nv_bfloat16, 8><<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(in), o, g, chunks);
+    else im2col_kernel<__nv_bfloat16, 1><<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(in), o, g, chunks);
+  }
+  UNREAL_LAUNCH_CHECK("im2col_kernel");
+  return UNREAL_OK;
+}
+
+extern "C" int unreal_col2im(const void* cols, int cols_dtype, void* out, int out_dtype, const float* bias, int relu,
+                             int s, int h, int w, int c, int kh, int kw, int stride, void* stream) {
+  UNREAL_REQUIRE(cols && out, "unreal_col2im: null buffer");
+  UNREAL_REQUIRE((cols_dtype == UNREAL_F32 || cols_dtype == UNREAL_BF16) && (out_dtype == UNREAL_F32 || out_dtype == UNREAL_BF16),
+                 "unreal_col2im: dtypes must be f32 or bf16");
+  ConvGeom g{s, h, w, c, kh, kw, stride, 0, 0};
+  int rc = check_geom("unreal_col2im", g);
+  if (rc != UNREAL_OK) return rc;
+  const int64_t total = (int64_t)s * h * w * c;
+  const int grid = grid_for_elems(total);
+  if (grid <= 0) return UNREAL_ECUDA;
+  cudaStream_t st = as_stream(stream);
+  if (cols_dtype == UNREAL_F32 && out_dtype == UNREAL_F32)
+    col2im_kernel<float, float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(cols), reinterpret_cast<float*>(out), bias, relu, g, total);
+  else if (cols_dtype == UNREAL_F32)
+    col2im_kernel<float, __nv_bfloat16><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(cols), reinterpret_cast<__nv_bfloat16*>(out), bias, relu, g, total);
+  else if (out_dtype == UNREAL_F32)
+    col2im_kernel<__nv_bfloat16, float><<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(cols), reinterpret_cast<float*>(out), bias, relu, g, total);
+  else
+    col2im_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(cols), reinterpret_cast<__nv_bfloat16*>(out), bias, relu, g, total);
+  UNREAL_LAUNCH_CHECK("col2im_kernel");
+  return UNREAL_OK;
+}
+
+extern "C" int unreal_lstm_cell_fwd(float* gates, const float* c_prev, float* c_out, float* h_out, void* h16_out,
+                                    int n, void* stream) {
+  UNREAL_REQUIRE(gates && c_prev && c_out && h_out && h16_out && n > 0, "unreal_lstm_cell_fwd: null buffer or n <= 0");
+  lstm_cell_fwd_kernel<<<(n * 256 + 255) / 256, 256, 0, as_stream(stream)>>>(
+      gates, c_prev, c_out, h_out, reinterpret_cast<__nv_bfloat16*>(h16_out), n);
+  UNREAL_LAUNCH_CHECK("lstm_cell_fwd_kernel");
+  return UNREAL_OK;
+}
+
+extern "C" int unreal_lstm_cell_bwd(const float* gates_act, const float* c_prev, const float* c, const float* dh,
+                                    float* dc, void* dgates_bf16, int n, void* stream) {
+  UNREAL_REQUIRE(gates_act && c_prev && c && dh && dc && dgates_bf16 && n > 0,
+                 "unreal_lstm_cell_bwd: null buffer or n <= 0");
+  lstm_cell_bwd_kernel<<<(n * 256 + 255) / 256, 256, 0, as_stream(stream)>>>(
+      gates_act, c_prev, c, dh, dc, reinterpret_cast<__nv_bfloat16*>(dgates_bf16), n);
+  UNREAL_LAUNCH_CHECK("lstm_cell_bwd_kernel");
+  return UNREAL_OK;
+}

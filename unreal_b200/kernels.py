@@ -321,3 +321,38 @@ def gemm_bf16(a, b, out=None, a_mn_major=False, b_mn_major=False, bias=None, add
        None if add is None else add.data_ptr(), 1 if relu else 0, 1 if accumulate else 0, int(split_k), m, n, k,
        stream_ptr())
   return out
+
+
+# ---------------------------------------------------------------------------- K7: conv / LSTM support
+def im2col(x, kh, kw, stride, out=None):
+  """x [S,H,W,C] f32 / u8 / bf16 -> bf16 [S*OH*OW, KH*KW*C] patches (HWIO column order)."""
+  s, h, w, c = x.shape
+  oh, ow = (h - kh) // stride + 1, (w - kw) // stride + 1
+  if out is None:
+    out = torch.empty(s * oh * ow, kh * kw * c, dtype=torch.bfloat16, device=x.device)
+  call("unreal_im2col", ptr(x, None, "x"), _lib.dtype_tag(x), ptr(out, torch.bfloat16, "out"), s, h, w, c, kh, kw,
+       stride, stream_ptr())
+  return out
+
+
+def col2im(cols, s, h, w, c, kh, kw, stride, bias=None, relu=False, out_dtype=torch.float32, out=None):
+  """cols [S*OH*OW, KH*KW*C] f32/bf16 -> [S,H,W,C]: sum of overlapping taps (+ bias, ReLU)."""
+  if out is None:
+    out = torch.empty(s, h, w, c, dtype=out_dtype, device=cols.device)
+  call("unreal_col2im", ptr(cols, None, "cols"), _lib.dtype_tag(cols), ptr(out, None, "out"), _lib.dtype_tag(out),
+       ptr(bias, torch.float32, "bias"), 1 if relu else 0, s, h, w, c, kh, kw, stride, stream_ptr())
+  return out
+
+
+def lstm_cell_fwd(gates, c_prev, c_out, h_out, h16_out):
+  n = gates.shape[0]
+  call("unreal_lstm_cell_fwd", ptr(gates, torch.float32, "gates"), ptr(c_prev, torch.float32, "c_prev"),
+       ptr(c_out, torch.float32, "c_out"), ptr(h_out, torch.float32, "h_out"), ptr(h16_out, torch.bfloat16, "h16_out"),
+       n, stream_ptr())
+
+
+def lstm_cell_bwd(gates_act, c_prev, c, dh, dc, dgates16):
+  n = gates_act.shape[0]
+  call("unreal_lstm_cell_bwd", ptr(gates_act, torch.float32), ptr(c_prev, torch.float32), ptr(c, torch.float32),
+       ptr(dh, torch.float32, "dh"), ptr(dc, torch.float32, "dc"), ptr(dgates16, torch.bfloat16, "dgates"), n,
+       stream_ptr())

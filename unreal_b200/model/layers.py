@@ -1,0 +1,170 @@
+"""Dense layers of UnrealModel as autograd Functions over the K7 kernels.
+
+Every matrix product -- forward, dgrad and wgrad -- is one call of the tcgen05 GEMM
+(`unreal_gemm_bf16`); weights keep TensorFlow's layouts ([in, out] for tf.matmul, HWIO for conv2d,
+[kh, kw, out, in] for conv2d_transpose; model/model.py:752-820) and are consumed where they lie:
+
+    forward   y  = x @ W            A = x (K-major),   B = W   as [K, N]  (MN-major)
+    dgrad     dx = dy @ W^T         A = dy (K-major),  B = W   as [N', K'] (K-major)
+    wgrad     dW = x^T @ dy         A = x (MN-major),  B = dy  (MN-major), split-K over the samples
+
+Activations travel in bf16 between layers (fp32 inside the LSTM cell, the heads and the losses);
+gradients are rounded to bf16 only where they become GEMM operands.  torch.autograd is used as the
+tape; the bias column sums and ReLU masks are the only torch element-wise ops on this path.
+"""
+import torch
+
+from .. import kernels as K
+
+_SM = 148
+
+
+def split_k_for(m, n, k):
+  """Split the reduction so that a wgrad (few output tiles, K = samples) fills the 148 SMs."""
+  bn = 128 if n > 64 else 64
+  tiles = ((m + 127) // 128) * ((n + bn - 1) // bn)
+  kb = (k + 63) // 64
+  want = (_SM + tiles - 1) // tiles
+  return max(1, min(want, max(1, kb // 4)))
+
+
+def _wgrad(x16, dy16):
+  """x16 [S, K_in], dy16 [S, N_out] (rows contiguous) -> f32 [K_in, N_out]."""
+  s, kin = x16.shape
+  nout = dy16.shape[1]
+  return K.gemm_bf16(x16, dy16, a_mn_major=True, b_mn_major=True, split_k=split_k_for(kin, nout, s))
+
+
+class LinearFn(torch.autograd.Function):
+  """y = act(x @ W + b): tf.matmul layers (model.py:337-340 fc1, :424 pc_fc1)."""
+
+  @staticmethod
+  def forward(ctx, x16, w16, w32, b32, relu, out_bf16):
+    y = K.gemm_bf16(x16, w16, b_mn_major=True, bias=b32, relu=relu,
+                    out_dtype=torch.bfloat16 if out_bf16 else torch.float32)
+    ctx.relu = relu
+    ctx.save_for_backward(x16, w16, y if relu else None)
+    return y
+
+  @staticmethod
+  def backward(ctx, dy):
+    x16, w16, y = ctx.saved_tensors
+    if ctx.relu:
+      dy = dy * (y > 0)
+    dy16 = dy.to(torch.bfloat16).contiguous()
+    dx = K.gemm_bf16(dy16, w16, out_dtype=torch.bfloat16) if ctx.needs_input_grad[0] else None
+    dw = _wgrad(x16, dy16)
+    db = dy16.float().sum(0)
+    return dx, None, dw, db, None, None
+
+
+class ConvFn(torch.autograd.Function):
+  """relu(conv2d(x, W, stride, VALID) + b) on NHWC input (model.py:283-289, :786-787) as
+  im2col + GEMM.  The patch matrix is recomputed in backward instead of being kept."""
+
+  @staticmethod
+  def forward(ctx, x, w16, w32, b32, kh, kw, stride):
+    s, h, w, c = x.shape
+    oh, ow = (h - kh) // stride + 1, (w - kw) // stride + 1
+    cols = K.im2col(x, kh, kw, stride)
+    o = w16.shape[1]
+    y = K.gemm_bf16(cols, w16, b_mn_major=True, bias=b32, relu=True, out_dtype=torch.bfloat16)
+    ctx.geom = (s, h, w, c, kh, kw, stride, oh, ow, o)
+    ctx.save_for_backward(x, w16, y)
+    return y.view(s, oh, ow, o)
+
+  @staticmethod
+  def backward(ctx, dy):
+    x, w16, y = ctx.saved_tensors
+    s, h, w, c, kh, kw, stride, oh, ow, o = ctx.geom
+    dy16 = (dy.reshape(-1, o) * (y > 0)).to(torch.bfloat16).contiguous()
+    cols = K.im2col(x, kh, kw, stride)
+    dw = _wgrad(cols, dy16).view(kh, kw, c, o)
+    db = dy16.float().sum(0)
+    dx = None
+    if ctx.needs_input_grad[0]:
+      dcols = K.gemm_bf16(dy16, w16, out_dtype=torch.bfloat16)          # [S*OH*OW, KH*KW*C]
+      dx = K.col2im(dcols, s, h, w, c, kh, kw, stride, out_dtype=torch.bfloat16)
+    return dx, None, dw, db, None, None, None
+
+
+class DeconvFn(torch.autograd.Function):
+  """relu(conv2d_transpose(x, W, stride 2, VALID) + b): [S,9,9,32] -> [S,20,20,O] with TF's
+  [kh, kw, out, in] filter (model.py:418-430, :803-820) as GEMM + col2im."""
+
+  @staticmethod
+  def forward(ctx, h16, w16, w32, b32, out_ch):
+    s = h16.shape[0]
+    x = h16.view(s * 81, 32)
+    cols = K.gemm_bf16(x, w16)                                            # f32 [S*81, 16*O]
+    y = K.col2im(cols, s, 20, 20, out_ch, 4, 4, 2, bias=b32, relu=True)
+    ctx.out_ch = out_ch
+    ctx.save_for_backward(h16, w16, y)
+    return y
+
+  @staticmethod
+  def backward(ctx, dy):
+    h16, w16, y = ctx.saved_tensors
+    o = ctx.out_ch
+    s = h16.shape[0]
+    dy = (dy * (y > 0)).contiguous()
+    dcols = K.im2col(dy, 4, 4, 2)                                         # bf16 [S*81, 16*O]
+    dh = K.gemm_bf16(dcols, w16, b_mn_major=True, out_dtype=torch.bfloat16).view(s, 2592)
+    x = h16.view(s * 81, 32)
+    dw = _wgrad(dcols, x).view(4, 4, o, 32)
+    db = dy.sum((0, 1, 2))
+    return dh, None, dw, db, None
+
+
+class LstmFn(torch.autograd.Function):
+  """dynamic_rnn over BasicLSTMCell(256) (model.py:110, :343-351), N envs in lock step.
+
+  xin16 [T,N,KX] bf16: columns [0, lstm_in) = concat(fc1 output, last_action_reward), the rest
+  zero padding (KX is lstm_in rounded up to 8 for the TMA row pitch).  The x-part of the kernel is
+  applied to all T*N rows in one GEMM; the h-part is the sequential per-step GEMM accumulated onto it.
+  """
+
+  @staticmethod
+  def forward(ctx, xin16, w16, w32, b32, c0, h0, lstm_in):
+    t, n, kx = xin16.shape
+    dev = xin16.device
+    x2 = xin16.view(t * n, kx)[:, :lstm_in]
+    gates = K.gemm_bf16(x2, w16[:lstm_in], b_mn_major=True, bias=b32).view(t, n, 1024)
+    c_all = torch.empty(t + 1, n, 256, device=dev)
+    h16_all = torch.empty(t + 1, n, 256, device=dev, dtype=torch.bfloat16)
+    h_all = torch.empty(t, n, 256, device=dev)
+    c_all[0].copy_(c0)
+    h16_all[0].copy_(h0)
+    wh = w16[lstm_in:]
+    for i in range(t):
+      K.gemm_bf16(h16_all[i], wh, out=gates[i], b_mn_major=True, accumulate=True)
+      K.lstm_cell_fwd(gates[i], c_all[i], c_all[i + 1], h_all[i], h16_all[i + 1])
+    ctx.lstm_in = lstm_in
+    ctx.save_for_backward(xin16, w16, gates, c_all, h16_all)
+    return h_all, c_all[t].clone(), h_all[t - 1].clone()
+
+  @staticmethod
+  def backward(ctx, dh_all, dc_last, dh_last):
+    xin16, w16, gates, c_all, h16_all = ctx.saved_tensors
+    lstm_in = ctx.lstm_in
+    t, n, kx = xin16.shape
+    dev = xin16.device
+    dh_all = dh_all.contiguous()
+    dc = torch.zeros(n, 256, device=dev) if dc_last is None else dc_last.clone().contiguous()
+    dgates = torch.empty(t, n, 1024, device=dev, dtype=torch.bfloat16)
+    wh = w16[lstm_in:]                                   # [256, 1024]: K-major B for dh = dgates @ Wh^T
+    dh_rec = None if dh_last is None else dh_last
+    for i in range(t - 1, -1, -1):
+      dh = dh_all[i] if dh_rec is None else dh_all[i] + dh_rec
+      K.lstm_cell_bwd(gates[i], c_all[i], c_all[i + 1], dh.contiguous(), dc, dgates[i])
+      if i > 0:
+        dh_rec = K.gemm_bf16(dgates[i], wh)
+    dg2 = dgates.view(t * n, 1024)
+    dw = torch.empty(lstm_in + 256, 1024, device=dev)
+    dw[:lstm_in] = _wgrad(xin16.view(t * n, kx)[:, :lstm_in], dg2)
+    dw[lstm_in:] = _wgrad(h16_all[:t].view(t * n, 256), dg2)
+    db = dg2.float().sum(0)
+    dxin = torch.zeros(t, n, kx, device=dev, dtype=torch.bfloat16)
+    # only the 256 fc1 columns carry a gradient (last_action_reward is an input)
+    K.gemm_bf16(dg2, w16[:256], out=dxin.view(t * n, kx)[:, :256])
+    return dxin, None, dw, db, None, None, None

@@ -1,0 +1,321 @@
+"""UnrealModel: drop-in for model/model.py (vanilla path, segnet_mode == 0), batched over N envs.
+
+Same constructor arguments and `run_*` helper surface as the reference (model.py:46-64, :625-728)
+with one documented deviation: there is no TensorFlow session, so the `sess` argument is accepted and
+ignored, inputs/outputs are torch CUDA tensors with a leading env axis, and `prepare_loss()` +
+the applier's `minimize_local` are replaced by the eager `update(feed, learning_rate, applier)`.
+
+Parameters live in ONE flat fp32 buffer in the reference's variable creation order (20 variables
+with all heads, model_test.py:8-20; TF layouts: [in,out] matmul kernels, HWIO conv filters,
+[kh,kw,out,in] deconv filters, one BasicLSTMCell kernel [(256+A+1+G)+256, 1024] with gates
+i, j, f, o) so that K6 updates them in one launch; a bf16 shadow of the same buffer feeds the
+tcgen05 GEMMs (K7).  Each variable starts on an 8-element boundary so the shadow views satisfy
+TMA's 16-byte alignment.
+
+The training graph follows model.py:137-598: the base tower unrolls the LSTM over the rollout from
+the fed start state; the PC and VR towers unroll from a zero state (:393, :459); RP concatenates
+three frames' conv features (:473-488); losses :490-598.  In the reference the batch axis of the
+training placeholders is TIME for one env; here tensors are [T, N, ...] and every env is one such
+unroll, `mask[t, n]` marking the steps that exist.  total loss = sum over envs (each env is one
+reference worker), scaled by `grad_scale` (default 1/N: the synchronous mean of N workers).
+"""
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from .. import _lib
+from .. import kernels as K
+from .layers import ConvFn, DeconvFn, LinearFn, LstmFn
+
+
+def _variable_specs(A, G, use_pc, use_rp):
+  lstm_in = 256 + A + 1 + G
+  specs = [
+      ("W_base_conv1", (8, 8, 3, 16), 8 * 8 * 3), ("b_base_conv1", (16,), 8 * 8 * 3),
+      ("W_base_conv2", (4, 4, 16, 32), 4 * 4 * 16), ("b_base_conv2", (32,), 4 * 4 * 16),
+      ("W_base_fc1", (2592, 256), 2592), ("b_base_fc1", (256,), 2592),
+      ("lstm_kernel", (lstm_in + 256, 1024), None), ("lstm_bias", (1024,), None),
+      ("W_base_fc_p", (256, A), 256), ("b_base_fc_p", (A,), 256),
+      ("W_base_fc_v", (256, 1), 256), ("b_base_fc_v", (1,), 256),
+  ]
+  if use_pc:
+    specs += [("W_pc_fc1", (256, 2592), 256), ("b_pc_fc1", (2592,), 256),
+              ("W_pc_deconv_v", (4, 4, 1, 32), 4 * 4 * 32), ("b_pc_deconv_v", (1,), 4 * 4 * 32),
+              ("W_pc_deconv_a", (4, 4, A, 32), 4 * 4 * 32), ("b_pc_deconv_a", (A,), 4 * 4 * 32)]
+  if use_rp:
+    specs += [("W_rp_fc1", (7776, 3), 7776), ("b_rp_fc1", (3,), 7776)]
+  return specs
+
+
+class UnrealModel(object):
+  def __init__(self, action_size, objective_size, thread_index, use_lstm, use_pixel_change, use_value_replay,
+               use_reward_prediction, pixel_change_lambda, entropy_beta, device, segnet_param_dict=None,
+               image_shape=(84, 84), is_training=True, n_classes=0, segnet_lambda=0.0, dropout=0.0,
+               for_display=False, num_envs=1, seed=0):
+    _lib.require_device()
+    segnet_param_dict = segnet_param_dict or {'segnet_mode': 0}
+    if segnet_param_dict.get('segnet_mode', 0) != 0:
+      raise _lib.UnrealError("segnet_mode != 0 (ErfNet encoder/decoder) is outside the B200 hot path")
+    if not use_lstm:
+      raise _lib.UnrealError("only the LSTM agent (use_lstm=True, the reference default) is on the B200 hot path")
+    if tuple(image_shape) != (84, 84):
+      raise _lib.UnrealError("the network is hard-wired to 84x84 frames (model.py:554, 9x9x32 flatten)")
+    self._device = torch.device(device if str(device).startswith("cuda") else "cuda:0")
+    self._action_size = A = int(action_size)
+    self._objective_size = G = int(objective_size)
+    self._thread_index = thread_index
+    self._use_lstm = use_lstm
+    self._use_pixel_change = use_pixel_change
+    self._use_value_replay = use_value_replay
+    self._use_reward_prediction = use_reward_prediction
+    self._pixel_change_lambda = float(pixel_change_lambda)
+    self._entropy_beta = float(entropy_beta)
+    self.segnet_mode = 0
+    self.is_training = is_training
+    self.for_display = for_display
+    self.num_envs = int(num_envs)
+    self.lstm_in = 256 + A + 1 + G
+    self.kx = (self.lstm_in + 7) // 8 * 8
+    self._build_variables(seed)
+    self.reset_state()
+
+  # ---- variables (model.py:752-783 initialisers) --------------------------------------
+  def _build_variables(self, seed):
+    A, G = self._action_size, self._objective_size
+    specs = _variable_specs(A, G, self._use_pixel_change, self._use_reward_prediction)
+    offsets, off = [], 0
+    for name, shape, _ in specs:
+      n = int(np.prod(shape))
+      offsets.append((name, shape, off, n))
+      off = (off + n + 7) // 8 * 8
+    self._padded = (off + 31) // 32 * 32
+    self.num_parameters = sum(o[3] for o in offsets)
+    rs = np.random.RandomState(seed)
+    host = np.zeros(self._padded, np.float32)
+    for (name, shape, o, n), (_, _, fan_in) in zip(offsets, specs):
+      if name == "lstm_kernel":       # BasicLSTMCell: TF default glorot-uniform kernel, zero bias
+        lim = np.sqrt(6.0 / (shape[0] + shape[1]))
+        v = rs.uniform(-lim, lim, size=shape)
+      elif name == "lstm_bias":
+        v = np.zeros(shape)
+      else:
+        d = 1.0 / np.sqrt(fan_in)
+        v = rs.uniform(-d, d, size=shape)
+      host[o:o + n] = v.astype(np.float32).reshape(-1)
+    self.flat = torch.from_numpy(host).to(self._device).requires_grad_(True)
+    self.flat16 = torch.zeros(self._padded, dtype=torch.bfloat16, device=self._device)
+    self._offsets = offsets
+    self.refresh_shadow()
+
+  def _views(self, flat):
+    return OrderedDict((name, flat[o:o + n].view(shape)) for name, shape, o, n in self._offsets)
+
+  def refresh_shadow(self):
+    """bf16 copy of the parameters for the GEMMs; call after every optimiser step."""
+    with torch.no_grad():
+      self.flat16.copy_(self.flat)
+    self.v16 = self._views(self.flat16)
+
+  def get_vars(self):
+    """The variables in creation order (views of the flat buffer), like model.py:729-730."""
+    return list(self._views(self.flat.detach()).values())
+
+  def named_vars(self):
+    return self._views(self.flat.detach())
+
+  def get_global_vars(self):
+    return self.get_vars()
+
+  def load_vars(self, named):
+    """Copy TF-layout arrays (dict name -> array) into the flat buffer."""
+    with torch.no_grad():
+      views = self._views(self.flat)
+      for k, v in named.items():
+        views[k].copy_(torch.as_tensor(np.asarray(v), dtype=torch.float32).to(self._device))
+    self.refresh_shadow()
+
+  def sync_from(self, src_network, name=None):
+    """model.py:735-749: copy the source network's variables (pairing by creation order)."""
+    with torch.no_grad():
+      self.flat.copy_(src_network.flat)
+    self.refresh_shadow()
+
+  # ---- towers -------------------------------------------------------------------------
+  def _w(self, p32, name, rows=None):
+    """(bf16 shadow as a [K,N] matrix, fp32 view that routes the gradient, bias view)."""
+    return self.v16[name], p32[name]
+
+  def _encoder(self, p32, images):
+    """model.py:281-289.  images [S,84,84,3] f32 / u8 -> h2 bf16 [S,9,9,32]."""
+    h1 = ConvFn.apply(images, self.v16["W_base_conv1"].view(192, 16), p32["W_base_conv1"], p32["b_base_conv1"], 8, 8, 4)
+    h2 = ConvFn.apply(h1, self.v16["W_base_conv2"].view(256, 32), p32["W_base_conv2"], p32["b_base_conv2"], 4, 4, 2)
+    return h2
+
+  def _lstm_input(self, p32, h2, lar, t, n):
+    """fc1 + concat with last_action_reward (model.py:332-343) -> bf16 [T,N,KX]."""
+    fc = LinearFn.apply(h2.view(t * n, 2592), self.v16["W_base_fc1"], p32["W_base_fc1"], p32["b_base_fc1"], True, True)
+    pad = self.kx - self.lstm_in
+    parts = [fc.view(t, n, 256), lar.to(torch.bfloat16)]
+    if pad:
+      parts.append(torch.zeros(t, n, pad, dtype=torch.bfloat16, device=fc.device))
+    return torch.cat(parts, dim=2)
+
+  def _tower(self, p32, images, lar, c0, h0):
+    """encoder + fc1 + LSTM unroll.  images [T,N,84,84,3], lar [T,N,A+1+G] -> h [T,N,256] f32."""
+    t, n = images.shape[:2]
+    h2 = self._encoder(p32, images.reshape(t * n, 84, 84, 3))
+    xin = self._lstm_input(p32, h2, lar, t, n)
+    return LstmFn.apply(xin, self.v16["lstm_kernel"], p32["lstm_kernel"], p32["lstm_bias"], c0, h0, self.lstm_in), h2
+
+  def _policy_value(self, p32, h):
+    """model.py:358-377 (tiny [.,256]x[256,A+1] products, fp32)."""
+    logits = h @ p32["W_base_fc_p"] + p32["b_base_fc_p"]
+    v = (h @ p32["W_base_fc_v"] + p32["b_base_fc_v"]).squeeze(-1)
+    return torch.softmax(logits, dim=-1), v
+
+  def _pc_q(self, p32, h):
+    """model.py:411-443.  h [S,256] f32 -> q [S,20,20,A], q_max [S,20,20]."""
+    A = self._action_size
+    hp = LinearFn.apply(h.to(torch.bfloat16), self.v16["W_pc_fc1"], p32["W_pc_fc1"], p32["b_pc_fc1"], True, True)
+    v = DeconvFn.apply(hp, self.v16["W_pc_deconv_v"].view(16, 32), p32["W_pc_deconv_v"], p32["b_pc_deconv_v"], 1)
+    a = DeconvFn.apply(hp, self.v16["W_pc_deconv_a"].view(16 * A, 32), p32["W_pc_deconv_a"], p32["b_pc_deconv_a"], A)
+    q = v + a - a.mean(dim=3, keepdim=True)
+    return q, q.max(dim=3).values
+
+  def _zeros_state(self, n):
+    z = torch.zeros(n, 256, device=self._device)
+    return z, z
+
+  # ---- acting-side helpers (model.py:625-728), batched over envs ----------------------
+  def reset_state(self, mask=None):
+    """model.py:625-628; `mask` [N] selects the envs whose state is zeroed (all when None)."""
+    if mask is None or not hasattr(self, "base_lstm_state_out"):
+      self.base_lstm_state_out = tuple(torch.zeros(self.num_envs, 256, device=self._device) for _ in range(2))
+    else:
+      keep = (mask == 0).to(torch.float32).unsqueeze(1)
+      self.base_lstm_state_out = tuple(s * keep for s in self.base_lstm_state_out)
+
+  def _images(self, s_t):
+    img = s_t['image'] if isinstance(s_t, dict) else s_t
+    if not isinstance(img, torch.Tensor):
+      img = torch.as_tensor(np.asarray(img, dtype=np.float32))
+    img = img.to(self._device)
+    return img.reshape(1, -1, 84, 84, 3)
+
+  def _lar(self, last_action_reward, n):
+    lar = last_action_reward
+    if not isinstance(lar, torch.Tensor):
+      lar = torch.as_tensor(np.asarray(lar, dtype=np.float32))
+    return lar.to(self._device, torch.float32).reshape(1, n, -1)
+
+  def _step(self, s_t, last_action_reward, state):
+    with torch.no_grad():
+      p32 = self._views(self.flat)
+      img = self._images(s_t)
+      n = img.shape[1]
+      (h, c1, h1), _ = self._tower(p32, img, self._lar(last_action_reward, n), state[0], state[1])
+      return p32, h[0], (c1, h1)
+
+  def run_base_policy_and_value(self, sess, s_t, last_action_reward, active=None, mode=""):
+    """model.py:630-660: one acting step; advances the LSTM state of the active envs."""
+    p32, h, new_state = self._step(s_t, last_action_reward, self.base_lstm_state_out)
+    with torch.no_grad():
+      pi, v = self._policy_value(p32, h)
+      if active is None:
+        self.base_lstm_state_out = new_state
+      else:
+        m = active.to(torch.bool).unsqueeze(1)
+        self.base_lstm_state_out = tuple(torch.where(m, a, b) for a, b in zip(new_state, self.base_lstm_state_out))
+    return pi, v, None
+
+  def run_base_value(self, sess, s_t, last_action_reward):
+    """model.py:687-704: bootstrap value; the LSTM state is NOT advanced."""
+    p32, h, _ = self._step(s_t, last_action_reward, self.base_lstm_state_out)
+    with torch.no_grad():
+      return self._policy_value(p32, h)[1]
+
+  def run_pc_q_max(self, sess, s_t, last_action_reward):
+    """model.py:707-712 (zero LSTM state)."""
+    img = self._images(s_t)
+    p32, h, _ = self._step(s_t, last_action_reward, self._zeros_state(img.shape[1]))
+    with torch.no_grad():
+      return self._pc_q(p32, h)[1]
+
+  def run_vr_value(self, sess, s_t, last_action_reward):
+    """model.py:715-720 (zero LSTM state)."""
+    img = self._images(s_t)
+    p32, h, _ = self._step(s_t, last_action_reward, self._zeros_state(img.shape[1]))
+    with torch.no_grad():
+      return self._policy_value(p32, h)[1]
+
+  def run_rp_c(self, sess, state_history):
+    """model.py:723-728: three frames [N,3,84,84,3] -> class probabilities [N,3]."""
+    with torch.no_grad():
+      return self._rp_c(self._views(self.flat), state_history)
+
+  def _rp_c(self, p32, images):
+    n = images.shape[0]
+    h2 = self._encoder(p32, images.reshape(n * 3, 84, 84, 3))
+    logits = h2.reshape(n, 7776).float() @ p32["W_rp_fc1"] + p32["b_rp_fc1"]
+    return torch.softmax(logits, dim=-1)
+
+  # ---- losses (model.py:490-598) -------------------------------------------------------
+  def loss(self, feed):
+    """Total UNREAL loss summed over envs, and its parts.  feed (all time-major CUDA tensors):
+       base: images [T,N,84,84,3], lar [T,N,A+1+G], a [T,N,A] one-hot, adv [T,N], R [T,N],
+             mask [T,N], c0 / h0 [N,256]
+       pc:   images [L,N,...], lar, a [L,N,A], R [L,N,20,20], mask [L,N]
+       vr:   images, lar, R [L,N], mask [L,N]
+       rp:   images [N,3,84,84,3], c [N,3] one-hot (zero, positive, negative)"""
+    p32 = self._views(self.flat)
+    parts = OrderedDict()
+    b = feed["base"]
+    (h, _, _), _ = self._tower(p32, b["images"], b["lar"], b["c0"], b["h0"])
+    pi, v = self._policy_value(p32, h)
+    log_pi = torch.log(pi.clamp(1e-20, 1.0))
+    entropy = -(pi * log_pi).sum(-1)
+    mask = b["mask"].to(torch.float32)
+    parts["policy"] = -((((log_pi * b["a"]).sum(-1)) * b["adv"] + entropy * self._entropy_beta) * mask).sum()
+    parts["value"] = 0.25 * (((b["R"] - v) ** 2) * mask).sum()
+    parts["entropy"] = (entropy * mask).sum().detach()
+    total = parts["policy"] + parts["value"]
+    if self._use_pixel_change and "pc" in feed:
+      f = feed["pc"]
+      L, n = f["images"].shape[:2]
+      (h, _, _), _ = self._tower(p32, f["images"], f["lar"], *self._zeros_state(n))
+      q, _ = self._pc_q(p32, h.reshape(L * n, 256))
+      qa = (q.view(L, n, 20, 20, -1) * f["a"][:, :, None, None, :]).sum(-1)
+      parts["pc"] = self._pixel_change_lambda * 0.5 * (((f["R"] - qa) ** 2) * f["mask"].float()[:, :, None, None]).sum()
+      total = total + parts["pc"]
+    if self._use_value_replay and "vr" in feed:
+      f = feed["vr"]
+      n = f["images"].shape[1]
+      (h, _, _), _ = self._tower(p32, f["images"], f["lar"], *self._zeros_state(n))
+      parts["vr"] = 0.5 * (((f["R"] - self._policy_value(p32, h)[1]) ** 2) * f["mask"].float()).sum()
+      total = total + parts["vr"]
+    if self._use_reward_prediction and "rp" in feed:
+      f = feed["rp"]
+      c = self._rp_c(p32, f["images"]).clamp(1e-20, 1.0)
+      parts["rp"] = -(f["c"] * torch.log(c)).sum()
+      total = total + parts["rp"]
+    return total, parts
+
+  def loss_and_grads(self, feed, grad_scale=1.0):
+    """-> (total, parts, flat gradient [padded P] of grad_scale * total)."""
+    self.flat.grad = None
+    total, parts = self.loss(feed)
+    (total * grad_scale).backward()
+    return total.detach(), {k: v.detach() for k, v in parts.items()}, self.flat.grad
+
+  def update(self, feed, learning_rate, grad_applier, grad_scale=None):
+    """One learner step: the reference's `sess.run(apply_gradients, feed_dict)` (trainer.py:543-559)."""
+    n = feed["base"]["images"].shape[1]
+    scale = (1.0 / n) if grad_scale is None else grad_scale
+    total, parts, grad = self.loss_and_grads(feed, scale)
+    norm = grad_applier.apply_flat_to(self.flat, grad, learning_rate)
+    self.refresh_shadow()
+    out = dict(parts)
+    out["total"] = total
+    out["grad_norm"] = norm
+    return out

@@ -72,6 +72,10 @@ class RMSPropApplier(object):
     self._total, self._padded = total, padded
     self._flat_var = flat
     self._flat_grad = torch.zeros(padded, dtype=torch.float32, device=dev)
+    self._alloc_slots(dev, world, rank)
+
+  def _alloc_slots(self, dev, world, rank):
+    padded = self._padded
     self._shard = padded // world
     self._lo = rank * self._shard
     # slots only for the owned slice (the whole buffer when world == 1)
@@ -96,6 +100,34 @@ class RMSPropApplier(object):
 
   def flat_parameters(self):
     return self._flat_var[:self._total]
+
+  def bind_flat(self, flat_var):
+    """Adopt a caller-owned flat fp32 parameter buffer (UnrealModel.flat) as the single global
+    variable: no re-homing, the slots cover it element for element."""
+    if self._vars is not None:
+      if self._flat_var.data_ptr() != flat_var.data_ptr():
+        raise _lib.UnrealError("RMSPropApplier is bound to one global variable list")
+      return
+    world, rank = self._world()
+    if flat_var.dtype != torch.float32 or not flat_var.is_cuda or not flat_var.is_contiguous():
+      raise _lib.UnrealError("bind_flat needs a contiguous float32 CUDA buffer; there is no CPU fallback")
+    if flat_var.numel() % (4 * world) != 0:
+      raise _lib.UnrealError("flat buffer length must be a multiple of 4 * world_size")
+    self._vars = [flat_var]
+    self._offsets = [(0, flat_var.numel())]
+    self._total = self._padded = flat_var.numel()
+    self._flat_var = flat_var.detach()
+    self._flat_grad = torch.zeros_like(self._flat_var)
+    self._alloc_slots(flat_var.device, world, rank)
+
+  def apply_flat_to(self, flat_var, flat_grad, learning_rate=None):
+    """Clip + RMSProp (+ the NCCL exchange when distributed) of `flat_grad` into `flat_var`."""
+    self.bind_flat(flat_var)
+    if flat_grad.data_ptr() != self._flat_grad.data_ptr():
+      if flat_grad.numel() != self._padded or flat_grad.dtype != torch.float32 or not flat_grad.is_contiguous():
+        raise _lib.UnrealError("flat_grad must be a contiguous float32 buffer of the parameters' length")
+      self._flat_grad = flat_grad
+    return self.apply_flat(learning_rate)
 
   # -- update -----------------------------------------------------------------------------
   def minimize_local(self, loss, global_var_list, local_var_list, thread_index, learning_rate=None):
