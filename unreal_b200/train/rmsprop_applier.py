@@ -35,6 +35,9 @@ class RMSPropApplier(object):
     self._vars = None
     self._group = process_group
     self._average = average_gradients
+    # the two device kernels (K6).  tests/test_sharded_applier.py swaps in a CPU stand-in to drive
+    # the partition + collective plumbing under gloo; the product path is always `kernels`.
+    self._ops = K
 
   # -- distributed helpers ---------------------------------------------------------------
   def _world(self):
@@ -51,7 +54,7 @@ class RMSPropApplier(object):
       return
     var_list = list(var_list)
     dev = var_list[0].device
-    if dev.type != "cuda":
+    if dev.type != "cuda" and self._ops is K:
       raise _lib.UnrealError("RMSPropApplier needs CUDA variables; there is no CPU fallback")
     world, rank = self._world()
     sizes = [v.numel() for v in var_list]
@@ -109,7 +112,7 @@ class RMSPropApplier(object):
         raise _lib.UnrealError("RMSPropApplier is bound to one global variable list")
       return
     world, rank = self._world()
-    if flat_var.dtype != torch.float32 or not flat_var.is_cuda or not flat_var.is_contiguous():
+    if flat_var.dtype != torch.float32 or not (flat_var.is_cuda or self._ops is not K) or not flat_var.is_contiguous():
       raise _lib.UnrealError("bind_flat needs a contiguous float32 CUDA buffer; there is no CPU fallback")
     if flat_var.numel() % (4 * world) != 0:
       raise _lib.UnrealError("flat buffer length must be a multiple of 4 * world_size")
@@ -163,17 +166,18 @@ class RMSPropApplier(object):
     lr = self._lr(learning_rate)
     world, _ = self._world()
     self._sumsq.zero_()
+    ops = self._ops
     if world == 1:
-      K.grad_sumsq(self._flat_grad, self._sumsq)
-      K.rmsprop_update(self._flat_var, self._rms, self._mom if self._momentum != 0.0 else None, self._flat_grad,
+      ops.grad_sumsq(self._flat_grad, self._sumsq)
+      ops.rmsprop_update(self._flat_var, self._rms, self._mom if self._momentum != 0.0 else None, self._flat_grad,
                        self._sumsq, lr, self._decay, self._momentum, self._epsilon, self._clip_norm,
                        grad_scale=1.0, grad_norm=self._norm)
       return self._norm
     dist.reduce_scatter_tensor(self._grad_shard, self._flat_grad, op=dist.ReduceOp.SUM, group=self._group)
-    K.grad_sumsq(self._grad_shard, self._sumsq)
+    ops.grad_sumsq(self._grad_shard, self._sumsq)
     dist.all_reduce(self._sumsq, op=dist.ReduceOp.SUM, group=self._group)      # 8 bytes
     var_shard = self._flat_var[self._lo:self._lo + self._shard]
-    K.rmsprop_update(var_shard, self._rms, self._mom if self._momentum != 0.0 else None, self._grad_shard,
+    ops.rmsprop_update(var_shard, self._rms, self._mom if self._momentum != 0.0 else None, self._grad_shard,
                      self._sumsq, lr, self._decay, self._momentum, self._epsilon, self._clip_norm,
                      grad_scale=(1.0 / world) if self._average else 1.0, grad_norm=self._norm)
     dist.all_gather_into_tensor(self._flat_var, var_shard, group=self._group)
