@@ -190,6 +190,8 @@ def run_b200(args):
   dev = torch.device("cuda", local)
   if world > 1:
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):
+      os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line (no version banner)
     dist.init_process_group("nccl", device_id=dev)
 
   from unreal_b200 import _lib
@@ -227,8 +229,11 @@ def run_b200(args):
   k4_ms = sum(e[2].elapsed_time(e[3]) for e in evs) / K
 
   # ---- host-buffer (e2e) arm: same pass through run_host() ----
-  h_act = eng.actions.cpu().numpy(); h_val = eng.values.cpu().numpy()
-  h_bv = eng.boot_value.cpu().numpy(); h_bq = eng.boot_q.cpu().numpy()
+  # the caller's host buffers are the engine's pinned staging arrays (filled in place once)
+  hbuf = eng.host_inputs()
+  hbuf["actions"][...] = eng.actions.cpu().numpy(); hbuf["values"][...] = eng.values.cpu().numpy()
+  hbuf["boot_value"][...] = eng.boot_value.cpu().numpy(); hbuf["boot_q"][...] = eng.boot_q.cpu().numpy()
+  h_act, h_val, h_bv, h_bq = hbuf["actions"], hbuf["values"], hbuf["boot_value"], hbuf["boot_q"]
   for _ in range(3):
     out = eng.run_host(h_act, h_val, h_bv, h_bq)
   ke = max(3, min(K, 200))
@@ -267,8 +272,9 @@ def run_b200(args):
         "dtype": args.obs_dtype, "data": "synthetic", "config": workload_config(args), "clocks": clocks,
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": eng.h2d_bytes_per_pass,
                 "d2h_bytes_per_step": eng.d2h_bytes_per_pass, "steps": ke, "ms_per_step": e2e_ms / ke,
-                "api": "unreal_b200.train.rollout.RolloutTargets.run_host (pinned host in/out; frames, "
-                       "pixel-change maps and PC targets stay in HBM for the learner)", "checksum_R": checksum},
+                "api": "unreal_b200.train.rollout.RolloutTargets.run_host (pinned host in/out, copies "
+                       "pipelined around the phases on a second stream; frames, pixel-change maps and PC "
+                       "targets stay in HBM for the learner)", "checksum_R": checksum},
         "gpu_launches": K * eng.launches_per_pass,
         "roofline": {"bound": "hbm", "kernel": "maze_cta_kernel (K1)" if args.obs_dtype == "f32" else "maze_warp_kernel (K1)",
                      "achieved": achieved, "peak": peak,

@@ -76,7 +76,7 @@ def test_two_gpu_learner_exchange():
   want = var.cpu().numpy()
   for r in results:
     assert np.allclose(r["flat"], want, rtol=1e-5, atol=1e-6)
-    assert abs(r["norm"] - float(np.sqrt((g.double() ** 2).sum()))) <= 1e-3
+    assert abs(r["norm"] - float(torch.sqrt((g.double() ** 2).sum()).cpu())) <= 1e-3
   # (2) both learners applied the same (mean) gradient: identical parameters afterwards
   assert np.array_equal(results[0]["after"], results[1]["after"])
   assert np.array_equal(results[0]["before"], results[1]["before"])

@@ -49,6 +49,7 @@ class RolloutTargets(object):
     # host staging for the host-buffer entry point (pinned, reused every pass)
     self._h_in = None
     self._h_out = None
+    self._copy_stream = None
 
   # launches per pass, by kernel
   @property
@@ -119,24 +120,64 @@ class RolloutTargets(object):
     self._ensure_host()
     return sum(v.numel() * v.element_size() for v in self._h_out.values())
 
-  def run_host(self, actions, values, boot_value, boot_q):
+  def host_inputs(self):
+    """Pinned host staging buffers (numpy views) a caller can fill in place: actions [T,N] i32,
+    values [T,N] f32, boot_value [N] f32, boot_q [N,20,20] f32.  Passing these same arrays (or
+    None) to run_host() skips the host-side staging copy."""
+    self._ensure_host()
+    return {k: v.numpy() for k, v in self._h_in.items()}
+
+  def run_host(self, actions=None, values=None, boot_value=None, boot_q=None):
     """One pass from HOST buffers (numpy or CPU tensors): copies the inputs host->device,
     runs the pass, copies rewards / terminals / returns / advantages back and returns them
     as numpy views of pinned memory (valid until the next call).  Frames, pixel-change maps
-    and PC targets stay on the device for the learner."""
+    and PC targets stay on the device for the learner.
+
+    The copies are pipelined around the three phases on a second stream: only the actions
+    (T*N*4 bytes) gate the first K1 launch; values / bootstraps travel while the T steps run,
+    rewards / terminals return under K3+K4 and returns / advantages under K4."""
     self._ensure_host()
     hi, ho = self._h_in, self._h_out
+    for name, arr in (("actions", actions), ("values", values), ("boot_value", boot_value), ("boot_q", boot_q)):
+      if arr is None:
+        continue
+      t = torch.as_tensor(arr)
+      if t.data_ptr() != hi[name].data_ptr():       # not already the pinned staging buffer
+        hi[name].copy_(t)
     with torch.cuda.device(self.device):
-      hi["actions"].copy_(torch.as_tensor(actions)); hi["values"].copy_(torch.as_tensor(values))
-      hi["boot_value"].copy_(torch.as_tensor(boot_value)); hi["boot_q"].copy_(torch.as_tensor(boot_q))
+      if self.use_graphs and self._graphs is None:
+        self._capture()
+      if self._copy_stream is None:
+        self._copy_stream = torch.cuda.Stream(self.device)
+        self._ev = [torch.cuda.Event() for _ in range(5)]
+      main = torch.cuda.current_stream()
+      side = self._copy_stream
+      ev_start, ev_in, ev_k1, ev_k3, ev_out = self._ev
+      phases = ([g.replay for g in self._graphs] if self.use_graphs
+                else [self._steps, self._returns, self._pc_targets])
+      ev_start.record(main)
       self.actions.copy_(hi["actions"], non_blocking=True)
-      self.values.copy_(hi["values"], non_blocking=True)
-      self.boot_value.copy_(hi["boot_value"], non_blocking=True)
-      self.boot_q.copy_(hi["boot_q"], non_blocking=True)
-      self.run_device()
-      ho["reward"].copy_(self.reward, non_blocking=True)
-      ho["terminal"].copy_(self.terminal, non_blocking=True)
-      ho["R"].copy_(self.R, non_blocking=True)
-      ho["adv"].copy_(self.adv, non_blocking=True)
-      torch.cuda.current_stream().synchronize()
+      side.wait_event(ev_start)                      # previous pass has finished with the inputs
+      with torch.cuda.stream(side):
+        self.values.copy_(hi["values"], non_blocking=True)
+        self.boot_value.copy_(hi["boot_value"], non_blocking=True)
+        self.boot_q.copy_(hi["boot_q"], non_blocking=True)
+        ev_in.record(side)
+      phases[0]()                                    # T x K1
+      ev_k1.record(main)
+      with torch.cuda.stream(side):
+        side.wait_event(ev_k1)
+        ho["reward"].copy_(self.reward, non_blocking=True)
+        ho["terminal"].copy_(self.terminal, non_blocking=True)
+      main.wait_event(ev_in)
+      phases[1]()                                    # K3
+      ev_k3.record(main)
+      with torch.cuda.stream(side):
+        side.wait_event(ev_k3)
+        ho["R"].copy_(self.R, non_blocking=True)
+        ho["adv"].copy_(self.adv, non_blocking=True)
+        ev_out.record(side)
+      phases[2]()                                    # K4
+      main.wait_event(ev_out)
+      main.synchronize()
     return {k: v.numpy() for k, v in ho.items()}
