@@ -25,7 +25,8 @@ SHAPES = [
 ]
 
 
-def bench(fn, iters=20):
+def bench(fn, iters=None):
+  iters = iters or ITERS
   for _ in range(3):
     fn()
   torch.cuda.synchronize()
@@ -39,7 +40,11 @@ def bench(fn, iters=20):
 
 
 out = open(sys.argv[1], "w") if len(sys.argv) > 1 else sys.stdout
+ONLY = os.environ.get("GEMM_ONLY")          # substring filter, e.g. GEMM_ONLY="fc1 fwd"
+ITERS = int(os.environ.get("GEMM_ITERS", "20"))
 for name, m, n, k, a_mn, b_mn, sk in SHAPES:
+  if ONLY and ONLY not in name:
+    continue
   a = torch.randn((k, m) if a_mn else (m, k), device=dev).to(torch.bfloat16)
   b = torch.randn((k, n) if b_mn else (n, k), device=dev).to(torch.bfloat16)
   c = torch.zeros(m, n, device=dev, dtype=torch.float32 if sk > 1 else torch.bfloat16)

@@ -50,6 +50,7 @@ struct GemmArgs {
   int c_bf16;       // 1: C is bf16, 0: f32
   int relu;
   int accumulate;   // 1: C += result (red.global.add.f32); implied by split_k > 1
+  int tma_store;    // 1: epilogue stages tiles in shared memory and stores / reduces them with TMA
 };
 
 template <int BN>
@@ -59,7 +60,8 @@ struct GemmCfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = (BN >= 256) ? 4 : (BN >= 128 ? 6 : 8);
   static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
+  static constexpr int kEpiBytes = 4 * 2 * 4096;  // 4 epilogue warps x 2 buffers x [32 rows x 128 B]
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*barriers, tmem slot*/ + kEpiBytes + 1024 /*alignment slack*/;
 };
 
 // ---- epilogue stores -------------------------------------------------------------------
@@ -67,10 +69,28 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, uint32_t src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int kPending>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kPending) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-                    const GemmArgs g) {
+                    const __grid_constant__ CUtensorMap tma_c, const GemmArgs g) {
   using Cfg = GemmCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   // 128-byte swizzle atoms are 1024 bytes: every operand tile starts on a 1024-byte boundary
@@ -91,6 +111,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&tma_a);
     prefetch_tensormap(&tma_b);
+    if (g.tma_store) prefetch_tensormap(&tma_c);
     for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
     fence_mbar_init();
@@ -171,6 +192,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     const int row_in_tile = quarter * 32 + lane;
     int acc = 0; uint32_t acc_phase = 0;
     const bool atomic = g.accumulate || g.split_k > 1;
+    // TMA-store path: each warp stages [32 rows x 128 bytes] (64 bf16 or 32 f32 columns) in its own
+    // double-buffered, 128B-swizzled shared-memory tile and hands it to the TMA engine, which
+    // writes whole 128-byte lines and clips rows / columns outside C.
+    const uint32_t ebuf = smem_base + Cfg::kStages * Cfg::kStageBytes + 1024u + (uint32_t)(warp - 2) * 8192u;
+    uint32_t ebuf_it = 0;
     for (int w = blockIdx.x; w < work_total; w += gridDim.x) {
       const int n_blk = w % num_n, m_blk = (w / num_n) % num_m, sp = w / (num_n * num_m);
       mbar_wait(tfull_bar(acc), acc_phase);
@@ -178,70 +204,110 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       const int row = m_blk * kBM + row_in_tile;
       const bool row_ok = row < g.m;
       const bool lead = (sp == 0);  // bias / addend are applied by the first K split only
+      const uint32_t tmem_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
+      if (g.tma_store) {
+        const int group = g.c_bf16 ? 64 : 32;          // columns per 128-byte staged row
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += group) {
+          const int gcol0 = n_blk * BN + c0;
+          if (gcol0 >= g.n) break;                     // uniform: the rest of the tile is outside C
+          const uint32_t buf = ebuf + (ebuf_it & 1u) * 4096u;
+          ++ebuf_it;
+          if (lane == 0) bulk_wait_read<1>();          // the store issued two groups ago has read `buf`
+          __syncwarp();
+          const uint32_t rowp = buf + (uint32_t)lane * 128u;
+#pragma unroll 1
+          for (int half = 0; half * 32 < group; ++half) {
+            uint32_t r[32];
+            tmem_ld32(tmem_row + (uint32_t)(c0 + half * 32), r);
+            tmem_ld_wait();
+            const int col0 = gcol0 + half * 32;
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+            if (g.bias != nullptr && lead) {
+              if (col0 + 32 <= g.n) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                  const float4 t = __ldg(reinterpret_cast<const float4*>(g.bias + col0 + j));
+                  v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) if (col0 + j < g.n) v[j] += __ldg(g.bias + col0 + j);
+              }
+            }
+            if (g.add != nullptr && lead && row_ok) {
+              const float* ap = reinterpret_cast<const float*>(g.add) + (size_t)row * g.ldc + col0;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) if (col0 + j < g.n) v[j] += ap[j];
+            }
+            if (g.relu) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+            }
+            if (g.c_bf16) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                __nv_bfloat162 p0 = __floats2bfloat162_rn(v[8 * q], v[8 * q + 1]);
+                __nv_bfloat162 p1 = __floats2bfloat162_rn(v[8 * q + 2], v[8 * q + 3]);
+                __nv_bfloat162 p2 = __floats2bfloat162_rn(v[8 * q + 4], v[8 * q + 5]);
+                __nv_bfloat162 p3 = __floats2bfloat162_rn(v[8 * q + 6], v[8 * q + 7]);
+                const uint32_t chunk = (uint32_t)(half * 4 + q) ^ (uint32_t)(lane & 7);
+                st_shared_v4(rowp + chunk * 16u, *reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1),
+                             *reinterpret_cast<uint32_t*>(&p2), *reinterpret_cast<uint32_t*>(&p3));
+              }
+            } else {
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                const uint32_t chunk = (uint32_t)q ^ (uint32_t)(lane & 7);
+                st_shared_v4(rowp + chunk * 16u, __float_as_uint(v[4 * q]), __float_as_uint(v[4 * q + 1]),
+                             __float_as_uint(v[4 * q + 2]), __float_as_uint(v[4 * q + 3]));
+              }
+            }
+          }
+          fence_proxy_async_smem();                    // generic-proxy writes -> visible to the TMA engine
+          __syncwarp();
+          if (lane == 0) {
+            if (atomic) tma_reduce_add_2d(&tma_c, buf, gcol0, m_blk * kBM + quarter * 32);
+            else tma_store_2d(&tma_c, buf, gcol0, m_blk * kBM + quarter * 32);
+            bulk_commit();
+          }
+        }
+      } else {
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t r[32];
-        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + c0), r);
+        tmem_ld32(tmem_row + (uint32_t)c0, r);
         tmem_ld_wait();
         const int col0 = n_blk * BN + c0;
         if (row_ok && col0 < g.n) {
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          const bool full = (col0 + 32 <= g.n);
           if (g.bias != nullptr && lead) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) if (full || col0 + j < g.n) v[j] += __ldg(g.bias + col0 + j);
+            for (int j = 0; j < 32; ++j) if (col0 + j < g.n) v[j] += __ldg(g.bias + col0 + j);
           }
           if (g.add != nullptr && lead) {
             const float* ap = reinterpret_cast<const float*>(g.add) + (size_t)row * g.ldc + col0;
-            if (full && ((g.ldc & 3) == 0)) {
 #pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                float4 t = *reinterpret_cast<const float4*>(ap + j);
-                v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) if (col0 + j < g.n) v[j] += ap[j];
-            }
+            for (int j = 0; j < 32; ++j) if (col0 + j < g.n) v[j] += ap[j];
           }
           if (g.relu) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
           }
+          // unaligned / odd leading dimensions: plain element stores
           if (g.c_bf16) {
             __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(g.c) + (size_t)row * g.ldc + col0;
-            if (full && ((g.ldc & 7) == 0)) {
 #pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                __nv_bfloat162 p0 = __floats2bfloat162_rn(v[j], v[j + 1]);
-                __nv_bfloat162 p1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
-                __nv_bfloat162 p2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]);
-                __nv_bfloat162 p3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
-                uint4 u;
-                u.x = *reinterpret_cast<uint32_t*>(&p0); u.y = *reinterpret_cast<uint32_t*>(&p1);
-                u.z = *reinterpret_cast<uint32_t*>(&p2); u.w = *reinterpret_cast<uint32_t*>(&p3);
-                *reinterpret_cast<uint4*>(cp + j) = u;
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) if (col0 + j < g.n) cp[j] = __float2bfloat16_rn(v[j]);
-            }
+            for (int j = 0; j < 32; ++j) if (col0 + j < g.n) cp[j] = __float2bfloat16_rn(v[j]);
           } else {
             float* cp = reinterpret_cast<float*>(g.c) + (size_t)row * g.ldc + col0;
-            const bool vec = full && ((g.ldc & 3) == 0);
             if (atomic) {
-              if (vec) {
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) red_add_v4(cp + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
-              } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) if (col0 + j < g.n) atomicAdd(cp + j, v[j]);
-              }
-            } else if (vec) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(cp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+              for (int j = 0; j < 32; ++j) if (col0 + j < g.n) atomicAdd(cp + j, v[j]);
             } else {
 #pragma unroll
               for (int j = 0; j < 32; ++j) if (col0 + j < g.n) cp[j] = v[j];
@@ -249,11 +315,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           }
         }
       }
+      }
       fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
+    if (lane == 0) bulk_wait_all();                    // staged tiles must be read before the CTA exits
   }
   __syncwarp();
   fence_before_sync();
@@ -282,22 +350,22 @@ static EncodeTiledFn encode_tiled() {
   return fn;
 }
 
-// row-major bf16 [rows, cols] with leading dimension ld; box = [box_rows, 64 cols], 128-byte swizzle
-int make_tma_2d_bf16(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+// row-major [rows, cols] matrix with leading dimension ld; box = [box_rows, 128 bytes], 128-byte swizzle
+int make_tma_2d(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows, bool f32) {
   EncodeTiledFn fn = encode_tiled();
   if (fn == nullptr) {
     set_error("cuTensorMapEncodeTiled is not available from the CUDA driver");
     return UNREAL_ECUDA;
   }
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * (f32 ? 4 : 2)};
+  cuuint32_t box[2] = {f32 ? 32u : 64u, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1u, 1u};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+  CUresult r = fn(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
-    set_error("cuTensorMapEncodeTiled failed (%d) for a [%lld x %lld] bf16 matrix, ld %lld", (int)r, (long long)rows,
+    set_error("cuTensorMapEncodeTiled failed (%d) for a [%lld x %lld] matrix, ld %lld", (int)r, (long long)rows,
               (long long)cols, (long long)ld);
     return UNREAL_ECUDA;
   }
@@ -305,7 +373,8 @@ int make_tma_2d_bf16(CUtensorMap* map, const void* base, int64_t rows, int64_t c
 }
 
 template <int BN, bool A_MN, bool B_MN>
-static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& g, cudaStream_t st) {
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmArgs& g,
+                       cudaStream_t st) {
   using Cfg = GemmCfg<BN>;
   static bool configured = false;
   auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN>;
@@ -318,7 +387,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmA
   const int sms = sm_count();
   if (sms <= 0) return UNREAL_ECUDA;
   const int grid = (int)(work < sms ? work : sms);
-  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(ta, tb, g);
+  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(ta, tb, tc, g);
   UNREAL_LAUNCH_CHECK("gemm_tcgen05_kernel");
   return UNREAL_OK;
 }
@@ -347,22 +416,35 @@ extern "C" int unreal_gemm_bf16(const void* a, int64_t lda, int a_mn_major, cons
                  "unreal_gemm_bf16: accumulate / split-K need an f32 output");
   UNREAL_REQUIRE(!(relu && (accumulate || split_k > 1)), "unreal_gemm_bf16: ReLU cannot be fused with accumulation");
   // tile width: wide tiles for wide outputs; MN-major B needs whole 64-column boxes
-  int bn = (n > 64) ? 128 : (n > 32 ? 64 : 32);
+  int bn = (n > 128) ? 256 : ((n > 64) ? 128 : (n > 32 ? 64 : 32));
+  { int forced = get_tunable("gemm_bn", 0); if (forced == 32 || forced == 64 || forced == 128 || forced == 256) bn = forced; }
   if (b_mn_major && bn < 64) bn = 64;
-  CUtensorMap ta, tb;
+  CUtensorMap ta, tb, tc;
   int rc;
-  if (a_mn_major) rc = make_tma_2d_bf16(&ta, a, k, m, lda, kBK); else rc = make_tma_2d_bf16(&ta, a, m, k, lda, kBM);
+  if (a_mn_major) rc = make_tma_2d(&ta, a, k, m, lda, kBK, false); else rc = make_tma_2d(&ta, a, m, k, lda, kBM, false);
   if (rc != UNREAL_OK) return rc;
-  if (b_mn_major) rc = make_tma_2d_bf16(&tb, b, k, n, ldb, kBK); else rc = make_tma_2d_bf16(&tb, b, n, k, ldb, bn);
+  if (b_mn_major) rc = make_tma_2d(&tb, b, k, n, ldb, kBK, false); else rc = make_tma_2d(&tb, b, n, k, ldb, bn, false);
   if (rc != UNREAL_OK) return rc;
-  GemmArgs g{c, bias, add, ldc, m, n, k, split_k, c_dtype == UNREAL_GEMM_OUT_BF16 ? 1 : 0, relu ? 1 : 0,
-             accumulate ? 1 : 0};
+  const bool c_bf16 = c_dtype == UNREAL_GEMM_OUT_BF16;
+  // TMA epilogue needs a 16-byte row pitch; odd leading dimensions fall back to element stores
+  int tma_store = ((ldc * (c_bf16 ? 2 : 4)) % 16 == 0) && get_tunable("gemm_tma_store", 1) != 0;
+  if (tma_store) {
+    rc = make_tma_2d(&tc, c, m, n, ldc, 32, !c_bf16);
+    if (rc != UNREAL_OK) return rc;
+  } else {
+    tc = ta;
+  }
+  GemmArgs g{c, bias, add, ldc, m, n, k, split_k, c_bf16 ? 1 : 0, relu ? 1 : 0, accumulate ? 1 : 0, tma_store};
   cudaStream_t st = as_stream(stream);
 #define UNREAL_GEMM_CASE(BN_, AMN_, BMN_) \
-  if (bn == BN_ && (a_mn_major != 0) == AMN_ && (b_mn_major != 0) == BMN_) return launch_gemm<BN_, AMN_, BMN_>(ta, tb, g, st);
+  if (bn == BN_ && (a_mn_major != 0) == AMN_ && (b_mn_major != 0) == BMN_) return launch_gemm<BN_, AMN_, BMN_>(ta, tb, tc, g, st);
   UNREAL_GEMM_CASE(32, false, false)
   UNREAL_GEMM_CASE(64, false, false)
   UNREAL_GEMM_CASE(128, false, false)
+  UNREAL_GEMM_CASE(256, false, false)
+  UNREAL_GEMM_CASE(256, false, true)
+  UNREAL_GEMM_CASE(256, true, false)
+  UNREAL_GEMM_CASE(256, true, true)
   UNREAL_GEMM_CASE(64, false, true)
   UNREAL_GEMM_CASE(128, false, true)
   UNREAL_GEMM_CASE(32, true, false)
