@@ -87,6 +87,131 @@ __device__ __forceinline__ void bulk_wait_read() {
 }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
+// One accumulator tile [32 rows of this warp x BN columns]: TMEM -> registers -> bias / addend /
+// ReLU -> C.  `lead` = this work item applies bias / addend (first K split).  TMA-store path: the
+// warp stages [32 rows x 128 bytes] (64 bf16 or 32 f32 columns) in its own double-buffered,
+// 128B-swizzled shared-memory tile and hands it to the TMA engine, which writes whole 128-byte
+// lines and clips rows / columns outside C.
+template <int BN>
+__device__ __forceinline__ void epilogue_tile(const GemmArgs& g, const CUtensorMap* tma_c, uint32_t tmem_row,
+                                              uint32_t ebuf, uint32_t& ebuf_it, int lane, int warp_row0, int n_blk,
+                                              bool lead) {
+  const bool atomic = g.accumulate || g.split_k > 1;
+  const int row = warp_row0 + lane;
+  const bool row_ok = row < g.m;
+  if (g.tma_store) {
+    const int group = g.c_bf16 ? 64 : 32;          // columns per 128-byte staged row
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += group) {
+      const int gcol0 = n_blk * BN + c0;
+      if (gcol0 >= g.n) break;                     // uniform: the rest of the tile is outside C
+      const uint32_t buf = ebuf + (ebuf_it & 1u) * 4096u;
+      ++ebuf_it;
+      if (lane == 0) bulk_wait_read<1>();          // the store issued two groups ago has read `buf`
+      __syncwarp();
+      const uint32_t rowp = buf + (uint32_t)lane * 128u;
+#pragma unroll 1
+      for (int half = 0; half * 32 < group; ++half) {
+        uint32_t r[32];
+        tmem_ld32(tmem_row + (uint32_t)(c0 + half * 32), r);
+        tmem_ld_wait();
+        const int col0 = gcol0 + half * 32;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        if (g.bias != nullptr && lead) {
+          if (col0 + 32 <= g.n) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 t = __ldg(reinterpret_cast<const float4*>(g.bias + col0 + j));
+              v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (col0 + j < g.n) v[j] += __ldg(g.bias + col0 + j);
+          }
+        }
+        if (g.add != nullptr && lead && row_ok) {
+          const float* ap = reinterpret_cast<const float*>(g.add) + (size_t)row * g.ldc + col0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) if (col0 + j < g.n) v[j] += ap[j];
+        }
+        if (g.relu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+        if (g.c_bf16) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            __nv_bfloat162 p0 = __floats2bfloat162_rn(v[8 * q], v[8 * q + 1]);
+            __nv_bfloat162 p1 = __floats2bfloat162_rn(v[8 * q + 2], v[8 * q + 3]);
+            __nv_bfloat162 p2 = __floats2bfloat162_rn(v[8 * q + 4], v[8 * q + 5]);
+            __nv_bfloat162 p3 = __floats2bfloat162_rn(v[8 * q + 6], v[8 * q + 7]);
+            const uint32_t chunk = (uint32_t)(half * 4 + q) ^ (uint32_t)(lane & 7);
+            st_shared_v4(rowp + chunk * 16u, *reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1),
+                         *reinterpret_cast<uint32_t*>(&p2), *reinterpret_cast<uint32_t*>(&p3));
+          }
+        } else {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const uint32_t chunk = (uint32_t)q ^ (uint32_t)(lane & 7);
+            st_shared_v4(rowp + chunk * 16u, __float_as_uint(v[4 * q]), __float_as_uint(v[4 * q + 1]),
+                         __float_as_uint(v[4 * q + 2]), __float_as_uint(v[4 * q + 3]));
+          }
+        }
+      }
+      fence_proxy_async_smem();                    // generic-proxy writes -> visible to the TMA engine
+      __syncwarp();
+      if (lane == 0) {
+        if (atomic) tma_reduce_add_2d(tma_c, buf, gcol0, warp_row0);
+        else tma_store_2d(tma_c, buf, gcol0, warp_row0);
+        bulk_commit();
+      }
+    }
+  } else {
+#pragma unroll 1
+  for (int c0 = 0; c0 < BN; c0 += 32) {
+    uint32_t r[32];
+    tmem_ld32(tmem_row + (uint32_t)c0, r);
+    tmem_ld_wait();
+    const int col0 = n_blk * BN + c0;
+    if (row_ok && col0 < g.n) {
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+      if (g.bias != nullptr && lead) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) if (col0 + j < g.n) v[j] += __ldg(g.bias + col0 + j);
+      }
+      if (g.add != nullptr && lead) {
+        const float* ap = reinterpret_cast<const float*>(g.add) + (size_t)row * g.ldc + col0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) if (col0 + j < g.n) v[j] += ap[j];
+      }
+      if (g.relu) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+      }
+      // unaligned / odd leading dimensions: plain element stores
+      if (g.c_bf16) {
+        __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(g.c) + (size_t)row * g.ldc + col0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) if (col0 + j < g.n) cp[j] = __float2bfloat16_rn(v[j]);
+      } else {
+        float* cp = reinterpret_cast<float*>(g.c) + (size_t)row * g.ldc + col0;
+        if (atomic) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) if (col0 + j < g.n) atomicAdd(cp + j, v[j]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) if (col0 + j < g.n) cp[j] = v[j];
+        }
+      }
+    }
+  }
+  }
+}
+
 template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
@@ -189,133 +314,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   } else {
     // ===== epilogue (warps 2..5): warp w may touch TMEM lanes 32*(w%4) .. +31 =====
     const int quarter = warp & 3;
-    const int row_in_tile = quarter * 32 + lane;
     int acc = 0; uint32_t acc_phase = 0;
-    const bool atomic = g.accumulate || g.split_k > 1;
-    // TMA-store path: each warp stages [32 rows x 128 bytes] (64 bf16 or 32 f32 columns) in its own
-    // double-buffered, 128B-swizzled shared-memory tile and hands it to the TMA engine, which
-    // writes whole 128-byte lines and clips rows / columns outside C.
     const uint32_t ebuf = smem_base + Cfg::kStages * Cfg::kStageBytes + 1024u + (uint32_t)(warp - 2) * 8192u;
     uint32_t ebuf_it = 0;
     for (int w = blockIdx.x; w < work_total; w += gridDim.x) {
       const int n_blk = w % num_n, m_blk = (w / num_n) % num_m, sp = w / (num_n * num_m);
       mbar_wait(tfull_bar(acc), acc_phase);
       fence_after_sync();
-      const int row = m_blk * kBM + row_in_tile;
-      const bool row_ok = row < g.m;
-      const bool lead = (sp == 0);  // bias / addend are applied by the first K split only
-      const uint32_t tmem_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
-      if (g.tma_store) {
-        const int group = g.c_bf16 ? 64 : 32;          // columns per 128-byte staged row
-#pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += group) {
-          const int gcol0 = n_blk * BN + c0;
-          if (gcol0 >= g.n) break;                     // uniform: the rest of the tile is outside C
-          const uint32_t buf = ebuf + (ebuf_it & 1u) * 4096u;
-          ++ebuf_it;
-          if (lane == 0) bulk_wait_read<1>();          // the store issued two groups ago has read `buf`
-          __syncwarp();
-          const uint32_t rowp = buf + (uint32_t)lane * 128u;
-#pragma unroll 1
-          for (int half = 0; half * 32 < group; ++half) {
-            uint32_t r[32];
-            tmem_ld32(tmem_row + (uint32_t)(c0 + half * 32), r);
-            tmem_ld_wait();
-            const int col0 = gcol0 + half * 32;
-            float v[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-            if (g.bias != nullptr && lead) {
-              if (col0 + 32 <= g.n) {
-#pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                  const float4 t = __ldg(reinterpret_cast<const float4*>(g.bias + col0 + j));
-                  v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
-                }
-              } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) if (col0 + j < g.n) v[j] += __ldg(g.bias + col0 + j);
-              }
-            }
-            if (g.add != nullptr && lead && row_ok) {
-              const float* ap = reinterpret_cast<const float*>(g.add) + (size_t)row * g.ldc + col0;
-#pragma unroll
-              for (int j = 0; j < 32; ++j) if (col0 + j < g.n) v[j] += ap[j];
-            }
-            if (g.relu) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-            }
-            if (g.c_bf16) {
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                __nv_bfloat162 p0 = __floats2bfloat162_rn(v[8 * q], v[8 * q + 1]);
-                __nv_bfloat162 p1 = __floats2bfloat162_rn(v[8 * q + 2], v[8 * q + 3]);
-                __nv_bfloat162 p2 = __floats2bfloat162_rn(v[8 * q + 4], v[8 * q + 5]);
-                __nv_bfloat162 p3 = __floats2bfloat162_rn(v[8 * q + 6], v[8 * q + 7]);
-                const uint32_t chunk = (uint32_t)(half * 4 + q) ^ (uint32_t)(lane & 7);
-                st_shared_v4(rowp + chunk * 16u, *reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1),
-                             *reinterpret_cast<uint32_t*>(&p2), *reinterpret_cast<uint32_t*>(&p3));
-              }
-            } else {
-#pragma unroll
-              for (int q = 0; q < 8; ++q) {
-                const uint32_t chunk = (uint32_t)q ^ (uint32_t)(lane & 7);
-                st_shared_v4(rowp + chunk * 16u, __float_as_uint(v[4 * q]), __float_as_uint(v[4 * q + 1]),
-                             __float_as_uint(v[4 * q + 2]), __float_as_uint(v[4 * q + 3]));
-              }
-            }
-          }
-          fence_proxy_async_smem();                    // generic-proxy writes -> visible to the TMA engine
-          __syncwarp();
-          if (lane == 0) {
-            if (atomic) tma_reduce_add_2d(&tma_c, buf, gcol0, m_blk * kBM + quarter * 32);
-            else tma_store_2d(&tma_c, buf, gcol0, m_blk * kBM + quarter * 32);
-            bulk_commit();
-          }
-        }
-      } else {
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld32(tmem_row + (uint32_t)c0, r);
-        tmem_ld_wait();
-        const int col0 = n_blk * BN + c0;
-        if (row_ok && col0 < g.n) {
-          float v[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          if (g.bias != nullptr && lead) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) if (col0 + j < g.n) v[j] += __ldg(g.bias + col0 + j);
-          }
-          if (g.add != nullptr && lead) {
-            const float* ap = reinterpret_cast<const float*>(g.add) + (size_t)row * g.ldc + col0;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) if (col0 + j < g.n) v[j] += ap[j];
-          }
-          if (g.relu) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-          }
-          // unaligned / odd leading dimensions: plain element stores
-          if (g.c_bf16) {
-            __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(g.c) + (size_t)row * g.ldc + col0;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) if (col0 + j < g.n) cp[j] = __float2bfloat16_rn(v[j]);
-          } else {
-            float* cp = reinterpret_cast<float*>(g.c) + (size_t)row * g.ldc + col0;
-            if (atomic) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) if (col0 + j < g.n) atomicAdd(cp + j, v[j]);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) if (col0 + j < g.n) cp[j] = v[j];
-            }
-          }
-        }
-      }
-      }
+      epilogue_tile<BN>(g, &tma_c, tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN), ebuf, ebuf_it,
+                        lane, m_blk * kBM + quarter * 32, n_blk, sp == 0);
       fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
@@ -329,6 +336,146 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   if (warp == 2) {
     fence_after_sync();
     tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+
+// ---- CTA-pair variant: 256 x 256 tile per cluster of two CTAs (tcgen05.mma.cta_group::2) ----------
+// Each CTA loads its own 128 rows of A and its own 128 of the tile's 256 B rows (so operand traffic
+// from L2 per SM is half that of two independent 128x256 tiles), the leader CTA issues the MMAs for
+// both, every CTA's TMEM receives its 128 accumulator rows and runs its own epilogue.
+constexpr int k2Stages = 6;
+constexpr int k2StageBytes = 2 * kBM * kBK * 2;   // A 16 KB + B half 16 KB
+constexpr int k2SmemBytes = k2Stages * k2StageBytes + 1024 + 4 * 2 * 4096 + 1024;
+
+template <bool A_MN, bool B_MN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+gemm2sm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                       const __grid_constant__ CUtensorMap tma_c, const GemmArgs g) {
+  constexpr int BN = 256;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + k2Stages * k2StageBytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (k2Stages + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * k2Stages + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * k2Stages + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * k2Stages + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+  const int num_m = (g.m + 2 * kBM - 1) / (2 * kBM), num_n = (g.n + BN - 1) / BN;
+  const int kb_total = (g.k + kBK - 1) / kBK;
+  const int kb_per = (kb_total + g.split_k - 1) / g.split_k;
+  const int work_total = num_m * num_n * g.split_k;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&tma_a);
+    prefetch_tensormap(&tma_b);
+    if (g.tma_store) prefetch_tensormap(&tma_c);
+    for (int s = 0; s < k2Stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 8); }
+    fence_mbar_init();
+  } else if (warp == 2) {
+    tmem_alloc_2sm<512>(tmem_slot);
+  }
+  fence_before_sync();
+  cluster_sync_all();                 // both CTAs' barriers exist before any remote arrive / TMA signal
+  fence_after_sync();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer (both CTAs): own A rows, own half of the B rows =====
+      int stage = 0; uint32_t phase = 0;
+      for (int w = cluster_id; w < work_total; w += num_clusters) {
+        const int n_blk = w % num_n, m_blk = (w / num_n) % num_m, sp = w / (num_n * num_m);
+        const int kb0 = sp * kb_per, kb1 = min(kb0 + kb_per, kb_total);
+        const int m0 = m_blk * 2 * kBM + (int)rank * kBM, n0 = n_blk * BN + (int)rank * (BN / 2);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t sa = smem_base + stage * k2StageBytes, sb = sa + kBM * kBK * 2;
+          if (leader) mbar_arrive_expect_tx(full_bar(stage), 2 * k2StageBytes);   // both CTAs' bytes
+          if (A_MN) {
+#pragma unroll
+            for (int b = 0; b < kBM / 64; ++b)
+              tma_load_2d_2sm(sa + b * (kBK * 128), &tma_a, full_bar(stage), m0 + b * 64, kb * kBK);
+          } else {
+            tma_load_2d_2sm(sa, &tma_a, full_bar(stage), kb * kBK, m0);
+          }
+          if (B_MN) {
+#pragma unroll
+            for (int b = 0; b < BN / 2 / 64; ++b)
+              tma_load_2d_2sm(sb + b * (kBK * 128), &tma_b, full_bar(stage), n0 + b * 64, kb * kBK);
+          } else {
+            tma_load_2d_2sm(sb, &tma_b, full_bar(stage), kb * kBK, n0);
+          }
+          if (++stage == k2Stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && leader) {
+      // ===== MMA issuer (leader CTA only) =====
+      constexpr uint32_t idesc = idesc_bf16_f32(2 * kBM, BN, A_MN, B_MN);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int w = cluster_id; w < work_total; w += num_clusters) {
+        const int sp = w / (num_n * num_m);
+        const int kb0 = sp * kb_per, kb1 = min(kb0 + kb_per, kb_total);
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);   // both CTAs' epilogues have drained this accumulator
+        fence_after_sync();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          fence_after_sync();
+          const uint32_t sa = smem_base + stage * k2StageBytes, sb = sa + kBM * kBK * 2;
+#pragma unroll
+          for (int k = 0; k < kBK / kUmmaK; ++k) {
+            const uint64_t ad = A_MN ? smem_desc_sw128(sa + k * 2048, kBK * 128, 1024)
+                                     : smem_desc_sw128(sa + k * 32, 16, 1024);
+            const uint64_t bd = B_MN ? smem_desc_sw128(sb + k * 2048, kBK * 128, 1024)
+                                     : smem_desc_sw128(sb + k * 32, 16, 1024);
+            mma_f16_2sm(tmem_d, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          mma_commit_2sm(empty_bar(stage), 3);        // frees the stage in BOTH CTAs
+          if (++stage == k2Stages) { stage = 0; phase ^= 1u; }
+        }
+        mma_commit_2sm(tfull_bar(acc), 3);            // accumulator complete, both epilogues may read
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else {
+    // ===== epilogue (warps 2..5 of both CTAs): this CTA's 128 accumulator rows =====
+    const int quarter = warp & 3;
+    int acc = 0; uint32_t acc_phase = 0;
+    const uint32_t ebuf = smem_base + k2Stages * k2StageBytes + 1024u + (uint32_t)(warp - 2) * 8192u;
+    uint32_t ebuf_it = 0;
+    for (int w = cluster_id; w < work_total; w += num_clusters) {
+      const int n_blk = w % num_n, m_blk = (w / num_n) % num_m, sp = w / (num_n * num_m);
+      mbar_wait(tfull_bar(acc), acc_phase);
+      fence_after_sync();
+      epilogue_tile<BN>(g, &tma_c, tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN), ebuf, ebuf_it,
+                        lane, m_blk * 2 * kBM + (int)rank * kBM + quarter * 32, n_blk, sp == 0);
+      fence_before_sync();
+      __syncwarp();
+      if (lane == 0) {
+        if (leader) mbar_arrive(tempty_bar(acc));
+        else mbar_arrive_remote(mapa_cluster(tempty_bar(acc), 0));
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+    if (lane == 0) bulk_wait_all();
+  }
+  __syncwarp();
+  fence_before_sync();
+  cluster_sync_all();                 // the peer may still be read by the leader's MMAs / signal its barriers
+  if (warp == 2) {
+    fence_after_sync();
+    tmem_dealloc_2sm<512>(tmem_base);
   }
 }
 
@@ -392,6 +539,25 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
   return UNREAL_OK;
 }
 
+template <bool A_MN, bool B_MN>
+static int launch_gemm_2sm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmArgs& g,
+                           cudaStream_t st) {
+  static bool configured = false;
+  auto kern = gemm2sm_tcgen05_kernel<A_MN, B_MN>;
+  if (!configured) {
+    UNREAL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, k2SmemBytes));
+    configured = true;
+  }
+  const int num_m = (g.m + 2 * kBM - 1) / (2 * kBM), num_n = (g.n + 255) / 256;
+  const int64_t work = (int64_t)num_m * num_n * g.split_k;
+  const int sms = sm_count();
+  if (sms <= 0) return UNREAL_ECUDA;
+  const int clusters = (int)(work < sms / 2 ? work : sms / 2);
+  kern<<<2 * clusters, kGemmThreads, k2SmemBytes, st>>>(ta, tb, tc, g);
+  UNREAL_LAUNCH_CHECK("gemm2sm_tcgen05_kernel");
+  return UNREAL_OK;
+}
+
 }  // namespace unreal
 
 using namespace unreal;
@@ -419,11 +585,19 @@ extern "C" int unreal_gemm_bf16(const void* a, int64_t lda, int a_mn_major, cons
   int bn = (n > 128) ? 256 : ((n > 64) ? 128 : (n > 32 ? 64 : 32));
   { int forced = get_tunable("gemm_bn", 0); if (forced == 32 || forced == 64 || forced == 128 || forced == 256) bn = forced; }
   if (b_mn_major && bn < 64) bn = 64;
+  // CTA-pair kernel (256 x 256 tiles) once there is at least one full wave of pairs
+  const int64_t work2 = (int64_t)((m + 255) / 256) * ((n + 255) / 256) * split_k;
+  // ... and the problem is compute-bound (long K): short-K, output-dominated shapes are paced by the
+  // epilogue, where independent CTAs measured faster (profiles/r1_gemm_bench_v4_2sm.jsonl)
+  int use_2sm = (n > 128) && work2 >= sm_count() / 2 && kb_total >= 16;
+  { int forced = get_tunable("gemm_2sm", -1); if (forced == 0) use_2sm = 0; else if (forced == 1 && n > 128) use_2sm = 1; }
+  if (use_2sm) bn = 256;
   CUtensorMap ta, tb, tc;
   int rc;
   if (a_mn_major) rc = make_tma_2d(&ta, a, k, m, lda, kBK, false); else rc = make_tma_2d(&ta, a, m, k, lda, kBM, false);
   if (rc != UNREAL_OK) return rc;
-  if (b_mn_major) rc = make_tma_2d(&tb, b, k, n, ldb, kBK, false); else rc = make_tma_2d(&tb, b, n, k, ldb, bn, false);
+  if (b_mn_major) rc = make_tma_2d(&tb, b, k, n, ldb, kBK, false);
+  else rc = make_tma_2d(&tb, b, n, k, ldb, use_2sm ? 128 : bn, false);   // a CTA of a pair loads half the B rows
   if (rc != UNREAL_OK) return rc;
   const bool c_bf16 = c_dtype == UNREAL_GEMM_OUT_BF16;
   // TMA epilogue needs a 16-byte row pitch; odd leading dimensions fall back to element stores
@@ -436,6 +610,10 @@ extern "C" int unreal_gemm_bf16(const void* a, int64_t lda, int a_mn_major, cons
   }
   GemmArgs g{c, bias, add, ldc, m, n, k, split_k, c_bf16 ? 1 : 0, relu ? 1 : 0, accumulate ? 1 : 0, tma_store};
   cudaStream_t st = as_stream(stream);
+  if (use_2sm) {
+    if (a_mn_major) return b_mn_major ? launch_gemm_2sm<true, true>(ta, tb, tc, g, st) : launch_gemm_2sm<true, false>(ta, tb, tc, g, st);
+    return b_mn_major ? launch_gemm_2sm<false, true>(ta, tb, tc, g, st) : launch_gemm_2sm<false, false>(ta, tb, tc, g, st);
+  }
 #define UNREAL_GEMM_CASE(BN_, AMN_, BMN_) \
   if (bn == BN_ && (a_mn_major != 0) == AMN_ && (b_mn_major != 0) == BMN_) return launch_gemm<BN_, AMN_, BMN_>(ta, tb, tc, g, st);
   UNREAL_GEMM_CASE(32, false, false)
