@@ -208,6 +208,18 @@ int unreal_lstm_cell_fwd(float* gates, const float* c_prev, float* c_out, float*
 int unreal_lstm_cell_bwd(const float* gates_act, const float* c_prev, const float* c, const float* dh, float* dc,
                          void* dgates_bf16, int n, void* stream);
 
+/* Fused convolutions of the encoder (model.py:281-289) as implicit GEMMs whose im2col is done by
+ * the TMA engine (multi-dimensional boxes over a space-to-depth view; no patch matrix in memory).
+ *   unreal_s2d_frames: frames [S,84,84,3] f32 / u8 (/255) -> x' bf16 [S,21,21,48],
+ *                      x'[Y,X,dy*12+dx*3+c] = frame[4Y+dy, 4X+dx, c].
+ *   unreal_conv_fwd  : layer 1: in = x' -> out bf16 [S,20,20,16] = relu(conv 8x8 s4 + bias)
+ *                      layer 2: in = h1 bf16 [S,20,20,16] -> out bf16 [S,9,9,32] = relu(conv 4x4 s2 + bias)
+ *                      w_taps bf16 [N,256]: for tap t = by*2+bx, columns 64t.. hold the filter slice
+ *                      W[s*by+dy, s*bx+dx, c, o] in (dy,dx,c) order (48 used columns for layer 1). */
+int unreal_s2d_frames(const void* frames, int dtype, void* out_bf16, int s, void* stream);
+int unreal_conv_fwd(const void* in_bf16, int layer, const void* w_taps_bf16, const float* bias, void* out_bf16, int s,
+                    void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -180,3 +180,35 @@ def test_update_applies_rmsprop_like_the_oracle():
   assert np.allclose(after, want, rtol=1e-5, atol=1e-7)
   assert abs(float(out["grad_norm"]) - norm) <= 1e-4 * norm
   assert torch.equal(m.flat16.float(), m.flat.detach().to(torch.bfloat16).float())
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.uint8])
+def test_fused_conv_forward_matches_direct_convolution(dtype):
+  """TMA-im2col convolutions (space-to-depth taps) against torch's conv2d on the same bf16-rounded
+  operands in fp32: only the fp32 summation order differs -> one bf16 ulp (2^-8 relative)."""
+  from unreal_b200 import kernels as K
+  import torch.nn.functional as F
+  dev = torch.device("cuda", 0)
+  g = torch.Generator(device=dev).manual_seed(3)
+  for s in (1, 5, 37):
+    if dtype == torch.uint8:
+      x = torch.randint(0, 256, (s, 84, 84, 3), device=dev, dtype=torch.uint8, generator=g)
+      xf = (x.float() / 255.0).to(torch.bfloat16).float()
+    else:
+      x = torch.rand(s, 84, 84, 3, device=dev, generator=g)
+      xf = x.to(torch.bfloat16).float()
+    w1 = ((torch.rand(8, 8, 3, 16, device=dev, generator=g) - 0.5) * 0.2).to(torch.bfloat16)
+    b1 = (torch.rand(16, device=dev, generator=g) - 0.5) * 0.1
+    w2 = ((torch.rand(4, 4, 16, 32, device=dev, generator=g) - 0.5) * 0.2).to(torch.bfloat16)
+    b2 = (torch.rand(32, device=dev, generator=g) - 0.5) * 0.1
+    xs = K.s2d_frames(x)
+    want_s2d = xf.view(s, 21, 4, 21, 4, 3).permute(0, 1, 3, 2, 4, 5).reshape(s, 21, 21, 48)
+    assert torch.equal(xs.float(), want_s2d)
+    h1 = K.conv_fwd(xs, 1, K.conv_taps(w1, 4), b1)
+    ref1 = F.relu(F.conv2d(xf.permute(0, 3, 1, 2), w1.float().permute(3, 2, 0, 1), b1, stride=4)).permute(0, 2, 3, 1)
+    assert tuple(h1.shape) == (s, 20, 20, 16)
+    assert torch.allclose(h1.float(), ref1, rtol=2.0 ** -7, atol=1e-3)
+    h2 = K.conv_fwd(h1, 2, K.conv_taps(w2, 2), b2)
+    ref2 = F.relu(F.conv2d(h1.float().permute(0, 3, 1, 2), w2.float().permute(3, 2, 0, 1), b2, stride=2)).permute(0, 2, 3, 1)
+    assert tuple(h2.shape) == (s, 9, 9, 32)
+    assert torch.allclose(h2.float(), ref2, rtol=2.0 ** -7, atol=1e-3)

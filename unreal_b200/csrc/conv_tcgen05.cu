@@ -1,0 +1,350 @@
+// K7 convolutions (model/model.py:281-289: conv 8x8x3->16 stride 4, conv 4x4x16->32 stride 2, VALID,
+// NHWC) as implicit GEMMs on tcgen05 with the im2col done by the TMA engine -- no patch matrix ever
+// exists in memory.
+//
+// A stride-s KxK convolution with K = 2s is a 2x2 stride-1 convolution over the space-to-depth view
+//     x'[Y, X, (dy, dx, c)] = x[s*Y + dy, s*X + dx, c]:
+//     out[oy, ox, :] = sum over the four taps (by, bx) of  x'[oy+by, ox+bx, :] . Wtap[by, bx]
+// so for one tap the GEMM A operand is just a shifted window of x' -- a multi-dimensional TMA box:
+//   conv1: x' is materialised once in bf16 by s2d_frames_kernel ([S,21,21,48], also the f32/u8 -> bf16
+//          conversion); a 4-D box {48->64 ch, 20 X, 5 Y, 1 sample} is 100 GEMM rows (5 output rows).
+//   conv2: x' is only a VIEW of h1 [S,20,20,16]: for each dy a 4-D tensor map {32 (dx,c), 10 X, 10 Y, S}
+//          based at row dy (TMA needs hierarchical strides, so dy cannot be a box dimension between
+//          the channel run and X; measured with scripts/probes/tma5d_probe.cu) with box {32, 9, 9, 1}
+//          lands 81 rows x 32 channels (one sample, half a tap) in shared memory.
+// The conv1 box arrives as rows of 128 bytes with the 128-byte swizzle, the conv2 boxes as rows of
+// 64 bytes with the 64-byte swizzle: both are K-major UMMA layouts as they land.
+// The four tap filters [N, 64] stay resident in shared memory for the whole (persistent) kernel.
+// Rows of the 128-row UMMA tile that the box does not cover hold stale data; they only produce
+// accumulator rows that the (row-clipped) TMA store never writes.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "tc05.cuh"
+
+namespace unreal {
+using namespace tc05;
+
+int make_tma_nd_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                     const uint32_t* box, int swizzle_bytes);   // gemm_tcgen05.cu
+
+constexpr int kConvThreads = 192;
+constexpr int kConvStages = 8;
+template <int MODE> struct ConvCfg;
+template <> struct ConvCfg<1> {      // conv1: 4 taps, 64 K-columns (48 used) per step, 128-byte rows
+  static constexpr int kSteps = 4, kRowBytes = 128, kStageBytes = 128 * 128, kMmaPerStep = 4;
+};
+template <> struct ConvCfg<2> {      // conv2: 4 taps x 2 dy, 32 K-columns per step, 64-byte rows
+  static constexpr int kSteps = 8, kRowBytes = 64, kStageBytes = 128 * 64, kMmaPerStep = 2;
+};
+
+struct ConvArgs {
+  const float* bias;
+  int items;          // work items: conv1 4 per sample (5 output rows each), conv2 1 per sample
+  int rows;           // valid GEMM rows per item: 100 / 81
+  int box_bytes;      // bytes one A box delivers
+  int mode;           // 1: conv1 over x', 2: conv2 over h1
+};
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+
+template <int N, int MODE>   // N output channels: 16 (conv1, MODE 1) or 32 (conv2, MODE 2)
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_a2,
+                        const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CUtensorMap tma_c,
+                        const ConvArgs g) {
+  using Cfg = ConvCfg<MODE>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  constexpr int kWTileBytes = N * Cfg::kRowBytes;          // one resident filter slice [N rows x kRowBytes]
+  constexpr int kWBytes = (Cfg::kSteps * kWTileBytes + 1023) / 1024 * 1024;
+  const uint32_t w_smem = smem_base;
+  const uint32_t a_smem = smem_base + kWBytes;
+  const uint32_t bar_base = a_smem + kConvStages * Cfg::kStageBytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kConvStages + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kConvStages + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kConvStages + 2 + a); };
+  const uint32_t w_bar = bar_base + 8u * (2 * kConvStages + 4);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kConvStages + 5);
+  const uint32_t ebuf_base = bar_base + 1024u;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&tma_a);
+    prefetch_tensormap(&tma_a2);
+    prefetch_tensormap(&tma_w);
+    prefetch_tensormap(&tma_c);
+    for (int s = 0; s < kConvStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    mbar_init(w_bar, 1);
+    fence_mbar_init();
+  } else if (warp == 2) {
+    tmem_alloc<64>(tmem_slot);
+  }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer: resident filter slices once, then one box per (item, step) =====
+      mbar_arrive_expect_tx(w_bar, Cfg::kSteps * kWTileBytes);
+#pragma unroll
+      for (int t = 0; t < Cfg::kSteps; ++t)
+        tma_load_2d(w_smem + t * kWTileBytes, &tma_w, w_bar, t * (Cfg::kRowBytes / 2), 0);
+      int stage = 0; uint32_t phase = 0;
+      for (int it = blockIdx.x; it < g.items; it += gridDim.x) {
+#pragma unroll 1
+        for (int st = 0; st < Cfg::kSteps; ++st) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          mbar_arrive_expect_tx(full_bar(stage), g.box_bytes);
+          const uint32_t dst = a_smem + stage * Cfg::kStageBytes;
+          if (MODE == 1) {
+            const int by = st >> 1, bx = st & 1;
+            tma_load_4d(dst, &tma_a, full_bar(stage), 0, bx, (it & 3) * 5 + by, it >> 2);
+          } else {
+            const int tap = st >> 1, dy = st & 1, by = tap >> 1, bx = tap & 1;
+            tma_load_4d(dst, dy ? &tma_a2 : &tma_a, full_bar(stage), 0, bx, by, it);
+          }
+          if (++stage == kConvStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer: UMMA 128 x N x 16 over every step's K columns =====
+      constexpr uint32_t idesc = idesc_bf16_f32(128, N, false, false);
+      mbar_wait(w_bar, 0);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int it = blockIdx.x; it < g.items; it += gridDim.x) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        fence_after_sync();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * 32);
+#pragma unroll 1
+        for (int st = 0; st < Cfg::kSteps; ++st) {
+          mbar_wait(full_bar(stage), phase);
+          fence_after_sync();
+          const uint32_t sa = a_smem + stage * Cfg::kStageBytes, sb = w_smem + st * kWTileBytes;
+#pragma unroll
+          for (int k = 0; k < Cfg::kMmaPerStep; ++k) {
+            const uint64_t ad = MODE == 1 ? smem_desc_sw128(sa + k * 32, 16, 1024) : smem_desc_sw64(sa + k * 32, 16, 512);
+            const uint64_t bd = MODE == 1 ? smem_desc_sw128(sb + k * 32, 16, 1024) : smem_desc_sw64(sb + k * 32, 16, 512);
+            mma_f16(tmem_d, ad, bd, idesc, (st > 0 || k > 0) ? 1u : 0u);
+          }
+          mma_commit(empty_bar(stage));
+          if (++stage == kConvStages) { stage = 0; phase ^= 1u; }
+        }
+        mma_commit(tfull_bar(acc));
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else {
+    // ===== epilogue: bias + ReLU + bf16, staged per warp, TMA store clipped to the item's rows =====
+    const int quarter = warp & 3;
+    const uint32_t ebuf = ebuf_base + (uint32_t)(warp - 2) * 8192u;
+    uint32_t ebuf_it = 0;
+    int acc = 0; uint32_t acc_phase = 0;
+    float b[N];
+#pragma unroll
+    for (int j = 0; j < N; ++j) b[j] = g.bias ? __ldg(g.bias + j) : 0.f;
+    for (int it = blockIdx.x; it < g.items; it += gridDim.x) {
+      mbar_wait(tfull_bar(acc), acc_phase);
+      fence_after_sync();
+      if (quarter * 32 < g.rows) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 32), r);
+        tmem_ld_wait();
+        const uint32_t buf = ebuf + (ebuf_it & 1u) * 4096u;
+        ++ebuf_it;
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        __syncwarp();
+        const uint32_t rowp = buf + (uint32_t)lane * 128u;
+#pragma unroll
+        for (int q = 0; q < N / 8; ++q) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float v0 = fmaxf(__uint_as_float(r[8 * q + 2 * j]) + b[8 * q + 2 * j], 0.f);
+            const float v1 = fmaxf(__uint_as_float(r[8 * q + 2 * j + 1]) + b[8 * q + 2 * j + 1], 0.f);
+            __nv_bfloat162 p = __floats2bfloat162_rn(v0, v1);
+            pk[j] = *reinterpret_cast<uint32_t*>(&p);
+          }
+          const uint32_t chunk = (uint32_t)q ^ (uint32_t)(lane & 7);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowp + chunk * 16u), "r"(pk[0]), "r"(pk[1]),
+                       "r"(pk[2]), "r"(pk[3]) : "memory");
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_3d(&tma_c, buf, 0, quarter * 32, it);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+      }
+      fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+  __syncwarp();
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 2) {
+    fence_after_sync();
+    tmem_dealloc<64>(tmem_base);
+  }
+}
+
+// space-to-depth + bf16 conversion of frames: in [S,84,84,3] f32 / u8 (/255) -> x' [S,21,21,48],
+// channel = dy*12 + dx*3 + c.  One thread per x' pixel: four 48-byte (f32) row pieces in, 96 bytes out.
+template <typename T>
+__global__ void __launch_bounds__(256) s2d_frames_kernel(const T* __restrict__ in, __nv_bfloat16* __restrict__ out,
+                                                         int64_t total) {
+  for (int64_t id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; id < total; id += (int64_t)gridDim.x * blockDim.x) {
+    const int X = (int)(id % 21);
+    const int Y = (int)((id / 21) % 21);
+    const int64_t s = id / 441;
+    const T* src = in + ((s * 84 + 4 * Y) * 84 + 4 * X) * 3;
+    uint32_t pk[24];
+#pragma unroll
+    for (int dy = 0; dy < 4; ++dy) {
+      float v[12];
+      if (sizeof(T) == 4) {
+        const float4* p = reinterpret_cast<const float4*>(src + dy * 252);
+        const float4 a = __ldcs(p), b = __ldcs(p + 1), c = __ldcs(p + 2);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+        v[8] = c.x; v[9] = c.y; v[10] = c.z; v[11] = c.w;
+      } else {
+        const uint32_t* p = reinterpret_cast<const uint32_t*>(src + dy * 252);   // 12 bytes, 4-byte aligned
+#pragma unroll
+        for (int w = 0; w < 3; ++w) {
+          const uint32_t u = __ldcs(p + w);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) v[4 * w + j] = __fdiv_rn((float)((u >> (8 * j)) & 255u), 255.0f);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 6; ++j) {
+        __nv_bfloat162 p2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+        pk[dy * 6 + j] = *reinterpret_cast<uint32_t*>(&p2);
+      }
+    }
+    uint4* dst = reinterpret_cast<uint4*>(out + id * 48);
+#pragma unroll
+    for (int j = 0; j < 6; ++j) dst[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+  }
+}
+
+template <int N, int MODE>
+static int launch_conv(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtensorMap& tw, const CUtensorMap& tc,
+                       const ConvArgs& g, cudaStream_t st) {
+  using Cfg = ConvCfg<MODE>;
+  constexpr int kWBytes = (Cfg::kSteps * N * Cfg::kRowBytes + 1023) / 1024 * 1024;
+  constexpr int kSmem = kWBytes + kConvStages * Cfg::kStageBytes + 1024 + 4 * 2 * 4096 + 1024;
+  static bool configured = false;
+  auto kern = conv_fwd_tcgen05_kernel<N, MODE>;
+  if (!configured) {
+    UNREAL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+    configured = true;
+  }
+  const int sms = sm_count();
+  if (sms <= 0) return UNREAL_ECUDA;
+  const int grid = g.items < sms ? g.items : sms;
+  kern<<<grid, kConvThreads, kSmem, st>>>(ta, ta2, tw, tc, g);
+  UNREAL_LAUNCH_CHECK("conv_fwd_tcgen05_kernel");
+  return UNREAL_OK;
+}
+
+}  // namespace unreal
+
+using namespace unreal;
+
+extern "C" int unreal_s2d_frames(const void* frames, int dtype, void* out_bf16, int s, void* stream) {
+  UNREAL_REQUIRE(frames && out_bf16 && s > 0, "unreal_s2d_frames: null buffer or s <= 0");
+  UNREAL_REQUIRE(dtype == UNREAL_F32 || dtype == UNREAL_U8, "unreal_s2d_frames: frames must be f32 or u8");
+  UNREAL_REQUIRE(aligned16(frames) && aligned16(out_bf16), "unreal_s2d_frames: buffers must be 16-byte aligned");
+  const int64_t total = (int64_t)s * 441;
+  const int sms = sm_count();
+  if (sms <= 0) return UNREAL_ECUDA;
+  int64_t want = (total + 255) / 256;
+  const int grid = (int)(want < (int64_t)sms * 16 ? want : (int64_t)sms * 16);
+  if (dtype == UNREAL_F32)
+    s2d_frames_kernel<float><<<grid, 256, 0, as_stream(stream)>>>(reinterpret_cast<const float*>(frames),
+                                                                 reinterpret_cast<__nv_bfloat16*>(out_bf16), total);
+  else
+    s2d_frames_kernel<uint8_t><<<grid, 256, 0, as_stream(stream)>>>(reinterpret_cast<const uint8_t*>(frames),
+                                                                   reinterpret_cast<__nv_bfloat16*>(out_bf16), total);
+  UNREAL_LAUNCH_CHECK("s2d_frames_kernel");
+  return UNREAL_OK;
+}
+
+extern "C" int unreal_conv_fwd(const void* in_bf16, int layer, const void* w_taps_bf16, const float* bias,
+                               void* out_bf16, int s, void* stream) {
+  UNREAL_REQUIRE(in_bf16 && w_taps_bf16 && out_bf16 && s > 0, "unreal_conv_fwd: null buffer or s <= 0");
+  UNREAL_REQUIRE(layer == 1 || layer == 2, "unreal_conv_fwd: layer must be 1 (conv1 over x') or 2 (conv2 over h1)");
+  UNREAL_REQUIRE(aligned16(in_bf16) && aligned16(w_taps_bf16) && aligned16(out_bf16),
+                 "unreal_conv_fwd: buffers must be 16-byte aligned");
+  CUtensorMap ta, ta2, tw, tc;
+  ConvArgs g;
+  g.bias = bias;
+  g.mode = layer;
+  int rc;
+  const int n = layer == 1 ? 16 : 32;
+  if (layer == 1) {
+    // x' [S][21][21][48] bf16
+    const uint64_t dims[4] = {48, 21, 21, (uint64_t)s};
+    const uint64_t strides[3] = {96, 96 * 21, 96 * 441};
+    const uint32_t box[4] = {64, 20, 5, 1};
+    rc = make_tma_nd_bf16(&ta, in_bf16, 4, dims, strides, box, 128);
+    g.items = s * 4; g.rows = 100; g.box_bytes = 64 * 20 * 5 * 2;
+    ta2 = ta;
+  } else {
+    // h1 [S][20][20][16]: rows y = 2Y + dy as {32 (dx,c), 10 X, 10 Y, S}, one map per dy
+    const uint64_t dims[4] = {32, 10, 10, (uint64_t)s};
+    const uint64_t strides[3] = {64, 1280, 12800};
+    const uint32_t box[4] = {32, 9, 9, 1};
+    rc = make_tma_nd_bf16(&ta, in_bf16, 4, dims, strides, box, 64);
+    if (rc != UNREAL_OK) return rc;
+    rc = make_tma_nd_bf16(&ta2, reinterpret_cast<const uint8_t*>(in_bf16) + 640, 4, dims, strides, box, 64);
+    g.items = s; g.rows = 81; g.box_bytes = 32 * 9 * 9 * 2;
+  }
+  if (rc != UNREAL_OK) return rc;
+  {
+    const uint64_t dims[2] = {256, (uint64_t)n};
+    const uint64_t strides[1] = {512};
+    const uint32_t box[2] = {layer == 1 ? 64u : 32u, (uint32_t)n};
+    rc = make_tma_nd_bf16(&tw, w_taps_bf16, 2, dims, strides, box, layer == 1 ? 128 : 64);
+    if (rc != UNREAL_OK) return rc;
+  }
+  {
+    // out [items][rows][n] bf16: the row bound clips the tile's unused rows
+    const uint64_t dims[3] = {(uint64_t)n, (uint64_t)g.rows, (uint64_t)g.items};
+    const uint64_t strides[2] = {(uint64_t)n * 2, (uint64_t)n * 2 * g.rows};
+    const uint32_t box[3] = {64, 32, 1};
+    rc = make_tma_nd_bf16(&tc, out_bf16, 3, dims, strides, box, 128);
+    if (rc != UNREAL_OK) return rc;
+  }
+  return layer == 1 ? launch_conv<16, 1>(ta, ta2, tw, tc, g, as_stream(stream))
+                    : launch_conv<32, 2>(ta, ta2, tw, tc, g, as_stream(stream));
+}

@@ -519,6 +519,28 @@ int make_tma_2d(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, 
   return UNREAL_OK;
 }
 
+
+// rank-N bf16 tensor map with the 128-byte swizzle (conv_tcgen05.cu: 4-D / 5-D im2col boxes)
+int make_tma_nd_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                     const uint32_t* box, int swizzle_bytes) {
+  EncodeTiledFn fn = encode_tiled();
+  if (fn == nullptr) {
+    set_error("cuTensorMapEncodeTiled is not available from the CUDA driver");
+    return UNREAL_ECUDA;
+  }
+  cuuint64_t d[5]; cuuint64_t st[4]; cuuint32_t b[5]; cuuint32_t e[5];
+  for (int i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; e[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) st[i] = strides_bytes[i];
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), d, st, b, e,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d) for a rank-%d bf16 tensor", (int)r, rank);
+    return UNREAL_ECUDA;
+  }
+  return UNREAL_OK;
+}
+
 template <int BN, bool A_MN, bool B_MN>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmArgs& g,
                        cudaStream_t st) {

@@ -121,6 +121,16 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr, uint32_t lbo
   d |= 2ull << 61;  // SWIZZLE_128B
   return d;
 }
+// 64-byte swizzle (rows of 64 bytes, 8-row atoms of 512 bytes)
+__device__ __forceinline__ uint64_t smem_desc_sw64(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFFu);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= 1ull << 46;
+  d |= 4ull << 61;  // SWIZZLE_64B
+  return d;
+}
 // .kind::f16 instruction descriptor: bf16 x bf16 -> f32, dense
 __host__ __device__ constexpr uint32_t idesc_bf16_f32(int m, int n, bool a_mn_major, bool b_mn_major) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn_major ? 1u : 0u) << 15) | ((b_mn_major ? 1u : 0u) << 16) |

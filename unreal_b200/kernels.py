@@ -356,3 +356,39 @@ def lstm_cell_bwd(gates_act, c_prev, c, dh, dc, dgates16):
   call("unreal_lstm_cell_bwd", ptr(gates_act, torch.float32), ptr(c_prev, torch.float32), ptr(c, torch.float32),
        ptr(dh, torch.float32, "dh"), ptr(dc, torch.float32, "dc"), ptr(dgates16, torch.bfloat16, "dgates"), n,
        stream_ptr())
+
+
+# ---------------------------------------------------------------------------- K7: fused convolutions
+def s2d_frames(frames, out=None):
+  """frames [S,84,84,3] f32 / u8 -> space-to-depth bf16 [S,21,21,48] (channel dy*12 + dx*3 + c)."""
+  s = frames.shape[0]
+  if tuple(frames.shape[1:]) != (84, 84, 3):
+    raise _lib.UnrealError("s2d_frames expects [S,84,84,3] frames")
+  if out is None:
+    out = torch.empty(s, 21, 21, 48, dtype=torch.bfloat16, device=frames.device)
+  call("unreal_s2d_frames", ptr(frames, None, "frames"), _lib.dtype_tag(frames), ptr(out, torch.bfloat16, "out"), s,
+       stream_ptr())
+  return out
+
+
+def conv_taps(w16, stride):
+  """HWIO filter [2s,2s,C,O] (bf16) -> tap-major K-major matrix [O, 4*64]: tap t = by*2+bx holds
+  W[s*by+dy, s*bx+dx, c, o] in (dy,dx,c) order, zero padded to 64 columns."""
+  k, _, c, o = w16.shape
+  s = stride
+  t = w16.reshape(2, s, 2, s, c, o).permute(5, 0, 2, 1, 3, 4).reshape(o, 4, s * s * c)   # [o, (by,bx), (dy,dx,c)]
+  out = torch.zeros(o, 4, 64, dtype=w16.dtype, device=w16.device)
+  out[:, :, :s * s * c] = t
+  return out.reshape(o, 256).contiguous()
+
+
+def conv_fwd(x, layer, w_taps, bias, out=None):
+  """layer 1: x = s2d frames [S,21,21,48] -> [S,20,20,16]; layer 2: x = h1 [S,20,20,16] -> [S,9,9,32]
+  (bias + ReLU fused, bf16 out)."""
+  s = x.shape[0]
+  shape = (s, 20, 20, 16) if layer == 1 else (s, 9, 9, 32)
+  if out is None:
+    out = torch.empty(*shape, dtype=torch.bfloat16, device=x.device)
+  call("unreal_conv_fwd", ptr(x, torch.bfloat16, "x"), int(layer), ptr(w_taps, torch.bfloat16, "w_taps"),
+       ptr(bias, torch.float32, "bias"), ptr(out, torch.bfloat16, "out"), s, stream_ptr())
+  return out
