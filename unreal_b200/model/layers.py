@@ -59,16 +59,25 @@ class LinearFn(torch.autograd.Function):
 
 
 class ConvFn(torch.autograd.Function):
-  """relu(conv2d(x, W, stride, VALID) + b) on NHWC input (model.py:283-289, :786-787) as
-  im2col + GEMM.  The patch matrix is recomputed in backward instead of being kept."""
+  """relu(conv2d(x, W, stride, VALID) + b) on NHWC input (model.py:283-289, :786-787).
+
+  Forward: the two encoder geometries (8x8x3 stride 4 on frames, 4x4x16 stride 2 on conv1's output)
+  run as implicit GEMMs whose im2col is done by the TMA engine (csrc/conv_tcgen05.cu; `taps` is the
+  tap-major filter shadow); any other geometry goes through im2col + GEMM.
+  Backward: wgrad is a split-K GEMM over the (recomputed) patch matrix, dgrad a GEMM + col2im."""
 
   @staticmethod
-  def forward(ctx, x, w16, w32, b32, kh, kw, stride):
+  def forward(ctx, x, w16, w32, b32, kh, kw, stride, taps):
     s, h, w, c = x.shape
     oh, ow = (h - kh) // stride + 1, (w - kw) // stride + 1
-    cols = K.im2col(x, kh, kw, stride)
     o = w16.shape[1]
-    y = K.gemm_bf16(cols, w16, b_mn_major=True, bias=b32, relu=True, out_dtype=torch.bfloat16)
+    if taps is not None and (h, w, c, kh, kw, stride, o) == (84, 84, 3, 8, 8, 4, 16) and x.dtype in (torch.float32, torch.uint8):
+      y = K.conv_fwd(K.s2d_frames(x), 1, taps, b32).view(s * oh * ow, o)
+    elif taps is not None and (h, w, c, kh, kw, stride, o) == (20, 20, 16, 4, 4, 2, 32) and x.dtype == torch.bfloat16:
+      y = K.conv_fwd(x, 2, taps, b32).view(s * oh * ow, o)
+    else:
+      cols = K.im2col(x, kh, kw, stride)
+      y = K.gemm_bf16(cols, w16, b_mn_major=True, bias=b32, relu=True, out_dtype=torch.bfloat16)
     ctx.geom = (s, h, w, c, kh, kw, stride, oh, ow, o)
     ctx.save_for_backward(x, w16, y)
     return y.view(s, oh, ow, o)
@@ -85,7 +94,7 @@ class ConvFn(torch.autograd.Function):
     if ctx.needs_input_grad[0]:
       dcols = K.gemm_bf16(dy16, w16, out_dtype=torch.bfloat16)          # [S*OH*OW, KH*KW*C]
       dx = K.col2im(dcols, s, h, w, c, kh, kw, stride, out_dtype=torch.bfloat16)
-    return dx, None, dw, db, None, None, None
+    return dx, None, dw, db, None, None, None, None
 
 
 class DeconvFn(torch.autograd.Function):

@@ -77,6 +77,7 @@ class UnrealModel(object):
     self.num_envs = int(num_envs)
     self.lstm_in = 256 + A + 1 + G
     self.kx = (self.lstm_in + 7) // 8 * 8
+    self.fused_conv = True    # False: convolutions as explicit im2col + GEMM (A/B switch for benchmarks)
     self._build_variables(seed)
     self.reset_state()
 
@@ -116,6 +117,9 @@ class UnrealModel(object):
     with torch.no_grad():
       self.flat16.copy_(self.flat)
     self.v16 = self._views(self.flat16)
+    # tap-major filter shadows of the two encoder convolutions (TMA-im2col kernels)
+    self.taps1 = K.conv_taps(self.v16["W_base_conv1"], 4) if self.fused_conv else None
+    self.taps2 = K.conv_taps(self.v16["W_base_conv2"], 2) if self.fused_conv else None
 
   def get_vars(self):
     """The variables in creation order (views of the flat buffer), like model.py:729-730."""
@@ -148,8 +152,10 @@ class UnrealModel(object):
 
   def _encoder(self, p32, images):
     """model.py:281-289.  images [S,84,84,3] f32 / u8 -> h2 bf16 [S,9,9,32]."""
-    h1 = ConvFn.apply(images, self.v16["W_base_conv1"].view(192, 16), p32["W_base_conv1"], p32["b_base_conv1"], 8, 8, 4)
-    h2 = ConvFn.apply(h1, self.v16["W_base_conv2"].view(256, 32), p32["W_base_conv2"], p32["b_base_conv2"], 4, 4, 2)
+    h1 = ConvFn.apply(images, self.v16["W_base_conv1"].view(192, 16), p32["W_base_conv1"], p32["b_base_conv1"], 8, 8, 4,
+                      self.taps1)
+    h2 = ConvFn.apply(h1, self.v16["W_base_conv2"].view(256, 32), p32["W_base_conv2"], p32["b_base_conv2"], 4, 4, 2,
+                      self.taps2)
     return h2
 
   def _lstm_input(self, p32, h2, lar, t, n):
