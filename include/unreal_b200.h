@@ -210,15 +210,21 @@ int unreal_lstm_cell_bwd(const float* gates_act, const float* c_prev, const floa
 
 /* Fused convolutions of the encoder (model.py:281-289) as implicit GEMMs whose im2col is done by
  * the TMA engine (multi-dimensional boxes over a space-to-depth view; no patch matrix in memory).
- *   unreal_s2d_frames: frames [S,84,84,3] f32 / u8 (/255) -> x' bf16 [S,21,21,48],
- *                      x'[Y,X,dy*12+dx*3+c] = frame[4Y+dy, 4X+dx, c].
- *   unreal_conv_fwd  : layer 1: in = x' -> out bf16 [S,20,20,16] = relu(conv 8x8 s4 + bias)
- *                      layer 2: in = h1 bf16 [S,20,20,16] -> out bf16 [S,9,9,32] = relu(conv 4x4 s2 + bias)
- *                      w_taps bf16 [N,256]: for tap t = by*2+bx, columns 64t.. hold the filter slice
- *                      W[s*by+dy, s*bx+dx, c, o] in (dy,dx,c) order (48 used columns for layer 1). */
+ *   unreal_s2d_frames: frames [S,84,84,3] f32 / u8 (/255) -> x'' bf16 [S,6,441,8] (plane-major):
+ *                      x''[s, q, Y*21+X, e] = frame[4Y+dy, 4X+dx, c], dy*12 + dx*3 + c = q*8 + e.
+ *   unreal_conv_fwd  : layer 1: in = x'' -> out bf16 [S,20,20,16] = relu(conv 8x8 s4 + bias);
+ *                        w bf16 [4 taps][6 chunks][16 out][8]: tap t = by*2+bx, W[4by+dy, 4bx+dx, c, o].
+ *                      layer 2: in = h1 bf16 [S,20,20,16] -> out bf16 [S,9,9,32] = relu(conv 4x4 s2 + bias);
+ *                        w bf16 [32,256]: columns 64t.. of tap t hold W[2by+dy, 2bx+dx, c, o] in (dy,dx,c) order. */
 int unreal_s2d_frames(const void* frames, int dtype, void* out_bf16, int s, void* stream);
 int unreal_conv_fwd(const void* in_bf16, int layer, const void* w_taps_bf16, const float* bias, void* out_bf16, int s,
                     void* stream);
+
+/* ReLU backward fused with the bias gradient (tf.nn.relu / bias_add gradients of the dense layers):
+ * out_bf16 = dy * (y > 0) and db[c] += sum_rows out[:, c]; y_bf16 NULL: no mask; out / db nullable.
+ * dy [rows, cols] bf16 or f32 (contiguous), cols a multiple of 8; the caller zeroes db. */
+int unreal_relu_grad(const void* dy, int dy_dtype, const void* y_bf16, void* out_bf16, float* db, int64_t rows,
+                     int cols, void* stream);
 
 #ifdef __cplusplus
 }

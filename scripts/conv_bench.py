@@ -28,10 +28,10 @@ S = int(sys.argv[1]) if len(sys.argv) > 1 else 40960
 out = open(sys.argv[2], "w") if len(sys.argv) > 2 else sys.stdout
 w1 = (torch.randn(8, 8, 3, 16, device=dev) * 0.05).to(torch.bfloat16); b1 = torch.zeros(16, device=dev)
 w2 = (torch.randn(4, 4, 16, 32, device=dev) * 0.05).to(torch.bfloat16); b2 = torch.zeros(32, device=dev)
-t1, t2 = K.conv_taps(w1, 4), K.conv_taps(w2, 2)
+t1, t2 = K.conv1_w_planes(w1), K.conv_taps(w2, 2)
 for dt in (torch.float32, torch.uint8):
   x = torch.rand(S, 84, 84, 3, device=dev) if dt == torch.float32 else torch.randint(0, 256, (S, 84, 84, 3), device=dev, dtype=torch.uint8)
-  xs = torch.empty(S, 21, 21, 48, dtype=torch.bfloat16, device=dev)
+  xs = torch.empty(S, 6, 441, 8, dtype=torch.bfloat16, device=dev)
   h1 = torch.empty(S, 20, 20, 16, dtype=torch.bfloat16, device=dev)
   h2 = torch.empty(S, 9, 9, 32, dtype=torch.bfloat16, device=dev)
   esz = x.element_size()

@@ -202,9 +202,9 @@ def test_fused_conv_forward_matches_direct_convolution(dtype):
     w2 = ((torch.rand(4, 4, 16, 32, device=dev, generator=g) - 0.5) * 0.2).to(torch.bfloat16)
     b2 = (torch.rand(32, device=dev, generator=g) - 0.5) * 0.1
     xs = K.s2d_frames(x)
-    want_s2d = xf.view(s, 21, 4, 21, 4, 3).permute(0, 1, 3, 2, 4, 5).reshape(s, 21, 21, 48)
+    want_s2d = xf.view(s, 21, 4, 21, 4, 3).permute(0, 1, 3, 2, 4, 5).reshape(s, 441, 6, 8).permute(0, 2, 1, 3)
     assert torch.equal(xs.float(), want_s2d)
-    h1 = K.conv_fwd(xs, 1, K.conv_taps(w1, 4), b1)
+    h1 = K.conv_fwd(xs, 1, K.conv1_w_planes(w1), b1)
     ref1 = F.relu(F.conv2d(xf.permute(0, 3, 1, 2), w1.float().permute(3, 2, 0, 1), b1, stride=4)).permute(0, 2, 3, 1)
     assert tuple(h1.shape) == (s, 20, 20, 16)
     assert torch.allclose(h1.float(), ref1, rtol=2.0 ** -7, atol=1e-3)

@@ -216,8 +216,9 @@ conv_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_
   }
 }
 
-// space-to-depth + bf16 conversion of frames: in [S,84,84,3] f32 / u8 (/255) -> x' [S,21,21,48],
-// channel = dy*12 + dx*3 + c.  One thread per x' pixel: four 48-byte (f32) row pieces in, 96 bytes out.
+// space-to-depth + bf16 conversion of frames: in [S,84,84,3] f32 / u8 (/255) -> x'' [S,6,441,8]
+// (pixel (Y,X) = Y*21+X, channel dy*12 + dx*3 + c split into six 8-channel planes).  One thread per
+// x' pixel: four 48-byte (f32) row pieces in, six coalesced 16-byte plane rows out.
 template <typename T>
 __global__ void __launch_bounds__(256) s2d_frames_kernel(const T* __restrict__ in, __nv_bfloat16* __restrict__ out,
                                                          int64_t total) {
@@ -250,9 +251,149 @@ __global__ void __launch_bounds__(256) s2d_frames_kernel(const T* __restrict__ i
         pk[dy * 6 + j] = *reinterpret_cast<uint32_t*>(&p2);
       }
     }
-    uint4* dst = reinterpret_cast<uint4*>(out + id * 48);
+    // plane-major: x'' [S][6 chunks of 8 channels][441 pixels][8]; consecutive threads (pixels) write
+    // consecutive 16-byte rows of each plane
+    const int pix = Y * 21 + X;
+    uint4* dst = reinterpret_cast<uint4*>(out) + (s * 6) * 441 + pix;
 #pragma unroll
-    for (int j = 0; j < 6; ++j) dst[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+    for (int j = 0; j < 6; ++j) dst[(int64_t)j * 441] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+  }
+}
+
+// ---- conv1, single-copy variant ----------------------------------------------------------------
+// x'' is stored plane-major (8-channel chunks as separate [441 x 16 B] planes), which is exactly the
+// un-swizzled K-major UMMA layout with a UNIFORM 16-byte row pitch.  One 3-D TMA box {8 ch, 126
+// pixels (6 x' rows), 6 planes} per work item (5 output rows) lands once in shared memory and all four
+// taps read it in place: tap (by,bx) is the same tile with the descriptor start address advanced by
+// (by*21 + bx) rows.  GEMM rows follow the 21-wide x' grid (row m' = oy*21 + ox); the column ox = 20
+// and rows >= 105 are garbage accumulator rows the epilogue skips.  HBM/L2 traffic per frame:
+// 42 KB of x'' in (each byte once) + 12.8 KB of h1 out.
+constexpr int kC1Stages = 12;
+constexpr int kC1PlaneBytes = 126 * 16;
+constexpr int kC1BoxBytes = 6 * kC1PlaneBytes;      // 12096
+constexpr int kC1StageBytes = 12288;
+constexpr int kC1WBytes = 4 * 6 * 16 * 16;          // [tap][chunk][16 out rows][8 ch] bf16
+constexpr int kC1Smem = kC1WBytes + kC1Stages * kC1StageBytes + 1024 /*barriers*/ + 1024 /*tail reads*/ + 1024 /*align*/;
+
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv1_fwd_tcgen05_kernel(const __nv_bfloat16* __restrict__ xpp, const __nv_bfloat16* __restrict__ w_planes,
+                         const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int items) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t w_smem = smem_base;
+  const uint32_t a_smem = smem_base + kC1WBytes;
+  const uint32_t bar_base = a_smem + kC1Stages * kC1StageBytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kC1Stages + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kC1Stages + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kC1Stages + 2 + a); };
+  const uint32_t w_bar = bar_base + 8u * (2 * kC1Stages + 4);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kC1Stages + 5);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < kC1Stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    mbar_init(w_bar, 1);
+    fence_mbar_init();
+  } else if (warp == 2) {
+    tmem_alloc<64>(tmem_slot);
+  }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== producer: resident filters (one bulk copy), then ONE box per item =====
+      mbar_arrive_expect_tx(w_bar, kC1WBytes);
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(w_smem), "l"(w_planes), "r"(kC1WBytes), "r"(w_bar) : "memory");
+      int stage = 0; uint32_t phase = 0;
+      for (int it = blockIdx.x; it < items; it += gridDim.x) {
+        mbar_wait(empty_bar(stage), phase ^ 1u);
+        mbar_arrive_expect_tx(full_bar(stage), kC1BoxBytes);
+        // each plane's 126 pixel rows are 2016 contiguous bytes in x'': six 1-D bulk copies (a tensor
+        // box with a 16-byte inner dimension costs the TMA engine one request per row: measured 2.3x slower)
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(xpp) + ((int64_t)(it >> 2) * 6 * 441 + (it & 3) * 105) * 16;
+        const uint32_t dst = a_smem + stage * kC1StageBytes;
+#pragma unroll
+        for (int q = 0; q < 6; ++q)
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                       ::"r"(dst + q * kC1PlaneBytes), "l"(src + (int64_t)q * 441 * 16), "r"(kC1PlaneBytes),
+                         "r"(full_bar(stage)) : "memory");
+        if (++stage == kC1Stages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer: 4 taps x 3 UMMA (128 x 16 x 16) on the one resident tile =====
+      constexpr uint32_t idesc = idesc_bf16_f32(128, 16, false, false);
+      mbar_wait(w_bar, 0);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int it = blockIdx.x; it < items; it += gridDim.x) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        mbar_wait(full_bar(stage), phase);
+        fence_after_sync();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * 32);
+        const uint32_t sa = a_smem + stage * kC1StageBytes;
+#pragma unroll
+        for (int tap = 0; tap < 4; ++tap) {
+          const uint32_t shift = (uint32_t)((tap >> 1) * 21 + (tap & 1)) * 16u;
+#pragma unroll
+          for (int j = 0; j < 3; ++j)
+            mma_f16(tmem_d, smem_desc_none(sa + 2 * j * kC1PlaneBytes + shift, kC1PlaneBytes, 128),
+                    smem_desc_none(w_smem + tap * 1536 + 2 * j * 256, 256, 128), idesc, (tap > 0 || j > 0) ? 1u : 0u);
+        }
+        mma_commit(empty_bar(stage));
+        mma_commit(tfull_bar(acc));
+        if (++stage == kC1Stages) { stage = 0; phase ^= 1u; }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else {
+    // ===== epilogue: bias + ReLU + bf16; row m' = oy*21 + ox -> h1[(item*5 + oy), ox, 0..15] =====
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const int oyl = r / 21, ox = r - oyl * 21;
+    const bool valid = r < 105 && ox < 20;
+    int acc = 0; uint32_t acc_phase = 0;
+    float b[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) b[j] = bias ? __ldg(bias + j) : 0.f;
+    for (int it = blockIdx.x; it < items; it += gridDim.x) {
+      mbar_wait(tfull_bar(acc), acc_phase);
+      fence_after_sync();
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 32), v);
+      tmem_ld_wait();
+      fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (valid) {
+        uint32_t pk[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          __nv_bfloat162 p = __floats2bfloat162_rn(fmaxf(__uint_as_float(v[2 * j]) + b[2 * j], 0.f),
+                                                   fmaxf(__uint_as_float(v[2 * j + 1]) + b[2 * j + 1], 0.f));
+          pk[j] = *reinterpret_cast<uint32_t*>(&p);
+        }
+        uint4* dst = reinterpret_cast<uint4*>(out + ((int64_t)it * 100 + oyl * 20 + ox) * 16);
+        dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+  __syncwarp();
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 2) {
+    fence_after_sync();
+    tmem_dealloc<64>(tmem_base);
   }
 }
 
@@ -312,12 +453,19 @@ extern "C" int unreal_conv_fwd(const void* in_bf16, int layer, const void* w_tap
   int rc;
   const int n = layer == 1 ? 16 : 32;
   if (layer == 1) {
-    // x' [S][21][21][48] bf16
-    const uint64_t dims[4] = {48, 21, 21, (uint64_t)s};
-    const uint64_t strides[3] = {96, 96 * 21, 96 * 441};
-    const uint32_t box[4] = {64, 20, 5, 1};
-    rc = make_tma_nd_bf16(&ta, in_bf16, 4, dims, strides, box, 128);
-    g.items = s * 4; g.rows = 100; g.box_bytes = 64 * 20 * 5 * 2;
+    // x'' [S*6 planes][441 pixels][8 ch] bf16: the kernel bulk-copies 126-pixel plane slices
+    static bool configured = false;
+    if (!configured) {
+      UNREAL_CUDA(cudaFuncSetAttribute(conv1_fwd_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kC1Smem));
+      configured = true;
+    }
+    const int sms = sm_count();
+    if (sms <= 0) return UNREAL_ECUDA;
+    const int items = s * 4;
+    conv1_fwd_tcgen05_kernel<<<items < sms ? items : sms, kConvThreads, kC1Smem, as_stream(stream)>>>(
+        reinterpret_cast<const __nv_bfloat16*>(in_bf16), reinterpret_cast<const __nv_bfloat16*>(w_taps_bf16), bias, reinterpret_cast<__nv_bfloat16*>(out_bf16), items);
+    UNREAL_LAUNCH_CHECK("conv1_fwd_tcgen05_kernel");
+    return UNREAL_OK;
     ta2 = ta;
   } else {
     // h1 [S][20][20][16]: rows y = 2Y + dy as {32 (dx,c), 10 X, 10 Y, S}, one map per dy

@@ -197,6 +197,72 @@ __global__ void __launch_bounds__(256) lstm_cell_bwd_kernel(const float* __restr
   dc[id] = dcv * f;
 }
 
+
+// ---- ReLU backward + bias gradient, fused ---------------------------------------------------------
+// out = dy * (y > 0) as bf16 (the operand of the dgrad / wgrad GEMMs) and db[c] += sum over rows of
+// out[:, c] in one pass; y == nullptr: no mask (plain bf16 copy / column sum).  Replaces the
+// compare / multiply / cast / float / sum chain of element-wise launches.
+// One thread per 8-column group of a row, threads laid over (row, group) in memory order; the grid
+// size is a multiple of the groups per row, so a thread keeps its column group while striding rows
+// and sums it in registers; block partials go through shared-memory atomics, one global atomic per
+// column per block.
+template <typename TD>
+__global__ void __launch_bounds__(256) relu_grad_kernel(const TD* __restrict__ dy, const __nv_bfloat16* __restrict__ y,
+                                                        __nv_bfloat16* __restrict__ out, float* __restrict__ db,
+                                                        int64_t rows, int cols) {
+  extern __shared__ float s_db[];
+  const int groups = cols >> 3;
+  if (db != nullptr) {
+    for (int c = threadIdx.x; c < cols; c += blockDim.x) s_db[c] = 0.f;
+    __syncthreads();
+  }
+  const int64_t total = rows * groups;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;          // multiple of `groups`
+  const int64_t id0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int c0 = (int)(id0 % groups) * 8;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  for (int64_t id = id0; id < total; id += stride) {
+    const int64_t off = id * 8;
+    float v[8];
+    if (sizeof(TD) == 2) {
+      const uint4 u = __ldcs(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(dy) + off));
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { const float2 f = __bfloat1622float2(h[j]); v[2 * j] = f.x; v[2 * j + 1] = f.y; }
+    } else {
+      const float4 a = __ldcs(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(dy) + off));
+      const float4 b = __ldcs(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(dy) + off + 4));
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    }
+    if (y != nullptr) {
+      const uint4 u = *reinterpret_cast<const uint4*>(y + off);
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __bfloat1622float2(h[j]);
+        if (!(f.x > 0.f)) v[2 * j] = 0.f;
+        if (!(f.y > 0.f)) v[2 * j + 1] = 0.f;
+      }
+    }
+    uint32_t pk[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      __nv_bfloat162 p = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+      pk[j] = *reinterpret_cast<uint32_t*>(&p);
+      const float2 f = __bfloat1622float2(p);          // the bias gradient sums the ROUNDED values,
+      acc[2 * j] += f.x; acc[2 * j + 1] += f.y;        // like dy16.float().sum(0)
+    }
+    if (out != nullptr) *reinterpret_cast<uint4*>(out + off) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  }
+  if (db == nullptr) return;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) atomicAdd(&s_db[c0 + j], acc[j]);
+  __syncthreads();
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) atomicAdd(db + c, s_db[c]);
+}
+
 static int grid_for_elems(int64_t total, int per_block = 256) {
   int sms = sm_count();
   if (sms <= 0) return 0;
@@ -302,5 +368,38 @@ extern "C" int unreal_lstm_cell_bwd(const float* gates_act, const float* c_prev,
   lstm_cell_bwd_kernel<<<(n * 256 + 255) / 256, 256, 0, as_stream(stream)>>>(
       gates_act, c_prev, c, dh, dc, reinterpret_cast<__nv_bfloat16*>(dgates_bf16), n);
   UNREAL_LAUNCH_CHECK("lstm_cell_bwd_kernel");
+  return UNREAL_OK;
+}
+
+extern "C" int unreal_relu_grad(const void* dy, int dy_dtype, const void* y_bf16, void* out_bf16, float* db,
+                                int64_t rows, int cols, void* stream) {
+  UNREAL_REQUIRE(dy != nullptr && rows > 0 && cols > 0, "unreal_relu_grad: null dy or empty shape");
+  UNREAL_REQUIRE(dy_dtype == UNREAL_BF16 || dy_dtype == UNREAL_F32, "unreal_relu_grad: dy must be bf16 or f32");
+  UNREAL_REQUIRE((cols & 7) == 0, "unreal_relu_grad: cols must be a multiple of 8");
+  UNREAL_REQUIRE(aligned16(dy) && aligned16(y_bf16) && aligned16(out_bf16), "unreal_relu_grad: 16-byte alignment");
+  const int sms = sm_count();
+  if (sms <= 0) return UNREAL_ECUDA;
+  const int groups = cols / 8;
+  UNREAL_REQUIRE(cols <= 8192, "unreal_relu_grad: cols must be <= 8192");
+  // grid * 256 must be a multiple of `groups`: grid = k * groups / gcd(groups, 256)
+  int g = groups, h = 256;
+  while (h) { int t = g % h; g = h; h = t; }
+  const int unit = groups / g;
+  const int64_t total = rows * groups;
+  int64_t want = (total + 255) / 256;
+  const int64_t cap = (int64_t)sms * 8;
+  if (want > cap) want = cap;
+  int64_t gx = (want + unit - 1) / unit * unit;
+  if (gx < unit) gx = unit;
+  const size_t shm = (size_t)cols * sizeof(float);
+  if (dy_dtype == UNREAL_BF16)
+    relu_grad_kernel<__nv_bfloat16><<<(unsigned)gx, 256, shm, as_stream(stream)>>>(
+        reinterpret_cast<const __nv_bfloat16*>(dy), reinterpret_cast<const __nv_bfloat16*>(y_bf16),
+        reinterpret_cast<__nv_bfloat16*>(out_bf16), db, rows, cols);
+  else
+    relu_grad_kernel<float><<<(unsigned)gx, 256, shm, as_stream(stream)>>>(
+        reinterpret_cast<const float*>(dy), reinterpret_cast<const __nv_bfloat16*>(y_bf16),
+        reinterpret_cast<__nv_bfloat16*>(out_bf16), db, rows, cols);
+  UNREAL_LAUNCH_CHECK("relu_grad_kernel");
   return UNREAL_OK;
 }

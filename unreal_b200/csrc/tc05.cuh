@@ -121,6 +121,16 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr, uint32_t lbo
   d |= 2ull << 61;  // SWIZZLE_128B
   return d;
 }
+// no swizzle ("interleaved" core matrices of 8 rows x 16 bytes): lbo = byte distance between the two
+// 16-byte K chunks of one UMMA, sbo = byte distance between consecutive 8-row groups
+__device__ __forceinline__ uint64_t smem_desc_none(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFFu);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= 1ull << 46;
+  return d;
+}
 // 64-byte swizzle (rows of 64 bytes, 8-row atoms of 512 bytes)
 __device__ __forceinline__ uint64_t smem_desc_sw64(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   uint64_t d = 0;

@@ -360,15 +360,23 @@ def lstm_cell_bwd(gates_act, c_prev, c, dh, dc, dgates16):
 
 # ---------------------------------------------------------------------------- K7: fused convolutions
 def s2d_frames(frames, out=None):
-  """frames [S,84,84,3] f32 / u8 -> space-to-depth bf16 [S,21,21,48] (channel dy*12 + dx*3 + c)."""
+  """frames [S,84,84,3] f32 / u8 -> space-to-depth bf16, plane-major [S,6,441,8]:
+  x''[s, q, Y*21+X, e] = frame[s, 4Y+dy, 4X+dx, c] with dy*12 + dx*3 + c = q*8 + e."""
   s = frames.shape[0]
   if tuple(frames.shape[1:]) != (84, 84, 3):
     raise _lib.UnrealError("s2d_frames expects [S,84,84,3] frames")
   if out is None:
-    out = torch.empty(s, 21, 21, 48, dtype=torch.bfloat16, device=frames.device)
+    out = torch.empty(s, 6, 441, 8, dtype=torch.bfloat16, device=frames.device)
   call("unreal_s2d_frames", ptr(frames, None, "frames"), _lib.dtype_tag(frames), ptr(out, torch.bfloat16, "out"), s,
        stream_ptr())
   return out
+
+
+def conv1_w_planes(w16):
+  """conv1 filter [8,8,3,16] (bf16) -> [4 taps, 6 channel chunks, 16 outputs, 8] : the un-swizzled
+  K-major UMMA B operand of each tap, resident in shared memory for the whole conv1 kernel."""
+  taps = conv_taps(w16, 4).view(16, 4, 64)[:, :, :48]
+  return taps.reshape(16, 4, 6, 8).permute(1, 2, 0, 3).contiguous()
 
 
 def conv_taps(w16, stride):
@@ -383,8 +391,8 @@ def conv_taps(w16, stride):
 
 
 def conv_fwd(x, layer, w_taps, bias, out=None):
-  """layer 1: x = s2d frames [S,21,21,48] -> [S,20,20,16]; layer 2: x = h1 [S,20,20,16] -> [S,9,9,32]
-  (bias + ReLU fused, bf16 out)."""
+  """layer 1: x = s2d frames [S,6,441,8], w_taps = conv1_w_planes(W) -> [S,20,20,16];
+  layer 2: x = h1 [S,20,20,16], w_taps = conv_taps(W, 2) -> [S,9,9,32]  (bias + ReLU fused, bf16 out)."""
   s = x.shape[0]
   shape = (s, 20, 20, 16) if layer == 1 else (s, 9, 9, 32)
   if out is None:
@@ -392,3 +400,15 @@ def conv_fwd(x, layer, w_taps, bias, out=None):
   call("unreal_conv_fwd", ptr(x, torch.bfloat16, "x"), int(layer), ptr(w_taps, torch.bfloat16, "w_taps"),
        ptr(bias, torch.float32, "bias"), ptr(out, torch.bfloat16, "out"), s, stream_ptr())
   return out
+
+
+def relu_grad(dy, y=None, want_out=True, want_db=True):
+  """dy [rows, cols] bf16 / f32, y bf16 or None -> (dy * (y > 0) as bf16, column sums f32)."""
+  rows, cols = dy.shape
+  if not dy.is_contiguous():
+    dy = dy.contiguous()
+  out = torch.empty(rows, cols, dtype=torch.bfloat16, device=dy.device) if want_out else None
+  db = torch.zeros(cols, dtype=torch.float32, device=dy.device) if want_db else None
+  call("unreal_relu_grad", ptr(dy, None, "dy"), _lib.dtype_tag(dy), ptr(y, torch.bfloat16, "y"),
+       ptr(out, torch.bfloat16, "out"), ptr(db, torch.float32, "db"), rows, cols, stream_ptr())
+  return out, db

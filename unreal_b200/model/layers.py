@@ -10,7 +10,7 @@ Every matrix product -- forward, dgrad and wgrad -- is one call of the tcgen05 G
 
 Activations travel in bf16 between layers (fp32 inside the LSTM cell, the heads and the losses);
 gradients are rounded to bf16 only where they become GEMM operands.  torch.autograd is used as the
-tape; the bias column sums and ReLU masks are the only torch element-wise ops on this path.
+tape; ReLU masks, bf16 rounding and bias column sums are one fused kernel (`unreal_relu_grad`).
 """
 import torch
 
@@ -49,12 +49,9 @@ class LinearFn(torch.autograd.Function):
   @staticmethod
   def backward(ctx, dy):
     x16, w16, y = ctx.saved_tensors
-    if ctx.relu:
-      dy = dy * (y > 0)
-    dy16 = dy.to(torch.bfloat16).contiguous()
+    dy16, db = K.relu_grad(dy, y if ctx.relu else None)       # mask + bf16 + bias gradient in one pass
     dx = K.gemm_bf16(dy16, w16, out_dtype=torch.bfloat16) if ctx.needs_input_grad[0] else None
     dw = _wgrad(x16, dy16)
-    db = dy16.float().sum(0)
     return dx, None, dw, db, None, None
 
 
@@ -86,10 +83,9 @@ class ConvFn(torch.autograd.Function):
   def backward(ctx, dy):
     x, w16, y = ctx.saved_tensors
     s, h, w, c, kh, kw, stride, oh, ow, o = ctx.geom
-    dy16 = (dy.reshape(-1, o) * (y > 0)).to(torch.bfloat16).contiguous()
+    dy16, db = K.relu_grad(dy.reshape(-1, o), y)
     cols = K.im2col(x, kh, kw, stride)
     dw = _wgrad(cols, dy16).view(kh, kw, c, o)
-    db = dy16.float().sum(0)
     dx = None
     if ctx.needs_input_grad[0]:
       dcols = K.gemm_bf16(dy16, w16, out_dtype=torch.bfloat16)          # [S*OH*OW, KH*KW*C]
@@ -172,7 +168,7 @@ class LstmFn(torch.autograd.Function):
     dw = torch.empty(lstm_in + 256, 1024, device=dev)
     dw[:lstm_in] = _wgrad(xin16.view(t * n, kx)[:, :lstm_in], dg2)
     dw[lstm_in:] = _wgrad(h16_all[:t].view(t * n, 256), dg2)
-    db = dg2.float().sum(0)
+    _, db = K.relu_grad(dg2, None, want_out=False)
     dxin = torch.zeros(t, n, kx, device=dev, dtype=torch.bfloat16)
     # only the 256 fc1 columns carry a gradient (last_action_reward is an input)
     K.gemm_bf16(dg2, w16[:256], out=dxin.view(t * n, kx)[:, :256])

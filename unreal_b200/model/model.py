@@ -118,7 +118,7 @@ class UnrealModel(object):
       self.flat16.copy_(self.flat)
     self.v16 = self._views(self.flat16)
     # tap-major filter shadows of the two encoder convolutions (TMA-im2col kernels)
-    self.taps1 = K.conv_taps(self.v16["W_base_conv1"], 4) if self.fused_conv else None
+    self.taps1 = K.conv1_w_planes(self.v16["W_base_conv1"]) if self.fused_conv else None
     self.taps2 = K.conv_taps(self.v16["W_base_conv2"], 2) if self.fused_conv else None
 
   def get_vars(self):
