@@ -51,6 +51,9 @@ def parse():
   p.add_argument("--envs-per-gpu", type=int, default=ENVS_PER_GPU)
   p.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
   p.add_argument("--no-cpu-baseline", action="store_true")
+  p.add_argument("--no-agent", action="store_true", help="skip the full-agent (configs[2]) side measurement")
+  p.add_argument("--agent-envs", type=int, default=2048, help="envs per GPU of the full-agent side measurement")
+  p.add_argument("--agent-updates", type=int, default=6)
   return p.parse_args()
 
 
@@ -174,6 +177,73 @@ def run_reference(args):
   return 0
 
 
+
+# --------------------------------------------------------------------------- full agent (side measurement)
+def measure_agent(torch, dist, dev, rank, world, envs, updates, history=2000):
+  """BASELINE configs[2] slice per GPU: `envs` mazes, per-env `history`-frame replay ring, RP/VR/PC
+  sampling, UnrealModel forward/backward on tcgen05 (K7), NCCL gradient exchange + fused RMSProp
+  (K6).  One update = 20 env-steps per env.  Reported beside the headline, never instead of it."""
+  import numpy as np
+  from unreal_b200.environment.environment import Environment
+  from unreal_b200.model.model import UnrealModel
+  from unreal_b200.train.rmsprop_applier import RMSPropApplier
+  from unreal_b200.train.sharding import env_seeds, env_shard
+  from unreal_b200.train.trainer import Trainer
+  Environment.action_size = -1
+  lo, hi = env_shard(envs * world, world, rank)
+  net = UnrealModel(4, 0, -1, True, True, True, True, 0.05, 0.001, dev, {'segnet_mode': 0}, (84, 84), True, 0, 0.0,
+                    0.0, num_envs=envs, seed=0)
+  applier = RMSPropApplier(7e-4, decay=0.99, momentum=0.0, epsilon=0.1, clip_norm=40.0)
+  tr = Trainer(rank, net, 7e-4, None, applier, 'maze', '', True, True, True, True, 0.05, 0.001, 20, 20, 0.99, 0.9,
+               history, 10 ** 9, str(dev), {'segnet_mode': 0}, (84, 84), True, 0, np.random.RandomState(1), 50.0, 0.0,
+               0.0, num_envs=envs, seeds=env_seeds(0xA3C, lo, hi))
+  tr.prepare()
+  t0 = time.perf_counter()
+  while not tr.experience.is_full():
+    tr.process(None, 0)
+  torch.cuda.synchronize(dev)
+  fill_s = time.perf_counter() - t0
+  for _ in range(2):
+    tr.process(None, 0)
+  upd = []
+  orig = net.update
+
+  def timed(feed, lr, ap):
+    a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+    a.record(); out = orig(feed, lr, ap); b.record(); upd.append((a, b))
+    return out
+
+  net.update = timed
+  e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+  if world > 1:
+    dist.barrier()
+  torch.cuda.synchronize(dev)
+  e0.record()
+  steps = 0
+  for _ in range(updates):
+    d, _ = tr.process(None, 0)
+    steps += d
+  e1.record()
+  if world > 1:
+    dist.barrier()
+  torch.cuda.synchronize(dev)
+  ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+  if world > 1:
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+  ms = float(ms)
+  upd_ms = sum(a.elapsed_time(b) for a, b in upd) / len(upd)
+  losses = {k: float(v) for k, v in tr.last_losses.items()}
+  mem = torch.cuda.max_memory_allocated(dev) / 1e9
+  tr.stop()
+  return {"workload": "configs[2] slice: %d maze envs per GPU, %d-frame replay ring per env, PC/VR/RP sampling, "
+                      "UnrealModel fwd/bwd (bf16 tcgen05 GEMMs, fp32 accumulate), %s fused clip+RMSProp"
+                      % (envs, history, "NCCL gradient exchange +" if world > 1 else "single-GPU"),
+          "envs_per_gpu": envs, "history": history, "updates": updates, "value": world * envs * 20 * updates / (ms * 1e-3),
+          "unit": "env-steps/s", "ms_per_update": ms / updates, "model_update_ms": upd_ms,
+          "updates_per_s": updates / (ms * 1e-3), "ring_fill_s": fill_s, "params": net.num_parameters,
+          "finite": bool(all(np.isfinite(v) for v in losses.values())), "grad_norm": losses.get("grad_norm"),
+          "peak_mem_gb": mem, "timing": "CUDA events around %d Trainer.process() calls, max over ranks" % updates}
+
 # --------------------------------------------------------------------------- B200 arm
 def run_b200(args):
   import torch
@@ -247,6 +317,16 @@ def run_b200(args):
   e2e_ms = e0.elapsed_time(e1)
   checksum = float(out["R"].sum())
 
+  h2d_bytes, d2h_bytes, launches_per_pass = eng.h2d_bytes_per_pass, eng.d2h_bytes_per_pass, eng.launches_per_pass
+  agent = None
+  if not args.no_agent:
+    try:
+      del eng, out, hbuf, h_act, h_val, h_bv, h_bq
+      torch.cuda.empty_cache()
+      agent = measure_agent(torch, dist, dev, rank, world, args.agent_envs, args.agent_updates)
+    except Exception as e:  # the side measurement must never cost the headline line
+      agent = {"error": repr(e)[:300]}
+
   times = torch.tensor([total_ms, e2e_ms], device=dev, dtype=torch.float64)
   if world > 1:
     dist.all_reduce(times, op=dist.ReduceOp.MAX)
@@ -270,12 +350,12 @@ def run_b200(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(args.warmup, 3),
         "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": args.obs_dtype, "data": "synthetic", "config": workload_config(args), "clocks": clocks,
-        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": eng.h2d_bytes_per_pass,
-                "d2h_bytes_per_step": eng.d2h_bytes_per_pass, "steps": ke, "ms_per_step": e2e_ms / ke,
+        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
+                "d2h_bytes_per_step": d2h_bytes, "steps": ke, "ms_per_step": e2e_ms / ke,
                 "api": "unreal_b200.train.rollout.RolloutTargets.run_host (pinned host in/out, copies "
                        "pipelined around the phases on a second stream; frames, pixel-change maps and PC "
                        "targets stay in HBM for the learner)", "checksum_R": checksum},
-        "gpu_launches": K * eng.launches_per_pass,
+        "gpu_launches": K * launches_per_pass,
         "roofline": {"bound": "hbm", "kernel": "maze_cta_kernel (K1)" if args.obs_dtype == "f32" else "maze_warp_kernel (K1)",
                      "achieved": achieved, "peak": peak,
                      "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650",
@@ -293,6 +373,8 @@ def run_b200(args):
           line["roofline"]["traffic"] = json.load(f).get(args.obs_dtype)
       except Exception:
         pass
+    if agent is not None:
+      line["agent"] = agent
     if not args.no_cpu_baseline and world == 1:
       from oracle import cpu_path
       procs = cpu_path.host_cores()
