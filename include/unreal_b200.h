@@ -224,7 +224,11 @@ int unreal_conv_fwd(const void* in_bf16, int layer, const void* w_taps_bf16, con
  * out_bf16 = dy * (y > 0) and db[c] += sum_rows out[:, c]; y_bf16 NULL: no mask; out / db nullable.
  * dy [rows, cols] bf16 or f32 (contiguous), cols a multiple of 8; the caller zeroes db. */
 int unreal_relu_grad(const void* dy, int dy_dtype, const void* y_bf16, void* out_bf16, float* db, int64_t rows,
-                     int cols, void* stream);
+                     int cols, int out_planes /* 1: out is [cols/8][rows][8] */, void* stream);
+/* conv1 filter gradient on the tensor path, reading the forward's x'' and the masked dY planes
+ * ([2][S*400][8] bf16 from unreal_relu_grad with out_planes = 1) once each:
+ * dw_taps f32 [4 taps][16 out][48 (dy,dx,c)] += sum_pixels dY * x' (caller zeroes dw_taps). */
+int unreal_conv1_wgrad(const void* xpp_bf16, const void* dy_planes_bf16, float* dw_taps, int s, void* stream);
 
 #ifdef __cplusplus
 }

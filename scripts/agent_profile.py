@@ -28,12 +28,15 @@ def main():
   for _ in range(2):
     tr.process(None, 0)
   torch.cuda.synchronize()
-  with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+  with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], record_shapes=True) as prof:
     for _ in range(2):
       tr.process(None, 0)
     torch.cuda.synchronize()
   with open(out, "w") as f:
     f.write(prof.key_averages().table(sort_by="cuda_time_total", row_limit=60, max_name_column_width=90))
+    f.write("\n\n==== by input shape ====\n")
+    f.write(prof.key_averages(group_by_input_shape=True).table(sort_by="cuda_time_total", row_limit=40,
+                                                                max_name_column_width=50, max_shapes_column_width=90))
 
 
 if __name__ == "__main__":

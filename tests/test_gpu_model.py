@@ -212,3 +212,27 @@ def test_fused_conv_forward_matches_direct_convolution(dtype):
     ref2 = F.relu(F.conv2d(h1.float().permute(0, 3, 1, 2), w2.float().permute(3, 2, 0, 1), b2, stride=2)).permute(0, 2, 3, 1)
     assert tuple(h2.shape) == (s, 9, 9, 32)
     assert torch.allclose(h2.float(), ref2, rtol=2.0 ** -7, atol=1e-3)
+
+
+def test_fused_conv1_wgrad_matches_autograd():
+  """Tensor-core conv1 filter gradient (x'' planes x dY planes, reduction over pixels in TMEM)
+  against torch autograd's conv2d weight gradient on the same bf16-rounded operands."""
+  from unreal_b200 import kernels as K
+  import torch.nn.functional as F
+  dev = torch.device("cuda", 0)
+  g = torch.Generator(device=dev).manual_seed(11)
+  for s in (1, 3, 150):          # 150 frames = 600 items: several per CTA, accumulators persist across them
+    x = torch.rand(s, 84, 84, 3, device=dev, generator=g)
+    xf = x.to(torch.bfloat16).float()
+    y = torch.rand(s * 400, 16, device=dev, generator=g).to(torch.bfloat16) - 0.3      # ReLU mask source
+    dy = (torch.randn(s * 400, 16, device=dev, generator=g) * 0.1).to(torch.bfloat16)
+    dyp, db = K.relu_grad(dy, y, planes=True)
+    masked = (dy.float() * (y.float() > 0)).to(torch.bfloat16).float()
+    assert torch.equal(dyp.permute(1, 0, 2).reshape(s * 400, 16).float(), masked)
+    assert torch.allclose(db, masked.sum(0), rtol=1e-4, atol=1e-3)
+    dw = K.conv1_wgrad(K.s2d_frames(x), dyp)
+    w = torch.zeros(16, 3, 8, 8, device=dev, requires_grad=True)
+    out = F.conv2d(xf.permute(0, 3, 1, 2), w, stride=4)                                   # [S,16,20,20]
+    out.backward(masked.view(s, 20, 20, 16).permute(0, 3, 1, 2))
+    ref = w.grad.permute(2, 3, 1, 0)                                                       # HWIO
+    assert torch.allclose(dw, ref, rtol=1e-3, atol=1e-3 * float(ref.abs().max()))

@@ -397,6 +397,134 @@ conv1_fwd_tcgen05_kernel(const __nv_bfloat16* __restrict__ xpp, const __nv_bfloa
   }
 }
 
+
+// ---- conv1 weight gradient, fused ---------------------------------------------------------------
+// dW[tap][o][(dy,dx,c)] = sum over samples and output pixels of dY[pix, o] * x'[pix + shift(tap), (dy,dx,c)]
+// -- the reduction runs over PIXELS, so both operands are "MN-major" for the tensor core and the same
+// plane-major tiles serve again: x'' planes are the B operand (N = 48 channels = 6 chunks, rows at a
+// 16-byte pitch, tap = start address shift), dY planes [2][S*400][8] (written by unreal_relu_grad) are
+// the A operand (M = 16 outputs = 2 chunks; the UMMA is issued with M = 128 and rows 16.. are
+// ignored).  One work item = 5 output rows = 112 grid rows (K): rows with ox = 20 and rows >= 105
+// are zero in the dY tile (zero-initialised once; bulk copies only ever write the twenty real rows
+// of each output row), so whatever finite data x'' holds there contributes nothing.  Each CTA keeps
+// its four [16 x 48] accumulators in TMEM across ALL its items and adds them to global once.
+// Traffic per frame: 42 KB of x'' + 12.8 KB of dY, each read once; no patch matrix.
+constexpr int kWgStages = 9;
+constexpr int kWgStageBytes = 16384;            // x'' tile 12 096 (+192 pad) | dY tile 2 x 112 x 16 = 3 584 (+512)
+constexpr int kWgDyOff = 12288;
+constexpr int kWgDyPlane = 112 * 16;
+constexpr int kWgTail = 32768;                   // A chunks 2..15 of the last stages read (ignored) rows here
+constexpr int kWgSmem = kWgStages * kWgStageBytes + kWgTail + 1024 + 1024;
+
+__global__ void __launch_bounds__(96, 1)
+conv1_wgrad_tcgen05_kernel(const __nv_bfloat16* __restrict__ xpp, const __nv_bfloat16* __restrict__ dyp,
+                           float* __restrict__ dw, int items, int64_t dy_plane_elems) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + kWgStages * kWgStageBytes + kWgTail;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kWgStages + s); };
+  const uint32_t done_bar = bar_base + 8u * (2 * kWgStages);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kWgStages + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // zero every tile byte once: padding rows of the x'' tiles and the never-written rows of the dY tiles
+  for (uint32_t off = threadIdx.x * 16u; off < (uint32_t)(kWgStages * kWgStageBytes + kWgTail); off += 96u * 16u)
+    asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(smem_base + off), "r"(0u) : "memory");
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < kWgStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    mbar_init(done_bar, 1);
+    fence_mbar_init();
+  } else if (warp == 2) {
+    tmem_alloc<256>(tmem_slot);
+  }
+  fence_proxy_async_smem();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int it = blockIdx.x; it < items; it += gridDim.x) {
+        mbar_wait(empty_bar(stage), phase ^ 1u);
+        mbar_arrive_expect_tx(full_bar(stage), kC1BoxBytes + 10 * 320);
+        const int64_t smp = it >> 2;
+        const int rb = it & 3;
+        const uint32_t dst = smem_base + stage * kWgStageBytes;
+        const uint8_t* xs = reinterpret_cast<const uint8_t*>(xpp) + (smp * 6 * 441 + rb * 105) * 16;
+#pragma unroll
+        for (int q = 0; q < 6; ++q)
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                       ::"r"(dst + q * kC1PlaneBytes), "l"(xs + (int64_t)q * 441 * 16), "r"(kC1PlaneBytes),
+                         "r"(full_bar(stage)) : "memory");
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const uint8_t* ds = reinterpret_cast<const uint8_t*>(dyp) + ((int64_t)c * dy_plane_elems / 8 + smp * 400 + rb * 100) * 16;
+#pragma unroll
+          for (int oyl = 0; oyl < 5; ++oyl)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(dst + kWgDyOff + c * kWgDyPlane + oyl * 21 * 16), "l"(ds + oyl * 320), "r"(320),
+                           "r"(full_bar(stage)) : "memory");
+        }
+        if (++stage == kWgStages) { stage = 0; phase ^= 1u; }
+      }
+    }
+    __syncwarp();
+    // ===== final epilogue (warp 0 owns TMEM lanes 0..31): rows 0..15 = output channels =====
+    mbar_wait(done_bar, 0);
+    fence_after_sync();
+#pragma unroll 1
+    for (int t = 0; t < 4; ++t) {
+      uint32_t v0[32], v1[32];
+      tmem_ld32(tmem_base + (uint32_t)(t * 64), v0);
+      tmem_ld32(tmem_base + (uint32_t)(t * 64 + 32), v1);
+      tmem_ld_wait();
+      if (lane < 16) {
+        float* o = dw + (t * 16 + lane) * 48;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) atomicAdd(o + j, __uint_as_float(v0[j]));
+#pragma unroll
+        for (int j = 0; j < 16; ++j) atomicAdd(o + 32 + j, __uint_as_float(v1[j]));
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = idesc_bf16_f32(128, 48, true, true);
+      int stage = 0; uint32_t phase = 0;
+      bool first = true;
+      for (int it = blockIdx.x; it < items; it += gridDim.x) {
+        mbar_wait(full_bar(stage), phase);
+        fence_after_sync();
+        const uint32_t sx = smem_base + stage * kWgStageBytes, sd = sx + kWgDyOff;
+#pragma unroll
+        for (int ks = 0; ks < 7; ++ks) {
+          // four independent accumulation chains (one per tap) are interleaved
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const uint32_t shift = (uint32_t)((t >> 1) * 21 + (t & 1)) * 16u;
+            mma_f16(tmem_base + (uint32_t)(t * 64), smem_desc_none(sd + ks * 256, 128, kWgDyPlane),
+                    smem_desc_none(sx + shift + ks * 256, 128, kC1PlaneBytes), idesc, (first && ks == 0) ? 0u : 1u);
+          }
+        }
+        first = false;
+        mma_commit(empty_bar(stage));
+        if (++stage == kWgStages) { stage = 0; phase ^= 1u; }
+      }
+      mma_commit(done_bar);
+    }
+  }
+  __syncwarp();
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 2) {
+    fence_after_sync();
+    tmem_dealloc<256>(tmem_base);
+  }
+}
+
 template <int N, int MODE>
 static int launch_conv(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtensorMap& tw, const CUtensorMap& tc,
                        const ConvArgs& g, cudaStream_t st) {
@@ -466,7 +594,6 @@ extern "C" int unreal_conv_fwd(const void* in_bf16, int layer, const void* w_tap
         reinterpret_cast<const __nv_bfloat16*>(in_bf16), reinterpret_cast<const __nv_bfloat16*>(w_taps_bf16), bias, reinterpret_cast<__nv_bfloat16*>(out_bf16), items);
     UNREAL_LAUNCH_CHECK("conv1_fwd_tcgen05_kernel");
     return UNREAL_OK;
-    ta2 = ta;
   } else {
     // h1 [S][20][20][16]: rows y = 2Y + dy as {32 (dx,c), 10 X, 10 Y, S}, one map per dy
     const uint64_t dims[4] = {32, 10, 10, (uint64_t)s};
@@ -495,4 +622,24 @@ extern "C" int unreal_conv_fwd(const void* in_bf16, int layer, const void* w_tap
   }
   return layer == 1 ? launch_conv<16, 1>(ta, ta2, tw, tc, g, as_stream(stream))
                     : launch_conv<32, 2>(ta, ta2, tw, tc, g, as_stream(stream));
+}
+
+extern "C" int unreal_conv1_wgrad(const void* xpp_bf16, const void* dy_planes_bf16, float* dw_taps, int s,
+                                  void* stream) {
+  UNREAL_REQUIRE(xpp_bf16 && dy_planes_bf16 && dw_taps && s > 0, "unreal_conv1_wgrad: null buffer or s <= 0");
+  UNREAL_REQUIRE(aligned16(xpp_bf16) && aligned16(dy_planes_bf16) && aligned16(dw_taps),
+                 "unreal_conv1_wgrad: buffers must be 16-byte aligned");
+  static bool configured = false;
+  if (!configured) {
+    UNREAL_CUDA(cudaFuncSetAttribute(conv1_wgrad_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmem));
+    configured = true;
+  }
+  const int sms = sm_count();
+  if (sms <= 0) return UNREAL_ECUDA;
+  const int items = s * 4;
+  conv1_wgrad_tcgen05_kernel<<<items < sms ? items : sms, 96, kWgSmem, as_stream(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(xpp_bf16), reinterpret_cast<const __nv_bfloat16*>(dy_planes_bf16), dw_taps,
+      items, (int64_t)s * 400 * 8);
+  UNREAL_LAUNCH_CHECK("conv1_wgrad_tcgen05_kernel");
+  return UNREAL_OK;
 }

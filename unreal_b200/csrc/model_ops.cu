@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(256) lstm_cell_bwd_kernel(const float* __restr
 template <typename TD>
 __global__ void __launch_bounds__(256) relu_grad_kernel(const TD* __restrict__ dy, const __nv_bfloat16* __restrict__ y,
                                                         __nv_bfloat16* __restrict__ out, float* __restrict__ db,
-                                                        int64_t rows, int cols) {
+                                                        int64_t rows, int cols, int planes) {
   extern __shared__ float s_db[];
   const int groups = cols >> 3;
   if (db != nullptr) {
@@ -254,7 +254,11 @@ __global__ void __launch_bounds__(256) relu_grad_kernel(const TD* __restrict__ d
       const float2 f = __bfloat1622float2(p);          // the bias gradient sums the ROUNDED values,
       acc[2 * j] += f.x; acc[2 * j + 1] += f.y;        // like dy16.float().sum(0)
     }
-    if (out != nullptr) *reinterpret_cast<uint4*>(out + off) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    if (out != nullptr) {
+      // planes: out[cols/8][rows][8] (8-column chunks as separate planes, the tensor-core wgrad layout)
+      const int64_t o = planes ? ((int64_t)(c0 >> 3) * rows + id / groups) * 8 : off;
+      *reinterpret_cast<uint4*>(out + o) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    }
   }
   if (db == nullptr) return;
 #pragma unroll
@@ -372,7 +376,7 @@ extern "C" int unreal_lstm_cell_bwd(const float* gates_act, const float* c_prev,
 }
 
 extern "C" int unreal_relu_grad(const void* dy, int dy_dtype, const void* y_bf16, void* out_bf16, float* db,
-                                int64_t rows, int cols, void* stream) {
+                                int64_t rows, int cols, int out_planes, void* stream) {
   UNREAL_REQUIRE(dy != nullptr && rows > 0 && cols > 0, "unreal_relu_grad: null dy or empty shape");
   UNREAL_REQUIRE(dy_dtype == UNREAL_BF16 || dy_dtype == UNREAL_F32, "unreal_relu_grad: dy must be bf16 or f32");
   UNREAL_REQUIRE((cols & 7) == 0, "unreal_relu_grad: cols must be a multiple of 8");
@@ -395,11 +399,11 @@ extern "C" int unreal_relu_grad(const void* dy, int dy_dtype, const void* y_bf16
   if (dy_dtype == UNREAL_BF16)
     relu_grad_kernel<__nv_bfloat16><<<(unsigned)gx, 256, shm, as_stream(stream)>>>(
         reinterpret_cast<const __nv_bfloat16*>(dy), reinterpret_cast<const __nv_bfloat16*>(y_bf16),
-        reinterpret_cast<__nv_bfloat16*>(out_bf16), db, rows, cols);
+        reinterpret_cast<__nv_bfloat16*>(out_bf16), db, rows, cols, out_planes);
   else
     relu_grad_kernel<float><<<(unsigned)gx, 256, shm, as_stream(stream)>>>(
         reinterpret_cast<const float*>(dy), reinterpret_cast<const __nv_bfloat16*>(y_bf16),
-        reinterpret_cast<__nv_bfloat16*>(out_bf16), db, rows, cols);
+        reinterpret_cast<__nv_bfloat16*>(out_bf16), db, rows, cols, out_planes);
   UNREAL_LAUNCH_CHECK("relu_grad_kernel");
   return UNREAL_OK;
 }

@@ -402,13 +402,27 @@ def conv_fwd(x, layer, w_taps, bias, out=None):
   return out
 
 
-def relu_grad(dy, y=None, want_out=True, want_db=True):
-  """dy [rows, cols] bf16 / f32, y bf16 or None -> (dy * (y > 0) as bf16, column sums f32)."""
+def relu_grad(dy, y=None, want_out=True, want_db=True, planes=False):
+  """dy [rows, cols] bf16 / f32, y bf16 or None -> (dy * (y > 0) as bf16, column sums f32).
+  planes=True: the bf16 output is laid out [cols/8, rows, 8] (8-column chunks as planes)."""
   rows, cols = dy.shape
   if not dy.is_contiguous():
     dy = dy.contiguous()
-  out = torch.empty(rows, cols, dtype=torch.bfloat16, device=dy.device) if want_out else None
+  out = None
+  if want_out:
+    out = torch.empty((cols // 8, rows, 8) if planes else (rows, cols), dtype=torch.bfloat16, device=dy.device)
   db = torch.zeros(cols, dtype=torch.float32, device=dy.device) if want_db else None
   call("unreal_relu_grad", ptr(dy, None, "dy"), _lib.dtype_tag(dy), ptr(y, torch.bfloat16, "y"),
-       ptr(out, torch.bfloat16, "out"), ptr(db, torch.float32, "db"), rows, cols, stream_ptr())
+       ptr(out, torch.bfloat16, "out"), ptr(db, torch.float32, "db"), rows, cols, 1 if planes else 0, stream_ptr())
   return out, db
+
+
+def conv1_wgrad(xpp, dy_planes):
+  """x'' [S,6,441,8] bf16 (forward's space-to-depth frames), dy_planes [2, S*400, 8] bf16 (masked
+  gradient of conv1's output) -> filter gradient in HWIO layout [8,8,3,16] f32."""
+  s = xpp.shape[0]
+  acc = torch.zeros(4, 16, 48, dtype=torch.float32, device=xpp.device)
+  call("unreal_conv1_wgrad", ptr(xpp, torch.bfloat16, "xpp"), ptr(dy_planes, torch.bfloat16, "dy_planes"),
+       ptr(acc, torch.float32), s, stream_ptr())
+  # acc[(by,bx), o, (dy,dx,c)] -> W[4by+dy, 4bx+dx, c, o]
+  return acc.view(2, 2, 16, 4, 4, 3).permute(0, 3, 1, 4, 5, 2).reshape(8, 8, 3, 16)

@@ -68,21 +68,27 @@ class ConvFn(torch.autograd.Function):
     s, h, w, c = x.shape
     oh, ow = (h - kh) // stride + 1, (w - kw) // stride + 1
     o = w16.shape[1]
+    xpp = None
     if taps is not None and (h, w, c, kh, kw, stride, o) == (84, 84, 3, 8, 8, 4, 16) and x.dtype in (torch.float32, torch.uint8):
-      y = K.conv_fwd(K.s2d_frames(x), 1, taps, b32).view(s * oh * ow, o)
+      xpp = K.s2d_frames(x)
+      y = K.conv_fwd(xpp, 1, taps, b32).view(s * oh * ow, o)
     elif taps is not None and (h, w, c, kh, kw, stride, o) == (20, 20, 16, 4, 4, 2, 32) and x.dtype == torch.bfloat16:
       y = K.conv_fwd(x, 2, taps, b32).view(s * oh * ow, o)
     else:
       cols = K.im2col(x, kh, kw, stride)
       y = K.gemm_bf16(cols, w16, b_mn_major=True, bias=b32, relu=True, out_dtype=torch.bfloat16)
     ctx.geom = (s, h, w, c, kh, kw, stride, oh, ow, o)
-    ctx.save_for_backward(x, w16, y)
+    # conv1 keeps its space-to-depth frames (42 KB/frame) for the fused wgrad instead of the frame
+    ctx.save_for_backward(x if xpp is None else None, w16, y, xpp)
     return y.view(s, oh, ow, o)
 
   @staticmethod
   def backward(ctx, dy):
-    x, w16, y = ctx.saved_tensors
+    x, w16, y, xpp = ctx.saved_tensors
     s, h, w, c, kh, kw, stride, oh, ow, o = ctx.geom
+    if xpp is not None:      # conv1: tensor-core wgrad straight from x'' and the masked dY planes
+      dyp, db = K.relu_grad(dy.reshape(-1, o), y, planes=True)
+      return None, None, K.conv1_wgrad(xpp, dyp), db, None, None, None, None
     dy16, db = K.relu_grad(dy.reshape(-1, o), y)
     cols = K.im2col(x, kh, kw, stride)
     dw = _wgrad(cols, dy16).view(kh, kw, c, o)
