@@ -104,6 +104,7 @@ class Trainer(object):
     self.success_rates = deque(maxlen=self.sr_size)
     self.environment = None
     self.last_feed = None
+    self._ring_full = False
 
   # -- RandomState hand-over for the single-env drop-in case ---------------------------------
   def _rng_in(self):
@@ -211,16 +212,15 @@ class Trainer(object):
       self.experience.add_frames(env.frame_rec)
       last_rec = torch.where(active.bool(), env.frame_rec, last_rec)
       self.episode_reward += self._rew[t]
+      # no host round trips inside the rollout: terminal handling is masked arithmetic, so the
+      # CPU keeps enqueueing ahead of the GPU (an all-terminated batch just idles through the steps)
       term_now = self._term[t] & active
-      if bool(term_now.any()):
-        ended |= term_now
-        net.reset_state(term_now)              # :293
-        self.episode_reward.mul_(1 - term_now.to(torch.float32))
+      ended |= term_now
+      net.reset_state(term_now)                # :293
+      self.episode_reward.mul_(1 - term_now.to(torch.float32))
       active = active & (1 - term_now)
-      if not bool(active.any()):
-        break
     lengths = self._active.sum(0).to(torch.int32)
-    self.local_t += int(lengths.max())
+    self._pending_local_t = lengths.max()      # read back once, after the update has been enqueued
     # bootstrap: V(new_state) with frame.get_action_reward for envs that did not end (:298-300)
     rec = K.frame_unpack(last_rec, fields=("action", "reward"))
     boot_lar = self._last_action_reward(rec["action"], rec["reward"])
@@ -287,7 +287,9 @@ class Trainer(object):
     with torch.cuda.device(self.device):
       self._rng_in()
       try:
-        if not self.experience.is_full():
+        if not self._ring_full:
+          self._ring_full = self.experience.is_full()     # sticky: a full ring stays full
+        if not self._ring_full:
           self._fill_experience(sess)
           return 0, None
         start_local_t = self.local_t
@@ -306,6 +308,7 @@ class Trainer(object):
       self.last_feed = feed
       if hasattr(self.local_network, 'update'):
         self.last_losses = self.local_network.update(feed, cur_learning_rate, self.grad_applier)
+      self.local_t += int(self._pending_local_t)
       if hasattr(self, 'start_time'):
         self._print_log(global_t)
       ended = feed['base']['terminal_end']
