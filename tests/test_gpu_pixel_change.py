@@ -82,3 +82,25 @@ def test_rejects_bad_shapes(K):
   with pytest.raises(_lib.UnrealError):
     K.pixel_change(b, b)
   assert K.pixel_change(torch.zeros(0, 84, 84, 3, device="cuda"), torch.zeros(0, 84, 84, 3, device="cuda")).shape == (0, 20, 20)
+
+
+@pytest.mark.parametrize("dt", ["f32", "u8"])
+def test_fast_84_path_equals_generic_kernel_on_many_sequences(K, dt):
+  """The TMA-staged 84x84x3 kernel (several work items per CTA, 3-deep frame ring) against the
+  generic kernel, bit for bit, in stream and pair form."""
+  from unreal_b200 import _lib
+  S, L = 1300, 3          # > resident CTAs, so every CTA walks several sequences
+  g = torch.Generator(device="cuda").manual_seed(5)
+  if dt == "u8":
+    frames = torch.randint(0, 256, (S, L + 1, 84, 84, 3), dtype=torch.uint8, device="cuda", generator=g)
+  else:
+    frames = torch.rand(S, L + 1, 84, 84, 3, device="cuda", generator=g)
+  fast = K.pixel_change_stream(frames)
+  fast_pair = K.pixel_change(frames[:, 1].contiguous(), frames[:, 0].contiguous())
+  _lib.set_tunable("pc84", 0)
+  try:
+    slow = K.pixel_change_stream(frames)
+  finally:
+    _lib.set_tunable("pc84", 1)
+  assert torch.equal(fast, slow)
+  assert torch.equal(fast_pair, slow[:, 0])

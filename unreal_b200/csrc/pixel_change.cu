@@ -14,6 +14,10 @@
 
 namespace unreal {
 
+// pixel_change84.cu: HBM-rate path for 84x84x3 frames; -100 = not applicable
+int pixel_change84(const void* p0, int64_t stride0, const void* p1, int64_t stride1, int dtype, float* pc,
+                   int sequences, int l, cudaStream_t st);
+
 constexpr int kMaxCellsPerCta = 64;  // 4 rows x 256 pixels = 1024 threads
 
 template <typename T> struct Px;
@@ -149,6 +153,11 @@ extern "C" int unreal_pixel_change(const void* cur, const void* prev, int dtype,
   if (rc) return rc;
   if (m == 0) return UNREAL_OK;
   UNREAL_REQUIRE(cur && prev && pc, "unreal_pixel_change: null buffer");
+  if (h == 84 && w == 84 && c == 3 && get_tunable("pc84", 1) != 0) {
+    const int64_t fb = 84 * 84 * 3 * (dtype == UNREAL_F32 ? 4 : 1);
+    rc = pixel_change84(prev, fb, cur, fb, dtype, pc, m, 1, as_stream(stream));
+    if (rc != -100) return rc;
+  }
   if (dtype == UNREAL_F32) return launch_c<float, false>(cur, prev, pc, m, 0, h, w, c, as_stream(stream));
   return launch_c<uint8_t, false>(cur, prev, pc, m, 0, h, w, c, as_stream(stream));
 }
@@ -160,6 +169,12 @@ extern "C" int unreal_pixel_change_stream(const void* frames, int dtype, float* 
   UNREAL_REQUIRE(l >= 0, "unreal_pixel_change_stream: negative sequence length");
   if (s == 0 || l == 0) return UNREAL_OK;
   UNREAL_REQUIRE(frames && pc, "unreal_pixel_change_stream: null buffer");
+  if (h == 84 && w == 84 && c == 3 && get_tunable("pc84", 1) != 0) {
+    const int64_t fb = 84 * 84 * 3 * (dtype == UNREAL_F32 ? 4 : 1);
+    rc = pixel_change84(frames, (l + 1) * fb, reinterpret_cast<const uint8_t*>(frames) + fb, (l + 1) * fb, dtype, pc,
+                        s, l, as_stream(stream));
+    if (rc != -100) return rc;
+  }
   if (dtype == UNREAL_F32) return launch_c<float, true>(frames, nullptr, pc, s, l, h, w, c, as_stream(stream));
   return launch_c<uint8_t, true>(frames, nullptr, pc, s, l, h, w, c, as_stream(stream));
 }

@@ -1,0 +1,181 @@
+// K2 fast path: Environment._calc_pixel_change (environment/environment.py:88-99) for 84x84x3
+// frames (the lab / indoor / gym observation shape), u8 (/255) or f32, pair or stream form.
+//
+// HBM-bound design: every frame is read from HBM exactly once, as ONE 16-byte-aligned TMA bulk copy
+// of its 2-pixel-cropped rows into a 3-deep ring of shared-memory buffers (prefetch of frame k+2
+// overlaps the reduction of frames k-1 / k); a frame serves as `cur` and then as `prev` from shared
+// memory.  One thread per 4x4 output cell reads its 4 x 12 values of both frames (word loads at a
+// 12-byte stride: bank-conflict free), and reduces in exactly numpy's order and roundings:
+//   pixel:  ((|a0-b0| + |a1-b1|) + |a2-b2|) / 3      (abs-diff, mean over channels)
+//   cell row: (((m0+m1)+m2)+m3) * 0.25                (mean over the 4 columns first, :90-91)
+//   cell:   (((r0+r1)+r2)+r3) * 0.25                  (then over the 4 rows)
+// so fp32 results are bit-identical to the generic kernel and to the reference's float32 evaluation.
+// u8 pixels are scaled by a shared-memory table of __fdiv_rn(v, 255) (the /255 of
+// lab_environment.py:99-102, correctly rounded), replicated once per bank (index v*32 + lane) so the
+// 96 data-dependent lookups of a cell never conflict (a single 256-entry table measured 3x slower).
+#include "common.cuh"
+#include "tc05.cuh"
+
+namespace unreal {
+using namespace tc05;
+
+constexpr int kRowElems84 = 84 * 3;   // 252
+
+template <typename T, int PR> struct Pc84 {
+  static constexpr int kFrameBytes = 84 * 84 * 3 * (int)sizeof(T);
+  static constexpr int kRowBytes = kRowElems84 * (int)sizeof(T);
+  static constexpr int kRegionBytes = 4 * PR * kRowBytes;          // the cropped rows of one part
+  static constexpr int kParts = 20 / PR;
+  static constexpr int kCells = PR * 20;
+  static constexpr int kThreads = (kCells + 31) / 32 * 32;
+  // the region starts at row 2 + 4*PR*part; copy from the 16-byte boundary below it
+  static constexpr int kLead = (2 * kRowBytes) % 16;               // same for every part (4*PR*kRowBytes % 16 == 0)
+  static constexpr int kCopyBytes = (kLead + kRegionBytes + 15) / 16 * 16;
+  static constexpr int kBufBytes = (kCopyBytes + 127) / 128 * 128;
+  static constexpr int kLutBytes = sizeof(T) == 1 ? 256 * 32 * 4 : 0;
+  static constexpr int kSmem = 3 * kBufBytes + kLutBytes + 64 /*barriers*/ + 128;
+  static_assert((4 * PR * kRowBytes) % 16 == 0, "part stride must keep the 16-byte phase");
+};
+
+struct Pc84Args {
+  const uint8_t* p0; int64_t stride0;   // frame 0 of sequence s:   p0 + s*stride0
+  const uint8_t* p1; int64_t stride1;   // frame f >= 1:            p1 + s*stride1 + (f-1)*frame_bytes
+  float* pc;
+  int sequences, l;
+};
+
+__device__ __forceinline__ float pc84_pixel(float a0, float a1, float a2, float b0, float b1, float b2) {
+  float s = fabsf(__fsub_rn(a0, b0));
+  s = __fadd_rn(s, fabsf(__fsub_rn(a1, b1)));
+  s = __fadd_rn(s, fabsf(__fsub_rn(a2, b2)));
+  // s / 3, correctly rounded, in three FMA-pipe instructions instead of the ~25 of __fdiv_rn:
+  // q = s*RN(1/3) corrected by one exact-remainder step.  Checked against __fdiv_rn for EVERY
+  // non-negative finite float on the B200 (scripts/probes/div3_probe.cu: 0 mismatches of 2^31-2^23).
+  const float r = 1.0f / 3.0f;
+  const float q = __fmul_rn(s, r);
+  return __fmaf_rn(__fmaf_rn(-3.0f, q, s), r, q);
+}
+
+template <typename T> struct CellRow;
+template <> struct CellRow<uint8_t> {
+  // 12 bytes at byte offset `off` (off % 4 == 2) of a shared buffer -> 12 floats through the table
+  static __device__ __forceinline__ void load(const uint8_t* buf, int off, const float* lut, float (&v)[12]) {
+    const uint32_t* wp = reinterpret_cast<const uint32_t*>(buf + (off - 2));
+    uint32_t w[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) w[k] = wp[k];
+#pragma unroll
+    for (int e = 0; e < 12; ++e) {
+      const int byte = e + 2;
+      v[e] = lut[((w[byte >> 2] >> (8 * (byte & 3))) & 255u) << 5];   // lut already points at this lane's bank
+    }
+  }
+};
+template <> struct CellRow<float> {
+  static __device__ __forceinline__ void load(const uint8_t* buf, int off, const float*, float (&v)[12]) {
+    const float2* fp = reinterpret_cast<const float2*>(buf + off);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) { const float2 t = fp[k]; v[2 * k] = t.x; v[2 * k + 1] = t.y; }
+  }
+};
+
+template <typename T, int PR>
+__global__ void __launch_bounds__(Pc84<T, PR>::kThreads) pixel_change84_kernel(const Pc84Args g) {
+  using P = Pc84<T, PR>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 127u) & ~127u;
+  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+  float* lut_all = reinterpret_cast<float*>(gen + 3 * P::kBufBytes);
+  const uint32_t bar0 = base + 3 * P::kBufBytes + P::kLutBytes;
+  const int tid = threadIdx.x;
+  if (sizeof(T) == 1) {
+    for (int e = tid; e < 256 * 32; e += P::kThreads) lut_all[e] = __fdiv_rn((float)(e >> 5), 255.0f);
+  }
+  const float* lut = lut_all + (tid & 31);
+  if (tid == 0) {
+    for (int b = 0; b < 3; ++b) mbar_init(bar0 + 8u * b, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  const int items = g.sequences * P::kParts;
+  const int nitems = (items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int per = g.l + 1;
+  const int total = nitems * per;
+  auto issue = [&](int k) {
+    const int itn = k / per, f = k - itn * per;
+    const int item = (int)blockIdx.x + itn * (int)gridDim.x;
+    const int s = item / P::kParts, part = item - s * P::kParts;
+    const uint8_t* frame = f == 0 ? g.p0 + (int64_t)s * g.stride0 : g.p1 + (int64_t)s * g.stride1 + (int64_t)(f - 1) * P::kFrameBytes;
+    const uint8_t* src = frame + (2 + 4 * PR * part) * P::kRowBytes - P::kLead;
+    const uint32_t bar = bar0 + 8u * (k % 3);
+    mbar_arrive_expect_tx(bar, P::kCopyBytes);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(base + (uint32_t)(k % 3) * P::kBufBytes), "l"(src), "r"(P::kCopyBytes), "r"(bar) : "memory");
+  };
+  if (tid == 0) {
+    if (total > 0) issue(0);
+    if (total > 1) issue(1);
+  }
+  const int ci = tid / 20, cj = tid - ci * 20;          // this thread's cell inside the part
+  for (int k = 0; k < total; ++k) {
+    const int b = k % 3;
+    mbar_wait(bar0 + 8u * b, (uint32_t)(k / 3) & 1u);
+    const int itn = k / per, f = k - itn * per;
+    if (f > 0 && tid < P::kCells) {
+      const uint8_t* cur = gen + b * P::kBufBytes;
+      const uint8_t* prv = gen + ((k + 2) % 3) * P::kBufBytes;
+      float rows[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int off = P::kLead + (4 * ci + r) * P::kRowBytes + (6 + 12 * cj) * (int)sizeof(T);
+        float a[12], p[12];
+        CellRow<T>::load(cur, off, lut, a);
+        CellRow<T>::load(prv, off, lut, p);
+        const float m0 = pc84_pixel(a[0], a[1], a[2], p[0], p[1], p[2]);
+        const float m1 = pc84_pixel(a[3], a[4], a[5], p[3], p[4], p[5]);
+        const float m2 = pc84_pixel(a[6], a[7], a[8], p[6], p[7], p[8]);
+        const float m3 = pc84_pixel(a[9], a[10], a[11], p[9], p[10], p[11]);
+        rows[r] = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(m0, m1), m2), m3), 0.25f);
+      }
+      const float cell = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(rows[0], rows[1]), rows[2]), rows[3]), 0.25f);
+      const int item = (int)blockIdx.x + itn * (int)gridDim.x;
+      const int s = item / P::kParts, part = item - s * P::kParts;
+      __stcs(g.pc + ((int64_t)s * g.l + (f - 1)) * 400 + part * P::kCells + tid, cell);
+    }
+    __syncthreads();                     // frame k-1's buffer is free: prefetch frame k+2 into it
+    if (tid == 0 && k + 2 < total) issue(k + 2);
+  }
+}
+
+template <typename T, int PR>
+static int launch84(const Pc84Args& g, cudaStream_t st) {
+  using P = Pc84<T, PR>;
+  static bool configured = false;
+  auto kern = pixel_change84_kernel<T, PR>;
+  if (!configured) {
+    UNREAL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, P::kSmem));
+    configured = true;
+  }
+  const int sms = sm_count();
+  if (sms <= 0) return UNREAL_ECUDA;
+  const int per_sm = (227 * 1024) / (P::kSmem + 1024);
+  const int64_t items = (int64_t)g.sequences * P::kParts;
+  const int64_t cap = (int64_t)sms * (per_sm < 1 ? 1 : per_sm);
+  const int grid = (int)(items < cap ? items : cap);
+  kern<<<grid, P::kThreads, P::kSmem, st>>>(g);
+  UNREAL_LAUNCH_CHECK("pixel_change84_kernel");
+  return UNREAL_OK;
+}
+
+// p0/p1 as in Pc84Args; returns UNREAL_OK after enqueueing, or -100 when the fast path does not apply
+int pixel_change84(const void* p0, int64_t stride0, const void* p1, int64_t stride1, int dtype, float* pc,
+                   int sequences, int l, cudaStream_t st) {
+  if (!aligned16(p0) || !aligned16(p1)) return -100;
+  Pc84Args g{reinterpret_cast<const uint8_t*>(p0), stride0, reinterpret_cast<const uint8_t*>(p1), stride1, pc,
+             sequences, l};
+  if (dtype == UNREAL_U8) return launch84<uint8_t, 20>(g, st);
+  return launch84<float, 10>(g, st);
+}
+
+}  // namespace unreal
