@@ -143,6 +143,10 @@ int unreal_replay_add(unreal_replay_t* r, const uint64_t* frame_rec /*[N]*/, voi
 /* is_full (:96-97) per env -> full [N] u8; count/top for tests (nullable). */
 int unreal_replay_state(unreal_replay_t* r, uint8_t* full, int32_t* count, int64_t* top,
                         int32_t* n_pos, int32_t* n_neg, void* stream);
+/* verbatim export (direction 0) / import (direction 1) of the ring for checkpoints: rec [N,H] u64,
+ * top [N] i64, count / n_pos / n_neg [N] i32 (device buffers). */
+int unreal_replay_copy(unreal_replay_t* r, int direction, uint64_t* rec, int64_t* top, int32_t* count,
+                       int32_t* n_pos, int32_t* n_neg, void* stream);
 /* sample_sequence(L) (:100-118) with the env's own MT stream: start [N], len [N] i32 and
  * the gathered records rec [N,L] u64 (entries >= len are 0). */
 int unreal_replay_sample_sequence(unreal_replay_t* r, uint32_t* mt, int32_t* mt_pos, int seq_len,

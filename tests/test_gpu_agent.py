@@ -65,3 +65,37 @@ def test_agent_trains_end_to_end():
     tr.process(None, 0)
   assert torch.isfinite(net.flat).all()
   tr.stop()
+
+
+def test_checkpoint_restores_the_exact_trajectory(tmp_path):
+  """Save mid-training, continue; restore into a FRESH agent and continue: same actions, same
+  replay samples (bit-exact integers), same losses up to the split-K atomics' summation order."""
+  from unreal_b200.train import checkpoint
+  n = 4
+  tr, net, ap = _agent(n, H=40, seed=3)
+  while not tr.experience.is_full():
+    tr.process(None, 0)
+  tr.process(None, 0)
+  path = str(tmp_path / "agent.pt")
+  checkpoint.save(path, tr, global_t=123)
+
+  def run(trainer):
+    out = []
+    for _ in range(2):
+      trainer.process(None, 0)
+      f = trainer.last_feed
+      out.append(dict(act=f['base']['a'].argmax(-1).cpu(), pc_start=f['pc']['start'].cpu(), vr_start=f['vr']['start'].cpu(),
+                      rp_start=f['rp']['start'].cpu(), R=f['base']['R'].cpu(), total=float(trainer.last_losses['total'])))
+    return out, trainer.local_network.flat.detach().cpu().clone()
+
+  a, pa = run(tr)
+  tr2, net2, ap2 = _agent(n, H=40, seed=99)       # different init: everything must come from the file
+  assert checkpoint.load(path, tr2) == 123
+  b, pb = run(tr2)
+  for x, y in zip(a, b):
+    for k in ("act", "pc_start", "vr_start", "rp_start"):
+      assert torch.equal(x[k], y[k]), k
+    assert torch.allclose(x["R"], y["R"], rtol=1e-4, atol=1e-5)
+    assert abs(x["total"] - y["total"]) <= 1e-3 * max(1.0, abs(x["total"]))
+  assert torch.allclose(pa, pb, rtol=1e-3, atol=1e-5)
+  tr.stop(); tr2.stop()

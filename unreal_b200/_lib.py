@@ -57,6 +57,7 @@ SIGNATURES = {
     "unreal_replay_reset": (c_int, [c_void_p, P]),
     "unreal_replay_add": (c_int, [c_void_p, P, P]),
     "unreal_replay_state": (c_int, [c_void_p, P, P, P, P, P, P]),
+    "unreal_replay_copy": (c_int, [c_void_p, c_int, P, P, P, P, P, P]),
     "unreal_replay_sample_sequence": (c_int, [c_void_p, P, P, c_int, P, P, P, P]),
     "unreal_replay_sample_rp": (c_int, [c_void_p, P, P, P, P, P]),
     "unreal_frame_unpack": (c_int, [P, c_int, P, P, P, P, P, P, P, P, P]),

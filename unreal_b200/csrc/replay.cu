@@ -234,3 +234,22 @@ extern "C" int unreal_frame_unpack(const uint64_t* rec, int m, int32_t* pos0, in
   UNREAL_LAUNCH_CHECK("frame_unpack_kernel");
   return UNREAL_OK;
 }
+
+// Checkpointing (main.py:356,469-519 saves only the network; the replay memory and RNG are lost on
+// restart there -- here the ring can be exported / imported verbatim).  direction 0: ring -> caller
+// buffers, 1: caller buffers -> ring.  rec [N,H] u64, top [N] i64, count / n_pos / n_neg [N] i32.
+extern "C" int unreal_replay_copy(unreal_replay_t* r, int direction, uint64_t* rec, int64_t* top, int32_t* count,
+                                  int32_t* n_pos, int32_t* n_neg, void* stream) {
+  UNREAL_REQUIRE(r && rec && top && count && n_pos && n_neg, "unreal_replay_copy: null argument");
+  UNREAL_REQUIRE(direction == 0 || direction == 1, "unreal_replay_copy: direction must be 0 (export) or 1 (import)");
+  cudaStream_t st = as_stream(stream);
+  const size_t n = (size_t)r->n;
+  struct { void* ring; void* user; size_t bytes; } parts[5] = {
+      {r->rec, rec, n * r->h * sizeof(uint64_t)}, {r->top, top, n * sizeof(int64_t)},
+      {r->count, count, n * sizeof(int32_t)}, {r->n_pos, n_pos, n * sizeof(int32_t)}, {r->n_neg, n_neg, n * sizeof(int32_t)}};
+  for (auto& p : parts) {
+    if (direction == 0) UNREAL_CUDA(cudaMemcpyAsync(p.user, p.ring, p.bytes, cudaMemcpyDeviceToDevice, st));
+    else UNREAL_CUDA(cudaMemcpyAsync(p.ring, p.user, p.bytes, cudaMemcpyDeviceToDevice, st));
+  }
+  return UNREAL_OK;
+}

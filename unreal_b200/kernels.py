@@ -229,6 +229,26 @@ class ReplayRing(object):
          ptr(out["n_neg"]), stream_ptr())
     return out
 
+  def export_state(self):
+    """Verbatim copy of the ring: dict(rec [N,H] i64, top i64, count / n_pos / n_neg i32)."""
+    d = self.device
+    out = dict(rec=torch.empty(self.n, self.h, dtype=torch.int64, device=d),
+               top=torch.empty(self.n, dtype=torch.int64, device=d),
+               count=torch.empty(self.n, dtype=torch.int32, device=d),
+               n_pos=torch.empty(self.n, dtype=torch.int32, device=d),
+               n_neg=torch.empty(self.n, dtype=torch.int32, device=d))
+    call("unreal_replay_copy", self._h, 0, ptr(out["rec"]), ptr(out["top"]), ptr(out["count"]), ptr(out["n_pos"]),
+         ptr(out["n_neg"]), stream_ptr())
+    return out
+
+  def import_state(self, st):
+    if tuple(st["rec"].shape) != (self.n, self.h):
+      raise _lib.UnrealError("replay checkpoint is for %s envs x frames, ring is %d x %d" % (tuple(st["rec"].shape), self.n, self.h))
+    t = {k: st[k].to(self.device).contiguous() for k in ("rec", "top", "count", "n_pos", "n_neg")}
+    call("unreal_replay_copy", self._h, 1, ptr(t["rec"], torch.int64), ptr(t["top"], torch.int64),
+         ptr(t["count"], torch.int32), ptr(t["n_pos"], torch.int32), ptr(t["n_neg"], torch.int32), stream_ptr())
+    torch.cuda.current_stream().synchronize()      # `t` must outlive the copies
+
   def sample_sequence(self, streams, seq_len):
     """-> start [N] i32, len [N] i32, rec [N, seq_len] i64 (zero past len)."""
     d = self.device
