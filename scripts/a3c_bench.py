@@ -1,0 +1,45 @@
+"""BASELINE configs[4] slice per GPU: MINOS-shaped synthetic observations (uint8 84x84 RGB; the
+reference model consumes no depth channel), 3 pointgoal actions, goal vector G = 2,
+A3C-LSTM forward/backward + fused clip+RMSProp on 1024 envs x T = 20 = 20 480 samples per update.
+Reports samples/s and the model's algorithmic FLOP rate (18.5 MFLOP/sample)."""
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+from unreal_b200.model.model import UnrealModel
+from unreal_b200.train.rmsprop_applier import RMSPropApplier
+
+dev = torch.device("cuda", 0)
+N = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
+T, A, G = 20, 3, 2
+iters = int(sys.argv[2]) if len(sys.argv) > 2 else 10
+m = UnrealModel(A, G, -1, True, False, False, False, 0.05, 0.001, dev, {'segnet_mode': 0}, (84, 84), True, 0, 0.0, 0.0,
+                num_envs=N, seed=0)
+ap = RMSPropApplier(7e-4, decay=0.99, momentum=0.0, epsilon=0.1, clip_norm=40.0)
+g = torch.Generator(device=dev).manual_seed(0)
+img = torch.randint(0, 256, (T, N, 84, 84, 3), dtype=torch.uint8, device=dev, generator=g)
+lar = torch.zeros(T, N, A + 1 + G, device=dev)
+lar.scatter_(2, torch.randint(0, A, (T, N, 1), device=dev, generator=g), 1.0)
+lar[..., A + 1:] = torch.rand(T, N, G, device=dev, generator=g)
+a = torch.zeros(T, N, A, device=dev).scatter_(2, torch.randint(0, A, (T, N, 1), device=dev, generator=g), 1.0)
+feed = {"base": dict(images=img, lar=lar, a=a, adv=torch.randn(T, N, device=dev, generator=g),
+                     R=torch.randn(T, N, device=dev, generator=g), mask=torch.ones(T, N, device=dev),
+                     c0=torch.zeros(N, 256, device=dev), h0=torch.zeros(N, 256, device=dev))}
+for _ in range(3):
+  out = m.update(feed, 7e-4, ap)
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(iters):
+  out = m.update(feed, 7e-4, ap)
+e1.record()
+torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / iters
+samples = N * T
+print(json.dumps(dict(workload="configs[4] slice: %d envs x T=20, u8 84x84x3 frames, A=3, G=2, A3C-LSTM fwd/bwd + RMSProp" % N,
+                      ms_per_update=ms, samples_per_s=samples / (ms * 1e-3), model_tflops=samples * 18.5e6 / (ms * 1e-3) / 1e12,
+                      frac_of_sustained_bf16_peak=samples * 18.5e6 / (ms * 1e-3) / 1e12 / 1393.1,
+                      finite=bool(torch.isfinite(out["total"])), params=m.num_parameters)))

@@ -236,3 +236,36 @@ def test_fused_conv1_wgrad_matches_autograd():
     out.backward(masked.view(s, 20, 20, 16).permute(0, 3, 1, 2))
     ref = w.grad.permute(2, 3, 1, 0)                                                       # HWIO
     assert torch.allclose(dw, ref, rtol=1e-3, atol=1e-3 * float(ref.abs().max()))
+
+
+def test_indoor_shaped_a3c_lstm_matches_oracle():
+  """BASELINE configs[4] shape: MINOS-like observations -- uint8 RGB frames (/255 on load,
+  indoor_environment.py:102-103), 3 actions (:16-20), a goal vector of G = 2 appended to
+  last_action_reward (experience.py:34-46) -- through the A3C-LSTM tower only (no aux heads)."""
+  from unreal_b200.model.model import UnrealModel
+  from oracle import model_oracle as M
+  dev = torch.device("cuda", 0)
+  A_, G_, T, N = 3, 2, 4, 3
+  m = UnrealModel(A_, G_, -1, True, False, False, False, 0.05, 0.001, dev, {'segnet_mode': 0}, (84, 84), True, 0, 0.0,
+                  0.0, num_envs=N, seed=5)
+  assert len(m.get_vars()) == 12                      # model_test.py: base only = 12 variables
+  rs = np.random.RandomState(8)
+  img8 = torch.from_numpy(rs.randint(0, 256, size=(T, N, 84, 84, 3)).astype(np.uint8))
+  lar = np.zeros((T, N, A_ + 1 + G_), np.float32)
+  np.put_along_axis(lar, rs.randint(0, A_, size=(T, N, 1)), 1.0, axis=-1)
+  lar[..., A_] = rs.randint(-1, 2, size=(T, N)); lar[..., A_ + 1:] = rs.rand(T, N, G_)
+  a = np.zeros((T, N, A_), np.float32); np.put_along_axis(a, rs.randint(0, A_, size=(T, N, 1)), 1.0, axis=-1)
+  base = dict(lar=torch.from_numpy(lar), a=torch.from_numpy(a), adv=torch.from_numpy(rs.randn(T, N).astype(np.float32)),
+              R=torch.from_numpy(rs.randn(T, N).astype(np.float32)), mask=torch.ones(T, N),
+              c0=torch.zeros(N, 256), h0=torch.zeros(N, 256))
+  feed_gpu = {"base": dict({k: v.to(dev) for k, v in base.items()}, images=img8.to(dev))}
+  total, parts, grad = m.loss_and_grads(feed_gpu)
+  params = {k: v.detach().cpu().clone() for k, v in m.named_vars().items()}
+  o = M.ModelOracle(params, A_, G_, 0.05, 0.001, emulate_bf16=True)
+  feed_cpu = {"base": dict(base, images=img8.float() / 255.0)}
+  rtotal, rparts, rgrads = o.loss_and_grads(feed_cpu)
+  for k in ("policy", "value"):
+    assert abs(float(parts[k]) - float(rparts[k])) <= 2e-3 * max(1.0, abs(float(rparts[k]))), k
+  got = {k: v.cpu() for k, v in m._views(grad).items()}
+  for k, rg in rgrads.items():
+    assert float((got[k] - rg).abs().max()) <= 3e-2 * float(rg.abs().max()) + 1e-6, k
