@@ -117,9 +117,17 @@ class UnrealModel(object):
     with torch.no_grad():
       self.flat16.copy_(self.flat)
     self.v16 = self._views(self.flat16)
-    # tap-major filter shadows of the two encoder convolutions (TMA-im2col kernels)
-    self.taps1 = K.conv1_w_planes(self.v16["W_base_conv1"]) if self.fused_conv else None
-    self.taps2 = K.conv_taps(self.v16["W_base_conv2"], 2) if self.fused_conv else None
+    # tap-major filter shadows of the two encoder convolutions (TMA-im2col kernels); refreshed IN PLACE
+    # so kernels captured in a CUDA graph keep reading the current filters
+    if self.fused_conv:
+      t1 = K.conv1_w_planes(self.v16["W_base_conv1"])
+      t2 = K.conv_taps(self.v16["W_base_conv2"], 2)
+      if getattr(self, "taps1", None) is None:
+        self.taps1, self.taps2 = t1, t2
+      else:
+        self.taps1.copy_(t1); self.taps2.copy_(t2)
+    else:
+      self.taps1 = self.taps2 = None
 
   def get_vars(self):
     """The variables in creation order (views of the flat buffer), like model.py:729-730."""
@@ -194,13 +202,29 @@ class UnrealModel(object):
     return z, z
 
   # ---- acting-side helpers (model.py:625-728), batched over envs ----------------------
+  # The acting LSTM state lives in two persistent [N,256] buffers that are only ever updated IN PLACE,
+  # so a CUDA graph that captured a rollout keeps reading / writing the live state on every replay.
+  @property
+  def base_lstm_state_out(self):
+    return (self._lstm_c, self._lstm_h)
+
+  @base_lstm_state_out.setter
+  def base_lstm_state_out(self, state):
+    c, h = state
+    with torch.no_grad():
+      self._lstm_c.copy_(torch.as_tensor(np.asarray(c.cpu() if isinstance(c, torch.Tensor) else c, dtype=np.float32)).to(self._device).view(-1, 256))
+      self._lstm_h.copy_(torch.as_tensor(np.asarray(h.cpu() if isinstance(h, torch.Tensor) else h, dtype=np.float32)).to(self._device).view(-1, 256))
+
   def reset_state(self, mask=None):
     """model.py:625-628; `mask` [N] selects the envs whose state is zeroed (all when None)."""
-    if mask is None or not hasattr(self, "base_lstm_state_out"):
-      self.base_lstm_state_out = tuple(torch.zeros(self.num_envs, 256, device=self._device) for _ in range(2))
+    if not hasattr(self, "_lstm_c"):
+      self._lstm_c = torch.zeros(self.num_envs, 256, device=self._device)
+      self._lstm_h = torch.zeros(self.num_envs, 256, device=self._device)
+    if mask is None:
+      self._lstm_c.zero_(); self._lstm_h.zero_()
     else:
       keep = (mask == 0).to(torch.float32).unsqueeze(1)
-      self.base_lstm_state_out = tuple(s * keep for s in self.base_lstm_state_out)
+      self._lstm_c.mul_(keep); self._lstm_h.mul_(keep)
 
   def _images(self, s_t):
     img = s_t['image'] if isinstance(s_t, dict) else s_t
@@ -229,10 +253,11 @@ class UnrealModel(object):
     with torch.no_grad():
       pi, v = self._policy_value(p32, h)
       if active is None:
-        self.base_lstm_state_out = new_state
+        self._lstm_c.copy_(new_state[0]); self._lstm_h.copy_(new_state[1])
       else:
         m = active.to(torch.bool).unsqueeze(1)
-        self.base_lstm_state_out = tuple(torch.where(m, a, b) for a, b in zip(new_state, self.base_lstm_state_out))
+        self._lstm_c.copy_(torch.where(m, new_state[0], self._lstm_c))
+        self._lstm_h.copy_(torch.where(m, new_state[1], self._lstm_h))
     return pi, v, None
 
   def run_base_value(self, sess, s_t, last_action_reward):

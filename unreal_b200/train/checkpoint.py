@@ -51,7 +51,7 @@ def load_state_dict(trainer, d):
   with torch.no_grad():
     net.flat.copy_(d["flat"].to(dev))
   net.refresh_shadow()
-  net.base_lstm_state_out = tuple(s.to(dev) for s in d["lstm"])
+  net.base_lstm_state_out = tuple(s.to(dev) for s in d["lstm"])      # copied into the persistent state buffers
   trainer.experience.ring.import_state(d["ring"])
   trainer._ring_full = bool(d["ring_full"])
   trainer.streams.mt.copy_(d["rng"]["mt"].to(dev)); trainer.streams.pos.copy_(d["rng"]["pos"].to(dev))

@@ -46,7 +46,7 @@ class Trainer(object):
                pixel_change_lambda, entropy_beta, local_t_max, n_step_TD, gamma, gamma_pc,
                experience_history_size, max_global_time_step, device, segnet_param_dict, image_shape,
                is_training, n_classes, random_state, termination_time, segnet_lambda, dropout,
-               num_envs=1, seeds=None, verbose=False):
+               num_envs=1, seeds=None, verbose=False, use_graphs=False):
     _lib.require_device()
     self.thread_index = thread_index
     self.learning_rate_input = learning_rate_input
@@ -105,6 +105,8 @@ class Trainer(object):
     self.environment = None
     self.last_feed = None
     self._ring_full = False
+    self.use_graphs = bool(use_graphs)      # capture the rollout + sampling phase into one CUDA graph
+    self._graph = None
 
   # -- RandomState hand-over for the single-env drop-in case ---------------------------------
   def _rng_in(self):
@@ -193,7 +195,9 @@ class Trainer(object):
   def _process_base(self, sess, global_t, summary_writer, summary_op_dict, summary_dict):
     env, net = self.environment, self.local_network
     n, T, d = self.num_envs, self.n_step_TD, self.device
-    start_lstm_state = net.base_lstm_state_out if self.use_lstm else None
+    # the model updates its state buffers in place: keep a copy of the state the rollout started from
+    state = net.base_lstm_state_out if self.use_lstm else None
+    start_lstm_state = None if state is None else tuple(x.clone() if isinstance(x, torch.Tensor) else x for x in state)
     active = torch.ones(n, dtype=torch.uint8, device=d)
     ended = torch.zeros(n, dtype=torch.uint8, device=d)
     self._obs[0].copy_(env.last_state['image'])
@@ -226,7 +230,10 @@ class Trainer(object):
     boot_lar = self._last_action_reward(rec["action"], rec["reward"])
     boot_obs = self._obs[1:].gather(
         0, (lengths.to(torch.int64) - 1).clamp_(min=0).view(1, n, 1, 1, 1).expand(1, n, 84, 84, 3))[0]
-    env.last_state = {'image': boot_obs}   # every env's current frame (the reset frame for ended envs)
+    # every env's current frame (the reset frame for ended envs) goes back into the env's own
+    # persistent frame buffer, which is where the next rollout starts reading (graph-replay safe)
+    env._obs.copy_(boot_obs)
+    env.last_state = {'image': env._obs}
     boot = net.run_base_value(sess, {'image': boot_obs}, boot_lar)
     boot = torch.where(ended.bool(), torch.zeros_like(boot), boot).contiguous()
     R, adv = K.nstep_returns(self._rew, self._val, self._term, boot, self.gamma)
@@ -281,6 +288,40 @@ class Trainer(object):
     c[:, 0] = zero.float(); c[:, 1] = (~zero & (r > 0)).float(); c[:, 2] = (~zero & (r < 0)).float()
     return dict(pos=f["pos0"][:, :3], c=c, start=start)
 
+  # -- rollout + replay sampling + targets: everything that feeds one update -------------------
+  def _data_phase(self, sess):
+    feed = {'base': self._process_base(sess, 0, None, None, {'placeholders': {}, 'values': {}})}
+    if self.use_pixel_change:
+      feed['pc'] = self._process_pc(sess)
+    if self.use_value_replay:
+      feed['vr'] = self._process_vr(sess)
+    if self.use_reward_prediction:
+      feed['rp'] = self._process_rp()
+    return feed
+
+  def _data_phase_graphed(self, sess):
+    """The data phase is ~1000 small launches with no host decision inside (terminal handling is
+    masked arithmetic): capture it ONCE into a CUDA graph and replay it.  Every buffer it touches
+    is persistent -- env / ring / RNG / LSTM state are updated in place, the filters' bf16 shadows
+    are refreshed in place -- so the replay acts on the live state and the returned feed tensors
+    keep their addresses."""
+    if self._graph is None:
+      # first call: run the phase eagerly (this IS this iteration's data, and it performs every lazy
+      # initialisation), then record the same code into a graph without executing it
+      feed = self._data_phase(sess)
+      pending = self._pending_local_t
+      torch.cuda.synchronize(self.device)
+      g = torch.cuda.CUDAGraph()
+      with torch.cuda.graph(g):
+        self._graph_feed = self._data_phase(sess)
+      self._graph_pending = self._pending_local_t
+      self._pending_local_t = pending
+      self._graph = g
+      return feed
+    self._pending_local_t = self._graph_pending
+    self._graph.replay()
+    return dict(self._graph_feed)
+
   # -- one iteration  trainer.py:438-636 -------------------------------------------------------
   def process(self, sess=None, global_t=0, summary_writer=None, summary_op_dict=None, score_input=None,
               sr_input=None, eval_input=None, entropy_input=None, term_global_t=None, losses_input=None):
@@ -294,15 +335,8 @@ class Trainer(object):
           return 0, None
         start_local_t = self.local_t
         cur_learning_rate = self._anneal_learning_rate(global_t)
-        feed = {'base': self._process_base(sess, global_t, summary_writer, summary_op_dict,
-                                           {'placeholders': {}, 'values': {}}),
-                'learning_rate': cur_learning_rate}
-        if self.use_pixel_change:
-          feed['pc'] = self._process_pc(sess)
-        if self.use_value_replay:
-          feed['vr'] = self._process_vr(sess)
-        if self.use_reward_prediction:
-          feed['rp'] = self._process_rp()
+        feed = self._data_phase_graphed(sess) if self.use_graphs else self._data_phase(sess)
+        feed['learning_rate'] = cur_learning_rate
       finally:
         self._rng_out()
       self.last_feed = feed
