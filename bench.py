@@ -196,7 +196,7 @@ def measure_agent(torch, dist, dev, rank, world, envs, updates, history=2000):
   applier = RMSPropApplier(7e-4, decay=0.99, momentum=0.0, epsilon=0.1, clip_norm=40.0)
   tr = Trainer(rank, net, 7e-4, None, applier, 'maze', '', True, True, True, True, 0.05, 0.001, 20, 20, 0.99, 0.9,
                history, 10 ** 9, str(dev), {'segnet_mode': 0}, (84, 84), True, 0, np.random.RandomState(1), 50.0, 0.0,
-               0.0, num_envs=envs, seeds=env_seeds(0xA3C, lo, hi), use_graphs=True)
+               0.0, num_envs=envs, seeds=env_seeds(0xA3C, lo, hi), use_graphs=True, obs_s2d=True)
   tr.prepare()
   t0 = time.perf_counter()
   while not tr.experience.is_full():

@@ -37,7 +37,8 @@ extern "C" {
 /* element type tags for observation / frame buffers */
 #define UNREAL_F32 0
 #define UNREAL_U8 1 /* 1.0 is stored as 255; loaders divide by 255 (lab/indoor/gym convention) */
-#define UNREAL_BF16 2 /* activations between the dense layers (K7) */
+#define UNREAL_BF16 2 /* activations between the dense layers (K7); as a maze obs_dtype: the frame in
+                         conv1's space-to-depth plane layout x'' [6][441][8] (see unreal_s2d_frames) */
 
 #define UNREAL_MAZE_GRID 7
 #define UNREAL_FRAME_HW 84

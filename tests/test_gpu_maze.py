@@ -180,3 +180,26 @@ def test_bad_arguments_fail_loudly(K):
     K.maze_step(st, torch.zeros(4, dtype=torch.int32))                         # host tensor
   rc = _lib.lib.unreal_maze_step(None, None, None, None, None, None, None, None, 0, None, None, 4, 0, None)
   assert rc == -1 and "non-null" in _lib.last_error()
+
+
+def test_s2d_render_equals_space_to_depth_of_the_f32_frame():
+  """obs_dtype bf16: K1 renders straight into conv1's plane layout; it must equal
+  unreal_s2d_frames of the f32 frame, for render and for step (with auto-reset)."""
+  from unreal_b200 import kernels as K
+  dev = torch.device("cuda", 0)
+  cells = torch.tensor([(x, y) for y in range(7) for x in range(7)], dtype=torch.int32, device=dev)
+  got = K.maze_render(cells, dtype=torch.bfloat16)
+  assert tuple(got.shape) == (49, 6, 441, 8)
+  want = K.s2d_frames(K.maze_render(cells, dtype=torch.float32))
+  assert torch.equal(got, want)
+  n = 300
+  g = torch.Generator(device=dev).manual_seed(0)
+  sa, sb = K.MazeState(n, dev), K.MazeState(n, dev)
+  oa = torch.empty(n, 84, 84, 3, device=dev); ob = torch.empty(n, 6, 441, 8, dtype=torch.bfloat16, device=dev)
+  pa = torch.empty(n, 20, 20, device=dev); pb = torch.empty(n, 20, 20, device=dev)
+  for _ in range(60):
+    act = torch.randint(0, 4, (n,), device=dev, dtype=torch.int32, generator=g)
+    ra, ta = K.maze_step(sa, act, obs=oa, pc=pa, auto_reset=True)
+    rb, tb = K.maze_step(sb, act, obs=ob, pc=pb, auto_reset=True)
+    assert torch.equal(ra, rb) and torch.equal(ta, tb) and torch.equal(pa, pb) and torch.equal(sa.pos, sb.pos)
+    assert torch.equal(ob, K.s2d_frames(oa))

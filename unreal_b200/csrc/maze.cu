@@ -326,6 +326,45 @@ __global__ void __launch_bounds__(kThreads) maze_cta_kernel(StepArgs a) {
   }
 }
 
+
+// ------------------------------------------------------------------------------------
+// x'' render: the frame directly in the conv1 kernels' input layout (csrc/conv_tcgen05.cu):
+// bf16 planes [6][441][8], x''[q][Y*21+X][e] = frame[4Y+dy, 4X+dx, c] with dy*12+dx*3+c = 8q+e.
+// A 4x4 pixel block lies inside one 12-pixel maze cell, so a plane row is one of three constant
+// 16-byte patterns (empty / wall: channel 0 / agent: channel 1).  42 336 B per frame instead of
+// 84 672 B of f32 plus a separate space-to-depth pass.
+// ------------------------------------------------------------------------------------
+template <bool kStep>
+__global__ void __launch_bounds__(256) maze_s2d_kernel(StepArgs a) {
+  __shared__ EnvInfo s_info;
+  const int tid = threadIdx.x;
+  const int e = blockIdx.x;
+  if (tid == 0) s_info = env_logic<kStep>(a, e);
+  __syncthreads();
+  const EnvInfo f = s_info;
+  if (!f.live) return;
+  if (a.pc != nullptr && tid >= 256 - kPcElems / 4) write_pc(a.pc + (size_t)e * kPcElems, f, tid - (256 - kPcElems / 4));
+  if (a.obs == nullptr) return;
+  uint4* out = reinterpret_cast<uint4*>(a.obs) + (size_t)e * (6 * 441);
+  for (int idx = tid; idx < 6 * 441; idx += 256) {
+    const int q = idx / 441, pix = idx - q * 441;
+    const int Y = pix / 21, X = pix - Y * 21;
+    const int cx = X / 3, cy = Y / 3;
+    const bool wall = (c_maze.wall_rows[cy] >> cx) & 1u;
+    const bool agent = (cx == f.rx) && (cy == f.ry);
+    const int base = (2 * q) % 3;                        // (8q) mod 3 = channel (mod 3) of element 0
+    uint32_t w[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int c0 = (base + 2 * k) % 3, c1 = (base + 2 * k + 1) % 3;     // walls: channel 0, agent: channel 1
+      const uint32_t lo = ((c0 == 0 && wall) || (c0 == 1 && agent)) ? 0x3f80u : 0u;
+      const uint32_t hi = ((c1 == 0 && wall) || (c1 == 1 && agent)) ? 0x3f80u : 0u;
+      w[k] = lo | (hi << 16);
+    }
+    __stcs(out + idx, make_uint4(w[0], w[1], w[2], w[3]));
+  }
+}
+
 // pixel change between arbitrary cell pairs (re-materialising maps of replayed frames)
 __global__ void __launch_bounds__(128) maze_pc_pairs_kernel(const int32_t* __restrict__ p0,
                                                             const int32_t* __restrict__ p1, float* pc, int m) {
@@ -358,6 +397,11 @@ static int launch_render(const StepArgs& a, int obs_dtype, cudaStream_t st) {
   if (a.n == 0) return UNREAL_OK;
   const int sms = sm_count();
   if (sms <= 0) return UNREAL_ECUDA;
+  if (obs_dtype == UNREAL_BF16) {
+    maze_s2d_kernel<kStep><<<a.n, 256, 0, st>>>(a);
+    UNREAL_LAUNCH_CHECK("maze_s2d_kernel");
+    return UNREAL_OK;
+  }
   // defaults = fastest measured on B200 (profiles/microbench_r1.md): f32 -> CTA per env with
   // 256 threads (99% of measured HBM peak), u8 -> warp per env.
   int variant = get_tunable("maze_render_variant", -1);
@@ -457,7 +501,8 @@ extern "C" int unreal_maze_step(int32_t* pos, const int32_t* action, const uint8
   UNREAL_REQUIRE(n >= 0, "unreal_maze_step: n < 0");
   UNREAL_REQUIRE(pos && action && reward && terminal && last_action && last_reward,
                  "unreal_maze_step: pos/action/reward/terminal/last_action/last_reward must be non-null");
-  UNREAL_REQUIRE(obs_dtype == UNREAL_F32 || obs_dtype == UNREAL_U8, "unreal_maze_step: bad obs_dtype %d", obs_dtype);
+  UNREAL_REQUIRE(obs_dtype == UNREAL_F32 || obs_dtype == UNREAL_U8 || obs_dtype == UNREAL_BF16,
+                 "unreal_maze_step: bad obs_dtype %d", obs_dtype);
   UNREAL_REQUIRE(aligned16(obs) && aligned16(pc), "unreal_maze_step: obs and pc must be 16-byte aligned");
   int rc = ensure_map();
   if (rc) return rc;
@@ -467,7 +512,8 @@ extern "C" int unreal_maze_step(int32_t* pos, const int32_t* action, const uint8
 
 extern "C" int unreal_maze_render(const int32_t* pos, void* obs, int obs_dtype, int m, void* stream) {
   UNREAL_REQUIRE(pos && obs && m >= 0, "unreal_maze_render: null argument or m < 0");
-  UNREAL_REQUIRE(obs_dtype == UNREAL_F32 || obs_dtype == UNREAL_U8, "unreal_maze_render: bad obs_dtype %d", obs_dtype);
+  UNREAL_REQUIRE(obs_dtype == UNREAL_F32 || obs_dtype == UNREAL_U8 || obs_dtype == UNREAL_BF16,
+                 "unreal_maze_render: bad obs_dtype %d", obs_dtype);
   UNREAL_REQUIRE(aligned16(obs), "unreal_maze_render: obs must be 16-byte aligned");
   int rc = ensure_map();
   if (rc) return rc;

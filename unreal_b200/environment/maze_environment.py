@@ -34,7 +34,7 @@ class BatchedMazeEnvironment(environment.Environment):
       self._walls = np.frombuffer(walls, np.uint8).reshape(7, 7).astype(bool)
       self.state = K.MazeState(self.num_envs, self.device)
       n = self.num_envs
-      self._obs = torch.empty(n, 84, 84, 3, dtype=obs_dtype, device=self.device)
+      self._obs = torch.empty(n, *K.obs_shape(obs_dtype), dtype=obs_dtype, device=self.device)
       self._pc = torch.empty(n, 20, 20, dtype=torch.float32, device=self.device)
       self._reward = torch.empty(n, dtype=torch.float32, device=self.device)
       self._terminal = torch.empty(n, dtype=torch.uint8, device=self.device)

@@ -67,10 +67,16 @@ def maze_step(state, action, obs=None, pc=None, reward=None, terminal=None, fram
   return reward, terminal
 
 
+def obs_shape(dtype):
+  """Per-frame shape of a maze observation buffer: [84,84,3] for f32 / u8, the space-to-depth planes
+  [6,441,8] for bf16 (the layout conv1 consumes directly)."""
+  return (6, 441, 8) if dtype == torch.bfloat16 else (FRAME, FRAME, 3)
+
+
 def maze_render(pos, out=None, dtype=torch.float32):
   m = pos.shape[0]
   if out is None:
-    out = torch.empty(m, FRAME, FRAME, 3, dtype=dtype, device=pos.device)
+    out = torch.empty(m, *obs_shape(dtype), dtype=dtype, device=pos.device)
   call("unreal_maze_render", ptr(pos, torch.int32, "pos"), ptr(out), _lib.dtype_tag(out), m, stream_ptr())
   return out
 

@@ -65,11 +65,17 @@ class ConvFn(torch.autograd.Function):
 
   @staticmethod
   def forward(ctx, x, w16, w32, b32, kh, kw, stride, taps):
-    s, h, w, c = x.shape
+    pre_s2d = x.dtype == torch.bfloat16 and tuple(x.shape[1:]) == (6, 441, 8)   # frames already as x'' planes
+    s, h, w, c = (x.shape[0], 84, 84, 3) if pre_s2d else x.shape
     oh, ow = (h - kh) // stride + 1, (w - kw) // stride + 1
     o = w16.shape[1]
     xpp = None
-    if taps is not None and (h, w, c, kh, kw, stride, o) == (84, 84, 3, 8, 8, 4, 16) and x.dtype in (torch.float32, torch.uint8):
+    if pre_s2d:
+      if taps is None:
+        raise RuntimeError("space-to-depth frames need the fused conv1 kernel (UnrealModel.fused_conv)")
+      xpp = x
+      y = K.conv_fwd(xpp, 1, taps, b32).view(s * oh * ow, o)
+    elif taps is not None and (h, w, c, kh, kw, stride, o) == (84, 84, 3, 8, 8, 4, 16) and x.dtype in (torch.float32, torch.uint8):
       xpp = K.s2d_frames(x)
       y = K.conv_fwd(xpp, 1, taps, b32).view(s * oh * ow, o)
     elif taps is not None and (h, w, c, kh, kw, stride, o) == (20, 20, 16, 4, 4, 2, 32) and x.dtype == torch.bfloat16:

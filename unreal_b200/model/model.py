@@ -178,7 +178,7 @@ class UnrealModel(object):
   def _tower(self, p32, images, lar, c0, h0):
     """encoder + fc1 + LSTM unroll.  images [T,N,84,84,3], lar [T,N,A+1+G] -> h [T,N,256] f32."""
     t, n = images.shape[:2]
-    h2 = self._encoder(p32, images.reshape(t * n, 84, 84, 3))
+    h2 = self._encoder(p32, images.reshape(t * n, *images.shape[2:]))
     xin = self._lstm_input(p32, h2, lar, t, n)
     return LstmFn.apply(xin, self.v16["lstm_kernel"], p32["lstm_kernel"], p32["lstm_bias"], c0, h0, self.lstm_in), h2
 
@@ -231,7 +231,7 @@ class UnrealModel(object):
     if not isinstance(img, torch.Tensor):
       img = torch.as_tensor(np.asarray(img, dtype=np.float32))
     img = img.to(self._device)
-    return img.reshape(1, -1, 84, 84, 3)
+    return img.reshape(1, -1, *K.obs_shape(img.dtype))
 
   def _lar(self, last_action_reward, n):
     lar = last_action_reward
@@ -287,7 +287,7 @@ class UnrealModel(object):
 
   def _rp_c(self, p32, images):
     n = images.shape[0]
-    h2 = self._encoder(p32, images.reshape(n * 3, 84, 84, 3))
+    h2 = self._encoder(p32, images.reshape(n * 3, *images.shape[2:]))
     logits = h2.reshape(n, 7776).float() @ p32["W_rp_fc1"] + p32["b_rp_fc1"]
     return torch.softmax(logits, dim=-1)
 
@@ -348,10 +348,13 @@ class UnrealModel(object):
     out = {'base': dict(images=b['si'], lar=b['last_action_rewards'], a=b['a'], adv=b['adv'], R=b['R'],
                         mask=b['active'], c0=c0, h0=h0)}
 
+    dt = b['si'].dtype                      # replayed frames are rendered in the rollout frames' format
+    shp = K.obs_shape(dt)
+
     def seq(f):
       n, l = f['pos'].shape[:2]
       pos = f['pos'].transpose(0, 1).contiguous().view(l * n, 2)
-      images = K.maze_render(pos).view(l, n, 84, 84, 3)
+      images = K.maze_render(pos, dtype=dt).view(l, n, *shp)
       mask = (torch.arange(l, device=pos.device).view(l, 1) < f['length'].view(1, n))
       return dict(images=images, lar=f['last_action_reward'].transpose(0, 1).contiguous(), mask=mask)
 
@@ -369,7 +372,7 @@ class UnrealModel(object):
     if 'rp' in feed:
       f = feed['rp']
       n = f['pos'].shape[0]
-      out['rp'] = dict(images=K.maze_render(f['pos'].contiguous().view(n * 3, 2)).view(n, 3, 84, 84, 3), c=f['c'])
+      out['rp'] = dict(images=K.maze_render(f['pos'].contiguous().view(n * 3, 2), dtype=dt).view(n, 3, *shp), c=f['c'])
     return out
 
   def update(self, feed, learning_rate, grad_applier, grad_scale=None):

@@ -46,7 +46,7 @@ class Trainer(object):
                pixel_change_lambda, entropy_beta, local_t_max, n_step_TD, gamma, gamma_pc,
                experience_history_size, max_global_time_step, device, segnet_param_dict, image_shape,
                is_training, n_classes, random_state, termination_time, segnet_lambda, dropout,
-               num_envs=1, seeds=None, verbose=False, use_graphs=False):
+               num_envs=1, seeds=None, verbose=False, use_graphs=False, obs_s2d=False):
     _lib.require_device()
     self.thread_index = thread_index
     self.learning_rate_input = learning_rate_input
@@ -106,6 +106,9 @@ class Trainer(object):
     self.last_feed = None
     self._ring_full = False
     self.use_graphs = bool(use_graphs)      # capture the rollout + sampling phase into one CUDA graph
+    # obs_s2d: K1 renders frames straight into conv1's space-to-depth bf16 plane layout (42 KB per
+    # frame, no f32 frame and no separate s2d pass); needs a network with the fused conv1 kernel
+    self.obs_dtype = torch.bfloat16 if obs_s2d else torch.float32
     self._graph = None
 
   # -- RandomState hand-over for the single-env drop-in case ---------------------------------
@@ -122,12 +125,12 @@ class Trainer(object):
     """trainer.py:132-135."""
     self.environment = Environment.create_environment(
         self.env_type, self.env_name, self.termination_time,
-        env_args={'num_envs': self.num_envs, 'device': self.device, 'auto_reset': True},
+        env_args={'num_envs': self.num_envs, 'device': self.device, 'auto_reset': True, 'obs_dtype': self.obs_dtype},
         thread_index=self.thread_index)
     n, d, T = self.num_envs, self.device, self.n_step_TD
     A = self.action_size
     # rollout buffers: obs has T+1 slots (state before each action + the bootstrap state)
-    self._obs = torch.empty(T + 1, n, 84, 84, 3, dtype=torch.float32, device=d)
+    self._obs = torch.zeros(T + 1, n, *K.obs_shape(self.obs_dtype), dtype=self.obs_dtype, device=d)
     self._pos = torch.zeros(T + 1, n, 2, dtype=torch.int32, device=d)
     self._lar = torch.zeros(T, n, A + 1, dtype=torch.float32, device=d)
     self._act = torch.zeros(T, n, dtype=torch.int32, device=d)
@@ -229,7 +232,7 @@ class Trainer(object):
     rec = K.frame_unpack(last_rec, fields=("action", "reward"))
     boot_lar = self._last_action_reward(rec["action"], rec["reward"])
     boot_obs = self._obs[1:].gather(
-        0, (lengths.to(torch.int64) - 1).clamp_(min=0).view(1, n, 1, 1, 1).expand(1, n, 84, 84, 3))[0]
+        0, (lengths.to(torch.int64) - 1).clamp_(min=0).view(1, n, 1, 1, 1).expand(1, n, *self._obs.shape[2:]))[0]
     # every env's current frame (the reset frame for ended envs) goes back into the env's own
     # persistent frame buffer, which is where the next rollout starts reading (graph-replay safe)
     env._obs.copy_(boot_obs)
@@ -250,7 +253,7 @@ class Trainer(object):
     take = lambda x: x.gather(1, idx_last.view(-1, *([1] * (x.dim() - 1))).expand(-1, 1, *x.shape[2:]))[:, 0]  # noqa: E731
     boot_pos = take(f["pos0"]).contiguous()
     boot_lar = self._last_action_reward(take(f["last_action"]), take(f["last_reward"]))
-    boot_state = {'image': K.maze_render(boot_pos), 'pos': boot_pos}
+    boot_state = {'image': K.maze_render(boot_pos, dtype=self.obs_dtype), 'pos': boot_pos}
     lar = self._last_action_reward(f["last_action"].reshape(-1), f["last_reward"].reshape(-1))
     lar = lar.view(self.num_envs, L, -1)
     return start, length, n_batch, f, boot_state, boot_lar, lar
