@@ -52,7 +52,7 @@ def parse():
   p.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
   p.add_argument("--no-cpu-baseline", action="store_true")
   p.add_argument("--no-agent", action="store_true", help="skip the full-agent (configs[2]) side measurement")
-  p.add_argument("--agent-envs", type=int, default=2048, help="envs per GPU of the full-agent side measurement")
+  p.add_argument("--agent-envs", type=int, default=8192, help="envs per GPU of the full-agent side measurement")
   p.add_argument("--agent-updates", type=int, default=6)
   return p.parse_args()
 

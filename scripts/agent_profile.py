@@ -21,7 +21,7 @@ def main():
   applier = RMSPropApplier(7e-4, decay=0.99, momentum=0.0, epsilon=0.1, clip_norm=40.0)
   tr = Trainer(0, net, 7e-4, None, applier, 'maze', '', True, True, True, True, 0.05, 0.001, 20, 20, 0.99, 0.9, 100,
                10 ** 8, "cuda:0", {'segnet_mode': 0}, (84, 84), True, 0, np.random.RandomState(1), 50.0, 0.0, 0.0,
-               num_envs=n, seeds=np.arange(n) + 11)
+               num_envs=n, seeds=np.arange(n) + 11, obs_s2d=True)
   tr.prepare()
   while not tr.experience.is_full():
     tr.process(None, 0)
