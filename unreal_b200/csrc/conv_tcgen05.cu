@@ -269,6 +269,8 @@ __global__ void __launch_bounds__(256) s2d_frames_kernel(const T* __restrict__ i
 // and rows >= 105 are garbage accumulator rows the epilogue skips.  HBM/L2 traffic per frame:
 // 42 KB of x'' in (each byte once) + 12.8 KB of h1 out.
 constexpr int kC1Stages = 12;
+constexpr int kC1Acc = 8;        // TMEM accumulator buffers (32 columns each): the MMA -> epilogue -> MMA hand-back
+                                 // costs ~2 us of barrier latency per item, so 2 buffers capped the kernel
 constexpr int kC1PlaneBytes = 126 * 16;
 constexpr int kC1BoxBytes = 6 * kC1PlaneBytes;      // 12096
 constexpr int kC1StageBytes = 12288;
@@ -286,18 +288,18 @@ conv1_fwd_tcgen05_kernel(const __nv_bfloat16* __restrict__ xpp, const __nv_bfloa
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kC1Stages + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kC1Stages + a); };
-  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kC1Stages + 2 + a); };
-  const uint32_t w_bar = bar_base + 8u * (2 * kC1Stages + 4);
-  const uint32_t tmem_slot = bar_base + 8u * (2 * kC1Stages + 5);
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kC1Stages + kC1Acc + a); };
+  const uint32_t w_bar = bar_base + 8u * (2 * kC1Stages + 2 * kC1Acc);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kC1Stages + 2 * kC1Acc + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < kC1Stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    for (int a = 0; a < kC1Acc; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
     mbar_init(w_bar, 1);
     fence_mbar_init();
   } else if (warp == 2) {
-    tmem_alloc<64>(tmem_slot);
+    tmem_alloc<kC1Acc * 32>(tmem_slot);
   }
   fence_before_sync();
   __syncthreads();
@@ -331,6 +333,8 @@ conv1_fwd_tcgen05_kernel(const __nv_bfloat16* __restrict__ xpp, const __nv_bfloa
     if (lane == 0) {
       // ===== MMA issuer: 4 taps x 3 UMMA (128 x 16 x 16) on the one resident tile =====
       constexpr uint32_t idesc = idesc_bf16_f32(128, 16, false, false);
+      constexpr uint32_t desc_hi = (128u >> 4) | (1u << 14);        // SBO = 128 B, descriptor version 1, no swizzle
+      const uint32_t w_lo0 = (w_smem >> 4) | ((256u >> 4) << 16);  // filter tiles: LBO = 256 B
       mbar_wait(w_bar, 0);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
@@ -339,19 +343,20 @@ conv1_fwd_tcgen05_kernel(const __nv_bfloat16* __restrict__ xpp, const __nv_bfloa
         mbar_wait(full_bar(stage), phase);
         fence_after_sync();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * 32);
-        const uint32_t sa = a_smem + stage * kC1StageBytes;
+        // descriptor low words: (address >> 4) | LBO field; every offset below is a multiple of 16 bytes
+        const uint32_t a_lo0 = ((a_smem + stage * kC1StageBytes) >> 4) | ((uint32_t)(kC1PlaneBytes >> 4) << 16);
 #pragma unroll
         for (int tap = 0; tap < 4; ++tap) {
-          const uint32_t shift = (uint32_t)((tap >> 1) * 21 + (tap & 1)) * 16u;
+          const uint32_t shift16 = (uint32_t)((tap >> 1) * 21 + (tap & 1));
 #pragma unroll
           for (int j = 0; j < 3; ++j)
-            mma_f16(tmem_d, smem_desc_none(sa + 2 * j * kC1PlaneBytes + shift, kC1PlaneBytes, 128),
-                    smem_desc_none(w_smem + tap * 1536 + 2 * j * 256, 256, 128), idesc, (tap > 0 || j > 0) ? 1u : 0u);
+            mma_f16_lohi(tmem_d, a_lo0 + (uint32_t)(2 * j * kC1PlaneBytes >> 4) + shift16, desc_hi,
+                         w_lo0 + (uint32_t)((tap * 1536 + 2 * j * 256) >> 4), desc_hi, idesc, (tap > 0 || j > 0) ? 1u : 0u);
         }
         mma_commit(empty_bar(stage));
         mma_commit(tfull_bar(acc));
         if (++stage == kC1Stages) { stage = 0; phase ^= 1u; }
-        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        if (++acc == kC1Acc) { acc = 0; acc_phase ^= 1u; }
       }
     }
   } else {
@@ -385,7 +390,7 @@ conv1_fwd_tcgen05_kernel(const __nv_bfloat16* __restrict__ xpp, const __nv_bfloa
         dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
       }
-      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      if (++acc == kC1Acc) { acc = 0; acc_phase ^= 1u; }
     }
   }
   __syncwarp();
@@ -393,7 +398,7 @@ conv1_fwd_tcgen05_kernel(const __nv_bfloat16* __restrict__ xpp, const __nv_bfloa
   __syncthreads();
   if (warp == 2) {
     fence_after_sync();
-    tmem_dealloc<64>(tmem_base);
+    tmem_dealloc<kC1Acc * 32>(tmem_base);
   }
 }
 
@@ -499,14 +504,17 @@ conv1_wgrad_tcgen05_kernel(const __nv_bfloat16* __restrict__ xpp, const __nv_bfl
         mbar_wait(full_bar(stage), phase);
         fence_after_sync();
         const uint32_t sx = smem_base + stage * kWgStageBytes, sd = sx + kWgDyOff;
+        // MN-major un-swizzled descriptors: LBO = 128 B (next 8 pixel rows), SBO = plane stride
+        const uint32_t a_lo0 = (sd >> 4) | ((128u >> 4) << 16), b_lo0 = (sx >> 4) | ((128u >> 4) << 16);
+        constexpr uint32_t a_hi = ((uint32_t)kWgDyPlane >> 4) | (1u << 14), b_hi = ((uint32_t)kC1PlaneBytes >> 4) | (1u << 14);
 #pragma unroll
         for (int ks = 0; ks < 7; ++ks) {
           // four independent accumulation chains (one per tap) are interleaved
 #pragma unroll
           for (int t = 0; t < 4; ++t) {
-            const uint32_t shift = (uint32_t)((t >> 1) * 21 + (t & 1)) * 16u;
-            mma_f16(tmem_base + (uint32_t)(t * 64), smem_desc_none(sd + ks * 256, 128, kWgDyPlane),
-                    smem_desc_none(sx + shift + ks * 256, 128, kC1PlaneBytes), idesc, (first && ks == 0) ? 0u : 1u);
+            const uint32_t shift16 = (uint32_t)((t >> 1) * 21 + (t & 1));
+            mma_f16_lohi(tmem_base + (uint32_t)(t * 64), a_lo0 + (uint32_t)(ks * 16), a_hi, b_lo0 + shift16 + (uint32_t)(ks * 16), b_hi,
+                         idesc, (first && ks == 0) ? 0u : 1u);
           }
         }
         first = false;
