@@ -98,6 +98,7 @@ class Trainer(object):
     self.local_t = 0
     self.initial_learning_rate = initial_learning_rate
     self.episode_reward = torch.zeros(n, dtype=torch.float32, device=d)
+    self.episode_stats = torch.zeros(2, dtype=torch.float64, device=d)   # [episodes finished, sum of scores]
     self.prev_local_t = -1
     self.prev_local_t_loss = 0
     self.sr_size = 50
@@ -223,6 +224,10 @@ class Trainer(object):
       # CPU keeps enqueueing ahead of the GPU (an all-terminated batch just idles through the steps)
       term_now = self._term[t] & active
       ended |= term_now
+      # episode statistics (the reference prints the score of every finished episode, :283-291)
+      tn = term_now.to(torch.float32)
+      self.episode_stats[0] += tn.sum()                              # finished episodes
+      self.episode_stats[1] += (self.episode_reward * tn).sum()      # sum of their scores
       net.reset_state(term_now)                # :293
       self.episode_reward.mul_(1 - term_now.to(torch.float32))
       active = active & (1 - term_now)
