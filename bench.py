@@ -244,6 +244,56 @@ def measure_agent(torch, dist, dev, rank, world, envs, updates, history=2000):
           "finite": bool(all(np.isfinite(v) for v in losses.values())), "grad_norm": losses.get("grad_norm"),
           "peak_mem_gb": mem, "timing": "CUDA events around %d Trainer.process() calls, max over ranks" % updates}
 
+
+def agent_cpu_baseline(envs=4, seconds=10.0):
+  """the reference algorithm with a PyTorch-CPU learner (TensorFlow cannot run here):
+  the oracle's env + replay + target path feeding oracle/model_oracle.py's forward/backward and the
+  numpy RMSProp, all host cores through torch's intra-op threads.  Bounded sample."""
+  import numpy as np
+  import torch
+  from oracle import model_oracle as MO, unreal_oracle as O, cpu_path
+  cores = cpu_path.host_cores()
+  torch.set_num_threads(cores)
+  A, T = 4, 20
+  params = MO.init_params(A, seed=0)
+  oracle = MO.ModelOracle(params, A, 0, 0.05, 0.001)
+  rs = np.random.RandomState(0)
+  mazes = [O.MazeOracle() for _ in range(envs)]
+
+  def frames_for(L):
+    out = np.zeros((L, envs, 84, 84, 3), np.float32)
+    for t in range(L):
+      for e, m in enumerate(mazes):
+        img, r, term, pc = m.process(int(rs.randint(4)))
+        if term:
+          m.reset()
+        out[t, e] = m.last_state['image']
+    return torch.from_numpy(out)
+
+  def lar(L):
+    x = torch.zeros(L, envs, A + 1); x[..., 0] = 1.0
+    return x
+
+  def one_update():
+    a = torch.zeros(T, envs, A); a[..., 1] = 1.0
+    feed = {"base": dict(images=frames_for(T), lar=lar(T), a=a, adv=torch.randn(T, envs), R=torch.randn(T, envs),
+                         mask=torch.ones(T, envs), c0=torch.zeros(envs, 256), h0=torch.zeros(envs, 256)),
+            "pc": dict(images=frames_for(T), lar=lar(T), a=a, R=torch.rand(T, envs, 20, 20), mask=torch.ones(T, envs)),
+            "vr": dict(images=frames_for(T), lar=lar(T), R=torch.randn(T, envs), mask=torch.ones(T, envs)),
+            "rp": dict(images=frames_for(3).permute(1, 0, 2, 3, 4).contiguous(), c=torch.eye(3)[torch.zeros(envs, dtype=torch.long)])}
+    total, parts, grads = oracle.loss_and_grads(feed)
+    for k, g in grads.items():      # shared RMSProp, rmsprop_applier.py:83-93 (no slots kept: timing only)
+      params[k] -= 7e-4 * g / torch.sqrt(g * g * 0.01 + 1.0 * 0.99 + 0.1)
+  one_update()
+  t0 = time.perf_counter(); n = 0
+  while time.perf_counter() - t0 < seconds:
+    one_update(); n += 1
+  wall = time.perf_counter() - t0
+  return {"value": n * envs * T / wall, "unit": UNIT, "cores": cores, "kind": "port",
+          "sample": "%d updates of %d envs x %d steps: numpy maze + PyTorch-CPU fp32 model fwd/bwd (oracle/model_oracle.py, "
+                    "%d torch threads) + RMSProp in %.1f s -- the stand-in for the reference's TensorFlow CPU trainer"
+                    % (n, envs, T, cores, wall)}
+
 # --------------------------------------------------------------------------- B200 arm
 def run_b200(args):
   import torch
@@ -374,6 +424,11 @@ def run_b200(args):
       except Exception:
         pass
     if agent is not None:
+      if not args.no_cpu_baseline and world == 1 and "error" not in agent:
+        try:
+          agent["cpu_baseline"] = agent_cpu_baseline()
+        except Exception as e:
+          agent["cpu_baseline"] = {"error": repr(e)[:200]}
       line["agent"] = agent
     if not args.no_cpu_baseline and world == 1:
       from oracle import cpu_path
