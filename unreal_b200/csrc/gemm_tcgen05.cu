@@ -344,15 +344,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
 // Each CTA loads its own 128 rows of A and its own 128 of the tile's 256 B rows (so operand traffic
 // from L2 per SM is half that of two independent 128x256 tiles), the leader CTA issues the MMAs for
 // both, every CTA's TMEM receives its 128 accumulator rows and runs its own epilogue.
-constexpr int k2Stages = 6;
-constexpr int k2StageBytes = 2 * kBM * kBK * 2;   // A 16 KB + B half 16 KB
-constexpr int k2SmemBytes = k2Stages * k2StageBytes + 1024 + 4 * 2 * 4096 + 1024;
+// BN = 256: A 16 KB + B half 16 KB per stage, 6 stages; BN = 128 (256 x 128 tiles, used when the
+// 256-wide tiling would leave the last wave of CTA pairs mostly empty): B half 8 KB, 8 stages.
+template <int BN> struct Cfg2 {
+  static constexpr int kStages = BN == 256 ? 6 : 8;
+  static constexpr int kStageBytes = kBM * kBK * 2 + (BN / 2) * kBK * 2;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 4 * 2 * 4096 + 1024;
+  static constexpr int kTmemCols = 2 * BN;
+};
 
-template <bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm2sm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                        const __grid_constant__ CUtensorMap tma_c, const GemmArgs g) {
-  constexpr int BN = 256;
+  constexpr int k2Stages = Cfg2<BN>::kStages, k2StageBytes = Cfg2<BN>::kStageBytes;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = smem_base + k2Stages * k2StageBytes;
@@ -379,7 +384,7 @@ gemm2sm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 8); }
     fence_mbar_init();
   } else if (warp == 2) {
-    tmem_alloc_2sm<512>(tmem_slot);
+    tmem_alloc_2sm<Cfg2<BN>::kTmemCols>(tmem_slot);
   }
   fence_before_sync();
   cluster_sync_all();                 // both CTAs' barriers exist before any remote arrive / TMA signal
@@ -475,7 +480,7 @@ gemm2sm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
   cluster_sync_all();                 // the peer may still be read by the leader's MMAs / signal its barriers
   if (warp == 2) {
     fence_after_sync();
-    tmem_dealloc_2sm<512>(tmem_base);
+    tmem_dealloc_2sm<Cfg2<BN>::kTmemCols>(tmem_base);
   }
 }
 
@@ -562,21 +567,21 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
   return UNREAL_OK;
 }
 
-template <bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN>
 static int launch_gemm_2sm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmArgs& g,
                            cudaStream_t st) {
   static bool configured = false;
-  auto kern = gemm2sm_tcgen05_kernel<A_MN, B_MN>;
+  auto kern = gemm2sm_tcgen05_kernel<BN, A_MN, B_MN>;
   if (!configured) {
-    UNREAL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, k2SmemBytes));
+    UNREAL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<BN>::kSmemBytes));
     configured = true;
   }
-  const int num_m = (g.m + 2 * kBM - 1) / (2 * kBM), num_n = (g.n + 255) / 256;
+  const int num_m = (g.m + 2 * kBM - 1) / (2 * kBM), num_n = (g.n + BN - 1) / BN;
   const int64_t work = (int64_t)num_m * num_n * g.split_k;
   const int sms = sm_count();
   if (sms <= 0) return UNREAL_ECUDA;
   const int clusters = (int)(work < sms / 2 ? work : sms / 2);
-  kern<<<2 * clusters, kGemmThreads, k2SmemBytes, st>>>(ta, tb, tc, g);
+  kern<<<2 * clusters, kGemmThreads, Cfg2<BN>::kSmemBytes, st>>>(ta, tb, tc, g);
   UNREAL_LAUNCH_CHECK("gemm2sm_tcgen05_kernel");
   return UNREAL_OK;
 }
@@ -614,13 +619,21 @@ extern "C" int unreal_gemm_bf16(const void* a, int64_t lda, int a_mn_major, cons
   // epilogue, where independent CTAs measured faster (profiles/r1_gemm_bench_v4_2sm.jsonl)
   int use_2sm = (n > 128) && work2 >= sm_count() / 2 && kb_total >= 16;
   { int forced = get_tunable("gemm_2sm", -1); if (forced == 0) use_2sm = 0; else if (forced == 1 && n > 128) use_2sm = 1; }
-  if (use_2sm) bn = 256;
+  if (use_2sm) {
+    // 256 x 256 tiles.  256 x 128 tiles fill the last wave of the 74 CTA pairs better (fc1: 8.6 waves
+    // instead of 4.3) but measured SLOWER everywhere (fc1 830 vs 1134 TFLOP/s, 4096^3 920 vs 1303,
+    // profiles/r1_gemm_bench_v5_2sm_bn128.jsonl): operand traffic per flop from L2 is what bounds this
+    // kernel, not the tail.  The narrow variant stays selectable with the tunable for experiments.
+    bn = 256;
+    int forced = get_tunable("gemm_2sm_bn", 0);
+    if (forced == 128 || forced == 256) bn = forced;
+  }
   CUtensorMap ta, tb, tc;
   int rc;
   if (a_mn_major) rc = make_tma_2d(&ta, a, k, m, lda, kBK, false); else rc = make_tma_2d(&ta, a, m, k, lda, kBM, false);
   if (rc != UNREAL_OK) return rc;
   if (b_mn_major) rc = make_tma_2d(&tb, b, k, n, ldb, kBK, false);
-  else rc = make_tma_2d(&tb, b, n, k, ldb, use_2sm ? 128 : bn, false);   // a CTA of a pair loads half the B rows
+  else rc = make_tma_2d(&tb, b, n, k, ldb, use_2sm ? bn / 2 : bn, false);   // a CTA of a pair loads half the B rows
   if (rc != UNREAL_OK) return rc;
   const bool c_bf16 = c_dtype == UNREAL_GEMM_OUT_BF16;
   // TMA epilogue needs a 16-byte row pitch; odd leading dimensions fall back to element stores
@@ -634,8 +647,13 @@ extern "C" int unreal_gemm_bf16(const void* a, int64_t lda, int a_mn_major, cons
   GemmArgs g{c, bias, add, ldc, m, n, k, split_k, c_bf16 ? 1 : 0, relu ? 1 : 0, accumulate ? 1 : 0, tma_store};
   cudaStream_t st = as_stream(stream);
   if (use_2sm) {
-    if (a_mn_major) return b_mn_major ? launch_gemm_2sm<true, true>(ta, tb, tc, g, st) : launch_gemm_2sm<true, false>(ta, tb, tc, g, st);
-    return b_mn_major ? launch_gemm_2sm<false, true>(ta, tb, tc, g, st) : launch_gemm_2sm<false, false>(ta, tb, tc, g, st);
+#define UNREAL_GEMM2_CASE(BN_, AMN_, BMN_) \
+  if (bn == BN_ && (a_mn_major != 0) == AMN_ && (b_mn_major != 0) == BMN_) return launch_gemm_2sm<BN_, AMN_, BMN_>(ta, tb, tc, g, st);
+    UNREAL_GEMM2_CASE(256, false, false) UNREAL_GEMM2_CASE(256, false, true)
+    UNREAL_GEMM2_CASE(256, true, false) UNREAL_GEMM2_CASE(256, true, true)
+    UNREAL_GEMM2_CASE(128, false, false) UNREAL_GEMM2_CASE(128, false, true)
+    UNREAL_GEMM2_CASE(128, true, false) UNREAL_GEMM2_CASE(128, true, true)
+#undef UNREAL_GEMM2_CASE
   }
 #define UNREAL_GEMM_CASE(BN_, AMN_, BMN_) \
   if (bn == BN_ && (a_mn_major != 0) == AMN_ && (b_mn_major != 0) == BMN_) return launch_gemm<BN_, AMN_, BMN_>(ta, tb, tc, g, st);
