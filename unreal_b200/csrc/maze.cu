@@ -346,22 +346,34 @@ __global__ void __launch_bounds__(256) maze_s2d_kernel(StepArgs a) {
   if (a.pc != nullptr && tid >= 256 - kPcElems / 4) write_pc(a.pc + (size_t)e * kPcElems, f, tid - (256 - kPcElems / 4));
   if (a.obs == nullptr) return;
   uint4* out = reinterpret_cast<uint4*>(a.obs) + (size_t)e * (6 * 441);
-  for (int idx = tid; idx < 6 * 441; idx += 256) {
-    const int q = idx / 441, pix = idx - q * 441;
+  // a thread owns pixels tid and tid + 256 of every plane: classify them once (bit0 wall, bit1 agent) ...
+  int kind[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int pix = tid + h * 256;
     const int Y = pix / 21, X = pix - Y * 21;
     const int cx = X / 3, cy = Y / 3;
-    const bool wall = (c_maze.wall_rows[cy] >> cx) & 1u;
-    const bool agent = (cx == f.rx) && (cy == f.ry);
-    const int base = (2 * q) % 3;                        // (8q) mod 3 = channel (mod 3) of element 0
-    uint32_t w[4];
+    kind[h] = pix < 441 ? (int)((c_maze.wall_rows[cy] >> cx) & 1u) | (((cx == f.rx) && (cy == f.ry)) ? 2 : 0) : -1;
+  }
+  // ... then per plane the 16-byte row is one of four constants: element i of plane q is channel
+  // (8q + i) mod 3; walls set channel 0, the agent channel 1
+#pragma unroll
+  for (int q = 0; q < 6; ++q) {
+    const int base = (2 * q) % 3;
+    uint32_t wl[4], ag[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const int c0 = (base + 2 * k) % 3, c1 = (base + 2 * k + 1) % 3;     // walls: channel 0, agent: channel 1
-      const uint32_t lo = ((c0 == 0 && wall) || (c0 == 1 && agent)) ? 0x3f80u : 0u;
-      const uint32_t hi = ((c1 == 0 && wall) || (c1 == 1 && agent)) ? 0x3f80u : 0u;
-      w[k] = lo | (hi << 16);
+      const int c0 = (base + 2 * k) % 3, c1 = (base + 2 * k + 1) % 3;
+      wl[k] = (c0 == 0 ? 0x3f80u : 0u) | (c1 == 0 ? 0x3f800000u : 0u);
+      ag[k] = (c0 == 1 ? 0x3f80u : 0u) | (c1 == 1 ? 0x3f800000u : 0u);
     }
-    __stcs(out + idx, make_uint4(w[0], w[1], w[2], w[3]));
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      if (kind[h] < 0) continue;
+      const uint32_t mw = (kind[h] & 1) ? 0xffffffffu : 0u, ma = (kind[h] & 2) ? 0xffffffffu : 0u;
+      __stcs(out + q * 441 + tid + h * 256, make_uint4((wl[0] & mw) | (ag[0] & ma), (wl[1] & mw) | (ag[1] & ma),
+                                                       (wl[2] & mw) | (ag[2] & ma), (wl[3] & mw) | (ag[3] & ma)));
+    }
   }
 }
 
@@ -408,10 +420,18 @@ static int launch_render(const StepArgs& a, int obs_dtype, cudaStream_t st) {
   if (variant < 0) variant = (obs_dtype == UNREAL_U8 && a.obs != nullptr) ? 2 : 0;
   if (a.obs == nullptr && variant == 1) variant = 0;  // nothing to stage through shared memory
   if (variant == 2) {
-    constexpr int kWarps = 4;
-    int grid = (a.n + kWarps - 1) / kWarps;
-    if (obs_dtype == UNREAL_F32) maze_warp_kernel<float, kStep, kWarps><<<grid, kWarps * 32, 0, st>>>(a);
-    else maze_warp_kernel<uint8_t, kStep, kWarps><<<grid, kWarps * 32, 0, st>>>(a);
+    const int warps = get_tunable("maze_warps_per_cta", 4);
+    if (obs_dtype == UNREAL_F32) {
+      maze_warp_kernel<float, kStep, 4><<<(a.n + 3) / 4, 128, 0, st>>>(a);
+    } else if (warps == 16) {
+      maze_warp_kernel<uint8_t, kStep, 16><<<(a.n + 15) / 16, 512, 0, st>>>(a);
+    } else if (warps == 8) {
+      maze_warp_kernel<uint8_t, kStep, 8><<<(a.n + 7) / 8, 256, 0, st>>>(a);
+    } else if (warps == 2) {
+      maze_warp_kernel<uint8_t, kStep, 2><<<(a.n + 1) / 2, 64, 0, st>>>(a);
+    } else {
+      maze_warp_kernel<uint8_t, kStep, 4><<<(a.n + 3) / 4, 128, 0, st>>>(a);
+    }
     UNREAL_LAUNCH_CHECK("maze_warp_kernel");
     return UNREAL_OK;
   }
