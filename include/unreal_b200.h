@@ -235,6 +235,14 @@ int unreal_relu_grad(const void* dy, int dy_dtype, const void* y_bf16, void* out
  * dw_taps f32 [4 taps][16 out][48 (dy,dx,c)] += sum_pixels dY * x' (caller zeroes dw_taps). */
 int unreal_conv1_wgrad(const void* xpp_bf16, const void* dy_planes_bf16, float* dw_taps, int s, void* stream);
 
+/* Pixel-control head: dueling combine, Q(a) gather and L2 loss in one pass (model.py:431-441, :531-546).
+ * y8 [samples*px, 8] f32 = merged deconv output after ReLU (channel 0 V, 1..A advantages, rest padding);
+ * act [samples] i32; target [samples*px] f32; mask [samples] f32.
+ * loss (nullable, double, accumulated): lam * 0.5 * sum mask * (target - Q[act])^2.
+ * dy8 (nullable): d loss / d (pre-ReLU output) scaled by *go (device scalar, nullable = 1). */
+int unreal_pc_loss(const float* y8, const int32_t* act, const float* target, const float* mask, int a, float lam,
+                   int64_t samples, int px_per_sample, double* loss, float* dy8, const float* go, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -267,6 +267,88 @@ __global__ void __launch_bounds__(256) relu_grad_kernel(const TD* __restrict__ d
   for (int c = threadIdx.x; c < cols; c += blockDim.x) atomicAdd(db + c, s_db[c]);
 }
 
+
+// ---- pixel-control head: dueling combine + Q(a) gather + L2 loss, fused (model.py:431-441, :531-546) ----
+// y [rows, 8] f32: the merged deconv output after ReLU, channel 0 = V, channels 1..A = advantages
+// (channels A+1..7 are padding).  q = V + Adv - mean_a Adv;  loss = lam * 0.5 * sum mask * (R - q[act])^2.
+// With dy != nullptr the same pass writes d loss / d (pre-ReLU deconv output), scaled by *go:
+//   g = go * lam * mask * (q[act] - R);  dV = g;  dAdv_k = g * ([k == act] - 1/A);  masked by y > 0.
+__global__ void __launch_bounds__(256) pc_loss_kernel(const float* __restrict__ y, const int32_t* __restrict__ act,
+                                                      const float* __restrict__ target, const float* __restrict__ mask,
+                                                      int A, float lam, int64_t rows, int px_per_sample,
+                                                      double* __restrict__ loss, float* __restrict__ dy,
+                                                      const float* __restrict__ go) {
+  float part = 0.f;
+  const float gscale = (dy != nullptr && go != nullptr) ? *go : 1.f;
+  const float inv_a = 1.0f / (float)A;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t smp = r / px_per_sample;
+    const float m = mask[smp];
+    const int a = act[smp];
+    const float4 lo = __ldcs(reinterpret_cast<const float4*>(y + r * 8));
+    const float4 hi = __ldcs(reinterpret_cast<const float4*>(y + r * 8 + 4));
+    const float v[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+    float sum = 0.f, qa = 0.f;
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+      if (k < A) { sum += v[1 + k]; if (k == a) qa = v[1 + k]; }
+    }
+    qa = v[0] + qa - sum * inv_a;
+    const float diff = qa - __ldcs(target + r);
+    part += m * diff * diff;
+    if (dy != nullptr) {
+      const float g = gscale * lam * m * diff;
+      float d[8];
+      d[0] = v[0] > 0.f ? g : 0.f;
+#pragma unroll
+      for (int k = 0; k < 7; ++k) d[1 + k] = (k < A && v[1 + k] > 0.f) ? g * ((k == a ? 1.f : 0.f) - inv_a) : 0.f;
+      __stcs(reinterpret_cast<float4*>(dy + r * 8), make_float4(d[0], d[1], d[2], d[3]));
+      __stcs(reinterpret_cast<float4*>(dy + r * 8 + 4), make_float4(d[4], d[5], d[6], d[7]));
+    }
+  }
+  if (loss == nullptr) return;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+  __shared__ float s_part[8];
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = part;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += (double)s_part[w];
+    atomicAdd(loss, 0.5 * (double)lam * t);
+  }
+}
+
+// col2im for f32 columns with C a multiple of 4 (the merged, padded deconv: C = 8): float4 per tap
+__global__ void __launch_bounds__(256) col2im_f32v4_kernel(const float* __restrict__ cols, float* __restrict__ out,
+                                                           const float* __restrict__ bias, int relu, ConvGeom g,
+                                                           int64_t total4) {
+  const int k = g.kh * g.kw * g.c;
+  const int c4n = g.c >> 2;
+  for (int64_t id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; id < total4; id += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = id;
+    const int c = (int)(r % c4n) * 4; r /= c4n;
+    const int x = (int)(r % g.w); r /= g.w;
+    const int y = (int)(r % g.h); r /= g.h;
+    const int64_t s = r;
+    float4 acc = bias ? make_float4(bias[c], bias[c + 1], bias[c + 2], bias[c + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int ky = y % g.stride; ky < g.kh; ky += g.stride) {
+      const int oy = (y - ky) / g.stride;
+      if (y - ky < 0 || oy >= g.oh) continue;
+      for (int kx = x % g.stride; kx < g.kw; kx += g.stride) {
+        const int ox = (x - kx) / g.stride;
+        if (x - kx < 0 || ox >= g.ow) continue;
+        const float4 t = __ldcs(reinterpret_cast<const float4*>(cols + ((s * g.oh + oy) * g.ow + ox) * (int64_t)k +
+                                                                (ky * g.kw + kx) * g.c + c));
+        acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+      }
+    }
+    if (relu) { acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f); }
+    reinterpret_cast<float4*>(out)[id] = acc;
+  }
+}
+
 static int grid_for_elems(int64_t total, int per_block = 256) {
   int sms = sm_count();
   if (sms <= 0) return 0;
@@ -344,6 +426,12 @@ extern "C" int unreal_col2im(const void* cols, int cols_dtype, void* out, int ou
     UNREAL_LAUNCH_CHECK("col2im_vec8_kernel");
     return UNREAL_OK;
   }
+  if (cols_dtype == UNREAL_F32 && out_dtype == UNREAL_F32 && (c & 3) == 0 && aligned16(cols) && aligned16(out)) {
+    const int64_t total4 = total / 4;
+    col2im_f32v4_kernel<<<grid_for_elems(total4), 256, 0, st>>>(reinterpret_cast<const float*>(cols), reinterpret_cast<float*>(out), bias, relu, g, total4);
+    UNREAL_LAUNCH_CHECK("col2im_f32v4_kernel");
+    return UNREAL_OK;
+  }
   if (cols_dtype == UNREAL_F32 && out_dtype == UNREAL_F32)
     col2im_kernel<float, float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(cols), reinterpret_cast<float*>(out), bias, relu, g, total);
   else if (cols_dtype == UNREAL_F32)
@@ -405,5 +493,20 @@ extern "C" int unreal_relu_grad(const void* dy, int dy_dtype, const void* y_bf16
         reinterpret_cast<const float*>(dy), reinterpret_cast<const __nv_bfloat16*>(y_bf16),
         reinterpret_cast<__nv_bfloat16*>(out_bf16), db, rows, cols, out_planes);
   UNREAL_LAUNCH_CHECK("relu_grad_kernel");
+  return UNREAL_OK;
+}
+
+extern "C" int unreal_pc_loss(const float* y8, const int32_t* act, const float* target, const float* mask, int a,
+                              float lam, int64_t samples, int px_per_sample, double* loss, float* dy8, const float* go,
+                              void* stream) {
+  UNREAL_REQUIRE(y8 && act && target && mask && samples > 0 && px_per_sample > 0, "unreal_pc_loss: null buffer or empty shape");
+  UNREAL_REQUIRE(a >= 1 && a <= 7, "unreal_pc_loss: action count %d not in 1..7 (8-channel padded head)", a);
+  UNREAL_REQUIRE(loss != nullptr || dy8 != nullptr, "unreal_pc_loss: nothing to compute");
+  UNREAL_REQUIRE(aligned16(y8) && aligned16(dy8), "unreal_pc_loss: 16-byte alignment");
+  const int64_t rows = samples * px_per_sample;
+  const int grid = grid_for_elems(rows);
+  if (grid <= 0) return UNREAL_ECUDA;
+  pc_loss_kernel<<<grid, 256, 0, as_stream(stream)>>>(y8, act, target, mask, a, lam, rows, px_per_sample, loss, dy8, go);
+  UNREAL_LAUNCH_CHECK("pc_loss_kernel");
   return UNREAL_OK;
 }

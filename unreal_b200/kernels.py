@@ -452,3 +452,15 @@ def conv1_wgrad(xpp, dy_planes):
        ptr(acc, torch.float32), s, stream_ptr())
   # acc[(by,bx), o, (dy,dx,c)] -> W[4by+dy, 4bx+dx, c, o]
   return acc.view(2, 2, 16, 4, 4, 3).permute(0, 3, 1, 4, 5, 2).reshape(8, 8, 3, 16)
+
+
+def pc_loss(y8, act, target, mask, num_actions, lam, want_loss=True, want_grad=False, go=None):
+  """Pixel-control dueling head + loss on the merged 8-channel deconv output y8 [S, px, 8] f32:
+  returns (loss as a 1-element float64 tensor or None, dy8 or None)."""
+  s, px = y8.shape[0], y8.shape[1]
+  loss = torch.zeros(1, dtype=torch.float64, device=y8.device) if want_loss else None
+  dy = torch.empty_like(y8) if want_grad else None
+  call("unreal_pc_loss", ptr(y8, torch.float32, "y8"), ptr(act, torch.int32, "act"), ptr(target, torch.float32, "target"),
+       ptr(mask, torch.float32, "mask"), int(num_actions), float(lam), s, px, ptr(loss, torch.float64),
+       ptr(dy, torch.float32), ptr(go, torch.float32, "go"), stream_ptr())
+  return loss, dy

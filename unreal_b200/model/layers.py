@@ -185,3 +185,53 @@ class LstmFn(torch.autograd.Function):
     # only the 256 fc1 columns carry a gradient (last_action_reward is an input)
     K.gemm_bf16(dg2, w16[:256], out=dxin.view(t * n, kx)[:, :256])
     return dxin, None, dw, db, None, None, None
+
+
+class Deconv8Fn(torch.autograd.Function):
+  """The pixel-control head's two transposed convolutions (value: 1 channel, advantage: A channels;
+  model.py:418-430) as ONE 8-channel deconv: y8[..., 0] = relu(deconv_v), y8[..., 1:1+A] =
+  relu(deconv_a), channels A+1..7 zero padding.  `w8` is the merged bf16 filter shadow
+  [(kh,kw,o8) = 128, 32]; the gradient is split back into the two TF-layout variables."""
+
+  @staticmethod
+  def forward(ctx, h16, w8, b8, wv32, bv32, wa32, ba32, num_actions):
+    s = h16.shape[0]
+    cols = K.gemm_bf16(h16.view(s * 81, 32), w8)                         # f32 [S*81, 128]
+    y = K.col2im(cols, s, 20, 20, 8, 4, 4, 2, bias=b8, relu=True)        # f32 [S,20,20,8]
+    ctx.num_actions = num_actions
+    ctx.save_for_backward(h16, w8)
+    return y
+
+  @staticmethod
+  def backward(ctx, dy):
+    """dy must already be masked by y > 0 (PcLossFn produces it that way)."""
+    h16, w8 = ctx.saved_tensors
+    a = ctx.num_actions
+    s = h16.shape[0]
+    dy = dy.contiguous()
+    dcols = K.im2col(dy, 4, 4, 2)                                          # bf16 [S*81, 128]
+    dh = K.gemm_bf16(dcols, w8, b_mn_major=True, out_dtype=torch.bfloat16).view(s, 2592)
+    dw8 = _wgrad(dcols, h16.view(s * 81, 32)).view(4, 4, 8, 32)
+    _, db8 = K.relu_grad(dy.view(s * 400, 8), None, want_out=False)
+    return (dh, None, None, dw8[:, :, 0:1].contiguous(), db8[0:1].clone(), dw8[:, :, 1:1 + a].contiguous(),
+            db8[1:1 + a].clone(), None)
+
+
+class PcLossFn(torch.autograd.Function):
+  """lam * 0.5 * sum mask * (R - Q[a])^2 with Q = V + Adv - mean Adv (model.py:431-441, :531-546) in
+  one fused pass over y8; the backward pass is the same kernel writing d loss / d (pre-ReLU y8)."""
+
+  @staticmethod
+  def forward(ctx, y8, act, target, mask, num_actions, lam):
+    loss, _ = K.pc_loss(y8.view(y8.shape[0], 400, 8), act, target, mask, num_actions, lam)
+    ctx.cfg = (num_actions, lam)
+    ctx.save_for_backward(y8, act, target, mask)
+    return loss[0].to(torch.float32)
+
+  @staticmethod
+  def backward(ctx, go):
+    y8, act, target, mask = ctx.saved_tensors
+    a, lam = ctx.cfg
+    _, dy = K.pc_loss(y8.view(y8.shape[0], 400, 8), act, target, mask, a, lam, want_loss=False, want_grad=True,
+                      go=go.to(torch.float32).reshape(1).contiguous())
+    return dy.view_as(y8), None, None, None, None, None

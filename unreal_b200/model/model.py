@@ -26,7 +26,7 @@ import torch
 
 from .. import _lib
 from .. import kernels as K
-from .layers import ConvFn, DeconvFn, LinearFn, LstmFn
+from .layers import ConvFn, Deconv8Fn, DeconvFn, LinearFn, LstmFn, PcLossFn
 
 
 def _variable_specs(A, G, use_pc, use_rp):
@@ -128,6 +128,19 @@ class UnrealModel(object):
         self.taps1.copy_(t1); self.taps2.copy_(t2)
     else:
       self.taps1 = self.taps2 = None
+    if self._use_pixel_change:
+      # merged 8-channel shadow of the two pixel-control deconv filters: channel 0 = value, 1..A = advantages
+      A = self._action_size
+      w8 = torch.zeros(4, 4, 8, 32, dtype=torch.bfloat16, device=self._device)
+      w8[:, :, 0:1] = self.v16["W_pc_deconv_v"]; w8[:, :, 1:1 + A] = self.v16["W_pc_deconv_a"]
+      b8 = torch.zeros(8, dtype=torch.float32, device=self._device)
+      with torch.no_grad():
+        v32 = self._views(self.flat)
+        b8[0:1] = v32["b_pc_deconv_v"]; b8[1:1 + A] = v32["b_pc_deconv_a"]
+      if getattr(self, "pc_w8", None) is None:
+        self.pc_w8, self.pc_b8 = w8.view(128, 32), b8
+      else:
+        self.pc_w8.copy_(w8.view(128, 32)); self.pc_b8.copy_(b8)
 
   def get_vars(self):
     """The variables in creation order (views of the flat buffer), like model.py:729-730."""
@@ -188,12 +201,21 @@ class UnrealModel(object):
     v = (h @ p32["W_base_fc_v"] + p32["b_base_fc_v"]).squeeze(-1)
     return torch.softmax(logits, dim=-1), v
 
-  def _pc_q(self, p32, h):
-    """model.py:411-443.  h [S,256] f32 -> q [S,20,20,A], q_max [S,20,20]."""
+  def _pc_head(self, p32, h):
+    """pc_fc1 + the merged deconv (model.py:411-430): h [S,256] f32 -> y8 [S,20,20,8] f32 after ReLU
+    (channel 0 = value stream, 1..A = advantage stream)."""
     A = self._action_size
+    if A > 7:
+      raise _lib.UnrealError("the merged pixel-control head supports up to 7 actions")
     hp = LinearFn.apply(h.to(torch.bfloat16), self.v16["W_pc_fc1"], p32["W_pc_fc1"], p32["b_pc_fc1"], True, True)
-    v = DeconvFn.apply(hp, self.v16["W_pc_deconv_v"].view(16, 32), p32["W_pc_deconv_v"], p32["b_pc_deconv_v"], 1)
-    a = DeconvFn.apply(hp, self.v16["W_pc_deconv_a"].view(16 * A, 32), p32["W_pc_deconv_a"], p32["b_pc_deconv_a"], A)
+    return Deconv8Fn.apply(hp, self.pc_w8, self.pc_b8, p32["W_pc_deconv_v"], p32["b_pc_deconv_v"],
+                           p32["W_pc_deconv_a"], p32["b_pc_deconv_a"], A)
+
+  def _pc_q(self, p32, h):
+    """model.py:431-441: dueling combine.  h [S,256] f32 -> q [S,20,20,A], q_max [S,20,20]."""
+    A = self._action_size
+    y8 = self._pc_head(p32, h)
+    v, a = y8[..., 0:1], y8[..., 1:1 + A]
     q = v + a - a.mean(dim=3, keepdim=True)
     return q, q.max(dim=3).values
 
@@ -315,9 +337,11 @@ class UnrealModel(object):
       f = feed["pc"]
       L, n = f["images"].shape[:2]
       (h, _, _), _ = self._tower(p32, f["images"], f["lar"], *self._zeros_state(n))
-      q, _ = self._pc_q(p32, h.reshape(L * n, 256))
-      qa = (q.view(L, n, 20, 20, -1) * f["a"][:, :, None, None, :]).sum(-1)
-      parts["pc"] = self._pixel_change_lambda * 0.5 * (((f["R"] - qa) ** 2) * f["mask"].float()[:, :, None, None]).sum()
+      y8 = self._pc_head(p32, h.reshape(L * n, 256))
+      act = f["a"].reshape(L * n, -1).argmax(-1).to(torch.int32)
+      parts["pc"] = PcLossFn.apply(y8, act, f["R"].reshape(L * n, 400).contiguous(),
+                                   f["mask"].reshape(L * n).to(torch.float32).contiguous(), self._action_size,
+                                   self._pixel_change_lambda)
       total = total + parts["pc"]
     if self._use_value_replay and "vr" in feed:
       f = feed["vr"]
