@@ -5,18 +5,21 @@
 // A stride-s KxK convolution with K = 2s is a 2x2 stride-1 convolution over the space-to-depth view
 //     x'[Y, X, (dy, dx, c)] = x[s*Y + dy, s*X + dx, c]:
 //     out[oy, ox, :] = sum over the four taps (by, bx) of  x'[oy+by, ox+bx, :] . Wtap[by, bx]
-// so for one tap the GEMM A operand is just a shifted window of x' -- a multi-dimensional TMA box:
-//   conv1: x' is materialised once in bf16 by s2d_frames_kernel ([S,21,21,48], also the f32/u8 -> bf16
-//          conversion); a 4-D box {48->64 ch, 20 X, 5 Y, 1 sample} is 100 GEMM rows (5 output rows).
+// so for one tap the GEMM A operand is just a shifted window of x':
+//   conv1: x'' = x' as six 8-channel planes [S,6,441,8] bf16 (s2d_frames_kernel, or rendered directly by
+//          K1's maze_s2d_kernel) is the UN-SWIZZLED K-major UMMA layout with a uniform 16-byte row
+//          pitch.  One work item (5 output rows) bulk-copies its 6 x 126-row tile ONCE; each tap is the
+//          same tile with the descriptor start address advanced by (by*21 + bx) rows
+//          (conv1_fwd_tcgen05_kernel).  conv1_wgrad_tcgen05_kernel reads the same tiles as the MN-major
+//          B operand of the filter gradient, with the masked dY as two 8-channel planes.
 //   conv2: x' is only a VIEW of h1 [S,20,20,16]: for each dy a 4-D tensor map {32 (dx,c), 10 X, 10 Y, S}
 //          based at row dy (TMA needs hierarchical strides, so dy cannot be a box dimension between
 //          the channel run and X; measured with scripts/probes/tma5d_probe.cu) with box {32, 9, 9, 1}
-//          lands 81 rows x 32 channels (one sample, half a tap) in shared memory.
-// The conv1 box arrives as rows of 128 bytes with the 128-byte swizzle, the conv2 boxes as rows of
-// 64 bytes with the 64-byte swizzle: both are K-major UMMA layouts as they land.
-// The four tap filters [N, 64] stay resident in shared memory for the whole (persistent) kernel.
-// Rows of the 128-row UMMA tile that the box does not cover hold stale data; they only produce
-// accumulator rows that the (row-clipped) TMA store never writes.
+//          lands 81 rows x 32 channels (one sample, half a tap) as 64-byte rows with the 64-byte
+//          swizzle = a K-major UMMA SW64 tile as it lands (conv_fwd_tcgen05_kernel<32, 2>).
+// Tap filters stay resident in shared memory for the whole (persistent) kernel.  Rows of the 128-row
+// UMMA tile that a box does not cover hold stale data; they only produce accumulator rows that the
+// row-clipped TMA store / the epilogue never writes.
 #include <cuda.h>
 #include <cuda_bf16.h>
 
@@ -31,32 +34,23 @@ int make_tma_nd_bf16(CUtensorMap* map, const void* base, int rank, const uint64_
 
 constexpr int kConvThreads = 192;
 constexpr int kConvStages = 8;
-template <int MODE> struct ConvCfg;
-template <> struct ConvCfg<1> {      // conv1: 4 taps, 64 K-columns (48 used) per step, 128-byte rows
-  static constexpr int kSteps = 4, kRowBytes = 128, kStageBytes = 128 * 128, kMmaPerStep = 4;
-};
+template <int MODE> struct ConvCfg;   // MODE 2 = conv2 (conv1 has its own single-copy kernel below)
 template <> struct ConvCfg<2> {      // conv2: 4 taps x 2 dy, 32 K-columns per step, 64-byte rows
   static constexpr int kSteps = 8, kRowBytes = 64, kStageBytes = 128 * 64, kMmaPerStep = 2;
 };
 
 struct ConvArgs {
   const float* bias;
-  int items;          // work items: conv1 4 per sample (5 output rows each), conv2 1 per sample
-  int rows;           // valid GEMM rows per item: 100 / 81
+  int items;          // work items: one per sample
+  int rows;           // valid GEMM rows per item: 81
   int box_bytes;      // bytes one A box delivers
-  int mode;           // 1: conv1 over x', 2: conv2 over h1
+  int mode;           // 2: conv2 over h1
 };
 
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2, int c3) {
   asm volatile(
       "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
-  asm volatile(
-      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
 }
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, uint32_t src, int c0, int c1, int c2) {
@@ -118,13 +112,8 @@ conv_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_
           mbar_wait(empty_bar(stage), phase ^ 1u);
           mbar_arrive_expect_tx(full_bar(stage), g.box_bytes);
           const uint32_t dst = a_smem + stage * Cfg::kStageBytes;
-          if (MODE == 1) {
-            const int by = st >> 1, bx = st & 1;
-            tma_load_4d(dst, &tma_a, full_bar(stage), 0, bx, (it & 3) * 5 + by, it >> 2);
-          } else {
-            const int tap = st >> 1, dy = st & 1, by = tap >> 1, bx = tap & 1;
-            tma_load_4d(dst, dy ? &tma_a2 : &tma_a, full_bar(stage), 0, bx, by, it);
-          }
+          const int tap = st >> 1, dy = st & 1, by = tap >> 1, bx = tap & 1;
+          tma_load_4d(dst, dy ? &tma_a2 : &tma_a, full_bar(stage), 0, bx, by, it);
           if (++stage == kConvStages) { stage = 0; phase ^= 1u; }
         }
       }
@@ -147,8 +136,8 @@ conv_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_
           const uint32_t sa = a_smem + stage * Cfg::kStageBytes, sb = w_smem + st * kWTileBytes;
 #pragma unroll
           for (int k = 0; k < Cfg::kMmaPerStep; ++k) {
-            const uint64_t ad = MODE == 1 ? smem_desc_sw128(sa + k * 32, 16, 1024) : smem_desc_sw64(sa + k * 32, 16, 512);
-            const uint64_t bd = MODE == 1 ? smem_desc_sw128(sb + k * 32, 16, 1024) : smem_desc_sw64(sb + k * 32, 16, 512);
+            const uint64_t ad = smem_desc_sw64(sa + k * 32, 16, 512);
+            const uint64_t bd = smem_desc_sw64(sb + k * 32, 16, 512);
             mma_f16(tmem_d, ad, bd, idesc, (st > 0 || k > 0) ? 1u : 0u);
           }
           mma_commit(empty_bar(stage));
@@ -616,8 +605,8 @@ extern "C" int unreal_conv_fwd(const void* in_bf16, int layer, const void* w_tap
   {
     const uint64_t dims[2] = {256, (uint64_t)n};
     const uint64_t strides[1] = {512};
-    const uint32_t box[2] = {layer == 1 ? 64u : 32u, (uint32_t)n};
-    rc = make_tma_nd_bf16(&tw, w_taps_bf16, 2, dims, strides, box, layer == 1 ? 128 : 64);
+    const uint32_t box[2] = {32u, (uint32_t)n};
+    rc = make_tma_nd_bf16(&tw, w_taps_bf16, 2, dims, strides, box, 64);
     if (rc != UNREAL_OK) return rc;
   }
   {
@@ -628,8 +617,7 @@ extern "C" int unreal_conv_fwd(const void* in_bf16, int layer, const void* w_tap
     rc = make_tma_nd_bf16(&tc, out_bf16, 3, dims, strides, box, 128);
     if (rc != UNREAL_OK) return rc;
   }
-  return layer == 1 ? launch_conv<16, 1>(ta, ta2, tw, tc, g, as_stream(stream))
-                    : launch_conv<32, 2>(ta, ta2, tw, tc, g, as_stream(stream));
+  return launch_conv<32, 2>(ta, ta2, tw, tc, g, as_stream(stream));
 }
 
 extern "C" int unreal_conv1_wgrad(const void* xpp_bf16, const void* dy_planes_bf16, float* dw_taps, int s,

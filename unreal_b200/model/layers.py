@@ -105,34 +105,6 @@ class ConvFn(torch.autograd.Function):
     return dx, None, dw, db, None, None, None, None
 
 
-class DeconvFn(torch.autograd.Function):
-  """relu(conv2d_transpose(x, W, stride 2, VALID) + b): [S,9,9,32] -> [S,20,20,O] with TF's
-  [kh, kw, out, in] filter (model.py:418-430, :803-820) as GEMM + col2im."""
-
-  @staticmethod
-  def forward(ctx, h16, w16, w32, b32, out_ch):
-    s = h16.shape[0]
-    x = h16.view(s * 81, 32)
-    cols = K.gemm_bf16(x, w16)                                            # f32 [S*81, 16*O]
-    y = K.col2im(cols, s, 20, 20, out_ch, 4, 4, 2, bias=b32, relu=True)
-    ctx.out_ch = out_ch
-    ctx.save_for_backward(h16, w16, y)
-    return y
-
-  @staticmethod
-  def backward(ctx, dy):
-    h16, w16, y = ctx.saved_tensors
-    o = ctx.out_ch
-    s = h16.shape[0]
-    dy = (dy * (y > 0)).contiguous()
-    dcols = K.im2col(dy, 4, 4, 2)                                         # bf16 [S*81, 16*O]
-    dh = K.gemm_bf16(dcols, w16, b_mn_major=True, out_dtype=torch.bfloat16).view(s, 2592)
-    x = h16.view(s * 81, 32)
-    dw = _wgrad(dcols, x).view(4, 4, o, 32)
-    db = dy.sum((0, 1, 2))
-    return dh, None, dw, db, None
-
-
 class LstmFn(torch.autograd.Function):
   """dynamic_rnn over BasicLSTMCell(256) (model.py:110, :343-351), N envs in lock step.
 

@@ -26,7 +26,7 @@ import torch
 
 from .. import _lib
 from .. import kernels as K
-from .layers import ConvFn, Deconv8Fn, DeconvFn, LinearFn, LstmFn, PcLossFn
+from .layers import ConvFn, Deconv8Fn, LinearFn, LstmFn, PcLossFn
 
 
 def _variable_specs(A, G, use_pc, use_rp):
@@ -167,10 +167,6 @@ class UnrealModel(object):
     self.refresh_shadow()
 
   # ---- towers -------------------------------------------------------------------------
-  def _w(self, p32, name, rows=None):
-    """(bf16 shadow as a [K,N] matrix, fp32 view that routes the gradient, bias view)."""
-    return self.v16[name], p32[name]
-
   def _encoder(self, p32, images):
     """model.py:281-289.  images [S,84,84,3] f32 / u8 -> h2 bf16 [S,9,9,32]."""
     h1 = ConvFn.apply(images, self.v16["W_base_conv1"].view(192, 16), p32["W_base_conv1"], p32["b_base_conv1"], 8, 8, 4,
