@@ -33,7 +33,8 @@ int make_tma_nd_bf16(CUtensorMap* map, const void* base, int rank, const uint64_
                      const uint32_t* box, int swizzle_bytes);   // gemm_tcgen05.cu
 
 constexpr int kConvThreads = 192;
-constexpr int kConvStages = 8;
+constexpr int kConvStages = 20;   // 8 boxes per sample: 2.5 samples in flight (8 stages = one sample was latency-bound)
+constexpr int kConvAcc = 4;       // TMEM accumulator buffers of 32 columns
 template <int MODE> struct ConvCfg;   // MODE 2 = conv2 (conv1 has its own single-copy kernel below)
 template <> struct ConvCfg<2> {      // conv2: 4 taps x 2 dy, 32 K-columns per step, 64-byte rows
   static constexpr int kSteps = 8, kRowBytes = 64, kStageBytes = 128 * 64, kMmaPerStep = 2;
@@ -74,9 +75,9 @@ conv_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kConvStages + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kConvStages + a); };
-  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kConvStages + 2 + a); };
-  const uint32_t w_bar = bar_base + 8u * (2 * kConvStages + 4);
-  const uint32_t tmem_slot = bar_base + 8u * (2 * kConvStages + 5);
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kConvStages + kConvAcc + a); };
+  const uint32_t w_bar = bar_base + 8u * (2 * kConvStages + 2 * kConvAcc);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kConvStages + 2 * kConvAcc + 1);
   const uint32_t ebuf_base = bar_base + 1024u;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -86,11 +87,11 @@ conv_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_
     prefetch_tensormap(&tma_w);
     prefetch_tensormap(&tma_c);
     for (int s = 0; s < kConvStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    for (int a = 0; a < kConvAcc; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
     mbar_init(w_bar, 1);
     fence_mbar_init();
   } else if (warp == 2) {
-    tmem_alloc<64>(tmem_slot);
+    tmem_alloc<kConvAcc * 32>(tmem_slot);
   }
   fence_before_sync();
   __syncthreads();
@@ -122,6 +123,7 @@ conv_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_
     if (lane == 0) {
       // ===== MMA issuer: UMMA 128 x N x 16 over every step's K columns =====
       constexpr uint32_t idesc = idesc_bf16_f32(128, N, false, false);
+      constexpr uint32_t kDescHiSw64 = (512u >> 4) | (1u << 14) | (4u << 29);
       mbar_wait(w_bar, 0);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
@@ -129,22 +131,22 @@ conv_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         fence_after_sync();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * 32);
-#pragma unroll 1
+#pragma unroll
         for (int st = 0; st < Cfg::kSteps; ++st) {
           mbar_wait(full_bar(stage), phase);
           fence_after_sync();
-          const uint32_t sa = a_smem + stage * Cfg::kStageBytes, sb = w_smem + st * kWTileBytes;
+          // SW64 K-major descriptors as (lo, hi) words: hi is constant (SBO 512 B, version 1, 64-byte swizzle),
+          // lo = (address >> 4) | LBO field; one add per UMMA instead of rebuilding 64-bit descriptors
+          const uint32_t a_lo = ((a_smem + stage * Cfg::kStageBytes) >> 4) | (1u << 16);
+          const uint32_t b_lo = ((w_smem + st * kWTileBytes) >> 4) | (1u << 16);
 #pragma unroll
-          for (int k = 0; k < Cfg::kMmaPerStep; ++k) {
-            const uint64_t ad = smem_desc_sw64(sa + k * 32, 16, 512);
-            const uint64_t bd = smem_desc_sw64(sb + k * 32, 16, 512);
-            mma_f16(tmem_d, ad, bd, idesc, (st > 0 || k > 0) ? 1u : 0u);
-          }
+          for (int k = 0; k < Cfg::kMmaPerStep; ++k)
+            mma_f16_lohi(tmem_d, a_lo + 2u * k, kDescHiSw64, b_lo + 2u * k, kDescHiSw64, idesc, (st > 0 || k > 0) ? 1u : 0u);
           mma_commit(empty_bar(stage));
           if (++stage == kConvStages) { stage = 0; phase ^= 1u; }
         }
         mma_commit(tfull_bar(acc));
-        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        if (++acc == kConvAcc) { acc = 0; acc_phase ^= 1u; }
       }
     }
   } else {
@@ -192,7 +194,7 @@ conv_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_
       fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
-      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      if (++acc == kConvAcc) { acc = 0; acc_phase ^= 1u; }
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
@@ -201,7 +203,7 @@ conv_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_
   __syncthreads();
   if (warp == 2) {
     fence_after_sync();
-    tmem_dealloc<64>(tmem_base);
+    tmem_dealloc<kConvAcc * 32>(tmem_base);
   }
 }
 
