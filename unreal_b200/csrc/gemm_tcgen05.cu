@@ -39,6 +39,7 @@ constexpr int kBM = 128;        // UMMA M (cta_group::1): accumulator row i live
 constexpr int kBK = 64;         // bf16 elements per stage along K = one 128-byte swizzle row
 constexpr int kUmmaK = 16;      // K per tcgen05.mma for 16-bit operands
 constexpr int kGemmThreads = 192;
+constexpr uint32_t kDescHiSw128 = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO 1024 B, version 1, 128-byte swizzle
 
 struct GemmArgs {
   void* c;
@@ -294,16 +295,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           mbar_wait(full_bar(stage), phase);
           fence_after_sync();
           const uint32_t sa = smem_base + stage * Cfg::kStageBytes, sb = sa + Cfg::kABytes;
+          // K-major: 16 elements = 32 bytes further inside the swizzle row; 8-row groups 1024 B apart.
+          // MN-major: 16 k-rows = two 8-row groups = 2048 bytes; 64-element MN chunks kBK*128 B apart.
+          // Descriptors as (lo, hi) words: hi is constant, lo = (address >> 4) | LBO field.
+          const uint32_t a_lo = (sa >> 4) | ((A_MN ? (uint32_t)(kBK * 128) >> 4 : 1u) << 16);
+          const uint32_t b_lo = (sb >> 4) | ((B_MN ? (uint32_t)(kBK * 128) >> 4 : 1u) << 16);
 #pragma unroll
-          for (int k = 0; k < kBK / kUmmaK; ++k) {
-            // K-major: 16 elements = 32 bytes further inside the swizzle row; 8-row groups 1024 B apart.
-            // MN-major: 16 k-rows = two 8-row groups = 2048 bytes; 64-element MN chunks kBK*128 B apart.
-            const uint64_t ad = A_MN ? smem_desc_sw128(sa + k * 2048, kBK * 128, 1024)
-                                     : smem_desc_sw128(sa + k * 32, 16, 1024);
-            const uint64_t bd = B_MN ? smem_desc_sw128(sb + k * 2048, kBK * 128, 1024)
-                                     : smem_desc_sw128(sb + k * 32, 16, 1024);
-            mma_f16(tmem_d, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-          }
+          for (int k = 0; k < kBK / kUmmaK; ++k)
+            mma_f16_lohi(tmem_d, a_lo + (uint32_t)k * (A_MN ? 128u : 2u), kDescHiSw128, b_lo + (uint32_t)k * (B_MN ? 128u : 2u),
+                         kDescHiSw128, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           mma_commit(empty_bar(stage));               // stage is free once these MMAs have read it
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
         }
