@@ -234,6 +234,9 @@ int unreal_relu_grad(const void* dy, int dy_dtype, const void* y_bf16, void* out
  * ([2][S*400][8] bf16 from unreal_relu_grad with out_planes = 1) once each:
  * dw_taps f32 [4 taps][16 out][48 (dy,dx,c)] += sum_pixels dY * x' (caller zeroes dw_taps). */
 int unreal_conv1_wgrad(const void* xpp_bf16, const void* dy_planes_bf16, float* dw_taps, int s, void* stream);
+/* conv2 filter gradient from h1 [S,20,20,16] bf16 and the masked dY2 [S*81,32] bf16, both read once through
+ * TMA boxes: dw_taps f32 [8 (tap,dy)][32 (dx,c)][32 out] += ... (caller zeroes dw_taps). */
+int unreal_conv2_wgrad(const void* h1_bf16, const void* dy_bf16, float* dw_taps, int s, void* stream);
 
 /* Pixel-control head: dueling combine, Q(a) gather and L2 loss in one pass (model.py:431-441, :531-546).
  * y8 [samples*px, 8] f32 = merged deconv output after ReLU (channel 0 V, 1..A advantages, rest padding);

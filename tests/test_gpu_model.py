@@ -269,3 +269,21 @@ def test_indoor_shaped_a3c_lstm_matches_oracle():
   got = {k: v.cpu() for k, v in m._views(grad).items()}
   for k, rg in rgrads.items():
     assert float((got[k] - rg).abs().max()) <= 3e-2 * float(rg.abs().max()) + 1e-6, k
+
+
+def test_fused_conv2_wgrad_matches_autograd():
+  """conv2 filter gradient through TMA boxes (MN-major SW64 operands, TMEM accumulators across
+  samples) against torch autograd on the same bf16-rounded operands."""
+  from unreal_b200 import kernels as K
+  import torch.nn.functional as F
+  dev = torch.device("cuda", 0)
+  g = torch.Generator(device=dev).manual_seed(12)
+  for s in (1, 2, 700):
+    h1 = torch.rand(s, 20, 20, 16, device=dev, generator=g).to(torch.bfloat16)
+    dy = (torch.randn(s * 81, 32, device=dev, generator=g) * 0.1).to(torch.bfloat16)
+    dw = K.conv2_wgrad(h1, dy)
+    w = torch.zeros(32, 16, 4, 4, device=dev, requires_grad=True)
+    out = F.conv2d(h1.float().permute(0, 3, 1, 2), w, stride=2)                       # [S,32,9,9]
+    out.backward(dy.float().view(s, 9, 9, 32).permute(0, 3, 1, 2))
+    ref = w.grad.permute(2, 3, 1, 0)                                                   # HWIO [4,4,16,32]
+    assert torch.allclose(dw, ref, rtol=1e-3, atol=1e-3 * float(ref.abs().max())), s

@@ -65,6 +65,7 @@ class ConvFn(torch.autograd.Function):
 
   @staticmethod
   def forward(ctx, x, w16, w32, b32, kh, kw, stride, taps):
+    ctx.fused2 = False
     pre_s2d = x.dtype == torch.bfloat16 and tuple(x.shape[1:]) == (6, 441, 8)   # frames already as x'' planes
     s, h, w, c = (x.shape[0], 84, 84, 3) if pre_s2d else x.shape
     oh, ow = (h - kh) // stride + 1, (w - kw) // stride + 1
@@ -80,6 +81,7 @@ class ConvFn(torch.autograd.Function):
       y = K.conv_fwd(xpp, 1, taps, b32).view(s * oh * ow, o)
     elif taps is not None and (h, w, c, kh, kw, stride, o) == (20, 20, 16, 4, 4, 2, 32) and x.dtype == torch.bfloat16:
       y = K.conv_fwd(x, 2, taps, b32).view(s * oh * ow, o)
+      ctx.fused2 = True
     else:
       cols = K.im2col(x, kh, kw, stride)
       y = K.gemm_bf16(cols, w16, b_mn_major=True, bias=b32, relu=True, out_dtype=torch.bfloat16)
@@ -96,8 +98,11 @@ class ConvFn(torch.autograd.Function):
       dyp, db = K.relu_grad(dy.reshape(-1, o), y, planes=True)
       return None, None, K.conv1_wgrad(xpp, dyp), db, None, None, None, None
     dy16, db = K.relu_grad(dy.reshape(-1, o), y)
-    cols = K.im2col(x, kh, kw, stride)
-    dw = _wgrad(cols, dy16).view(kh, kw, c, o)
+    if ctx.fused2:           # conv2: the filter gradient straight from h1 and dY2 through TMA boxes
+      dw = K.conv2_wgrad(x, dy16)
+    else:
+      cols = K.im2col(x, kh, kw, stride)
+      dw = _wgrad(cols, dy16).view(kh, kw, c, o)
     dx = None
     if ctx.needs_input_grad[0]:
       dcols = K.gemm_bf16(dy16, w16, out_dtype=torch.bfloat16)          # [S*OH*OW, KH*KW*C]
