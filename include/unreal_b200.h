@@ -237,6 +237,10 @@ int unreal_conv1_wgrad(const void* xpp_bf16, const void* dy_planes_bf16, float* 
 /* conv2 filter gradient from h1 [S,20,20,16] bf16 and the masked dY2 [S*81,32] bf16, both read once through
  * TMA boxes: dw_taps f32 [8 (tap,dy)][32 (dx,c)][32 out] += ... (caller zeroes dw_taps). */
 int unreal_conv2_wgrad(const void* h1_bf16, const void* dy_bf16, float* dw_taps, int s, void* stream);
+/* conv2 input gradient (transposed convolution) as a 4-tap implicit GEMM over zero-filling TMA boxes:
+ * dy [S*81,32] bf16, w_dtaps bf16 [4 taps][64 (dy,dx,c)][32 out] = W2[2by+dy, 2bx+dx, c, o]
+ * -> dh1 bf16 [S,20,20,16] (un-masked; unreal_relu_grad applies conv1's ReLU mask). */
+int unreal_conv2_dgrad(const void* dy_bf16, const void* w_dtaps_bf16, void* dh1_bf16, int s, void* stream);
 
 /* Pixel-control head: dueling combine, Q(a) gather and L2 loss in one pass (model.py:431-441, :531-546).
  * y8 [samples*px, 8] f32 = merged deconv output after ReLU (channel 0 V, 1..A advantages, rest padding);

@@ -209,6 +209,13 @@ def test_fused_conv_forward_matches_direct_convolution(dtype):
     assert tuple(h1.shape) == (s, 20, 20, 16)
     assert torch.allclose(h1.float(), ref1, rtol=2.0 ** -7, atol=1e-3)
     h2 = K.conv_fwd(h1, 2, K.conv_taps(w2, 2), b2)
+    # transposed convolution (input gradient of conv2) through the zero-filling TMA boxes
+    dy2 = (torch.randn(s * 81, 32, device=dev, generator=g) * 0.1).to(torch.bfloat16)
+    dh1 = K.conv2_dgrad(dy2, K.conv2_dgrad_taps(w2))
+    ref_dh1 = F.conv_transpose2d(dy2.float().view(s, 9, 9, 32).permute(0, 3, 1, 2), w2.float().permute(3, 2, 0, 1),
+                                 stride=2).permute(0, 2, 3, 1)
+    assert tuple(dh1.shape) == (s, 20, 20, 16)
+    assert torch.allclose(dh1.float(), ref_dh1, rtol=2.0 ** -7, atol=1e-3)
     ref2 = F.relu(F.conv2d(h1.float().permute(0, 3, 1, 2), w2.float().permute(3, 2, 0, 1), b2, stride=2)).permute(0, 2, 3, 1)
     assert tuple(h2.shape) == (s, 9, 9, 32)
     assert torch.allclose(h2.float(), ref2, rtol=2.0 ** -7, atol=1e-3)

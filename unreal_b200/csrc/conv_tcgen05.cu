@@ -643,6 +643,143 @@ conv2_wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __gr
   }
 }
 
+
+// ---- conv2 input gradient (transposed convolution), fused -----------------------------------------
+// dh1[y, x, c] = sum over taps of dY2[(y-ky)/2, (x-kx)/2, :] . W2[ky, kx, c, :].  In the space-to-depth
+// view (y = 2Y+dy, ky = 2by+dy ...) this is again a 2x2 tap sum over a 10x10 grid:
+//     dh1'[(Y,X), (dy,dx,c)] = sum_{by,bx} dY2pad[(Y-by, X-bx), :] . Wd[(by,bx)][(dy,dx,c), :]
+// and the zero padding is free: a 4-D TMA box {32 o, 10 X, 10 Y, 1} over dY2 [S,9,9,32] at the SIGNED
+// coordinates (0, -bx, -by, s) zero-fills everything outside the 9x9 image.  Each box lands as a
+// 100-row K-major SW64 tile (K = 32 outputs), the four [64 x 32] tap filters stay resident, and the
+// epilogue writes the [100 x 64] tile straight into the dense [S,20,20,16] gradient (each thread owns
+// a 2x2 pixel block = two contiguous 64-byte runs).  Replaces the GEMM that materialised
+// [S*81, 256] columns (41 KB per sample) plus unreal_col2im.
+constexpr int kDgStages = 16;
+constexpr int kDgAcc = 4;                          // 64 TMEM columns each
+constexpr int kDgABytes = 128 * 64;
+constexpr int kDgWBytes = 4 * 64 * 64;             // four tap filters [64 rows x 64 B]
+constexpr int kDgSmem = kDgWBytes + kDgStages * kDgABytes + 1024 + 1024;
+
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv2_dgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_w,
+                           __nv_bfloat16* __restrict__ out, int samples) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t w_smem = smem_base;
+  const uint32_t a_smem = smem_base + kDgWBytes;
+  const uint32_t bar_base = a_smem + kDgStages * kDgABytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kDgStages + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kDgStages + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kDgStages + kDgAcc + a); };
+  const uint32_t w_bar = bar_base + 8u * (2 * kDgStages + 2 * kDgAcc);
+  const uint32_t tmem_slot = w_bar + 8u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&tma_a); prefetch_tensormap(&tma_w);
+    for (int s = 0; s < kDgStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < kDgAcc; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    mbar_init(w_bar, 1);
+    fence_mbar_init();
+  } else if (warp == 2) {
+    tmem_alloc<kDgAcc * 64>(tmem_slot);
+  }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(w_bar, kDgWBytes);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) tma_load_2d(w_smem + t * 4096, &tma_w, w_bar, 0, t * 64);
+      int stage = 0; uint32_t phase = 0;
+      for (int it = blockIdx.x; it < samples; it += gridDim.x) {
+#pragma unroll 1
+        for (int tap = 0; tap < 4; ++tap) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          mbar_arrive_expect_tx(full_bar(stage), 32 * 10 * 10 * 2);
+          tma_load_4d(a_smem + stage * kDgABytes, &tma_a, full_bar(stage), 0, -(tap & 1), -(tap >> 1), it);
+          if (++stage == kDgStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = idesc_bf16_f32(128, 64, false, false);
+      constexpr uint32_t hi = (512u >> 4) | (1u << 14) | (4u << 29);     // K-major SW64
+      mbar_wait(w_bar, 0);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int it = blockIdx.x; it < samples; it += gridDim.x) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        fence_after_sync();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * 64);
+#pragma unroll
+        for (int tap = 0; tap < 4; ++tap) {
+          mbar_wait(full_bar(stage), phase);
+          fence_after_sync();
+          const uint32_t a_lo = ((a_smem + stage * kDgABytes) >> 4) | (1u << 16);
+          const uint32_t b_lo = ((w_smem + tap * 4096) >> 4) | (1u << 16);
+#pragma unroll
+          for (int k = 0; k < 2; ++k)
+            mma_f16_lohi(tmem_d, a_lo + 2u * k, hi, b_lo + 2u * k, hi, idesc, (tap > 0 || k > 0) ? 1u : 0u);
+          mma_commit(empty_bar(stage));
+          if (++stage == kDgStages) { stage = 0; phase ^= 1u; }
+        }
+        mma_commit(tfull_bar(acc));
+        if (++acc == kDgAcc) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else {
+    // ===== epilogue: row m' = Y*10 + X holds the 2x2 pixel block (2Y+dy, 2X+dx), 16 channels each =====
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const int Y = r / 10, X = r - Y * 10;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int it = blockIdx.x; it < samples; it += gridDim.x) {
+      mbar_wait(tfull_bar(acc), acc_phase);
+      fence_after_sync();
+      uint32_t v0[32], v1[32];
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 64);
+      tmem_ld32(taddr, v0);            // dy = 0: (dx, c) = 32 values = pixels (2Y, 2X) and (2Y, 2X+1)
+      tmem_ld32(taddr + 32, v1);       // dy = 1
+      tmem_ld_wait();
+      fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (r < 100) {
+        __nv_bfloat16* base = out + (((int64_t)it * 20 + 2 * Y) * 20 + 2 * X) * 16;
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy) {
+          const uint32_t* v = dy ? v1 : v0;
+          uint4* dst = reinterpret_cast<uint4*>(base + dy * 320);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint32_t pk[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              __nv_bfloat162 p = __floats2bfloat162_rn(__uint_as_float(v[8 * q + 2 * j]), __uint_as_float(v[8 * q + 2 * j + 1]));
+              pk[j] = *reinterpret_cast<uint32_t*>(&p);
+            }
+            dst[q] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          }
+        }
+      }
+      if (++acc == kDgAcc) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+  __syncwarp();
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 2) {
+    fence_after_sync();
+    tmem_dealloc<kDgAcc * 64>(tmem_base);
+  }
+}
+
 template <int N, int MODE>
 static int launch_conv(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtensorMap& tw, const CUtensorMap& tc,
                        const ConvArgs& g, cudaStream_t st) {
@@ -790,5 +927,36 @@ extern "C" int unreal_conv2_wgrad(const void* h1_bf16, const void* dy_bf16, floa
   if (sms <= 0) return UNREAL_ECUDA;
   conv2_wgrad_tcgen05_kernel<<<s < sms ? s : sms, 96, kW2Smem, as_stream(stream)>>>(ta, ta2, td, dw_taps, s);
   UNREAL_LAUNCH_CHECK("conv2_wgrad_tcgen05_kernel");
+  return UNREAL_OK;
+}
+
+extern "C" int unreal_conv2_dgrad(const void* dy_bf16, const void* w_dtaps_bf16, void* dh1_bf16, int s, void* stream) {
+  UNREAL_REQUIRE(dy_bf16 && w_dtaps_bf16 && dh1_bf16 && s > 0, "unreal_conv2_dgrad: null buffer or s <= 0");
+  UNREAL_REQUIRE(aligned16(dy_bf16) && aligned16(w_dtaps_bf16) && aligned16(dh1_bf16), "unreal_conv2_dgrad: 16-byte alignment");
+  CUtensorMap ta, tw;
+  {
+    const uint64_t dims[4] = {32, 9, 9, (uint64_t)s};           // dY2 [S][9 Y][9 X][32 o]
+    const uint64_t strides[3] = {64, 64 * 9, 64 * 81};
+    const uint32_t box[4] = {32, 10, 10, 1};                   // one row / column of zero fill around the image
+    int rc = make_tma_nd_bf16(&ta, dy_bf16, 4, dims, strides, box, 64);
+    if (rc != UNREAL_OK) return rc;
+  }
+  {
+    const uint64_t dims[2] = {32, 256};                          // [4 taps x 64 (dy,dx,c) rows][32 o]
+    const uint64_t strides[1] = {64};
+    const uint32_t box[2] = {32, 64};
+    int rc = make_tma_nd_bf16(&tw, w_dtaps_bf16, 2, dims, strides, box, 64);
+    if (rc != UNREAL_OK) return rc;
+  }
+  static bool configured = false;
+  if (!configured) {
+    UNREAL_CUDA(cudaFuncSetAttribute(conv2_dgrad_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDgSmem));
+    configured = true;
+  }
+  const int sms = sm_count();
+  if (sms <= 0) return UNREAL_ECUDA;
+  conv2_dgrad_tcgen05_kernel<<<s < sms ? s : sms, kConvThreads, kDgSmem, as_stream(stream)>>>(
+      ta, tw, reinterpret_cast<__nv_bfloat16*>(dh1_bf16), s);
+  UNREAL_LAUNCH_CHECK("conv2_dgrad_tcgen05_kernel");
   return UNREAL_OK;
 }

@@ -475,3 +475,19 @@ def conv2_wgrad(h1, dy16):
        stream_ptr())
   # acc[(by,bx,dy), (dx,c), o] -> W[2by+dy, 2bx+dx, c, o]
   return acc.view(2, 2, 2, 2, 16, 32).permute(0, 2, 1, 3, 4, 5).reshape(4, 4, 16, 32)
+
+
+def conv2_dgrad_taps(w16):
+  """conv2 filter [4,4,16,32] bf16 (HWIO) -> [4 taps, 64 (dy,dx,c), 32 out]: the resident B tiles of
+  the transposed-convolution kernel, W[2by+dy, 2bx+dx, c, o]."""
+  return w16.reshape(2, 2, 2, 2, 16, 32).permute(0, 2, 1, 3, 4, 5).reshape(4, 64, 32).contiguous()
+
+
+def conv2_dgrad(dy16, w_dtaps, out=None):
+  """dy16 [S*81, 32] bf16 -> gradient w.r.t. conv2's input, dense bf16 [S,20,20,16] (un-masked)."""
+  s = dy16.shape[0] // 81
+  if out is None:
+    out = torch.empty(s, 20, 20, 16, dtype=torch.bfloat16, device=dy16.device)
+  call("unreal_conv2_dgrad", ptr(dy16, torch.bfloat16, "dy16"), ptr(w_dtaps, torch.bfloat16, "w_dtaps"),
+       ptr(out, torch.bfloat16, "out"), s, stream_ptr())
+  return out

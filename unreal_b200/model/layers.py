@@ -80,8 +80,10 @@ class ConvFn(torch.autograd.Function):
       xpp = K.s2d_frames(x)
       y = K.conv_fwd(xpp, 1, taps, b32).view(s * oh * ow, o)
     elif taps is not None and (h, w, c, kh, kw, stride, o) == (20, 20, 16, 4, 4, 2, 32) and x.dtype == torch.bfloat16:
-      y = K.conv_fwd(x, 2, taps, b32).view(s * oh * ow, o)
+      # conv2: taps = (forward tap filters [32,256], transposed-conv tap filters [4,64,32])
+      y = K.conv_fwd(x, 2, taps[0], b32).view(s * oh * ow, o)
       ctx.fused2 = True
+      ctx.dtaps = taps[1]
     else:
       cols = K.im2col(x, kh, kw, stride)
       y = K.gemm_bf16(cols, w16, b_mn_major=True, bias=b32, relu=True, out_dtype=torch.bfloat16)
@@ -105,8 +107,11 @@ class ConvFn(torch.autograd.Function):
       dw = _wgrad(cols, dy16).view(kh, kw, c, o)
     dx = None
     if ctx.needs_input_grad[0]:
-      dcols = K.gemm_bf16(dy16, w16, out_dtype=torch.bfloat16)          # [S*OH*OW, KH*KW*C]
-      dx = K.col2im(dcols, s, h, w, c, kh, kw, stride, out_dtype=torch.bfloat16)
+      if ctx.fused2:         # transposed convolution as a 4-tap implicit GEMM over zero-filling TMA boxes
+        dx = K.conv2_dgrad(dy16, ctx.dtaps)
+      else:
+        dcols = K.gemm_bf16(dy16, w16, out_dtype=torch.bfloat16)          # [S*OH*OW, KH*KW*C]
+        dx = K.col2im(dcols, s, h, w, c, kh, kw, stride, out_dtype=torch.bfloat16)
     return dx, None, dw, db, None, None, None, None
 
 

@@ -122,10 +122,11 @@ class UnrealModel(object):
     if self.fused_conv:
       t1 = K.conv1_w_planes(self.v16["W_base_conv1"])
       t2 = K.conv_taps(self.v16["W_base_conv2"], 2)
+      d2 = K.conv2_dgrad_taps(self.v16["W_base_conv2"])
       if getattr(self, "taps1", None) is None:
-        self.taps1, self.taps2 = t1, t2
+        self.taps1, self.taps2 = t1, (t2, d2)
       else:
-        self.taps1.copy_(t1); self.taps2.copy_(t2)
+        self.taps1.copy_(t1); self.taps2[0].copy_(t2); self.taps2[1].copy_(d2)
     else:
       self.taps1 = self.taps2 = None
     if self._use_pixel_change:
