@@ -33,7 +33,7 @@ int make_tma_nd_bf16(CUtensorMap* map, const void* base, int rank, const uint64_
                      const uint32_t* box, int swizzle_bytes);   // gemm_tcgen05.cu
 
 constexpr int kConvThreads = 192;
-constexpr int kConvStages = 20;   // 8 boxes per sample: 2.5 samples in flight (8 stages = one sample was latency-bound)
+constexpr int kConvStages = 8;    // one sample in flight per CTA, two CTAs per SM (the MMA-issuing thread bounds a CTA)
 constexpr int kConvAcc = 4;       // TMEM accumulator buffers of 32 columns
 template <int MODE> struct ConvCfg;   // MODE 2 = conv2 (conv1 has its own single-copy kernel below)
 template <> struct ConvCfg<2> {      // conv2: 4 taps x 2 dy, 32 K-columns per step, 64-byte rows
@@ -59,8 +59,8 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, uint32_t src,
                ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 
-template <int N, int MODE>   // N output channels: 16 (conv1, MODE 1) or 32 (conv2, MODE 2)
-__global__ void __launch_bounds__(kConvThreads, 1)
+template <int N, int MODE>   // N output channels: 32 (conv2, MODE 2)
+__global__ void __launch_bounds__(kConvThreads, 2)
 conv_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_a2,
                         const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CUtensorMap tma_c,
                         const ConvArgs g) {
@@ -259,8 +259,8 @@ __global__ void __launch_bounds__(256) s2d_frames_kernel(const T* __restrict__ i
 // (by*21 + bx) rows.  GEMM rows follow the 21-wide x' grid (row m' = oy*21 + ox); the column ox = 20
 // and rows >= 105 are garbage accumulator rows the epilogue skips.  HBM/L2 traffic per frame:
 // 42 KB of x'' in (each byte once) + 12.8 KB of h1 out.
-constexpr int kC1Stages = 12;
-constexpr int kC1Acc = 8;        // TMEM accumulator buffers (32 columns each): the MMA -> epilogue -> MMA hand-back
+constexpr int kC1Stages = 6;      // x 12 KB; two CTAs per SM (each has ONE MMA-issuing thread, which is what bounds it)
+constexpr int kC1Acc = 4;        // TMEM accumulator buffers (32 columns each): the MMA -> epilogue -> MMA hand-back
                                  // costs ~2 us of barrier latency per item, so 2 buffers capped the kernel
 constexpr int kC1PlaneBytes = 126 * 16;
 constexpr int kC1BoxBytes = 6 * kC1PlaneBytes;      // 12096
@@ -268,7 +268,7 @@ constexpr int kC1StageBytes = 12288;
 constexpr int kC1WBytes = 4 * 6 * 16 * 16;          // [tap][chunk][16 out rows][8 ch] bf16
 constexpr int kC1Smem = kC1WBytes + kC1Stages * kC1StageBytes + 1024 /*barriers*/ + 1024 /*tail reads*/ + 1024 /*align*/;
 
-__global__ void __launch_bounds__(kConvThreads, 1)
+__global__ void __launch_bounds__(kConvThreads, 2)
 conv1_fwd_tcgen05_kernel(const __nv_bfloat16* __restrict__ xpp, const __nv_bfloat16* __restrict__ w_planes,
                          const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int items) {
   extern __shared__ uint8_t smem_raw[];
@@ -405,14 +405,14 @@ conv1_fwd_tcgen05_kernel(const __nv_bfloat16* __restrict__ xpp, const __nv_bfloa
 // of each output row), so whatever finite data x'' holds there contributes nothing.  Each CTA keeps
 // its four [16 x 48] accumulators in TMEM across ALL its items and adds them to global once.
 // Traffic per frame: 42 KB of x'' + 12.8 KB of dY, each read once; no patch matrix.
-constexpr int kWgStages = 9;
+constexpr int kWgStages = 4;      // two CTAs per SM
 constexpr int kWgStageBytes = 16384;            // x'' tile 12 096 (+192 pad) | dY tile 2 x 112 x 16 = 3 584 (+512)
 constexpr int kWgDyOff = 12288;
 constexpr int kWgDyPlane = 112 * 16;
 constexpr int kWgTail = 32768;                   // A chunks 2..15 of the last stages read (ignored) rows here
 constexpr int kWgSmem = kWgStages * kWgStageBytes + kWgTail + 1024 + 1024;
 
-__global__ void __launch_bounds__(96, 1)
+__global__ void __launch_bounds__(96, 2)
 conv1_wgrad_tcgen05_kernel(const __nv_bfloat16* __restrict__ xpp, const __nv_bfloat16* __restrict__ dyp,
                            float* __restrict__ dw, int items, int64_t dy_plane_elems) {
   extern __shared__ uint8_t smem_raw[];
@@ -533,13 +533,13 @@ conv1_wgrad_tcgen05_kernel(const __nv_bfloat16* __restrict__ xpp, const __nv_bfl
 // B operand.  Tile rows the boxes never write were zeroed once, so K rows 81..95 contribute exactly 0.
 // Eight [32 x 32] accumulators live in TMEM across ALL samples of a CTA and are added to global
 // once.  Replaces unreal_im2col (41 KB per sample written and re-read) + the split-K GEMM.
-constexpr int kW2AStages = 16;
+constexpr int kW2AStages = 8;     // two CTAs per SM
 constexpr int kW2BStages = 3;
 constexpr int kW2ABytes = 128 * 64;
 constexpr int kW2BBytes = 8192;                   // 96 rows x 64 B used
 constexpr int kW2Smem = kW2AStages * kW2ABytes + kW2BStages * kW2BBytes + 8192 /*tail for the ignored A rows 32..127*/ + 1024 + 1024;
 
-__global__ void __launch_bounds__(96, 1)
+__global__ void __launch_bounds__(96, 2)
 conv2_wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_a2,
                            const __grid_constant__ CUtensorMap tma_dy, float* __restrict__ dw, int samples) {
   extern __shared__ uint8_t smem_raw[];
@@ -654,13 +654,13 @@ conv2_wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __gr
 // epilogue writes the [100 x 64] tile straight into the dense [S,20,20,16] gradient (each thread owns
 // a 2x2 pixel block = two contiguous 64-byte runs).  Replaces the GEMM that materialised
 // [S*81, 256] columns (41 KB per sample) plus unreal_col2im.
-constexpr int kDgStages = 16;
+constexpr int kDgStages = 8;      // two CTAs per SM
 constexpr int kDgAcc = 4;                          // 64 TMEM columns each
 constexpr int kDgABytes = 128 * 64;
 constexpr int kDgWBytes = 4 * 64 * 64;             // four tap filters [64 rows x 64 B]
 constexpr int kDgSmem = kDgWBytes + kDgStages * kDgABytes + 1024 + 1024;
 
-__global__ void __launch_bounds__(kConvThreads, 1)
+__global__ void __launch_bounds__(kConvThreads, 2)
 conv2_dgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_w,
                            __nv_bfloat16* __restrict__ out, int samples) {
   extern __shared__ uint8_t smem_raw[];
@@ -794,7 +794,7 @@ static int launch_conv(const CUtensorMap& ta, const CUtensorMap& ta2, const CUte
   }
   const int sms = sm_count();
   if (sms <= 0) return UNREAL_ECUDA;
-  const int grid = g.items < sms ? g.items : sms;
+  const int grid = g.items < 2 * sms ? g.items : 2 * sms;
   kern<<<grid, kConvThreads, kSmem, st>>>(ta, ta2, tw, tc, g);
   UNREAL_LAUNCH_CHECK("conv_fwd_tcgen05_kernel");
   return UNREAL_OK;
@@ -845,7 +845,8 @@ extern "C" int unreal_conv_fwd(const void* in_bf16, int layer, const void* w_tap
     const int sms = sm_count();
     if (sms <= 0) return UNREAL_ECUDA;
     const int items = s * 4;
-    conv1_fwd_tcgen05_kernel<<<items < sms ? items : sms, kConvThreads, kC1Smem, as_stream(stream)>>>(
+    const int ctas = 2 * sms;
+    conv1_fwd_tcgen05_kernel<<<items < ctas ? items : ctas, kConvThreads, kC1Smem, as_stream(stream)>>>(
         reinterpret_cast<const __nv_bfloat16*>(in_bf16), reinterpret_cast<const __nv_bfloat16*>(w_taps_bf16), bias, reinterpret_cast<__nv_bfloat16*>(out_bf16), items);
     UNREAL_LAUNCH_CHECK("conv1_fwd_tcgen05_kernel");
     return UNREAL_OK;
@@ -891,7 +892,7 @@ extern "C" int unreal_conv1_wgrad(const void* xpp_bf16, const void* dy_planes_bf
   const int sms = sm_count();
   if (sms <= 0) return UNREAL_ECUDA;
   const int items = s * 4;
-  conv1_wgrad_tcgen05_kernel<<<items < sms ? items : sms, 96, kWgSmem, as_stream(stream)>>>(
+  conv1_wgrad_tcgen05_kernel<<<items < 2 * sms ? items : 2 * sms, 96, kWgSmem, as_stream(stream)>>>(
       reinterpret_cast<const __nv_bfloat16*>(xpp_bf16), reinterpret_cast<const __nv_bfloat16*>(dy_planes_bf16), dw_taps,
       items, (int64_t)s * 400 * 8);
   UNREAL_LAUNCH_CHECK("conv1_wgrad_tcgen05_kernel");
@@ -925,7 +926,7 @@ extern "C" int unreal_conv2_wgrad(const void* h1_bf16, const void* dy_bf16, floa
   }
   const int sms = sm_count();
   if (sms <= 0) return UNREAL_ECUDA;
-  conv2_wgrad_tcgen05_kernel<<<s < sms ? s : sms, 96, kW2Smem, as_stream(stream)>>>(ta, ta2, td, dw_taps, s);
+  conv2_wgrad_tcgen05_kernel<<<s < 2 * sms ? s : 2 * sms, 96, kW2Smem, as_stream(stream)>>>(ta, ta2, td, dw_taps, s);
   UNREAL_LAUNCH_CHECK("conv2_wgrad_tcgen05_kernel");
   return UNREAL_OK;
 }
@@ -955,7 +956,7 @@ extern "C" int unreal_conv2_dgrad(const void* dy_bf16, const void* w_dtaps_bf16,
   }
   const int sms = sm_count();
   if (sms <= 0) return UNREAL_ECUDA;
-  conv2_dgrad_tcgen05_kernel<<<s < sms ? s : sms, kConvThreads, kDgSmem, as_stream(stream)>>>(
+  conv2_dgrad_tcgen05_kernel<<<s < 2 * sms ? s : 2 * sms, kConvThreads, kDgSmem, as_stream(stream)>>>(
       ta, tw, reinterpret_cast<__nv_bfloat16*>(dh1_bf16), s);
   UNREAL_LAUNCH_CHECK("conv2_dgrad_tcgen05_kernel");
   return UNREAL_OK;
