@@ -163,6 +163,29 @@ int unreal_frame_unpack(const uint64_t* rec, int m, int32_t* pos0, int32_t* pos1
                         float* reward, uint8_t* terminal, int32_t* last_action, float* last_reward,
                         uint8_t* valid, void* stream);
 
+/* ---- K5 framed mode: payloads of generic-frame envs beside the record ring ----
+ * For lab / gym / indoor / synthetic frames (environment/{lab,gym,indoor}_environment.py process())
+ * the state has no closed form, so what the reference's deque keeps by reference (experience.py:10-18,
+ * :71: frame.state['image'], .pixel_change, float .reward / .last_reward, state['objective']) lives in
+ * caller-owned payload arrays [N, H, item] addressed by the ring slot of the record.
+ * unreal_frame_pack: records for unreal_replay_add from SoA step outputs (cells 0; reward and
+ *   last_reward stored as their SIGN, the only thing the ring tests :76-80; inactive envs -> invalid 0). */
+int unreal_frame_pack(const int32_t* action, const float* reward, const uint8_t* terminal,
+                      const int32_t* last_action /*nullable*/, const float* last_reward /*nullable*/,
+                      const uint8_t* active /*nullable*/, uint64_t* rec, int n, void* stream);
+/* add_frame (:63-93) that also reports where the frame went: slot [N] i32 = ring slot written, or -1
+ * when the frame was discarded (invalid record, terminal directly after terminal :64-67). */
+int unreal_replay_add_slots(unreal_replay_t* r, const uint64_t* frame_rec, int32_t* slot, void* stream);
+/* payload [N,H,item_bytes] <- src [N,item_bytes] at slot[e] (skipped for slot[e] < 0).  item_bytes a
+ * multiple of 4; 128-bit accesses when it is a multiple of 16 and both pointers are 16-byte aligned. */
+int unreal_ring_store(void* payload, const void* src, const int32_t* slot, int n_envs, int history_size,
+                      long long item_bytes, void* stream);
+/* The payloads of a sampled sequence (sample_sequence :109-117 / sample_rp_sequence :146-151 collecting
+ * self._frames[start+i]): out item (e,t) <- payload[e, (top[e]+start[e]+t) % H] for t < len[e] (len NULL:
+ * all seq_len), zeros beyond and for start[e] < 0.  out is [L,N,item] when time_major else [N,L,item]. */
+int unreal_replay_gather(unreal_replay_t* r, const void* payload, long long item_bytes, const int32_t* start,
+                         const int32_t* len /*nullable*/, int seq_len, int time_major, void* out, void* stream);
+
 /* ---- K6: shared RMSProp with global-norm clip, train/rmsprop_applier.py ---------------
  * _apply_gradients (:109-132): g <- grad * clip / max(||grad||, clip)  (tf.clip_by_global_norm :121)
  * _apply_dense (:83-93) = TF ApplyRMSProp:  ms += (g*g - ms)*(1-decay);

@@ -382,6 +382,49 @@ def rmsprop_step(vars_, rms_, mom_, grads, lr, decay=0.9, momentum=0.0, epsilon=
 # one worker's rollout + replay targets (train/trainer.py:176-205, :218-436)
 # --------------------------------------------------------------------------
 
+class TableFrameEnvOracle(object):
+  """A generic-frame env with the instance contract of the reference's lab / gym / indoor classes
+  (environment/lab_environment.py:94-131, indoor_environment.py:63-139): `last_state['image']` is
+  `uint8 / 255.0` as float32, `process(action) -> (state, reward, terminal, pixel_change)` with the
+  pixel change from environment.py:93-99 on the float32 frames, `reset()` starts a new episode.
+  Frames, float rewards and terminals are a hash of (env id, step counter, action) into a seeded table
+  -- the numpy twin of unreal_b200/environment/frame_environment.py:TableFrameProducer, so the device
+  path and this oracle see the same frame stream (test infrastructure for SURVEY.md 8f-4)."""
+  K_FRAMES = 32
+  MOD = 1000003
+
+  def __init__(self, env_id, table):
+    self.env_id = int(env_id)
+    self.table = table                  # uint8 [K, H, W, 3]
+    self.counter = 0
+    self.reset()
+
+  def _hash(self, a_plus_1):
+    return (self.env_id * 7919 + self.counter * 104729 + a_plus_1 * 613) % self.MOD
+
+  def _frame(self, h):
+    return self.table[h % self.K_FRAMES].astype(np.float32) / np.float32(255.0)   # lab_environment.py:99-102
+
+  def reset(self):
+    self.counter += 1
+    self.last_state = {'image': self._frame(self._hash(0))}
+    self.last_action = 0
+    self.last_reward = 0
+
+  def process(self, action, flag=1):
+    self.counter += 1
+    h = self._hash(int(action) + 1)
+    image = self._frame(h)
+    reward = float(((h // self.K_FRAMES) % 5) - 2) * 0.5 if h % 3 == 0 else 0.0
+    terminal = (h % 29 == 0)
+    pc = pixel_change(image, self.last_state['image'])
+    state = {'image': image}
+    self.last_state = state
+    self.last_action = action
+    self.last_reward = reward
+    return state, reward, terminal, pc
+
+
 class RolloutOracle(object):
   """One reference ``Trainer`` worth of host logic on one maze: warm-up fill,
   on-policy rollout with n-step returns, and the three replay targets.
@@ -394,8 +437,8 @@ class RolloutOracle(object):
   """
 
   def __init__(self, history_size, random_state, net, n_step_TD=20, local_t_max=20,
-               gamma=0.99, gamma_pc=0.9, action_size=4):
-    self.env = MazeOracle()
+               gamma=0.99, gamma_pc=0.9, action_size=4, env=None):
+    self.env = MazeOracle() if env is None else env   # any env with the Environment instance contract
     self.ring = RingOracle(history_size, random_state)
     self.random_state = random_state
     self.net = net
@@ -412,7 +455,7 @@ class RolloutOracle(object):
 
   def _step(self, action):
     env = self.env
-    prev_state, prev_pos = env.last_state, (env.x, env.y)
+    prev_state, prev_pos = env.last_state, (getattr(env, 'x', 0), getattr(env, 'y', 0))
     last_action, last_reward = env.last_action, env.last_reward
     image, reward, terminal, pc = env.process(action)
     frame = dict(state=prev_state, pos=prev_pos, reward=reward, action=action, terminal=terminal,
@@ -442,7 +485,7 @@ class RolloutOracle(object):
       lar = concat_action_and_reward(env.last_action, self.action_size, env.last_reward)
       pi, v, _ = self.net.run_base_policy_and_value(None, env.last_state, lar, "")
       action = self.choose_action(pi)
-      states.append(env.last_state); pos.append((env.x, env.y)); lars.append(lar)
+      states.append(env.last_state); pos.append((getattr(env, 'x', 0), getattr(env, 'y', 0))); lars.append(lar)
       actions.append(action); values.append(v)
       image, frame = self._step(action)
       self.episode_reward += frame['reward']
@@ -457,7 +500,7 @@ class RolloutOracle(object):
     R = 0.0
     if not terminal_end:
       R = self.net.run_base_value(
-          None, {'image': image},
+          None, image if isinstance(image, dict) else {'image': image},   # the maze returns a bare array (:125)
           concat_action_and_reward(frame['action'], self.action_size, frame['reward']))
     batch_R, batch_adv, batch_a = [], [], []
     for ai, ri, Vi in zip(actions[::-1], rewards[::-1], values[::-1]):

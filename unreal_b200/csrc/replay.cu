@@ -142,6 +142,95 @@ __global__ void frame_unpack_kernel(const uint64_t* __restrict__ rec, int m, int
   if (valid) valid[i] = (uint8_t)frame_valid(r);
 }
 
+// ---- framed mode (lab / gym / indoor / synthetic frames have no closed form) ------------
+// The 8-byte record keeps the index logic (action, reward SIGN, terminal, last_action); everything
+// the reference's deque holds by reference -- the 84x84x3 frame, the pixel-change map, the float
+// reward, the objective vector -- lives in caller-owned payload arrays [N, H, item] addressed by the
+// same slot, written by ring_store and read back by replay_gather.
+
+__global__ void replay_add_slots_kernel(unreal_replay R, const uint64_t* __restrict__ frames, int32_t* slot) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= R.n) return;
+  const RingRef r = ring_of(R, e);
+  const int64_t index = *r.top + *r.count;           // where ring_add writes when it accepts the frame
+  slot[e] = ring_add(r, frames[e]) ? (int32_t)(index % R.h) : -1;
+}
+
+__global__ void frame_pack_kernel(const int32_t* __restrict__ action, const float* __restrict__ reward,
+                                  const uint8_t* __restrict__ terminal, const int32_t* __restrict__ last_action,
+                                  const float* __restrict__ last_reward, const uint8_t* __restrict__ active,
+                                  uint64_t* __restrict__ rec, int n) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  if (active && !active[e]) { rec[e] = 0ull; return; }
+  const float r = reward[e], lr = last_reward ? last_reward[e] : 0.f;
+  rec[e] = frame_pack(0, 0, 0, 0, action[e], (r > 0.f) - (r < 0.f), terminal[e], last_action ? last_action[e] : 0,
+                      (lr > 0.f) - (lr < 0.f));
+}
+
+// payload[e, slot[e], :] <- src[e, :]; one CTA per env walks the item in W-sized words
+template <typename W>
+__global__ void __launch_bounds__(256) ring_store_kernel(W* __restrict__ payload, const W* __restrict__ src,
+                                                         const int32_t* __restrict__ slot, int h, int words) {
+  const int e = blockIdx.x;
+  const int s = slot[e];
+  if (s < 0) return;
+  W* dst = payload + ((size_t)e * h + s) * words;
+  const W* from = src + (size_t)e * words;
+  for (int w = threadIdx.x; w < words; w += blockDim.x) dst[w] = from[w];
+}
+
+// small items (a reward, an objective vector): one thread per word
+template <typename W>
+__global__ void ring_store_flat_kernel(W* __restrict__ payload, const W* __restrict__ src,
+                                       const int32_t* __restrict__ slot, int n, int h, int words) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)n * words) return;
+  const int e = (int)(i / words), w = (int)(i % words);
+  const int s = slot[e];
+  if (s >= 0) payload[((size_t)e * h + s) * words + w] = src[i];
+}
+
+__device__ __forceinline__ long long gather_src_item(const unreal_replay& R, const int32_t* start, const int32_t* len,
+                                                     int e, int t) {
+  const int st = start[e];
+  if (st < 0 || (len && t >= len[e])) return -1;
+  return (long long)e * R.h + (R.top[e] + st + t) % R.h;
+}
+
+// out item (e, t) <- payload[e, (top + start + t) % H] for t < len[e], zeros beyond; one CTA per item
+template <typename W>
+__global__ void __launch_bounds__(256) replay_gather_kernel(unreal_replay R, const W* __restrict__ payload,
+                                                            const int32_t* __restrict__ start,
+                                                            const int32_t* __restrict__ len, int L, int time_major,
+                                                            W* __restrict__ out, int words) {
+  const int e = blockIdx.x / L, t = blockIdx.x % L;
+  const long long src = gather_src_item(R, start, len, e, t);
+  W* dst = out + (time_major ? ((size_t)t * R.n + e) : (size_t)blockIdx.x) * words;
+  W zero; memset(&zero, 0, sizeof(W));
+  if (src < 0) {
+    for (int w = threadIdx.x; w < words; w += blockDim.x) dst[w] = zero;
+    return;
+  }
+  const W* from = payload + (size_t)src * words;
+  for (int w = threadIdx.x; w < words; w += blockDim.x) dst[w] = from[w];
+}
+
+template <typename W>
+__global__ void replay_gather_flat_kernel(unreal_replay R, const W* __restrict__ payload,
+                                          const int32_t* __restrict__ start, const int32_t* __restrict__ len, int L,
+                                          int time_major, W* __restrict__ out, int words) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)R.n * L * words) return;
+  const long long item = i / words;
+  const int w = (int)(i % words);
+  const int e = (int)(item / L), t = (int)(item % L);
+  const long long src = gather_src_item(R, start, len, e, t);
+  W v; memset(&v, 0, sizeof(W));
+  if (src >= 0) v = payload[(size_t)src * words + w];
+  out[(time_major ? ((size_t)t * R.n + e) : (size_t)item) * words + w] = v;
+}
+
 }  // namespace unreal
 
 using namespace unreal;
@@ -251,5 +340,71 @@ extern "C" int unreal_replay_copy(unreal_replay_t* r, int direction, uint64_t* r
     if (direction == 0) UNREAL_CUDA(cudaMemcpyAsync(p.user, p.ring, p.bytes, cudaMemcpyDeviceToDevice, st));
     else UNREAL_CUDA(cudaMemcpyAsync(p.ring, p.user, p.bytes, cudaMemcpyDeviceToDevice, st));
   }
+  return UNREAL_OK;
+}
+
+// ---- framed mode ---------------------------------------------------------------------------------------
+extern "C" int unreal_frame_pack(const int32_t* action, const float* reward, const uint8_t* terminal,
+                                 const int32_t* last_action, const float* last_reward, const uint8_t* active,
+                                 uint64_t* rec, int n, void* stream) {
+  UNREAL_REQUIRE(n >= 0, "unreal_frame_pack: negative size");
+  if (n == 0) return UNREAL_OK;
+  UNREAL_REQUIRE(action && reward && terminal && rec, "unreal_frame_pack: null argument");
+  frame_pack_kernel<<<(n + 255) / 256, 256, 0, as_stream(stream)>>>(action, reward, terminal, last_action, last_reward,
+                                                                   active, rec, n);
+  UNREAL_LAUNCH_CHECK("frame_pack_kernel");
+  return UNREAL_OK;
+}
+
+extern "C" int unreal_replay_add_slots(unreal_replay_t* r, const uint64_t* frame_rec, int32_t* slot, void* stream) {
+  UNREAL_REQUIRE(r && frame_rec && slot, "unreal_replay_add_slots: null argument");
+  replay_add_slots_kernel<<<(r->n + 127) / 128, 128, 0, as_stream(stream)>>>(*r, frame_rec, slot);
+  UNREAL_LAUNCH_CHECK("replay_add_slots_kernel");
+  return UNREAL_OK;
+}
+
+extern "C" int unreal_ring_store(void* payload, const void* src, const int32_t* slot, int n_envs, int history_size,
+                                 long long item_bytes, void* stream) {
+  UNREAL_REQUIRE(payload && src && slot, "unreal_ring_store: null argument");
+  UNREAL_REQUIRE(n_envs >= 1 && history_size >= 1, "unreal_ring_store: bad ring shape %d x %d", n_envs, history_size);
+  UNREAL_REQUIRE(item_bytes >= 4 && item_bytes % 4 == 0 && item_bytes < (1ll << 31),
+                 "unreal_ring_store: item_bytes %lld must be a positive multiple of 4", item_bytes);
+  cudaStream_t st = as_stream(stream);
+  const bool v16 = item_bytes % 16 == 0 && aligned16(payload) && aligned16(src);
+  const int words = (int)(item_bytes / (v16 ? 16 : 4));
+  if (words >= 128) {
+    if (v16) ring_store_kernel<uint4><<<n_envs, 256, 0, st>>>((uint4*)payload, (const uint4*)src, slot, history_size, words);
+    else ring_store_kernel<uint32_t><<<n_envs, 256, 0, st>>>((uint32_t*)payload, (const uint32_t*)src, slot, history_size, words);
+  } else {
+    const long long total = (long long)n_envs * words;
+    const unsigned grid = (unsigned)((total + 255) / 256);
+    if (v16) ring_store_flat_kernel<uint4><<<grid, 256, 0, st>>>((uint4*)payload, (const uint4*)src, slot, n_envs, history_size, words);
+    else ring_store_flat_kernel<uint32_t><<<grid, 256, 0, st>>>((uint32_t*)payload, (const uint32_t*)src, slot, n_envs, history_size, words);
+  }
+  UNREAL_LAUNCH_CHECK("ring_store_kernel");
+  return UNREAL_OK;
+}
+
+extern "C" int unreal_replay_gather(unreal_replay_t* r, const void* payload, long long item_bytes, const int32_t* start,
+                                    const int32_t* len, int seq_len, int time_major, void* out, void* stream) {
+  UNREAL_REQUIRE(r && payload && start && out, "unreal_replay_gather: null argument");
+  UNREAL_REQUIRE(seq_len >= 1 && seq_len <= r->h, "unreal_replay_gather: seq_len %d not in 1..%d", seq_len, r->h);
+  UNREAL_REQUIRE(item_bytes >= 4 && item_bytes % 4 == 0 && item_bytes < (1ll << 31),
+                 "unreal_replay_gather: item_bytes %lld must be a positive multiple of 4", item_bytes);
+  cudaStream_t st = as_stream(stream);
+  const bool v16 = item_bytes % 16 == 0 && aligned16(payload) && aligned16(out);
+  const int words = (int)(item_bytes / (v16 ? 16 : 4));
+  const long long items = (long long)r->n * seq_len;
+  UNREAL_REQUIRE(items < (1ll << 31), "unreal_replay_gather: %lld items exceed the grid", items);
+  if (words >= 128) {
+    if (v16) replay_gather_kernel<uint4><<<(unsigned)items, 256, 0, st>>>(*r, (const uint4*)payload, start, len, seq_len, time_major, (uint4*)out, words);
+    else replay_gather_kernel<uint32_t><<<(unsigned)items, 256, 0, st>>>(*r, (const uint32_t*)payload, start, len, seq_len, time_major, (uint32_t*)out, words);
+  } else {
+    const long long total = items * words;
+    const unsigned grid = (unsigned)((total + 255) / 256);
+    if (v16) replay_gather_flat_kernel<uint4><<<grid, 256, 0, st>>>(*r, (const uint4*)payload, start, len, seq_len, time_major, (uint4*)out, words);
+    else replay_gather_flat_kernel<uint32_t><<<grid, 256, 0, st>>>(*r, (const uint32_t*)payload, start, len, seq_len, time_major, (uint32_t*)out, words);
+  }
+  UNREAL_LAUNCH_CHECK("replay_gather_kernel");
   return UNREAL_OK;
 }

@@ -223,6 +223,41 @@ class ReplayRing(object):
       raise _lib.UnrealError("frame_rec must hold one record per env")
     call("unreal_replay_add", self._h, ptr(frame_rec, torch.int64, "frame_rec"), stream_ptr())
 
+  def add_slots(self, frame_rec, out=None):
+    """add() that reports the ring slot each frame went to: [N] i32, -1 where it was discarded."""
+    if frame_rec.numel() != self.n:
+      raise _lib.UnrealError("frame_rec must hold one record per env")
+    slot = out if out is not None else torch.empty(self.n, dtype=torch.int32, device=self.device)
+    call("unreal_replay_add_slots", self._h, ptr(frame_rec, torch.int64, "frame_rec"), ptr(slot, torch.int32, "slot"),
+         stream_ptr())
+    return slot
+
+  def store(self, payload, src, slot):
+    """payload [N,H,...] <- src [N,...] at slot [N] (framed mode; skipped where slot < 0)."""
+    if payload.shape[0] != self.n or payload.shape[1] != self.h or tuple(payload.shape[2:]) != tuple(src.shape[1:]) \
+        or src.shape[0] != self.n or payload.dtype != src.dtype:
+      raise _lib.UnrealError("ring payload %s / source %s do not match a %d x %d ring" %
+                             (tuple(payload.shape), tuple(src.shape), self.n, self.h))
+    item = payload[0, 0].numel() * payload.element_size()
+    call("unreal_ring_store", ptr(payload, name="payload"), ptr(src, name="src"), ptr(slot, torch.int32, "slot"),
+         self.n, self.h, item, stream_ptr())
+
+  def gather(self, payload, start, length, seq_len, time_major=True, out=None):
+    """Payloads of the sampled sequences: [L,N,...] (time_major) or [N,L,...]; zero past `length`
+    (None: all seq_len items, the reward-prediction case)."""
+    if payload.shape[0] != self.n or payload.shape[1] != self.h:
+      raise _lib.UnrealError("ring payload %s does not match a %d x %d ring" % (tuple(payload.shape), self.n, self.h))
+    item_shape = tuple(payload.shape[2:])
+    shape = ((seq_len, self.n) if time_major else (self.n, seq_len)) + item_shape
+    if out is None:
+      out = torch.empty(shape, dtype=payload.dtype, device=self.device)
+    elif tuple(out.shape) != shape or out.dtype != payload.dtype:
+      raise _lib.UnrealError("gather output must be %s %s" % (shape, payload.dtype))
+    item = payload[0, 0].numel() * payload.element_size()
+    call("unreal_replay_gather", self._h, ptr(payload, name="payload"), item, ptr(start, torch.int32, "start"),
+         ptr(length, torch.int32, "length"), int(seq_len), 1 if time_major else 0, ptr(out, name="out"), stream_ptr())
+    return out
+
   def state(self):
     """-> dict(full u8, count i32, top i64, n_pos i32, n_neg i32), each [N]."""
     d = self.device
@@ -287,6 +322,17 @@ def frame_unpack(rec, fields=("pos0", "pos1", "action", "reward", "terminal", "l
   call("unreal_frame_unpack", ptr(rec, torch.int64, "rec"), m, g("pos0"), g("pos1"), g("action"), g("reward"),
        g("terminal"), g("last_action"), g("last_reward"), g("valid"), stream_ptr())
   return out
+
+
+def frame_pack(action, reward, terminal, last_action=None, last_reward=None, active=None, out=None):
+  """SoA step outputs of a generic-frame env -> packed records [N] i64 (rewards as their sign)."""
+  n = action.numel()
+  rec = out if out is not None else torch.empty(n, dtype=torch.int64, device=action.device)
+  call("unreal_frame_pack", ptr(action, torch.int32, "action"), ptr(reward, torch.float32, "reward"),
+       ptr(terminal, torch.uint8, "terminal"), ptr(last_action, torch.int32, "last_action"),
+       ptr(last_reward, torch.float32, "last_reward"), ptr(active, torch.uint8, "active"),
+       ptr(rec, torch.int64, "rec"), n, stream_ptr())
+  return rec
 
 
 # ---------------------------------------------------------------------------- optimiser

@@ -373,6 +373,10 @@ class UnrealModel(object):
     shp = K.obs_shape(dt)
 
     def seq(f):
+      if 'images' in f:       # framed ring (FrameTrainer): the replayed frames themselves, time-major
+        l, n = f['images'].shape[:2]
+        mask = (torch.arange(l, device=f['images'].device).view(l, 1) < f['length'].view(1, n))
+        return dict(images=f['images'], lar=f['last_action_reward'].transpose(0, 1).contiguous(), mask=mask)
       n, l = f['pos'].shape[:2]
       pos = f['pos'].transpose(0, 1).contiguous().view(l * n, 2)
       images = K.maze_render(pos, dtype=dt).view(l, n, *shp)
@@ -392,6 +396,9 @@ class UnrealModel(object):
       out['vr'] = d
     if 'rp' in feed:
       f = feed['rp']
+      if 'images' in f:
+        out['rp'] = dict(images=f['images'].contiguous(), c=f['c'])
+        return out
       n = f['pos'].shape[0]
       out['rp'] = dict(images=K.maze_render(f['pos'].contiguous().view(n * 3, 2), dtype=dt).view(n, 3, *shp), c=f['c'])
     return out

@@ -159,3 +159,68 @@ class BatchedExperience(object):
     st = self.ring.state()
     return "{} envs: {} frames, {} zero rewards, {} non zero rewards (env 0)".format(
         self.num_envs, int(st["count"][0]), int(st["n_pos"][0]), int(st["n_neg"][0]))
+
+
+class FramedExperience(BatchedExperience):
+  """BatchedExperience for generic-frame envs (lab / gym / indoor / synthetic).
+
+  The record ring keeps the reference's index semantics (experience.py:63-153); what the reference's
+  deque holds by reference in each ExperienceFrame (:10-18) lives in payload rings addressed by the
+  record's slot: `frames` u8 [N,H,h,w,3] (the state BEFORE the action; 21 168 B per 84x84 frame),
+  `pc` f32 [N,H,20,20] (pixel change caused by the action), `scalars` f32 [N,H,2] (reward,
+  last_reward -- float rewards, indoor_environment.py:113) and `objective` f32 [N,H,G] when the
+  state carries one.  H = 2000 at 1024 envs per GPU is 43 GB of frames + 3.3 GB of maps.
+  """
+
+  def __init__(self, num_envs, history_size, seeds, device='cuda:0', streams=None, frame_shape=(84, 84, 3),
+               objective_size=0):
+    BatchedExperience.__init__(self, num_envs, history_size, seeds, device, streams)
+    n, h, d = self.num_envs, self.history_size, self.device
+    fh, fw = frame_shape[:2]
+    self.frame_shape = tuple(frame_shape)
+    self.pc_shape = ((fh - 4) // 4, (fw - 4) // 4)
+    self.objective_size = int(objective_size)
+    self.frames = torch.zeros(n, h, *self.frame_shape, dtype=torch.uint8, device=d)
+    self.pc = torch.zeros(n, h, *self.pc_shape, dtype=torch.float32, device=d)
+    self.scalars = torch.zeros(n, h, 2, dtype=torch.float32, device=d)
+    self.objective = torch.zeros(n, h, self.objective_size, dtype=torch.float32, device=d) if objective_size else None
+    self._slot = torch.zeros(n, dtype=torch.int32, device=d)
+
+  def add_frames(self, frame_rec, frame=None, pixel_change=None, reward=None, last_reward=None, objective=None):
+    """add_frame (:63-93) for every env with a valid record; payloads follow the record's slot."""
+    with torch.cuda.device(self.device):
+      slot = self.ring.add_slots(frame_rec, out=self._slot)
+      self.ring.store(self.frames, frame, slot)
+      self.ring.store(self.pc, pixel_change, slot)
+      self.ring.store(self.scalars, torch.stack((reward, last_reward), dim=1), slot)
+      if self.objective is not None:
+        self.ring.store(self.objective, objective, slot)
+
+  def _fields(self, rec, start, length, seq_len):
+    f = K.frame_unpack(rec, fields=("action", "terminal", "last_action", "valid"))
+    sc = self.ring.gather(self.scalars, start, length, seq_len, time_major=False)       # [N,L,2]
+    f["reward"] = sc[..., 0].contiguous()
+    f["last_reward"] = sc[..., 1].contiguous()
+    if self.objective is not None:
+      f["objective"] = self.ring.gather(self.objective, start, length, seq_len, time_major=False)
+    return f
+
+  def sample_sequence(self, sequence_size):
+    """-> start [N], len [N], dict of fields [N,L] (float rewards; frames / maps via gather_*)."""
+    with torch.cuda.device(self.device):
+      start, length, rec = self.ring.sample_sequence(self.streams, sequence_size)
+      return start, length, self._fields(rec, start, length, sequence_size)
+
+  def sample_rp_sequence(self):
+    with torch.cuda.device(self.device):
+      start, rec = self.ring.sample_rp(self.streams)
+      return start, self._fields(rec, start, None, 4)
+
+  def gather_frames(self, start, length, seq_len, time_major=True):
+    """The sampled frames' states: u8 [L,N,h,w,3] (zero past `length`)."""
+    with torch.cuda.device(self.device):
+      return self.ring.gather(self.frames, start, length, seq_len, time_major)
+
+  def gather_pixel_change(self, start, length, seq_len, time_major=True):
+    with torch.cuda.device(self.device):
+      return self.ring.gather(self.pc, start, length, seq_len, time_major)

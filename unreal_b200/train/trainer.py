@@ -41,12 +41,26 @@ LOSS_AND_EVAL_LOG_INTERVAL = 5000
 
 
 class Trainer(object):
+  def __new__(cls, *args, **kwargs):
+    # env types without a closed form (synthetic / indoor-shaped frames, host simulators) are driven by
+    # the framed-ring subclass; `Trainer(...)` stays the one constructor, as in the reference
+    env_type = args[5] if len(args) > 5 else kwargs.get('env_type')
+    if cls is Trainer and env_type != 'maze':
+      from .frame_trainer import FrameTrainer
+      return object.__new__(FrameTrainer)
+    return object.__new__(cls)
+
+  def _make_experience(self, streams):
+    if self.env_type != 'maze':
+      raise _lib.UnrealError("the compact-record Trainer drives env_type 'maze'")
+    return BatchedExperience(self.num_envs, self.experience_history_size, None, self.device, streams=streams)
+
   def __init__(self, thread_index, global_network, initial_learning_rate, learning_rate_input, grad_applier,
                env_type, env_name, use_lstm, use_pixel_change, use_value_replay, use_reward_prediction,
                pixel_change_lambda, entropy_beta, local_t_max, n_step_TD, gamma, gamma_pc,
                experience_history_size, max_global_time_step, device, segnet_param_dict, image_shape,
                is_training, n_classes, random_state, termination_time, segnet_lambda, dropout,
-               num_envs=1, seeds=None, verbose=False, use_graphs=False, obs_s2d=False):
+               num_envs=1, seeds=None, verbose=False, use_graphs=False, obs_s2d=False, env_args=None):
     _lib.require_device()
     self.thread_index = thread_index
     self.learning_rate_input = learning_rate_input
@@ -70,8 +84,6 @@ class Trainer(object):
     self.segnet_mode = self.segnet_param_dict.get("segnet_mode", 0)
     if self.segnet_mode:
       raise _lib.UnrealError("segnet_mode != 0 (ErfNet encoder/decoder) is outside the B200 hot path")
-    if env_type != 'maze':
-      raise _lib.UnrealError("the batched Trainer drives env_type 'maze'")
     self.is_training = is_training
     self.n_classes = n_classes
     self.segnet_lambda = segnet_lambda
@@ -79,6 +91,7 @@ class Trainer(object):
     self.termination_time = termination_time
     self.dropout = dropout
     self.verbose = verbose
+    self.env_args = dict(env_args or {})     # extra create_environment arguments (framed env types)
     self.num_envs = int(num_envs)
     self.device = torch.device(device if str(device).startswith("cuda") else "cuda:0")
     if seeds is None and self.num_envs > 1:
@@ -93,7 +106,8 @@ class Trainer(object):
     n, d = self.num_envs, self.device
     with torch.cuda.device(d):
       streams = K.MtStreams([0] * n if seeds is None else seeds, d)
-    self.experience = BatchedExperience(n, experience_history_size, None, d, streams=streams)
+    self.image_shape = tuple(image_shape) if image_shape is not None else (84, 84)
+    self.experience = self._make_experience(streams)
     self.streams = streams
     self.local_t = 0
     self.initial_learning_rate = initial_learning_rate
