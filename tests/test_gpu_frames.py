@@ -267,3 +267,73 @@ def test_frame_trainer_runs_the_real_network():
   losses = {k: float(v) for k, v in tr.last_losses.items()}
   assert all(np.isfinite(list(losses.values()))), losses
   assert float((net.flat.detach() - before).abs().max()) > 0
+
+
+def _real_agent(n, H=40, seed=0, graphs=False):
+  from unreal_b200.environment.environment import Environment
+  from unreal_b200.model.model import UnrealModel
+  from unreal_b200.train.rmsprop_applier import RMSPropApplier
+  from unreal_b200.train.trainer import Trainer
+  Environment.action_size = -1
+  net = UnrealModel(3, 0, -1, True, True, True, True, 0.05, 0.001, DEV, {'segnet_mode': 0}, (84, 84), True, 0, 0.0, 0.0,
+                    num_envs=n, seed=seed)
+  applier = RMSPropApplier(7e-4, decay=0.99, momentum=0.0, epsilon=0.1, clip_norm=40.0)
+  tr = Trainer(0, net, 7e-4, None, applier, 'synthetic', '', True, True, True, True, 0.05, 0.001, 20, 20, 0.99, 0.9, H,
+               10 ** 8, DEV, {'segnet_mode': 0}, (84, 84), True, 0, np.random.RandomState(1), 50.0, 0.0, 0.0,
+               num_envs=n, seeds=np.arange(n) + 3, env_args={'producer': 'table', 'seed': 2}, use_graphs=graphs)
+  tr.prepare()
+  return tr
+
+
+def test_frame_trainer_graphed_data_phase_equals_eager():
+  """Rollout through the env adapter + framed sampling + gathers + targets replayed as ONE CUDA graph give
+  the same feeds as the eager path (integers and frames bit-exact), including the capturing iteration."""
+  n = 5
+  tr_e, tr_g = _real_agent(n, seed=2), _real_agent(n, seed=2, graphs=True)
+  for tr in (tr_e, tr_g):
+    while not tr.experience.is_full():
+      tr.process(None, 0)
+  for it in range(4):
+    de, _ = tr_e.process(None, 0)
+    dg, _ = tr_g.process(None, 0)
+    assert de == dg
+    fe, fg = tr_e.last_feed, tr_g.last_feed
+    assert torch.equal(fe['base']['a'], fg['base']['a']), it
+    assert torch.equal(fe['base']['active'], fg['base']['active'])
+    assert torch.equal(fe['base']['si'], fg['base']['si'])
+    for k in ('pc', 'vr', 'rp'):
+      assert torch.equal(fe[k]['start'], fg[k]['start']), (it, k)
+      assert torch.equal(fe[k]['images'], fg[k]['images']), (it, k)
+    assert torch.allclose(fe['base']['R'], fg['base']['R'], rtol=1e-3, atol=1e-4)
+    assert torch.allclose(fe['pc']['R'], fg['pc']['R'], rtol=1e-3, atol=1e-4)
+  assert torch.allclose(tr_e.local_network.flat, tr_g.local_network.flat, rtol=1e-3, atol=1e-5)
+
+
+def test_frame_trainer_checkpoint_restores_the_exact_trajectory(tmp_path):
+  from unreal_b200.train import checkpoint
+  n = 4
+  tr = _real_agent(n, seed=3)
+  while not tr.experience.is_full():
+    tr.process(None, 0)
+  tr.process(None, 0)
+  path = str(tmp_path / "framed_agent.pt")
+  checkpoint.save(path, tr, global_t=77)
+
+  def run(trainer):
+    out = []
+    for _ in range(2):
+      trainer.process(None, 0)
+      f = trainer.last_feed
+      out.append(dict(act=f['base']['a'].argmax(-1).cpu(), si=f['base']['si'].cpu().clone(),
+                      pc_start=f['pc']['start'].cpu(), pc_img=f['pc']['images'].cpu().clone(),
+                      rp_start=f['rp']['start'].cpu(), total=float(trainer.last_losses['total'])))
+    return out
+
+  a = run(tr)
+  tr2 = _real_agent(n, seed=99)
+  assert checkpoint.load(path, tr2) == 77
+  b = run(tr2)
+  for x, y in zip(a, b):
+    for k in ("act", "si", "pc_start", "pc_img", "rp_start"):
+      assert torch.equal(x[k], y[k]), k
+    assert abs(x["total"] - y["total"]) <= 1e-3 * max(1.0, abs(x["total"]))

@@ -71,6 +71,12 @@ class TableFrameProducer(FrameProducer):
   def _hash(self, a_plus_1):
     return (self.env_id * 7919 + self.counter * 104729 + a_plus_1 * 613) % self.MOD
 
+  def export_state(self):
+    return {"counter": self.counter}
+
+  def import_state(self, st):
+    self.counter.copy_(st["counter"].to(self.device))
+
   def reset(self, mask, out, objective=None):
     m = torch.ones(self.num_envs, dtype=torch.bool, device=self.device) if mask is None else mask.to(torch.bool)
     self.counter.add_(m.to(torch.int64))
@@ -102,6 +108,13 @@ class RandomFrameProducer(FrameProducer):
     self.episode_len = int(episode_len)
     self.gen = torch.Generator(device=self.device).manual_seed(int(seed))
     self.t = torch.zeros(self.num_envs, dtype=torch.int32, device=self.device)
+
+  def export_state(self):
+    return {"t": self.t, "generator": self.gen.get_state()}
+
+  def import_state(self, st):
+    self.t.copy_(st["t"].to(self.device))
+    self.gen.set_state(st["generator"].cpu())
 
   def _draw(self, mask, out):
     fresh = torch.randint(0, 256, out.shape, dtype=torch.uint8, device=self.device, generator=self.gen)
@@ -233,6 +246,23 @@ class BatchedFrameEnvironment(environment.Environment):
         keep = mask == 0
         self.last_action.mul_(keep.to(torch.int32)); self.last_reward.mul_(keep.to(torch.float32))
     self.last_state = self._state(self._cur)
+
+  def export_state(self):
+    """Everything the next step depends on (checkpoints): the current frames are state, not a function of it."""
+    if not hasattr(self.producer, "export_state"):
+      raise _lib.UnrealError("%s cannot be checkpointed (host simulators keep their own state)" % type(self.producer).__name__)
+    d = {"frame": self._cur, "last_action": self.last_action, "last_reward": self.last_reward}
+    if self.objective is not None:
+      d["objective"] = self.objective
+    d.update({"producer." + k: v for k, v in self.producer.export_state().items()})
+    return d
+
+  def import_state(self, st):
+    self.set_current(st["frame"].to(self.device))
+    self.last_action.copy_(st["last_action"].to(self.device)); self.last_reward.copy_(st["last_reward"].to(self.device))
+    if self.objective is not None:
+      self.objective.copy_(st["objective"].to(self.device))
+    self.producer.import_state({k[len("producer."):]: v for k, v in st.items() if k.startswith("producer.")})
 
   def set_current(self, frame):
     """Adopt `frame` [N,H,W,3] as every env's current frame (copied into the env's own buffer)."""

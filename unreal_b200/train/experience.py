@@ -224,3 +224,19 @@ class FramedExperience(BatchedExperience):
   def gather_pixel_change(self, start, length, seq_len, time_major=True):
     with torch.cuda.device(self.device):
       return self.ring.gather(self.pc, start, length, seq_len, time_major)
+
+  def _payloads(self):
+    d = dict(frames=self.frames, pc=self.pc, scalars=self.scalars)
+    if self.objective is not None:
+      d["objective"] = self.objective
+    return d
+
+  def payload_state(self):
+    """The payload rings, verbatim (checkpoints)."""
+    return dict(self._payloads())
+
+  def load_payload_state(self, st):
+    for k, v in self._payloads().items():
+      if tuple(st[k].shape) != tuple(v.shape):
+        raise _lib.UnrealError("payload %s of the checkpoint is %s, ring has %s" % (k, tuple(st[k].shape), tuple(v.shape)))
+      v.copy_(st[k].to(self.device))
