@@ -264,6 +264,12 @@ int unreal_conv2_wgrad(const void* h1_bf16, const void* dy_bf16, float* dw_taps,
  * dy [S*81,32] bf16, w_dtaps bf16 [4 taps][64 (dy,dx,c)][32 out] = W2[2by+dy, 2bx+dx, c, o]
  * -> dh1 bf16 [S,20,20,16] (un-masked; unreal_relu_grad applies conv1's ReLU mask). */
 int unreal_conv2_dgrad(const void* dy_bf16, const void* w_dtaps_bf16, void* dh1_bf16, int s, void* stream);
+/* The pixel-control head's two transposed convolutions as ONE 8-channel deconv, forward (model.py:418-430,
+ * :803-820 conv2d_transpose 4x4 stride 2 VALID + bias + ReLU): h bf16 [S,9,9,32], w_dtaps bf16
+ * [4 taps, 32 (dy,dx,c8), 32 in] (the merged [kh,kw,8,32] filter in unreal_conv2_dgrad's tap order),
+ * bias8 f32 [8] (nullable) -> y8 f32 [S,20,20,8].  Same tcgen05 kernel as unreal_conv2_dgrad with 8 channels. */
+int unreal_pc_deconv_fwd(const void* h_bf16, const void* w_dtaps_bf16, const float* bias8, float* y8, int s,
+                         void* stream);
 
 /* Pixel-control head: dueling combine, Q(a) gather and L2 loss in one pass (model.py:431-441, :531-546).
  * y8 [samples*px, 8] f32 = merged deconv output after ReLU (channel 0 V, 1..A advantages, rest padding);

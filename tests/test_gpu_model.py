@@ -294,3 +294,25 @@ def test_fused_conv2_wgrad_matches_autograd():
     out.backward(dy.float().view(s, 9, 9, 32).permute(0, 3, 1, 2))
     ref = w.grad.permute(2, 3, 1, 0)                                                   # HWIO [4,4,16,32]
     assert torch.allclose(dw, ref, rtol=1e-3, atol=1e-3 * float(ref.abs().max())), s
+
+
+def test_fused_pc_deconv_forward_matches_conv_transpose():
+  """The pixel-control head's merged 8-channel deconv forward (conv2's transposed-convolution tcgen05
+  kernel at 8 channels, bias + ReLU epilogue) against torch conv_transpose2d in fp32 on the same
+  bf16-rounded operands, and against the GEMM + col2im path it replaces."""
+  from unreal_b200 import kernels as K
+  import torch.nn.functional as F
+  dev = torch.device("cuda", 0)
+  g = torch.Generator(device=dev).manual_seed(21)
+  for s in (1, 3, 500):
+    h = torch.rand(s, 9, 9, 32, device=dev, generator=g).to(torch.bfloat16)
+    w8 = ((torch.rand(4, 4, 8, 32, device=dev, generator=g) - 0.5) * 0.2).to(torch.bfloat16)     # [kh,kw,out,in]
+    b8 = (torch.rand(8, device=dev, generator=g) - 0.5) * 0.1
+    y = K.pc_deconv_fwd(h, K.pc_deconv_taps(w8), b8)
+    assert tuple(y.shape) == (s, 20, 20, 8) and y.dtype == torch.float32
+    ref = F.conv_transpose2d(h.float().permute(0, 3, 1, 2), w8.float().permute(3, 2, 0, 1), bias=b8, stride=2)
+    ref = torch.relu(ref).permute(0, 2, 3, 1)
+    assert torch.allclose(y, ref, rtol=1e-4, atol=1e-5), (s, float((y - ref).abs().max()))
+    cols = K.gemm_bf16(h.view(s * 81, 32), w8.view(128, 32))
+    old = K.col2im(cols, s, 20, 20, 8, 4, 4, 2, bias=b8, relu=True)
+    assert torch.allclose(y, old, rtol=1e-4, atol=1e-5)

@@ -660,9 +660,16 @@ constexpr int kDgABytes = 128 * 64;
 constexpr int kDgWBytes = 4 * 64 * 64;             // four tap filters [64 rows x 64 B]
 constexpr int kDgSmem = kDgWBytes + kDgStages * kDgABytes + 1024 + 1024;
 
+// CO = 16: conv2's input gradient, bf16 out.  CO = 8: the pixel-control head's merged deconv FORWARD
+// (model.py:418-430: the same 4x4 stride-2 VALID transposed convolution [S,9,9,32] -> [S,20,20,8], filter
+// [kh,kw,out,in] = conv2's HWIO with c = out): N = 32 accumulator columns, epilogue adds the bias, applies
+// ReLU and writes f32 -- replaces a GEMM into 41 KB/sample of f32 columns + col2im.
+template <int CO>
 __global__ void __launch_bounds__(kConvThreads, 2)
 conv2_dgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_w,
-                           __nv_bfloat16* __restrict__ out, int samples) {
+                           void* __restrict__ out_raw, const float* __restrict__ bias, int samples) {
+  constexpr int kN = 4 * CO;                         // (dy, dx, c) accumulator columns
+  constexpr int kTapBytes = kN * 64;                 // one resident tap filter [kN rows x 64 B]
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t w_smem = smem_base;
@@ -692,9 +699,9 @@ conv2_dgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __gr
 
   if (warp == 0) {
     if (lane == 0) {
-      mbar_arrive_expect_tx(w_bar, kDgWBytes);
+      mbar_arrive_expect_tx(w_bar, 4 * kTapBytes);
 #pragma unroll
-      for (int t = 0; t < 4; ++t) tma_load_2d(w_smem + t * 4096, &tma_w, w_bar, 0, t * 64);
+      for (int t = 0; t < 4; ++t) tma_load_2d(w_smem + t * kTapBytes, &tma_w, w_bar, 0, t * kN);
       int stage = 0; uint32_t phase = 0;
       for (int it = blockIdx.x; it < samples; it += gridDim.x) {
 #pragma unroll 1
@@ -708,7 +715,7 @@ conv2_dgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __gr
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = idesc_bf16_f32(128, 64, false, false);
+      constexpr uint32_t idesc = idesc_bf16_f32(128, kN, false, false);
       constexpr uint32_t hi = (512u >> 4) | (1u << 14) | (4u << 29);     // K-major SW64
       mbar_wait(w_bar, 0);
       int stage = 0; uint32_t phase = 0;
@@ -722,7 +729,7 @@ conv2_dgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __gr
           mbar_wait(full_bar(stage), phase);
           fence_after_sync();
           const uint32_t a_lo = ((a_smem + stage * kDgABytes) >> 4) | (1u << 16);
-          const uint32_t b_lo = ((w_smem + tap * 4096) >> 4) | (1u << 16);
+          const uint32_t b_lo = ((w_smem + tap * kTapBytes) >> 4) | (1u << 16);
 #pragma unroll
           for (int k = 0; k < 2; ++k)
             mma_f16_lohi(tmem_d, a_lo + 2u * k, hi, b_lo + 2u * k, hi, idesc, (tap > 0 || k > 0) ? 1u : 0u);
@@ -739,11 +746,44 @@ conv2_dgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __gr
     const int r = quarter * 32 + lane;
     const int Y = r / 10, X = r - Y * 10;
     int acc = 0; uint32_t acc_phase = 0;
+    float b8[8];
+    if constexpr (CO == 8) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) b8[c] = bias ? __ldg(bias + c) : 0.f;
+    }
     for (int it = blockIdx.x; it < samples; it += gridDim.x) {
       mbar_wait(tfull_bar(acc), acc_phase);
       fence_after_sync();
-      uint32_t v0[32], v1[32];
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 64);
+      if constexpr (CO == 8) {
+        // one load: column (dy, dx, c) = dy*16 + dx*8 + c; each dy is 16 contiguous floats (pixels 2X, 2X+1)
+        uint32_t v[32];
+        tmem_ld32(taddr, v);
+        tmem_ld_wait();
+        fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(acc));
+        if (r < 100) {
+          float* base = reinterpret_cast<float*>(out_raw) + (((int64_t)it * 20 + 2 * Y) * 20 + 2 * X) * 8;
+#pragma unroll
+          for (int dy = 0; dy < 2; ++dy) {
+            float4* dst = reinterpret_cast<float4*>(base + dy * 160);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              float4 o;
+              o.x = fmaxf(__uint_as_float(v[dy * 16 + 4 * q + 0]) + b8[(4 * q + 0) & 7], 0.f);
+              o.y = fmaxf(__uint_as_float(v[dy * 16 + 4 * q + 1]) + b8[(4 * q + 1) & 7], 0.f);
+              o.z = fmaxf(__uint_as_float(v[dy * 16 + 4 * q + 2]) + b8[(4 * q + 2) & 7], 0.f);
+              o.w = fmaxf(__uint_as_float(v[dy * 16 + 4 * q + 3]) + b8[(4 * q + 3) & 7], 0.f);
+              dst[q] = o;
+            }
+          }
+        }
+        if (++acc == kDgAcc) { acc = 0; acc_phase ^= 1u; }
+        continue;
+      }
+      __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(out_raw);
+      uint32_t v0[32], v1[32];
       tmem_ld32(taddr, v0);            // dy = 0: (dx, c) = 32 values = pixels (2Y, 2X) and (2Y, 2X+1)
       tmem_ld32(taddr + 32, v1);       // dy = 1
       tmem_ld_wait();
@@ -931,9 +971,8 @@ extern "C" int unreal_conv2_wgrad(const void* h1_bf16, const void* dy_bf16, floa
   return UNREAL_OK;
 }
 
-extern "C" int unreal_conv2_dgrad(const void* dy_bf16, const void* w_dtaps_bf16, void* dh1_bf16, int s, void* stream) {
-  UNREAL_REQUIRE(dy_bf16 && w_dtaps_bf16 && dh1_bf16 && s > 0, "unreal_conv2_dgrad: null buffer or s <= 0");
-  UNREAL_REQUIRE(aligned16(dy_bf16) && aligned16(w_dtaps_bf16) && aligned16(dh1_bf16), "unreal_conv2_dgrad: 16-byte alignment");
+template <int CO>
+static int launch_deconv(const void* dy_bf16, const void* w_dtaps_bf16, void* out, const float* bias, int s, void* stream) {
   CUtensorMap ta, tw;
   {
     const uint64_t dims[4] = {32, 9, 9, (uint64_t)s};           // dY2 [S][9 Y][9 X][32 o]
@@ -943,21 +982,33 @@ extern "C" int unreal_conv2_dgrad(const void* dy_bf16, const void* w_dtaps_bf16,
     if (rc != UNREAL_OK) return rc;
   }
   {
-    const uint64_t dims[2] = {32, 256};                          // [4 taps x 64 (dy,dx,c) rows][32 o]
+    const uint64_t dims[2] = {32, 16 * CO};                      // [4 taps x 4*CO (dy,dx,c) rows][32 o]
     const uint64_t strides[1] = {64};
-    const uint32_t box[2] = {32, 64};
+    const uint32_t box[2] = {32, 4 * CO};
     int rc = make_tma_nd_bf16(&tw, w_dtaps_bf16, 2, dims, strides, box, 64);
     if (rc != UNREAL_OK) return rc;
   }
   static bool configured = false;
   if (!configured) {
-    UNREAL_CUDA(cudaFuncSetAttribute(conv2_dgrad_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDgSmem));
+    UNREAL_CUDA(cudaFuncSetAttribute(conv2_dgrad_tcgen05_kernel<CO>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDgSmem));
     configured = true;
   }
   const int sms = sm_count();
   if (sms <= 0) return UNREAL_ECUDA;
-  conv2_dgrad_tcgen05_kernel<<<s < 2 * sms ? s : 2 * sms, kConvThreads, kDgSmem, as_stream(stream)>>>(
-      ta, tw, reinterpret_cast<__nv_bfloat16*>(dh1_bf16), s);
+  conv2_dgrad_tcgen05_kernel<CO><<<s < 2 * sms ? s : 2 * sms, kConvThreads, kDgSmem, as_stream(stream)>>>(ta, tw, out, bias, s);
   UNREAL_LAUNCH_CHECK("conv2_dgrad_tcgen05_kernel");
   return UNREAL_OK;
+}
+
+extern "C" int unreal_conv2_dgrad(const void* dy_bf16, const void* w_dtaps_bf16, void* dh1_bf16, int s, void* stream) {
+  UNREAL_REQUIRE(dy_bf16 && w_dtaps_bf16 && dh1_bf16 && s > 0, "unreal_conv2_dgrad: null buffer or s <= 0");
+  UNREAL_REQUIRE(aligned16(dy_bf16) && aligned16(w_dtaps_bf16) && aligned16(dh1_bf16), "unreal_conv2_dgrad: 16-byte alignment");
+  return launch_deconv<16>(dy_bf16, w_dtaps_bf16, dh1_bf16, nullptr, s, stream);
+}
+
+extern "C" int unreal_pc_deconv_fwd(const void* h_bf16, const void* w_dtaps_bf16, const float* bias8, float* y8, int s,
+                                    void* stream) {
+  UNREAL_REQUIRE(h_bf16 && w_dtaps_bf16 && y8 && s > 0, "unreal_pc_deconv_fwd: null buffer or s <= 0");
+  UNREAL_REQUIRE(aligned16(h_bf16) && aligned16(w_dtaps_bf16) && aligned16(y8), "unreal_pc_deconv_fwd: 16-byte alignment");
+  return launch_deconv<8>(h_bf16, w_dtaps_bf16, y8, bias8, s, stream);
 }

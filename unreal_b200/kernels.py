@@ -537,3 +537,18 @@ def conv2_dgrad(dy16, w_dtaps, out=None):
   call("unreal_conv2_dgrad", ptr(dy16, torch.bfloat16, "dy16"), ptr(w_dtaps, torch.bfloat16, "w_dtaps"),
        ptr(out, torch.bfloat16, "out"), s, stream_ptr())
   return out
+
+
+def pc_deconv_taps(w8):
+  """merged pixel-control deconv filter [4,4,8,32] bf16 ([kh,kw,out,in]) -> [4 taps, 32 (dy,dx,c), 32 in]."""
+  return w8.reshape(2, 2, 2, 2, 8, 32).permute(0, 2, 1, 3, 4, 5).reshape(4, 32, 32).contiguous()
+
+
+def pc_deconv_fwd(h16, w_dtaps, bias8, out=None):
+  """h16 bf16 [S,9,9,32] (any view of S*2592) -> relu(conv2d_transpose + bias) f32 [S,20,20,8]."""
+  s = h16.numel() // 2592
+  if out is None:
+    out = torch.empty(s, 20, 20, 8, dtype=torch.float32, device=h16.device)
+  call("unreal_pc_deconv_fwd", ptr(h16, torch.bfloat16, "h16"), ptr(w_dtaps, torch.bfloat16, "w_dtaps"),
+       ptr(bias8, torch.float32, "bias8"), ptr(out, torch.float32, "out"), s, stream_ptr())
+  return out

@@ -173,13 +173,18 @@ class Deconv8Fn(torch.autograd.Function):
   """The pixel-control head's two transposed convolutions (value: 1 channel, advantage: A channels;
   model.py:418-430) as ONE 8-channel deconv: y8[..., 0] = relu(deconv_v), y8[..., 1:1+A] =
   relu(deconv_a), channels A+1..7 zero padding.  `w8` is the merged bf16 filter shadow
-  [(kh,kw,o8) = 128, 32]; the gradient is split back into the two TF-layout variables."""
+  [(kh,kw,o8) = 128, 32]; the gradient is split back into the two TF-layout variables.  Forward with
+  `taps` (the tap-major shadow): unreal_pc_deconv_fwd, conv2's transposed-convolution tcgen05 kernel at 8
+  channels with the bias + ReLU epilogue; without: GEMM into f32 columns + col2im."""
 
   @staticmethod
-  def forward(ctx, h16, w8, b8, wv32, bv32, wa32, ba32, num_actions):
+  def forward(ctx, h16, w8, b8, wv32, bv32, wa32, ba32, num_actions, taps=None):
     s = h16.shape[0]
-    cols = K.gemm_bf16(h16.view(s * 81, 32), w8)                         # f32 [S*81, 128]
-    y = K.col2im(cols, s, 20, 20, 8, 4, 4, 2, bias=b8, relu=True)        # f32 [S,20,20,8]
+    if taps is not None:     # the transposed convolution as a 4-tap implicit GEMM over zero-filling TMA boxes
+      y = K.pc_deconv_fwd(h16, taps, b8)                                 # f32 [S,20,20,8]
+    else:
+      cols = K.gemm_bf16(h16.view(s * 81, 32), w8)                       # f32 [S*81, 128]
+      y = K.col2im(cols, s, 20, 20, 8, 4, 4, 2, bias=b8, relu=True)      # f32 [S,20,20,8]
     ctx.num_actions = num_actions
     ctx.save_for_backward(h16, w8)
     return y
@@ -196,7 +201,7 @@ class Deconv8Fn(torch.autograd.Function):
     dw8 = _wgrad(dcols, h16.view(s * 81, 32)).view(4, 4, 8, 32)
     _, db8 = K.relu_grad(dy.view(s * 400, 8), None, want_out=False)
     return (dh, None, None, dw8[:, :, 0:1].contiguous(), db8[0:1].clone(), dw8[:, :, 1:1 + a].contiguous(),
-            db8[1:1 + a].clone(), None)
+            db8[1:1 + a].clone(), None, None)
 
 
 class PcLossFn(torch.autograd.Function):

@@ -138,10 +138,11 @@ class UnrealModel(object):
       with torch.no_grad():
         v32 = self._views(self.flat)
         b8[0:1] = v32["b_pc_deconv_v"]; b8[1:1 + A] = v32["b_pc_deconv_a"]
+      t8 = K.pc_deconv_taps(w8)           # tap-major shadow for the fused tcgen05 deconv forward
       if getattr(self, "pc_w8", None) is None:
-        self.pc_w8, self.pc_b8 = w8.view(128, 32), b8
+        self.pc_w8, self.pc_b8, self.pc_taps = w8.view(128, 32), b8, t8
       else:
-        self.pc_w8.copy_(w8.view(128, 32)); self.pc_b8.copy_(b8)
+        self.pc_w8.copy_(w8.view(128, 32)); self.pc_b8.copy_(b8); self.pc_taps.copy_(t8)
 
   def get_vars(self):
     """The variables in creation order (views of the flat buffer), like model.py:729-730."""
@@ -206,7 +207,7 @@ class UnrealModel(object):
       raise _lib.UnrealError("the merged pixel-control head supports up to 7 actions")
     hp = LinearFn.apply(h.to(torch.bfloat16), self.v16["W_pc_fc1"], p32["W_pc_fc1"], p32["b_pc_fc1"], True, True)
     return Deconv8Fn.apply(hp, self.pc_w8, self.pc_b8, p32["W_pc_deconv_v"], p32["b_pc_deconv_v"],
-                           p32["W_pc_deconv_a"], p32["b_pc_deconv_a"], A)
+                           p32["W_pc_deconv_a"], p32["b_pc_deconv_a"], A, self.pc_taps if self.fused_conv else None)
 
   def _pc_q(self, p32, h):
     """model.py:431-441: dueling combine.  h [S,256] f32 -> q [S,20,20,A], q_max [S,20,20]."""
