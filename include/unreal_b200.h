@@ -264,6 +264,12 @@ int unreal_conv2_wgrad(const void* h1_bf16, const void* dy_bf16, float* dw_taps,
  * dy [S*81,32] bf16, w_dtaps bf16 [4 taps][64 (dy,dx,c)][32 out] = W2[2by+dy, 2bx+dx, c, o]
  * -> dh1 bf16 [S,20,20,16] (un-masked; unreal_relu_grad applies conv1's ReLU mask). */
 int unreal_conv2_dgrad(const void* dy_bf16, const void* w_dtaps_bf16, void* dh1_bf16, int s, void* stream);
+/* unreal_conv2_dgrad fused with the ReLU gradient of the layer below (conv1, model.py:285: h1 = relu(...)):
+ * the transposed convolution's result is masked by h1 > 0, rounded to bf16 and written as the two
+ * 8-channel planes [2][S*400][8] that unreal_conv1_wgrad consumes; db1 [16] f32 (caller-zeroed, atomically
+ * accumulated, nullable) receives conv1's bias gradient.  Replaces unreal_conv2_dgrad + unreal_relu_grad. */
+int unreal_conv2_dgrad_relu(const void* dy_bf16, const void* w_dtaps_bf16, const void* h1_bf16,
+                            void* dy1_planes_bf16, float* db1, int s, void* stream);
 /* The pixel-control head's two transposed convolutions as ONE 8-channel deconv, forward (model.py:418-430,
  * :803-820 conv2d_transpose 4x4 stride 2 VALID + bias + ReLU): h bf16 [S,9,9,32], w_dtaps bf16
  * [4 taps, 32 (dy,dx,c8), 32 in] (the merged [kh,kw,8,32] filter in unreal_conv2_dgrad's tap order),

@@ -316,3 +316,36 @@ def test_fused_pc_deconv_forward_matches_conv_transpose():
     cols = K.gemm_bf16(h.view(s * 81, 32), w8.view(128, 32))
     old = K.col2im(cols, s, 20, 20, 8, 4, 4, 2, bias=b8, relu=True)
     assert torch.allclose(y, old, rtol=1e-4, atol=1e-5)
+
+
+def test_conv2_dgrad_relu_equals_dgrad_then_relu_grad():
+  """The fused transposed-convolution + ReLU-gradient epilogue writes exactly the planes the two-pass
+  path (unreal_conv2_dgrad -> unreal_relu_grad(planes)) produces, and the same bias gradient."""
+  from unreal_b200 import kernels as K
+  dev = torch.device("cuda", 0)
+  g = torch.Generator(device=dev).manual_seed(5)
+  for s in (1, 3, 600):
+    dy = (torch.randn(s * 81, 32, device=dev, generator=g) * 0.1).to(torch.bfloat16)
+    w = ((torch.rand(4, 4, 16, 32, device=dev, generator=g) - 0.5) * 0.2).to(torch.bfloat16)
+    h1 = torch.relu(torch.randn(s, 20, 20, 16, device=dev, generator=g)).to(torch.bfloat16)     # about half zeros
+    taps = K.conv2_dgrad_taps(w)
+    dense = K.conv2_dgrad(dy, taps)
+    want_planes, want_db = K.relu_grad(dense.view(s * 400, 16), h1.view(s * 400, 16), planes=True)
+    planes, db = K.conv2_dgrad_relu(dy, taps, h1)
+    assert torch.equal(planes, want_planes), s
+    assert torch.allclose(db, want_db, rtol=1e-4, atol=1e-4 * float(want_db.abs().max() + 1e-6)), s
+
+
+def test_fused_encoder_backward_equals_layerwise_backward():
+  """EncoderFn (one autograd node, cross-layer fused backward) gives the same loss and gradients as the
+  two ConvFn nodes with the dense gradient and the relu_grad pass between them."""
+  dev = torch.device("cuda", 0)
+  net_a, net_b = _model(dev, seed=4), _model(dev, seed=4)
+  net_b.fused_encoder = False
+  gpu = _to(_feed(5, 3, 4, seed=9), dev)
+  ta, pa, ga = net_a.loss_and_grads(gpu)
+  tb, pb, gb = net_b.loss_and_grads(gpu)
+  assert abs(float(ta) - float(tb)) <= 1e-5 * max(1.0, abs(float(tb)))
+  va, vb = net_a._views(ga), net_b._views(gb)
+  for k in va:      # same operands, same roundings: only the order of the fp32 atomics differs
+    assert torch.allclose(va[k], vb[k], rtol=2e-3, atol=2e-3 * float(vb[k].abs().max() + 1e-12)), k

@@ -667,7 +667,8 @@ constexpr int kDgSmem = kDgWBytes + kDgStages * kDgABytes + 1024 + 1024;
 template <int CO>
 __global__ void __launch_bounds__(kConvThreads, 2)
 conv2_dgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_w,
-                           void* __restrict__ out_raw, const float* __restrict__ bias, int samples) {
+                           void* __restrict__ out_raw, const float* __restrict__ bias, int samples,
+                           const __nv_bfloat16* __restrict__ mask_y, float* __restrict__ db) {
   constexpr int kN = 4 * CO;                         // (dy, dx, c) accumulator columns
   constexpr int kTapBytes = kN * 64;                 // one resident tap filter [kN rows x 64 B]
   extern __shared__ uint8_t smem_raw[];
@@ -751,6 +752,9 @@ conv2_dgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __gr
 #pragma unroll
       for (int c = 0; c < 8; ++c) b8[c] = bias ? __ldg(bias + c) : 0.f;
     }
+    float dbacc[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) dbacc[c] = 0.f;
     for (int it = blockIdx.x; it < samples; it += gridDim.x) {
       mbar_wait(tfull_bar(acc), acc_phase);
       fence_after_sync();
@@ -790,6 +794,40 @@ conv2_dgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __gr
       fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (mask_y != nullptr) {
+        // fused ReLU gradient of the layer below (conv1): mask by h1 > 0, round to bf16, write the two
+        // 8-channel PLANES conv1's tensor-core wgrad consumes ([2][S*400][8]) and accumulate the bias
+        // gradient -- the dense gradient is never written and no separate relu_grad pass reads it back
+        if (r < 100) {
+          const int64_t pix = ((int64_t)it * 20 + 2 * Y) * 20 + 2 * X;
+          const int64_t plane = (int64_t)samples * 400;
+#pragma unroll
+          for (int dy = 0; dy < 2; ++dy) {
+            const uint32_t* v = dy ? v1 : v0;
+            const uint4* ysrc = reinterpret_cast<const uint4*>(mask_y + (pix + dy * 20) * 16);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {          // q = dx*2 + plane half: 8 channels of pixel (2Y+dy, 2X+dx)
+              const uint4 yu = __ldg(ysrc + q);
+              const __nv_bfloat162* yh = reinterpret_cast<const __nv_bfloat162*>(&yu);
+              uint32_t pk[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 yf = __bfloat1622float2(yh[j]);
+                const float a = yf.x > 0.f ? __uint_as_float(v[8 * q + 2 * j]) : 0.f;
+                const float b = yf.y > 0.f ? __uint_as_float(v[8 * q + 2 * j + 1]) : 0.f;
+                __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
+                pk[j] = *reinterpret_cast<uint32_t*>(&p);
+                const float2 f = __bfloat1622float2(p);      // the bias gradient sums the ROUNDED values
+                dbacc[(q & 1) * 8 + 2 * j] += f.x; dbacc[(q & 1) * 8 + 2 * j + 1] += f.y;
+              }
+              __nv_bfloat16* dst = out + ((q & 1) * plane + pix + dy * 20 + (q >> 1)) * 8;
+              *reinterpret_cast<uint4*>(dst) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            }
+          }
+        }
+        if (++acc == kDgAcc) { acc = 0; acc_phase ^= 1u; }
+        continue;
+      }
       if (r < 100) {
         __nv_bfloat16* base = out + (((int64_t)it * 20 + 2 * Y) * 20 + 2 * X) * 16;
 #pragma unroll
@@ -809,6 +847,15 @@ conv2_dgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __gr
         }
       }
       if (++acc == kDgAcc) { acc = 0; acc_phase ^= 1u; }
+    }
+    if (CO == 16 && mask_y != nullptr && db != nullptr) {
+#pragma unroll
+      for (int c = 0; c < 16; ++c) {
+        float x = dbacc[c];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        if (lane == 0) atomicAdd(db + c, x);
+      }
     }
   }
   __syncwarp();
@@ -972,7 +1019,8 @@ extern "C" int unreal_conv2_wgrad(const void* h1_bf16, const void* dy_bf16, floa
 }
 
 template <int CO>
-static int launch_deconv(const void* dy_bf16, const void* w_dtaps_bf16, void* out, const float* bias, int s, void* stream) {
+static int launch_deconv(const void* dy_bf16, const void* w_dtaps_bf16, void* out, const float* bias, int s, void* stream,
+                         const void* mask_y = nullptr, float* db = nullptr) {
   CUtensorMap ta, tw;
   {
     const uint64_t dims[4] = {32, 9, 9, (uint64_t)s};           // dY2 [S][9 Y][9 X][32 o]
@@ -995,7 +1043,8 @@ static int launch_deconv(const void* dy_bf16, const void* w_dtaps_bf16, void* ou
   }
   const int sms = sm_count();
   if (sms <= 0) return UNREAL_ECUDA;
-  conv2_dgrad_tcgen05_kernel<CO><<<s < 2 * sms ? s : 2 * sms, kConvThreads, kDgSmem, as_stream(stream)>>>(ta, tw, out, bias, s);
+  conv2_dgrad_tcgen05_kernel<CO><<<s < 2 * sms ? s : 2 * sms, kConvThreads, kDgSmem, as_stream(stream)>>>(
+      ta, tw, out, bias, s, reinterpret_cast<const __nv_bfloat16*>(mask_y), db);
   UNREAL_LAUNCH_CHECK("conv2_dgrad_tcgen05_kernel");
   return UNREAL_OK;
 }
@@ -1004,6 +1053,14 @@ extern "C" int unreal_conv2_dgrad(const void* dy_bf16, const void* w_dtaps_bf16,
   UNREAL_REQUIRE(dy_bf16 && w_dtaps_bf16 && dh1_bf16 && s > 0, "unreal_conv2_dgrad: null buffer or s <= 0");
   UNREAL_REQUIRE(aligned16(dy_bf16) && aligned16(w_dtaps_bf16) && aligned16(dh1_bf16), "unreal_conv2_dgrad: 16-byte alignment");
   return launch_deconv<16>(dy_bf16, w_dtaps_bf16, dh1_bf16, nullptr, s, stream);
+}
+
+extern "C" int unreal_conv2_dgrad_relu(const void* dy_bf16, const void* w_dtaps_bf16, const void* h1_bf16,
+                                       void* dy1_planes_bf16, float* db1, int s, void* stream) {
+  UNREAL_REQUIRE(dy_bf16 && w_dtaps_bf16 && h1_bf16 && dy1_planes_bf16 && s > 0, "unreal_conv2_dgrad_relu: null buffer or s <= 0");
+  UNREAL_REQUIRE(aligned16(dy_bf16) && aligned16(w_dtaps_bf16) && aligned16(h1_bf16) && aligned16(dy1_planes_bf16),
+                 "unreal_conv2_dgrad_relu: 16-byte alignment");
+  return launch_deconv<16>(dy_bf16, w_dtaps_bf16, dy1_planes_bf16, nullptr, s, stream, h1_bf16, db1);
 }
 
 extern "C" int unreal_pc_deconv_fwd(const void* h_bf16, const void* w_dtaps_bf16, const float* bias8, float* y8, int s,

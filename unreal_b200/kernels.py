@@ -552,3 +552,15 @@ def pc_deconv_fwd(h16, w_dtaps, bias8, out=None):
   call("unreal_pc_deconv_fwd", ptr(h16, torch.bfloat16, "h16"), ptr(w_dtaps, torch.bfloat16, "w_dtaps"),
        ptr(bias8, torch.float32, "bias8"), ptr(out, torch.float32, "out"), s, stream_ptr())
   return out
+
+
+def conv2_dgrad_relu(dy16, w_dtaps, h1):
+  """conv2's input gradient fused with conv1's ReLU gradient: dy16 [S*81,32] bf16, h1 [S,20,20,16] bf16 ->
+  (masked gradient as conv1-wgrad planes [2, S*400, 8] bf16, conv1 bias gradient [16] f32)."""
+  s = dy16.shape[0] // 81
+  planes = torch.empty(2, s * 400, 8, dtype=torch.bfloat16, device=dy16.device)
+  db = torch.zeros(16, dtype=torch.float32, device=dy16.device)
+  call("unreal_conv2_dgrad_relu", ptr(dy16, torch.bfloat16, "dy16"), ptr(w_dtaps, torch.bfloat16, "w_dtaps"),
+       ptr(h1, torch.bfloat16, "h1"), ptr(planes, torch.bfloat16, "planes"), ptr(db, torch.float32, "db"), s,
+       stream_ptr())
+  return planes, db

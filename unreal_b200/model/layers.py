@@ -115,6 +115,36 @@ class ConvFn(torch.autograd.Function):
     return dx, None, dw, db, None, None, None, None
 
 
+class EncoderFn(torch.autograd.Function):
+  """The whole encoder (model.py:281-289: conv 8x8x3->16 stride 4 + ReLU, conv 4x4x16->32 stride 2 + ReLU) as
+  ONE autograd node over the fused tcgen05 kernels, so the backward pass can fuse ACROSS the two layers:
+  conv2's transposed convolution masks its result by h1 > 0 in the epilogue and writes conv1's wgrad planes
+  and bias gradient directly (`unreal_conv2_dgrad_relu`) -- the dense [S,20,20,16] gradient and the separate
+  ReLU-gradient pass over it (38 KB per frame of HBM traffic) do not exist.  Frames: f32 / u8 [S,84,84,3] or
+  the space-to-depth planes bf16 [S,6,441,8]."""
+
+  @staticmethod
+  def forward(ctx, x, w1_32, b1_32, w2_32, b2_32, taps1, taps2):
+    pre_s2d = x.dtype == torch.bfloat16 and tuple(x.shape[1:]) == (6, 441, 8)
+    s = x.shape[0]
+    xpp = x if pre_s2d else K.s2d_frames(x)
+    h1 = K.conv_fwd(xpp, 1, taps1, b1_32)                      # bf16 [S,20,20,16]
+    h2 = K.conv_fwd(h1.view(s, 20, 20, 16), 2, taps2[0], b2_32)
+    ctx.dtaps = taps2[1]
+    ctx.save_for_backward(xpp, h1, h2)
+    return h2.view(s, 9, 9, 32)
+
+  @staticmethod
+  def backward(ctx, dh2):
+    xpp, h1, h2 = ctx.saved_tensors
+    s = xpp.shape[0]
+    dy2, db2 = K.relu_grad(dh2.reshape(-1, 32), h2.view(-1, 32))
+    dw2 = K.conv2_wgrad(h1.view(s, 20, 20, 16), dy2)
+    dy1_planes, db1 = K.conv2_dgrad_relu(dy2, ctx.dtaps, h1)
+    dw1 = K.conv1_wgrad(xpp, dy1_planes)
+    return None, dw1, db1, dw2, db2, None, None
+
+
 class LstmFn(torch.autograd.Function):
   """dynamic_rnn over BasicLSTMCell(256) (model.py:110, :343-351), N envs in lock step.
 

@@ -26,7 +26,7 @@ import torch
 
 from .. import _lib
 from .. import kernels as K
-from .layers import ConvFn, Deconv8Fn, LinearFn, LstmFn, PcLossFn
+from .layers import ConvFn, Deconv8Fn, EncoderFn, LinearFn, LstmFn, PcLossFn
 
 
 def _variable_specs(A, G, use_pc, use_rp):
@@ -78,6 +78,7 @@ class UnrealModel(object):
     self.lstm_in = 256 + A + 1 + G
     self.kx = (self.lstm_in + 7) // 8 * 8
     self.fused_conv = True    # False: convolutions as explicit im2col + GEMM (A/B switch for benchmarks)
+    self.fused_encoder = True # False: conv1 / conv2 as separate autograd nodes (dense gradient + relu_grad pass between them)
     self._build_variables(seed)
     self.reset_state()
 
@@ -171,6 +172,9 @@ class UnrealModel(object):
   # ---- towers -------------------------------------------------------------------------
   def _encoder(self, p32, images):
     """model.py:281-289.  images [S,84,84,3] f32 / u8 -> h2 bf16 [S,9,9,32]."""
+    if self.fused_conv and self.fused_encoder:
+      return EncoderFn.apply(images, p32["W_base_conv1"], p32["b_base_conv1"], p32["W_base_conv2"], p32["b_base_conv2"],
+                             self.taps1, self.taps2)
     h1 = ConvFn.apply(images, self.v16["W_base_conv1"].view(192, 16), p32["W_base_conv1"], p32["b_base_conv1"], 8, 8, 4,
                       self.taps1)
     h2 = ConvFn.apply(h1, self.v16["W_base_conv2"].view(256, 32), p32["W_base_conv2"], p32["b_base_conv2"], 4, 4, 2,
