@@ -33,11 +33,17 @@ int make_tma_nd_bf16(CUtensorMap* map, const void* base, int rank, const uint64_
                      const uint32_t* box, int swizzle_bytes);   // gemm_tcgen05.cu
 
 constexpr int kConvThreads = 192;
-constexpr int kConvStages = 8;    // one sample in flight per CTA, two CTAs per SM (the MMA-issuing thread bounds a CTA)
 constexpr int kConvAcc = 4;       // TMEM accumulator buffers of 32 columns
 template <int MODE> struct ConvCfg;   // MODE 2 = conv2 (conv1 has its own single-copy kernel below)
-template <> struct ConvCfg<2> {      // conv2: 4 taps x 2 dy, 32 K-columns per step, 64-byte rows
-  static constexpr int kSteps = 8, kRowBytes = 64, kStageBytes = 128 * 64, kMmaPerStep = 2;
+template <> struct ConvCfg<2> {      // conv2: one step per filter row ky = 2by+dy; a box row is the 4 pixels
+  // 2X..2X+3 of image row 2(Y+by)+dy = 64 (kx,c) K-columns = 128 bytes (rows of neighbouring X OVERLAP in
+  // global memory: dim-1 stride 64 B under a 128-byte dim-0 extent; scripts/probes/tma_overlap_probe.cu), so a
+  // sample is 4 boxes of 81 x 128 B instead of 8 of 81 x 64 B: half the TMA instructions, barrier round trips
+  // and row requests.  A stage holds the 81 landed rows (88 = next multiple of the 8-row swizzle atom); the
+  // 128-row UMMA reads on into the next stage, producing accumulator rows nobody stores.
+  static constexpr int kSteps = 4, kRowBytes = 128, kStageBytes = 88 * 128, kMmaPerStep = 4;
+  static constexpr int kStages = 6;  // 1.5 samples in flight per CTA, two CTAs per SM
+  static constexpr int kEpiWarps = 3;   // 81 rows: quarters 0..2 store
 };
 
 struct ConvArgs {
@@ -71,13 +77,13 @@ conv_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_
   constexpr int kWBytes = (Cfg::kSteps * kWTileBytes + 1023) / 1024 * 1024;
   const uint32_t w_smem = smem_base;
   const uint32_t a_smem = smem_base + kWBytes;
-  const uint32_t bar_base = a_smem + kConvStages * Cfg::kStageBytes;
+  const uint32_t bar_base = a_smem + Cfg::kStages * Cfg::kStageBytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (kConvStages + s); };
-  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kConvStages + a); };
-  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kConvStages + kConvAcc + a); };
-  const uint32_t w_bar = bar_base + 8u * (2 * kConvStages + 2 * kConvAcc);
-  const uint32_t tmem_slot = bar_base + 8u * (2 * kConvStages + 2 * kConvAcc + 1);
+  auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::kStages + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::kStages + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::kStages + kConvAcc + a); };
+  const uint32_t w_bar = bar_base + 8u * (2 * Cfg::kStages + 2 * kConvAcc);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::kStages + 2 * kConvAcc + 1);
   const uint32_t ebuf_base = bar_base + 1024u;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -86,7 +92,7 @@ conv_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_
     prefetch_tensormap(&tma_a2);
     prefetch_tensormap(&tma_w);
     prefetch_tensormap(&tma_c);
-    for (int s = 0; s < kConvStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int a = 0; a < kConvAcc; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
     mbar_init(w_bar, 1);
     fence_mbar_init();
@@ -113,9 +119,9 @@ conv_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_
           mbar_wait(empty_bar(stage), phase ^ 1u);
           mbar_arrive_expect_tx(full_bar(stage), g.box_bytes);
           const uint32_t dst = a_smem + stage * Cfg::kStageBytes;
-          const int tap = st >> 1, dy = st & 1, by = tap >> 1, bx = tap & 1;
-          tma_load_4d(dst, dy ? &tma_a2 : &tma_a, full_bar(stage), 0, bx, by, it);
-          if (++stage == kConvStages) { stage = 0; phase ^= 1u; }
+          const int by = st >> 1, dy = st & 1;
+          tma_load_4d(dst, dy ? &tma_a2 : &tma_a, full_bar(stage), 0, 0, by, it);
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
         }
       }
     }
@@ -123,7 +129,7 @@ conv_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_
     if (lane == 0) {
       // ===== MMA issuer: UMMA 128 x N x 16 over every step's K columns =====
       constexpr uint32_t idesc = idesc_bf16_f32(128, N, false, false);
-      constexpr uint32_t kDescHiSw64 = (512u >> 4) | (1u << 14) | (4u << 29);
+      constexpr uint32_t kDescHiSw64 = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO 1024 B, version 1, 128-byte swizzle
       mbar_wait(w_bar, 0);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
@@ -143,7 +149,7 @@ conv_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_
           for (int k = 0; k < Cfg::kMmaPerStep; ++k)
             mma_f16_lohi(tmem_d, a_lo + 2u * k, kDescHiSw64, b_lo + 2u * k, kDescHiSw64, idesc, (st > 0 || k > 0) ? 1u : 0u);
           mma_commit(empty_bar(stage));
-          if (++stage == kConvStages) { stage = 0; phase ^= 1u; }
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
         }
         mma_commit(tfull_bar(acc));
         if (++acc == kConvAcc) { acc = 0; acc_phase ^= 1u; }
@@ -152,7 +158,7 @@ conv_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_
   } else {
     // ===== epilogue: bias + ReLU + bf16, staged per warp, TMA store clipped to the item's rows =====
     const int quarter = warp & 3;
-    const uint32_t ebuf = ebuf_base + (uint32_t)(warp - 2) * 8192u;
+    const uint32_t ebuf = ebuf_base + (uint32_t)(quarter < Cfg::kEpiWarps ? quarter : 0) * 8192u;
     uint32_t ebuf_it = 0;
     int acc = 0; uint32_t acc_phase = 0;
     float b[N];
@@ -872,7 +878,8 @@ static int launch_conv(const CUtensorMap& ta, const CUtensorMap& ta2, const CUte
                        const ConvArgs& g, cudaStream_t st) {
   using Cfg = ConvCfg<MODE>;
   constexpr int kWBytes = (Cfg::kSteps * N * Cfg::kRowBytes + 1023) / 1024 * 1024;
-  constexpr int kSmem = kWBytes + kConvStages * Cfg::kStageBytes + 1024 + 4 * 2 * 4096 + 1024;
+  // + 5 KB: the last stage's 128-row UMMA read runs 40 rows past its 88-row stage into barriers / epilogue buffers
+  constexpr int kSmem = kWBytes + Cfg::kStages * Cfg::kStageBytes + 1024 + Cfg::kEpiWarps * 2 * 4096 + 1024;
   static bool configured = false;
   auto kern = conv_fwd_tcgen05_kernel<N, MODE>;
   if (!configured) {
@@ -938,21 +945,22 @@ extern "C" int unreal_conv_fwd(const void* in_bf16, int layer, const void* w_tap
     UNREAL_LAUNCH_CHECK("conv1_fwd_tcgen05_kernel");
     return UNREAL_OK;
   } else {
-    // h1 [S][20][20][16]: rows y = 2Y + dy as {32 (dx,c), 10 X, 10 Y, S}, one map per dy
-    const uint64_t dims[4] = {32, 10, 10, (uint64_t)s};
+    // h1 [S][20][20][16]: image rows y = 2Y' + dy as {64 (4 pixels x 16 c), 9 X (stride 2 pixels: rows overlap),
+    // 10 Y', S}, one map per dy; the box at Y' = by is filter row ky = 2by+dy for all 81 outputs
+    const uint64_t dims[4] = {64, 9, 10, (uint64_t)s};
     const uint64_t strides[3] = {64, 1280, 12800};
-    const uint32_t box[4] = {32, 9, 9, 1};
-    rc = make_tma_nd_bf16(&ta, in_bf16, 4, dims, strides, box, 64);
+    const uint32_t box[4] = {64, 9, 9, 1};
+    rc = make_tma_nd_bf16(&ta, in_bf16, 4, dims, strides, box, 128);
     if (rc != UNREAL_OK) return rc;
-    rc = make_tma_nd_bf16(&ta2, reinterpret_cast<const uint8_t*>(in_bf16) + 640, 4, dims, strides, box, 64);
-    g.items = s; g.rows = 81; g.box_bytes = 32 * 9 * 9 * 2;
+    rc = make_tma_nd_bf16(&ta2, reinterpret_cast<const uint8_t*>(in_bf16) + 640, 4, dims, strides, box, 128);
+    g.items = s; g.rows = 81; g.box_bytes = 64 * 9 * 9 * 2;
   }
   if (rc != UNREAL_OK) return rc;
   {
-    const uint64_t dims[2] = {256, (uint64_t)n};
+    const uint64_t dims[2] = {256, (uint64_t)n};                 // [o][(ky,kx,c)]: one 64-column slice per filter row
     const uint64_t strides[1] = {512};
-    const uint32_t box[2] = {32u, (uint32_t)n};
-    rc = make_tma_nd_bf16(&tw, w_taps_bf16, 2, dims, strides, box, 64);
+    const uint32_t box[2] = {64u, (uint32_t)n};
+    rc = make_tma_nd_bf16(&tw, w_taps_bf16, 2, dims, strides, box, 128);
     if (rc != UNREAL_OK) return rc;
   }
   {

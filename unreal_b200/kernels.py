@@ -447,11 +447,11 @@ def s2d_frames(frames, out=None):
 def conv1_w_planes(w16):
   """conv1 filter [8,8,3,16] (bf16) -> [4 taps, 6 channel chunks, 16 outputs, 8] : the un-swizzled
   K-major UMMA B operand of each tap, resident in shared memory for the whole conv1 kernel."""
-  taps = conv_taps(w16, 4).view(16, 4, 64)[:, :, :48]
+  taps = _tap_major(w16, 4).view(16, 4, 64)[:, :, :48]
   return taps.reshape(16, 4, 6, 8).permute(1, 2, 0, 3).contiguous()
 
 
-def conv_taps(w16, stride):
+def _tap_major(w16, stride):
   """HWIO filter [2s,2s,C,O] (bf16) -> tap-major K-major matrix [O, 4*64]: tap t = by*2+bx holds
   W[s*by+dy, s*bx+dx, c, o] in (dy,dx,c) order, zero padded to 64 columns."""
   k, _, c, o = w16.shape
@@ -460,6 +460,15 @@ def conv_taps(w16, stride):
   out = torch.zeros(o, 4, 64, dtype=w16.dtype, device=w16.device)
   out[:, :, :s * s * c] = t
   return out.reshape(o, 256).contiguous()
+
+
+def conv_taps(w16, stride):
+  """conv2's HWIO filter [4,4,16,32] (bf16) -> the K-major matrix [O, 256] the fused kernel keeps resident:
+  K = (ky, kx, c), i.e. one 64-column (128-byte) slice per filter row ky."""
+  k, _, c, o = w16.shape
+  if (k, c, stride) != (4, 16, 2):
+    raise _lib.UnrealError("conv_taps: the fused forward kernel is conv2's geometry (4x4x16, stride 2)")
+  return w16.reshape(k * k * c, o).t().contiguous()
 
 
 def conv_fwd(x, layer, w_taps, bias, out=None):
