@@ -403,19 +403,18 @@ conv1_fwd_tcgen05_kernel(const __nv_bfloat16* __restrict__ xpp, const __nv_bfloa
 // ---- conv1 weight gradient, fused ---------------------------------------------------------------
 // dW[tap][o][(dy,dx,c)] = sum over samples and output pixels of dY[pix, o] * x'[pix + shift(tap), (dy,dx,c)]
 // -- the reduction runs over PIXELS, so both operands are "MN-major" for the tensor core and the same
-// plane-major tiles serve again: x'' planes are the B operand (N = 48 channels = 6 chunks, rows at a
-// 16-byte pitch, tap = start address shift), dY planes [2][S*400][8] (written by unreal_relu_grad) are
-// the A operand (M = 16 outputs = 2 chunks; the UMMA is issued with M = 128 and rows 16.. are
-// ignored).  One work item = 5 output rows = 112 grid rows (K): rows with ox = 20 and rows >= 105
+// plane-major tiles serve again: x'' planes are the A operand (M = 48 channels = 6 chunks of the 16 a
+// 128-row UMMA reads, rows at a 16-byte pitch, tap = start address shift), dY planes [2][S*400][8]
+// (written by unreal_conv2_dgrad_relu / unreal_relu_grad) are the B operand (N = 16 outputs = 2 chunks).  One work item = 5 output rows = 112 grid rows (K): rows with ox = 20 and rows >= 105
 // are zero in the dY tile (zero-initialised once; bulk copies only ever write the twenty real rows
 // of each output row), so whatever finite data x'' holds there contributes nothing.  Each CTA keeps
-// its four [16 x 48] accumulators in TMEM across ALL its items and adds them to global once.
+// its four [48 x 16] accumulators in TMEM across ALL its items and adds them to global once.
 // Traffic per frame: 42 KB of x'' + 12.8 KB of dY, each read once; no patch matrix.
 constexpr int kWgStages = 4;      // two CTAs per SM
 constexpr int kWgStageBytes = 16384;            // x'' tile 12 096 (+192 pad) | dY tile 2 x 112 x 16 = 3 584 (+512)
 constexpr int kWgDyOff = 12288;
 constexpr int kWgDyPlane = 112 * 16;
-constexpr int kWgTail = 32768;                   // A chunks 2..15 of the last stages read (ignored) rows here
+constexpr int kWgTail = 32768;                   // A chunks 6..15 of the last stages read (ignored) rows here
 constexpr int kWgSmem = kWgStages * kWgStageBytes + kWgTail + 1024 + 1024;
 
 __global__ void __launch_bounds__(96, 2)
@@ -475,26 +474,12 @@ conv1_wgrad_tcgen05_kernel(const __nv_bfloat16* __restrict__ xpp, const __nv_bfl
       }
     }
     __syncwarp();
-    // ===== final epilogue (warp 0 owns TMEM lanes 0..31): rows 0..15 = output channels =====
-    mbar_wait(done_bar, 0);
-    fence_after_sync();
-#pragma unroll 1
-    for (int t = 0; t < 4; ++t) {
-      uint32_t v0[32], v1[32];
-      tmem_ld32(tmem_base + (uint32_t)(t * 64), v0);
-      tmem_ld32(tmem_base + (uint32_t)(t * 64 + 32), v1);
-      tmem_ld_wait();
-      if (lane < 16) {
-        float* o = dw + (t * 16 + lane) * 48;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) atomicAdd(o + j, __uint_as_float(v0[j]));
-#pragma unroll
-        for (int j = 0; j < 16; ++j) atomicAdd(o + 32 + j, __uint_as_float(v1[j]));
-      }
-    }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = idesc_bf16_f32(128, 48, true, true);
+      // x'' is the A operand (M = (dy,dx,c) channels: 6 real 8-channel chunks of the 16 a 128-row UMMA reads, the
+      // rest land in accumulator rows nobody reads), dY the B operand (N = 16 outputs): a UMMA costs
+      // max(M,128) * N / 256 cycles, so N = 16 is a third of the tensor-pipe time of the transposed form (N = 48)
+      constexpr uint32_t idesc = idesc_bf16_f32(128, 16, true, true);
       int stage = 0; uint32_t phase = 0;
       bool first = true;
       for (int it = blockIdx.x; it < items; it += gridDim.x) {
@@ -502,15 +487,15 @@ conv1_wgrad_tcgen05_kernel(const __nv_bfloat16* __restrict__ xpp, const __nv_bfl
         fence_after_sync();
         const uint32_t sx = smem_base + stage * kWgStageBytes, sd = sx + kWgDyOff;
         // MN-major un-swizzled descriptors: LBO = 128 B (next 8 pixel rows), SBO = plane stride
-        const uint32_t a_lo0 = (sd >> 4) | ((128u >> 4) << 16), b_lo0 = (sx >> 4) | ((128u >> 4) << 16);
-        constexpr uint32_t a_hi = ((uint32_t)kWgDyPlane >> 4) | (1u << 14), b_hi = ((uint32_t)kC1PlaneBytes >> 4) | (1u << 14);
+        const uint32_t a_lo0 = (sx >> 4) | ((128u >> 4) << 16), b_lo0 = (sd >> 4) | ((128u >> 4) << 16);
+        constexpr uint32_t a_hi = ((uint32_t)kC1PlaneBytes >> 4) | (1u << 14), b_hi = ((uint32_t)kWgDyPlane >> 4) | (1u << 14);
 #pragma unroll
         for (int ks = 0; ks < 7; ++ks) {
           // four independent accumulation chains (one per tap) are interleaved
 #pragma unroll
           for (int t = 0; t < 4; ++t) {
             const uint32_t shift16 = (uint32_t)((t >> 1) * 21 + (t & 1));
-            mma_f16_lohi(tmem_base + (uint32_t)(t * 64), a_lo0 + (uint32_t)(ks * 16), a_hi, b_lo0 + shift16 + (uint32_t)(ks * 16), b_hi,
+            mma_f16_lohi(tmem_base + (uint32_t)(t * 16), a_lo0 + shift16 + (uint32_t)(ks * 16), a_hi, b_lo0 + (uint32_t)(ks * 16), b_hi,
                          idesc, (first && ks == 0) ? 0u : 1u);
           }
         }
@@ -519,6 +504,24 @@ conv1_wgrad_tcgen05_kernel(const __nv_bfloat16* __restrict__ xpp, const __nv_bfl
         if (++stage == kWgStages) { stage = 0; phase ^= 1u; }
       }
       mma_commit(done_bar);
+    }
+    __syncwarp();
+  }
+  if (warp < 2) {
+    // ===== final epilogue: accumulator row m = (dy,dx,c) channel lives in TMEM lane m (warp 0: 0..31, warp 1:
+    // 32..47), columns t*16 + o =====
+    mbar_wait(done_bar, 0);
+    fence_after_sync();
+    const int m = warp * 32 + lane;
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(half * 32), v);     // taps 2*half, 2*half+1
+      tmem_ld_wait();
+      if (m < 48) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) atomicAdd(dw + ((2 * half) * 16 + j) * 48 + m, __uint_as_float(v[j]));
+      }
     }
   }
   __syncwarp();
