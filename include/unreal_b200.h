@@ -243,7 +243,7 @@ int unreal_lstm_cell_bwd(const float* gates_act, const float* c_prev, const floa
  *   unreal_conv_fwd  : layer 1: in = x'' -> out bf16 [S,20,20,16] = relu(conv 8x8 s4 + bias);
  *                        w bf16 [4 taps][6 chunks][16 out][8]: tap t = by*2+bx, W[4by+dy, 4bx+dx, c, o].
  *                      layer 2: in = h1 bf16 [S,20,20,16] -> out bf16 [S,9,9,32] = relu(conv 4x4 s2 + bias);
- *                        w bf16 [32,256]: columns 64t.. of tap t hold W[2by+dy, 2bx+dx, c, o] in (dy,dx,c) order. */
+ *                        w bf16 [32 out, 256]: column (ky*4 + kx)*16 + c holds W[ky, kx, c, o] (HWIO transposed). */
 int unreal_s2d_frames(const void* frames, int dtype, void* out_bf16, int s, void* stream);
 int unreal_conv_fwd(const void* in_bf16, int layer, const void* w_taps_bf16, const float* bias, void* out_bf16, int s,
                     void* stream);
@@ -258,7 +258,7 @@ int unreal_relu_grad(const void* dy, int dy_dtype, const void* y_bf16, void* out
  * dw_taps f32 [4 taps][16 out][48 (dy,dx,c)] += sum_pixels dY * x' (caller zeroes dw_taps). */
 int unreal_conv1_wgrad(const void* xpp_bf16, const void* dy_planes_bf16, float* dw_taps, int s, void* stream);
 /* conv2 filter gradient from h1 [S,20,20,16] bf16 and the masked dY2 [S*81,32] bf16, both read once through
- * TMA boxes: dw_taps f32 [8 (tap,dy)][32 (dx,c)][32 out] += ... (caller zeroes dw_taps). */
+ * TMA boxes: dw_taps f32 [4 ky][64 (kx,c)][32 out] = HWIO [4,4,16,32] += ... (caller zeroes dw_taps). */
 int unreal_conv2_wgrad(const void* h1_bf16, const void* dy_bf16, float* dw_taps, int s, void* stream);
 /* conv2 input gradient (transposed convolution) as a 4-tap implicit GEMM over zero-filling TMA boxes:
  * dy [S*81,32] bf16, w_dtaps bf16 [4 taps][64 (dy,dx,c)][32 out] = W2[2by+dy, 2bx+dx, c, o]

@@ -535,18 +535,19 @@ conv1_wgrad_tcgen05_kernel(const __nv_bfloat16* __restrict__ xpp, const __nv_bfl
 
 
 // ---- conv2 weight gradient, fused ---------------------------------------------------------------
-// dW2[(tap,dy)][(dx,c), o] = sum over samples and output pixels of h1box[pix, (dx,c)] * dY2[pix, o]:
-// the SAME eight 4-D TMA boxes per sample as the forward kernel (81 rows x 64 B, 64-byte swizzle) are
-// now the MN-major A operand (M = 32 (dx,c) values, K = pixels), the sample's masked dY2 [81, 32]
+// dW2[ky][(kx,c), o] = sum over samples and output pixels of h1box[pix, (kx,c)] * dY2[pix, o]:
+// the SAME four 4-D TMA boxes per sample as the forward kernel (81 overlapping rows x 128 B, 128-byte
+// swizzle) are now the MN-major A operand (M = 64 (kx,c) values, K = pixels), the sample's masked dY2 [81, 32]
 // lands through a 3-D box of 96 rows (rows 81..95 are out of bounds = TMA zero fill) as the MN-major
 // B operand.  Tile rows the boxes never write were zeroed once, so K rows 81..95 contribute exactly 0.
-// Eight [32 x 32] accumulators live in TMEM across ALL samples of a CTA and are added to global
+// Four [64 x 32] accumulators live in TMEM across ALL samples of a CTA and are added to global
 // once.  Replaces unreal_im2col (41 KB per sample written and re-read) + the split-K GEMM.
-constexpr int kW2AStages = 8;     // two CTAs per SM
+constexpr int kW2AStages = 6;     // 1.5 samples in flight per CTA, two CTAs per SM
 constexpr int kW2BStages = 3;
-constexpr int kW2ABytes = 128 * 64;
+constexpr int kW2ABytes = 96 * 128;               // 81 landed rows of 128 B (+ rows the zero dY rows cancel)
 constexpr int kW2BBytes = 8192;                   // 96 rows x 64 B used
-constexpr int kW2Smem = kW2AStages * kW2ABytes + kW2BStages * kW2BBytes + 8192 /*tail for the ignored A rows 32..127*/ + 1024 + 1024;
+constexpr int kW2Tail = kW2ABytes;                // the ignored A rows 64..127 of the last stage read here
+constexpr int kW2Smem = kW2AStages * kW2ABytes + kW2BStages * kW2BBytes + kW2Tail + 1024 + 1024;
 
 __global__ void __launch_bounds__(96, 2)
 conv2_wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_a2,
@@ -555,7 +556,7 @@ conv2_wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __gr
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_smem = smem_base;
   const uint32_t b_smem = a_smem + kW2AStages * kW2ABytes;
-  const uint32_t bar_base = b_smem + kW2BStages * kW2BBytes + 8192;
+  const uint32_t bar_base = b_smem + kW2BStages * kW2BBytes + kW2Tail;
   auto fullA = [&](int s) { return bar_base + 8u * s; };
   auto emptyA = [&](int s) { return bar_base + 8u * (kW2AStages + s); };
   auto fullB = [&](int s) { return bar_base + 8u * (2 * kW2AStages + s); };
@@ -564,7 +565,7 @@ conv2_wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __gr
   const uint32_t tmem_slot = done_bar + 8u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  for (uint32_t off = threadIdx.x * 16u; off < (uint32_t)(kW2AStages * kW2ABytes + kW2BStages * kW2BBytes + 8192); off += 96u * 16u)
+  for (uint32_t off = threadIdx.x * 16u; off < (uint32_t)(kW2AStages * kW2ABytes + kW2BStages * kW2BBytes + kW2Tail); off += 96u * 16u)
     asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(smem_base + off), "r"(0u) : "memory");
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&tma_a); prefetch_tensormap(&tma_a2); prefetch_tensormap(&tma_dy);
@@ -591,33 +592,23 @@ conv2_wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __gr
         tma_load_3d(b_smem + sb * kW2BBytes, &tma_dy, fullB(sb), 0, 0, it);
         if (++sb == kW2BStages) { sb = 0; pb ^= 1u; }
 #pragma unroll 1
-        for (int st = 0; st < 8; ++st) {
-          const int tap = st >> 1, dy = st & 1, by = tap >> 1, bx = tap & 1;
+        for (int st = 0; st < 4; ++st) {          // st = filter row ky = 2by + dy
+          const int by = st >> 1, dy = st & 1;
           mbar_wait(emptyA(sa), pa ^ 1u);
-          mbar_arrive_expect_tx(fullA(sa), 32 * 9 * 9 * 2);
-          tma_load_4d(a_smem + sa * kW2ABytes, dy ? &tma_a2 : &tma_a, fullA(sa), 0, bx, by, it);
+          mbar_arrive_expect_tx(fullA(sa), 64 * 9 * 9 * 2);
+          tma_load_4d(a_smem + sa * kW2ABytes, dy ? &tma_a2 : &tma_a, fullA(sa), 0, 0, by, it);
           if (++sa == kW2AStages) { sa = 0; pa ^= 1u; }
         }
       }
     }
     __syncwarp();
-    // ===== final epilogue: TMEM lanes 0..31 = the 32 (dx,c) rows of each of the 8 accumulators =====
-    mbar_wait(done_bar, 0);
-    fence_after_sync();
-#pragma unroll 1
-    for (int st = 0; st < 8; ++st) {
-      uint32_t v[32];
-      tmem_ld32(tmem_base + (uint32_t)(st * 32), v);
-      tmem_ld_wait();
-      float* o = dw + (st * 32 + lane) * 32;
-#pragma unroll
-      for (int j = 0; j < 32; ++j) atomicAdd(o + j, __uint_as_float(v[j]));
-    }
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = idesc_bf16_f32(128, 32, true, true);
-      // MN-major SW64 descriptors: lo = (addr >> 4) | LBO (stride of the next 32-element M chunk; only the
-      // first chunk is real, the others read the next stage / the zeroed tail), hi = SBO 512 B (next 8 pixel rows)
+      // MN-major descriptors.  A (h1 box, 128-byte rows, SW128): lo = (addr >> 4) | LBO (stride of the next
+      // 64-element M chunk; only the first chunk is real, the second reads the next stage / the tail),
+      // hi = SBO 1024 B (next 8 pixel rows).  B (dY2, 64-byte rows, SW64): SBO 512 B.
+      constexpr uint32_t hi_a = (1024u >> 4) | (1u << 14) | (2u << 29);
       constexpr uint32_t hi = (512u >> 4) | (1u << 14) | (4u << 29);
       int sa = 0; uint32_t pa = 0; int sb = 0; uint32_t pb = 0;
       bool first = true;
@@ -625,13 +616,13 @@ conv2_wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __gr
         mbar_wait(fullB(sb), pb);
         const uint32_t b_lo = ((b_smem + sb * kW2BBytes) >> 4) | ((64u >> 4) << 16);
 #pragma unroll 1
-        for (int st = 0; st < 8; ++st) {
+        for (int st = 0; st < 4; ++st) {
           mbar_wait(fullA(sa), pa);
           fence_after_sync();
           const uint32_t a_lo = ((a_smem + sa * kW2ABytes) >> 4) | (((uint32_t)kW2ABytes >> 4) << 16);
 #pragma unroll
           for (int ks = 0; ks < 6; ++ks)
-            mma_f16_lohi(tmem_base + (uint32_t)(st * 32), a_lo + (uint32_t)(ks * 64), hi, b_lo + (uint32_t)(ks * 64), hi, idesc,
+            mma_f16_lohi(tmem_base + (uint32_t)(st * 32), a_lo + (uint32_t)(ks * 128), hi_a, b_lo + (uint32_t)(ks * 64), hi, idesc,
                          (first && ks == 0) ? 0u : 1u);
           mma_commit(emptyA(sa));
           if (++sa == kW2AStages) { sa = 0; pa ^= 1u; }
@@ -641,6 +632,23 @@ conv2_wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __gr
         if (++sb == kW2BStages) { sb = 0; pb ^= 1u; }
       }
       mma_commit(done_bar);
+    }
+    __syncwarp();
+  }
+  if (warp < 2) {
+    // ===== final epilogue: accumulator ky, row m = (kx,c) in TMEM lane m (warp 0: 0..31, warp 1: 32..63),
+    // column o -> dW2 in HWIO order [ky][(kx,c)][o] =====
+    mbar_wait(done_bar, 0);
+    fence_after_sync();
+    const int m = warp * 32 + lane;
+#pragma unroll 1
+    for (int st = 0; st < 4; ++st) {
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(st * 32), v);
+      tmem_ld_wait();
+      float* o = dw + (st * 64 + m) * 32;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) atomicAdd(o + j, __uint_as_float(v[j]));
     }
   }
   __syncwarp();
@@ -1002,12 +1010,12 @@ extern "C" int unreal_conv2_wgrad(const void* h1_bf16, const void* dy_bf16, floa
   UNREAL_REQUIRE(aligned16(h1_bf16) && aligned16(dy_bf16) && aligned16(dw_taps), "unreal_conv2_wgrad: 16-byte alignment");
   CUtensorMap ta, ta2, td;
   {
-    const uint64_t dims[4] = {32, 10, 10, (uint64_t)s};
+    const uint64_t dims[4] = {64, 9, 10, (uint64_t)s};          // the forward's overlapping 128-byte rows
     const uint64_t strides[3] = {64, 1280, 12800};
-    const uint32_t box[4] = {32, 9, 9, 1};
-    int rc = make_tma_nd_bf16(&ta, h1_bf16, 4, dims, strides, box, 64);
+    const uint32_t box[4] = {64, 9, 9, 1};
+    int rc = make_tma_nd_bf16(&ta, h1_bf16, 4, dims, strides, box, 128);
     if (rc != UNREAL_OK) return rc;
-    rc = make_tma_nd_bf16(&ta2, reinterpret_cast<const uint8_t*>(h1_bf16) + 640, 4, dims, strides, box, 64);
+    rc = make_tma_nd_bf16(&ta2, reinterpret_cast<const uint8_t*>(h1_bf16) + 640, 4, dims, strides, box, 128);
     if (rc != UNREAL_OK) return rc;
   }
   {

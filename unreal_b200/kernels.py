@@ -525,11 +525,10 @@ def conv2_wgrad(h1, dy16):
   """h1 [S,20,20,16] bf16, dy16 [S*81, 32] bf16 (masked gradient of conv2's output) -> filter gradient
   in HWIO layout [4,4,16,32] f32, the im2col done by TMA boxes."""
   s = h1.shape[0]
-  acc = torch.zeros(8, 32, 32, dtype=torch.float32, device=h1.device)
+  acc = torch.zeros(4, 4, 16, 32, dtype=torch.float32, device=h1.device)     # the kernel accumulates in HWIO order
   call("unreal_conv2_wgrad", ptr(h1, torch.bfloat16, "h1"), ptr(dy16, torch.bfloat16, "dy16"), ptr(acc, torch.float32), s,
        stream_ptr())
-  # acc[(by,bx,dy), (dx,c), o] -> W[2by+dy, 2bx+dx, c, o]
-  return acc.view(2, 2, 2, 2, 16, 32).permute(0, 2, 1, 3, 4, 5).reshape(4, 4, 16, 32)
+  return acc
 
 
 def conv2_dgrad_taps(w16):
