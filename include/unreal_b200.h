@@ -200,6 +200,11 @@ int unreal_grad_sumsq(const float* grad, int64_t p, double* sumsq, void* stream)
 int unreal_rmsprop_update(float* var, float* rms, float* mom, const float* grad, int64_t p,
                           const double* sumsq, float grad_scale, float lr, float decay, float momentum,
                           float eps, float clip_norm, float* grad_norm, void* stream);
+/* same, with the learning rate read from device memory (lr_dev [1] f32) when the kernel runs: a CUDA graph
+ * that captured the update keeps following the annealed rate of trainer.py:140-144. */
+int unreal_rmsprop_update_dlr(float* var, float* rms, float* mom, const float* grad, int64_t p,
+                              const double* sumsq, float grad_scale, const float* lr_dev, float decay, float momentum,
+                              float eps, float clip_norm, float* grad_norm, void* stream);
 
 /* ---- K7: dense layers of UnrealModel (model/model.py:281-598) on the tcgen05 tensor path ------
  * C[M,N] (=|+=) act(A*B + bias + add), bf16 operands, fp32 accumulation in TMEM.

@@ -28,18 +28,32 @@ a = torch.zeros(T, N, A, device=dev).scatter_(2, torch.randint(0, A, (T, N, 1), 
 feed = {"base": dict(images=img, lar=lar, a=a, adv=torch.randn(T, N, device=dev, generator=g),
                      R=torch.randn(T, N, device=dev, generator=g), mask=torch.ones(T, N, device=dev),
                      c0=torch.zeros(N, 256, device=dev), h0=torch.zeros(N, 256, device=dev))}
+graph = bool(int(sys.argv[3])) if len(sys.argv) > 3 else True
+lr = torch.full((1,), 7e-4, device=dev)      # device scalar: K6 reads it when it runs, so a graph follows the anneal
 for _ in range(3):
-  out = m.update(feed, 7e-4, ap)
+  out = m.update(feed, lr, ap)
+torch.cuda.synchronize()
+if graph:                                    # the whole update (fwd, bwd, clip + RMSProp, shadow refresh) as ONE CUDA graph
+  g = torch.cuda.CUDAGraph()
+  with torch.cuda.graph(g):
+    out = m.update(feed, lr, ap)
+  step = g.replay
+else:
+  def step():
+    global out
+    out = m.update(feed, lr, ap)
+for _ in range(2):
+  step()
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
 for _ in range(iters):
-  out = m.update(feed, 7e-4, ap)
+  step()
 e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / iters
 samples = N * T
-print(json.dumps(dict(workload="configs[4] slice: %d envs x T=20, u8 84x84x3 frames, A=3, G=2, A3C-LSTM fwd/bwd + RMSProp" % N,
+print(json.dumps(dict(cuda_graph=graph, workload="configs[4] slice: %d envs x T=20, u8 84x84x3 frames, A=3, G=2, A3C-LSTM fwd/bwd + RMSProp" % N,
                       ms_per_update=ms, samples_per_s=samples / (ms * 1e-3), model_tflops=samples * 18.5e6 / (ms * 1e-3) / 1e12,
                       frac_of_sustained_bf16_peak=samples * 18.5e6 / (ms * 1e-3) / 1e12 / 1393.1,
                       finite=bool(torch.isfinite(out["total"])), params=m.num_parameters)))

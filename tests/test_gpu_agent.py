@@ -112,9 +112,10 @@ def test_graphed_data_phase_equals_eager():
   for tr in (tr_e, tr_g):
     while not tr.experience.is_full():
       tr.process(None, 0)
-  for it in range(4):
-    de, _ = tr_e.process(None, 0)
-    dg, _ = tr_g.process(None, 0)
+  for it in range(5):
+    # the learner update is captured too (iteration 1) and replayed with the annealed rate (global_t moves)
+    de, _ = tr_e.process(None, it * 2000000)
+    dg, _ = tr_g.process(None, it * 2000000)
     assert de == dg
     fe, fg = tr_e.last_feed, tr_g.last_feed
     assert torch.equal(fe['base']['a'], fg['base']['a']), it
@@ -124,7 +125,10 @@ def test_graphed_data_phase_equals_eager():
       assert torch.equal(fe[k]['start'], fg[k]['start']), (it, k)
     assert torch.allclose(fe['base']['R'], fg['base']['R'], rtol=1e-3, atol=1e-4)
     assert torch.allclose(fe['pc']['R'], fg['pc']['R'], rtol=1e-3, atol=1e-4)
+  assert tr_g._ugraph is not None, "the update graph must have been captured"
   assert torch.allclose(tr_e.local_network.flat, tr_g.local_network.flat, rtol=1e-3, atol=1e-5)
+  for k in ("total", "grad_norm"):
+    assert torch.allclose(tr_e.last_losses[k].float(), tr_g.last_losses[k].float(), rtol=2e-3, atol=1e-4), k
   tr_e.stop(); tr_g.stop()
 
 

@@ -68,6 +68,8 @@ SIGNATURES = {
     "unreal_grad_sumsq": (c_int, [P, c_int64, P, P]),
     "unreal_rmsprop_update": (c_int, [P, P, P, P, c_int64, P, c_float, c_float, c_float, c_float, c_float,
                                       c_float, P, P]),
+    "unreal_rmsprop_update_dlr": (c_int, [P, P, P, P, c_int64, P, c_float, P, c_float, c_float, c_float,
+                                          c_float, P, P]),
     "unreal_gemm_bf16": (c_int, [P, c_int64, c_int, P, c_int64, c_int, P, c_int64, c_int, P, P, c_int, c_int, c_int,
                                  c_int, c_int, c_int, P]),
     "unreal_im2col": (c_int, [P, c_int, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),

@@ -53,7 +53,8 @@ template <bool kMom>
 __global__ void __launch_bounds__(256) rmsprop_kernel(float* __restrict__ var, float* __restrict__ rms,
                                                       float* __restrict__ mom, const float* __restrict__ grad,
                                                       int64_t p, const double* __restrict__ sumsq, RmsArgs a,
-                                                      float* grad_norm) {
+                                                      float* grad_norm, const float* __restrict__ lr_dev) {
+  if (lr_dev != nullptr) a.lr = *lr_dev;     // learning rate from device memory (CUDA-graph replays with an annealed rate)
   // norm of the (scaled) gradient and TF's clip factor, recomputed per thread from one double
   float norm = 0.f, scale = a.grad_scale;
   if (sumsq != nullptr) {
@@ -113,9 +114,9 @@ extern "C" int unreal_grad_sumsq(const float* grad, int64_t p, double* sumsq, vo
   return UNREAL_OK;
 }
 
-extern "C" int unreal_rmsprop_update(float* var, float* rms, float* mom, const float* grad, int64_t p,
-                                     const double* sumsq, float grad_scale, float lr, float decay, float momentum,
-                                     float eps, float clip_norm, float* grad_norm, void* stream) {
+static int rmsprop_launch(float* var, float* rms, float* mom, const float* grad, int64_t p, const double* sumsq,
+                          float grad_scale, float lr, const float* lr_dev, float decay, float momentum, float eps,
+                          float clip_norm, float* grad_norm, void* stream) {
   UNREAL_REQUIRE(p >= 0, "unreal_rmsprop_update: negative size");
   if (p == 0) return UNREAL_OK;
   UNREAL_REQUIRE(var && rms && grad, "unreal_rmsprop_update: var, rms and grad must be non-null");
@@ -126,8 +127,23 @@ extern "C" int unreal_rmsprop_update(float* var, float* rms, float* mom, const f
   RmsArgs a{grad_scale, lr, 1.0f - decay, momentum, eps, clip_norm};
   int grid = grid_for(p, 4);
   if (grid <= 0) return UNREAL_ECUDA;
-  if (mom != nullptr) rmsprop_kernel<true><<<grid, 256, 0, as_stream(stream)>>>(var, rms, mom, grad, p, sumsq, a, grad_norm);
-  else rmsprop_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(var, rms, nullptr, grad, p, sumsq, a, grad_norm);
+  if (mom != nullptr) rmsprop_kernel<true><<<grid, 256, 0, as_stream(stream)>>>(var, rms, mom, grad, p, sumsq, a, grad_norm, lr_dev);
+  else rmsprop_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(var, rms, nullptr, grad, p, sumsq, a, grad_norm, lr_dev);
   UNREAL_LAUNCH_CHECK("rmsprop_kernel");
   return UNREAL_OK;
+}
+
+extern "C" int unreal_rmsprop_update(float* var, float* rms, float* mom, const float* grad, int64_t p,
+                                     const double* sumsq, float grad_scale, float lr, float decay, float momentum,
+                                     float eps, float clip_norm, float* grad_norm, void* stream) {
+  return rmsprop_launch(var, rms, mom, grad, p, sumsq, grad_scale, lr, nullptr, decay, momentum, eps, clip_norm, grad_norm,
+                        stream);
+}
+
+extern "C" int unreal_rmsprop_update_dlr(float* var, float* rms, float* mom, const float* grad, int64_t p,
+                                         const double* sumsq, float grad_scale, const float* lr_dev, float decay,
+                                         float momentum, float eps, float clip_norm, float* grad_norm, void* stream) {
+  UNREAL_REQUIRE(lr_dev != nullptr, "unreal_rmsprop_update_dlr: lr_dev is null");
+  return rmsprop_launch(var, rms, mom, grad, p, sumsq, grad_scale, 0.f, lr_dev, decay, momentum, eps, clip_norm, grad_norm,
+                        stream);
 }

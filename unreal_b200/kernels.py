@@ -345,6 +345,12 @@ def grad_sumsq(grad, out=None):
 
 
 def rmsprop_update(var, rms, mom, grad, sumsq, lr, decay, momentum, eps, clip_norm, grad_scale=1.0, grad_norm=None):
+  if isinstance(lr, torch.Tensor):       # learning rate in device memory (read when the kernel runs)
+    call("unreal_rmsprop_update_dlr", ptr(var, torch.float32, "var"), ptr(rms, torch.float32, "rms"),
+         ptr(mom, torch.float32, "mom"), ptr(grad, torch.float32, "grad"), var.numel(),
+         ptr(sumsq, torch.float64, "sumsq"), float(grad_scale), ptr(lr, torch.float32, "lr"), float(decay), float(momentum),
+         float(eps), float(clip_norm), ptr(grad_norm, torch.float32, "grad_norm"), stream_ptr())
+    return grad_norm
   call("unreal_rmsprop_update", ptr(var, torch.float32, "var"), ptr(rms, torch.float32, "rms"),
        ptr(mom, torch.float32, "mom"), ptr(grad, torch.float32, "grad"), var.numel(),
        ptr(sumsq, torch.float64, "sumsq"), float(grad_scale), float(lr), float(decay), float(momentum), float(eps),

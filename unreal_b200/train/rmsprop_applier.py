@@ -144,6 +144,8 @@ class RMSPropApplier(object):
     lr = self._learning_rate if learning_rate is None else learning_rate
     if callable(lr):
       lr = lr()
+    if isinstance(lr, torch.Tensor) and lr.is_cuda:
+      return lr                             # device scalar: read by K6 when it runs (CUDA-graph replays)
     return float(lr)
 
   def _apply_gradients(self, global_var_list, local_grad_list, name=None, thread_index=None, learning_rate=None):

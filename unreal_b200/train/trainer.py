@@ -125,6 +125,10 @@ class Trainer(object):
     # frame, no f32 frame and no separate s2d pass); needs a network with the fused conv1 kernel
     self.obs_dtype = torch.bfloat16 if obs_s2d else torch.float32
     self._graph = None
+    self.graph_update = True                # with use_graphs: capture the learner update as well (single process)
+    self._ugraph = None
+    self._ugraph_out = None
+    self._lr_dev = None
 
   # -- RandomState hand-over for the single-env drop-in case ---------------------------------
   def _rng_in(self):
@@ -344,6 +348,32 @@ class Trainer(object):
     self._graph.replay()
     return dict(self._graph_feed)
 
+  def _update(self, feed, learning_rate):
+    """The learner step (`sess.run(apply_gradients)`, trainer.py:543-559).  With use_graphs and a single
+    process the whole update -- feed conversion, forward, backward, clip + RMSProp, shadow refresh, some
+    hundreds of launches -- is captured ONCE into a CUDA graph over the data phase's static feed tensors
+    and replayed; the annealed learning rate travels through a device scalar that K6 reads when it runs."""
+    net, ap = self.local_network, self.grad_applier
+    distributed = ap is not None and getattr(ap, "_world", None) is not None and ap._world()[0] > 1
+    if not (self.use_graphs and self.graph_update) or distributed or self._graph is None:
+      return net.update(feed, learning_rate, ap)
+    if self._lr_dev is None:
+      self._lr_dev = torch.zeros(1, dtype=torch.float32, device=self.device)
+    self._lr_dev.fill_(float(learning_rate))
+    if self._ugraph is None:
+      if any(feed[k] is not self._graph_feed[k] for k in self._graph_feed):
+        return net.update(feed, learning_rate, ap)     # the capturing iteration of the data phase: eager feed
+      static_feed = dict(self._graph_feed)
+      out = net.update(static_feed, self._lr_dev, ap)  # this iteration's update, eagerly (also warms every lazy path)
+      torch.cuda.synchronize(self.device)
+      g = torch.cuda.CUDAGraph()
+      with torch.cuda.graph(g):                        # recorded, not executed
+        self._ugraph_out = net.update(static_feed, self._lr_dev, ap)
+      self._ugraph = g
+      return out
+    self._ugraph.replay()
+    return self._ugraph_out
+
   # -- one iteration  trainer.py:438-636 -------------------------------------------------------
   def process(self, sess=None, global_t=0, summary_writer=None, summary_op_dict=None, score_input=None,
               sr_input=None, eval_input=None, entropy_input=None, term_global_t=None, losses_input=None):
@@ -363,7 +393,7 @@ class Trainer(object):
         self._rng_out()
       self.last_feed = feed
       if hasattr(self.local_network, 'update'):
-        self.last_losses = self.local_network.update(feed, cur_learning_rate, self.grad_applier)
+        self.last_losses = self._update(feed, cur_learning_rate)
       self.local_t += int(self._pending_local_t)
       if hasattr(self, 'start_time'):
         self._print_log(global_t)
