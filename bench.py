@@ -206,14 +206,14 @@ def measure_agent(torch, dist, dev, rank, world, envs, updates, history=2000):
   for _ in range(2):
     tr.process(None, 0)
   upd = []
-  orig = net.update
+  orig = tr._update          # the learner step: eager net.update() or the replay of its CUDA graph
 
-  def timed(feed, lr, ap):
+  def timed(feed, lr):
     a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
-    a.record(); out = orig(feed, lr, ap); b.record(); upd.append((a, b))
+    a.record(); out = orig(feed, lr); b.record(); upd.append((a, b))
     return out
 
-  net.update = timed
+  tr._update = timed
   e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
   if world > 1:
     dist.barrier()
@@ -242,7 +242,8 @@ def measure_agent(torch, dist, dev, rank, world, envs, updates, history=2000):
           "unit": "env-steps/s", "ms_per_update": ms / updates, "model_update_ms": upd_ms,
           "updates_per_s": updates / (ms * 1e-3), "ring_fill_s": fill_s, "params": net.num_parameters,
           "finite": bool(all(np.isfinite(v) for v in losses.values())), "grad_norm": losses.get("grad_norm"),
-          "peak_mem_gb": mem, "timing": "CUDA events around %d Trainer.process() calls, max over ranks" % updates}
+          "peak_mem_gb": mem, "update_cuda_graph": tr._ugraph is not None,
+          "timing": "CUDA events around %d Trainer.process() calls, max over ranks" % updates}
 
 
 def agent_cpu_baseline(envs=4, seconds=10.0):
