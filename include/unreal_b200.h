@@ -262,6 +262,10 @@ int unreal_relu_grad(const void* dy, int dy_dtype, const void* y_bf16, void* out
  * ([2][S*400][8] bf16 from unreal_relu_grad with out_planes = 1) once each:
  * dw_taps f32 [4 taps][16 out][48 (dy,dx,c)] += sum_pixels dY * x' (caller zeroes dw_taps). */
 int unreal_conv1_wgrad(const void* xpp_bf16, const void* dy_planes_bf16, float* dw_taps, int s, void* stream);
+/* same, with the dY planes on the x'' grid's 21-pixel row pitch ([2][S*420][8], column ox = 20 zero; written by
+ * unreal_conv2_dgrad_relu with pitch21 = 1): one 1680-byte bulk copy per plane and work item instead of five
+ * 320-byte ones. */
+int unreal_conv1_wgrad_p21(const void* xpp_bf16, const void* dy_planes21_bf16, float* dw_taps, int s, void* stream);
 /* conv2 filter gradient from h1 [S,20,20,16] bf16 and the masked dY2 [S*81,32] bf16, both read once through
  * TMA boxes: dw_taps f32 [4 ky][64 (kx,c)][32 out] = HWIO [4,4,16,32] += ... (caller zeroes dw_taps). */
 int unreal_conv2_wgrad(const void* h1_bf16, const void* dy_bf16, float* dw_taps, int s, void* stream);
@@ -271,10 +275,11 @@ int unreal_conv2_wgrad(const void* h1_bf16, const void* dy_bf16, float* dw_taps,
 int unreal_conv2_dgrad(const void* dy_bf16, const void* w_dtaps_bf16, void* dh1_bf16, int s, void* stream);
 /* unreal_conv2_dgrad fused with the ReLU gradient of the layer below (conv1, model.py:285: h1 = relu(...)):
  * the transposed convolution's result is masked by h1 > 0, rounded to bf16 and written as the two
- * 8-channel planes [2][S*400][8] that unreal_conv1_wgrad consumes; db1 [16] f32 (caller-zeroed, atomically
+ * 8-channel planes [2][S*400][8] that unreal_conv1_wgrad consumes (pitch21 != 0: [2][S*420][8] on a 21-pixel row
+ * pitch with a zero column, for unreal_conv1_wgrad_p21); db1 [16] f32 (caller-zeroed, atomically
  * accumulated, nullable) receives conv1's bias gradient.  Replaces unreal_conv2_dgrad + unreal_relu_grad. */
 int unreal_conv2_dgrad_relu(const void* dy_bf16, const void* w_dtaps_bf16, const void* h1_bf16,
-                            void* dy1_planes_bf16, float* db1, int s, void* stream);
+                            void* dy1_planes_bf16, float* db1, int s, int pitch21, void* stream);
 /* The pixel-control head's two transposed convolutions as ONE 8-channel deconv, forward (model.py:418-430,
  * :803-820 conv2d_transpose 4x4 stride 2 VALID + bias + ReLU): h bf16 [S,9,9,32], w_dtaps bf16
  * [4 taps, 32 (dy,dx,c8), 32 in] (the merged [kh,kw,8,32] filter in unreal_conv2_dgrad's tap order),

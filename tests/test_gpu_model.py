@@ -334,6 +334,12 @@ def test_conv2_dgrad_relu_equals_dgrad_then_relu_grad():
     planes, db = K.conv2_dgrad_relu(dy, taps, h1)
     assert torch.equal(planes, want_planes), s
     assert torch.allclose(db, want_db, rtol=1e-4, atol=1e-4 * float(want_db.abs().max() + 1e-6)), s
+    # the 21-pixel-pitch form conv1's wgrad copies in one piece per plane: same values, zero column 20
+    p21, _ = K.conv2_dgrad_relu(dy, taps, h1, pitch21=True)
+    p21 = p21.view(2, s, 20, 21, 8)
+    assert torch.equal(p21[:, :, :, :20], want_planes.view(2, s, 20, 20, 8)) and not p21[:, :, :, 20].any()
+    xpp = torch.rand(s, 6, 441, 8, device=dev, generator=g).to(torch.bfloat16)
+    assert torch.allclose(K.conv1_wgrad(xpp, p21.view(2, s * 420, 8)), K.conv1_wgrad(xpp, want_planes), rtol=1e-4, atol=1e-4)
 
 
 def test_fused_encoder_backward_equals_layerwise_backward():

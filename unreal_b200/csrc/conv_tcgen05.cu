@@ -419,7 +419,7 @@ constexpr int kWgSmem = kWgStages * kWgStageBytes + kWgTail + 1024 + 1024;
 
 __global__ void __launch_bounds__(96, 2)
 conv1_wgrad_tcgen05_kernel(const __nv_bfloat16* __restrict__ xpp, const __nv_bfloat16* __restrict__ dyp,
-                           float* __restrict__ dw, int items, int64_t dy_plane_elems) {
+                           float* __restrict__ dw, int items, int64_t dy_plane_elems, int pitch21) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = smem_base + kWgStages * kWgStageBytes + kWgTail;
@@ -451,7 +451,7 @@ conv1_wgrad_tcgen05_kernel(const __nv_bfloat16* __restrict__ xpp, const __nv_bfl
       int stage = 0; uint32_t phase = 0;
       for (int it = blockIdx.x; it < items; it += gridDim.x) {
         mbar_wait(empty_bar(stage), phase ^ 1u);
-        mbar_arrive_expect_tx(full_bar(stage), kC1BoxBytes + 10 * 320);
+        mbar_arrive_expect_tx(full_bar(stage), kC1BoxBytes + (pitch21 ? 2 * 1680 : 10 * 320));
         const int64_t smp = it >> 2;
         const int rb = it & 3;
         const uint32_t dst = smem_base + stage * kWgStageBytes;
@@ -461,14 +461,24 @@ conv1_wgrad_tcgen05_kernel(const __nv_bfloat16* __restrict__ xpp, const __nv_bfl
           asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                        ::"r"(dst + q * kC1PlaneBytes), "l"(xs + (int64_t)q * 441 * 16), "r"(kC1PlaneBytes),
                          "r"(full_bar(stage)) : "memory");
+        if (pitch21) {
+          // planes already on the x'' grid's 21-pixel row pitch (column 20 zero): ONE 1680-byte copy per plane
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          const uint8_t* ds = reinterpret_cast<const uint8_t*>(dyp) + ((int64_t)c * dy_plane_elems / 8 + smp * 400 + rb * 100) * 16;
-#pragma unroll
-          for (int oyl = 0; oyl < 5; ++oyl)
+          for (int c = 0; c < 2; ++c) {
+            const uint8_t* ds = reinterpret_cast<const uint8_t*>(dyp) + ((int64_t)c * dy_plane_elems / 8 + smp * 420 + rb * 105) * 16;
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"(dst + kWgDyOff + c * kWgDyPlane + oyl * 21 * 16), "l"(ds + oyl * 320), "r"(320),
-                           "r"(full_bar(stage)) : "memory");
+                         ::"r"(dst + kWgDyOff + c * kWgDyPlane), "l"(ds), "r"(1680), "r"(full_bar(stage)) : "memory");
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            const uint8_t* ds = reinterpret_cast<const uint8_t*>(dyp) + ((int64_t)c * dy_plane_elems / 8 + smp * 400 + rb * 100) * 16;
+#pragma unroll
+            for (int oyl = 0; oyl < 5; ++oyl)
+              asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                           ::"r"(dst + kWgDyOff + c * kWgDyPlane + oyl * 21 * 16), "l"(ds + oyl * 320), "r"(320),
+                             "r"(full_bar(stage)) : "memory");
+          }
         }
         if (++stage == kWgStages) { stage = 0; phase ^= 1u; }
       }
@@ -685,7 +695,7 @@ template <int CO>
 __global__ void __launch_bounds__(kConvThreads, 2)
 conv2_dgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_w,
                            void* __restrict__ out_raw, const float* __restrict__ bias, int samples,
-                           const __nv_bfloat16* __restrict__ mask_y, float* __restrict__ db) {
+                           const __nv_bfloat16* __restrict__ mask_y, float* __restrict__ db, int pitch21) {
   constexpr int kN = 4 * CO;                         // (dy, dx, c) accumulator columns
   constexpr int kTapBytes = kN * 64;                 // one resident tap filter [kN rows x 64 B]
   extern __shared__ uint8_t smem_raw[];
@@ -817,7 +827,10 @@ conv2_dgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __gr
         // gradient -- the dense gradient is never written and no separate relu_grad pass reads it back
         if (r < 100) {
           const int64_t pix = ((int64_t)it * 20 + 2 * Y) * 20 + 2 * X;
-          const int64_t plane = (int64_t)samples * 400;
+          // output pixel index: dense [S*400], or on conv1-wgrad's 21-pixel row pitch [S*420] (column 20 zero)
+          const int rowp = pitch21 ? 21 : 20;
+          const int64_t opix = ((int64_t)it * 20 + 2 * Y) * rowp + 2 * X;
+          const int64_t plane = (int64_t)samples * 20 * rowp;
 #pragma unroll
           for (int dy = 0; dy < 2; ++dy) {
             const uint32_t* v = dy ? v1 : v0;
@@ -837,8 +850,12 @@ conv2_dgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __gr
                 const float2 f = __bfloat1622float2(p);      // the bias gradient sums the ROUNDED values
                 dbacc[(q & 1) * 8 + 2 * j] += f.x; dbacc[(q & 1) * 8 + 2 * j + 1] += f.y;
               }
-              __nv_bfloat16* dst = out + ((q & 1) * plane + pix + dy * 20 + (q >> 1)) * 8;
+              __nv_bfloat16* dst = out + ((q & 1) * plane + opix + dy * rowp + (q >> 1)) * 8;
               *reinterpret_cast<uint4*>(dst) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            }
+            if (pitch21 && X == 9) {           // the zero column ox = 20 of both planes
+              *reinterpret_cast<uint4*>(out + (opix + dy * 21 + 2) * 8) = make_uint4(0u, 0u, 0u, 0u);
+              *reinterpret_cast<uint4*>(out + (plane + opix + dy * 21 + 2) * 8) = make_uint4(0u, 0u, 0u, 0u);
             }
           }
         }
@@ -985,8 +1002,8 @@ extern "C" int unreal_conv_fwd(const void* in_bf16, int layer, const void* w_tap
   return launch_conv<32, 2>(ta, ta2, tw, tc, g, as_stream(stream));
 }
 
-extern "C" int unreal_conv1_wgrad(const void* xpp_bf16, const void* dy_planes_bf16, float* dw_taps, int s,
-                                  void* stream) {
+static int conv1_wgrad_launch(const void* xpp_bf16, const void* dy_planes_bf16, float* dw_taps, int s, int pitch21,
+                              void* stream) {
   UNREAL_REQUIRE(xpp_bf16 && dy_planes_bf16 && dw_taps && s > 0, "unreal_conv1_wgrad: null buffer or s <= 0");
   UNREAL_REQUIRE(aligned16(xpp_bf16) && aligned16(dy_planes_bf16) && aligned16(dw_taps),
                  "unreal_conv1_wgrad: buffers must be 16-byte aligned");
@@ -1000,9 +1017,18 @@ extern "C" int unreal_conv1_wgrad(const void* xpp_bf16, const void* dy_planes_bf
   const int items = s * 4;
   conv1_wgrad_tcgen05_kernel<<<items < 2 * sms ? items : 2 * sms, 96, kWgSmem, as_stream(stream)>>>(
       reinterpret_cast<const __nv_bfloat16*>(xpp_bf16), reinterpret_cast<const __nv_bfloat16*>(dy_planes_bf16), dw_taps,
-      items, (int64_t)s * 400 * 8);
+      items, (int64_t)s * (pitch21 ? 420 : 400) * 8, pitch21);
   UNREAL_LAUNCH_CHECK("conv1_wgrad_tcgen05_kernel");
   return UNREAL_OK;
+}
+
+extern "C" int unreal_conv1_wgrad(const void* xpp_bf16, const void* dy_planes_bf16, float* dw_taps, int s, void* stream) {
+  return conv1_wgrad_launch(xpp_bf16, dy_planes_bf16, dw_taps, s, 0, stream);
+}
+
+extern "C" int unreal_conv1_wgrad_p21(const void* xpp_bf16, const void* dy_planes21_bf16, float* dw_taps, int s,
+                                      void* stream) {
+  return conv1_wgrad_launch(xpp_bf16, dy_planes21_bf16, dw_taps, s, 1, stream);
 }
 
 extern "C" int unreal_conv2_wgrad(const void* h1_bf16, const void* dy_bf16, float* dw_taps, int s, void* stream) {
@@ -1039,7 +1065,7 @@ extern "C" int unreal_conv2_wgrad(const void* h1_bf16, const void* dy_bf16, floa
 
 template <int CO>
 static int launch_deconv(const void* dy_bf16, const void* w_dtaps_bf16, void* out, const float* bias, int s, void* stream,
-                         const void* mask_y = nullptr, float* db = nullptr) {
+                         const void* mask_y = nullptr, float* db = nullptr, int pitch21 = 0) {
   CUtensorMap ta, tw;
   {
     const uint64_t dims[4] = {32, 9, 9, (uint64_t)s};           // dY2 [S][9 Y][9 X][32 o]
@@ -1063,7 +1089,7 @@ static int launch_deconv(const void* dy_bf16, const void* w_dtaps_bf16, void* ou
   const int sms = sm_count();
   if (sms <= 0) return UNREAL_ECUDA;
   conv2_dgrad_tcgen05_kernel<CO><<<s < 2 * sms ? s : 2 * sms, kConvThreads, kDgSmem, as_stream(stream)>>>(
-      ta, tw, out, bias, s, reinterpret_cast<const __nv_bfloat16*>(mask_y), db);
+      ta, tw, out, bias, s, reinterpret_cast<const __nv_bfloat16*>(mask_y), db, pitch21);
   UNREAL_LAUNCH_CHECK("conv2_dgrad_tcgen05_kernel");
   return UNREAL_OK;
 }
@@ -1075,11 +1101,11 @@ extern "C" int unreal_conv2_dgrad(const void* dy_bf16, const void* w_dtaps_bf16,
 }
 
 extern "C" int unreal_conv2_dgrad_relu(const void* dy_bf16, const void* w_dtaps_bf16, const void* h1_bf16,
-                                       void* dy1_planes_bf16, float* db1, int s, void* stream) {
+                                       void* dy1_planes_bf16, float* db1, int s, int pitch21, void* stream) {
   UNREAL_REQUIRE(dy_bf16 && w_dtaps_bf16 && h1_bf16 && dy1_planes_bf16 && s > 0, "unreal_conv2_dgrad_relu: null buffer or s <= 0");
   UNREAL_REQUIRE(aligned16(dy_bf16) && aligned16(w_dtaps_bf16) && aligned16(h1_bf16) && aligned16(dy1_planes_bf16),
                  "unreal_conv2_dgrad_relu: 16-byte alignment");
-  return launch_deconv<16>(dy_bf16, w_dtaps_bf16, dy1_planes_bf16, nullptr, s, stream, h1_bf16, db1);
+  return launch_deconv<16>(dy_bf16, w_dtaps_bf16, dy1_planes_bf16, nullptr, s, stream, h1_bf16, db1, pitch21 ? 1 : 0);
 }
 
 extern "C" int unreal_pc_deconv_fwd(const void* h_bf16, const void* w_dtaps_bf16, const float* bias8, float* y8, int s,

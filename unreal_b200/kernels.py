@@ -509,8 +509,9 @@ def conv1_wgrad(xpp, dy_planes):
   gradient of conv1's output) -> filter gradient in HWIO layout [8,8,3,16] f32."""
   s = xpp.shape[0]
   acc = torch.zeros(4, 16, 48, dtype=torch.float32, device=xpp.device)
-  call("unreal_conv1_wgrad", ptr(xpp, torch.bfloat16, "xpp"), ptr(dy_planes, torch.bfloat16, "dy_planes"),
-       ptr(acc, torch.float32), s, stream_ptr())
+  p21 = dy_planes.shape[1] == s * 420          # planes on the 21-pixel row pitch (conv2_dgrad_relu(pitch21=True))
+  call("unreal_conv1_wgrad_p21" if p21 else "unreal_conv1_wgrad", ptr(xpp, torch.bfloat16, "xpp"),
+       ptr(dy_planes, torch.bfloat16, "dy_planes"), ptr(acc, torch.float32), s, stream_ptr())
   # acc[(by,bx), o, (dy,dx,c)] -> W[4by+dy, 4bx+dx, c, o]
   return acc.view(2, 2, 16, 4, 4, 3).permute(0, 3, 1, 4, 5, 2).reshape(8, 8, 3, 16)
 
@@ -568,13 +569,14 @@ def pc_deconv_fwd(h16, w_dtaps, bias8, out=None):
   return out
 
 
-def conv2_dgrad_relu(dy16, w_dtaps, h1):
+def conv2_dgrad_relu(dy16, w_dtaps, h1, pitch21=False):
   """conv2's input gradient fused with conv1's ReLU gradient: dy16 [S*81,32] bf16, h1 [S,20,20,16] bf16 ->
-  (masked gradient as conv1-wgrad planes [2, S*400, 8] bf16, conv1 bias gradient [16] f32)."""
+  (masked gradient as conv1-wgrad planes [2, S*400, 8] bf16 -- or [2, S*420, 8] on the x'' grid's 21-pixel
+  row pitch with a zero column when pitch21 -- and conv1's bias gradient [16] f32)."""
   s = dy16.shape[0] // 81
-  planes = torch.empty(2, s * 400, 8, dtype=torch.bfloat16, device=dy16.device)
+  planes = torch.empty(2, s * (420 if pitch21 else 400), 8, dtype=torch.bfloat16, device=dy16.device)
   db = torch.zeros(16, dtype=torch.float32, device=dy16.device)
   call("unreal_conv2_dgrad_relu", ptr(dy16, torch.bfloat16, "dy16"), ptr(w_dtaps, torch.bfloat16, "w_dtaps"),
        ptr(h1, torch.bfloat16, "h1"), ptr(planes, torch.bfloat16, "planes"), ptr(db, torch.float32, "db"), s,
-       stream_ptr())
+       1 if pitch21 else 0, stream_ptr())
   return planes, db

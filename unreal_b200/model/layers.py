@@ -140,7 +140,7 @@ class EncoderFn(torch.autograd.Function):
     s = xpp.shape[0]
     dy2, db2 = K.relu_grad(dh2.reshape(-1, 32), h2.view(-1, 32))
     dw2 = K.conv2_wgrad(h1.view(s, 20, 20, 16), dy2)
-    dy1_planes, db1 = K.conv2_dgrad_relu(dy2, ctx.dtaps, h1)
+    dy1_planes, db1 = K.conv2_dgrad_relu(dy2, ctx.dtaps, h1, pitch21=True)
     dw1 = K.conv1_wgrad(xpp, dy1_planes)
     return None, dw1, db1, dw2, db2, None, None
 
