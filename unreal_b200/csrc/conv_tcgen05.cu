@@ -489,7 +489,10 @@ conv1_wgrad_tcgen05_kernel(const __nv_bfloat16* __restrict__ xpp, const __nv_bfl
       // x'' is the A operand (M = (dy,dx,c) channels: 6 real 8-channel chunks of the 16 a 128-row UMMA reads, the
       // rest land in accumulator rows nobody reads), dY the B operand (N = 16 outputs): a UMMA costs
       // max(M,128) * N / 256 cycles, so N = 16 is a third of the tensor-pipe time of the transposed form (N = 48)
-      constexpr uint32_t idesc = idesc_bf16_f32(128, 16, true, true);
+      // M = 64, not 128: the MN-major A operand is read from shared memory chunk by chunk, and at 128 B/clk a
+      // 128-row read (16 chunks x 16 pixels x 16 B = 4 KB per UMMA, 10 of the 16 chunks garbage) is what bounds
+      // the kernel; 64 rows (6 real chunks of 8) halve it
+      constexpr uint32_t idesc = idesc_bf16_f32(64, 16, true, true);
       int stage = 0; uint32_t phase = 0;
       bool first = true;
       for (int it = blockIdx.x; it < items; it += gridDim.x) {
@@ -517,18 +520,18 @@ conv1_wgrad_tcgen05_kernel(const __nv_bfloat16* __restrict__ xpp, const __nv_bfl
     }
     __syncwarp();
   }
-  if (warp < 2) {
-    // ===== final epilogue: accumulator row m = (dy,dx,c) channel lives in TMEM lane m (warp 0: 0..31, warp 1:
-    // 32..47), columns t*16 + o =====
+  {
+    // ===== final epilogue: a 64-row accumulator keeps row m = (dy,dx,c) in lane 32*(m/16) + m%16, i.e. 16 rows in
+    // each warp's TMEM sub-partition (warps 0..2: m = 0..47; rows 48..63 are the garbage chunks), columns t*16 + o =====
     mbar_wait(done_bar, 0);
     fence_after_sync();
-    const int m = warp * 32 + lane;
+    const int m = warp * 16 + lane;
 #pragma unroll 1
     for (int half = 0; half < 2; ++half) {
       uint32_t v[32];
       tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(half * 32), v);     // taps 2*half, 2*half+1
       tmem_ld_wait();
-      if (m < 48) {
+      if (lane < 16) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) atomicAdd(dw + ((2 * half) * 16 + j) * 48 + m, __uint_as_float(v[j]));
       }
