@@ -410,14 +410,14 @@ conv1_fwd_tcgen05_kernel(const __nv_bfloat16* __restrict__ xpp, const __nv_bfloa
 // of each output row), so whatever finite data x'' holds there contributes nothing.  Each CTA keeps
 // its four [48 x 16] accumulators in TMEM across ALL its items and adds them to global once.
 // Traffic per frame: 42 KB of x'' + 12.8 KB of dY, each read once; no patch matrix.
-constexpr int kWgStages = 4;      // two CTAs per SM
+constexpr int kWgStages = 4;      // three CTAs per SM (68 KB and 64 TMEM columns each)
 constexpr int kWgStageBytes = 16384;            // x'' tile 12 096 (+192 pad) | dY tile 2 x 112 x 16 = 3 584 (+512)
 constexpr int kWgDyOff = 12288;
 constexpr int kWgDyPlane = 112 * 16;
-constexpr int kWgTail = 32768;                   // A chunks 6..15 of the last stages read (ignored) rows here
+constexpr int kWgTail = 2048;                    // A chunks 6, 7 of the last stage read (ignored) rows here
 constexpr int kWgSmem = kWgStages * kWgStageBytes + kWgTail + 1024 + 1024;
 
-__global__ void __launch_bounds__(96, 2)
+__global__ void __launch_bounds__(96, 3)
 conv1_wgrad_tcgen05_kernel(const __nv_bfloat16* __restrict__ xpp, const __nv_bfloat16* __restrict__ dyp,
                            float* __restrict__ dw, int items, int64_t dy_plane_elems, int pitch21) {
   extern __shared__ uint8_t smem_raw[];
@@ -437,7 +437,7 @@ conv1_wgrad_tcgen05_kernel(const __nv_bfloat16* __restrict__ xpp, const __nv_bfl
     mbar_init(done_bar, 1);
     fence_mbar_init();
   } else if (warp == 2) {
-    tmem_alloc<256>(tmem_slot);
+    tmem_alloc<64>(tmem_slot);
   }
   fence_proxy_async_smem();
   fence_before_sync();
@@ -542,7 +542,7 @@ conv1_wgrad_tcgen05_kernel(const __nv_bfloat16* __restrict__ xpp, const __nv_bfl
   __syncthreads();
   if (warp == 2) {
     fence_after_sync();
-    tmem_dealloc<256>(tmem_base);
+    tmem_dealloc<64>(tmem_base);
   }
 }
 
@@ -1018,7 +1018,7 @@ static int conv1_wgrad_launch(const void* xpp_bf16, const void* dy_planes_bf16, 
   const int sms = sm_count();
   if (sms <= 0) return UNREAL_ECUDA;
   const int items = s * 4;
-  conv1_wgrad_tcgen05_kernel<<<items < 2 * sms ? items : 2 * sms, 96, kWgSmem, as_stream(stream)>>>(
+  conv1_wgrad_tcgen05_kernel<<<items < 3 * sms ? items : 3 * sms, 96, kWgSmem, as_stream(stream)>>>(
       reinterpret_cast<const __nv_bfloat16*>(xpp_bf16), reinterpret_cast<const __nv_bfloat16*>(dy_planes_bf16), dw_taps,
       items, (int64_t)s * (pitch21 ? 420 : 400) * 8, pitch21);
   UNREAL_LAUNCH_CHECK("conv1_wgrad_tcgen05_kernel");
