@@ -562,7 +562,7 @@ constexpr int kW2BBytes = 8192;                   // 96 rows x 64 B used
 constexpr int kW2Tail = kW2ABytes;                // the ignored A rows 64..127 of the last stage read here
 constexpr int kW2Smem = kW2AStages * kW2ABytes + kW2BStages * kW2BBytes + kW2Tail + 1024 + 1024;
 
-__global__ void __launch_bounds__(96, 2)
+__global__ void __launch_bounds__(128, 2)
 conv2_wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_a2,
                            const __grid_constant__ CUtensorMap tma_dy, float* __restrict__ dw, int samples) {
   extern __shared__ uint8_t smem_raw[];
@@ -578,7 +578,7 @@ conv2_wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __gr
   const uint32_t tmem_slot = done_bar + 8u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  for (uint32_t off = threadIdx.x * 16u; off < (uint32_t)(kW2AStages * kW2ABytes + kW2BStages * kW2BBytes + kW2Tail); off += 96u * 16u)
+  for (uint32_t off = threadIdx.x * 16u; off < (uint32_t)(kW2AStages * kW2ABytes + kW2BStages * kW2BBytes + kW2Tail); off += 128u * 16u)
     asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(smem_base + off), "r"(0u) : "memory");
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&tma_a); prefetch_tensormap(&tma_a2); prefetch_tensormap(&tma_dy);
@@ -617,7 +617,7 @@ conv2_wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __gr
     __syncwarp();
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = idesc_bf16_f32(128, 32, true, true);
+      constexpr uint32_t idesc = idesc_bf16_f32(64, 32, true, true);   // 64 rows: all of them real, half the A read
       // MN-major descriptors.  A (h1 box, 128-byte rows, SW128): lo = (addr >> 4) | LBO (stride of the next
       // 64-element M chunk; only the first chunk is real, the second reads the next stage / the tail),
       // hi = SBO 1024 B (next 8 pixel rows).  B (dY2, 64-byte rows, SW64): SBO 512 B.
@@ -648,20 +648,22 @@ conv2_wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __gr
     }
     __syncwarp();
   }
-  if (warp < 2) {
-    // ===== final epilogue: accumulator ky, row m = (kx,c) in TMEM lane m (warp 0: 0..31, warp 1: 32..63),
-    // column o -> dW2 in HWIO order [ky][(kx,c)][o] =====
+  {
+    // ===== final epilogue: accumulator ky, row m = (kx,c) of a 64-row accumulator in TMEM lane 32*(m/16) + m%16
+    // (16 rows in each of the four warps' sub-partitions), column o -> dW2 in HWIO order [ky][(kx,c)][o] =====
     mbar_wait(done_bar, 0);
     fence_after_sync();
-    const int m = warp * 32 + lane;
+    const int m = warp * 16 + lane;
 #pragma unroll 1
     for (int st = 0; st < 4; ++st) {
       uint32_t v[32];
       tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(st * 32), v);
       tmem_ld_wait();
       float* o = dw + (st * 64 + m) * 32;
+      if (lane < 16) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) atomicAdd(o + j, __uint_as_float(v[j]));
+        for (int j = 0; j < 32; ++j) atomicAdd(o + j, __uint_as_float(v[j]));
+      }
     }
   }
   __syncwarp();
@@ -1061,7 +1063,7 @@ extern "C" int unreal_conv2_wgrad(const void* h1_bf16, const void* dy_bf16, floa
   }
   const int sms = sm_count();
   if (sms <= 0) return UNREAL_ECUDA;
-  conv2_wgrad_tcgen05_kernel<<<s < 2 * sms ? s : 2 * sms, 96, kW2Smem, as_stream(stream)>>>(ta, ta2, td, dw_taps, s);
+  conv2_wgrad_tcgen05_kernel<<<s < 2 * sms ? s : 2 * sms, 128, kW2Smem, as_stream(stream)>>>(ta, ta2, td, dw_taps, s);
   UNREAL_LAUNCH_CHECK("conv2_wgrad_tcgen05_kernel");
   return UNREAL_OK;
 }
