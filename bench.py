@@ -54,6 +54,9 @@ def parse():
   p.add_argument("--no-agent", action="store_true", help="skip the full-agent (configs[2]) side measurement")
   p.add_argument("--agent-envs", type=int, default=8192, help="envs per GPU of the full-agent side measurement")
   p.add_argument("--agent-updates", type=int, default=6)
+  p.add_argument("--agent-obs", default="cells", choices=["cells", "s2d", "f32"],
+                 help="full-agent observations: agent cells (conv1 renders its tiles in shared memory, no frame in HBM), "
+                      "K1-rendered x'' planes, or f32 frames")
   return p.parse_args()
 
 
@@ -179,7 +182,7 @@ def run_reference(args):
 
 
 # --------------------------------------------------------------------------- full agent (side measurement)
-def measure_agent(torch, dist, dev, rank, world, envs, updates, history=2000):
+def measure_agent(torch, dist, dev, rank, world, envs, updates, history=2000, obs='cells'):
   """BASELINE configs[2] slice per GPU: `envs` mazes, per-env `history`-frame replay ring, RP/VR/PC
   sampling, UnrealModel forward/backward on tcgen05 (K7), NCCL gradient exchange + fused RMSProp
   (K6).  One update = 20 env-steps per env.  Reported beside the headline, never instead of it."""
@@ -196,7 +199,7 @@ def measure_agent(torch, dist, dev, rank, world, envs, updates, history=2000):
   applier = RMSPropApplier(7e-4, decay=0.99, momentum=0.0, epsilon=0.1, clip_norm=40.0)
   tr = Trainer(rank, net, 7e-4, None, applier, 'maze', '', True, True, True, True, 0.05, 0.001, 20, 20, 0.99, 0.9,
                history, 10 ** 9, str(dev), {'segnet_mode': 0}, (84, 84), True, 0, np.random.RandomState(1), 50.0, 0.0,
-               0.0, num_envs=envs, seeds=env_seeds(0xA3C, lo, hi), use_graphs=True, obs_s2d=True)
+               0.0, num_envs=envs, seeds=env_seeds(0xA3C, lo, hi), use_graphs=True, obs_s2d=(obs == 's2d'), obs_cells=(obs == 'cells'))
   tr.prepare()
   t0 = time.perf_counter()
   while not tr.experience.is_full():
@@ -238,7 +241,11 @@ def measure_agent(torch, dist, dev, rank, world, envs, updates, history=2000):
   return {"workload": "configs[2] slice: %d maze envs per GPU, %d-frame replay ring per env, PC/VR/RP sampling, "
                       "UnrealModel fwd/bwd (bf16 tcgen05 GEMMs, fp32 accumulate), %s fused clip+RMSProp"
                       % (envs, history, "NCCL gradient exchange +" if world > 1 else "single-GPU"),
-          "envs_per_gpu": envs, "history": history, "updates": updates, "value": world * envs * 20 * updates / (ms * 1e-3),
+          "envs_per_gpu": envs, "history": history, "updates": updates,
+          "observations": {"cells": "agent cells int32 [N,2]; conv1 fwd / wgrad synthesise their x'' tiles in shared memory "
+                                    "(render fused into the consumer: no frame is written to or read from HBM)",
+                           "s2d": "x'' bf16 planes rendered by K1 (42 KB per frame)",
+                           "f32": "f32 frames rendered by K1 (85 KB per frame) + space-to-depth pass"}[obs], "value": world * envs * 20 * updates / (ms * 1e-3),
           "unit": "env-steps/s", "ms_per_update": ms / updates, "model_update_ms": upd_ms,
           "updates_per_s": updates / (ms * 1e-3), "ring_fill_s": fill_s, "params": net.num_parameters,
           "finite": bool(all(np.isfinite(v) for v in losses.values())), "grad_norm": losses.get("grad_norm"),
@@ -374,7 +381,7 @@ def run_b200(args):
     try:
       del eng, out, hbuf, h_act, h_val, h_bv, h_bq
       torch.cuda.empty_cache()
-      agent = measure_agent(torch, dist, dev, rank, world, args.agent_envs, args.agent_updates)
+      agent = measure_agent(torch, dist, dev, rank, world, args.agent_envs, args.agent_updates, obs=args.agent_obs)
     except Exception as e:  # the side measurement must never cost the headline line
       agent = {"error": repr(e)[:300]}
 

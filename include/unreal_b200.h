@@ -265,6 +265,15 @@ int unreal_conv1_wgrad(const void* xpp_bf16, const void* dy_planes_bf16, float* 
 /* same, with the dY planes on the x'' grid's 21-pixel row pitch ([2][S*420][8], column ox = 20 zero; written by
  * unreal_conv2_dgrad_relu with pitch21 = 1): one 1680-byte bulk copy per plane and work item instead of five
  * 320-byte ones. */
+/* Render-fused conv1 for the maze env type: pos [S,2] i32 (agent cell x, y of each frame) instead of frames.
+ * The kernels synthesise each work item's x'' tile in shared memory from the cell and the wall map set by
+ * unreal_maze_set_map (maze_environment.py:30-41, :57-60, :93-96: the frame is a pure function of the position),
+ * bit-identical to what unreal_maze_render(dtype bf16) would have written: no frame is written to or read from
+ * HBM for the forward pass or the filter gradient.  out / dw_taps / dy planes as in unreal_conv_fwd (layer 1) /
+ * unreal_conv1_wgrad_p21. */
+int unreal_conv1_fwd_maze(const int32_t* pos, const void* w_taps_bf16, const float* bias, void* out_bf16, int s,
+                          void* stream);
+int unreal_conv1_wgrad_maze(const int32_t* pos, const void* dy_planes21_bf16, float* dw_taps, int s, void* stream);
 int unreal_conv1_wgrad_p21(const void* xpp_bf16, const void* dy_planes21_bf16, float* dw_taps, int s, void* stream);
 /* conv2 filter gradient from h1 [S,20,20,16] bf16 and the masked dY2 [S*81,32] bf16, both read once through
  * TMA boxes: dw_taps f32 [4 ky][64 (kx,c)][32 out] = HWIO [4,4,16,32] += ... (caller zeroes dw_taps). */

@@ -160,3 +160,33 @@ def test_s2d_observation_agent_equals_f32_agent():
       assert abs(a - b) <= 1e-3 * max(1.0, abs(a)), (it, k, a, b)
   assert tr_b.last_feed['base']['si'].dtype == torch.bfloat16
   tr_a.stop(); tr_b.stop()
+
+
+def test_cell_observation_agent_equals_frame_agent():
+  """obs_cells=True: observations are the agent cells and conv1 (forward and filter gradient) renders its input
+  tiles in shared memory -- no frame in HBM anywhere.  Must train exactly like the agent that materialises
+  frames: same actions, same replay samples, same losses, same parameters."""
+  n = 4
+  tr_a, net_a, _ = _agent(n, H=40, seed=6)
+  _, net_b, _ = _agent(n, H=40, seed=6)
+  from unreal_b200.train.trainer import Trainer
+  from unreal_b200.train.rmsprop_applier import RMSPropApplier
+  ap = RMSPropApplier(7e-4, decay=0.99, momentum=0.0, epsilon=0.1, clip_norm=40.0)
+  tr_b = Trainer(0, net_b, 7e-4, None, ap, 'maze', '', True, True, True, True, 0.05, 0.001, 20, 20, 0.99, 0.9, 40,
+                 10 ** 7, "cuda:0", {'segnet_mode': 0}, (84, 84), True, 0, np.random.RandomState(1), 50.0, 0.0, 0.0,
+                 num_envs=n, seeds=np.arange(n) + 11, obs_cells=True, use_graphs=True)
+  tr_b.prepare()
+  for tr in (tr_a, tr_b):
+    while not tr.experience.is_full():
+      tr.process(None, 0)
+  for it in range(4):
+    tr_a.process(None, 0); tr_b.process(None, 0)
+    assert torch.equal(tr_a.last_feed['base']['a'], tr_b.last_feed['base']['a']), it
+    assert torch.equal(tr_a.last_feed['pc']['start'], tr_b.last_feed['pc']['start'])
+    assert torch.equal(tr_a.last_feed['base']['pos'], tr_b.last_feed['base']['si']), "the cell observations are the positions"
+    for k in ("policy", "value", "pc", "vr", "rp"):
+      a, b = float(tr_a.last_losses[k]), float(tr_b.last_losses[k])
+      assert abs(a - b) <= 1e-3 * max(1.0, abs(a)), (it, k, a, b)
+  assert tr_b.last_feed['base']['si'].dtype == torch.int32
+  assert torch.allclose(net_a.flat, net_b.flat, rtol=1e-3, atol=1e-5)
+  tr_a.stop(); tr_b.stop()

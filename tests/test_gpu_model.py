@@ -355,3 +355,31 @@ def test_fused_encoder_backward_equals_layerwise_backward():
   va, vb = net_a._views(ga), net_b._views(gb)
   for k in va:      # same operands, same roundings: only the order of the fp32 atomics differs
     assert torch.allclose(va[k], vb[k], rtol=2e-3, atol=2e-3 * float(vb[k].abs().max() + 1e-12)), k
+
+
+def test_render_fused_conv1_equals_conv1_on_rendered_frames():
+  """unreal_conv1_fwd_maze / unreal_conv1_wgrad_maze build the x'' tiles from the agent cells in shared memory:
+  bit-identical outputs to the same kernels reading frames rendered by K1 (every free cell of the map)."""
+  from oracle import unreal_oracle as O
+  from unreal_b200 import kernels as K
+  dev = torch.device("cuda", 0)
+  g = torch.Generator(device=dev).manual_seed(3)
+  cells = [(x, y) for y in range(7) for x in range(7) if not O.WALLS[y, x]]
+  pos = torch.tensor(cells * 9, dtype=torch.int32, device=dev)           # 306 frames: several waves of work items
+  s = pos.shape[0]
+  w1 = ((torch.rand(8, 8, 3, 16, device=dev, generator=g) - 0.5) * 0.3).to(torch.bfloat16)
+  b1 = (torch.rand(16, device=dev, generator=g) - 0.5) * 0.1
+  taps = K.conv1_w_planes(w1)
+  xpp = K.maze_render(pos, dtype=torch.bfloat16)
+  want = K.conv_fwd(xpp, 1, taps, b1)
+  got = K.conv1_fwd_maze(pos, taps, b1)
+  assert torch.equal(got, want)
+  # and against the plain convolution of the oracle's float frame
+  frames = torch.from_numpy(np.stack([O.maze_render(x, y) for x, y in cells]).astype(np.float32)).to(dev)
+  ref = torch.relu(torch.nn.functional.conv2d(frames.permute(0, 3, 1, 2), w1.float().permute(3, 2, 0, 1), b1, stride=4))
+  assert torch.allclose(got[:len(cells)].float(), ref.permute(0, 2, 3, 1), rtol=2e-2, atol=2e-2)
+  dy = (torch.randn(2, s * 420, 8, device=dev, generator=g) * 0.1).to(torch.bfloat16)
+  dy.view(2, s, 20, 21, 8)[:, :, :, 20] = 0
+  a = K.conv1_wgrad_maze(pos, dy)
+  b = K.conv1_wgrad(xpp, dy)
+  assert torch.allclose(a, b, rtol=1e-5, atol=1e-5 * float(b.abs().max()))

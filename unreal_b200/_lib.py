@@ -85,6 +85,8 @@ SIGNATURES = {
     "unreal_pc_deconv_fwd": (c_int, [P, P, P, P, c_int, P]),
     "unreal_conv2_dgrad_relu": (c_int, [P, P, P, P, P, c_int, c_int, P]),
     "unreal_conv1_wgrad_p21": (c_int, [P, P, P, c_int, P]),
+    "unreal_conv1_fwd_maze": (c_int, [P, P, P, P, c_int, P]),
+    "unreal_conv1_wgrad_maze": (c_int, [P, P, P, c_int, P]),
     "unreal_pc_loss": (c_int, [P, P, P, P, c_int, c_float, c_int64, c_int, P, P, P, P]),
 }
 

@@ -32,6 +32,42 @@ using namespace tc05;
 int make_tma_nd_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                      const uint32_t* box, int swizzle_bytes);   // gemm_tcgen05.cu
 
+int maze_walls49(uint64_t* out);     // maze.cu
+
+// Render-fused conv1 input (maze env type): the x'' tile of a work item (6 planes x 126 pixel rows x 16 B, rows
+// rb*105.. of the 21x21 space-to-depth grid) is a pure function of the agent cell and the constant wall map --
+// a 4x4 pixel block lies inside one 12-pixel maze cell, so each plane row is one of three constant 16-byte
+// patterns (csrc/maze.cu:maze_s2d_kernel writes the same bytes to HBM).  One warp writes it straight into
+// the stage the UMMA reads: the frame never exists in HBM, neither for the forward nor for the filter gradient.
+__device__ __forceinline__ void maze_tile_to_smem(uint32_t dst, uint64_t walls49, int ax, int ay, int rb, int lane) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int p = lane + 32 * j;
+    if (p < 126) {
+      const int gp = rb * 105 + p;
+      const int Y = gp / 21, X = gp - Y * 21;
+      const int cx = X / 3, cy = Y / 3;
+      const uint32_t mw = ((walls49 >> (cy * 7 + cx)) & 1ull) ? 0xffffffffu : 0u;
+      const uint32_t ma = (cx == ax && cy == ay) ? 0xffffffffu : 0u;
+#pragma unroll
+      for (int q = 0; q < 6; ++q) {
+        // element i of plane q is channel (8q + i) mod 3; walls set channel 0, the agent channel 1 (bf16 1.0 = 0x3f80)
+        const int base = (2 * q) % 3;
+        uint32_t v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int c0 = (base + 2 * k) % 3, c1 = (base + 2 * k + 1) % 3;
+          const uint32_t wl = (c0 == 0 ? 0x3f80u : 0u) | (c1 == 0 ? 0x3f800000u : 0u);
+          const uint32_t ag = (c0 == 1 ? 0x3f80u : 0u) | (c1 == 1 ? 0x3f800000u : 0u);
+          v[k] = (wl & mw) | (ag & ma);
+        }
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (uint32_t)(q * 126 * 16 + p * 16)), "r"(v[0]),
+                     "r"(v[1]), "r"(v[2]), "r"(v[3]) : "memory");
+      }
+    }
+  }
+}
+
 constexpr int kConvThreads = 192;
 constexpr int kConvAcc = 4;       // TMEM accumulator buffers of 32 columns
 template <int MODE> struct ConvCfg;   // MODE 2 = conv2 (conv1 has its own single-copy kernel below)
@@ -276,7 +312,8 @@ constexpr int kC1Smem = kC1WBytes + kC1Stages * kC1StageBytes + 1024 /*barriers*
 
 __global__ void __launch_bounds__(kConvThreads, 2)
 conv1_fwd_tcgen05_kernel(const __nv_bfloat16* __restrict__ xpp, const __nv_bfloat16* __restrict__ w_planes,
-                         const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int items) {
+                         const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int items,
+                         const int32_t* __restrict__ maze_pos, uint64_t walls49) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t w_smem = smem_base;
@@ -304,7 +341,24 @@ conv1_fwd_tcgen05_kernel(const __nv_bfloat16* __restrict__ xpp, const __nv_bfloa
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-  if (warp == 0) {
+  if (warp == 0 && maze_pos != nullptr) {
+    // ===== render-fused producer (maze): the warp WRITES each item's x'' tile from the agent cell =====
+    if (lane == 0) {
+      mbar_arrive_expect_tx(w_bar, kC1WBytes);
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(w_smem), "l"(w_planes), "r"(kC1WBytes), "r"(w_bar) : "memory");
+    }
+    int stage = 0; uint32_t phase = 0;
+    for (int it = blockIdx.x; it < items; it += gridDim.x) {
+      const int2 cell = __ldg(reinterpret_cast<const int2*>(maze_pos) + (it >> 2));
+      mbar_wait(empty_bar(stage), phase ^ 1u);
+      maze_tile_to_smem(a_smem + stage * kC1StageBytes, walls49, cell.x, cell.y, it & 3, lane);
+      fence_proxy_async_smem();            // generic-proxy writes -> visible to the tensor core's async-proxy reads
+      __syncwarp();
+      if (lane == 0) mbar_arrive(full_bar(stage));
+      if (++stage == kC1Stages) { stage = 0; phase ^= 1u; }
+    }
+  } else if (warp == 0) {
     if (lane == 0) {
       // ===== producer: resident filters (one bulk copy), then ONE box per item =====
       mbar_arrive_expect_tx(w_bar, kC1WBytes);
@@ -419,7 +473,8 @@ constexpr int kWgSmem = kWgStages * kWgStageBytes + kWgTail + 1024 + 1024;
 
 __global__ void __launch_bounds__(96, 3)
 conv1_wgrad_tcgen05_kernel(const __nv_bfloat16* __restrict__ xpp, const __nv_bfloat16* __restrict__ dyp,
-                           float* __restrict__ dw, int items, int64_t dy_plane_elems, int pitch21) {
+                           float* __restrict__ dw, int items, int64_t dy_plane_elems, int pitch21,
+                           const int32_t* __restrict__ maze_pos, uint64_t walls49) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = smem_base + kWgStages * kWgStageBytes + kWgTail;
@@ -446,7 +501,30 @@ conv1_wgrad_tcgen05_kernel(const __nv_bfloat16* __restrict__ xpp, const __nv_bfl
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-  if (warp == 0) {
+  if (warp == 0 && maze_pos != nullptr) {
+    // ===== render-fused producer (maze): the x'' tile is written by the warp, only dY comes from HBM =====
+    int stage = 0; uint32_t phase = 0;
+    for (int it = blockIdx.x; it < items; it += gridDim.x) {
+      const int64_t smp = it >> 2;
+      const int rb = it & 3;
+      const int2 cell = __ldg(reinterpret_cast<const int2*>(maze_pos) + smp);
+      mbar_wait(empty_bar(stage), phase ^ 1u);
+      const uint32_t dst = smem_base + stage * kWgStageBytes;
+      maze_tile_to_smem(dst, walls49, cell.x, cell.y, rb, lane);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive_expect_tx(full_bar(stage), 2 * 1680);
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const uint8_t* ds = reinterpret_cast<const uint8_t*>(dyp) + ((int64_t)c * dy_plane_elems / 8 + smp * 420 + rb * 105) * 16;
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                       ::"r"(dst + kWgDyOff + c * kWgDyPlane), "l"(ds), "r"(1680), "r"(full_bar(stage)) : "memory");
+        }
+      }
+      if (++stage == kWgStages) { stage = 0; phase ^= 1u; }
+    }
+  } else if (warp == 0) {
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       for (int it = blockIdx.x; it < items; it += gridDim.x) {
@@ -950,6 +1028,30 @@ extern "C" int unreal_s2d_frames(const void* frames, int dtype, void* out_bf16, 
   return UNREAL_OK;
 }
 
+extern "C" int unreal_conv1_fwd_maze(const int32_t* pos, const void* w_taps_bf16, const float* bias, void* out_bf16, int s,
+                                     void* stream) {
+  UNREAL_REQUIRE(pos && w_taps_bf16 && out_bf16 && s > 0, "unreal_conv1_fwd_maze: null buffer or s <= 0");
+  UNREAL_REQUIRE(aligned16(w_taps_bf16) && aligned16(out_bf16) && (reinterpret_cast<uintptr_t>(pos) & 7u) == 0,
+                 "unreal_conv1_fwd_maze: alignment (pos 8, buffers 16 bytes)");
+  uint64_t walls = 0;
+  int rc = maze_walls49(&walls);
+  if (rc != UNREAL_OK) return rc;
+  static bool configured = false;
+  if (!configured) {
+    UNREAL_CUDA(cudaFuncSetAttribute(conv1_fwd_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kC1Smem));
+    configured = true;
+  }
+  const int sms = sm_count();
+  if (sms <= 0) return UNREAL_ECUDA;
+  const int items = s * 4;
+  const int ctas = 2 * sms;
+  conv1_fwd_tcgen05_kernel<<<items < ctas ? items : ctas, kConvThreads, kC1Smem, as_stream(stream)>>>(
+      nullptr, reinterpret_cast<const __nv_bfloat16*>(w_taps_bf16), bias, reinterpret_cast<__nv_bfloat16*>(out_bf16), items,
+      pos, walls);
+  UNREAL_LAUNCH_CHECK("conv1_fwd_tcgen05_kernel(maze)");
+  return UNREAL_OK;
+}
+
 extern "C" int unreal_conv_fwd(const void* in_bf16, int layer, const void* w_taps_bf16, const float* bias,
                                void* out_bf16, int s, void* stream) {
   UNREAL_REQUIRE(in_bf16 && w_taps_bf16 && out_bf16 && s > 0, "unreal_conv_fwd: null buffer or s <= 0");
@@ -974,7 +1076,8 @@ extern "C" int unreal_conv_fwd(const void* in_bf16, int layer, const void* w_tap
     const int items = s * 4;
     const int ctas = 2 * sms;
     conv1_fwd_tcgen05_kernel<<<items < ctas ? items : ctas, kConvThreads, kC1Smem, as_stream(stream)>>>(
-        reinterpret_cast<const __nv_bfloat16*>(in_bf16), reinterpret_cast<const __nv_bfloat16*>(w_taps_bf16), bias, reinterpret_cast<__nv_bfloat16*>(out_bf16), items);
+        reinterpret_cast<const __nv_bfloat16*>(in_bf16), reinterpret_cast<const __nv_bfloat16*>(w_taps_bf16), bias,
+        reinterpret_cast<__nv_bfloat16*>(out_bf16), items, nullptr, 0ull);
     UNREAL_LAUNCH_CHECK("conv1_fwd_tcgen05_kernel");
     return UNREAL_OK;
   } else {
@@ -1008,7 +1111,7 @@ extern "C" int unreal_conv_fwd(const void* in_bf16, int layer, const void* w_tap
 }
 
 static int conv1_wgrad_launch(const void* xpp_bf16, const void* dy_planes_bf16, float* dw_taps, int s, int pitch21,
-                              void* stream) {
+                              void* stream, const int32_t* maze_pos = nullptr) {
   UNREAL_REQUIRE(xpp_bf16 && dy_planes_bf16 && dw_taps && s > 0, "unreal_conv1_wgrad: null buffer or s <= 0");
   UNREAL_REQUIRE(aligned16(xpp_bf16) && aligned16(dy_planes_bf16) && aligned16(dw_taps),
                  "unreal_conv1_wgrad: buffers must be 16-byte aligned");
@@ -1019,16 +1122,27 @@ static int conv1_wgrad_launch(const void* xpp_bf16, const void* dy_planes_bf16, 
   }
   const int sms = sm_count();
   if (sms <= 0) return UNREAL_ECUDA;
+  uint64_t walls = 0;
+  if (maze_pos != nullptr) {
+    int rc = maze_walls49(&walls);
+    if (rc != UNREAL_OK) return rc;
+  }
   const int items = s * 4;
   conv1_wgrad_tcgen05_kernel<<<items < 3 * sms ? items : 3 * sms, 96, kWgSmem, as_stream(stream)>>>(
       reinterpret_cast<const __nv_bfloat16*>(xpp_bf16), reinterpret_cast<const __nv_bfloat16*>(dy_planes_bf16), dw_taps,
-      items, (int64_t)s * (pitch21 ? 420 : 400) * 8, pitch21);
+      items, (int64_t)s * (pitch21 ? 420 : 400) * 8, pitch21, maze_pos, walls);
   UNREAL_LAUNCH_CHECK("conv1_wgrad_tcgen05_kernel");
   return UNREAL_OK;
 }
 
 extern "C" int unreal_conv1_wgrad(const void* xpp_bf16, const void* dy_planes_bf16, float* dw_taps, int s, void* stream) {
   return conv1_wgrad_launch(xpp_bf16, dy_planes_bf16, dw_taps, s, 0, stream);
+}
+
+extern "C" int unreal_conv1_wgrad_maze(const int32_t* pos, const void* dy_planes21_bf16, float* dw_taps, int s, void* stream) {
+  UNREAL_REQUIRE(pos != nullptr && (reinterpret_cast<uintptr_t>(pos) & 7u) == 0, "unreal_conv1_wgrad_maze: pos null or not 8-byte aligned");
+  return conv1_wgrad_launch(dy_planes21_bf16 /* x'' is synthesised; any aligned non-null pointer */, dy_planes21_bf16, dw_taps, s, 1,
+                            stream, pos);
 }
 
 extern "C" int unreal_conv1_wgrad_p21(const void* xpp_bf16, const void* dy_planes21_bf16, float* dw_taps, int s,

@@ -491,6 +491,20 @@ extern "C" int unreal_maze_set_map(const char* map49_host) {
   return UNREAL_OK;
 }
 
+namespace unreal {
+// the 7x7 wall map as 49 bits (bit cy*7 + cx), for the render-fused conv1 kernels in conv_tcgen05.cu
+int maze_walls49(uint64_t* out) {
+  if (!h_maze_ready) {
+    int rc = unreal_maze_set_map(nullptr);
+    if (rc != UNREAL_OK) return rc;
+  }
+  uint64_t w = 0;
+  for (int cy = 0; cy < UNREAL_MAZE_GRID; ++cy) w |= (uint64_t)(h_maze.wall_rows[cy] & 0x7fu) << (7 * cy);
+  *out = w;
+  return UNREAL_OK;
+}
+}  // namespace unreal
+
 extern "C" int unreal_maze_get_layout(int* sx, int* sy, int* gx, int* gy, uint8_t* walls49_host) {
   int rc = ensure_map();
   if (rc) return rc;

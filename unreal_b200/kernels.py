@@ -55,6 +55,11 @@ def maze_step(state, action, obs=None, pc=None, reward=None, terminal=None, fram
     reward = torch.empty(n, dtype=torch.float32, device=dev)
   if terminal is None:
     terminal = torch.empty(n, dtype=torch.uint8, device=dev)
+  cell_obs = obs if (obs is not None and obs.dtype == torch.int32) else None
+  if cell_obs is not None:      # "cell observation": the frame stays implicit (render-fused conv1), obs receives the cells
+    if cell_obs.numel() != n * 2:
+      raise _lib.UnrealError("an int32 (cell) observation buffer must hold [N,2]")
+    obs = None
   if obs is not None and obs.numel() != n * FRAME * FRAME * 3:
     raise _lib.UnrealError("obs must hold [N,84,84,3]")
   if pc is not None and (pc.numel() != n * PC * PC or pc.dtype != torch.float32):
@@ -64,17 +69,31 @@ def maze_step(state, action, obs=None, pc=None, reward=None, terminal=None, fram
        ptr(state.last_action, torch.int32), ptr(state.last_reward, torch.float32),
        ptr(obs), _lib.dtype_tag(obs) if obs is not None else _lib.F32, ptr(pc),
        ptr(frame_rec, torch.int64, "frame_rec"), n, 1 if auto_reset else 0, stream_ptr())
+  if cell_obs is not None:
+    if active is None:
+      cell_obs.copy_(state.pos.view_as(cell_obs))
+    else:                        # like the render kernels: rows of inactive envs are left alone
+      cell_obs.copy_(torch.where(active.view(n, 1).bool(), state.pos.view(n, 2), cell_obs.view(n, 2)).view_as(cell_obs))
   return reward, terminal
 
 
 def obs_shape(dtype):
   """Per-frame shape of a maze observation buffer: [84,84,3] for f32 / u8, the space-to-depth planes
-  [6,441,8] for bf16 (the layout conv1 consumes directly)."""
+  [6,441,8] for bf16 (the layout conv1 consumes directly), and [2] for int32 -- the agent CELL itself: a maze
+  frame is a pure function of it, and the render-fused conv1 kernels (unreal_conv1_fwd_maze /
+  unreal_conv1_wgrad_maze) build their input tiles from the cell, so no frame exists in HBM at all."""
+  if dtype == torch.int32:
+    return (2,)
   return (6, 441, 8) if dtype == torch.bfloat16 else (FRAME, FRAME, 3)
 
 
 def maze_render(pos, out=None, dtype=torch.float32):
   m = pos.shape[0]
+  if (out is not None and out.dtype == torch.int32) or (out is None and dtype == torch.int32):
+    if out is None:              # cell observation: the "render" of a cell is the cell
+      return pos.reshape(m, 2).clone()
+    out.copy_(pos.view_as(out))
+    return out
   if out is None:
     out = torch.empty(m, *obs_shape(dtype), dtype=dtype, device=pos.device)
   call("unreal_maze_render", ptr(pos, torch.int32, "pos"), ptr(out), _lib.dtype_tag(out), m, stream_ptr())
@@ -580,3 +599,24 @@ def conv2_dgrad_relu(dy16, w_dtaps, h1, pitch21=False):
        ptr(h1, torch.bfloat16, "h1"), ptr(planes, torch.bfloat16, "planes"), ptr(db, torch.float32, "db"), s,
        1 if pitch21 else 0, stream_ptr())
   return planes, db
+
+
+def conv1_fwd_maze(pos, w_taps, bias, out=None):
+  """Render-fused conv1 forward for maze frames: pos [S,2] i32 (agent cells) -> h1 bf16 [S,20,20,16]."""
+  s = pos.shape[0]
+  if out is None:
+    out = torch.empty(s, 20, 20, 16, dtype=torch.bfloat16, device=pos.device)
+  call("unreal_conv1_fwd_maze", ptr(pos, torch.int32, "pos"), ptr(w_taps, torch.bfloat16, "w_taps"),
+       ptr(bias, torch.float32, "bias"), ptr(out, torch.bfloat16, "out"), s, stream_ptr())
+  return out
+
+
+def conv1_wgrad_maze(pos, dy_planes21):
+  """Render-fused conv1 filter gradient: pos [S,2] i32, dy planes [2, S*420, 8] bf16 -> HWIO [8,8,3,16] f32."""
+  s = pos.shape[0]
+  if dy_planes21.shape[1] != s * 420:
+    raise _lib.UnrealError("conv1_wgrad_maze needs the dY planes on the 21-pixel row pitch")
+  acc = torch.zeros(4, 16, 48, dtype=torch.float32, device=pos.device)
+  call("unreal_conv1_wgrad_maze", ptr(pos, torch.int32, "pos"), ptr(dy_planes21, torch.bfloat16, "dy_planes"),
+       ptr(acc, torch.float32), s, stream_ptr())
+  return acc.view(2, 2, 16, 4, 4, 3).permute(0, 3, 1, 4, 5, 2).reshape(8, 8, 3, 16)

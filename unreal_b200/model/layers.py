@@ -120,15 +120,21 @@ class EncoderFn(torch.autograd.Function):
   ONE autograd node over the fused tcgen05 kernels, so the backward pass can fuse ACROSS the two layers:
   conv2's transposed convolution masks its result by h1 > 0 in the epilogue and writes conv1's wgrad planes
   and bias gradient directly (`unreal_conv2_dgrad_relu`) -- the dense [S,20,20,16] gradient and the separate
-  ReLU-gradient pass over it (38 KB per frame of HBM traffic) do not exist.  Frames: f32 / u8 [S,84,84,3] or
-  the space-to-depth planes bf16 [S,6,441,8]."""
+  ReLU-gradient pass over it (38 KB per frame of HBM traffic) do not exist.  Frames: f32 / u8 [S,84,84,3], the
+  space-to-depth planes bf16 [S,6,441,8], or maze CELLS int32 [S,2] (the conv1 kernels then synthesise their
+  input tiles in shared memory: unreal_conv1_fwd_maze / unreal_conv1_wgrad_maze)."""
 
   @staticmethod
   def forward(ctx, x, w1_32, b1_32, w2_32, b2_32, taps1, taps2):
     pre_s2d = x.dtype == torch.bfloat16 and tuple(x.shape[1:]) == (6, 441, 8)
     s = x.shape[0]
-    xpp = x if pre_s2d else K.s2d_frames(x)
-    h1 = K.conv_fwd(xpp, 1, taps1, b1_32)                      # bf16 [S,20,20,16]
+    ctx.cells = x.dtype == torch.int32                          # maze cells [S,2]: render-fused conv1, no frame in HBM
+    if ctx.cells:
+      xpp = x.contiguous()
+      h1 = K.conv1_fwd_maze(xpp, taps1, b1_32)
+    else:
+      xpp = x if pre_s2d else K.s2d_frames(x)
+      h1 = K.conv_fwd(xpp, 1, taps1, b1_32)                    # bf16 [S,20,20,16]
     h2 = K.conv_fwd(h1.view(s, 20, 20, 16), 2, taps2[0], b2_32)
     ctx.dtaps = taps2[1]
     ctx.save_for_backward(xpp, h1, h2)
@@ -141,7 +147,7 @@ class EncoderFn(torch.autograd.Function):
     dy2, db2 = K.relu_grad(dh2.reshape(-1, 32), h2.view(-1, 32))
     dw2 = K.conv2_wgrad(h1.view(s, 20, 20, 16), dy2)
     dy1_planes, db1 = K.conv2_dgrad_relu(dy2, ctx.dtaps, h1, pitch21=True)
-    dw1 = K.conv1_wgrad(xpp, dy1_planes)
+    dw1 = K.conv1_wgrad_maze(xpp, dy1_planes) if ctx.cells else K.conv1_wgrad(xpp, dy1_planes)
     return None, dw1, db1, dw2, db2, None, None
 
 

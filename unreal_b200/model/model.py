@@ -171,10 +171,13 @@ class UnrealModel(object):
 
   # ---- towers -------------------------------------------------------------------------
   def _encoder(self, p32, images):
-    """model.py:281-289.  images [S,84,84,3] f32 / u8 -> h2 bf16 [S,9,9,32]."""
+    """model.py:281-289.  images [S,84,84,3] f32 / u8, x'' planes bf16 [S,6,441,8] or maze cells int32 [S,2]
+    -> h2 bf16 [S,9,9,32]."""
     if self.fused_conv and self.fused_encoder:
       return EncoderFn.apply(images, p32["W_base_conv1"], p32["b_base_conv1"], p32["W_base_conv2"], p32["b_base_conv2"],
                              self.taps1, self.taps2)
+    if images.dtype == torch.int32:
+      raise _lib.UnrealError("cell observations (int32 [S,2]) need the fused encoder (fused_conv and fused_encoder)")
     h1 = ConvFn.apply(images, self.v16["W_base_conv1"].view(192, 16), p32["W_base_conv1"], p32["b_base_conv1"], 8, 8, 4,
                       self.taps1)
     h2 = ConvFn.apply(h1, self.v16["W_base_conv2"].view(256, 32), p32["W_base_conv2"], p32["b_base_conv2"], 4, 4, 2,

@@ -60,7 +60,7 @@ class Trainer(object):
                pixel_change_lambda, entropy_beta, local_t_max, n_step_TD, gamma, gamma_pc,
                experience_history_size, max_global_time_step, device, segnet_param_dict, image_shape,
                is_training, n_classes, random_state, termination_time, segnet_lambda, dropout,
-               num_envs=1, seeds=None, verbose=False, use_graphs=False, obs_s2d=False, env_args=None):
+               num_envs=1, seeds=None, verbose=False, use_graphs=False, obs_s2d=False, env_args=None, obs_cells=False):
     _lib.require_device()
     self.thread_index = thread_index
     self.learning_rate_input = learning_rate_input
@@ -124,6 +124,10 @@ class Trainer(object):
     # obs_s2d: K1 renders frames straight into conv1's space-to-depth bf16 plane layout (42 KB per
     # frame, no f32 frame and no separate s2d pass); needs a network with the fused conv1 kernel
     self.obs_dtype = torch.bfloat16 if obs_s2d else torch.float32
+    # obs_cells: observations are the agent CELLS (int32 [N,2]); frames stay implicit -- the network's conv1
+    # kernels render their input tiles in shared memory (maze only; needs UnrealModel's fused encoder)
+    if obs_cells:
+      self.obs_dtype = torch.int32
     self._graph = None
     self.graph_update = True                # with use_graphs: capture the learner update as well (single process)
     self._ugraph = None
@@ -255,7 +259,8 @@ class Trainer(object):
     rec = K.frame_unpack(last_rec, fields=("action", "reward"))
     boot_lar = self._last_action_reward(rec["action"], rec["reward"])
     boot_obs = self._obs[1:].gather(
-        0, (lengths.to(torch.int64) - 1).clamp_(min=0).view(1, n, 1, 1, 1).expand(1, n, *self._obs.shape[2:]))[0]
+        0, (lengths.to(torch.int64) - 1).clamp_(min=0).view(1, n, *([1] * (self._obs.dim() - 2))).expand(
+            1, n, *self._obs.shape[2:]))[0]
     # every env's current frame (the reset frame for ended envs) goes back into the env's own
     # persistent frame buffer, which is where the next rollout starts reading (graph-replay safe)
     env._obs.copy_(boot_obs)
