@@ -11,6 +11,7 @@ from torch.profiler import ProfilerActivity, profile
 def main():
   n = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
   out = sys.argv[2] if len(sys.argv) > 2 else "gpurun_out/agent_profile.txt"
+  mode = sys.argv[3] if len(sys.argv) > 3 else "cells"
   from unreal_b200.environment.environment import Environment
   from unreal_b200.model.model import UnrealModel
   from unreal_b200.train.rmsprop_applier import RMSPropApplier
@@ -21,7 +22,7 @@ def main():
   applier = RMSPropApplier(7e-4, decay=0.99, momentum=0.0, epsilon=0.1, clip_norm=40.0)
   tr = Trainer(0, net, 7e-4, None, applier, 'maze', '', True, True, True, True, 0.05, 0.001, 20, 20, 0.99, 0.9, 100,
                10 ** 8, "cuda:0", {'segnet_mode': 0}, (84, 84), True, 0, np.random.RandomState(1), 50.0, 0.0, 0.0,
-               num_envs=n, seeds=np.arange(n) + 11, obs_s2d=True)
+               num_envs=n, seeds=np.arange(n) + 11, obs_s2d=(mode == "s2d"), obs_cells=(mode == "cells"), use_graphs=False)
   tr.prepare()
   while not tr.experience.is_full():
     tr.process(None, 0)
