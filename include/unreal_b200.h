@@ -252,6 +252,10 @@ int unreal_lstm_cell_bwd(const float* gates_act, const float* c_prev, const floa
 int unreal_s2d_frames(const void* frames, int dtype, void* out_bf16, int s, void* stream);
 int unreal_conv_fwd(const void* in_bf16, int layer, const void* w_taps_bf16, const float* bias, void* out_bf16, int s,
                     void* stream);
+/* conv2's geometry (4x4 stride 2 VALID over [S,20,20,16] -> [S,9,9,32]) without bias and ReLU: the input gradient of
+ * the pixel-control head's transposed convolution (model.py:418-430 backward) is this convolution of d loss / d y
+ * (padded to 16 channels) with the deconv filter; w as in unreal_conv_fwd layer 2. */
+int unreal_conv2_fwd_linear(const void* in_bf16, const void* w_taps_bf16, void* out_bf16, int s, void* stream);
 
 /* ReLU backward fused with the bias gradient (tf.nn.relu / bias_add gradients of the dense layers):
  * out_bf16 = dy * (y > 0) and db[c] += sum_rows out[:, c]; y_bf16 NULL: no mask; out / db nullable.
@@ -303,6 +307,10 @@ int unreal_pc_deconv_fwd(const void* h_bf16, const void* w_dtaps_bf16, const flo
  * dy8 (nullable): d loss / d (pre-ReLU output) scaled by *go (device scalar, nullable = 1). */
 int unreal_pc_loss(const float* y8, const int32_t* act, const float* target, const float* mask, int a, float lam,
                    int64_t samples, int px_per_sample, double* loss, float* dy8, const float* go, void* stream);
+/* gradient only, written as the conv2-geometry input of the deconv's backward: dy16 bf16 [S*px, 16] (channels 8..15
+ * zero) and the deconv bias gradient db8 [8] f32 (caller-zeroed, atomically accumulated, nullable). */
+int unreal_pc_loss_grad16(const float* y8, const int32_t* act, const float* target, const float* mask, int a, float lam,
+                          int64_t samples, int px_per_sample, void* dy16_bf16, float* db8, const float* go, void* stream);
 
 #ifdef __cplusplus
 }

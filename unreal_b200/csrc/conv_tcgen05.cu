@@ -88,6 +88,7 @@ struct ConvArgs {
   int rows;           // valid GEMM rows per item: 81
   int box_bytes;      // bytes one A box delivers
   int mode;           // 2: conv2 over h1
+  int relu;           // apply max(., 0) in the epilogue
 };
 
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2, int c3) {
@@ -217,8 +218,9 @@ conv_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_
           uint32_t pk[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const float v0 = fmaxf(__uint_as_float(r[8 * q + 2 * j]) + b[8 * q + 2 * j], 0.f);
-            const float v1 = fmaxf(__uint_as_float(r[8 * q + 2 * j + 1]) + b[8 * q + 2 * j + 1], 0.f);
+            float v0 = __uint_as_float(r[8 * q + 2 * j]) + b[8 * q + 2 * j];
+            float v1 = __uint_as_float(r[8 * q + 2 * j + 1]) + b[8 * q + 2 * j + 1];
+            if (g.relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
             __nv_bfloat162 p = __floats2bfloat162_rn(v0, v1);
             pk[j] = *reinterpret_cast<uint32_t*>(&p);
           }
@@ -1052,8 +1054,8 @@ extern "C" int unreal_conv1_fwd_maze(const int32_t* pos, const void* w_taps_bf16
   return UNREAL_OK;
 }
 
-extern "C" int unreal_conv_fwd(const void* in_bf16, int layer, const void* w_taps_bf16, const float* bias,
-                               void* out_bf16, int s, void* stream) {
+static int conv_fwd_impl(const void* in_bf16, int layer, const void* w_taps_bf16, const float* bias, void* out_bf16, int s,
+                         int relu, void* stream) {
   UNREAL_REQUIRE(in_bf16 && w_taps_bf16 && out_bf16 && s > 0, "unreal_conv_fwd: null buffer or s <= 0");
   UNREAL_REQUIRE(layer == 1 || layer == 2, "unreal_conv_fwd: layer must be 1 (conv1 over x') or 2 (conv2 over h1)");
   UNREAL_REQUIRE(aligned16(in_bf16) && aligned16(w_taps_bf16) && aligned16(out_bf16),
@@ -1062,6 +1064,7 @@ extern "C" int unreal_conv_fwd(const void* in_bf16, int layer, const void* w_tap
   ConvArgs g;
   g.bias = bias;
   g.mode = layer;
+  g.relu = relu;
   int rc;
   const int n = layer == 1 ? 16 : 32;
   if (layer == 1) {
@@ -1108,6 +1111,15 @@ extern "C" int unreal_conv_fwd(const void* in_bf16, int layer, const void* w_tap
     if (rc != UNREAL_OK) return rc;
   }
   return launch_conv<32, 2>(ta, ta2, tw, tc, g, as_stream(stream));
+}
+
+extern "C" int unreal_conv_fwd(const void* in_bf16, int layer, const void* w_taps_bf16, const float* bias,
+                               void* out_bf16, int s, void* stream) {
+  return conv_fwd_impl(in_bf16, layer, w_taps_bf16, bias, out_bf16, s, 1, stream);
+}
+
+extern "C" int unreal_conv2_fwd_linear(const void* in_bf16, const void* w_taps_bf16, void* out_bf16, int s, void* stream) {
+  return conv_fwd_impl(in_bf16, 2, w_taps_bf16, nullptr, out_bf16, s, 0, stream);
 }
 
 static int conv1_wgrad_launch(const void* xpp_bf16, const void* dy_planes_bf16, float* dw_taps, int s, int pitch21,

@@ -277,9 +277,11 @@ __global__ void __launch_bounds__(256) pc_loss_kernel(const float* __restrict__ 
                                                       const float* __restrict__ target, const float* __restrict__ mask,
                                                       int A, float lam, int64_t rows, int px_per_sample,
                                                       double* __restrict__ loss, float* __restrict__ dy,
-                                                      const float* __restrict__ go) {
+                                                      const float* __restrict__ go, __nv_bfloat16* __restrict__ dy16,
+                                                      float* __restrict__ db8) {
   float part = 0.f;
-  const float gscale = (dy != nullptr && go != nullptr) ? *go : 1.f;
+  float dbacc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const float gscale = ((dy != nullptr || dy16 != nullptr) && go != nullptr) ? *go : 1.f;
   const float inv_a = 1.0f / (float)A;
   for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x) {
     const int64_t smp = r / px_per_sample;
@@ -296,14 +298,40 @@ __global__ void __launch_bounds__(256) pc_loss_kernel(const float* __restrict__ 
     qa = v[0] + qa - sum * inv_a;
     const float diff = qa - __ldcs(target + r);
     part += m * diff * diff;
-    if (dy != nullptr) {
+    if (dy != nullptr || dy16 != nullptr) {
       const float g = gscale * lam * m * diff;
       float d[8];
       d[0] = v[0] > 0.f ? g : 0.f;
 #pragma unroll
       for (int k = 0; k < 7; ++k) d[1 + k] = (k < A && v[1 + k] > 0.f) ? g * ((k == a ? 1.f : 0.f) - inv_a) : 0.f;
-      __stcs(reinterpret_cast<float4*>(dy + r * 8), make_float4(d[0], d[1], d[2], d[3]));
-      __stcs(reinterpret_cast<float4*>(dy + r * 8 + 4), make_float4(d[4], d[5], d[6], d[7]));
+      if (dy != nullptr) {
+        __stcs(reinterpret_cast<float4*>(dy + r * 8), make_float4(d[0], d[1], d[2], d[3]));
+        __stcs(reinterpret_cast<float4*>(dy + r * 8 + 4), make_float4(d[4], d[5], d[6], d[7]));
+      }
+      if (dy16 != nullptr) {
+        // the gradient as conv2-geometry input [rows, 16] bf16 (channels 8..15 zero): the deconv's backward runs on
+        // the encoder's conv2 kernels; the bias gradient sums the ROUNDED values (as unreal_relu_grad does)
+        uint32_t pk[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          __nv_bfloat162 p = __floats2bfloat162_rn(d[2 * j], d[2 * j + 1]);
+          pk[j] = *reinterpret_cast<uint32_t*>(&p);
+          const float2 f = __bfloat1622float2(p);
+          dbacc[2 * j] += f.x; dbacc[2 * j + 1] += f.y;
+        }
+        uint4* o = reinterpret_cast<uint4*>(dy16 + r * 16);
+        o[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        o[1] = make_uint4(0u, 0u, 0u, 0u);
+      }
+    }
+  }
+  if (dy16 != nullptr && db8 != nullptr) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      float x = dbacc[c];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+      if ((threadIdx.x & 31) == 0) atomicAdd(db8 + c, x);
     }
   }
   if (loss == nullptr) return;
@@ -506,7 +534,24 @@ extern "C" int unreal_pc_loss(const float* y8, const int32_t* act, const float* 
   const int64_t rows = samples * px_per_sample;
   const int grid = grid_for_elems(rows);
   if (grid <= 0) return UNREAL_ECUDA;
-  pc_loss_kernel<<<grid, 256, 0, as_stream(stream)>>>(y8, act, target, mask, a, lam, rows, px_per_sample, loss, dy8, go);
+  pc_loss_kernel<<<grid, 256, 0, as_stream(stream)>>>(y8, act, target, mask, a, lam, rows, px_per_sample, loss, dy8, go,
+                                                      nullptr, nullptr);
   UNREAL_LAUNCH_CHECK("pc_loss_kernel");
+  return UNREAL_OK;
+}
+
+extern "C" int unreal_pc_loss_grad16(const float* y8, const int32_t* act, const float* target, const float* mask, int a,
+                                     float lam, int64_t samples, int px_per_sample, void* dy16_bf16, float* db8,
+                                     const float* go, void* stream) {
+  UNREAL_REQUIRE(y8 && act && target && mask && dy16_bf16 && samples > 0 && px_per_sample > 0,
+                 "unreal_pc_loss_grad16: null buffer or empty shape");
+  UNREAL_REQUIRE(a >= 1 && a <= 7, "unreal_pc_loss_grad16: action count %d not in 1..7 (8-channel padded head)", a);
+  UNREAL_REQUIRE(aligned16(y8) && aligned16(dy16_bf16), "unreal_pc_loss_grad16: 16-byte alignment");
+  const int64_t rows = samples * px_per_sample;
+  const int grid = grid_for_elems(rows);
+  if (grid <= 0) return UNREAL_ECUDA;
+  pc_loss_kernel<<<grid, 256, 0, as_stream(stream)>>>(y8, act, target, mask, a, lam, rows, px_per_sample, nullptr, nullptr, go,
+                                                      reinterpret_cast<__nv_bfloat16*>(dy16_bf16), db8);
+  UNREAL_LAUNCH_CHECK("pc_loss_kernel(grad16)");
   return UNREAL_OK;
 }

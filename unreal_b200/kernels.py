@@ -620,3 +620,25 @@ def conv1_wgrad_maze(pos, dy_planes21):
   call("unreal_conv1_wgrad_maze", ptr(pos, torch.int32, "pos"), ptr(dy_planes21, torch.bfloat16, "dy_planes"),
        ptr(acc, torch.float32), s, stream_ptr())
   return acc.view(2, 2, 16, 4, 4, 3).permute(0, 3, 1, 4, 5, 2).reshape(8, 8, 3, 16)
+
+
+def pc_loss_grad16(y8, act, target, mask, num_actions, lam, go):
+  """d pixel-control loss / d (pre-ReLU deconv output) as bf16 [S, px, 16] (channels 8..15 zero: conv2's input
+  geometry) plus the deconv bias gradient [8] f32."""
+  s, px = y8.shape[0], y8.shape[1]
+  dy16 = torch.empty(s, px, 16, dtype=torch.bfloat16, device=y8.device)
+  db8 = torch.zeros(8, dtype=torch.float32, device=y8.device)
+  call("unreal_pc_loss_grad16", ptr(y8, torch.float32, "y8"), ptr(act, torch.int32, "act"), ptr(target, torch.float32, "target"),
+       ptr(mask, torch.float32, "mask"), int(num_actions), float(lam), s, px, ptr(dy16, torch.bfloat16),
+       ptr(db8, torch.float32), ptr(go, torch.float32, "go"), stream_ptr())
+  return dy16, db8
+
+
+def conv2_fwd_linear(x, w_taps, out=None):
+  """conv2's geometry without bias / ReLU: x bf16 [S,20,20,16], w_taps = conv_taps(W [4,4,16,32], 2) -> bf16 [S,9,9,32]."""
+  s = x.shape[0]
+  if out is None:
+    out = torch.empty(s, 9, 9, 32, dtype=torch.bfloat16, device=x.device)
+  call("unreal_conv2_fwd_linear", ptr(x, torch.bfloat16, "x"), ptr(w_taps, torch.bfloat16, "w_taps"),
+       ptr(out, torch.bfloat16, "out"), s, stream_ptr())
+  return out

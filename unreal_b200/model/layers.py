@@ -258,3 +258,34 @@ class PcLossFn(torch.autograd.Function):
     _, dy = K.pc_loss(y8.view(y8.shape[0], 400, 8), act, target, mask, a, lam, want_loss=False, want_grad=True,
                       go=go.to(torch.float32).reshape(1).contiguous())
     return dy.view_as(y8), None, None, None, None, None
+
+
+class PcHeadLossFn(torch.autograd.Function):
+  """The pixel-control head after pc_fc1 and its loss as ONE autograd node (model.py:418-441, :531-546): merged
+  8-channel deconv forward (conv2's transposed-convolution kernel) -> dueling / gather / L2 loss kernel.  The
+  backward pass never leaves the encoder's conv2 kernels: the loss gradient is written as conv2-geometry input
+  (bf16, 16 channels, with the deconv bias gradient), the input gradient is conv2's FORWARD kernel over it
+  (`unreal_conv2_fwd_linear`: d/dx of a transposed convolution is the convolution) and the filter gradient is
+  conv2's wgrad kernel with the roles of activation and gradient exchanged -- no im2col, no column matrices."""
+
+  @staticmethod
+  def forward(ctx, h16, taps, b8, lin_taps, wv32, bv32, wa32, ba32, act, target, mask, num_actions, lam):
+    s = h16.shape[0]
+    y8 = K.pc_deconv_fwd(h16, taps, b8)                                 # f32 [S,20,20,8]
+    loss, _ = K.pc_loss(y8.view(s, 400, 8), act, target, mask, num_actions, lam)
+    ctx.cfg = (num_actions, lam)
+    ctx.lin_taps = lin_taps
+    ctx.save_for_backward(h16, y8, act, target, mask)
+    return loss[0].to(torch.float32)
+
+  @staticmethod
+  def backward(ctx, go):
+    h16, y8, act, target, mask = ctx.saved_tensors
+    a, lam = ctx.cfg
+    s = h16.shape[0]
+    dy16, db8 = K.pc_loss_grad16(y8.view(s, 400, 8), act, target, mask, a, lam, go.to(torch.float32).reshape(1).contiguous())
+    dy16 = dy16.view(s, 20, 20, 16)
+    dh = K.conv2_fwd_linear(dy16, ctx.lin_taps).view(s, 2592)
+    dw16 = K.conv2_wgrad(dy16, h16.reshape(s * 81, 32))                  # [4,4,16,32]: channels 8..15 are padding
+    return (dh, None, None, None, dw16[:, :, 0:1].contiguous(), db8[0:1].clone(), dw16[:, :, 1:1 + a].contiguous(),
+            db8[1:1 + a].clone(), None, None, None, None, None)

@@ -26,7 +26,7 @@ import torch
 
 from .. import _lib
 from .. import kernels as K
-from .layers import ConvFn, Deconv8Fn, EncoderFn, LinearFn, LstmFn, PcLossFn
+from .layers import ConvFn, Deconv8Fn, EncoderFn, LinearFn, LstmFn, PcHeadLossFn, PcLossFn
 
 
 def _variable_specs(A, G, use_pc, use_rp):
@@ -140,10 +140,13 @@ class UnrealModel(object):
         v32 = self._views(self.flat)
         b8[0:1] = v32["b_pc_deconv_v"]; b8[1:1 + A] = v32["b_pc_deconv_a"]
       t8 = K.pc_deconv_taps(w8)           # tap-major shadow for the fused tcgen05 deconv forward
+      w16 = torch.zeros(4, 4, 16, 32, dtype=torch.bfloat16, device=self._device)
+      w16[:, :, :8] = w8                  # the same filter in conv2's geometry: the deconv's input gradient is conv2's forward
+      l8 = K.conv_taps(w16, 2)
       if getattr(self, "pc_w8", None) is None:
-        self.pc_w8, self.pc_b8, self.pc_taps = w8.view(128, 32), b8, t8
+        self.pc_w8, self.pc_b8, self.pc_taps, self.pc_lin_taps = w8.view(128, 32), b8, t8, l8
       else:
-        self.pc_w8.copy_(w8.view(128, 32)); self.pc_b8.copy_(b8); self.pc_taps.copy_(t8)
+        self.pc_w8.copy_(w8.view(128, 32)); self.pc_b8.copy_(b8); self.pc_taps.copy_(t8); self.pc_lin_taps.copy_(l8)
 
   def get_vars(self):
     """The variables in creation order (views of the flat buffer), like model.py:729-730."""
@@ -342,11 +345,18 @@ class UnrealModel(object):
       f = feed["pc"]
       L, n = f["images"].shape[:2]
       (h, _, _), _ = self._tower(p32, f["images"], f["lar"], *self._zeros_state(n))
-      y8 = self._pc_head(p32, h.reshape(L * n, 256))
       act = f["a"].reshape(L * n, -1).argmax(-1).to(torch.int32)
-      parts["pc"] = PcLossFn.apply(y8, act, f["R"].reshape(L * n, 400).contiguous(),
-                                   f["mask"].reshape(L * n).to(torch.float32).contiguous(), self._action_size,
-                                   self._pixel_change_lambda)
+      tgt = f["R"].reshape(L * n, 400).contiguous()
+      msk = f["mask"].reshape(L * n).to(torch.float32).contiguous()
+      if self.fused_conv and self.fused_encoder:
+        hp = LinearFn.apply(h.reshape(L * n, 256).to(torch.bfloat16), self.v16["W_pc_fc1"], p32["W_pc_fc1"], p32["b_pc_fc1"],
+                            True, True)
+        parts["pc"] = PcHeadLossFn.apply(hp, self.pc_taps, self.pc_b8, self.pc_lin_taps, p32["W_pc_deconv_v"],
+                                         p32["b_pc_deconv_v"], p32["W_pc_deconv_a"], p32["b_pc_deconv_a"], act, tgt, msk,
+                                         self._action_size, self._pixel_change_lambda)
+      else:
+        y8 = self._pc_head(p32, h.reshape(L * n, 256))
+        parts["pc"] = PcLossFn.apply(y8, act, tgt, msk, self._action_size, self._pixel_change_lambda)
       total = total + parts["pc"]
     if self._use_value_replay and "vr" in feed:
       f = feed["vr"]
