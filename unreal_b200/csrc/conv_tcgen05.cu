@@ -466,11 +466,15 @@ conv1_fwd_tcgen05_kernel(const __nv_bfloat16* __restrict__ xpp, const __nv_bfloa
 // of each output row), so whatever finite data x'' holds there contributes nothing.  Each CTA keeps
 // its four [48 x 16] accumulators in TMEM across ALL its items and adds them to global once.
 // Traffic per frame: 42 KB of x'' + 12.8 KB of dY, each read once; no patch matrix.
-constexpr int kWgStages = 4;      // three CTAs per SM (68 KB and 64 TMEM columns each)
-constexpr int kWgStageBytes = 16384;            // x'' tile 12 096 (+192 pad) | dY tile 2 x 112 x 16 = 3 584 (+512)
+// The four taps share ONE x'' tile and differ only by a pixel shift; instead of shifting A (four UMMAs per K step,
+// each re-reading 2 KB of x'' from shared memory -- the tensor core's operand fetch was 90 % busy at 30 % math,
+// profiles/r1_conv_s3_kernels_summary.txt) the dY tile is landed FOUR times, plane (tap, half) at row offset
+// shift(tap): B[q, (tap,o)] = dY[q - shift(tap), o], N = 64, and one UMMA per K step reads x'' once.
+constexpr int kWgStages = 2;      // three CTAs per SM (58 KB and 64 TMEM columns each)
+constexpr int kWgStageBytes = 28672;            // x'' tile 12 096 (+192 pad) | dY: 4 taps x 2 halves x 128 rows x 16 B
 constexpr int kWgDyOff = 12288;
-constexpr int kWgDyPlane = 112 * 16;
-constexpr int kWgTail = 2048;                    // A chunks 6, 7 of the last stage read (ignored) rows here
+constexpr int kWgDyPlane = 128 * 16;
+constexpr int kWgTail = 0;
 constexpr int kWgSmem = kWgStages * kWgStageBytes + kWgTail + 1024 + 1024;
 
 __global__ void __launch_bounds__(96, 3)
@@ -516,12 +520,15 @@ conv1_wgrad_tcgen05_kernel(const __nv_bfloat16* __restrict__ xpp, const __nv_bfl
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) {
-        mbar_arrive_expect_tx(full_bar(stage), 2 * 1680);
+        mbar_arrive_expect_tx(full_bar(stage), 8 * 1680);
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
           const uint8_t* ds = reinterpret_cast<const uint8_t*>(dyp) + ((int64_t)c * dy_plane_elems / 8 + smp * 420 + rb * 105) * 16;
-          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                       ::"r"(dst + kWgDyOff + c * kWgDyPlane), "l"(ds), "r"(1680), "r"(full_bar(stage)) : "memory");
+#pragma unroll
+          for (int t = 0; t < 4; ++t)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(dst + kWgDyOff + (t * 2 + c) * kWgDyPlane + ((t >> 1) * 21 + (t & 1)) * 16), "l"(ds), "r"(1680),
+                           "r"(full_bar(stage)) : "memory");
         }
       }
       if (++stage == kWgStages) { stage = 0; phase ^= 1u; }
@@ -531,7 +538,7 @@ conv1_wgrad_tcgen05_kernel(const __nv_bfloat16* __restrict__ xpp, const __nv_bfl
       int stage = 0; uint32_t phase = 0;
       for (int it = blockIdx.x; it < items; it += gridDim.x) {
         mbar_wait(empty_bar(stage), phase ^ 1u);
-        mbar_arrive_expect_tx(full_bar(stage), kC1BoxBytes + (pitch21 ? 2 * 1680 : 10 * 320));
+        mbar_arrive_expect_tx(full_bar(stage), kC1BoxBytes + (pitch21 ? 8 * 1680 : 40 * 320));
         const int64_t smp = it >> 2;
         const int rb = it & 3;
         const uint32_t dst = smem_base + stage * kWgStageBytes;
@@ -546,18 +553,23 @@ conv1_wgrad_tcgen05_kernel(const __nv_bfloat16* __restrict__ xpp, const __nv_bfl
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
             const uint8_t* ds = reinterpret_cast<const uint8_t*>(dyp) + ((int64_t)c * dy_plane_elems / 8 + smp * 420 + rb * 105) * 16;
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"(dst + kWgDyOff + c * kWgDyPlane), "l"(ds), "r"(1680), "r"(full_bar(stage)) : "memory");
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+              asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                           ::"r"(dst + kWgDyOff + (t * 2 + c) * kWgDyPlane + ((t >> 1) * 21 + (t & 1)) * 16), "l"(ds), "r"(1680),
+                             "r"(full_bar(stage)) : "memory");
           }
         } else {
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
             const uint8_t* ds = reinterpret_cast<const uint8_t*>(dyp) + ((int64_t)c * dy_plane_elems / 8 + smp * 400 + rb * 100) * 16;
+#pragma unroll 1
+            for (int t = 0; t < 4; ++t)
 #pragma unroll
-            for (int oyl = 0; oyl < 5; ++oyl)
-              asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                           ::"r"(dst + kWgDyOff + c * kWgDyPlane + oyl * 21 * 16), "l"(ds + oyl * 320), "r"(320),
-                             "r"(full_bar(stage)) : "memory");
+              for (int oyl = 0; oyl < 5; ++oyl)
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(dst + kWgDyOff + (t * 2 + c) * kWgDyPlane + ((t >> 1) * 21 + (t & 1) + oyl * 21) * 16),
+                               "l"(ds + oyl * 320), "r"(320), "r"(full_bar(stage)) : "memory");
           }
         }
         if (++stage == kWgStages) { stage = 0; phase ^= 1u; }
@@ -572,7 +584,8 @@ conv1_wgrad_tcgen05_kernel(const __nv_bfloat16* __restrict__ xpp, const __nv_bfl
       // M = 64, not 128: the MN-major A operand is read from shared memory chunk by chunk, and at 128 B/clk a
       // 128-row read (16 chunks x 16 pixels x 16 B = 4 KB per UMMA, 10 of the 16 chunks garbage) is what bounds
       // the kernel; 64 rows (6 real chunks of 8) halve it
-      constexpr uint32_t idesc = idesc_bf16_f32(64, 16, true, true);
+      // N = 64 = (tap, o): the four shifted dY copies are the 8 chunks of ONE B operand
+      constexpr uint32_t idesc = idesc_bf16_f32(64, 64, true, true);
       int stage = 0; uint32_t phase = 0;
       bool first = true;
       for (int it = blockIdx.x; it < items; it += gridDim.x) {
@@ -582,16 +595,11 @@ conv1_wgrad_tcgen05_kernel(const __nv_bfloat16* __restrict__ xpp, const __nv_bfl
         // MN-major un-swizzled descriptors: LBO = 128 B (next 8 pixel rows), SBO = plane stride
         const uint32_t a_lo0 = (sx >> 4) | ((128u >> 4) << 16), b_lo0 = (sd >> 4) | ((128u >> 4) << 16);
         constexpr uint32_t a_hi = ((uint32_t)kC1PlaneBytes >> 4) | (1u << 14), b_hi = ((uint32_t)kWgDyPlane >> 4) | (1u << 14);
+        // K = 128 grid rows: x'' rows 0..125 (+2 zero pad rows) against dY rows shifted by up to 22
 #pragma unroll
-        for (int ks = 0; ks < 7; ++ks) {
-          // four independent accumulation chains (one per tap) are interleaved
-#pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            const uint32_t shift16 = (uint32_t)((t >> 1) * 21 + (t & 1));
-            mma_f16_lohi(tmem_base + (uint32_t)(t * 16), a_lo0 + shift16 + (uint32_t)(ks * 16), a_hi, b_lo0 + (uint32_t)(ks * 16), b_hi,
-                         idesc, (first && ks == 0) ? 0u : 1u);
-          }
-        }
+        for (int ks = 0; ks < 8; ++ks)
+          mma_f16_lohi(tmem_base, a_lo0 + (uint32_t)(ks * 16), a_hi, b_lo0 + (uint32_t)(ks * 16), b_hi, idesc,
+                       (first && ks == 0) ? 0u : 1u);
         first = false;
         mma_commit(empty_bar(stage));
         if (++stage == kWgStages) { stage = 0; phase ^= 1u; }
