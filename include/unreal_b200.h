@@ -236,6 +236,11 @@ int unreal_col2im(const void* cols, int cols_dtype, void* out, int out_dtype, co
  * c = c_prev*f + i*j, h = tanh(c)*o; h16 is the bf16 copy fed to the next step's GEMM. */
 int unreal_lstm_cell_fwd(float* gates, const float* c_prev, float* c_out, float* h_out, void* h16_out, int n,
                          void* stream);
+/* same; h16_out rows are h16_ld elements apart (>= 256): the bf16 h is written straight into columns of the next
+ * step's concatenated [x_t, h_{t-1}] GEMM operand, so each step is ONE GEMM over K = |x| + 256 that writes the gate
+ * pre-activations once (no separate x-part GEMM, no read-modify-write accumulation). */
+int unreal_lstm_cell_fwd_ld(float* gates, const float* c_prev, float* c_out, float* h_out, void* h16_out, int h16_ld,
+                            int n, void* stream);
 /* backward of the above: dh [N,256] total gradient wrt h_t; dc [N,256] in: wrt c_t, out: wrt
  * c_{t-1}; dgates bf16 [N,1024] wrt the pre-activations. */
 int unreal_lstm_cell_bwd(const float* gates_act, const float* c_prev, const float* c, const float* dh, float* dc,

@@ -156,7 +156,7 @@ __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __ex
 // gates [N,1024] pre-activations (i | j | f | o blocks of 256) are replaced by their activations
 __global__ void __launch_bounds__(256) lstm_cell_fwd_kernel(float* __restrict__ gates, const float* __restrict__ c_prev,
                                                             float* __restrict__ c_out, float* __restrict__ h_out,
-                                                            __nv_bfloat16* __restrict__ h16_out, int n) {
+                                                            __nv_bfloat16* __restrict__ h16_out, int n, int h16_ld) {
   const int id = blockIdx.x * blockDim.x + threadIdx.x;
   if (id >= n * 256) return;
   const int e = id >> 8, u = id & 255;
@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(256) lstm_cell_fwd_kernel(float* __restrict__ 
   gr[u] = i; gr[256 + u] = j; gr[512 + u] = f; gr[768 + u] = o;
   c_out[id] = c;
   h_out[id] = h;
-  h16_out[id] = __float2bfloat16_rn(h);
+  h16_out[(size_t)e * h16_ld + u] = __float2bfloat16_rn(h);     // h16_ld > 256: straight into the next step's [x, h] GEMM operand
 }
 
 // dh: total gradient wrt h_t (heads + recurrent); dc: in = gradient wrt c_t from step t+1,
@@ -476,7 +476,17 @@ extern "C" int unreal_lstm_cell_fwd(float* gates, const float* c_prev, float* c_
                                     int n, void* stream) {
   UNREAL_REQUIRE(gates && c_prev && c_out && h_out && h16_out && n > 0, "unreal_lstm_cell_fwd: null buffer or n <= 0");
   lstm_cell_fwd_kernel<<<(n * 256 + 255) / 256, 256, 0, as_stream(stream)>>>(
-      gates, c_prev, c_out, h_out, reinterpret_cast<__nv_bfloat16*>(h16_out), n);
+      gates, c_prev, c_out, h_out, reinterpret_cast<__nv_bfloat16*>(h16_out), n, 256);
+  UNREAL_LAUNCH_CHECK("lstm_cell_fwd_kernel");
+  return UNREAL_OK;
+}
+
+extern "C" int unreal_lstm_cell_fwd_ld(float* gates, const float* c_prev, float* c_out, float* h_out, void* h16_out,
+                                       int h16_ld, int n, void* stream) {
+  UNREAL_REQUIRE(gates && c_prev && c_out && h_out && h16_out && n > 0, "unreal_lstm_cell_fwd_ld: null buffer or n <= 0");
+  UNREAL_REQUIRE(h16_ld >= 256, "unreal_lstm_cell_fwd_ld: h16_ld %d < 256", h16_ld);
+  lstm_cell_fwd_kernel<<<(n * 256 + 255) / 256, 256, 0, as_stream(stream)>>>(
+      gates, c_prev, c_out, h_out, reinterpret_cast<__nv_bfloat16*>(h16_out), n, h16_ld);
   UNREAL_LAUNCH_CHECK("lstm_cell_fwd_kernel");
   return UNREAL_OK;
 }

@@ -442,9 +442,17 @@ def col2im(cols, s, h, w, c, kh, kw, stride, bias=None, relu=False, out_dtype=to
 
 
 def lstm_cell_fwd(gates, c_prev, c_out, h_out, h16_out):
+  """h16_out [n,256] bf16; a column slice of a wider row-major buffer is accepted (rows stride(0) apart)."""
   n = gates.shape[0]
-  call("unreal_lstm_cell_fwd", ptr(gates, torch.float32, "gates"), ptr(c_prev, torch.float32, "c_prev"),
-       ptr(c_out, torch.float32, "c_out"), ptr(h_out, torch.float32, "h_out"), ptr(h16_out, torch.bfloat16, "h16_out"),
+  if h16_out.is_contiguous():
+    call("unreal_lstm_cell_fwd", ptr(gates, torch.float32, "gates"), ptr(c_prev, torch.float32, "c_prev"),
+         ptr(c_out, torch.float32, "c_out"), ptr(h_out, torch.float32, "h_out"), ptr(h16_out, torch.bfloat16, "h16_out"),
+         n, stream_ptr())
+    return
+  if h16_out.dim() != 2 or h16_out.shape[1] != 256 or h16_out.stride(1) != 1 or h16_out.dtype != torch.bfloat16:
+    raise _lib.UnrealError("h16_out must be bf16 [n,256] with contiguous rows")
+  call("unreal_lstm_cell_fwd_ld", ptr(gates, torch.float32, "gates"), ptr(c_prev, torch.float32, "c_prev"),
+       ptr(c_out, torch.float32, "c_out"), ptr(h_out, torch.float32, "h_out"), h16_out.data_ptr(), int(h16_out.stride(0)),
        n, stream_ptr())
 
 

@@ -155,39 +155,45 @@ class LstmFn(torch.autograd.Function):
   """dynamic_rnn over BasicLSTMCell(256) (model.py:110, :343-351), N envs in lock step.
 
   xin16 [T,N,KX] bf16: columns [0, lstm_in) = concat(fc1 output, last_action_reward), the rest
-  zero padding (KX is lstm_in rounded up to 8 for the TMA row pitch).  The x-part of the kernel is
-  applied to all T*N rows in one GEMM; the h-part is the sequential per-step GEMM accumulated onto it.
+  zero padding (KX is lstm_in rounded up to 8 for the TMA row pitch).  `wcat16` [KX+256, 1024] is the cell's
+  kernel in that row layout (x rows, zero rows for the padding, h rows).  Each step is ONE GEMM over the
+  concatenated operand [x_t, h_{t-1}] (K = KX + 256) whose epilogue adds the bias and writes the gate
+  pre-activations once; the cell kernel writes h_t (bf16) straight into step t+1's operand columns.  (The
+  earlier form -- one GEMM for all x-parts, then a read-modify-write accumulation of h W_h per step -- moved
+  100 MB per step through HBM for the gates at 8192 envs instead of 33.5 MB.)
   """
 
   @staticmethod
-  def forward(ctx, xin16, w16, w32, b32, c0, h0, lstm_in):
+  def forward(ctx, xin16, wcat16, w32, b32, c0, h0, lstm_in):
     t, n, kx = xin16.shape
+    kc = kx + 256
     dev = xin16.device
-    x2 = xin16.view(t * n, kx)[:, :lstm_in]
-    gates = K.gemm_bf16(x2, w16[:lstm_in], b_mn_major=True, bias=b32).view(t, n, 1024)
+    xh = torch.empty(t, n, kc, device=dev, dtype=torch.bfloat16)
+    xh[:, :, :kx].copy_(xin16)
+    xh[0, :, kx:].copy_(h0)
+    gates = torch.empty(t, n, 1024, device=dev)
     c_all = torch.empty(t + 1, n, 256, device=dev)
-    h16_all = torch.empty(t + 1, n, 256, device=dev, dtype=torch.bfloat16)
     h_all = torch.empty(t, n, 256, device=dev)
+    h16_last = torch.empty(n, 256, device=dev, dtype=torch.bfloat16)
     c_all[0].copy_(c0)
-    h16_all[0].copy_(h0)
-    wh = w16[lstm_in:]
     for i in range(t):
-      K.gemm_bf16(h16_all[i], wh, out=gates[i], b_mn_major=True, accumulate=True)
-      K.lstm_cell_fwd(gates[i], c_all[i], c_all[i + 1], h_all[i], h16_all[i + 1])
+      K.gemm_bf16(xh[i], wcat16, out=gates[i], b_mn_major=True, bias=b32)
+      K.lstm_cell_fwd(gates[i], c_all[i], c_all[i + 1], h_all[i], xh[i + 1, :, kx:] if i + 1 < t else h16_last)
     ctx.lstm_in = lstm_in
-    ctx.save_for_backward(xin16, w16, gates, c_all, h16_all)
+    ctx.kx = kx
+    ctx.save_for_backward(xh, wcat16, gates, c_all)
     return h_all, c_all[t].clone(), h_all[t - 1].clone()
 
   @staticmethod
   def backward(ctx, dh_all, dc_last, dh_last):
-    xin16, w16, gates, c_all, h16_all = ctx.saved_tensors
-    lstm_in = ctx.lstm_in
-    t, n, kx = xin16.shape
-    dev = xin16.device
+    xh, wcat16, gates, c_all = ctx.saved_tensors
+    lstm_in, kx = ctx.lstm_in, ctx.kx
+    t, n, kc = xh.shape
+    dev = xh.device
     dh_all = dh_all.contiguous()
     dc = torch.zeros(n, 256, device=dev) if dc_last is None else dc_last.clone().contiguous()
     dgates = torch.empty(t, n, 1024, device=dev, dtype=torch.bfloat16)
-    wh = w16[lstm_in:]                                   # [256, 1024]: K-major B for dh = dgates @ Wh^T
+    wh = wcat16[kx:]                                     # [256, 1024]: K-major B for dh = dgates @ Wh^T
     dh_rec = None if dh_last is None else dh_last
     for i in range(t - 1, -1, -1):
       dh = dh_all[i] if dh_rec is None else dh_all[i] + dh_rec
@@ -195,13 +201,12 @@ class LstmFn(torch.autograd.Function):
       if i > 0:
         dh_rec = K.gemm_bf16(dgates[i], wh)
     dg2 = dgates.view(t * n, 1024)
-    dw = torch.empty(lstm_in + 256, 1024, device=dev)
-    dw[:lstm_in] = _wgrad(xin16.view(t * n, kx)[:, :lstm_in], dg2)
-    dw[lstm_in:] = _wgrad(h16_all[:t].view(t * n, 256), dg2)
+    dwcat = _wgrad(xh.view(t * n, kc), dg2)              # one wgrad over [x, h]: rows of the x part, padding, h part
+    dw = torch.cat((dwcat[:lstm_in], dwcat[kx:]), dim=0)
     _, db = K.relu_grad(dg2, None, want_out=False)
     dxin = torch.zeros(t, n, kx, device=dev, dtype=torch.bfloat16)
     # only the 256 fc1 columns carry a gradient (last_action_reward is an input)
-    K.gemm_bf16(dg2, w16[:256], out=dxin.view(t * n, kx)[:, :256])
+    K.gemm_bf16(dg2, wcat16[:256], out=dxin.view(t * n, kx)[:, :256])
     return dxin, None, dw, db, None, None, None
 
 

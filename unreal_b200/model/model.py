@@ -118,6 +118,11 @@ class UnrealModel(object):
     with torch.no_grad():
       self.flat16.copy_(self.flat)
     self.v16 = self._views(self.flat16)
+    # the LSTM kernel in the row layout of the per-step GEMM operand [x (KX columns, zero padded), h]
+    wl = self.v16["lstm_kernel"]
+    if getattr(self, "wcat16", None) is None:
+      self.wcat16 = torch.zeros(self.kx + 256, 1024, dtype=torch.bfloat16, device=self._device)
+    self.wcat16[:self.lstm_in].copy_(wl[:self.lstm_in]); self.wcat16[self.kx:].copy_(wl[self.lstm_in:])
     # tap-major filter shadows of the two encoder convolutions (TMA-im2col kernels); refreshed IN PLACE
     # so kernels captured in a CUDA graph keep reading the current filters
     if self.fused_conv:
@@ -201,7 +206,7 @@ class UnrealModel(object):
     t, n = images.shape[:2]
     h2 = self._encoder(p32, images.reshape(t * n, *images.shape[2:]))
     xin = self._lstm_input(p32, h2, lar, t, n)
-    return LstmFn.apply(xin, self.v16["lstm_kernel"], p32["lstm_kernel"], p32["lstm_bias"], c0, h0, self.lstm_in), h2
+    return LstmFn.apply(xin, self.wcat16, p32["lstm_kernel"], p32["lstm_bias"], c0, h0, self.lstm_in), h2
 
   def _policy_value(self, p32, h):
     """model.py:358-377 (tiny [.,256]x[256,A+1] products, fp32)."""
