@@ -9,6 +9,7 @@ import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 
+from unreal_b200 import _lib
 from unreal_b200.model.model import UnrealModel
 from unreal_b200.train.rmsprop_applier import RMSPropApplier
 
@@ -35,7 +36,7 @@ for _ in range(3):
 torch.cuda.synchronize()
 if graph:                                    # the whole update (fwd, bwd, clip + RMSProp, shadow refresh) as ONE CUDA graph
   g = torch.cuda.CUDAGraph()
-  with torch.cuda.graph(g):
+  with _lib.graph_capture(g):
     out = m.update(feed, lr, ap)
   step = g.replay
 else:

@@ -157,3 +157,25 @@ def stream_ptr(stream=None):
 
 def set_tunable(name, value):
   call("unreal_set_tunable", name.encode(), int(value))
+
+
+import contextlib
+import gc
+
+
+@contextlib.contextmanager
+def graph_capture(graph):
+  """`torch.cuda.graph(graph)` with Python's cyclic garbage collector held off for the duration of the capture.
+  A collection that runs mid-capture can finalise objects of earlier work whose destructors call cudaFree /
+  cudaGraphExecDestroy (library-owned replay rings, old CUDA graphs): a prohibited call during a global-mode
+  stream capture, which invalidates it (cudaErrorStreamCaptureInvalidated) -- at a random allocation, i.e. flaky.
+  Collect first, then keep the collector off until the capture has ended."""
+  gc.collect()
+  was_enabled = gc.isenabled()
+  gc.disable()
+  try:
+    with torch.cuda.graph(graph):
+      yield
+  finally:
+    if was_enabled:
+      gc.enable()

@@ -15,6 +15,7 @@ pass costs three graph launches.  All rollout buffers stay resident in HBM for t
 """
 import torch
 
+from .. import _lib
 from .. import kernels as K
 
 
@@ -76,7 +77,7 @@ class RolloutTargets(object):
     graphs = []
     for fn in (self._steps, self._returns, self._pc_targets):
       g = torch.cuda.CUDAGraph()
-      with torch.cuda.graph(g):
+      with _lib.graph_capture(g):
         fn()
       graphs.append(g)
     self._graphs = graphs

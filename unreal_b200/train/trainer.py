@@ -343,7 +343,7 @@ class Trainer(object):
       pending = self._pending_local_t
       torch.cuda.synchronize(self.device)
       g = torch.cuda.CUDAGraph()
-      with torch.cuda.graph(g):
+      with _lib.graph_capture(g):
         self._graph_feed = self._data_phase(sess)
       self._graph_pending = self._pending_local_t
       self._pending_local_t = pending
@@ -372,7 +372,7 @@ class Trainer(object):
       out = net.update(static_feed, self._lr_dev, ap)  # this iteration's update, eagerly (also warms every lazy path)
       torch.cuda.synchronize(self.device)
       g = torch.cuda.CUDAGraph()
-      with torch.cuda.graph(g):                        # recorded, not executed
+      with _lib.graph_capture(g):                      # recorded, not executed
         self._ugraph_out = net.update(static_feed, self._lr_dev, ap)
       self._ugraph = g
       return out
