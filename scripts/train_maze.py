@@ -2,7 +2,7 @@
 RMSProp.  Logs finished episodes and mean episode score (+1 goal, -1 per wall hit) per window; a
 random policy scores about -25 over a ~110-step episode, the optimal path is 11 steps with score +1.
 
-    python scripts/train_maze.py [envs] [seconds] [lr] [out.jsonl]
+    python scripts/train_maze.py [envs] [seconds] [lr] [out.jsonl|-] [cells|s2d|f32] [graphs 0|1] [seed]
 """
 import json
 import os
@@ -21,7 +21,10 @@ from unreal_b200.train.trainer import Trainer
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
 seconds = float(sys.argv[2]) if len(sys.argv) > 2 else 120.0
 lr = float(sys.argv[3]) if len(sys.argv) > 3 else 7.0710678e-4
-out = open(sys.argv[4], "w") if len(sys.argv) > 4 else sys.stdout
+out = open(sys.argv[4], "w") if len(sys.argv) > 4 and sys.argv[4] != "-" else sys.stdout
+obs = sys.argv[5] if len(sys.argv) > 5 else "cells"      # cells: render fused into conv1; s2d: K1-rendered x'' planes; f32
+graphs = bool(int(sys.argv[6])) if len(sys.argv) > 6 else True
+seed0 = int(sys.argv[7]) if len(sys.argv) > 7 else 0xA3C
 dev = torch.device("cuda", 0)
 net = UnrealModel(4, 0, -1, True, True, True, True, 0.05, 0.001, dev, {'segnet_mode': 0}, (84, 84), True, 0, 0.0, 0.0,
                   num_envs=n, seed=0)
@@ -29,7 +32,7 @@ applier = RMSPropApplier(lr, decay=0.99, momentum=0.0, epsilon=0.1, clip_norm=40
 max_t = 10 ** 10
 tr = Trainer(0, net, lr, None, applier, 'maze', '', True, True, True, True, 0.05, 0.001, 20, 20, 0.99, 0.9, 2000, max_t,
              "cuda:0", {'segnet_mode': 0}, (84, 84), True, 0, np.random.RandomState(1), 50.0, 0.0, 0.0, num_envs=n,
-             seeds=np.arange(n) + 0xA3C, use_graphs=True, obs_s2d=True)
+             seeds=np.arange(n) + seed0, use_graphs=graphs, obs_cells=(obs == 'cells'), obs_s2d=(obs == 's2d'))
 tr.prepare()
 while not tr.experience.is_full():
   tr.process(None, 0)

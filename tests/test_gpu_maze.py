@@ -203,3 +203,35 @@ def test_s2d_render_equals_space_to_depth_of_the_f32_frame():
     rb, tb = K.maze_step(sb, act, obs=ob, pc=pb, auto_reset=True)
     assert torch.equal(ra, rb) and torch.equal(ta, tb) and torch.equal(pa, pb) and torch.equal(sa.pos, sb.pos)
     assert torch.equal(ob, K.s2d_frames(oa))
+
+
+def test_observation_modes_agree_through_resets_and_masks():
+  """K1 with f32 frames, x'' planes (bf16) and cell observations (int32, frames implicit) steps the same mazes:
+  identical positions / rewards / terminals / records / pixel change, and every active env's observation is the
+  render of its (post-auto-reset) cell -- over enough random steps to see hundreds of episode ends."""
+  import torch
+  from unreal_b200 import kernels as K
+  from unreal_b200.environment.maze_environment import BatchedMazeEnvironment
+  n = 2048
+  envs = {m: BatchedMazeEnvironment(n, "cuda:0", obs_dtype=dt, auto_reset=True)
+          for m, dt in (("f32", torch.float32), ("s2d", torch.bfloat16), ("cells", torch.int32))}
+  g = torch.Generator(device="cuda").manual_seed(0)
+  terms = 0
+  for step in range(600):
+    act = torch.randint(0, 4, (n,), device="cuda", generator=g, dtype=torch.int32)
+    active = (torch.rand(n, device="cuda", generator=g) < 0.9).to(torch.uint8)
+    outs = {m: e.process(act, active=active) for m, e in envs.items()}
+    ref = envs["f32"]
+    pos = ref.state.pos
+    am = active.bool()
+    for m, e in envs.items():
+      assert torch.equal(e.state.pos, pos) and torch.equal(e.frame_rec, ref.frame_rec), (step, m)
+      assert torch.equal(outs[m][1], outs["f32"][1]) and torch.equal(outs[m][2], outs["f32"][2]), (step, m)
+      assert torch.equal(e.state.last_action, ref.state.last_action) and torch.equal(e.state.last_reward, ref.state.last_reward)
+      assert torch.equal(outs[m][3][am], outs["f32"][3][am]), (step, m, "pixel change")
+    if step % 20 == 0:
+      assert torch.equal(outs["f32"][0]['image'][am], K.maze_render(pos, dtype=torch.float32)[am]), step
+      assert torch.equal(outs["s2d"][0]['image'][am], K.maze_render(pos, dtype=torch.bfloat16)[am]), step
+    assert torch.equal(outs["cells"][0]['image'][am], pos[am]), step
+    terms += int((outs["f32"][2] & active).sum())
+  assert terms > 100
