@@ -382,6 +382,11 @@ def rmsprop_step(vars_, rms_, mom_, grads, lr, decay=0.9, momentum=0.0, epsilon=
 # one worker's rollout + replay targets (train/trainer.py:176-205, :218-436)
 # --------------------------------------------------------------------------
 
+def make_frame_table(seed, frame_shape=(84, 84, 3), k_frames=32):
+  """The seeded table of uint8 frames behind TableFrameEnvOracle (same formula as the device producer's)."""
+  return np.random.RandomState(seed).randint(0, 256, size=(k_frames,) + tuple(frame_shape)).astype(np.uint8)
+
+
 class TableFrameEnvOracle(object):
   """A generic-frame env with the instance contract of the reference's lab / gym / indoor classes
   (environment/lab_environment.py:94-131, indoor_environment.py:63-139): `last_state['image']` is

@@ -229,6 +229,72 @@ def gen_trainer(name, H, n_iter, n_step_TD, seed, net_seed):
         "dtype adv", np.asarray(base_adv).dtype)
 
 
+# ---------------------------------------------------------------------------
+# D. the same reference functions on a GENERIC-FRAME env (the lab / gym / indoor process() shape):
+#    frames come from the oracle's table-hashed frame source, everything under test is the reference's
+# ---------------------------------------------------------------------------
+def gen_trainer_frames(name, H, n_iter, n_step_TD, seed, net_seed, table_seed):
+  import zlib
+  sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+  from oracle import unreal_oracle as O
+
+  class FrameShim(O.TableFrameEnvOracle):
+    def process(self, action, flag=0):
+      out = O.TableFrameEnvOracle.process(self, action)
+      self._last_full_state = {'success': bool(out[2])}     # trainer.py:285 reads it on terminal
+      return out
+
+  crc = lambda img: zlib.crc32(np.ascontiguousarray(img, np.float32).tobytes())   # noqa: E731
+  rs = np.random.RandomState(seed)
+  net = FakeNet(net_seed, 3)
+  me = types.SimpleNamespace(
+      experience=Experience(H, rs), local_t_max=20, action_size=3, gamma=0.99, gamma_pc=0.9,
+      n_step_TD=n_step_TD, environment=FrameShim(0, O.make_frame_table(table_seed)), local_network=net, use_lstm=True,
+      segnet_mode=0, segnet_param_dict={'segnet_mode': 0}, thread_index=1, local_t=0, episode_reward=0,
+      success_rates=deque(maxlen=50), sr_size=50, random_state=rs)
+  me.choose_action = lambda pi: Trainer.choose_action(me, pi)
+  n_fill = 0
+  import io, contextlib
+  while not me.experience.is_full():
+    with contextlib.redirect_stdout(io.StringIO()):
+      Trainer._fill_experience(me, None)
+    n_fill += 1
+  out = {"cfg": np.array([H, n_iter, n_step_TD, seed, net_seed, n_fill, table_seed], np.int64)}
+  base_len = []; base_crc = []; base_lar = []; base_a = []; base_adv = []; base_R = []
+  pc_len = []; pc_crc = []; pc_lar = []; pc_a = []; pc_sum = []; pc_probe = []
+  vr_len = []; vr_crc = []; vr_lar = []; vr_R = []
+  rp_crc = []; rp_c = []
+  for it in range(n_iter):
+    sd = {'placeholders': {}, 'values': {}}
+    with contextlib.redirect_stdout(io.StringIO()):
+      si, _, lar, a, adv, R, _ = Trainer._process_base(me, None, 0, None, None, sd)
+    base_len.append(len(si))
+    for k in range(len(si)):
+      base_crc.append(crc(si[k])); base_lar.append(lar[k]); base_a.append(a[k]); base_adv.append(adv[k]); base_R.append(R[k])
+    si, lar, a, R = Trainer._process_pc(me, None)
+    pc_len.append(len(si))
+    for k in range(len(si)):
+      pc_crc.append(crc(si[k])); pc_lar.append(lar[k]); pc_a.append(a[k])
+      pc_sum.append(np.sum(R[k], dtype=np.float64)); pc_probe.append(np.asarray(R[k], np.float64).reshape(-1)[PC_PROBE])
+    si, lar, R = Trainer._process_vr(me, None)
+    vr_len.append(len(si))
+    for k in range(len(si)):
+      vr_crc.append(crc(si[k])); vr_lar.append(lar[k]); vr_R.append(R[k])
+    si, c = Trainer._process_rp(me)
+    rp_crc.append([crc(s_) for s_ in si]); rp_c.append(c[0])
+  out.update(
+      base_len=np.array(base_len), base_crc=np.array(base_crc, np.uint32), base_lar=np.array(base_lar, np.float64),
+      base_a=np.array(base_a, np.float64), base_adv=np.array(base_adv, np.float64), base_R=np.array(base_R, np.float64),
+      pc_len=np.array(pc_len), pc_crc=np.array(pc_crc, np.uint32), pc_lar=np.array(pc_lar, np.float64),
+      pc_a=np.array(pc_a, np.float64), pc_R_sum=np.array(pc_sum), pc_R_probe=np.array(pc_probe),
+      vr_len=np.array(vr_len), vr_crc=np.array(vr_crc, np.uint32), vr_lar=np.array(vr_lar, np.float64),
+      vr_R=np.array(vr_R, np.float64), rp_crc=np.array(rp_crc, np.uint32), rp_c=np.array(rp_c, np.float64),
+      final_top=np.array([me.experience._top_frame_index, me.local_t]))
+  np.savez_compressed(os.path.join(HERE, "trainer_%s.npz" % name), **out)
+  print("trainer", name, "fill", n_fill, "iters", n_iter, "base steps", sum(base_len),
+        "episodes ended", int(sum(1 for l in base_len if l < n_step_TD)))
+
+
 PC_FULL = 400
 PC_PROBE = np.array([0, 19, 21, 63, 105, 147, 168, 189, 210, 231, 252, 294, 336, 378, 380, 399])
 
@@ -244,3 +310,4 @@ if __name__ == "__main__":
   gen_experience()
   gen_trainer("h2000", 2000, 300, 20, 0xA3C, 99)
   gen_trainer("h100", 100, 400, 20, 5, 17)
+  gen_trainer_frames("frames_h120", 120, 200, 20, 21, 33, 6)

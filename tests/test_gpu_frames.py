@@ -108,6 +108,7 @@ def test_frame_env_matches_oracle_env_step_by_step():
   N = 6
   env = _make_env(N)
   table = TableFrameProducer.make_table(5)
+  assert np.array_equal(table, O.make_frame_table(5)), "device producer and oracle env hash into the same frame table"
   oracles = [O.TableFrameEnvOracle(e, table) for e in range(N)]
   rs = np.random.RandomState(0)
   exact = True

@@ -167,3 +167,53 @@ def test_global_norm_clip():
   np.testing.assert_allclose(O.global_norm(clipped), 40.0, rtol=1e-6)
   small, n2 = O.clip_by_global_norm([np.ones(4, np.float32)], 40.0)
   assert np.array_equal(small[0], np.ones(4, np.float32)) and n2 == 2.0
+
+
+def test_generic_frame_rollout_targets_match_reference(golden_dir):
+  """the REFERENCE's Trainer._fill_experience / _process_base / _pc / _vr / _rp and Experience, driven
+  on a generic-frame env (frames as `uint8 / 255` float32, float rewards, episode ends: the lab / gym / indoor
+  process() shape), against the oracle's RolloutOracle on the same frame stream: sampled frames by checksum,
+  last_action_reward vectors, actions, n-step returns / advantages, PC and VR targets, RP classes, ring top."""
+  import zlib
+  g = _load(golden_dir, "trainer_frames_h120.npz")
+  H, n_iter, n_step, seed, net_seed, n_fill, table_seed = [int(v) for v in g["cfg"]]
+  crc = lambda img: zlib.crc32(np.ascontiguousarray(img, np.float32).tobytes())   # noqa: E731
+  rs = np.random.RandomState(seed)
+  w = O.RolloutOracle(H, rs, FakeNet(net_seed, 3), n_step_TD=n_step, action_size=3,
+                      env=O.TableFrameEnvOracle(0, O.make_frame_table(table_seed)))
+  fills = 0
+  while not w.ring.is_full():
+    w.fill_step()
+    fills += 1
+  assert fills == n_fill
+  bi = pi = vi = 0
+  ended = 0
+  for it in range(n_iter):
+    b = w.process_base()
+    ended += int(b['terminal_end'])
+    assert len(b['states']) == g["base_len"][it]
+    for k in range(len(b['states'])):
+      assert crc(b['states'][k]['image']) == g["base_crc"][bi]
+      assert np.array_equal(b['lar'][k], g["base_lar"][bi]) and np.array_equal(b['a'][k], g["base_a"][bi])
+      assert b['R'][k] == g["base_R"][bi] and b['adv'][k] == g["base_adv"][bi]
+      bi += 1
+    p = w.process_pc()
+    assert len(p['states']) == g["pc_len"][it]
+    for k in range(len(p['states'])):
+      assert crc(p['states'][k]['image']) == g["pc_crc"][pi]
+      assert np.array_equal(p['lar'][k], g["pc_lar"][pi]) and np.array_equal(p['a'][k], g["pc_a"][pi])
+      m = np.asarray(p['R'][k], np.float64)
+      assert np.sum(m, dtype=np.float64) == g["pc_R_sum"][pi]
+      assert np.array_equal(m.reshape(-1)[PC_PROBE], g["pc_R_probe"][pi])
+      pi += 1
+    v = w.process_vr()
+    assert len(v['states']) == g["vr_len"][it]
+    for k in range(len(v['states'])):
+      assert crc(v['states'][k]['image']) == g["vr_crc"][vi]
+      assert np.array_equal(v['lar'][k], g["vr_lar"][vi]) and v['R'][k] == g["vr_R"][vi]
+      vi += 1
+    r = w.process_rp()
+    assert [crc(s['image']) for s in r['states']] == list(g["rp_crc"][it])
+    assert r['c'] == list(g["rp_c"][it])
+  assert ended > 50, "the fixture covers rollouts that end in a terminal"
+  assert (w.ring.top, w.local_t) == tuple(g["final_top"])
