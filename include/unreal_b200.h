@@ -305,6 +305,23 @@ int unreal_conv2_dgrad_relu(const void* dy_bf16, const void* w_dtaps_bf16, const
 int unreal_pc_deconv_fwd(const void* h_bf16, const void* w_dtaps_bf16, const float* bias8, float* y8, int s,
                          void* stream);
 
+/* Policy / value heads and the A3C losses in one pass over h [M,256] f32 (model.py:358-377 heads; :499-527 base
+ * policy + entropy + value loss; :556-565 value-replay loss): logits = h Wp + bp, pi = softmax, v = h Wv + bv
+ * (Wp [256,A], Wv [256]: TF [in,out] layouts, fp32).  Every output is nullable:
+ *   pi_out [M,A], v_out [M]                       the acting outputs of run_base_policy_and_value / run_base_value
+ *   sums [3] f64 += (policy loss, value loss, entropy) with act [M] i32, adv, r, mask [M] f32 (mask NULL: all ones):
+ *     policy = -sum mask (log pi[a] adv + entropy_beta H), value = value_coef sum mask (r - v)^2, pi clamped to [1e-20,1]
+ *   dz [M,A] = d policy / d logits, dv [M] = d value / d v   (consumed by unreal_a3c_head_bwd)
+ * act NULL: no policy loss (value replay); r NULL: no value loss; a = 0 / wp NULL: value head only. */
+int unreal_a3c_head_loss(const float* h, const float* wp, const float* bp, const float* wv, const float* bv,
+                         const int32_t* act, const float* adv, const float* r, const float* mask, int64_t m, int a,
+                         float entropy_beta, float value_coef, float* pi_out, float* v_out, double* sums, float* dz,
+                         float* dv, void* stream);
+/* backward of the two heads: go2 [2] f32 on the device = incoming gradients of (policy, value) losses;
+ * dh [M,256] = go_p dz Wp^T + go_v dv Wv^T (written), dwp [256,A] / dbp [A] / dwv [256] / dbv [1] += (caller-zeroed). */
+int unreal_a3c_head_bwd(const float* h, const float* wp, const float* wv, const float* dz, const float* dv,
+                        const float* go2, int64_t m, int a, float* dh, float* dwp, float* dbp, float* dwv, float* dbv,
+                        void* stream);
 /* Pixel-control head: dueling combine, Q(a) gather and L2 loss in one pass (model.py:431-441, :531-546).
  * y8 [samples*px, 8] f32 = merged deconv output after ReLU (channel 0 V, 1..A advantages, rest padding);
  * act [samples] i32; target [samples*px] f32; mask [samples] f32.

@@ -383,3 +383,40 @@ def test_render_fused_conv1_equals_conv1_on_rendered_frames():
   a = K.conv1_wgrad_maze(pos, dy)
   b = K.conv1_wgrad(xpp, dy)
   assert torch.allclose(a, b, rtol=1e-5, atol=1e-5 * float(b.abs().max()))
+
+
+def test_fused_heads_match_torch_heads():
+  """unreal_a3c_head_loss / unreal_a3c_head_bwd (policy + value heads, softmax, A3C losses and their gradients in
+  two sweeps over h) against the same arithmetic written in torch fp32 with autograd."""
+  from unreal_b200 import kernels as K
+  from unreal_b200.model.layers import A3CHeadLossFn
+  dev = torch.device("cuda", 0)
+  g = torch.Generator(device=dev).manual_seed(8)
+  for m, a in ((5, 4), (1000, 3), (4097, 6)):
+    h = torch.randn(m, 256, device=dev, generator=g, requires_grad=True)
+    wp = (torch.randn(256, a, device=dev, generator=g) * 0.1).requires_grad_(True)
+    bp = (torch.randn(a, device=dev, generator=g) * 0.1).requires_grad_(True)
+    wv = (torch.randn(256, 1, device=dev, generator=g) * 0.1).requires_grad_(True)
+    bv = (torch.randn(1, device=dev, generator=g) * 0.1).requires_grad_(True)
+    act = torch.randint(0, a, (m,), device=dev, generator=g, dtype=torch.int32)
+    adv = torch.randn(m, device=dev, generator=g); ret = torch.randn(m, device=dev, generator=g)
+    mask = (torch.rand(m, device=dev, generator=g) < 0.8).float()
+    beta = 0.01
+    pol, val, ent = A3CHeadLossFn.apply(h, wp, bp, wv, bv, act, adv, ret, mask, beta, 0.25)
+    (pol * 0.7 + val * 1.3).backward()
+    got = [x.grad.clone() for x in (h, wp, bp, wv, bv)]
+    for x in (h, wp, bp, wv, bv):
+      x.grad = None
+    pi = torch.softmax(h @ wp + bp, -1); v = (h @ wv + bv).squeeze(-1)
+    lp = torch.log(pi.clamp(1e-20, 1.0)); H = -(pi * lp).sum(-1)
+    onehot = torch.nn.functional.one_hot(act.long(), a).float()
+    rpol = -((((lp * onehot).sum(-1)) * adv + H * beta) * mask).sum(); rval = 0.25 * (((ret - v) ** 2) * mask).sum()
+    (rpol * 0.7 + rval * 1.3).backward()
+    ref = [x.grad.clone() for x in (h, wp, bp, wv, bv)]
+    assert torch.allclose(pol, rpol, rtol=1e-4, atol=1e-3) and torch.allclose(val, rval, rtol=1e-4, atol=1e-3)
+    assert torch.allclose(ent, (H * mask).sum(), rtol=1e-4, atol=1e-3)
+    for x, y, name in zip(got, ref, "h wp bp wv bv".split()):
+      assert torch.allclose(x, y, rtol=1e-3, atol=1e-4 * float(y.abs().max() + 1e-6)), (m, a, name)
+    out = K.a3c_head(h.detach(), wp.detach().contiguous(), bp.detach(), wv.detach().reshape(256).contiguous(), bv.detach(),
+                     want_pi=True, want_v=True)
+    assert torch.allclose(out["pi"], pi.detach(), rtol=1e-4, atol=1e-6) and torch.allclose(out["v"], v.detach(), rtol=1e-4, atol=1e-5)

@@ -348,6 +348,177 @@ __global__ void __launch_bounds__(256) pc_loss_kernel(const float* __restrict__ 
   }
 }
 
+// ---- policy / value heads + A3C losses, fused (model.py:358-377 heads; :499-527 base loss; :556-565 VR loss) ----
+// h [M,256] f32 (LSTM output), Wp [256,A], bp [A], Wv [256], bv [1] (TF [in,out] layouts).  One warp per row; the
+// warp keeps its 8 x (A+1) weight slice in registers and walks rows persistently.
+//   logits = h Wp + bp;  pi = softmax(logits);  v = h Wv + bv
+//   policy = -sum mask * (log pi[a] * adv + beta * H),  H = -sum_k pi_k log pi_k   (pi clamped to [1e-20, 1] like :499-514)
+//   value  = coef * sum mask * (R - v)^2        (coef 0.25 base :527, 0.5 value replay :565)
+// The same pass writes d policy / d logits (dz) and d value / d v (dv) for the backward kernel:
+//   dz_j = mask * (-adv * ([j == a] - pi_j) + beta * pi_j * (log pi_j + H)),   dv = -2 coef mask (R - v).
+constexpr int kHeadMaxA = 7;
+
+struct HeadW {
+  float wp[8][kHeadMaxA];
+  float wv[8];
+};
+
+__device__ __forceinline__ void head_load_w(HeadW& w, const float* __restrict__ Wp, const float* __restrict__ Wv, int A,
+                                            int lane) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int k = lane + 32 * i;
+#pragma unroll
+    for (int j = 0; j < kHeadMaxA; ++j) w.wp[i][j] = (j < A) ? Wp[k * A + j] : 0.f;
+    w.wv[i] = Wv ? Wv[k] : 0.f;
+  }
+}
+
+__device__ __forceinline__ float warp_sum(float x) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+  return x;
+}
+
+__global__ void __launch_bounds__(256) a3c_head_loss_kernel(const float* __restrict__ h, const float* __restrict__ Wp,
+                                                            const float* __restrict__ bp, const float* __restrict__ Wv,
+                                                            const float* __restrict__ bv, const int32_t* __restrict__ act,
+                                                            const float* __restrict__ adv, const float* __restrict__ R,
+                                                            const float* __restrict__ mask, int64_t M, int A, float beta,
+                                                            float coef, float* __restrict__ pi_out, float* __restrict__ v_out,
+                                                            double* __restrict__ sums, float* __restrict__ dz,
+                                                            float* __restrict__ dv) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  HeadW w;
+  head_load_w(w, Wp, Wv, A, lane);
+  float s_pol = 0.f, s_val = 0.f, s_ent = 0.f;
+  for (int64_t r = warp0; r < M; r += nwarps) {
+    float z[kHeadMaxA + 1];
+#pragma unroll
+    for (int j = 0; j <= kHeadMaxA; ++j) z[j] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float x = h[r * 256 + lane + 32 * i];
+#pragma unroll
+      for (int j = 0; j < kHeadMaxA; ++j) z[j] = fmaf(x, w.wp[i][j], z[j]);
+      z[kHeadMaxA] = fmaf(x, w.wv[i], z[kHeadMaxA]);
+    }
+#pragma unroll
+    for (int j = 0; j <= kHeadMaxA; ++j) z[j] = warp_sum(z[j]);
+    const float v = z[kHeadMaxA] + (bv ? bv[0] : 0.f);
+    float mx = -3.0e38f;
+#pragma unroll
+    for (int j = 0; j < kHeadMaxA; ++j) if (j < A) { z[j] += bp[j]; mx = fmaxf(mx, z[j]); }
+    float den = 0.f, p[kHeadMaxA];
+#pragma unroll
+    for (int j = 0; j < kHeadMaxA; ++j) { p[j] = (j < A) ? __expf(z[j] - mx) : 0.f; den += p[j]; }
+    const float inv = 1.0f / den;
+    float H = 0.f, lp[kHeadMaxA];
+#pragma unroll
+    for (int j = 0; j < kHeadMaxA; ++j) {
+      p[j] *= inv;
+      lp[j] = __logf(fminf(fmaxf(p[j], 1e-20f), 1.0f));
+      if (j < A) H -= p[j] * lp[j];
+    }
+    if (lane == 0) {
+      if (v_out) v_out[r] = v;
+      if (pi_out) for (int j = 0; j < A; ++j) pi_out[r * A + j] = p[j];
+      const float m = mask ? mask[r] : 1.f;
+      if (act != nullptr) {
+        const int a = act[r];
+        const float ad = adv[r];
+        float lpa = 0.f;
+#pragma unroll
+        for (int j = 0; j < kHeadMaxA; ++j) if (j == a) lpa = lp[j];
+        s_pol -= m * (lpa * ad + beta * H);
+        s_ent += m * H;
+        if (dz) for (int j = 0; j < A; ++j) dz[r * A + j] = m * (-ad * ((j == a ? 1.f : 0.f) - p[j]) + beta * p[j] * (lp[j] + H));
+      }
+      if (R != nullptr) {
+        const float d = R[r] - v;
+        s_val += coef * m * d * d;
+        if (dv) dv[r] = -2.f * coef * m * d;
+      }
+    }
+  }
+  if (sums == nullptr) return;
+  // lane 0 of every warp holds the partial sums
+  __shared__ float sp[8][3];
+  if (lane == 0) { sp[threadIdx.x >> 5][0] = s_pol; sp[threadIdx.x >> 5][1] = s_val; sp[threadIdx.x >> 5][2] = s_ent; }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    double t = 0.0;
+    for (int q = 0; q < (int)(blockDim.x >> 5); ++q) t += (double)sp[q][threadIdx.x];
+    atomicAdd(sums + threadIdx.x, t);
+  }
+}
+
+// dh = go_p * dz Wp^T + go_v * dv Wv^T;  dWp += go_p * h^T dz;  dbp += go_p * sum dz;  dWv += go_v * h^T dv;  dbv += ...
+__global__ void __launch_bounds__(256) a3c_head_bwd_kernel(const float* __restrict__ h, const float* __restrict__ Wp,
+                                                           const float* __restrict__ Wv, const float* __restrict__ dz,
+                                                           const float* __restrict__ dv, const float* __restrict__ go,
+                                                           int64_t M, int A, float* __restrict__ dh, float* __restrict__ dWp,
+                                                           float* __restrict__ dbp, float* __restrict__ dWv,
+                                                           float* __restrict__ dbv) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const float gp = dz ? go[0] : 0.f, gv = dv ? go[1] : 0.f;
+  HeadW w;
+  head_load_w(w, Wp, Wv, A, lane);
+  float aw[8][kHeadMaxA + 1];      // this lane's rows k = lane + 32 i of [dWp | dWv]
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j <= kHeadMaxA; ++j) aw[i][j] = 0.f;
+  float ab[kHeadMaxA + 1];
+#pragma unroll
+  for (int j = 0; j <= kHeadMaxA; ++j) ab[j] = 0.f;
+  for (int64_t r = warp0; r < M; r += nwarps) {
+    float g[kHeadMaxA + 1];
+#pragma unroll
+    for (int j = 0; j < kHeadMaxA; ++j) g[j] = (dz && j < A) ? gp * dz[r * A + j] : 0.f;
+    g[kHeadMaxA] = dv ? gv * dv[r] : 0.f;
+#pragma unroll
+    for (int j = 0; j <= kHeadMaxA; ++j) ab[j] += g[j];      // every lane holds the same sums; lane 0 reports them
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int k = lane + 32 * i;
+      const float x = h[r * 256 + k];
+      float d = g[kHeadMaxA] * w.wv[i];
+#pragma unroll
+      for (int j = 0; j < kHeadMaxA; ++j) { d = fmaf(g[j], w.wp[i][j], d); aw[i][j] = fmaf(x, g[j], aw[i][j]); }
+      aw[i][kHeadMaxA] = fmaf(x, g[kHeadMaxA], aw[i][kHeadMaxA]);
+      dh[r * 256 + k] = d;
+    }
+  }
+  // reduce the 8 warps of the CTA in shared memory, then one atomic per element and CTA
+  __shared__ float sw[256][kHeadMaxA + 1];
+  for (int i = threadIdx.x; i < 256 * (kHeadMaxA + 1); i += blockDim.x) (&sw[0][0])[i] = 0.f;
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j <= kHeadMaxA; ++j) atomicAdd(&sw[lane + 32 * i][j], aw[i][j]);
+  __shared__ float sb[kHeadMaxA + 1];
+  if (threadIdx.x <= kHeadMaxA) sb[threadIdx.x] = 0.f;
+  __syncthreads();
+  if (lane == 0)
+#pragma unroll
+    for (int j = 0; j <= kHeadMaxA; ++j) atomicAdd(&sb[j], ab[j]);
+  __syncthreads();
+  for (int i = threadIdx.x; i < 256 * (kHeadMaxA + 1); i += blockDim.x) {
+    const int k = i / (kHeadMaxA + 1), j = i - k * (kHeadMaxA + 1);
+    const float x = sw[k][j];
+    if (j < A) { if (dWp) atomicAdd(dWp + k * A + j, x); }
+    else if (j == kHeadMaxA) { if (dWv) atomicAdd(dWv + k, x); }
+  }
+  if (threadIdx.x < A && dbp) atomicAdd(dbp + threadIdx.x, sb[threadIdx.x]);
+  if (threadIdx.x == kHeadMaxA && dbv) atomicAdd(dbv, sb[kHeadMaxA]);
+}
+
 // col2im for f32 columns with C a multiple of 4 (the merged, padded deconv: C = 8): float4 per tap
 __global__ void __launch_bounds__(256) col2im_f32v4_kernel(const float* __restrict__ cols, float* __restrict__ out,
                                                            const float* __restrict__ bias, int relu, ConvGeom g,
@@ -563,5 +734,40 @@ extern "C" int unreal_pc_loss_grad16(const float* y8, const int32_t* act, const 
   pc_loss_kernel<<<grid, 256, 0, as_stream(stream)>>>(y8, act, target, mask, a, lam, rows, px_per_sample, nullptr, nullptr, go,
                                                       reinterpret_cast<__nv_bfloat16*>(dy16_bf16), db8);
   UNREAL_LAUNCH_CHECK("pc_loss_kernel(grad16)");
+  return UNREAL_OK;
+}
+
+extern "C" int unreal_a3c_head_loss(const float* h, const float* wp, const float* bp, const float* wv, const float* bv,
+                                    const int32_t* act, const float* adv, const float* r, const float* mask, int64_t m,
+                                    int a, float entropy_beta, float value_coef, float* pi_out, float* v_out,
+                                    double* sums, float* dz, float* dv, void* stream) {
+  UNREAL_REQUIRE(h && m > 0, "unreal_a3c_head_loss: null h or m <= 0");
+  UNREAL_REQUIRE(a >= 0 && a <= kHeadMaxA, "unreal_a3c_head_loss: action count %d not in 0..7", a);
+  UNREAL_REQUIRE(a == 0 || (wp && bp), "unreal_a3c_head_loss: policy weights missing");
+  UNREAL_REQUIRE(act == nullptr || (adv != nullptr && a > 0), "unreal_a3c_head_loss: act needs adv and the policy head");
+  UNREAL_REQUIRE(r == nullptr || wv != nullptr, "unreal_a3c_head_loss: returns need the value head");
+  const int sms = sm_count();
+  if (sms <= 0) return UNREAL_ECUDA;
+  int64_t want = (m + 7) / 8;
+  const int grid = (int)(want < (int64_t)sms * 4 ? want : (int64_t)sms * 4);
+  a3c_head_loss_kernel<<<grid, 256, 0, as_stream(stream)>>>(h, wp, bp, wv, bv, act, adv, r, mask, m, a, entropy_beta, value_coef,
+                                                           pi_out, v_out, sums, dz, dv);
+  UNREAL_LAUNCH_CHECK("a3c_head_loss_kernel");
+  return UNREAL_OK;
+}
+
+extern "C" int unreal_a3c_head_bwd(const float* h, const float* wp, const float* wv, const float* dz, const float* dv,
+                                   const float* go2, int64_t m, int a, float* dh, float* dwp, float* dbp, float* dwv,
+                                   float* dbv, void* stream) {
+  UNREAL_REQUIRE(h && go2 && dh && m > 0, "unreal_a3c_head_bwd: null buffer or m <= 0");
+  UNREAL_REQUIRE(a >= 0 && a <= kHeadMaxA, "unreal_a3c_head_bwd: action count %d not in 0..7", a);
+  UNREAL_REQUIRE(dz == nullptr || (wp && a > 0), "unreal_a3c_head_bwd: dz needs the policy weights");
+  UNREAL_REQUIRE(dv == nullptr || wv, "unreal_a3c_head_bwd: dv needs the value weights");
+  const int sms = sm_count();
+  if (sms <= 0) return UNREAL_ECUDA;
+  int64_t want = (m + 7) / 8;
+  const int grid = (int)(want < (int64_t)sms * 2 ? want : (int64_t)sms * 2);
+  a3c_head_bwd_kernel<<<grid, 256, 0, as_stream(stream)>>>(h, wp, wv, dz, dv, go2, m, a, dh, dwp, dbp, dwv, dbv);
+  UNREAL_LAUNCH_CHECK("a3c_head_bwd_kernel");
   return UNREAL_OK;
 }

@@ -650,3 +650,46 @@ def conv2_fwd_linear(x, w_taps, out=None):
   call("unreal_conv2_fwd_linear", ptr(x, torch.bfloat16, "x"), ptr(w_taps, torch.bfloat16, "w_taps"),
        ptr(out, torch.bfloat16, "out"), s, stream_ptr())
   return out
+
+
+def a3c_head(h, wp, bp, wv, bv, act=None, adv=None, ret=None, mask=None, entropy_beta=0.0, value_coef=0.25,
+             want_pi=False, want_v=False, want_sums=False, want_grads=False):
+  """Policy / value heads (+ A3C losses) over h [M,256] f32 in one pass.  Returns a dict with the requested
+  pi [M,A], v [M], sums f64 [3] (policy, value, entropy), dz [M,A], dv [M]."""
+  m = h.shape[0]
+  a = 0 if wp is None else wp.shape[1]
+  d = h.device
+  out = {}
+  if want_pi:
+    out["pi"] = torch.empty(m, a, dtype=torch.float32, device=d)
+  if want_v:
+    out["v"] = torch.empty(m, dtype=torch.float32, device=d)
+  if want_sums:
+    out["sums"] = torch.zeros(3, dtype=torch.float64, device=d)
+  if want_grads:
+    if act is not None:
+      out["dz"] = torch.empty(m, a, dtype=torch.float32, device=d)
+    if ret is not None:
+      out["dv"] = torch.empty(m, dtype=torch.float32, device=d)
+  call("unreal_a3c_head_loss", ptr(h, torch.float32, "h"), ptr(wp, torch.float32, "wp"), ptr(bp, torch.float32, "bp"),
+       ptr(wv, torch.float32, "wv"), ptr(bv, torch.float32, "bv"), ptr(act, torch.int32, "act"),
+       ptr(adv, torch.float32, "adv"), ptr(ret, torch.float32, "ret"), ptr(mask, torch.float32, "mask"), m, a,
+       float(entropy_beta), float(value_coef), ptr(out.get("pi")), ptr(out.get("v")), ptr(out.get("sums")),
+       ptr(out.get("dz")), ptr(out.get("dv")), stream_ptr())
+  return out
+
+
+def a3c_head_bwd(h, wp, wv, dz, dv, go2):
+  """-> dh [M,256], dwp [256,A] or None, dbp [A] or None, dwv [256], dbv [1] (fp32)."""
+  m = h.shape[0]
+  a = 0 if wp is None else wp.shape[1]
+  d = h.device
+  dh = torch.empty(m, 256, dtype=torch.float32, device=d)
+  dwp = torch.zeros(256, a, dtype=torch.float32, device=d) if dz is not None else None
+  dbp = torch.zeros(a, dtype=torch.float32, device=d) if dz is not None else None
+  dwv = torch.zeros(256, dtype=torch.float32, device=d) if dv is not None else None
+  dbv = torch.zeros(1, dtype=torch.float32, device=d) if dv is not None else None
+  call("unreal_a3c_head_bwd", ptr(h, torch.float32, "h"), ptr(wp, torch.float32, "wp"), ptr(wv, torch.float32, "wv"),
+       ptr(dz, torch.float32, "dz"), ptr(dv, torch.float32, "dv"), ptr(go2, torch.float32, "go2"), m, a, ptr(dh), ptr(dwp),
+       ptr(dbp), ptr(dwv), ptr(dbv), stream_ptr())
+  return dh, dwp, dbp, dwv, dbv

@@ -294,3 +294,30 @@ class PcHeadLossFn(torch.autograd.Function):
     dw16 = K.conv2_wgrad(dy16, h16.reshape(s * 81, 32))                  # [4,4,16,32]: channels 8..15 are padding
     return (dh, None, None, None, dw16[:, :, 0:1].contiguous(), db8[0:1].clone(), dw16[:, :, 1:1 + a].contiguous(),
             db8[1:1 + a].clone(), None, None, None, None, None)
+
+
+class A3CHeadLossFn(torch.autograd.Function):
+  """Policy / value heads and their losses as ONE autograd node over two kernels (model.py:358-377, :499-527, :556-565):
+  the forward pass computes logits, softmax, value, the policy / value / entropy sums and the gradients w.r.t. logits
+  and value in one sweep over h; the backward pass is one more sweep (dh and the four head gradients).  `act` None:
+  value loss only (the value-replay tower).  Returns (policy_loss, value_loss, entropy) as fp32 scalars."""
+
+  @staticmethod
+  def forward(ctx, h, wp, bp, wv, bv, act, adv, ret, mask, entropy_beta, value_coef):
+    h = h.contiguous()
+    wv1 = wv.reshape(256).contiguous()
+    out = K.a3c_head(h, wp.contiguous() if act is not None else None, bp, wv1, bv, act, adv, ret, mask, entropy_beta,
+                     value_coef, want_sums=True, want_grads=True)
+    ctx.has_policy = act is not None
+    ctx.save_for_backward(h, wp.contiguous() if act is not None else None, wv1, out.get("dz"), out.get("dv"))
+    sums = out["sums"].to(torch.float32)
+    return sums[0].clone(), sums[1].clone(), sums[2].clone()
+
+  @staticmethod
+  def backward(ctx, g_pol, g_val, g_ent):
+    h, wp, wv1, dz, dv = ctx.saved_tensors
+    zero = torch.zeros((), dtype=torch.float32, device=h.device)
+    go2 = torch.stack((g_pol.to(torch.float32) if g_pol is not None else zero,
+                       g_val.to(torch.float32) if g_val is not None else zero)).contiguous()
+    dh, dwp, dbp, dwv, dbv = K.a3c_head_bwd(h, wp, wv1, dz, dv, go2)
+    return (dh, dwp, dbp, None if dwv is None else dwv.view(256, 1), dbv, None, None, None, None, None, None)

@@ -26,7 +26,7 @@ import torch
 
 from .. import _lib
 from .. import kernels as K
-from .layers import ConvFn, Deconv8Fn, EncoderFn, LinearFn, LstmFn, PcHeadLossFn, PcLossFn
+from .layers import A3CHeadLossFn, ConvFn, Deconv8Fn, EncoderFn, LinearFn, LstmFn, PcHeadLossFn, PcLossFn
 
 
 def _variable_specs(A, G, use_pc, use_rp):
@@ -79,6 +79,7 @@ class UnrealModel(object):
     self.kx = (self.lstm_in + 7) // 8 * 8
     self.fused_conv = True    # False: convolutions as explicit im2col + GEMM (A/B switch for benchmarks)
     self.fused_encoder = True # False: conv1 / conv2 as separate autograd nodes (dense gradient + relu_grad pass between them)
+    self.fused_heads = True   # False: policy / value heads and their losses as torch ops
     self._build_variables(seed)
     self.reset_state()
 
@@ -209,7 +210,13 @@ class UnrealModel(object):
     return LstmFn.apply(xin, self.wcat16, p32["lstm_kernel"], p32["lstm_bias"], c0, h0, self.lstm_in), h2
 
   def _policy_value(self, p32, h):
-    """model.py:358-377 (tiny [.,256]x[256,A+1] products, fp32)."""
+    """model.py:358-377 (tiny [.,256]x[256,A+1] products, fp32).  Without autograd (acting, bootstraps): one fused
+    head kernel (logits + softmax + value); with autograd: plain torch ops (the losses use A3CHeadLossFn instead)."""
+    if self.fused_heads and not torch.is_grad_enabled() and self._action_size <= 7:
+      lead = h.shape[:-1]
+      out = K.a3c_head(h.reshape(-1, 256).contiguous(), p32["W_base_fc_p"].contiguous(), p32["b_base_fc_p"],
+                       p32["W_base_fc_v"].reshape(256).contiguous(), p32["b_base_fc_v"], want_pi=True, want_v=True)
+      return out["pi"].view(*lead, self._action_size), out["v"].view(*lead)
     logits = h @ p32["W_base_fc_p"] + p32["b_base_fc_p"]
     v = (h @ p32["W_base_fc_v"] + p32["b_base_fc_v"]).squeeze(-1)
     return torch.softmax(logits, dim=-1), v
@@ -338,13 +345,21 @@ class UnrealModel(object):
     parts = OrderedDict()
     b = feed["base"]
     (h, _, _), _ = self._tower(p32, b["images"], b["lar"], b["c0"], b["h0"])
-    pi, v = self._policy_value(p32, h)
-    log_pi = torch.log(pi.clamp(1e-20, 1.0))
-    entropy = -(pi * log_pi).sum(-1)
     mask = b["mask"].to(torch.float32)
-    parts["policy"] = -((((log_pi * b["a"]).sum(-1)) * b["adv"] + entropy * self._entropy_beta) * mask).sum()
-    parts["value"] = 0.25 * (((b["R"] - v) ** 2) * mask).sum()
-    parts["entropy"] = (entropy * mask).sum().detach()
+    if self.fused_heads and self._action_size <= 7:
+      t_, n_ = h.shape[:2]
+      pol, val, ent = A3CHeadLossFn.apply(
+          h.reshape(t_ * n_, 256), p32["W_base_fc_p"], p32["b_base_fc_p"], p32["W_base_fc_v"], p32["b_base_fc_v"],
+          b["a"].reshape(t_ * n_, -1).argmax(-1).to(torch.int32), b["adv"].reshape(-1).contiguous(),
+          b["R"].reshape(-1).contiguous(), mask.reshape(-1).contiguous(), self._entropy_beta, 0.25)
+      parts["policy"], parts["value"], parts["entropy"] = pol, val, ent.detach()
+    else:
+      pi, v = self._policy_value(p32, h)
+      log_pi = torch.log(pi.clamp(1e-20, 1.0))
+      entropy = -(pi * log_pi).sum(-1)
+      parts["policy"] = -((((log_pi * b["a"]).sum(-1)) * b["adv"] + entropy * self._entropy_beta) * mask).sum()
+      parts["value"] = 0.25 * (((b["R"] - v) ** 2) * mask).sum()
+      parts["entropy"] = (entropy * mask).sum().detach()
     total = parts["policy"] + parts["value"]
     if self._use_pixel_change and "pc" in feed:
       f = feed["pc"]
@@ -367,7 +382,13 @@ class UnrealModel(object):
       f = feed["vr"]
       n = f["images"].shape[1]
       (h, _, _), _ = self._tower(p32, f["images"], f["lar"], *self._zeros_state(n))
-      parts["vr"] = 0.5 * (((f["R"] - self._policy_value(p32, h)[1]) ** 2) * f["mask"].float()).sum()
+      if self.fused_heads:
+        l_, n_ = h.shape[:2]
+        _, parts["vr"], _ = A3CHeadLossFn.apply(
+            h.reshape(l_ * n_, 256), p32["W_base_fc_p"], p32["b_base_fc_p"], p32["W_base_fc_v"], p32["b_base_fc_v"],
+            None, None, f["R"].reshape(-1).contiguous(), f["mask"].float().reshape(-1).contiguous(), 0.0, 0.5)
+      else:
+        parts["vr"] = 0.5 * (((f["R"] - self._policy_value(p32, h)[1]) ** 2) * f["mask"].float()).sum()
       total = total + parts["vr"]
     if self._use_reward_prediction and "rp" in feed:
       f = feed["rp"]
