@@ -338,3 +338,37 @@ def test_frame_trainer_checkpoint_restores_the_exact_trajectory(tmp_path):
     for k in ("act", "si", "pc_start", "pc_img", "rp_start"):
       assert torch.equal(x[k], y[k]), k
     assert abs(x["total"] - y["total"]) <= 1e-3 * max(1.0, abs(x["total"]))
+
+
+def test_new_entry_points_reject_bad_arguments():
+  """The C ABI returns UNREAL_EINVAL with a message (never crashes) for null / misaligned / out-of-range arguments of
+  the framed-ring and render-fused entry points."""
+  from unreal_b200 import _lib, kernels as K
+  dev = torch.device(DEV)
+  ring = K.ReplayRing(2, 8, dev)
+  payload = torch.zeros(2, 8, 4, dtype=torch.float32, device=dev)
+  start = torch.zeros(2, dtype=torch.int32, device=dev)
+  with pytest.raises(_lib.UnrealError, match="seq_len"):
+    ring.gather(payload, start, None, 9)                              # longer than the ring
+  with pytest.raises(_lib.UnrealError):
+    ring.gather(torch.zeros(3, 8, 4, device=dev), start, None, 2)     # payload of another ring shape
+  sp = _lib.stream_ptr()
+  assert _lib.lib.unreal_replay_gather(ring._h, None, 16, start.data_ptr(), None, 2, 1, payload.data_ptr(), sp) != 0
+  assert "null" in _lib.last_error()
+  assert _lib.lib.unreal_ring_store(payload.data_ptr(), payload.data_ptr(), start.data_ptr(), 2, 8, 6, sp) != 0
+  assert "multiple of 4" in _lib.last_error()
+  assert _lib.lib.unreal_frame_pack(None, None, None, None, None, None, None, 4, sp) != 0
+  pos = torch.zeros(5, 2, dtype=torch.int32, device=dev)
+  w = torch.zeros(4, 6, 16, 8, dtype=torch.bfloat16, device=dev)
+  out = torch.zeros(4, 20, 20, 16, dtype=torch.bfloat16, device=dev)
+  assert _lib.lib.unreal_conv1_fwd_maze(pos.data_ptr() + 4, w.data_ptr(), None, out.data_ptr(), 4, sp) != 0   # pos not 8-byte aligned
+  assert "align" in _lib.last_error()
+  assert _lib.lib.unreal_conv1_fwd_maze(pos.data_ptr(), w.data_ptr(), None, out.data_ptr(), 0, sp) != 0
+  with pytest.raises(_lib.UnrealError, match="21-pixel"):
+    K.conv1_wgrad_maze(pos, torch.zeros(2, 5 * 400, 8, dtype=torch.bfloat16, device=dev))
+  h = torch.zeros(4, 256, device=dev)
+  assert _lib.lib.unreal_a3c_head_loss(h.data_ptr(), None, None, None, None, None, None, None, None, 4, 9, 0.0, 0.25,
+                                       None, None, None, None, None, sp) != 0
+  assert "action count" in _lib.last_error()
+  torch.cuda.synchronize()
+  ring.close()
