@@ -186,6 +186,20 @@ int unreal_ring_store(void* payload, const void* src, const int32_t* slot, int n
 int unreal_replay_gather(unreal_replay_t* r, const void* payload, long long item_bytes, const int32_t* start,
                          const int32_t* len /*nullable*/, int seq_len, int time_major, void* out, void* stream);
 
+/* ---- rollout bookkeeping (Trainer._process_base, trainer.py:228-296), fused ------------------------------------
+ * unreal_rollout_lar: ExperienceFrame.concat_action_and_reward (experience.py:34-46) for every env:
+ *   lar [N, A+1+G] f32 = one-hot(last_action, A) ++ [last_reward] ++ objective [N,G] (G = 0: objective NULL).
+ * unreal_rollout_post: what follows env.process() in the rollout loop (:265-296), terminal handling as masked
+ *   arithmetic so the window never returns to the host: term_now = terminal & active; last_rec = frame_rec where
+ *   active; episode_reward += reward; stats [2] f64 += (episodes finished, sum of their scores); for finished envs
+ *   ended = 1, active = 0, episode_reward = 0 and their LSTM state rows (lstm_c / lstm_h [N,256] f32, both nullable)
+ *   are zeroed (local_network.reset_state :293).  active / ended [N] u8, last_rec [N] u64 in / out. */
+int unreal_rollout_lar(const int32_t* last_action, const float* last_reward, const float* objective, int n, int a, int g,
+                       float* lar, void* stream);
+int unreal_rollout_post(const float* reward, const uint8_t* terminal, const uint64_t* frame_rec, int n, uint8_t* active,
+                        uint8_t* ended, uint64_t* last_rec, float* episode_reward, float* lstm_c, float* lstm_h,
+                        double* stats, void* stream);
+
 /* ---- K6: shared RMSProp with global-norm clip, train/rmsprop_applier.py ---------------
  * _apply_gradients (:109-132): g <- grad * clip / max(||grad||, clip)  (tf.clip_by_global_norm :121)
  * _apply_dense (:83-93) = TF ApplyRMSProp:  ms += (g*g - ms)*(1-decay);

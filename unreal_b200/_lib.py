@@ -65,6 +65,8 @@ SIGNATURES = {
     "unreal_replay_add_slots": (c_int, [c_void_p, P, P, P]),
     "unreal_ring_store": (c_int, [P, P, P, c_int, c_int, c_int64, P]),
     "unreal_replay_gather": (c_int, [c_void_p, P, c_int64, P, P, c_int, c_int, P, P]),
+    "unreal_rollout_lar": (c_int, [P, P, P, c_int, c_int, c_int, P, P]),
+    "unreal_rollout_post": (c_int, [P, P, P, c_int, P, P, P, P, P, P, P, P]),
     "unreal_grad_sumsq": (c_int, [P, c_int64, P, P]),
     "unreal_rmsprop_update": (c_int, [P, P, P, P, c_int64, P, c_float, c_float, c_float, c_float, c_float,
                                       c_float, P, P]),

@@ -417,7 +417,9 @@ static int launch_render(const StepArgs& a, int obs_dtype, cudaStream_t st) {
   // defaults = fastest measured on B200 (profiles/microbench_r1.md): f32 -> CTA per env with
   // 256 threads (99% of measured HBM peak), u8 -> warp per env.
   int variant = get_tunable("maze_render_variant", -1);
-  if (variant < 0) variant = (obs_dtype == UNREAL_U8 && a.obs != nullptr) ? 2 : 0;
+  // no frame to write (cell observations / K1 as a pure stepper): one WARP per env -- a 256-thread CTA per env costs
+  // 33 us per step at 8192 envs for 13 MB of pixel-change maps
+  if (variant < 0) variant = (a.obs == nullptr || obs_dtype == UNREAL_U8) ? 2 : 0;
   if (a.obs == nullptr && variant == 1) variant = 0;  // nothing to stage through shared memory
   if (variant == 2) {
     const int warps = get_tunable("maze_warps_per_cta", 4);

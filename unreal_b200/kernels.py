@@ -693,3 +693,23 @@ def a3c_head_bwd(h, wp, wv, dz, dv, go2):
        ptr(dz, torch.float32, "dz"), ptr(dv, torch.float32, "dv"), ptr(go2, torch.float32, "go2"), m, a, ptr(dh), ptr(dwp),
        ptr(dbp), ptr(dwv), ptr(dbv), stream_ptr())
   return dh, dwp, dbp, dwv, dbv
+
+
+def rollout_lar(last_action, last_reward, num_actions, objective=None, out=None):
+  """one-hot(last_action) ++ [last_reward] (++ objective) for every env -> [N, A+1+G] f32."""
+  n = last_action.shape[0]
+  g = 0 if objective is None else objective.shape[1]
+  if out is None:
+    out = torch.empty(n, num_actions + 1 + g, dtype=torch.float32, device=last_action.device)
+  call("unreal_rollout_lar", ptr(last_action, torch.int32, "last_action"), ptr(last_reward, torch.float32, "last_reward"),
+       ptr(objective, torch.float32, "objective"), n, int(num_actions), g, ptr(out, torch.float32, "lar"), stream_ptr())
+  return out
+
+
+def rollout_post(reward, terminal, frame_rec, active, ended, last_rec, episode_reward, lstm_c, lstm_h, stats):
+  """The bookkeeping after one env step of the rollout window, in place (see include/unreal_b200.h)."""
+  call("unreal_rollout_post", ptr(reward, torch.float32, "reward"), ptr(terminal, torch.uint8, "terminal"),
+       ptr(frame_rec, torch.int64, "frame_rec"), reward.shape[0], ptr(active, torch.uint8, "active"),
+       ptr(ended, torch.uint8, "ended"), ptr(last_rec, torch.int64, "last_rec"),
+       ptr(episode_reward, torch.float32, "episode_reward"), ptr(lstm_c, torch.float32, "lstm_c"),
+       ptr(lstm_h, torch.float32, "lstm_h"), ptr(stats, torch.float64, "stats"), stream_ptr())

@@ -230,29 +230,27 @@ class Trainer(object):
     self._pos[0].copy_(env.state.pos)
     self._active.zero_(); self._rew.zero_(); self._term.zero_()
     last_rec = torch.zeros(n, dtype=torch.int64, device=d)
+    # networks with the persistent [N,256] LSTM state buffers (UnrealModel) get them zeroed by the bookkeeping kernel
+    lstm_c, lstm_h = getattr(net, "_lstm_c", None), getattr(net, "_lstm_h", None)
+    fused_state = isinstance(lstm_c, torch.Tensor) and isinstance(lstm_h, torch.Tensor)
     for t in range(T):
-      lar = self._last_action_reward(env.last_action, env.last_reward)
+      lar = K.rollout_lar(env.last_action, env.last_reward, self.action_size, out=self._lar[t])   # straight into the feed
       pi, v, _ = net.run_base_policy_and_value(sess, {'image': self._obs[t]}, lar, active)
       action = self.choose_action(pi, active)
-      self._lar[t].copy_(lar); self._val[t].copy_(v); self._act[t].copy_(action); self._active[t].copy_(active)
+      self._val[t].copy_(v); self._act[t].copy_(action); self._active[t].copy_(active)
       # the new frame lands in obs[t+1]; envs whose rollout already ended are skipped by the kernel
       env.process(action, active=active, out_obs=self._obs[t + 1], out_pc=self._pc[t],
                   out_reward=self._rew[t], out_terminal=self._term[t])
       self._pos[t + 1].copy_(env.state.pos)
       self.experience.add_frames(env.frame_rec)
-      last_rec = torch.where(active.bool(), env.frame_rec, last_rec)
-      self.episode_reward += self._rew[t]
-      # no host round trips inside the rollout: terminal handling is masked arithmetic, so the
-      # CPU keeps enqueueing ahead of the GPU (an all-terminated batch just idles through the steps)
-      term_now = self._term[t] & active
-      ended |= term_now
-      # episode statistics (the reference prints the score of every finished episode, :283-291)
-      tn = term_now.to(torch.float32)
-      self.episode_stats[0] += tn.sum()                              # finished episodes
-      self.episode_stats[1] += (self.episode_reward * tn).sum()      # sum of their scores
-      net.reset_state(term_now)                # :293
-      self.episode_reward.mul_(1 - term_now.to(torch.float32))
-      active = active & (1 - term_now)
+      if not fused_state:
+        net.reset_state(self._term[t] & active)      # :293
+      # everything else of :265-296 in one launch, terminal handling as masked arithmetic (no host round trip, the
+      # CPU keeps enqueueing ahead of the GPU; an all-terminated batch just idles through the steps): last record,
+      # episode reward / statistics (the reference prints every finished episode's score, :283-291), `ended`,
+      # LSTM state reset, `active`
+      K.rollout_post(self._rew[t], self._term[t], env.frame_rec, active, ended, last_rec, self.episode_reward,
+                     lstm_c if fused_state else None, lstm_h if fused_state else None, self.episode_stats)
     lengths = self._active.sum(0).to(torch.int32)
     self._pending_local_t = lengths.max()      # read back once, after the update has been enqueued
     # bootstrap: V(new_state) with frame.get_action_reward for envs that did not end (:298-300)
