@@ -255,6 +255,11 @@ int unreal_lstm_cell_fwd(float* gates, const float* c_prev, float* c_out, float*
  * pre-activations once (no separate x-part GEMM, no read-modify-write accumulation). */
 int unreal_lstm_cell_fwd_ld(float* gates, const float* c_prev, float* c_out, float* h_out, void* h16_out, int h16_ld,
                             int n, void* stream);
+/* acting step (run_base_policy_and_value, model.py:630-660): the cell applied in place to the persistent state
+ * c_state / h_state [N,256] f32 of the envs with active[e] != 0 (active NULL: all); h_out [N,256] (nullable) = the
+ * state's h afterwards (unchanged for inactive envs). */
+int unreal_lstm_cell_act(const float* gates, float* c_state, float* h_state, float* h_out, const uint8_t* active, int n,
+                         void* stream);
 /* backward of the above: dh [N,256] total gradient wrt h_t; dc [N,256] in: wrt c_t, out: wrt
  * c_{t-1}; dgates bf16 [N,1024] wrt the pre-activations. */
 int unreal_lstm_cell_bwd(const float* gates_act, const float* c_prev, const float* c, const float* dh, float* dc,

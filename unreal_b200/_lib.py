@@ -78,6 +78,7 @@ SIGNATURES = {
     "unreal_col2im": (c_int, [P, c_int, P, c_int, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "unreal_lstm_cell_fwd": (c_int, [P, P, P, P, P, c_int, P]),
     "unreal_lstm_cell_fwd_ld": (c_int, [P, P, P, P, P, c_int, c_int, P]),
+    "unreal_lstm_cell_act": (c_int, [P, P, P, P, P, c_int, P]),
     "unreal_lstm_cell_bwd": (c_int, [P, P, P, P, P, P, c_int, P]),
     "unreal_s2d_frames": (c_int, [P, c_int, P, c_int, P]),
     "unreal_conv_fwd": (c_int, [P, c_int, P, P, P, c_int, P]),

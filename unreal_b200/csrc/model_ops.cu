@@ -173,6 +173,30 @@ __global__ void __launch_bounds__(256) lstm_cell_fwd_kernel(float* __restrict__ 
   h16_out[(size_t)e * h16_ld + u] = __float2bfloat16_rn(h);     // h16_ld > 256: straight into the next step's [x, h] GEMM operand
 }
 
+// Acting step: the cell applied IN PLACE to the persistent state of the envs with active[e] != 0 (the others keep
+// their state and report their old h): replaces cell + two masked selects + two copies per env step.
+__global__ void __launch_bounds__(256) lstm_cell_act_kernel(const float* __restrict__ gates, float* __restrict__ c_state,
+                                                            float* __restrict__ h_state, float* __restrict__ h_out,
+                                                            const uint8_t* __restrict__ active, int n) {
+  const int id = blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= n * 256) return;
+  const int e = id >> 8, u = id & 255;
+  if (active != nullptr && active[e] == 0) {
+    if (h_out != nullptr) h_out[id] = h_state[id];
+    return;
+  }
+  const float* gr = gates + (size_t)e * 1024;
+  const float i = sigmoidf_(gr[u]);
+  const float j = tanhf(gr[256 + u]);
+  const float f = sigmoidf_(gr[512 + u] + 1.0f);   // forget_bias = 1.0
+  const float o = sigmoidf_(gr[768 + u]);
+  const float c = c_state[id] * f + i * j;
+  const float h = tanhf(c) * o;
+  c_state[id] = c;
+  h_state[id] = h;
+  if (h_out != nullptr) h_out[id] = h;
+}
+
 // dh: total gradient wrt h_t (heads + recurrent); dc: in = gradient wrt c_t from step t+1,
 // out = gradient wrt c_{t-1}.  dgates are the gradients wrt the PRE-activations, as bf16 (the
 // operand dtype of the dgrad / wgrad GEMMs that consume them).
@@ -659,6 +683,14 @@ extern "C" int unreal_lstm_cell_fwd_ld(float* gates, const float* c_prev, float*
   lstm_cell_fwd_kernel<<<(n * 256 + 255) / 256, 256, 0, as_stream(stream)>>>(
       gates, c_prev, c_out, h_out, reinterpret_cast<__nv_bfloat16*>(h16_out), n, h16_ld);
   UNREAL_LAUNCH_CHECK("lstm_cell_fwd_kernel");
+  return UNREAL_OK;
+}
+
+extern "C" int unreal_lstm_cell_act(const float* gates, float* c_state, float* h_state, float* h_out, const uint8_t* active,
+                                    int n, void* stream) {
+  UNREAL_REQUIRE(gates && c_state && h_state && n > 0, "unreal_lstm_cell_act: null buffer or n <= 0");
+  lstm_cell_act_kernel<<<(n * 256 + 255) / 256, 256, 0, as_stream(stream)>>>(gates, c_state, h_state, h_out, active, n);
+  UNREAL_LAUNCH_CHECK("lstm_cell_act_kernel");
   return UNREAL_OK;
 }
 

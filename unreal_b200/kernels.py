@@ -713,3 +713,12 @@ def rollout_post(reward, terminal, frame_rec, active, ended, last_rec, episode_r
        ptr(ended, torch.uint8, "ended"), ptr(last_rec, torch.int64, "last_rec"),
        ptr(episode_reward, torch.float32, "episode_reward"), ptr(lstm_c, torch.float32, "lstm_c"),
        ptr(lstm_h, torch.float32, "lstm_h"), ptr(stats, torch.float64, "stats"), stream_ptr())
+
+
+def lstm_cell_act(gates, c_state, h_state, h_out=None, active=None):
+  """Acting step of the cell, in place on the persistent state of the active envs; h_out receives the state's h."""
+  n = gates.shape[0]
+  call("unreal_lstm_cell_act", ptr(gates, torch.float32, "gates"), ptr(c_state, torch.float32, "c_state"),
+       ptr(h_state, torch.float32, "h_state"), ptr(h_out, torch.float32, "h_out"), ptr(active, torch.uint8, "active"), n,
+       stream_ptr())
+  return h_out

@@ -80,6 +80,7 @@ class UnrealModel(object):
     self.fused_conv = True    # False: convolutions as explicit im2col + GEMM (A/B switch for benchmarks)
     self.fused_encoder = True # False: conv1 / conv2 as separate autograd nodes (dense gradient + relu_grad pass between them)
     self.fused_heads = True   # False: policy / value heads and their losses as torch ops
+    self._act_xh = {}         # acting-step [x, h] GEMM operands by batch size (persistent: padding columns stay zero)
     self._build_variables(seed)
     self.reset_state()
 
@@ -286,11 +287,42 @@ class UnrealModel(object):
       p32 = self._views(self.flat)
       img = self._images(s_t)
       n = img.shape[1]
+      if self.fused_conv and self.fused_encoder:
+        gates = self._step_gates(p32, img[0], self._lar(last_action_reward, n)[0], state[1])
+        c1 = torch.empty(n, 256, device=self._device); h1 = torch.empty(n, 256, device=self._device)
+        h16 = torch.empty(n, 256, device=self._device, dtype=torch.bfloat16)
+        K.lstm_cell_fwd(gates, state[0].contiguous(), c1, h1, h16)
+        return p32, h1, (c1, h1)
       (h, c1, h1), _ = self._tower(p32, img, self._lar(last_action_reward, n), state[0], state[1])
       return p32, h[0], (c1, h1)
 
+  def _step_gates(self, p32, images, lar, h_prev):
+    """One acting step up to the LSTM gate pre-activations, without the training path's glue: fc1 writes straight
+    into the [x, h] operand of the step GEMM (`_act_xh`, persistent, padding columns stay zero), the last action /
+    reward vector and h are cast into their columns, one GEMM gives the gates [N,1024] f32."""
+    n = images.shape[0]
+    h2 = EncoderFn.apply(images, p32["W_base_conv1"], p32["b_base_conv1"], p32["W_base_conv2"], p32["b_base_conv2"],
+                         self.taps1, self.taps2)
+    xh = self._act_xh.get(n)
+    if xh is None:
+      xh = self._act_xh[n] = torch.zeros(n, self.kx + 256, dtype=torch.bfloat16, device=self._device)
+    K.gemm_bf16(h2.view(n, 2592), self.v16["W_base_fc1"], out=xh[:, :256], b_mn_major=True, bias=p32["b_base_fc1"], relu=True)
+    xh[:, 256:self.lstm_in].copy_(lar)
+    xh[:, self.kx:].copy_(h_prev)
+    return K.gemm_bf16(xh, self.wcat16, b_mn_major=True, bias=p32["lstm_bias"])
+
   def run_base_policy_and_value(self, sess, s_t, last_action_reward, active=None, mode=""):
     """model.py:630-660: one acting step; advances the LSTM state of the active envs."""
+    if self.fused_conv and self.fused_encoder:
+      with torch.no_grad():
+        p32 = self._views(self.flat)
+        img = self._images(s_t)
+        n = img.shape[1]
+        gates = self._step_gates(p32, img[0], self._lar(last_action_reward, n)[0], self._lstm_h)
+        h = torch.empty(n, 256, device=self._device)
+        K.lstm_cell_act(gates, self._lstm_c, self._lstm_h, h, active)      # in place on the state of the active envs
+        pi, v = self._policy_value(p32, h)
+      return pi, v, None
     p32, h, new_state = self._step(s_t, last_action_reward, self.base_lstm_state_out)
     with torch.no_grad():
       pi, v = self._policy_value(p32, h)
