@@ -264,6 +264,10 @@ int unreal_lstm_cell_act(const float* gates, float* c_state, float* h_state, flo
  * c_{t-1}; dgates bf16 [N,1024] wrt the pre-activations. */
 int unreal_lstm_cell_bwd(const float* gates_act, const float* c_prev, const float* c, const float* dh, float* dc,
                          void* dgates_bf16, int n, void* stream);
+/* same with the gradient w.r.t. h_t given as two addends, dh + dh_rec (heads' gradient and the recurrent one from
+ * step t+1; dh_rec nullable): saves the element-wise add between the steps of the backward unroll. */
+int unreal_lstm_cell_bwd2(const float* gates_act, const float* c_prev, const float* c, const float* dh,
+                          const float* dh_rec, float* dc, void* dgates_bf16, int n, void* stream);
 
 /* Fused convolutions of the encoder (model.py:281-289) as implicit GEMMs whose im2col is done by
  * the TMA engine (multi-dimensional boxes over a space-to-depth view; no patch matrix in memory).

@@ -80,6 +80,7 @@ SIGNATURES = {
     "unreal_lstm_cell_fwd_ld": (c_int, [P, P, P, P, P, c_int, c_int, P]),
     "unreal_lstm_cell_act": (c_int, [P, P, P, P, P, c_int, P]),
     "unreal_lstm_cell_bwd": (c_int, [P, P, P, P, P, P, c_int, P]),
+    "unreal_lstm_cell_bwd2": (c_int, [P, P, P, P, P, P, P, c_int, P]),
     "unreal_s2d_frames": (c_int, [P, c_int, P, c_int, P]),
     "unreal_conv_fwd": (c_int, [P, c_int, P, P, P, c_int, P]),
     "unreal_relu_grad": (c_int, [P, c_int, P, P, P, c_int64, c_int, c_int, P]),

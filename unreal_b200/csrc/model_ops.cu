@@ -203,14 +203,15 @@ __global__ void __launch_bounds__(256) lstm_cell_act_kernel(const float* __restr
 __global__ void __launch_bounds__(256) lstm_cell_bwd_kernel(const float* __restrict__ gates_act,
                                                             const float* __restrict__ c_prev, const float* __restrict__ c,
                                                             const float* __restrict__ dh, float* __restrict__ dc,
-                                                            __nv_bfloat16* __restrict__ dgates, int n) {
+                                                            __nv_bfloat16* __restrict__ dgates, int n,
+                                                            const float* __restrict__ dh2) {
   const int id = blockIdx.x * blockDim.x + threadIdx.x;
   if (id >= n * 256) return;
   const int e = id >> 8, u = id & 255;
   const float* gr = gates_act + (size_t)e * 1024;
   const float i = gr[u], j = gr[256 + u], f = gr[512 + u], o = gr[768 + u];
   const float tc = tanhf(c[id]);
-  const float dhv = dh[id];
+  const float dhv = dh[id] + (dh2 ? dh2[id] : 0.f);     // heads' gradient (+ the recurrent one from step t+1)
   const float d_o = dhv * tc;
   const float dcv = dc[id] + dhv * o * (1.0f - tc * tc);
   __nv_bfloat16* dg = dgates + (size_t)e * 1024;
@@ -699,7 +700,17 @@ extern "C" int unreal_lstm_cell_bwd(const float* gates_act, const float* c_prev,
   UNREAL_REQUIRE(gates_act && c_prev && c && dh && dc && dgates_bf16 && n > 0,
                  "unreal_lstm_cell_bwd: null buffer or n <= 0");
   lstm_cell_bwd_kernel<<<(n * 256 + 255) / 256, 256, 0, as_stream(stream)>>>(
-      gates_act, c_prev, c, dh, dc, reinterpret_cast<__nv_bfloat16*>(dgates_bf16), n);
+      gates_act, c_prev, c, dh, dc, reinterpret_cast<__nv_bfloat16*>(dgates_bf16), n, nullptr);
+  UNREAL_LAUNCH_CHECK("lstm_cell_bwd_kernel");
+  return UNREAL_OK;
+}
+
+extern "C" int unreal_lstm_cell_bwd2(const float* gates_act, const float* c_prev, const float* c, const float* dh,
+                                     const float* dh_rec, float* dc, void* dgates_bf16, int n, void* stream) {
+  UNREAL_REQUIRE(gates_act && c_prev && c && dh && dc && dgates_bf16 && n > 0,
+                 "unreal_lstm_cell_bwd2: null buffer or n <= 0");
+  lstm_cell_bwd_kernel<<<(n * 256 + 255) / 256, 256, 0, as_stream(stream)>>>(
+      gates_act, c_prev, c, dh, dc, reinterpret_cast<__nv_bfloat16*>(dgates_bf16), n, dh_rec);
   UNREAL_LAUNCH_CHECK("lstm_cell_bwd_kernel");
   return UNREAL_OK;
 }

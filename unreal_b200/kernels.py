@@ -456,14 +456,14 @@ def lstm_cell_fwd(gates, c_prev, c_out, h_out, h16_out):
        n, stream_ptr())
 
 
-def lstm_cell_bwd(gates_act, c_prev, c, dh, dc, dgates16):
+def lstm_cell_bwd(gates_act, c_prev, c, dh, dc, dgates16, dh_rec=None):
+  """dh (+ dh_rec): gradient w.r.t. h_t; dc in / out; dgates16 [n,1024] bf16 out."""
   n = gates_act.shape[0]
-  call("unreal_lstm_cell_bwd", ptr(gates_act, torch.float32), ptr(c_prev, torch.float32), ptr(c, torch.float32),
-       ptr(dh, torch.float32, "dh"), ptr(dc, torch.float32, "dc"), ptr(dgates16, torch.bfloat16, "dgates"), n,
-       stream_ptr())
+  call("unreal_lstm_cell_bwd2", ptr(gates_act, torch.float32, "gates_act"), ptr(c_prev, torch.float32, "c_prev"),
+       ptr(c, torch.float32, "c"), ptr(dh, torch.float32, "dh"), ptr(dh_rec, torch.float32, "dh_rec"),
+       ptr(dc, torch.float32, "dc"), ptr(dgates16, torch.bfloat16, "dgates16"), n, stream_ptr())
 
 
-# ---------------------------------------------------------------------------- K7: fused convolutions
 def s2d_frames(frames, out=None):
   """frames [S,84,84,3] f32 / u8 -> space-to-depth bf16, plane-major [S,6,441,8]:
   x''[s, q, Y*21+X, e] = frame[s, 4Y+dy, 4X+dx, c] with dy*12 + dx*3 + c = q*8 + e."""

@@ -154,8 +154,8 @@ class EncoderFn(torch.autograd.Function):
 class LstmFn(torch.autograd.Function):
   """dynamic_rnn over BasicLSTMCell(256) (model.py:110, :343-351), N envs in lock step.
 
-  xin16 [T,N,KX] bf16: columns [0, lstm_in) = concat(fc1 output, last_action_reward), the rest
-  zero padding (KX is lstm_in rounded up to 8 for the TMA row pitch).  `wcat16` [KX+256, 1024] is the cell's
+  Step operand row [KX+256] bf16: columns [0, lstm_in) = concat(fc1 output, last_action_reward), zero padding up
+  to KX (lstm_in rounded up to 8 for the TMA row pitch), then h_{t-1}.  `wcat16` [KX+256, 1024] is the cell's
   kernel in that row layout (x rows, zero rows for the padding, h rows).  Each step is ONE GEMM over the
   concatenated operand [x_t, h_{t-1}] (K = KX + 256) whose epilogue adds the bias and writes the gate
   pre-activations once; the cell kernel writes h_t (bf16) straight into step t+1's operand columns.  (The
@@ -164,12 +164,16 @@ class LstmFn(torch.autograd.Function):
   """
 
   @staticmethod
-  def forward(ctx, xin16, wcat16, w32, b32, c0, h0, lstm_in):
-    t, n, kx = xin16.shape
+  def forward(ctx, fc16, lar, wcat16, w32, b32, c0, h0, lstm_in, kx):
+    """fc16 [T,N,256] bf16 (fc1 output), lar [T,N,lstm_in-256] f32: packed straight into the step operands."""
+    t, n = fc16.shape[:2]
     kc = kx + 256
-    dev = xin16.device
+    dev = fc16.device
     xh = torch.empty(t, n, kc, device=dev, dtype=torch.bfloat16)
-    xh[:, :, :kx].copy_(xin16)
+    xh[:, :, :256].copy_(fc16)
+    xh[:, :, 256:lstm_in].copy_(lar)
+    if kx > lstm_in:
+      xh[:, :, lstm_in:kx].zero_()
     xh[0, :, kx:].copy_(h0)
     gates = torch.empty(t, n, 1024, device=dev)
     c_all = torch.empty(t + 1, n, 256, device=dev)
@@ -194,20 +198,18 @@ class LstmFn(torch.autograd.Function):
     dc = torch.zeros(n, 256, device=dev) if dc_last is None else dc_last.clone().contiguous()
     dgates = torch.empty(t, n, 1024, device=dev, dtype=torch.bfloat16)
     wh = wcat16[kx:]                                     # [256, 1024]: K-major B for dh = dgates @ Wh^T
-    dh_rec = None if dh_last is None else dh_last
+    dh_rec = None if dh_last is None else dh_last.contiguous()
     for i in range(t - 1, -1, -1):
-      dh = dh_all[i] if dh_rec is None else dh_all[i] + dh_rec
-      K.lstm_cell_bwd(gates[i], c_all[i], c_all[i + 1], dh.contiguous(), dc, dgates[i])
+      K.lstm_cell_bwd(gates[i], c_all[i], c_all[i + 1], dh_all[i], dc, dgates[i], dh_rec)    # dh = dh_all[i] + dh_rec
       if i > 0:
         dh_rec = K.gemm_bf16(dgates[i], wh)
     dg2 = dgates.view(t * n, 1024)
     dwcat = _wgrad(xh.view(t * n, kc), dg2)              # one wgrad over [x, h]: rows of the x part, padding, h part
     dw = torch.cat((dwcat[:lstm_in], dwcat[kx:]), dim=0)
     _, db = K.relu_grad(dg2, None, want_out=False)
-    dxin = torch.zeros(t, n, kx, device=dev, dtype=torch.bfloat16)
     # only the 256 fc1 columns carry a gradient (last_action_reward is an input)
-    K.gemm_bf16(dg2, wcat16[:256], out=dxin.view(t * n, kx)[:, :256])
-    return dxin, None, dw, db, None, None, None
+    dfc = K.gemm_bf16(dg2, wcat16[:256], out_dtype=torch.bfloat16).view(t, n, 256)
+    return dfc, None, None, dw, db, None, None, None, None
 
 
 class Deconv8Fn(torch.autograd.Function):

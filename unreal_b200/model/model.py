@@ -194,21 +194,18 @@ class UnrealModel(object):
                       self.taps2)
     return h2
 
-  def _lstm_input(self, p32, h2, lar, t, n):
-    """fc1 + concat with last_action_reward (model.py:332-343) -> bf16 [T,N,KX]."""
+  def _lstm_input(self, p32, h2, t, n):
+    """fc1 (model.py:332-340) -> bf16 [T,N,256]; LstmFn packs it with last_action_reward into the step operands (:343)."""
     fc = LinearFn.apply(h2.view(t * n, 2592), self.v16["W_base_fc1"], p32["W_base_fc1"], p32["b_base_fc1"], True, True)
-    pad = self.kx - self.lstm_in
-    parts = [fc.view(t, n, 256), lar.to(torch.bfloat16)]
-    if pad:
-      parts.append(torch.zeros(t, n, pad, dtype=torch.bfloat16, device=fc.device))
-    return torch.cat(parts, dim=2)
+    return fc.view(t, n, 256)
 
   def _tower(self, p32, images, lar, c0, h0):
     """encoder + fc1 + LSTM unroll.  images [T,N,84,84,3], lar [T,N,A+1+G] -> h [T,N,256] f32."""
     t, n = images.shape[:2]
     h2 = self._encoder(p32, images.reshape(t * n, *images.shape[2:]))
-    xin = self._lstm_input(p32, h2, lar, t, n)
-    return LstmFn.apply(xin, self.wcat16, p32["lstm_kernel"], p32["lstm_bias"], c0, h0, self.lstm_in), h2
+    fc = self._lstm_input(p32, h2, t, n)
+    return LstmFn.apply(fc, lar.to(torch.float32), self.wcat16, p32["lstm_kernel"], p32["lstm_bias"], c0, h0, self.lstm_in,
+                        self.kx), h2
 
   def _policy_value(self, p32, h):
     """model.py:358-377 (tiny [.,256]x[256,A+1] products, fp32).  Without autograd (acting, bootstraps): one fused
