@@ -372,3 +372,49 @@ def test_new_entry_points_reject_bad_arguments():
   assert "action count" in _lib.last_error()
   torch.cuda.synchronize()
   ring.close()
+
+
+def test_registered_host_simulators_drive_the_trainer():
+  """INTEGRATION.md B2 end to end: reference-style host env objects registered as an env type, Trainer(...) builds the
+  framed trainer over them and produces the same feeds as one oracle worker per env."""
+  from unreal_b200.environment import frame_environment as FE
+  from unreal_b200.environment.environment import Environment
+  from unreal_b200.train.trainer import Trainer
+  N, H, T = 3, 40, 20
+  table = O.make_frame_table(12)
+  sims = [O.TableFrameEnvOracle(e, table) for e in range(N)]
+  for sim in sims:
+    sim.counter = 0          # the adapter's constructor resets once, like a worker's env constructor does
+  Environment.register('hostsim', lambda name, args, tt, ti: FE.BatchedFrameEnvironment(
+      FE.HostEnvProducer(sims, args['device'], 3), args['device']), action_size=3)
+  try:
+    Environment.action_size = -1
+    seeds = [7 + e for e in range(N)]
+    net_seeds = [90 + e for e in range(N)]
+    net = _EndAwareNet(net_seeds, DEV, action_size=3)
+    tr = Trainer(1, net, 7e-4, None, None, 'hostsim', '', True, True, True, True, 0.05, 1e-3, 20, T, 0.99, 0.9, H, 10 ** 7,
+                 DEV, {'segnet_mode': 0}, (84, 84), True, 0, np.random.RandomState(0), 50.0, 0.0, 0.0, num_envs=N, seeds=seeds)
+    net.attach(tr)
+    tr.prepare()
+    workers = [O.RolloutOracle(H, np.random.RandomState(s), FakeNet(ns, 3), n_step_TD=T, action_size=3,
+                               env=O.TableFrameEnvOracle(e, table)) for e, (s, ns) in enumerate(zip(seeds, net_seeds))]
+    while not tr.experience.is_full():
+      tr.process(None, 0)
+      for w in workers:
+        w.fill_step()
+    for it in range(4):
+      tr.process(None, 0)
+      f = tr.last_feed
+      for e, w in enumerate(workers):
+        b = w.process_base(); p = w.process_pc(); w.process_vr(); r = w.process_rp()
+        L = len(b['states'])
+        assert int(f['base']['length'][e]) == L
+        assert np.array_equal(f['base']['si'][:L, e].cpu().numpy(), np.stack([_u8(s['image']) for s in b['states']]))
+        _close(f['base']['R'][:L, e].cpu().numpy(), np.array(b['R'], np.float64))
+        Lp = len(p['states'])
+        assert int(f['pc']['length'][e]) == Lp
+        _close(f['pc']['R'][e, :Lp].cpu().numpy(), np.stack(p['R']).astype(np.float64))
+        assert list(f['rp']['c'][e].cpu().numpy()) == r['c']
+  finally:
+    Environment._registry.pop('hostsim', None)
+    Environment.action_size = -1

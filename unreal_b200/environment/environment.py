@@ -17,6 +17,17 @@ from .. import kernels as K
 class Environment(object):
   # cached action size (environment.py:13, :46-47)
   action_size = -1
+  # env types added by the integrator: env_type -> (factory, action_size, objective_size)
+  _registry = {}
+
+  @staticmethod
+  def register(env_type, factory, action_size, objective_size=0):
+    """Make `create_environment(env_type, ...)` build `factory(env_name, env_args, termination_time, thread_index)`
+    -- typically a BatchedFrameEnvironment over host simulators (lab / gym / indoor) -- and let
+    get_action_size / get_objective_size answer for it, the way environment.py:30-72 dispatches on env_type."""
+    if env_type in ('maze', 'synthetic'):
+      raise _lib.UnrealError("env_type %r is built in" % (env_type,))
+    Environment._registry[env_type] = (factory, int(action_size), int(objective_size))
 
   @staticmethod
   def create_environment(env_type, env_name, termination_time=50.0, env_args=None, thread_index=0):
@@ -31,9 +42,11 @@ class Environment(object):
     if env_type == 'synthetic':
       from . import synthetic_environment
       return synthetic_environment.SyntheticIndoorEnvironment(env_name, env_args, termination_time, thread_index)
+    if env_type in Environment._registry:
+      return Environment._registry[env_type][0](env_name, env_args, termination_time, thread_index)
     raise _lib.UnrealError(
         "env_type %r needs an external simulator (deepmind_lab / gym / MINOS) that is outside the "
-        "B200 hot path; use 'maze' or 'synthetic'" % (env_type,))
+        "B200 hot path; use 'maze' or 'synthetic', or Environment.register() a frame producer for it" % (env_type,))
 
   @staticmethod
   def get_action_size(env_type, env_name):
@@ -46,6 +59,8 @@ class Environment(object):
     elif env_type == 'synthetic':
       from . import synthetic_environment
       Environment.action_size = synthetic_environment.SyntheticIndoorEnvironment.get_action_size(env_name)
+    elif env_type in Environment._registry:
+      Environment.action_size = Environment._registry[env_type][1]
     else:
       raise _lib.UnrealError("env_type %r is outside the B200 hot path" % (env_type,))
     return Environment.action_size
@@ -56,6 +71,8 @@ class Environment(object):
     if env_type == 'synthetic':
       from . import synthetic_environment
       return synthetic_environment.SyntheticIndoorEnvironment.get_objective_size(env_name)
+    if env_type in Environment._registry:
+      return Environment._registry[env_type][2]
     return 0
 
   def __init__(self):
