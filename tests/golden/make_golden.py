@@ -295,6 +295,24 @@ def gen_trainer_frames(name, H, n_iter, n_step_TD, seed, net_seed, table_seed):
         "episodes ended", int(sum(1 for l in base_len if l < n_step_TD)))
 
 
+# ---------------------------------------------------------------------------
+# E. Environment._calc_pixel_change on generic frames (the lab / gym / indoor call, environment.py:88-99):
+#    float32 `uint8 / 255` frames of several sizes and channel counts
+# ---------------------------------------------------------------------------
+def gen_pixel_change():
+  env = Environment()
+  rs = np.random.RandomState(77)
+  out = {}
+  for i, (h, w, c) in enumerate([(84, 84, 3), (100, 120, 3), (44, 44, 1), (84, 84, 4), (36, 52, 3)]):
+    a = (rs.randint(0, 256, size=(h, w, c)).astype(np.float32) / 255.0).astype(np.float32)
+    b = (rs.randint(0, 256, size=(h, w, c)).astype(np.float32) / 255.0).astype(np.float32)
+    pc = env._calc_pixel_change(a, b)
+    out["a%d" % i] = (a * 255.0 + 0.5).astype(np.uint8); out["b%d" % i] = (b * 255.0 + 0.5).astype(np.uint8)
+    out["pc%d" % i] = pc
+    print("pixel change", (h, w, c), "->", pc.shape, pc.dtype)
+  np.savez_compressed(os.path.join(HERE, "pixel_change_golden.npz"), **out)
+
+
 PC_FULL = 400
 PC_PROBE = np.array([0, 19, 21, 63, 105, 147, 168, 189, 210, 231, 252, 294, 336, 378, 380, 399])
 
@@ -311,3 +329,4 @@ if __name__ == "__main__":
   gen_trainer("h2000", 2000, 300, 20, 0xA3C, 99)
   gen_trainer("h100", 100, 400, 20, 5, 17)
   gen_trainer_frames("frames_h120", 120, 200, 20, 21, 33, 6)
+  gen_pixel_change()

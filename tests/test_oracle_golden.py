@@ -217,3 +217,17 @@ def test_generic_frame_rollout_targets_match_reference(golden_dir):
     assert r['c'] == list(g["rp_c"][it])
   assert ended > 50, "the fixture covers rollouts that end in a terminal"
   assert (w.ring.top, w.local_t) == tuple(g["final_top"])
+
+
+def test_generic_pixel_change_matches_reference(golden_dir):
+  """Environment._calc_pixel_change (environment.py:88-99) of the REFERENCE on float32 `uint8 / 255` frames of
+  several sizes / channel counts, against the oracle's restatement: bit-equal float32 maps."""
+  g = _load(golden_dir, "pixel_change_golden.npz")
+  n = len([k for k in g if k.startswith("pc")])
+  assert n == 5
+  for i in range(n):
+    a = g["a%d" % i].astype(np.float32) / np.float32(255.0)
+    b = g["b%d" % i].astype(np.float32) / np.float32(255.0)
+    pc = O.pixel_change(a, b)
+    assert pc.dtype == g["pc%d" % i].dtype and pc.shape == g["pc%d" % i].shape
+    assert np.array_equal(pc, g["pc%d" % i]), i
