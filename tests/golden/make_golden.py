@@ -313,6 +313,22 @@ def gen_pixel_change():
   np.savez_compressed(os.path.join(HERE, "pixel_change_golden.npz"), **out)
 
 
+# ---------------------------------------------------------------------------
+# F. ExperienceFrame.concat_action_and_reward with an objective vector (experience.py:34-46; the indoor state)
+# ---------------------------------------------------------------------------
+def gen_lar():
+  rs = np.random.RandomState(3)
+  acts = rs.randint(0, 3, size=64); rews = (rs.randint(-2, 3, size=64) * 0.25).astype(np.float64)
+  objs = rs.rand(64, 2).astype(np.float32)
+  with_obj = np.stack([ExperienceFrame.concat_action_and_reward(int(a), 3, float(r), {'image': None, 'objective': o})
+                       for a, r, o in zip(acts, rews, objs)])
+  without = np.stack([ExperienceFrame.concat_action_and_reward(int(a), 3, float(r), {'image': None})
+                      for a, r in zip(acts, rews)])
+  np.savez_compressed(os.path.join(HERE, "lar_golden.npz"), action=acts, reward=rews, objective=objs, with_obj=with_obj,
+                      without=without)
+  print("lar", with_obj.shape, with_obj.dtype, without.shape)
+
+
 PC_FULL = 400
 PC_PROBE = np.array([0, 19, 21, 63, 105, 147, 168, 189, 210, 231, 252, 294, 336, 378, 380, 399])
 
@@ -330,3 +346,4 @@ if __name__ == "__main__":
   gen_trainer("h100", 100, 400, 20, 5, 17)
   gen_trainer_frames("frames_h120", 120, 200, 20, 21, 33, 6)
   gen_pixel_change()
+  gen_lar()

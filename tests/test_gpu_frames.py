@@ -418,3 +418,17 @@ def test_registered_host_simulators_drive_the_trainer():
   finally:
     Environment._registry.pop('hostsim', None)
     Environment.action_size = -1
+
+
+def test_rollout_lar_kernel_matches_reference_vectors(golden_dir):
+  """unreal_rollout_lar (one-hot(last_action) ++ [last_reward] ++ objective) against the REFERENCE's
+  ExperienceFrame.concat_action_and_reward outputs (tests/golden/lar_golden.npz)."""
+  import os
+  from unreal_b200 import kernels as K
+  with np.load(os.path.join(golden_dir, "lar_golden.npz")) as z:
+    g = {k: z[k] for k in z.files}
+  act = torch.from_numpy(g["action"].astype(np.int32)).to(DEV)
+  rew = torch.from_numpy(g["reward"].astype(np.float32)).to(DEV)
+  obj = torch.from_numpy(g["objective"]).to(DEV)
+  assert np.array_equal(K.rollout_lar(act, rew, 3, objective=obj).cpu().numpy(), g["with_obj"].astype(np.float32))
+  assert np.array_equal(K.rollout_lar(act, rew, 3).cpu().numpy(), g["without"].astype(np.float32))

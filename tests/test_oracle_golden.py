@@ -231,3 +231,12 @@ def test_generic_pixel_change_matches_reference(golden_dir):
     pc = O.pixel_change(a, b)
     assert pc.dtype == g["pc%d" % i].dtype and pc.shape == g["pc%d" % i].shape
     assert np.array_equal(pc, g["pc%d" % i]), i
+
+
+def test_concat_action_and_reward_matches_reference(golden_dir):
+  """ExperienceFrame.concat_action_and_reward (experience.py:34-46) with and without the state's objective vector."""
+  g = _load(golden_dir, "lar_golden.npz")
+  for i in range(len(g["action"])):
+    a, r = int(g["action"][i]), float(g["reward"][i])
+    assert np.array_equal(O.concat_action_and_reward(a, 3, r, g["objective"][i]), g["with_obj"][i])
+    assert np.array_equal(O.concat_action_and_reward(a, 3, r), g["without"][i])
