@@ -234,7 +234,12 @@ def measure_agent(torch, dist, dev, rank, world, envs, updates, history=2000, ob
   if world > 1:
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
   ms = float(ms)
+  steps_t = torch.tensor([float(steps)], device=dev, dtype=torch.float64)
+  if world > 1:
+    dist.all_reduce(steps_t, op=dist.ReduceOp.SUM)
+  steps_all = int(steps_t.item())
   upd_ms = sum(a.elapsed_time(b) for a, b in upd) / len(upd)
+  nccl_parity = check_nccl_parity(torch, dist, dev, rank, world, net, applier) if world > 1 else None
   losses = {k: float(v) for k, v in tr.last_losses.items()}
   mem = torch.cuda.max_memory_allocated(dev) / 1e9
   tr.stop()
@@ -245,12 +250,105 @@ def measure_agent(torch, dist, dev, rank, world, envs, updates, history=2000, ob
           "observations": {"cells": "agent cells int32 [N,2]; conv1 fwd / wgrad synthesise their x'' tiles in shared memory "
                                     "(render fused into the consumer: no frame is written to or read from HBM)",
                            "s2d": "x'' bf16 planes rendered by K1 (42 KB per frame)",
-                           "f32": "f32 frames rendered by K1 (85 KB per frame) + space-to-depth pass"}[obs], "value": world * envs * 20 * updates / (ms * 1e-3),
+                           "f32": "f32 frames rendered by K1 (85 KB per frame) + space-to-depth pass"}[obs],
+          # env steps actually taken: the sum over envs of the rollout lengths Trainer.process() returns (an env whose
+          # episode ends mid-window idles for the rest of it, trainer.py:279-296), summed over ranks
+          "value": steps_all / (ms * 1e-3), "env_steps": steps_all, "slot_steps": world * envs * 20 * updates,
           "unit": "env-steps/s", "ms_per_update": ms / updates, "model_update_ms": upd_ms,
           "updates_per_s": updates / (ms * 1e-3), "ring_fill_s": fill_s, "params": net.num_parameters,
           "finite": bool(all(np.isfinite(v) for v in losses.values())), "grad_norm": losses.get("grad_norm"),
           "peak_mem_gb": mem, "update_cuda_graph": tr._ugraph is not None,
-          "timing": "CUDA events around %d Trainer.process() calls, max over ranks" % updates}
+          "timing": "CUDA events around %d Trainer.process() calls, max over ranks" % updates,
+          "nccl_parity": nccl_parity}
+
+
+def check_nccl_parity(torch, dist, dev, rank, world, net, applier):
+  """The assertions of tests/test_gpu_multi.py on the live learner group, outside every timed region:
+  (1) the NCCL-sharded clip + RMSProp (reduce-scatter -> shard update -> all-gather) equals the single-GPU K6 kernels
+  applied to the mean gradient; (2) the learners' parameters are bit-identical on all ranks."""
+  from unreal_b200 import kernels as K
+  from unreal_b200.train.rmsprop_applier import RMSPropApplier
+  out = {}
+  try:
+    p = net.flat.numel()
+    gen = torch.Generator(device=dev).manual_seed(77)                    # same `var` on every rank
+    var0 = torch.randn(p, device=dev, generator=gen)
+    grad = torch.randn(p, device=dev, generator=torch.Generator(device=dev).manual_seed(1000 + rank)) * 0.05
+    ap = RMSPropApplier(7e-4, decay=0.99, momentum=0.0, epsilon=0.1, clip_norm=40.0)
+    flat = var0.clone()
+    norm = ap.apply_flat_to(flat, grad.clone(), 7e-4)
+    gsum = grad.clone()
+    dist.all_reduce(gsum, op=dist.ReduceOp.SUM)
+    gmean = gsum / world
+    ref = var0.clone(); rms = torch.ones(p, device=dev)
+    ref_norm = torch.zeros(1, device=dev)
+    K.rmsprop_update(ref, rms, None, gmean, K.grad_sumsq(gmean), 7e-4, 0.99, 0.0, 0.1, 40.0, grad_norm=ref_norm)
+    err = float(((flat - ref).abs() / ref.abs().clamp_min(1.0)).max())
+    out["sharded_vs_single_gpu_max_rel_err"] = err
+    out["grad_norm_rel_err"] = abs(float(norm) - float(ref_norm)) / max(float(ref_norm), 1e-12)
+    # (2) the agent's own parameters after its updates: compare every rank's buffer with rank 0's, bit for bit
+    mine = net.flat.detach().clone()
+    zero = mine.clone()
+    dist.broadcast(zero, src=0)
+    same = torch.tensor([1.0 if torch.equal(mine, zero) else 0.0], device=dev)
+    dist.all_reduce(same, op=dist.ReduceOp.MIN)
+    sh = flat.clone()
+    dist.broadcast(sh, src=0)
+    same2 = torch.tensor([1.0 if torch.equal(sh, flat) else 0.0], device=dev)
+    dist.all_reduce(same2, op=dist.ReduceOp.MIN)
+    out["params_bit_identical_across_ranks"] = bool(same.item() == 1.0 and same2.item() == 1.0)
+    out["tolerance"] = 1e-5
+    out["status"] = "ok" if (err <= 1e-5 and out["grad_norm_rel_err"] <= 1e-5 and
+                             out["params_bit_identical_across_ranks"]) else "FAILED"
+  except Exception as e:
+    out = {"status": "error", "error": repr(e)[:300]}
+  return out
+
+
+def parity_check(torch, eng, envs=64):
+  """After the timed loops: ONE more pass of the benched engine (4096 envs, CUDA graphs, the state the timed passes left
+  behind), checked against the oracle on a slice of `envs` environments -- transitions, pixel change, last frames,
+  n-step returns, PC targets, all bit for bit (the oracle only checks; nothing it computes is timed or shipped)."""
+  import numpy as np
+  from oracle import unreal_oracle as O
+  t = eng.t
+  try:
+    torch.cuda.synchronize(eng.device)
+    pos0 = eng.state.pos[:envs].cpu().numpy().copy()
+    eng.run_device()
+    torch.cuda.synchronize(eng.device)
+    acts = eng.actions[:, :envs].cpu().numpy(); vals = eng.values[:, :envs].cpu().numpy()
+    boot = eng.boot_value[:envs].cpu().numpy(); bq = eng.boot_q[:envs].cpu().numpy()
+    rew = np.zeros((t, envs), np.float32); term = np.zeros((t, envs), np.uint8)
+    pcs = np.zeros((t, envs, 20, 20), np.float32)
+    last = [None] * envs
+    for e in range(envs):
+      env = O.MazeOracle()
+      env.x, env.y = int(pos0[e, 0]), int(pos0[e, 1])
+      env.last_state = {'image': O.maze_render(env.x, env.y)}
+      for i in range(t):
+        img, r, tm, pc = env.process(int(acts[i, e]))
+        rew[i, e] = r; term[i, e] = tm; pcs[i, e] = pc
+        if tm:
+          env.reset()
+      last[e] = env.last_state['image']
+    scale = 255.0 if eng.obs.dtype == torch.uint8 else 1.0
+    ok = np.array_equal(eng.reward[:, :envs].cpu().numpy(), rew) and np.array_equal(eng.terminal[:, :envs].cpu().numpy(), term)
+    ok = ok and np.array_equal(eng.pc[:, :envs].cpu().numpy(), pcs)
+    got_obs = eng.obs[t - 1, :envs].cpu().numpy()
+    ok = ok and all(np.array_equal(got_obs[e], (last[e] * scale).astype(got_obs.dtype)) for e in range(envs))
+    R, adv = O.nstep_returns_segmented(rew, vals, term, boot, eng.gamma, np.float32)
+    ok = ok and np.array_equal(eng.R[:, :envs].cpu().numpy(), R) and np.array_equal(eng.adv[:, :envs].cpu().numpy(), adv)
+    want = np.zeros_like(pcs)
+    acc = bq.astype(np.float32).copy()
+    for i in range(t - 1, -1, -1):
+      acc = np.where(term[i][:, None, None] != 0, np.float32(0), acc)
+      acc = pcs[i] + np.float32(eng.gamma_pc) * acc
+      want[i] = acc
+    ok = ok and np.array_equal(eng.pc_tgt[:, :envs].cpu().numpy(), want)
+    return "ok" if ok else "FAILED", "%d envs x %d steps of the benched engine vs the oracle, bit-exact" % (envs, t)
+  except Exception as e:
+    return "error: " + repr(e)[:200], ""
 
 
 def agent_cpu_baseline(envs=4, seconds=10.0):
@@ -374,6 +472,7 @@ def run_b200(args):
   barrier()
   e2e_ms = e0.elapsed_time(e1)
   checksum = float(out["R"].sum())
+  parity, parity_what = parity_check(torch, eng) if rank == 0 else ("", "")
 
   h2d_bytes, d2h_bytes, launches_per_pass = eng.h2d_bytes_per_pass, eng.d2h_bytes_per_pass, eng.launches_per_pass
   agent = None
@@ -413,7 +512,7 @@ def run_b200(args):
                 "api": "unreal_b200.train.rollout.RolloutTargets.run_host (pinned host in/out, copies "
                        "pipelined around the phases on a second stream; frames, pixel-change maps and PC "
                        "targets stay in HBM for the learner)", "checksum_R": checksum},
-        "gpu_launches": K * launches_per_pass,
+        "gpu_launches": K * launches_per_pass, "parity_check": parity, "parity_check_what": parity_what,
         "roofline": {"bound": "hbm", "kernel": "maze_cta_kernel (K1)" if args.obs_dtype == "f32" else "maze_warp_kernel (K1)",
                      "achieved": achieved, "peak": peak,
                      "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650",

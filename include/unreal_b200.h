@@ -99,6 +99,10 @@ int unreal_maze_pixel_change(const int32_t* pos0, const int32_t* pos1, float* pc
  * cur, prev: [M,H,W,C] of dtype (u8 values are divided by 255); pc: [M,(H-4)/4,(W-4)/4] f32. */
 int unreal_pixel_change(const void* cur, const void* prev, int dtype, float* pc, int m, int h, int w,
                         int c, void* stream);
+/* Environment._subsample (environment.py:88-91) on its own: a [M,H,W] f32 -> out [M,H/width,W/width] f32, the mean
+ * over width x width blocks taken like numpy's reshape(...).mean(-1).mean(1): columns of a block row first (left to
+ * right, then / width), then the block's rows (top to bottom, then / width).  H and W must be multiples of width. */
+int unreal_subsample(const float* a, float* out, int m, int h, int w, int width, void* stream);
 /* stream form: frames [S, L+1, H,W,C]; pc [S, L, ph, pw] with pc[s,i] = change(frames[s,i+1],
  * frames[s,i]).  Every frame is read from HBM once. */
 int unreal_pixel_change_stream(const void* frames, int dtype, float* pc, int s, int l, int h, int w,

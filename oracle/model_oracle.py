@@ -6,8 +6,11 @@ TEST INFRASTRUCTURE (see ``oracle/__init__.py``): imported only by ``tests/``,
 **PARITY UNPINNED.**  The arithmetic of model.py lives in TensorFlow 1.x (unpinned; README says
 r1.0), which is neither under ``/root/reference`` nor installable here, and the reference's own
 ``model/model_test.py`` pins only the variable COUNT (20 / 18 / 12 / 14), which
-``tests/test_model_oracle.py`` checks.  Everything below restates model.py line by line with the
-documented TF-1 semantics of the ops it calls:
+``tests/test_model_oracle.py`` checks.  What anchors the restatement instead (same file): every op against a direct
+loop implementation of TF's documented definition; the LSTM unroll against ``torch.nn.LSTMCell`` fed the same
+weights with permuted gate columns; autograd against float64 central differences of the total loss in all 20
+variables; and every head's loss against numbers worked out by hand from model.py's formulas.  Everything below
+restates model.py line by line with the documented TF-1 semantics of the ops it calls:
 
   tf.nn.conv2d NHWC / HWIO / VALID                      model.py:283-289, :786-787
   tf.matmul + relu, flatten in NHWC order               model.py:332-340
@@ -92,6 +95,9 @@ class ModelOracle(object):
     self.pc_lambda = pixel_change_lambda
     self.entropy_beta = entropy_beta
     self.q = emulate_bf16
+    # float32 like the reference's placeholders (model.py:141 "float"); float64 parameters switch every tensor to
+    # double, which is what the finite-difference gradient check of tests/test_model_oracle.py runs in
+    self.dtype = next(iter(params.values())).dtype
 
   def w(self, name):
     t = self.p[name]
@@ -100,7 +106,7 @@ class ModelOracle(object):
   # model.py:281-289
   def encoder(self, images):
     """images [S,84,84,3] -> [S,9,9,32] (NHWC)."""
-    x = _bf16(images.float(), self.q).permute(0, 3, 1, 2)
+    x = _bf16(images.to(self.dtype), self.q).permute(0, 3, 1, 2)
     h1 = F.relu(F.conv2d(x, self.w("W_base_conv1").permute(3, 2, 0, 1), self.p["b_base_conv1"], stride=4))
     h1 = _bf16(h1, self.q)
     h2 = F.relu(F.conv2d(h1, self.w("W_base_conv2").permute(3, 2, 0, 1), self.p["b_base_conv2"], stride=2))
@@ -112,7 +118,7 @@ class ModelOracle(object):
     T, N = conv_out.shape[:2]
     flat = conv_out.reshape(T * N, 2592)
     fc = F.relu(flat @ self.w("W_base_fc1") + self.p["b_base_fc1"]).reshape(T, N, 256)
-    x = _bf16(torch.cat([fc, lar.float()], dim=2), self.q)
+    x = _bf16(torch.cat([fc, lar.to(self.dtype)], dim=2), self.q)
     kernel, bias = self.w("lstm_kernel"), self.p["lstm_bias"]
     c, h = c0, h0
     outs = []
@@ -150,7 +156,7 @@ class ModelOracle(object):
     return q, q.max(dim=3).values
 
   def _zero_state(self, n):
-    z = torch.zeros(n, 256)
+    z = torch.zeros(n, 256, dtype=self.dtype)
     return z, z
 
   def pc_forward(self, images, lar):

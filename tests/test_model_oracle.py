@@ -103,3 +103,211 @@ def test_losses_follow_model_py():
   want = -((np.log(0.2) * 2.0 + ent[0] * 0.001) + (np.log(0.25) * -1.0 + ent[1] * 0.001))
   assert abs(float(pol) - want) < 1e-5
   assert abs(float(val) - 0.25 * (0.25 + 0.25)) < 1e-6      # 0.5 * tf.nn.l2_loss = 0.25 * sum sq
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# Independent anchors of the restatement (TensorFlow cannot run here, so parity with TF stays unpinned; these tie
+# the oracle to (a) another implementation of the same cell, (b) the true derivative of its own forward pass, and
+# (c) numbers worked out by hand from model.py's formulas).
+# ----------------------------------------------------------------------------------------------------------------
+def _feed(T, N, A, seed, dtype=torch.float32):
+  rs = np.random.RandomState(seed)
+  t = lambda *s: torch.tensor(rs.rand(*s), dtype=dtype)      # noqa: E731
+  tn = lambda *s: torch.tensor(rs.randn(*s), dtype=dtype)    # noqa: E731
+  onehot = lambda *s: torch.eye(A, dtype=dtype)[torch.from_numpy(rs.randint(0, A, size=s))]   # noqa: E731
+  lar = lambda L: torch.cat([onehot(L, N), tn(L, N, 1)], dim=2)     # noqa: E731
+  mask = torch.ones(T, N, dtype=dtype)
+  mask[T - 1, 0] = 0.0                                               # one env's window is a step shorter
+  return {"base": dict(images=t(T, N, 84, 84, 3), lar=lar(T), a=onehot(T, N), adv=tn(T, N), R=tn(T, N), mask=mask,
+                       c0=tn(N, 256) * 0.1, h0=tn(N, 256) * 0.1),
+          "pc": dict(images=t(T, N, 84, 84, 3), lar=lar(T), a=onehot(T, N), R=t(T, N, 20, 20), mask=mask),
+          "vr": dict(images=t(T, N, 84, 84, 3), lar=lar(T), R=tn(T, N), mask=mask),
+          "rp": dict(images=t(N, 3, 84, 84, 3), c=torch.eye(3, dtype=dtype)[torch.from_numpy(rs.randint(0, 3, size=N))])}
+
+
+def test_lstm_matches_torch_lstmcell_with_permuted_gates():
+  """BasicLSTMCell (gates i, j, f, o on concat([x, h]) @ kernel, forget_bias 1.0 added to f; model.py:110) against
+  torch.nn.LSTMCell (gates i, f, g, o; separate input / hidden weights, no forget bias): an independently written
+  cell fed the SAME weights, columns permuted, must give the same unroll."""
+  A = 4
+  p = M.init_params(A, seed=8)
+  p["lstm_bias"] = torch.tensor(np.random.RandomState(9).randn(1024) * 0.1, dtype=torch.float32)
+  o = M.ModelOracle(p, A)
+  rs = np.random.RandomState(10)
+  T, N = 5, 3
+  conv = torch.tensor(rs.rand(T, N, 9, 9, 32), dtype=torch.float32)
+  lar = torch.tensor(rs.rand(T, N, A + 1), dtype=torch.float32)
+  c0 = torch.tensor(rs.randn(N, 256) * 0.3, dtype=torch.float32)
+  h0 = torch.tensor(rs.randn(N, 256) * 0.3, dtype=torch.float32)
+  out, (c, h) = o.lstm_layer(conv, lar, c0, h0)
+
+  n_in = 256 + A + 1
+  k, b = p["lstm_kernel"], p["lstm_bias"]
+  i_, j_, f_, o_ = [slice(q * 256, (q + 1) * 256) for q in range(4)]
+  order = (i_, f_, j_, o_)                                          # TF (i, j, f, o) -> torch (i, f, g = j, o)
+  cell = torch.nn.LSTMCell(n_in, 256)
+  with torch.no_grad():
+    cell.weight_ih.copy_(torch.cat([k[:n_in, s] for s in order], dim=1).t())
+    cell.weight_hh.copy_(torch.cat([k[n_in:, s] for s in order], dim=1).t())
+    bias = torch.cat([b[s] for s in order]).clone()
+    bias[256:512] += 1.0                                            # forget_bias
+    cell.bias_ih.copy_(bias)
+    cell.bias_hh.zero_()
+    fc = torch.relu(conv.reshape(T * N, 2592) @ p["W_base_fc1"] + p["b_base_fc1"]).reshape(T, N, 256)
+    hh, cc = h0, c0
+    for t in range(T):
+      hh, cc = cell(torch.cat([fc[t], lar[t]], dim=1), (hh, cc))
+      assert torch.allclose(out[t], hh, rtol=1e-5, atol=1e-6), t
+  assert torch.allclose(c, cc, rtol=1e-5, atol=1e-6) and torch.allclose(h, hh, rtol=1e-5, atol=1e-6)
+
+
+def test_gradients_match_fp64_finite_differences():
+  """The gradient every CUDA gradient test is compared with must be the derivative of the oracle's own forward
+  pass: central differences of the TOTAL loss (all four heads, a ragged mask, non-zero start state) in float64
+  against autograd, at random coordinates of every one of the 20 variables."""
+  A, T, N = 4, 2, 2
+  p32 = M.init_params(A, seed=12)
+  p = {k: v.double() * (3.0 if k.startswith("W_base_conv") else 1.0) for k, v in p32.items()}
+  p["lstm_bias"] = torch.tensor(np.random.RandomState(13).randn(1024) * 0.1, dtype=torch.float64)
+  o = M.ModelOracle(p, A, 0, 0.05, 0.001)
+  feed = _feed(T, N, A, seed=14, dtype=torch.float64)
+  _, parts, grads = o.loss_and_grads(feed)
+  assert set(parts) == {"policy", "value", "pc", "vr", "rp"}
+  rs = np.random.RandomState(15)
+  eps = 1e-6
+  worst = 0.0
+  for name, g in grads.items():
+    flat = p[name].view(-1)
+    # coordinates where the gradient is large enough to be measured, plus random ones
+    top = torch.topk(g.view(-1).abs(), min(3, flat.numel())).indices.tolist()
+    picks = set(top) | set(int(i) for i in rs.randint(0, flat.numel(), size=3))
+    for i in picks:
+      keep = float(flat[i])
+      with torch.no_grad():
+        flat[i] = keep + eps
+        lp = float(o.total_loss(feed)[0])
+        flat[i] = keep - eps
+        lm = float(o.total_loss(feed)[0])
+        flat[i] = keep
+      fd = (lp - lm) / (2 * eps)
+      an = float(g.view(-1)[i])
+      err = abs(fd - an) / max(abs(an), abs(fd), 1e-3)
+      worst = max(worst, err)
+      assert err <= 2e-5, (name, i, fd, an)
+  assert worst <= 2e-5
+
+
+def test_every_head_against_a_hand_computed_answer():
+  """model.py's formulas worked out by hand for parameters that make every unit of a layer carry the same value, so
+  the whole network collapses to scalar arithmetic (python floats below; the oracle runs in float64).  Pins the
+  constants a restatement can get wrong: VALID output sizes, NHWC flatten, the forget bias, the (c, h) order, the
+  zero start state of PC / VR, conv2d_transpose's overlap counts, the dueling mean, 0.5 * l2_loss = 0.25 * sum of
+  squares for the base value loss vs 0.5 * sum of squares for value replay, lambda * 0.5 for pixel control, the
+  entropy sign, and the reward-prediction class order."""
+  import math
+  A = 4
+  sg = lambda z: 1.0 / (1.0 + math.exp(-z))      # noqa: E731
+  p = {k: torch.zeros(s, dtype=torch.float64) for k, s, _ in M.variable_specs(A, 0)}
+  p["b_base_conv1"] += 0.5                       # conv1: W = 0 -> h1 = 0.5 everywhere (20x20x16)
+  p["W_base_conv2"] += 0.01; p["b_base_conv2"] += 0.1
+  h2 = 4 * 4 * 16 * 0.5 * 0.01 + 0.1             # = 1.38 on all 9x9x32
+  p["W_base_fc1"] += 0.001
+  fc = 2592 * h2 * 0.001                         # every one of the 256 units
+  n_in = 256 + A + 1
+  bi, bj, bf, bo = 0.3, 0.7, -0.2, 0.1
+  p["lstm_bias"][0:256] = bi; p["lstm_bias"][256:512] = bj; p["lstm_bias"][512:768] = bf; p["lstm_bias"][768:] = bo
+  p["lstm_kernel"][:256, 256:512] = 0.0005       # fc units -> candidate gate j
+  p["lstm_kernel"][256 + A, 0:256] = 0.05        # last reward -> input gate i
+  p["lstm_kernel"][256 + 2, 512:768] = 0.4       # last action == 2 -> forget gate f
+  p["lstm_kernel"][n_in:, 768:] = 0.001          # h_{t-1} units -> output gate o
+  p["W_base_fc_p"][:, 1] = 0.01; p["b_base_fc_p"][3] = 0.2
+  p["W_base_fc_v"] += 0.002; p["b_base_fc_v"] += 0.1
+  p["W_pc_fc1"] += 0.001
+  p["W_pc_deconv_v"] += 0.01; p["b_pc_deconv_v"] += 0.05
+  for a in range(A):
+    p["W_pc_deconv_a"][:, :, a, :] = 0.01 * (a + 1)
+  p["b_pc_deconv_a"] += -0.02
+  p["W_rp_fc1"][:, 0] = 1e-4; p["W_rp_fc1"][:, 1] = 2e-4; p["W_rp_fc1"][:, 2] = -1e-4
+  p["b_rp_fc1"][2] = 0.3
+  o = M.ModelOracle(p, A, 0, pixel_change_lambda=0.05, entropy_beta=0.001)
+
+  def unroll(last_actions, last_rewards, c, h):
+    """-> list of h_t (a scalar: all 256 units are equal), final (c, h)."""
+    hs = []
+    for la, lr in zip(last_actions, last_rewards):
+      i = bi + 0.05 * lr
+      j = bj + 256 * fc * 0.0005
+      f = bf + (0.4 if la == 2 else 0.0)
+      g = bo + 256 * h * 0.001
+      c = c * sg(f + 1.0) + sg(i) * math.tanh(j)
+      h = math.tanh(c) * sg(g)
+      hs.append(h)
+    return hs, c, h
+
+  def heads(h):
+    z = [0.0, 256 * h * 0.01, 0.0, 0.2]
+    m = max(z)
+    e = [math.exp(v - m) for v in z]
+    pi = [v / sum(e) for v in e]
+    return pi, 256 * h * 0.002 + 0.1
+
+  T, N = 3, 1
+  img = torch.full((T, N, 84, 84, 3), 0.37, dtype=torch.float64)     # conv1's W is zero: any image gives h1 = 0.5
+  la, lr = [2, 0, 2], [0.0, 1.0, -1.0]
+  lar = torch.zeros(T, N, A + 1, dtype=torch.float64)
+  for t in range(T):
+    lar[t, 0, la[t]] = 1.0; lar[t, 0, A] = lr[t]
+  acts, adv, R = [1, 3, 0], [0.5, -1.5, 2.0], [1.0, 0.2, -0.4]
+  a1 = torch.zeros(T, N, A, dtype=torch.float64)
+  for t in range(T):
+    a1[t, 0, acts[t]] = 1.0
+  c0, h0 = 0.2, -0.1
+  ones = torch.ones(T, N, dtype=torch.float64)
+  pc_R = torch.full((T, N, 20, 20), 0.3, dtype=torch.float64)
+  feed = {"base": dict(images=img, lar=lar, a=a1, adv=torch.tensor(adv, dtype=torch.float64).view(T, N),
+                       R=torch.tensor(R, dtype=torch.float64).view(T, N), mask=ones,
+                       c0=torch.full((N, 256), c0, dtype=torch.float64), h0=torch.full((N, 256), h0, dtype=torch.float64)),
+          "pc": dict(images=img, lar=lar, a=a1, R=pc_R, mask=ones),
+          "vr": dict(images=img, lar=lar, R=torch.tensor(R, dtype=torch.float64).view(T, N), mask=ones),
+          "rp": dict(images=img[:, 0].unsqueeze(0), c=torch.tensor([[0.0, 0.0, 1.0]], dtype=torch.float64))}
+  total, parts = o.total_loss(feed)
+
+  # base (model.py:499-517): start state fed, policy = -sum(log pi(a) * adv + beta * H), value = 0.5 * l2_loss(R - V)
+  hs, c_end, h_end = unroll(la, lr, c0, h0)
+  pol = val = 0.0
+  for t in range(T):
+    pi, v = heads(hs[t])
+    H = -sum(q * math.log(q) for q in pi)
+    pol -= math.log(pi[acts[t]]) * adv[t] + 0.001 * H
+    val += 0.25 * (R[t] - v) ** 2
+  assert abs(float(parts["policy"]) - pol) <= 1e-12 * max(1.0, abs(pol))
+  assert abs(float(parts["value"]) - val) <= 1e-12
+  _, _, state = o.base_forward(img, lar, feed["base"]["c0"], feed["base"]["h0"])
+  assert abs(float(state[0][0, 7]) - c_end) <= 1e-12 and abs(float(state[1][0, 200]) - h_end) <= 1e-12   # (c, h)
+
+  # value replay (:556-565): ZERO start state (:459), 0.5 * sum of squares
+  hz, _, _ = unroll(la, lr, 0.0, 0.0)
+  vr = sum(0.5 * (R[t] - heads(hz[t])[1]) ** 2 for t in range(T))
+  assert abs(float(parts["vr"]) - vr) <= 1e-12
+
+  # pixel control (:411-443, :531-546): zero start state (:393); conv2d_transpose 4x4 stride 2 over 9x9 -> 20x20:
+  # an output row y receives cnt(y) = #{(i, kh): 2i + kh = y} kernel taps: 1 at the two border rows on each side, else 2
+  cnt = [sum(1 for i in range(9) for k in range(4) if 2 * i + k == y) for y in range(20)]
+  assert cnt == [1, 1] + [2] * 16 + [1, 1]
+  pc = 0.0
+  for t in range(T):
+    hp = max(256 * hz[t] * 0.001, 0.0)
+    for y in range(20):
+      for x in range(20):
+        taps = cnt[y] * cnt[x] * 32 * hp
+        v = max(taps * 0.01 + 0.05, 0.0)
+        ad = [max(taps * 0.01 * (a + 1) - 0.02, 0.0) for a in range(A)]
+        q = v + ad[acts[t]] - sum(ad) / A
+        pc += 0.05 * 0.5 * (0.3 - q) ** 2
+  assert abs(float(parts["pc"]) - pc) <= 1e-10 * max(1.0, pc)
+
+  # reward prediction (:473-488, :571-575): 3 frames' features concatenated, classes [zero, positive, negative]
+  z = [7776 * h2 * 1e-4, 7776 * h2 * 2e-4, 7776 * h2 * -1e-4 + 0.3]
+  rp = -(z[2] - math.log(sum(math.exp(v) for v in z)))
+  assert abs(float(parts["rp"]) - rp) <= 1e-12 * max(1.0, abs(rp))
+  assert abs(float(total) - (pol + val + vr + pc + rp)) <= 1e-9 * max(1.0, abs(float(total)))

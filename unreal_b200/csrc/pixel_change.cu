@@ -134,6 +134,26 @@ static int launch_c(const void* x, const void* y, float* pc, int m, int l, int h
   return UNREAL_OK;
 }
 
+// _subsample alone (environment.py:88-91): one thread per output cell, numpy's order of operations
+__global__ void subsample_kernel(const float* __restrict__ a, float* __restrict__ out, int H, int W, int width, int oh,
+                                 int ow, size_t total) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int j = (int)(idx % ow);
+  const int i = (int)((idx / ow) % oh);
+  const size_t m = idx / ((size_t)ow * oh);
+  const float* base = a + (m * H + (size_t)i * width) * W + (size_t)j * width;
+  const float wf = (float)width;
+  float acc = 0.f;
+  for (int r = 0; r < width; ++r) {
+    float s = base[(size_t)r * W];
+    for (int c = 1; c < width; ++c) s = __fadd_rn(s, base[(size_t)r * W + c]);
+    const float row = __fdiv_rn(s, wf);                 // .mean(-1)
+    acc = r == 0 ? row : __fadd_rn(acc, row);
+  }
+  out[idx] = __fdiv_rn(acc, wf);                        // .mean(1)
+}
+
 static int check_shape(const char* fn, int m, int h, int w, int dtype) {
   UNREAL_REQUIRE(m >= 0, "%s: negative batch", fn);
   UNREAL_REQUIRE(h >= 8 && w >= 8 && (h - 4) % 4 == 0 && (w - 4) % 4 == 0,
@@ -177,4 +197,17 @@ extern "C" int unreal_pixel_change_stream(const void* frames, int dtype, float* 
   }
   if (dtype == UNREAL_F32) return launch_c<float, true>(frames, nullptr, pc, s, l, h, w, c, as_stream(stream));
   return launch_c<uint8_t, true>(frames, nullptr, pc, s, l, h, w, c, as_stream(stream));
+}
+
+extern "C" int unreal_subsample(const float* a, float* out, int m, int h, int w, int width, void* stream) {
+  UNREAL_REQUIRE(m >= 0 && h > 0 && w > 0 && width > 0, "unreal_subsample: bad sizes");
+  UNREAL_REQUIRE(h % width == 0 && w % width == 0, "unreal_subsample: %dx%d is not a multiple of the block width %d", h, w,
+                 width);
+  if (m == 0) return UNREAL_OK;
+  UNREAL_REQUIRE(a && out, "unreal_subsample: null buffer");
+  const size_t total = (size_t)m * (h / width) * (w / width);
+  subsample_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(a, out, h, w, width, h / width, w / width,
+                                                                                 total);
+  UNREAL_LAUNCH_CHECK("subsample_kernel");
+  return UNREAL_OK;
 }

@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(kPcThreads) pc_targets_kernel(const float4* __
   const size_t idx = (size_t)blockIdx.x * kPcThreads + threadIdx.x;
   if (idx >= per_t) return;
   const int n = (int)(idx / kPcVec);
-  const int n_t = len ? min(len[n], T) : T;
+  const int n_t = len ? max(0, min(len[n], T)) : T;   // a not-ready ring reports len 0 -> n_batch -1: clamp, never store at t = -1
   const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
   float4 cur[kPcChunk], nxt[kPcChunk];
   uint8_t tcur[kPcChunk], tnxt[kPcChunk];

@@ -94,10 +94,10 @@ class Environment(object):
   # the device (K2); they fail loudly without one.
   def _subsample(self, a, average_width):
     """environment.py:88-91: mean over average_width x average_width blocks (columns, then rows)."""
-    t = torch.as_tensor(np.ascontiguousarray(a)).cuda()
-    s = t.shape
-    sh = (s[0] // average_width, average_width, s[1] // average_width, average_width)
-    return t.reshape(sh).mean(-1).mean(1).cpu().numpy()
+    a = np.asarray(a)
+    t = torch.as_tensor(np.ascontiguousarray(a, dtype=np.float32)).cuda().unsqueeze(0)
+    out = K.subsample(t, int(average_width))[0].cpu().numpy()      # unreal_subsample
+    return out.astype(np.float64) if a.dtype == np.float64 else out
 
   def _calc_pixel_change(self, state, last_state):
     """environment.py:93-99 through unreal_pixel_change (K2)."""

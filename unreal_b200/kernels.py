@@ -132,6 +132,15 @@ def pixel_change_stream(frames, out=None):
   return out
 
 
+def subsample(a, width, out=None):
+  """a [M,H,W] f32 -> [M,H/width,W/width]: Environment._subsample (environment.py:88-91)."""
+  m, h, w = a.shape
+  if out is None:
+    out = torch.empty(m, h // width, w // width, dtype=torch.float32, device=a.device)
+  call("unreal_subsample", ptr(a, torch.float32, "a"), ptr(out, torch.float32, "out"), m, h, w, int(width), stream_ptr())
+  return out
+
+
 # ---------------------------------------------------------------------------- targets
 def nstep_returns(r, v, term, boot, gamma, out_R=None, out_adv=None):
   t, n = r.shape

@@ -52,22 +52,19 @@ class FrameTrainer(Trainer):
     return lar
 
   def _fill_experience(self, sess):
-    """trainer.py:176-205 for every env."""
+    """trainer.py:176-205 for every env still warming up (a full ring = a worker that has left the warm-up)."""
     env = self.environment
+    act = self._fill_mask()
     obj = env.objective.clone() if env.objective is not None else None
     last_action, last_reward = env.last_action.clone(), env.last_reward.clone()
     lar = self._last_action_reward(last_action, last_reward, obj)
     prev = env.last_state['image']
-    pi, _, _ = self.local_network.run_base_policy_and_value(sess, env.last_state, lar, None)
-    action = self.choose_action(pi)
-    _, reward, _, pc = env.process(action)        # terminal envs are reset inside (:201-202)
+    pi, _, _ = self.local_network.run_base_policy_and_value(sess, env.last_state, lar, act)
+    action = self.choose_action(pi, act)
+    _, reward, _, pc = env.process(action, active=act)        # terminal envs are reset inside (:201-202)
     self.experience.add_frames(env.frame_rec, frame=prev, pixel_change=pc, reward=reward, last_reward=last_reward,
                                objective=obj)
-    full = self.experience.ring.state()["full"]
-    if bool(full.any()):
-      env.reset(full)                             # :203-205
-      if self.verbose:
-        print("Replay buffer filled")
+    self._fill_done(env)                                      # :203-205
 
   # -- [Base A3C]  trainer.py:218-336 ----------------------------------------------------------
   def _process_base(self, sess, global_t, summary_writer, summary_op_dict, summary_dict):
@@ -77,6 +74,7 @@ class FrameTrainer(Trainer):
     start_lstm_state = None if state is None else tuple(x.clone() if isinstance(x, torch.Tensor) else x for x in state)
     active = torch.ones(n, dtype=torch.uint8, device=d)
     ended = torch.zeros(n, dtype=torch.uint8, device=d)
+    stats0 = self.episode_stats.clone()
     self._obs[0].copy_(env.last_state['image'])
     env._cur = self._obs[0]
     self._active.zero_(); self._rew.zero_(); self._term.zero_()
@@ -109,7 +107,7 @@ class FrameTrainer(Trainer):
       self.episode_reward.mul_(1 - tn)
       active = active & (1 - term_now)
     lengths = self._active.sum(0).to(torch.int32)
-    self._pending_local_t = lengths.max()
+    self._set_pending(lengths, stats0)
     # bootstrap: V(new_state) with frame.get_action_reward for envs that did not end (:298-300)
     boot_lar = self._last_action_reward(last_action, last_reward, last_obj)
     boot_obs = self._obs[1:].gather(
@@ -133,7 +131,7 @@ class FrameTrainer(Trainer):
     n = self.num_envs
     ex = self.experience
     start, length, f = ex.sample_sequence(L)
-    n_batch = (length - 1).to(torch.int32)                  # the last frame is only the bootstrap state
+    n_batch = (length - 1).clamp_(min=0).to(torch.int32)    # the last frame is only the bootstrap state
     images = ex.gather_frames(start, length, L)             # [L,N,h,w,3] u8, zero past len
     idx_last = (length.to(torch.int64) - 1).clamp_(min=0)
     lar = self._lar_seq(f, L)

@@ -195,19 +195,37 @@ class Trainer(object):
     out[:, -1] = last_reward
     return out
 
-  def _fill_experience(self, sess):
-    """trainer.py:176-205: one policy forward, one env step, one add_frame, for every env."""
-    env = self.environment
-    lar = self._last_action_reward(env.last_action, env.last_reward)
-    pi, _, _ = self.local_network.run_base_policy_and_value(sess, env.last_state, lar, None)
-    action = self.choose_action(pi)
-    env.process(action)                       # auto-reset covers `if terminal: reset()` (:201-202)
-    self.experience.add_frames(env.frame_rec)
+  def _fill_mask(self):
+    """Warm-up mask: an env whose ring is full is one reference worker that has left `_fill_experience`
+    (trainer.py:446-448) -- it is frozen (no step, no RNG draw, no frame) until the slowest ring is full."""
+    if getattr(self, "_fill_active", None) is None:
+      self._fill_active = torch.ones(self.num_envs, dtype=torch.uint8, device=self.device)
+    return self._fill_active
+
+  def _fill_done(self, env):
+    """trainer.py:203-205, without a host round trip: reset the envs whose ring became full in THIS step
+    (once, like the reference) and take them out of the warm-up."""
     full = self.experience.ring.state()["full"]
-    if bool(full.any()):
-      env.reset(full)                         # :203-205
-      if self.verbose:
-        print("Replay buffer filled")
+    newly = full & self._fill_active
+    env.reset(newly)
+    self._fill_active = self._fill_active & (1 - full)
+
+  def _fill_experience(self, sess):
+    """trainer.py:176-205: one policy forward, one env step, one add_frame, for every env still warming up."""
+    env = self.environment
+    act = self._fill_mask()
+    lar = self._last_action_reward(env.last_action, env.last_reward)
+    pi, _, _ = self.local_network.run_base_policy_and_value(sess, env.last_state, lar, act)
+    action = self.choose_action(pi, act)
+    env.process(action, active=act)           # auto-reset covers `if terminal: reset()` (:201-202)
+    self.experience.add_frames(env.frame_rec)  # frozen envs carry an invalid record: nothing is added
+    self._fill_done(env)
+
+  def _set_pending(self, lengths, stats0):
+    """What process() returns, as ONE small device tensor (a single read-back per iteration):
+    [env steps taken in this window = sum of the rollout lengths (trainer.py:277 `local_t += 1` per step of every
+    worker; main.py:125 adds each worker's diff to global_t), episodes finished in it, sum of their scores]. """
+    self._pending = torch.cat((lengths.sum().to(torch.float64).view(1), self.episode_stats - stats0))
 
   def _print_log(self, global_t):
     if (self.thread_index == 0) and (self.local_t - self.prev_local_t >= PERFORMANCE_LOG_INTERVAL):
@@ -226,6 +244,7 @@ class Trainer(object):
     start_lstm_state = None if state is None else tuple(x.clone() if isinstance(x, torch.Tensor) else x for x in state)
     active = torch.ones(n, dtype=torch.uint8, device=d)
     ended = torch.zeros(n, dtype=torch.uint8, device=d)
+    stats0 = self.episode_stats.clone()       # [episodes finished, sum of their scores] before this window
     self._obs[0].copy_(env.last_state['image'])
     self._pos[0].copy_(env.state.pos)
     self._active.zero_(); self._rew.zero_(); self._term.zero_()
@@ -252,7 +271,7 @@ class Trainer(object):
       K.rollout_post(self._rew[t], self._term[t], env.frame_rec, active, ended, last_rec, self.episode_reward,
                      lstm_c if fused_state else None, lstm_h if fused_state else None, self.episode_stats)
     lengths = self._active.sum(0).to(torch.int32)
-    self._pending_local_t = lengths.max()      # read back once, after the update has been enqueued
+    self._set_pending(lengths, stats0)         # read back once, after the update has been enqueued
     # bootstrap: V(new_state) with frame.get_action_reward for envs that did not end (:298-300)
     rec = K.frame_unpack(last_rec, fields=("action", "reward"))
     boot_lar = self._last_action_reward(rec["action"], rec["reward"])
@@ -274,7 +293,7 @@ class Trainer(object):
   def _sample_sequence(self):
     L = self.local_t_max + 1
     start, length, f = self.experience.sample_sequence(L)
-    n_batch = (length - 1).to(torch.int32)                  # the last frame is only the bootstrap state
+    n_batch = (length - 1).clamp_(min=0).to(torch.int32)    # the last frame is only the bootstrap state
     idx_last = (length.to(torch.int64) - 1).clamp_(min=0)
     take = lambda x: x.gather(1, idx_last.view(-1, *([1] * (x.dim() - 1))).expand(-1, 1, *x.shape[2:]))[:, 0]  # noqa: E731
     boot_pos = take(f["pos0"]).contiguous()
@@ -338,16 +357,16 @@ class Trainer(object):
       # first call: run the phase eagerly (this IS this iteration's data, and it performs every lazy
       # initialisation), then record the same code into a graph without executing it
       feed = self._data_phase(sess)
-      pending = self._pending_local_t
+      pending = self._pending
       torch.cuda.synchronize(self.device)
       g = torch.cuda.CUDAGraph()
       with _lib.graph_capture(g):
         self._graph_feed = self._data_phase(sess)
-      self._graph_pending = self._pending_local_t
-      self._pending_local_t = pending
+      self._graph_pending = self._pending
+      self._pending = pending
       self._graph = g
       return feed
-    self._pending_local_t = self._graph_pending
+    self._pending = self._graph_pending
     self._graph.replay()
     return dict(self._graph_feed)
 
@@ -397,9 +416,18 @@ class Trainer(object):
       self.last_feed = feed
       if hasattr(self.local_network, 'update'):
         self.last_losses = self._update(feed, cur_learning_rate)
-      self.local_t += int(self._pending_local_t)
+      steps, finished, score_sum = self._pending.tolist()       # the iteration's only host read-back
+      self.local_t += int(steps)
       if hasattr(self, 'start_time'):
         self._print_log(global_t)
-      ended = feed['base']['terminal_end']
-      episode_score = None   # per-env scores are device side; see self.episode_reward
+      # trainer.py:451, :481: the score of the episode that ended in this rollout, else None.  With num_envs > 1
+      # several workers' episodes can end in one window: their MEAN score (each is one reference worker's return).
+      episode_score = None
+      if finished > 0:
+        episode_score = score_sum / finished
+        if self.num_envs == 1 and float(episode_score).is_integer():
+          episode_score = int(episode_score)                      # maze rewards are ints, like the reference's sum
+        if self.verbose:
+          print("Trainer {}>>> score={}".format(self.thread_index, episode_score))     # :281
+      # :635-636: env steps actually taken (sum over envs -- what main.py:125 accumulates into global_t)
       return self.local_t - start_local_t, episode_score
