@@ -349,6 +349,14 @@ int unreal_a3c_head_loss(const float* h, const float* wp, const float* bp, const
 int unreal_a3c_head_bwd(const float* h, const float* wp, const float* wv, const float* dz, const float* dv,
                         const float* go2, int64_t m, int a, float* dh, float* dwp, float* dbp, float* dwv, float* dbv,
                         void* stream);
+/* Reward-prediction head after its fc GEMM (model.py:482-488 softmax, :571-575 loss).  logits8 [N,8] f32: columns 0..2 =
+ * features . W_rp (the bf16 tcgen05 GEMM on the weight shadow padded to 8 columns), bias [3] added here.
+ *   p_out (nullable) [N,3] = softmax(logits + bias)                                  (run_rp_c, model.py:723-728)
+ *   loss  (nullable, double, accumulated) += -sum c log(clip(p, 1e-20, 1)) with c [N,3] f32 ([zero, positive, negative])
+ *   dz16  (nullable) bf16 [N,8] = *go * d loss / d logits (columns 3..7 zero: the GEMM operand of the backward pass),
+ *   db [3] += column sums of dz (caller-zeroed).  go: device scalar, nullable = 1. */
+int unreal_rp_loss(const float* logits8, const float* bias, const float* c, int64_t n, float* p_out, double* loss,
+                   void* dz16, float* db, const float* go, void* stream);
 /* Pixel-control head: dueling combine, Q(a) gather and L2 loss in one pass (model.py:431-441, :531-546).
  * y8 [samples*px, 8] f32 = merged deconv output after ReLU (channel 0 V, 1..A advantages, rest padding);
  * act [samples] i32; target [samples*px] f32; mask [samples] f32.

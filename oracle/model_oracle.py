@@ -179,7 +179,7 @@ class ModelOracle(object):
     """images [N,3,84,84,3] -> rp_c [N,3]."""
     N = images.shape[0]
     enc = self.encoder(images.reshape(N * 3, 84, 84, 3)).reshape(N, 7776)
-    return F.softmax(enc @ self.p["W_rp_fc1"] + self.p["b_rp_fc1"], dim=-1)
+    return F.softmax(enc @ self.w("W_rp_fc1") + self.p["b_rp_fc1"], dim=-1)
 
   # model.py:490-598 ------------------------------------------------------------------
   def base_loss(self, pi, v, a_onehot, adv, R, mask):

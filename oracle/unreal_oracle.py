@@ -485,6 +485,7 @@ class RolloutOracle(object):
     env = self.env
     states, pos, lars, actions, rewards, values = [], [], [], [], [], []
     terminal_end = False
+    score = None                       # summary_dict['values']['score_input'] (trainer.py:281-283) -> process()'s episode_score
     image = frame = None
     for _ in range(self.n_step_TD):
       lar = concat_action_and_reward(env.last_action, self.action_size, env.last_reward)
@@ -498,6 +499,7 @@ class RolloutOracle(object):
       self.local_t += 1
       if frame['terminal']:
         terminal_end = True
+        score = self.episode_reward
         self.episode_reward = 0
         env.reset()
         self.net.reset_state()
@@ -514,7 +516,7 @@ class RolloutOracle(object):
       a = np.zeros([self.action_size]); a[ai] = 1.0
       batch_a.append(a)
     return dict(states=states, pos=pos, lar=lars, a=batch_a[::-1], adv=batch_adv[::-1],
-                R=batch_R[::-1], terminal_end=terminal_end)
+                R=batch_R[::-1], terminal_end=terminal_end, score=score)
 
   def _lar(self, f):
     return concat_action_and_reward(f['last_action'], self.action_size, f['last_reward'])

@@ -420,3 +420,42 @@ def test_fused_heads_match_torch_heads():
     out = K.a3c_head(h.detach(), wp.detach().contiguous(), bp.detach(), wv.detach().reshape(256).contiguous(), bv.detach(),
                      want_pi=True, want_v=True)
     assert torch.allclose(out["pi"], pi.detach(), rtol=1e-4, atol=1e-6) and torch.allclose(out["v"], v.detach(), rtol=1e-4, atol=1e-5)
+
+
+def test_rp_head_on_the_device_path_matches_torch():
+  """The reward-prediction head (model.py:479-488, :571-575) as tcgen05 GEMMs on the padded bf16 weight shadow +
+  unreal_rp_loss (bias, softmax, clipped cross-entropy, d loss / d logits as the backward GEMMs' bf16 operand),
+  against the same arithmetic in torch fp32 with autograd on the bf16-rounded operands.  Soft and one-hot targets,
+  batch sizes off the 128-row tile, and run_rp_c's probabilities."""
+  from unreal_b200 import kernels as K
+  from unreal_b200.model.layers import RpHeadLossFn
+  dev = torch.device("cuda", 0)
+  g = torch.Generator(device=dev).manual_seed(21)
+  for n in (3, 130, 1000):
+    h2 = torch.relu(torch.randn(n, 7776, device=dev, generator=g)).to(torch.bfloat16).requires_grad_(True)
+    w32 = (torch.randn(7776, 3, device=dev, generator=g) * 0.02).requires_grad_(True)
+    b32 = (torch.randn(3, device=dev, generator=g) * 0.1).requires_grad_(True)
+    w8 = torch.zeros(7776, 8, dtype=torch.bfloat16, device=dev)
+    w8[:, :3] = w32.detach()
+    cls = torch.randint(0, 3, (n,), device=dev, generator=g)
+    c = torch.nn.functional.one_hot(cls, 3).float()
+    if n == 130:
+      c = torch.rand(n, 3, device=dev, generator=g)                  # the kernel takes the reference's general c
+    loss = RpHeadLossFn.apply(h2, w8, w32, b32, c)
+    (loss * 0.6).backward()
+    got = [h2.grad.float().clone(), w32.grad.clone(), b32.grad.clone()]
+    for x in (h2, w32, b32):
+      x.grad = None
+    hf = h2.detach().float().requires_grad_(True)
+    wf = w8[:, :3].float().detach().requires_grad_(True)
+    p = torch.softmax(hf @ wf + b32, -1)
+    rloss = -(c * torch.log(p.clamp(1e-20, 1.0))).sum()
+    (rloss * 0.6).backward()
+    assert torch.allclose(loss, rloss.detach(), rtol=1e-4, atol=1e-3), n
+    # dY is rounded to bf16 where it becomes a GEMM operand (2^-9 per element), dh2 is a bf16 tensor
+    for x, y, name in zip(got, (hf.grad, wf.grad, b32.grad), ("h2", "W", "b")):
+      assert float((x - y).abs().max()) <= 1e-2 * float(y.abs().max()) + 1e-7, (n, name)
+    logits8 = K.gemm_bf16(h2.detach(), w8, b_mn_major=True)
+    pr = K.rp_loss(logits8, b32.detach().contiguous(), want_p=True)["p"]
+    assert torch.allclose(pr, p.detach(), rtol=1e-4, atol=1e-6)
+    assert torch.allclose(logits8[:, 3:], torch.zeros_like(logits8[:, 3:]))

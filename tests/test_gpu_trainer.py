@@ -142,12 +142,17 @@ def test_many_envs_each_matches_its_own_oracle_worker():
     for w in workers:
       w.fill_step()
   assert all(w.ring.is_full() for w in workers)
+  scored = 0
   for it in range(40):
-    tr.process(None, 0)
+    diff, episode_score = tr.process(None, 0)
     f = tr.last_feed
+    steps, scores = 0, []
     for e, w in enumerate(workers):
       b = w.process_base(); p = w.process_pc(); v = w.process_vr(); r = w.process_rp()
       L = len(b['pos'])
+      steps += L
+      if b['score'] is not None:
+        scores.append(b['score'])
       assert int(f['base']['length'][e]) == L
       assert np.array_equal(f['base']['pos'][:L, e].cpu().numpy(), np.array(b['pos']))
       _close(f['base']['R'][:L, e].cpu().numpy(), np.array(b['R'], np.float64))
@@ -161,3 +166,11 @@ def test_many_envs_each_matches_its_own_oracle_worker():
       _close(f['vr']['R'][e, :Lv].cpu().numpy(), np.array(v['R'], np.float64))
       assert np.array_equal(f['rp']['pos'][e].cpu().numpy(), np.array(r['pos']))
       assert list(f['rp']['c'][e].cpu().numpy()) == r['c']
+    # the return contract (trainer.py:451, :481, :635-636; main.py:125 adds the diff to global_t): env steps actually
+    # taken by all workers, and the score of the episodes that ended in this window (their mean when several did)
+    assert diff == steps
+    if scores:
+      scored += 1
+      assert episode_score is not None and abs(episode_score - float(np.mean(scores))) <= 1e-6
+    else:
+      assert episode_score is None

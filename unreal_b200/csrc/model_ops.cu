@@ -593,6 +593,65 @@ static int check_geom(const char* fn, ConvGeom& g) {
   return UNREAL_OK;
 }
 
+// Reward-prediction head after the fc GEMM (model.py:482-488, :571-575): logits8 [N,8] f32 hold h2 . W_rp in columns
+// 0..2 (the bf16 tcgen05 GEMM on the weight shadow padded to 8 columns; no bias yet).  One thread per sample:
+//   z = logits + b;  p = softmax(z);  loss += -sum_k c_k log(clip(p_k, 1e-20, 1));
+//   dz_j = go * sum_k c_k [p_k >= 1e-20] (p_j - delta_kj)      -> dz16 bf16 [N,8] (columns 3..7 zero), db [3] += sum_n dz
+__global__ void __launch_bounds__(256) rp_loss_kernel(const float* __restrict__ logits8, const float* __restrict__ bias,
+                                                      const float* __restrict__ c, int64_t n, float* __restrict__ p_out,
+                                                      double* __restrict__ loss, __nv_bfloat16* __restrict__ dz16,
+                                                      float* __restrict__ db, const float* __restrict__ go) {
+  const float b0 = bias[0], b1 = bias[1], b2 = bias[2];
+  const float g = go ? *go : 1.f;
+  double lsum = 0.0;
+  float d0 = 0.f, d1 = 0.f, d2 = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 l = *reinterpret_cast<const float4*>(logits8 + i * 8);
+    const float z0 = l.x + b0, z1 = l.y + b1, z2 = l.z + b2;
+    const float m = fmaxf(z0, fmaxf(z1, z2));
+    const float e0 = expf(z0 - m), e1 = expf(z1 - m), e2 = expf(z2 - m);
+    const float inv = 1.f / (e0 + e1 + e2);
+    const float p0 = e0 * inv, p1 = e1 * inv, p2 = e2 * inv;
+    if (p_out) { p_out[i * 3] = p0; p_out[i * 3 + 1] = p1; p_out[i * 3 + 2] = p2; }
+    if (c == nullptr) continue;
+    const float c0 = c[i * 3], c1 = c[i * 3 + 1], c2 = c[i * 3 + 2];
+    if (loss) {
+      lsum -= (double)(c0 * logf(fminf(fmaxf(p0, 1e-20f), 1.f)) + c1 * logf(fminf(fmaxf(p1, 1e-20f), 1.f)) +
+                       c2 * logf(fminf(fmaxf(p2, 1e-20f), 1.f)));
+    }
+    if (dz16) {
+      const float k0 = p0 >= 1e-20f ? c0 : 0.f, k1 = p1 >= 1e-20f ? c1 : 0.f, k2 = p2 >= 1e-20f ? c2 : 0.f;
+      const float ks = k0 + k1 + k2;
+      const float g0 = g * (ks * p0 - k0), g1 = g * (ks * p1 - k1), g2 = g * (ks * p2 - k2);
+      __align__(16) __nv_bfloat16 o[8];
+      o[0] = __float2bfloat16(g0); o[1] = __float2bfloat16(g1); o[2] = __float2bfloat16(g2);
+#pragma unroll
+      for (int q = 3; q < 8; ++q) o[q] = __float2bfloat16(0.f);
+      *reinterpret_cast<uint4*>(dz16 + i * 8) = *reinterpret_cast<const uint4*>(o);
+      d0 += g0; d1 += g1; d2 += g2;
+    }
+  }
+  // block reduction: loss (double) and the three bias-gradient sums
+  __shared__ double s_l[8];
+  __shared__ float s_d[8][3];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lsum += __shfl_down_sync(0xffffffffu, lsum, o);
+    d0 += __shfl_down_sync(0xffffffffu, d0, o);
+    d1 += __shfl_down_sync(0xffffffffu, d1, o);
+    d2 += __shfl_down_sync(0xffffffffu, d2, o);
+  }
+  const int w = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) { s_l[w] = lsum; s_d[w][0] = d0; s_d[w][1] = d1; s_d[w][2] = d2; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double L = 0.0; float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    for (int q = 0; q < (int)(blockDim.x >> 5); ++q) { L += s_l[q]; a0 += s_d[q][0]; a1 += s_d[q][1]; a2 += s_d[q][2]; }
+    if (loss && c) atomicAdd(loss, L);
+    if (db && dz16) { atomicAdd(db, a0); atomicAdd(db + 1, a1); atomicAdd(db + 2, a2); }
+  }
+}
+
 }  // namespace unreal
 
 using namespace unreal;
@@ -812,5 +871,20 @@ extern "C" int unreal_a3c_head_bwd(const float* h, const float* wp, const float*
   const int grid = (int)(want < (int64_t)sms * 2 ? want : (int64_t)sms * 2);
   a3c_head_bwd_kernel<<<grid, 256, 0, as_stream(stream)>>>(h, wp, wv, dz, dv, go2, m, a, dh, dwp, dbp, dwv, dbv);
   UNREAL_LAUNCH_CHECK("a3c_head_bwd_kernel");
+  return UNREAL_OK;
+}
+
+extern "C" int unreal_rp_loss(const float* logits8, const float* bias, const float* c, int64_t n, float* p_out, double* loss,
+                              void* dz16, float* db, const float* go, void* stream) {
+  UNREAL_REQUIRE(logits8 && bias && n > 0, "unreal_rp_loss: null buffer or n <= 0");
+  UNREAL_REQUIRE(aligned16(logits8) && aligned16(dz16), "unreal_rp_loss: logits8 / dz16 must be 16-byte aligned");
+  UNREAL_REQUIRE(c != nullptr || (loss == nullptr && dz16 == nullptr), "unreal_rp_loss: loss / gradient need the targets");
+  const int sms = sm_count();
+  if (sms <= 0) return UNREAL_ECUDA;
+  int64_t want = (n + 255) / 256;
+  const int grid = (int)(want < (int64_t)sms * 4 ? want : (int64_t)sms * 4);
+  rp_loss_kernel<<<grid, 256, 0, as_stream(stream)>>>(logits8, bias, c, n, p_out, loss, reinterpret_cast<__nv_bfloat16*>(dz16),
+                                                     db, go);
+  UNREAL_LAUNCH_CHECK("rp_loss_kernel");
   return UNREAL_OK;
 }

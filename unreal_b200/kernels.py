@@ -704,6 +704,25 @@ def a3c_head_bwd(h, wp, wv, dz, dv, go2):
   return dh, dwp, dbp, dwv, dbv
 
 
+def rp_loss(logits8, bias, c=None, want_p=False, want_loss=False, want_grad=False, go=None):
+  """Reward-prediction softmax / cross-entropy on logits8 [N,8] f32 (columns 0..2; bias [3] added inside):
+  -> dict(p [N,3], loss f64 [1], dz16 bf16 [N,8], db [3]) with the requested entries."""
+  n = logits8.shape[0]
+  d = logits8.device
+  out = {}
+  if want_p:
+    out["p"] = torch.empty(n, 3, dtype=torch.float32, device=d)
+  if want_loss:
+    out["loss"] = torch.zeros(1, dtype=torch.float64, device=d)
+  if want_grad:
+    out["dz16"] = torch.empty(n, 8, dtype=torch.bfloat16, device=d)
+    out["db"] = torch.zeros(3, dtype=torch.float32, device=d)
+  call("unreal_rp_loss", ptr(logits8, torch.float32, "logits8"), ptr(bias, torch.float32, "bias"), ptr(c, torch.float32, "c"),
+       n, ptr(out.get("p")), ptr(out.get("loss")), ptr(out.get("dz16")), ptr(out.get("db")), ptr(go, torch.float32, "go"),
+       stream_ptr())
+  return out
+
+
 def rollout_lar(last_action, last_reward, num_actions, objective=None, out=None):
   """one-hot(last_action) ++ [last_reward] (++ objective) for every env -> [N, A+1+G] f32."""
   n = last_action.shape[0]

@@ -323,3 +323,28 @@ class A3CHeadLossFn(torch.autograd.Function):
                        g_val.to(torch.float32) if g_val is not None else zero)).contiguous()
     dh, dwp, dbp, dwv, dbv = K.a3c_head_bwd(h, wp, wv1, dz, dv, go2)
     return (dh, dwp, dbp, None if dwv is None else dwv.view(256, 1), dbv, None, None, None, None, None, None)
+
+
+class RpHeadLossFn(torch.autograd.Function):
+  """The reward-prediction head and its loss as ONE autograd node (model.py:479-488 fc 7776 -> 3 + softmax, :571-575
+  cross-entropy with the clipped probabilities): the fc is the tcgen05 GEMM over a bf16 shadow of W_rp padded to 8
+  columns (`w8`, [7776, 8]; TMA needs 16-byte rows), split-K so that the 64 row tiles of a 8192-sample batch fill the
+  SMs; `unreal_rp_loss` adds the bias and does softmax, loss and d loss / d logits (as the bf16 [N,8] GEMM operand, with
+  the bias gradient) in one pass.  Backward: dh2 = dz . W^T and dW = h2^T . dz are two more tcgen05 GEMMs."""
+
+  @staticmethod
+  def forward(ctx, h2_16, w8, w32, b32, c):
+    n = h2_16.shape[0]
+    logits8 = K.gemm_bf16(h2_16, w8, b_mn_major=True, split_k=split_k_for(n, 8, h2_16.shape[1]))
+    out = K.rp_loss(logits8, b32, c, want_loss=True)
+    ctx.save_for_backward(h2_16, w8, logits8, b32, c)
+    return out["loss"][0].to(torch.float32)
+
+  @staticmethod
+  def backward(ctx, go):
+    h2_16, w8, logits8, b32, c = ctx.saved_tensors
+    out = K.rp_loss(logits8, b32, c, want_grad=True, go=go.to(torch.float32).reshape(1).contiguous())
+    dz16 = out["dz16"]
+    dh2 = K.gemm_bf16(dz16, w8, out_dtype=torch.bfloat16) if ctx.needs_input_grad[0] else None     # [N,8] . [7776,8]^T
+    dw = _wgrad(h2_16, dz16)[:, :3].contiguous()
+    return dh2, None, dw, out["db"], None

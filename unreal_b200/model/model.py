@@ -26,7 +26,7 @@ import torch
 
 from .. import _lib
 from .. import kernels as K
-from .layers import A3CHeadLossFn, ConvFn, Deconv8Fn, EncoderFn, LinearFn, LstmFn, PcHeadLossFn, PcLossFn
+from .layers import A3CHeadLossFn, ConvFn, Deconv8Fn, EncoderFn, LinearFn, LstmFn, PcHeadLossFn, PcLossFn, RpHeadLossFn, split_k_for
 
 
 def _variable_specs(A, G, use_pc, use_rp):
@@ -137,6 +137,11 @@ class UnrealModel(object):
         self.taps1.copy_(t1); self.taps2[0].copy_(t2); self.taps2[1].copy_(d2)
     else:
       self.taps1 = self.taps2 = None
+    if self._use_reward_prediction:
+      # W_rp [7776,3] as a bf16 [7776,8] shadow (zero columns 3..7): the B operand of the head's tcgen05 GEMM
+      if getattr(self, "rp_w8", None) is None:
+        self.rp_w8 = torch.zeros(7776, 8, dtype=torch.bfloat16, device=self._device)
+      self.rp_w8[:, :3].copy_(self.v16["W_rp_fc1"])
     if self._use_pixel_change:
       # merged 8-channel shadow of the two pixel-control deconv filters: channel 0 = value, 1..A = advantages
       A = self._action_size
@@ -356,11 +361,16 @@ class UnrealModel(object):
     with torch.no_grad():
       return self._rp_c(self._views(self.flat), state_history)
 
-  def _rp_c(self, p32, images):
+  def _rp_features(self, p32, images):
+    """model.py:475-480: the three frames' conv features, concatenated -> bf16 [N, 7776]."""
     n = images.shape[0]
-    h2 = self._encoder(p32, images.reshape(n * 3, *images.shape[2:]))
-    logits = h2.reshape(n, 7776).float() @ p32["W_rp_fc1"] + p32["b_rp_fc1"]
-    return torch.softmax(logits, dim=-1)
+    return self._encoder(p32, images.reshape(n * 3, *images.shape[2:])).reshape(n, 7776)
+
+  def _rp_c(self, p32, images):
+    """model.py:482-488 on the device path: tcgen05 GEMM on the padded weight shadow + fused bias / softmax."""
+    h2 = self._rp_features(p32, images)
+    logits8 = K.gemm_bf16(h2, self.rp_w8, b_mn_major=True, split_k=split_k_for(h2.shape[0], 8, 7776))
+    return K.rp_loss(logits8, p32["b_rp_fc1"].contiguous(), want_p=True)["p"]
 
   # ---- losses (model.py:490-598) -------------------------------------------------------
   def loss(self, feed):
@@ -421,8 +431,8 @@ class UnrealModel(object):
       total = total + parts["vr"]
     if self._use_reward_prediction and "rp" in feed:
       f = feed["rp"]
-      c = self._rp_c(p32, f["images"]).clamp(1e-20, 1.0)
-      parts["rp"] = -(f["c"] * torch.log(c)).sum()
+      parts["rp"] = RpHeadLossFn.apply(self._rp_features(p32, f["images"]), self.rp_w8, p32["W_rp_fc1"], p32["b_rp_fc1"],
+                                       f["c"].to(torch.float32).contiguous())
       total = total + parts["rp"]
     return total, parts
 
