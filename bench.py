@@ -49,6 +49,9 @@ def parse():
   p.add_argument("--impl", default="b200", choices=["b200", "reference"])
   p.add_argument("--obs-dtype", default="f32", choices=["f32", "u8"])
   p.add_argument("--envs-per-gpu", type=int, default=ENVS_PER_GPU)
+  p.add_argument("--window-kernel", default="auto", choices=["auto", "on", "off"],
+                 help="K1 as ONE launch over the T steps of a pass (the T actions are inputs) instead of T launches; "
+                      "auto: on for u8 frames, off for f32")
   p.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
   p.add_argument("--no-cpu-baseline", action="store_true")
   p.add_argument("--no-agent", action="store_true", help="skip the full-agent (configs[2]) side measurement")
@@ -65,6 +68,7 @@ def workload_config(args):
       "workload": "configs[1]: %d batched maze envs per GPU, fused step/render/pixel-change (K1) x %d + "
                   "20-step n-step returns/advantages (K3) + PC Q-targets (K4)" % (args.envs_per_gpu, ROLLOUT),
       "envs_per_gpu": args.envs_per_gpu, "rollout_len": ROLLOUT, "obs_dtype": args.obs_dtype,
+      "k1_launches_per_pass": "1 (window kernel)" if (args.window_kernel == "on" or (args.window_kernel == "auto" and args.obs_dtype == "u8")) else str(ROLLOUT),
       "gamma": 0.99, "gamma_pc": 0.9,
       "l2": "every pass writes a %.1f GB rollout buffer (obs+pc+targets), far larger than the 126 MB L2" % (
           args.envs_per_gpu * ROLLOUT * (K1_BYTES[args.obs_dtype] + 1600) / 1e9),
@@ -258,6 +262,10 @@ def measure_agent(torch, dist, dev, rank, world, envs, updates, history=2000, ob
           "updates_per_s": updates / (ms * 1e-3), "ring_fill_s": fill_s, "params": net.num_parameters,
           "finite": bool(all(np.isfinite(v) for v in losses.values())), "grad_norm": losses.get("grad_norm"),
           "peak_mem_gb": mem, "update_cuda_graph": tr._ugraph is not None,
+          "update_graph_mode": ("none (eager)" if tr._ugraph is None else
+                                "one graph incl. the NCCL exchange" if (world > 1 and tr.nccl_in_graph) else
+                                "graph A (fwd+bwd) + eager NCCL exchange around K6 (5 launches) + graph B (shadow refresh)"
+                                if world > 1 else "one graph"),
           "timing": "CUDA events around %d Trainer.process() calls, max over ranks" % updates,
           "nccl_parity": nccl_parity}
 
@@ -351,6 +359,124 @@ def parity_check(torch, eng, envs=64):
     return "error: " + repr(e)[:200], ""
 
 
+def measure_pc_stress(torch, dev, peak, seq=50000, dtype_name="u8"):
+  """BASELINE configs[3]: pixel-control target stress -- synthetic 84x84x3 frame stream (u8, scaled by /255 on load like
+  lab / indoor / gym frames), 20x20 cells, n = 20, gamma_pc = 0.9, 1 M frames per batch: K2 (stream pixel change, every
+  frame read from HBM once) + K4 (PC Q-target scan).  Frames/s and the fraction of measured HBM on SURVEY 8(d)'s bytes."""
+  from unreal_b200 import kernels as K
+  L = 20
+  dtype = torch.uint8 if dtype_name == "u8" else torch.float32
+  g = torch.Generator(device=dev).manual_seed(0)
+  frames = torch.empty(seq, L + 1, 84, 84, 3, dtype=dtype, device=dev)
+  for i in range(0, seq, 2500):
+    chunk = frames[i:i + 2500]
+    chunk.copy_(torch.randint(0, 256, chunk.shape, dtype=torch.uint8, device=dev, generator=g) if dtype == torch.uint8
+                else torch.rand(chunk.shape, device=dev, generator=g))
+  boot = torch.rand(seq, 20, 20, device=dev, generator=g)
+  pc = torch.empty(seq, L, 20, 20, device=dev)
+  pc_t = torch.empty(L, seq, 20, 20, device=dev)
+  tgt = torch.empty(L, seq, 20, 20, device=dev)
+
+  def timed(fn, iters=5):
+    for _ in range(3):
+      fn()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+      fn()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    return e0.elapsed_time(e1) / iters * 1e-3
+
+  n_frames = seq * L
+  t2 = timed(lambda: K.pixel_change_stream(frames, pc))
+  b2 = seq * (L + 1) * 21168 * frames.element_size() + n_frames * 1600
+  pc_t.copy_(pc.transpose(0, 1))
+  t4 = timed(lambda: K.pc_targets(pc_t, None, None, boot, 0.9, tgt))
+  b4 = n_frames * 3200 + seq * 1600
+  checksum = float(tgt[:, :64].double().sum())
+  del frames, pc, pc_t, tgt
+  torch.cuda.empty_cache()
+  return {"workload": "configs[3]: %d sequences x (20+1) %s frames 84x84x3 = %d frames per batch (%.1f GB resident, >> L2), "
+                      "K2 stream pixel change + K4 PC Q-targets, gamma_pc 0.9" % (seq, dtype_name, n_frames, b2 / 1e9),
+          "frames": n_frames, "value": n_frames / (t2 + t4), "unit": "frames/s", "ms_per_batch": (t2 + t4) * 1e3,
+          "k2": {"ms": t2 * 1e3, "frames_per_s": n_frames / t2, "gbs": b2 / t2 / 1e9, "frac": b2 / t2 / 1e9 / peak,
+                 "algorithmic_bytes_per_frame": b2 / n_frames},
+          "k4": {"ms": t4 * 1e3, "gbs": b4 / t4 / 1e9, "frac": b4 / t4 / 1e9 / peak},
+          "pass_gbs": (b2 + b4) / (t2 + t4) / 1e9, "pass_frac": (b2 + b4) / (t2 + t4) / 1e9 / peak,
+          "target": "SURVEY 8(d): >= 0.6 of measured HBM (>= 150 M u8 frames/s)", "checksum_tgt": checksum}
+
+
+def measure_a3c(torch, dist, dev, rank, world, envs=1024, iters=10):
+  """BASELINE configs[4] per GPU: MINOS-shaped synthetic observations (u8 84x84 RGB; the reference model consumes no depth
+  channel), 3 pointgoal actions, goal vector G = 2, A3C-LSTM forward/backward + shared RMSProp on
+  `envs` envs x T = 20 per GPU (batch 8192 x T over 8 GPUs).  The update replays CUDA graphs; under NCCL the gradient
+  exchange sits between graph A (fwd+bwd) and graph B (shadow refresh)."""
+  from unreal_b200 import _lib
+  from unreal_b200.model.model import UnrealModel
+  from unreal_b200.train.rmsprop_applier import RMSPropApplier
+  N, T, A, G = envs, 20, 3, 2
+  m = UnrealModel(A, G, -1, True, False, False, False, 0.05, 0.001, dev, {'segnet_mode': 0}, (84, 84), True, 0, 0.0, 0.0,
+                  num_envs=N, seed=0)
+  ap = RMSPropApplier(7e-4, decay=0.99, momentum=0.0, epsilon=0.1, clip_norm=40.0)
+  g = torch.Generator(device=dev).manual_seed(rank)
+  img = torch.randint(0, 256, (T, N, 84, 84, 3), dtype=torch.uint8, device=dev, generator=g)
+  lar = torch.zeros(T, N, A + 1 + G, device=dev)
+  lar.scatter_(2, torch.randint(0, A, (T, N, 1), device=dev, generator=g), 1.0)
+  lar[..., A + 1:] = torch.rand(T, N, G, device=dev, generator=g)
+  a = torch.zeros(T, N, A, device=dev).scatter_(2, torch.randint(0, A, (T, N, 1), device=dev, generator=g), 1.0)
+  feed = {"base": dict(images=img, lar=lar, a=a, adv=torch.randn(T, N, device=dev, generator=g),
+                       R=torch.randn(T, N, device=dev, generator=g), mask=torch.ones(T, N, device=dev),
+                       c0=torch.zeros(N, 256, device=dev), h0=torch.zeros(N, 256, device=dev))}
+  lr = torch.full((1,), 7e-4, device=dev)
+  for _ in range(3):
+    out = m.update(feed, lr, ap)
+  torch.cuda.synchronize(dev)
+  ga = torch.cuda.CUDAGraph()
+  if world == 1:
+    with _lib.graph_capture(ga):
+      out = m.update(feed, lr, ap)
+    step = ga.replay
+    mode = "one graph"
+  else:
+    with _lib.graph_capture(ga):
+      total, parts, grad = m.update_gradient(feed)
+    gb = torch.cuda.CUDAGraph()
+    with _lib.graph_capture(gb):
+      m.refresh_shadow()
+    out = {"total": total}
+
+    def step():
+      ga.replay(); ap.apply_flat_to(m.flat, grad, lr); gb.replay()
+    mode = "graph A (fwd+bwd) + eager NCCL exchange around K6 + graph B (shadow refresh)"
+  for _ in range(2):
+    step()
+  if world > 1:
+    dist.barrier()
+  torch.cuda.synchronize(dev)
+  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  e0.record()
+  for _ in range(iters):
+    step()
+  e1.record()
+  if world > 1:
+    dist.barrier()
+  torch.cuda.synchronize(dev)
+  t_ms = torch.tensor([e0.elapsed_time(e1) / iters], dtype=torch.float64, device=dev)
+  if world > 1:
+    dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+  ms = float(t_ms)
+  samples = N * T * world
+  return {"workload": "configs[4]: %d envs x T=20 per GPU (batch %d x 20 over %d GPU%s), u8 84x84x3 synthetic indoor-shaped frames, "
+                      "A=3, goal vector G=2, A3C-LSTM fwd/bwd + %sfused clip+RMSProp" % (
+                          N, N * world, world, "s" if world > 1 else "", "NCCL-sharded " if world > 1 else ""),
+          "value": samples / (ms * 1e-3), "unit": "samples/s", "ms_per_update": ms, "update_graph_mode": mode,
+          "model_tflops": samples * 18.5e6 / (ms * 1e-3) / 1e12,
+          "frac_of_sustained_bf16_peak_per_gpu": samples * 18.5e6 / (ms * 1e-3) / 1e12 / 1393.1 / world,
+          "finite": bool(torch.isfinite(out["total"])), "params": m.num_parameters}
+
+
 def agent_cpu_baseline(envs=4, seconds=10.0):
   """the reference algorithm with a PyTorch-CPU learner (TensorFlow cannot run here):
   the oracle's env + replay + target path feeding oracle/model_oracle.py's forward/backward and the
@@ -425,7 +551,9 @@ def run_b200(args):
   _lib.require_device()
   n, t = args.envs_per_gpu, ROLLOUT
   obs_dtype = torch.float32 if args.obs_dtype == "f32" else torch.uint8
-  eng = RolloutTargets(n, t, 0.99, 0.9, obs_dtype, dev, auto_reset=True, use_graphs=True)
+  eng = RolloutTargets(n, t, 0.99, 0.9, obs_dtype, dev, auto_reset=True, use_graphs=True,
+                       window_kernel={"auto": None, "on": True, "off": False}[args.window_kernel])
+  window = eng.window_kernel
   g = torch.Generator(device=dev).manual_seed(1234 + rank)
   eng.actions.copy_(torch.randint(0, 4, (t, n), device=dev, dtype=torch.int32, generator=g))
   eng.values.copy_(torch.randn(t, n, device=dev, generator=torch.Generator(device=dev).manual_seed(rank)))
@@ -450,7 +578,7 @@ def run_b200(args):
   barrier()
   clocks = sampler.stop()
   total_ms = evs[0][0].elapsed_time(evs[-1][3])
-  k1_ms = sum(e[0].elapsed_time(e[1]) for e in evs) / (K * t)
+  k1_ms = sum(e[0].elapsed_time(e[1]) for e in evs) / (K * (1 if window else t))    # per K1 launch
   k3_ms = sum(e[1].elapsed_time(e[2]) for e in evs) / K
   k4_ms = sum(e[2].elapsed_time(e[3]) for e in evs) / K
 
@@ -484,6 +612,26 @@ def run_b200(args):
     except Exception as e:  # the side measurement must never cost the headline line
       agent = {"error": repr(e)[:300]}
 
+  side = {}
+  if not args.no_agent:
+    peak_gbs = 6535.7
+    try:
+      with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+        peak_gbs = float(json.load(f).get("hbm_gbs", peak_gbs))
+    except Exception:
+      pass
+    try:
+      torch.cuda.empty_cache()
+      side["a3c"] = measure_a3c(torch, dist, dev, rank, world)
+    except Exception as e:
+      side["a3c"] = {"error": repr(e)[:300]}
+    if world == 1:
+      try:
+        torch.cuda.empty_cache()
+        side["pc_stress"] = measure_pc_stress(torch, dev, peak_gbs)
+      except Exception as e:
+        side["pc_stress"] = {"error": repr(e)[:300]}
+
   times = torch.tensor([total_ms, e2e_ms], device=dev, dtype=torch.float64)
   if world > 1:
     dist.all_reduce(times, op=dist.ReduceOp.MAX)
@@ -500,7 +648,7 @@ def run_b200(args):
     except Exception:
       pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    k1_bytes = n * K1_BYTES[args.obs_dtype]
+    k1_bytes = n * K1_BYTES[args.obs_dtype] * (t if window else 1)
     achieved = k1_bytes / (k1_ms * 1e-3) / 1e9
     path_bytes = steps_per_pass * (K1_BYTES[args.obs_dtype] + K3_BYTES_PER_ENV_STEP + K4_BYTES_PER_ENV_STEP)
     line = {
@@ -513,7 +661,9 @@ def run_b200(args):
                        "pipelined around the phases on a second stream; frames, pixel-change maps and PC "
                        "targets stay in HBM for the learner)", "checksum_R": checksum},
         "gpu_launches": K * launches_per_pass, "parity_check": parity, "parity_check_what": parity_what,
-        "roofline": {"bound": "hbm", "kernel": "maze_cta_kernel (K1)" if args.obs_dtype == "f32" else "maze_warp_kernel (K1)",
+        "roofline": {"bound": "hbm", "kernel": ("maze_window_%s_kernel (K1, all %d steps of a pass in one launch + the state kernel)" % (
+                         "cta" if args.obs_dtype == "f32" else "warp", t)) if window else (
+                         "maze_cta_kernel (K1)" if args.obs_dtype == "f32" else "maze_warp_kernel (K1)"),
                      "achieved": achieved, "peak": peak,
                      "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650",
                      "unit": "GB/s", "frac": achieved / peak, "traffic": None,
@@ -537,6 +687,7 @@ def run_b200(args):
         except Exception as e:
           agent["cpu_baseline"] = {"error": repr(e)[:200]}
       line["agent"] = agent
+    line.update(side)
     if not args.no_cpu_baseline and world == 1:
       from oracle import cpu_path
       procs = cpu_path.host_cores()

@@ -87,6 +87,14 @@ int unreal_maze_step(int32_t* pos, const int32_t* action /*[N]*/, const uint8_t*
                      float* last_reward, void* obs, int obs_dtype, float* pc, uint64_t* frame_rec,
                      int n, int auto_reset, void* stream);
 
+/* Window form of unreal_maze_step: T <= 32 process() calls of every env in one launch, for callers that hold the T
+ * actions up front (BASELINE configs[1]: the actions are an input of the pass).  action / reward / terminal / frame_rec
+ * are [T,N], obs [T,N,84,84,3] (f32 or u8, nullable), pc [T,N,20,20] (nullable), all time-major; pos / last_action /
+ * last_reward [N] are advanced by the T steps.  Same results as T unreal_maze_step calls without an `active` mask. */
+int unreal_maze_window(int32_t* pos, const int32_t* action, float* reward, uint8_t* terminal, int32_t* last_action,
+                       float* last_reward, void* obs, int obs_dtype, float* pc, uint64_t* frame_rec, int n, int t,
+                       int auto_reset, void* stream);
+
 /* _get_current_image (:93-96) for M cells: pos [M,2] -> obs [M,84,84,3]. Used to
  * re-materialise frames sampled from the compact replay ring. */
 int unreal_maze_render(const int32_t* pos, void* obs, int obs_dtype, int m, void* stream);

@@ -111,10 +111,13 @@ def _check_pass(eng, out, oracle, actions, values, boot, boot_q, table, host):
 
 @pytest.mark.parametrize("obs_dtype", [torch.float32, torch.uint8], ids=["f32", "u8"])
 @pytest.mark.parametrize("host", [False, True], ids=["run_device", "run_host"])
-def test_benched_rollout_targets_match_the_oracle(obs_dtype, host):
+@pytest.mark.parametrize("window", [False, True], ids=["k1-per-step", "k1-window"])
+def test_benched_rollout_targets_match_the_oracle(obs_dtype, host, window):
+  """`window`: K1 as T per-step launches, or as ONE launch over the T steps (unreal_maze_window: every work item
+  re-simulates its env's integer steps from the window's start state) -- bench.py's default for u8 frames."""
   from unreal_b200.train.rollout import RolloutTargets
   dev = torch.device("cuda", 0)
-  eng = RolloutTargets(N, T, GAMMA, GAMMA_PC, obs_dtype, dev, auto_reset=True, use_graphs=True)
+  eng = RolloutTargets(N, T, GAMMA, GAMMA_PC, obs_dtype, dev, auto_reset=True, use_graphs=True, window_kernel=window)
   table = _frame_table(obs_dtype, dev)
   oracle = _OracleBatch(N)
   rs = np.random.RandomState(42 + int(host))
@@ -146,7 +149,7 @@ def test_benched_rollout_sees_episode_ends():
   from unreal_b200.train.rollout import RolloutTargets
   dev = torch.device("cuda", 0)
   n = 256
-  eng = RolloutTargets(n, T, GAMMA, GAMMA_PC, torch.float32, dev, auto_reset=True, use_graphs=True)
+  eng = RolloutTargets(n, T, GAMMA, GAMMA_PC, torch.float32, dev, auto_reset=True, use_graphs=True, window_kernel=True)
   # S=(0,2) -> down to (0,6)... find a shortest path with the oracle's own move function (BFS)
   from collections import deque
   prev = {O.START: None}

@@ -42,6 +42,7 @@ SIGNATURES = {
     "unreal_maze_get_layout": (c_int, [POINTER(c_int)] * 4 + [POINTER(c_uint8)]),
     "unreal_maze_reset": (c_int, [P, P, P, P, c_int, P]),
     "unreal_maze_step": (c_int, [P, P, P, P, P, P, P, P, c_int, P, P, c_int, c_int, P]),
+    "unreal_maze_window": (c_int, [P, P, P, P, P, P, P, c_int, P, P, c_int, c_int, c_int, P]),
     "unreal_maze_render": (c_int, [P, P, c_int, c_int, P]),
     "unreal_maze_pixel_change": (c_int, [P, P, P, c_int, P]),
     "unreal_pixel_change": (c_int, [P, P, c_int, P, c_int, c_int, c_int, c_int, P]),
@@ -181,8 +182,13 @@ def graph_capture(graph):
   gc.collect()
   was_enabled = gc.isenabled()
   gc.disable()
+  # with a process group alive, NCCL's watchdog thread polls CUDA events while we capture: in the default global mode
+  # any such call from another thread can invalidate (or, with collectives inside the capture, stall) it; thread-local
+  # mode scopes the capture's restrictions to this thread
+  import torch.distributed as dist
+  mode = "thread_local" if (dist.is_available() and dist.is_initialized()) else "global"
   try:
-    with torch.cuda.graph(graph):
+    with torch.cuda.graph(graph, capture_error_mode=mode):
       yield
   finally:
     if was_enabled:

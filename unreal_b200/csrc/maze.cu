@@ -328,6 +328,139 @@ __global__ void __launch_bounds__(kThreads) maze_cta_kernel(StepArgs a) {
 
 
 // ------------------------------------------------------------------------------------
+// Window form: T rollout steps of every env in ONE launch, for callers that hold the T actions up front (scripted
+// policies, re-simulation of recorded trajectories, BASELINE configs[1] whose actions are an input of the pass).
+// Work item b = t*N + e writes step t of env e into the time-major [T,N,...] buffers, in the same address order as T
+// per-step launches -- but without the T launch ramps / drains and without the inter-launch dependency on the state:
+// every item re-simulates its env's integer steps 0..t-1 from the window's start state (t <= 31 iterations of a few
+// instructions, all lanes of a warp in lock step, actions fetched by lanes 0..t in one load and broadcast by shuffle)
+// and then performs step t exactly like env_logic.  The start state is only READ here; maze_window_state_kernel
+// (one thread per env, launched after) advances pos / last_action / last_reward by the T steps.
+// ------------------------------------------------------------------------------------
+struct WindowArgs {
+  const int32_t* pos;
+  const int32_t* last_action;
+  const float* last_reward;
+  const int32_t* action;   // [T,N]
+  float* reward;           // [T,N]
+  uint8_t* terminal;       // [T,N]
+  void* obs;               // [T,N,84,84,3] (nullable)
+  float* pc;               // [T,N,20,20]   (nullable)
+  uint64_t* rec;           // [T,N]         (nullable)
+  int n, t, auto_reset;
+};
+
+struct MazeCursor { int x, y, la; float lr; };
+
+__device__ __forceinline__ void cursor_advance(MazeCursor& c, const MazeStep& s, int act, int auto_reset) {
+  if (s.terminal && auto_reset) { c.x = c_maze.start_x; c.y = c_maze.start_y; c.la = 0; c.lr = 0.f; }
+  else { c.x = s.x1; c.y = s.y1; c.la = act; c.lr = (float)s.reward; }
+}
+
+// executed by all 32 lanes of a warp (uniform control flow); lane 0 writes the small outputs of item (t, e)
+__device__ __forceinline__ EnvInfo window_logic(const WindowArgs& a, int e, int t, int lane) {
+  const int mine = (lane <= t) ? a.action[(size_t)lane * a.n + e] : 0;
+  MazeCursor c{a.pos[2 * e], a.pos[2 * e + 1], a.last_action[e], a.last_reward[e]};
+  for (int s = 0; s < t; ++s) {
+    const int act = __shfl_sync(0xffffffffu, mine, s);
+    cursor_advance(c, maze_step_core(c_maze, c.x, c.y, act), act, a.auto_reset);
+  }
+  const int act = __shfl_sync(0xffffffffu, mine, t);
+  const MazeStep st = maze_step_core(c_maze, c.x, c.y, act);
+  const size_t b = (size_t)t * a.n + e;
+  if (lane == 0) {
+    if (a.rec) a.rec[b] = frame_pack(c.x, c.y, st.x1, st.y1, act, st.reward, st.terminal, c.la, (int)c.lr);
+    a.reward[b] = (float)st.reward;
+    a.terminal[b] = (uint8_t)st.terminal;
+  }
+  EnvInfo o;
+  o.x0 = c.x; o.y0 = c.y; o.x1 = st.x1; o.y1 = st.y1; o.live = 1;
+  const bool reset = st.terminal && a.auto_reset;
+  o.rx = reset ? c_maze.start_x : st.x1;
+  o.ry = reset ? c_maze.start_y : st.y1;
+  return o;
+}
+
+__global__ void maze_window_state_kernel(int32_t* pos, int32_t* last_action, float* last_reward,
+                                         const int32_t* __restrict__ action, int n, int t, int auto_reset) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  MazeCursor c{pos[2 * e], pos[2 * e + 1], last_action[e], last_reward[e]};
+  for (int s = 0; s < t; ++s) {
+    const int act = action[(size_t)s * n + e];
+    cursor_advance(c, maze_step_core(c_maze, c.x, c.y, act), act, auto_reset);
+  }
+  pos[2 * e] = c.x; pos[2 * e + 1] = c.y; last_action[e] = c.la; last_reward[e] = c.lr;
+}
+
+// one CTA per item, the render of maze_cta_kernel
+template <typename T, int kThreads>
+__global__ void __launch_bounds__(kThreads) maze_window_cta_kernel(WindowArgs a) {
+  __shared__ EnvInfo s_info;
+  constexpr int kChunksPerGroup = 63;
+  constexpr int R = kThreads / kChunksPerGroup;
+  constexpr int G = Chunk<T>::kGroupsPerBand;
+  constexpr int kGroups = G * UNREAL_MAZE_GRID;
+  const int tid = threadIdx.x;
+  const size_t b = blockIdx.x;
+  const int t = (int)(b / a.n), e = (int)(b - (size_t)t * a.n);
+  if (tid < 32) {
+    const EnvInfo f = window_logic(a, e, t, tid);
+    if (tid == 0) s_info = f;
+  }
+  const int gsub = tid / kChunksPerGroup;
+  const int c = tid - gsub * kChunksPerGroup;
+  const ChunkMasks m = make_masks<T>(c);
+  __syncthreads();
+  const EnvInfo f = s_info;
+  if (a.pc != nullptr && tid >= kThreads - kPcElems / 4) write_pc(a.pc + b * kPcElems, f, tid - (kThreads - kPcElems / 4));
+  if (a.obs == nullptr || gsub >= R) return;
+  uint4* out = reinterpret_cast<uint4*>(reinterpret_cast<T*>(a.obs) + b * kFrameElems) + c;
+#pragma unroll
+  for (int j = 0; j < (kGroups + R - 1) / R; ++j) {
+    const int g = gsub + R * j;
+    if (g < kGroups) {
+      const int cy = g / G;
+      __stcs(out + (size_t)g * kChunksPerGroup, band_value(m, c_maze.wall_rows[cy], cy == f.ry, f.rx));
+    }
+  }
+}
+
+// one warp per item, the render of maze_warp_kernel
+template <typename T, int kWarps>
+__global__ void __launch_bounds__(kWarps * 32) maze_window_warp_kernel(WindowArgs a) {
+  const int lane = threadIdx.x & 31;
+  const size_t b = (size_t)blockIdx.x * kWarps + (threadIdx.x >> 5);
+  if (b >= (size_t)a.n * a.t) return;
+  const int t = (int)(b / a.n), e = (int)(b - (size_t)t * a.n);
+  const EnvInfo f = window_logic(a, e, t, lane);
+  if (a.pc != nullptr) {
+    float* pc = a.pc + b * kPcElems;
+#pragma unroll
+    for (int q = lane; q < kPcElems / 4; q += 32) write_pc(pc, f, q);
+  }
+  if (a.obs == nullptr) return;
+  constexpr int G = Chunk<T>::kGroupsPerBand;
+  constexpr int kChunksPerGroup = 63;
+  const ChunkMasks m0 = make_masks<T>(lane);
+  const ChunkMasks m1 = make_masks<T>(lane + 32);
+  const bool has1 = lane + 32 < kChunksPerGroup;
+  uint4* out = reinterpret_cast<uint4*>(reinterpret_cast<T*>(a.obs) + b * kFrameElems) + lane;
+#pragma unroll
+  for (int cy = 0; cy < UNREAL_MAZE_GRID; ++cy) {
+    const uint32_t walls = c_maze.wall_rows[cy];
+    const uint4 v0 = band_value(m0, walls, cy == f.ry, f.rx);
+    const uint4 v1 = band_value(m1, walls, cy == f.ry, f.rx);
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      uint4* p = out + (size_t)(cy * G + g) * kChunksPerGroup;
+      __stcs(p, v0);
+      if (has1) __stcs(p + 32, v1);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------
 // x'' render: the frame directly in the conv1 kernels' input layout (csrc/conv_tcgen05.cu):
 // bf16 planes [6][441][8], x''[q][Y*21+X][e] = frame[4Y+dy, 4X+dx, c] with dy*12+dx*3+c = 8q+e.
 // A 4x4 pixel block lies inside one 12-pixel maze cell, so a plane row is one of three constant
@@ -564,5 +697,38 @@ extern "C" int unreal_maze_pixel_change(const int32_t* pos0, const int32_t* pos1
   long long threads = (long long)m * (kPcElems / 4);
   maze_pc_pairs_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, as_stream(stream)>>>(pos0, pos1, pc, m);
   UNREAL_LAUNCH_CHECK("maze_pc_pairs_kernel");
+  return UNREAL_OK;
+}
+
+extern "C" int unreal_maze_window(int32_t* pos, const int32_t* action, float* reward, uint8_t* terminal, int32_t* last_action,
+                                  float* last_reward, void* obs, int obs_dtype, float* pc, uint64_t* frame_rec, int n, int t,
+                                  int auto_reset, void* stream) {
+  UNREAL_REQUIRE(n >= 0 && t >= 0, "unreal_maze_window: negative size");
+  UNREAL_REQUIRE(t <= 32, "unreal_maze_window: at most 32 steps per window (got %d)", t);
+  UNREAL_REQUIRE(pos && action && reward && terminal && last_action && last_reward,
+                 "unreal_maze_window: pos/action/reward/terminal/last_action/last_reward must be non-null");
+  UNREAL_REQUIRE(obs_dtype == UNREAL_F32 || obs_dtype == UNREAL_U8, "unreal_maze_window: obs_dtype must be f32 or u8");
+  UNREAL_REQUIRE(aligned16(obs) && aligned16(pc), "unreal_maze_window: obs and pc must be 16-byte aligned");
+  UNREAL_REQUIRE((long long)n * t < 2147483647LL / 4, "unreal_maze_window: window too large for one launch");
+  int rc = ensure_map();
+  if (rc) return rc;
+  if (n == 0 || t == 0) return UNREAL_OK;
+  cudaStream_t st = as_stream(stream);
+  WindowArgs a{pos, last_action, last_reward, action, reward, terminal, obs, pc, frame_rec, n, t, auto_reset};
+  const long long items = (long long)n * t;
+  int variant = get_tunable("maze_render_variant", -1);
+  if (variant < 0 || variant == 1) variant = (obs == nullptr || obs_dtype == UNREAL_U8) ? 2 : 0;
+  if (variant == 2) {
+    if (obs_dtype == UNREAL_F32) maze_window_warp_kernel<float, 4><<<(unsigned)((items + 3) / 4), 128, 0, st>>>(a);
+    else if (get_tunable("maze_warps_per_cta", 4) == 8) maze_window_warp_kernel<uint8_t, 8><<<(unsigned)((items + 7) / 8), 256, 0, st>>>(a);
+    else maze_window_warp_kernel<uint8_t, 4><<<(unsigned)((items + 3) / 4), 128, 0, st>>>(a);
+    UNREAL_LAUNCH_CHECK("maze_window_warp_kernel");
+  } else {
+    if (obs_dtype == UNREAL_F32) maze_window_cta_kernel<float, 256><<<(unsigned)items, 256, 0, st>>>(a);
+    else maze_window_cta_kernel<uint8_t, 256><<<(unsigned)items, 256, 0, st>>>(a);
+    UNREAL_LAUNCH_CHECK("maze_window_cta_kernel");
+  }
+  maze_window_state_kernel<<<(n + 127) / 128, 128, 0, st>>>(pos, last_action, last_reward, action, n, t, auto_reset);
+  UNREAL_LAUNCH_CHECK("maze_window_state_kernel");
   return UNREAL_OK;
 }

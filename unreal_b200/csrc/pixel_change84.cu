@@ -10,9 +10,14 @@
 //   cell row: (((m0+m1)+m2)+m3) * 0.25                (mean over the 4 columns first, :90-91)
 //   cell:   (((r0+r1)+r2)+r3) * 0.25                  (then over the 4 rows)
 // so fp32 results are bit-identical to the generic kernel and to the reference's float32 evaluation.
-// u8 pixels are scaled by a shared-memory table of __fdiv_rn(v, 255) (the /255 of
-// lab_environment.py:99-102, correctly rounded), replicated once per bank (index v*32 + lane) so the
-// 96 data-dependent lookups of a cell never conflict (a single 256-entry table measured 3x slower).
+// u8 frames (`pixel_change84_u8_kernel`): a byte becomes the float32 `v / 255` of lab_environment.py:99-102 in four
+// ALU instructions and no memory access -- PRMT drops it into the mantissa of 2^23 (0x4B000000 | v), one FADD
+// removes the 2^23, and v / 255 correctly rounded is  fma(v, hi, RN(v * lo))  with hi = RN(1/255),
+// lo = RN(1/255 - hi): equal to __fdiv_rn(v, 255) for all 256 byte values (checked exhaustively here on the host at
+// library load and by tests/test_gpu_pixel_change.py on the device).  A thread owns one 4x4 cell for a whole
+// sequence and keeps the previous frame's 48 converted values in REGISTERS, so every byte is converted once and
+// the only shared-memory traffic is 16 word loads per cell and frame.  (Round 1 pushed every byte of both frames
+// through a bank-replicated shared-memory table: 192 dependent LDS per cell, LSU-bound at 0.31 of HBM.)
 #include "common.cuh"
 #include "tc05.cuh"
 
@@ -148,6 +153,124 @@ __global__ void __launch_bounds__(Pc84<T, PR>::kThreads) pixel_change84_kernel(c
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// u8 frames: conversion in registers, previous frame kept in registers (see the header comment)
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float u8_over_255(uint32_t word, int byte) {
+  // (float)v exactly: byte -> low mantissa bits of 2^23, minus 2^23
+  const float v = __uint_as_float(__byte_perm(word, 0x4B000000u, 0x7540u | (uint32_t)byte)) - 8388608.0f;
+  const float hi = 0x1.010102p-8f;       // RN(1/255)
+  const float lo = -0x1.fdfdfep-33f;     // RN(1/255 - hi)
+  return __fmaf_rn(v, hi, __fmul_rn(v, lo));
+}
+
+struct Pc84U8 {
+  static constexpr int kRowBytes = kRowElems84;                    // 252
+  static constexpr int kRegionBytes = 80 * kRowBytes;              // rows 2..81
+  static constexpr int kLead = (2 * kRowBytes) % 16;               // 8
+  static constexpr int kCopyBytes = (kLead + kRegionBytes + 15) / 16 * 16;
+  static constexpr int kBufBytes = (kCopyBytes + 127) / 128 * 128;
+  static constexpr int kBufs = 3;
+  static constexpr int kThreads = 416;                             // 400 cells + 16 idle lanes
+  static constexpr int kSmem = kBufs * kBufBytes + 64 + 128;
+  static constexpr int kFrameBytes = 84 * 84 * 3;
+};
+
+// kMinBlocks = 2: two CTAs per SM at 72 registers (a few spills); 1: one CTA per SM, no spills.
+template <int kMinBlocks>
+__global__ void __launch_bounds__(Pc84U8::kThreads, kMinBlocks) pixel_change84_u8_kernel(const Pc84Args g) {
+  using P = Pc84U8;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 127u) & ~127u;
+  const uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t bar0 = base + P::kBufs * P::kBufBytes;
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    for (int b = 0; b < P::kBufs; ++b) mbar_init(bar0 + 8u * b, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  const int items = g.sequences;
+  const int nitems = (items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int per = g.l + 1;
+  const int total = nitems * per;
+  auto issue = [&](int k) {
+    const int itn = k / per, f = k - itn * per;
+    const int s = (int)blockIdx.x + itn * (int)gridDim.x;
+    const uint8_t* frame = f == 0 ? g.p0 + (int64_t)s * g.stride0 : g.p1 + (int64_t)s * g.stride1 + (int64_t)(f - 1) * P::kFrameBytes;
+    const uint8_t* src = frame + 2 * P::kRowBytes - P::kLead;
+    const uint32_t bar = bar0 + 8u * (k % P::kBufs);
+    mbar_arrive_expect_tx(bar, P::kCopyBytes);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(base + (uint32_t)(k % P::kBufs) * P::kBufBytes), "l"(src), "r"(P::kCopyBytes), "r"(bar) : "memory");
+  };
+  if (tid == 0) {
+    if (total > 0) issue(0);
+    if (total > 1) issue(1);
+  }
+  const bool live = tid < 400;
+  const int cell = live ? tid : 0;
+  const int ci = cell / 20, cj = cell - ci * 20;
+  // byte offset of the word holding the cell's first byte (the cell starts 2 bytes into it: (6 + 12 cj) % 4 == 2)
+  const int off0 = P::kLead + 4 * ci * P::kRowBytes + (6 + 12 * cj) - 2;
+  float prev[4][12];
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int e = 0; e < 12; ++e) prev[r][e] = 0.f;
+  for (int k = 0; k < total; ++k) {
+    const int b = k % P::kBufs;
+    mbar_wait(bar0 + 8u * b, (uint32_t)(k / P::kBufs) & 1u);
+    const int itn = k / per, f = k - itn * per;
+    const uint8_t* cur = gen + b * P::kBufBytes + off0;
+    float rows[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const uint32_t* wp = reinterpret_cast<const uint32_t*>(cur + r * P::kRowBytes);
+      const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2], w3 = wp[3];
+      float a[12];
+#pragma unroll
+      for (int e = 0; e < 12; ++e) {
+        const int byte = e + 2;
+        const uint32_t w = (byte >> 2) == 0 ? w0 : ((byte >> 2) == 1 ? w1 : ((byte >> 2) == 2 ? w2 : w3));
+        a[e] = u8_over_255(w, byte & 3);
+      }
+      const float m0 = pc84_pixel(a[0], a[1], a[2], prev[r][0], prev[r][1], prev[r][2]);
+      const float m1 = pc84_pixel(a[3], a[4], a[5], prev[r][3], prev[r][4], prev[r][5]);
+      const float m2 = pc84_pixel(a[6], a[7], a[8], prev[r][6], prev[r][7], prev[r][8]);
+      const float m3 = pc84_pixel(a[9], a[10], a[11], prev[r][9], prev[r][10], prev[r][11]);
+      rows[r] = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(m0, m1), m2), m3), 0.25f);
+#pragma unroll
+      for (int e = 0; e < 12; ++e) prev[r][e] = a[e];      // this frame is the next one's `last_state`
+    }
+    if (f > 0 && live) {
+      const float v = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(rows[0], rows[1]), rows[2]), rows[3]), 0.25f);
+      const int s = (int)blockIdx.x + itn * (int)gridDim.x;
+      __stcs(g.pc + ((int64_t)s * g.l + (f - 1)) * 400 + tid, v);
+    }
+    __syncthreads();                     // every thread has read buffer b: frame k+2... reuses the buffer of k-1
+    if (tid == 0 && k + 2 < total) issue(k + 2);
+  }
+}
+
+template <int kMinBlocks>
+static int launch84_u8(const Pc84Args& g, cudaStream_t st) {
+  using P = Pc84U8;
+  static bool configured = false;
+  auto kern = pixel_change84_u8_kernel<kMinBlocks>;
+  if (!configured) {
+    UNREAL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, P::kSmem));
+    configured = true;
+  }
+  const int sms = sm_count();
+  if (sms <= 0) return UNREAL_ECUDA;
+  const int64_t cap = (int64_t)sms * kMinBlocks;
+  const int grid = (int)(g.sequences < cap ? g.sequences : cap);
+  kern<<<grid, P::kThreads, P::kSmem, st>>>(g);
+  UNREAL_LAUNCH_CHECK("pixel_change84_u8_kernel");
+  return UNREAL_OK;
+}
+
 template <typename T, int PR>
 static int launch84(const Pc84Args& g, cudaStream_t st) {
   using P = Pc84<T, PR>;
@@ -174,7 +297,10 @@ int pixel_change84(const void* p0, int64_t stride0, const void* p1, int64_t stri
   if (!aligned16(p0) || !aligned16(p1)) return -100;
   Pc84Args g{reinterpret_cast<const uint8_t*>(p0), stride0, reinterpret_cast<const uint8_t*>(p1), stride1, pc,
              sequences, l};
-  if (dtype == UNREAL_U8) return launch84<uint8_t, 20>(g, st);
+  if (dtype == UNREAL_U8) {
+    if (get_tunable("pc84_u8_lut", 0) != 0) return launch84<uint8_t, 20>(g, st);   // round-1 table kernel (A/B)
+    return get_tunable("pc84_u8_ctas", 2) == 1 ? launch84_u8<1>(g, st) : launch84_u8<2>(g, st);
+  }
   return launch84<float, 10>(g, st);
 }
 

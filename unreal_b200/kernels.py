@@ -77,6 +77,29 @@ def maze_step(state, action, obs=None, pc=None, reward=None, terminal=None, fram
   return reward, terminal
 
 
+def maze_window(state, actions, obs=None, pc=None, reward=None, terminal=None, frame_rec=None, auto_reset=False):
+  """T process() calls of every env in ONE launch (the T actions are known up front): actions [T,N] i32; obs
+  [T,N,84,84,3] f32 / u8, pc [T,N,20,20], reward / terminal / frame_rec [T,N] are filled when given.  Equal to T
+  maze_step() calls; `state` ends T steps later."""
+  t, n = actions.shape
+  dev = state.device
+  if n != state.n:
+    raise _lib.UnrealError("actions must be [T, %d]" % state.n)
+  if reward is None:
+    reward = torch.empty(t, n, dtype=torch.float32, device=dev)
+  if terminal is None:
+    terminal = torch.empty(t, n, dtype=torch.uint8, device=dev)
+  if obs is not None and (obs.numel() != t * n * FRAME * FRAME * 3 or obs.dtype not in (torch.float32, torch.uint8)):
+    raise _lib.UnrealError("obs must hold [T,N,84,84,3] float32 or uint8")
+  if pc is not None and (pc.numel() != t * n * PC * PC or pc.dtype != torch.float32):
+    raise _lib.UnrealError("pc must be float32 [T,N,20,20]")
+  call("unreal_maze_window", ptr(state.pos, torch.int32), ptr(actions, torch.int32, "actions"), ptr(reward, torch.float32),
+       ptr(terminal, torch.uint8), ptr(state.last_action, torch.int32), ptr(state.last_reward, torch.float32), ptr(obs),
+       _lib.dtype_tag(obs) if obs is not None else _lib.F32, ptr(pc), ptr(frame_rec, torch.int64, "frame_rec"), n, t,
+       1 if auto_reset else 0, stream_ptr())
+  return reward, terminal
+
+
 def obs_shape(dtype):
   """Per-frame shape of a maze observation buffer: [84,84,3] for f32 / u8, the space-to-depth planes
   [6,441,8] for bf16 (the layout conv1 consumes directly), and [2] for int32 -- the agent CELL itself: a maze

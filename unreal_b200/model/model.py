@@ -486,6 +486,15 @@ class UnrealModel(object):
       out['rp'] = dict(images=K.maze_render(f['pos'].contiguous().view(n * 3, 2), dtype=dt).view(n, 3, *shp), c=f['c'])
     return out
 
+  def update_gradient(self, feed, grad_scale=None):
+    """The first half of update(): forward + backward of all heads -> (total, parts, flat gradient).  The learner under
+    NCCL replays this as one CUDA graph and runs the gradient exchange + K6 after it (Trainer._update)."""
+    if 'si' in feed["base"]:
+      feed = self.feed_from_trainer(feed)
+    n = feed["base"]["images"].shape[1]
+    scale = (1.0 / n) if grad_scale is None else grad_scale
+    return self.loss_and_grads(feed, scale)
+
   def update(self, feed, learning_rate, grad_applier, grad_scale=None):
     """One learner step: the reference's `sess.run(apply_gradients, feed_dict)` (trainer.py:543-559)."""
     if 'si' in feed["base"]:

@@ -21,7 +21,7 @@ from .. import kernels as K
 
 class RolloutTargets(object):
   def __init__(self, num_envs, rollout_len=20, gamma=0.99, gamma_pc=0.9, obs_dtype=torch.float32,
-               device="cuda:0", auto_reset=True, use_graphs=True):
+               device="cuda:0", auto_reset=True, use_graphs=True, window_kernel=None):
     self.n = int(num_envs)
     self.t = int(rollout_len)
     self.gamma = float(gamma)
@@ -29,6 +29,12 @@ class RolloutTargets(object):
     self.device = torch.device(device)
     self.auto_reset = auto_reset
     self.use_graphs = use_graphs
+    # the T actions of a pass are inputs, so all T steps can go out as ONE launch (unreal_maze_window) instead of T
+    # K1 launches; default: on for u8 frames (the per-step launch ramp is a third of a 14 us transfer), off for f32
+    # (per-step launches already run at 0.99 of HBM).  Same results either way (tests/test_gpu_rollout_bench_config.py).
+    self.window_kernel = (obs_dtype == torch.uint8) if window_kernel is None else bool(window_kernel)
+    if self.window_kernel and self.t > 32:
+      raise _lib.UnrealError("the window kernel covers at most 32 rollout steps")
     d, n, t = self.device, self.n, self.t
     with torch.cuda.device(d):
       self.state = K.MazeState(n, d)
@@ -55,10 +61,14 @@ class RolloutTargets(object):
   # launches per pass, by kernel
   @property
   def launches_per_pass(self):
-    return self.t + 2
+    return (2 if self.window_kernel else self.t) + 2
 
   # ---- the three phases, eager --------------------------------------------------------
   def _steps(self):
+    if self.window_kernel:
+      K.maze_window(self.state, self.actions, obs=self.obs, pc=self.pc, reward=self.reward, terminal=self.terminal,
+                    frame_rec=self.frame_rec, auto_reset=self.auto_reset)
+      return
     for t in range(self.t):
       K.maze_step(self.state, self.actions[t], obs=self.obs[t], pc=self.pc[t], reward=self.reward[t],
                   terminal=self.terminal[t], frame_rec=self.frame_rec[t], auto_reset=self.auto_reset)

@@ -131,7 +131,10 @@ class Trainer(object):
     self._graph = None
     self.graph_update = True                # with use_graphs: capture the learner update as well (single process)
     self._ugraph = None
+    self._ugraph_b = None
     self._ugraph_out = None
+    import os
+    self.nccl_in_graph = os.environ.get("UNREAL_NCCL_IN_GRAPH", "0") == "1"   # capture the gradient exchange too
     self._lr_dev = None
 
   # -- RandomState hand-over for the single-env drop-in case ---------------------------------
@@ -371,17 +374,21 @@ class Trainer(object):
     return dict(self._graph_feed)
 
   def _update(self, feed, learning_rate):
-    """The learner step (`sess.run(apply_gradients)`, trainer.py:543-559).  With use_graphs and a single
-    process the whole update -- feed conversion, forward, backward, clip + RMSProp, shadow refresh, some
-    hundreds of launches -- is captured ONCE into a CUDA graph over the data phase's static feed tensors
-    and replayed; the annealed learning rate travels through a device scalar that K6 reads when it runs."""
+    """The learner step (`sess.run(apply_gradients)`, trainer.py:543-559).  With use_graphs the whole update -- feed
+    conversion, forward, backward, clip + RMSProp, shadow refresh, some hundreds of launches -- is captured ONCE into
+    CUDA graphs over the data phase's static feed tensors and replayed; the annealed learning rate travels through a
+    device scalar that K6 reads when it runs.  Single process: one graph.  Under NCCL: graph A (forward +
+    backward -> flat gradient), then the exchange step launched eagerly -- reduce-scatter, sum of squares of the shard,
+    8-byte all-reduce, fused clip + RMSProp on the shard, all-gather: five launches -- then graph B (bf16 / tap-major
+    shadow refresh); `nccl_in_graph` captures the collectives as well (one graph, like the single-process case)."""
     net, ap = self.local_network, self.grad_applier
     distributed = ap is not None and getattr(ap, "_world", None) is not None and ap._world()[0] > 1
-    if not (self.use_graphs and self.graph_update) or distributed or self._graph is None:
+    if not (self.use_graphs and self.graph_update) or self._graph is None:
       return net.update(feed, learning_rate, ap)
     if self._lr_dev is None:
       self._lr_dev = torch.zeros(1, dtype=torch.float32, device=self.device)
     self._lr_dev.fill_(float(learning_rate))
+    split = distributed and not self.nccl_in_graph
     if self._ugraph is None:
       if any(feed[k] is not self._graph_feed[k] for k in self._graph_feed):
         return net.update(feed, learning_rate, ap)     # the capturing iteration of the data phase: eager feed
@@ -389,11 +396,25 @@ class Trainer(object):
       out = net.update(static_feed, self._lr_dev, ap)  # this iteration's update, eagerly (also warms every lazy path)
       torch.cuda.synchronize(self.device)
       g = torch.cuda.CUDAGraph()
-      with _lib.graph_capture(g):                      # recorded, not executed
-        self._ugraph_out = net.update(static_feed, self._lr_dev, ap)
-      self._ugraph = g
+      if not split:
+        with _lib.graph_capture(g):                    # recorded, not executed
+          self._ugraph_out = net.update(static_feed, self._lr_dev, ap)
+        self._ugraph = g
+        return out
+      with _lib.graph_capture(g):
+        total, parts, grad = net.update_gradient(static_feed)
+      g2 = torch.cuda.CUDAGraph()
+      with _lib.graph_capture(g2):
+        net.refresh_shadow()
+      self._ugraph, self._ugraph_b = g, g2
+      self._ugraph_out = dict(parts)
+      self._ugraph_out["total"] = total
+      self._ugraph_grad = grad
       return out
     self._ugraph.replay()
+    if split:
+      self._ugraph_out["grad_norm"] = ap.apply_flat_to(net.flat, self._ugraph_grad, self._lr_dev)
+      self._ugraph_b.replay()
     return self._ugraph_out
 
   # -- one iteration  trainer.py:438-636 -------------------------------------------------------
