@@ -107,6 +107,10 @@ int unreal_maze_pixel_change(const int32_t* pos0, const int32_t* pos1, float* pc
  * cur, prev: [M,H,W,C] of dtype (u8 values are divided by 255); pc: [M,(H-4)/4,(W-4)/4] f32. */
 int unreal_pixel_change(const void* cur, const void* prev, int dtype, float* pc, int m, int h, int w,
                         int c, void* stream);
+/* Device self-check of the division-free roundings K2's u8 kernel uses in place of `/ 3` and `/ 255`:
+ * mismatches[0] = floats s in [2^-100, 2^100] (all 2^31 - ... of them, and 0) whose two-instruction s/3 differs from the
+ * correctly rounded quotient; mismatches[1] = (byte value, byte lane) pairs whose v/255 differs.  Both must be 0. */
+int unreal_selfcheck_arith(unsigned long long* mismatches, void* stream);
 /* Environment._subsample (environment.py:88-91) on its own: a [M,H,W] f32 -> out [M,H/width,W/width] f32, the mean
  * over width x width blocks taken like numpy's reshape(...).mean(-1).mean(1): columns of a block row first (left to
  * right, then / width), then the block's rows (top to bottom, then / width).  H and W must be multiples of width. */

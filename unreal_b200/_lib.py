@@ -47,6 +47,7 @@ SIGNATURES = {
     "unreal_maze_pixel_change": (c_int, [P, P, P, c_int, P]),
     "unreal_pixel_change": (c_int, [P, P, c_int, P, c_int, c_int, c_int, c_int, P]),
     "unreal_pixel_change_stream": (c_int, [P, c_int, P, c_int, c_int, c_int, c_int, c_int, P]),
+    "unreal_selfcheck_arith": (c_int, [P, P]),
     "unreal_subsample": (c_int, [P, P, c_int, c_int, c_int, c_int, P]),
     "unreal_nstep_returns": (c_int, [P, P, P, P, c_float, P, P, c_int, c_int, P]),
     "unreal_sequence_returns": (c_int, [P, P, P, c_float, P, c_int, c_int, P]),
@@ -193,3 +194,9 @@ def graph_capture(graph):
   finally:
     if was_enabled:
       gc.enable()
+
+
+# A/B switches for the benchmark scripts without editing them: UNREAL_TUNABLES="name=value,name=value"
+for _kv in filter(None, os.environ.get("UNREAL_TUNABLES", "").split(",")):
+  _k, _, _v = _kv.partition("=")
+  set_tunable(_k.strip(), int(_v))

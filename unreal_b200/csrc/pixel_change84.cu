@@ -56,6 +56,7 @@ __device__ __forceinline__ float pc84_pixel(float a0, float a1, float a2, float 
   // s / 3, correctly rounded, in three FMA-pipe instructions instead of the ~25 of __fdiv_rn:
   // q = s*RN(1/3) corrected by one exact-remainder step.  Checked against __fdiv_rn for EVERY
   // non-negative finite float on the B200 (scripts/probes/div3_probe.cu: 0 mismatches of 2^31-2^23).
+  // (The u8 kernel, which is instruction-bound, uses the two-instruction div3_exact below.)
   const float r = 1.0f / 3.0f;
   const float q = __fmul_rn(s, r);
   return __fmaf_rn(__fmaf_rn(-3.0f, q, s), r, q);
@@ -156,12 +157,30 @@ __global__ void __launch_bounds__(Pc84<T, PR>::kThreads) pixel_change84_kernel(c
 // ---------------------------------------------------------------------------------------------------------------
 // u8 frames: conversion in registers, previous frame kept in registers (see the header comment)
 // ---------------------------------------------------------------------------------------------------------------
+// byte `byte` of `word` -> float32 v / 255, correctly rounded: I2F.U8 with the byte selector (one instruction on the
+// conversion pipe), then fma(v, hi, RN(v * lo)) with hi = RN(1/255), lo = RN(1/255 - hi).  Equal to __fdiv_rn(v, 255)
+// for all 256 values (unreal_selfcheck_arith, tests/test_gpu_pixel_change.py).
 __device__ __forceinline__ float u8_over_255(uint32_t word, int byte) {
-  // (float)v exactly: byte -> low mantissa bits of 2^23, minus 2^23
-  const float v = __uint_as_float(__byte_perm(word, 0x4B000000u, 0x7540u | (uint32_t)byte)) - 8388608.0f;
-  const float hi = 0x1.010102p-8f;       // RN(1/255)
-  const float lo = -0x1.fdfdfep-33f;     // RN(1/255 - hi)
+  const float v = (float)((word >> (8 * byte)) & 0xffu);
+  const float hi = 0x1.010102p-8f;
+  const float lo = -0x1.fdfdfep-33f;
   return __fmaf_rn(v, hi, __fmul_rn(v, lo));
+}
+
+// s / 3 correctly rounded in TWO instructions: fma(s, hi, RN(s * lo)), hi = RN(1/3), lo = RN(1/3 - hi) -- the
+// double-word-constant multiplication.  Equal to __fdiv_rn(s, 3) for every float in [2^-100, 2^100] and for 0
+// (unreal_selfcheck_arith runs all 2^31 of them on the device; the sums here lie in {0} U [2^-9, 3]).
+__device__ __forceinline__ float div3_exact(float s) {
+  const float hi = 0x1.555556p-2f;
+  const float lo = -0x1.555556p-27f;
+  return __fmaf_rn(s, hi, __fmul_rn(s, lo));
+}
+
+__device__ __forceinline__ float pc84_pixel2(float a0, float a1, float a2, float b0, float b1, float b2) {
+  float s = fabsf(__fsub_rn(a0, b0));
+  s = __fadd_rn(s, fabsf(__fsub_rn(a1, b1)));
+  s = __fadd_rn(s, fabsf(__fsub_rn(a2, b2)));
+  return div3_exact(s);
 }
 
 struct Pc84U8 {
@@ -170,23 +189,47 @@ struct Pc84U8 {
   static constexpr int kLead = (2 * kRowBytes) % 16;               // 8
   static constexpr int kCopyBytes = (kLead + kRegionBytes + 15) / 16 * 16;
   static constexpr int kBufBytes = (kCopyBytes + 127) / 128 * 128;
-  static constexpr int kBufs = 3;
-  static constexpr int kThreads = 416;                             // 400 cells + 16 idle lanes
-  static constexpr int kSmem = kBufs * kBufBytes + 64 + 128;
+  static constexpr int kBufs = 4;
+  static constexpr int kComputeWarps = 13;                         // 400 cells + 16 idle lanes
+  static constexpr int kThreads = (kComputeWarps + 1) * 32;        // + the TMA producer warp
+  static constexpr int kSmem = kBufs * kBufBytes + 128 + 128;
   static constexpr int kFrameBytes = 84 * 84 * 3;
 };
 
-// kMinBlocks = 2: two CTAs per SM at 72 registers (a few spills); 1: one CTA per SM, no spills.
-template <int kMinBlocks>
-__global__ void __launch_bounds__(Pc84U8::kThreads, kMinBlocks) pixel_change84_u8_kernel(const Pc84Args g) {
+// one frame of one cell: 4 x 4 word loads, 48 conversions into cur[], the 16 pixel means against prev[]
+__device__ __forceinline__ float pc84_u8_cell(const uint8_t* cellp, float (&cur)[48], const float (&prev)[48]) {
+  float rows[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const uint32_t* wp = reinterpret_cast<const uint32_t*>(cellp + r * Pc84U8::kRowBytes);
+    const uint32_t w[4] = {wp[0], wp[1], wp[2], wp[3]};
+#pragma unroll
+    for (int e = 0; e < 12; ++e) cur[r * 12 + e] = u8_over_255(w[(e + 2) >> 2], (e + 2) & 3);
+    const float* a = cur + r * 12;
+    const float* p = prev + r * 12;
+    const float m0 = pc84_pixel2(a[0], a[1], a[2], p[0], p[1], p[2]);
+    const float m1 = pc84_pixel2(a[3], a[4], a[5], p[3], p[4], p[5]);
+    const float m2 = pc84_pixel2(a[6], a[7], a[8], p[6], p[7], p[8]);
+    const float m3 = pc84_pixel2(a[9], a[10], a[11], p[9], p[10], p[11]);
+    rows[r] = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(m0, m1), m2), m3), 0.25f);
+  }
+  return __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(rows[0], rows[1]), rows[2]), rows[3]), 0.25f);
+}
+
+// Warp-specialised: warp 13 is the TMA producer (one bulk copy per frame into a 4-deep ring, gated by per-buffer `empty`
+// barriers), warps 0..12 own one cell per thread and run free of each other -- a warp waits on `full[b]`, reduces its
+// cells and arrives on `empty[b]`; there is no CTA-wide barrier in the loop.  The previous frame's 48 values ping-pong
+// between two register arrays (frame k in A against B, frame k+1 in B against A: no copies).
+__global__ void __launch_bounds__(Pc84U8::kThreads, 1) pixel_change84_u8_kernel(const Pc84Args g) {
   using P = Pc84U8;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 127u) & ~127u;
   const uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
-  const uint32_t bar0 = base + P::kBufs * P::kBufBytes;
+  const uint32_t full0 = base + P::kBufs * P::kBufBytes;
+  const uint32_t empty0 = full0 + 8u * P::kBufs;
   const int tid = threadIdx.x;
   if (tid == 0) {
-    for (int b = 0; b < P::kBufs; ++b) mbar_init(bar0 + 8u * b, 1);
+    for (int b = 0; b < P::kBufs; ++b) { mbar_init(full0 + 8u * b, 1); mbar_init(empty0 + 8u * b, P::kComputeWarps); }
     fence_mbar_init();
   }
   __syncthreads();
@@ -194,81 +237,92 @@ __global__ void __launch_bounds__(Pc84U8::kThreads, kMinBlocks) pixel_change84_u
   const int nitems = (items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int per = g.l + 1;
   const int total = nitems * per;
-  auto issue = [&](int k) {
-    const int itn = k / per, f = k - itn * per;
-    const int s = (int)blockIdx.x + itn * (int)gridDim.x;
-    const uint8_t* frame = f == 0 ? g.p0 + (int64_t)s * g.stride0 : g.p1 + (int64_t)s * g.stride1 + (int64_t)(f - 1) * P::kFrameBytes;
-    const uint8_t* src = frame + 2 * P::kRowBytes - P::kLead;
-    const uint32_t bar = bar0 + 8u * (k % P::kBufs);
-    mbar_arrive_expect_tx(bar, P::kCopyBytes);
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(base + (uint32_t)(k % P::kBufs) * P::kBufBytes), "l"(src), "r"(P::kCopyBytes), "r"(bar) : "memory");
-  };
-  if (tid == 0) {
-    if (total > 0) issue(0);
-    if (total > 1) issue(1);
+  const int warp = tid >> 5, lane = tid & 31;
+
+  if (warp == P::kComputeWarps) {                      // ---- producer
+    if (lane == 0) {
+      for (int k = 0; k < total; ++k) {
+        const int b = k % P::kBufs;
+        if (k >= P::kBufs) mbar_wait(empty0 + 8u * b, (uint32_t)(k / P::kBufs - 1) & 1u);
+        const int itn = k / per, f = k - itn * per;
+        const int s = (int)blockIdx.x + itn * (int)gridDim.x;
+        const uint8_t* frame = f == 0 ? g.p0 + (int64_t)s * g.stride0 : g.p1 + (int64_t)s * g.stride1 + (int64_t)(f - 1) * P::kFrameBytes;
+        const uint8_t* src = frame + 2 * P::kRowBytes - P::kLead;
+        const uint32_t bar = full0 + 8u * b;
+        mbar_arrive_expect_tx(bar, P::kCopyBytes);
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(base + (uint32_t)b * P::kBufBytes), "l"(src), "r"(P::kCopyBytes), "r"(bar) : "memory");
+      }
+    }
+    return;
   }
-  const bool live = tid < 400;
+
+  const bool live = tid < 400;                         // ---- consumers
   const int cell = live ? tid : 0;
   const int ci = cell / 20, cj = cell - ci * 20;
   // byte offset of the word holding the cell's first byte (the cell starts 2 bytes into it: (6 + 12 cj) % 4 == 2)
   const int off0 = P::kLead + 4 * ci * P::kRowBytes + (6 + 12 * cj) - 2;
-  float prev[4][12];
+  float A[48], B[48];
 #pragma unroll
-  for (int r = 0; r < 4; ++r)
-#pragma unroll
-    for (int e = 0; e < 12; ++e) prev[r][e] = 0.f;
-  for (int k = 0; k < total; ++k) {
+  for (int e = 0; e < 48; ++e) A[e] = B[e] = 0.f;
+  auto step = [&](int k, float (&cur)[48], const float (&prev)[48]) {
     const int b = k % P::kBufs;
-    mbar_wait(bar0 + 8u * b, (uint32_t)(k / P::kBufs) & 1u);
+    mbar_wait(full0 + 8u * b, (uint32_t)(k / P::kBufs) & 1u);
+    const float v = pc84_u8_cell(gen + b * P::kBufBytes + off0, cur, prev);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty0 + 8u * b);       // this warp is done with buffer b
     const int itn = k / per, f = k - itn * per;
-    const uint8_t* cur = gen + b * P::kBufBytes + off0;
-    float rows[4];
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      const uint32_t* wp = reinterpret_cast<const uint32_t*>(cur + r * P::kRowBytes);
-      const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2], w3 = wp[3];
-      float a[12];
-#pragma unroll
-      for (int e = 0; e < 12; ++e) {
-        const int byte = e + 2;
-        const uint32_t w = (byte >> 2) == 0 ? w0 : ((byte >> 2) == 1 ? w1 : ((byte >> 2) == 2 ? w2 : w3));
-        a[e] = u8_over_255(w, byte & 3);
-      }
-      const float m0 = pc84_pixel(a[0], a[1], a[2], prev[r][0], prev[r][1], prev[r][2]);
-      const float m1 = pc84_pixel(a[3], a[4], a[5], prev[r][3], prev[r][4], prev[r][5]);
-      const float m2 = pc84_pixel(a[6], a[7], a[8], prev[r][6], prev[r][7], prev[r][8]);
-      const float m3 = pc84_pixel(a[9], a[10], a[11], prev[r][9], prev[r][10], prev[r][11]);
-      rows[r] = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(m0, m1), m2), m3), 0.25f);
-#pragma unroll
-      for (int e = 0; e < 12; ++e) prev[r][e] = a[e];      // this frame is the next one's `last_state`
-    }
     if (f > 0 && live) {
-      const float v = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(rows[0], rows[1]), rows[2]), rows[3]), 0.25f);
       const int s = (int)blockIdx.x + itn * (int)gridDim.x;
       __stcs(g.pc + ((int64_t)s * g.l + (f - 1)) * 400 + tid, v);
     }
-    __syncthreads();                     // every thread has read buffer b: frame k+2... reuses the buffer of k-1
-    if (tid == 0 && k + 2 < total) issue(k + 2);
+  };
+  for (int k = 0; k < total; k += 2) {
+    step(k, A, B);
+    if (k + 1 < total) step(k + 1, B, A);
   }
 }
 
-template <int kMinBlocks>
 static int launch84_u8(const Pc84Args& g, cudaStream_t st) {
   using P = Pc84U8;
   static bool configured = false;
-  auto kern = pixel_change84_u8_kernel<kMinBlocks>;
   if (!configured) {
-    UNREAL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, P::kSmem));
+    UNREAL_CUDA(cudaFuncSetAttribute(pixel_change84_u8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P::kSmem));
     configured = true;
   }
   const int sms = sm_count();
   if (sms <= 0) return UNREAL_ECUDA;
-  const int64_t cap = (int64_t)sms * kMinBlocks;
-  const int grid = (int)(g.sequences < cap ? g.sequences : cap);
-  kern<<<grid, P::kThreads, P::kSmem, st>>>(g);
+  const int grid = g.sequences < sms ? g.sequences : sms;
+  pixel_change84_u8_kernel<<<grid, P::kThreads, P::kSmem, st>>>(g);
   UNREAL_LAUNCH_CHECK("pixel_change84_u8_kernel");
   return UNREAL_OK;
+}
+
+// Exhaustive device check of the two division-free roundings above against __fdiv_rn.
+__global__ void selfcheck_arith_kernel(unsigned long long* out) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  const uint64_t id = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long bad3 = 0, bad255 = 0;
+  // every float in [2^-100, 2^100): exponent fields 27 .. 226
+  for (uint64_t i = (27ull << 23) + id; i < (227ull << 23); i += stride) {
+    const float s = __uint_as_float((uint32_t)i);
+    if (__float_as_uint(div3_exact(s)) != __float_as_uint(__fdiv_rn(s, 3.0f))) ++bad3;
+  }
+  if (id == 0 && __float_as_uint(div3_exact(0.f)) != 0u) ++bad3;
+  if (id < 256 * 4) {                                   // every byte value in every byte lane of a word
+    const uint32_t v = (uint32_t)(id >> 2), lane_b = (uint32_t)(id & 3);
+    const uint32_t word = (v << (8 * lane_b)) | (0xA5A5A5A5u & ~(0xffu << (8 * lane_b)));
+    float got;
+    switch (lane_b) {
+      case 0: got = u8_over_255(word, 0); break;
+      case 1: got = u8_over_255(word, 1); break;
+      case 2: got = u8_over_255(word, 2); break;
+      default: got = u8_over_255(word, 3); break;
+    }
+    if (__float_as_uint(got) != __float_as_uint(__fdiv_rn((float)v, 255.0f))) ++bad255;
+  }
+  if (bad3) atomicAdd(out, bad3);
+  if (bad255) atomicAdd(out + 1, bad255);
 }
 
 template <typename T, int PR>
@@ -299,9 +353,20 @@ int pixel_change84(const void* p0, int64_t stride0, const void* p1, int64_t stri
              sequences, l};
   if (dtype == UNREAL_U8) {
     if (get_tunable("pc84_u8_lut", 0) != 0) return launch84<uint8_t, 20>(g, st);   // round-1 table kernel (A/B)
-    return get_tunable("pc84_u8_ctas", 2) == 1 ? launch84_u8<1>(g, st) : launch84_u8<2>(g, st);
+    return launch84_u8(g, st);
   }
   return launch84<float, 10>(g, st);
 }
 
 }  // namespace unreal
+
+// mismatches[0]: floats s in [2^-100, 2^100] (and 0) where the two-instruction s/3 differs from __fdiv_rn(s, 3);
+// mismatches[1]: (byte value, byte lane) pairs where the three-instruction v/255 differs from __fdiv_rn(v, 255).
+extern "C" int unreal_selfcheck_arith(unsigned long long* mismatches, void* stream) {
+  UNREAL_REQUIRE(mismatches != nullptr, "unreal_selfcheck_arith: null output");
+  cudaStream_t st = unreal::as_stream(stream);
+  UNREAL_CUDA(cudaMemsetAsync(mismatches, 0, 2 * sizeof(unsigned long long), st));
+  unreal::selfcheck_arith_kernel<<<148 * 8, 256, 0, st>>>(mismatches);
+  UNREAL_LAUNCH_CHECK("selfcheck_arith_kernel");
+  return UNREAL_OK;
+}

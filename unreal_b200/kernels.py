@@ -155,6 +155,13 @@ def pixel_change_stream(frames, out=None):
   return out
 
 
+def selfcheck_arith():
+  """-> (mismatches of the two-instruction s/3 over every float in [2^-100, 2^100], mismatches of v/255 over all bytes)."""
+  out = torch.zeros(2, dtype=torch.int64, device="cuda")
+  call("unreal_selfcheck_arith", ptr(out), stream_ptr())
+  return tuple(int(x) for x in out.tolist())
+
+
 def subsample(a, width, out=None):
   """a [M,H,W] f32 -> [M,H/width,W/width]: Environment._subsample (environment.py:88-91)."""
   m, h, w = a.shape

@@ -23,7 +23,8 @@ from .. import kernels as K
 
 class RMSPropApplier(object):
   def __init__(self, learning_rate, decay=0.9, momentum=0.0, epsilon=1e-10, clip_norm=40.0,
-               device="/cpu:0", name="RMSPropApplier", process_group=None, average_gradients=True):
+               device="/cpu:0", name="RMSPropApplier", process_group=None, average_gradients=True,
+               keep_momentum_slot=True):
     self._name = name
     self._learning_rate = learning_rate
     self._decay = decay
@@ -35,6 +36,10 @@ class RMSPropApplier(object):
     self._vars = None
     self._group = process_group
     self._average = average_gradients
+    # TF's ApplyRMSProp writes the `momentum` slot even when momentum == 0 (mom = lr * g / sqrt(ms + eps), then
+    # var -= mom; rmsprop_applier.py:86-93), and get_slot() can observe it: keep doing so by default (28 B per parameter
+    # instead of 20 B; K6 is latency-bound at P = 1.9 M either way).  False: skip the dead store.
+    self._keep_mom = bool(keep_momentum_slot)
     # the two device kernels (K6).  tests/test_sharded_applier.py swaps in a CPU stand-in to drive
     # the partition + collective plumbing under gloo; the product path is always `kernels`.
     self._ops = K
@@ -171,7 +176,7 @@ class RMSPropApplier(object):
     ops = self._ops
     if world == 1:
       ops.grad_sumsq(self._flat_grad, self._sumsq)
-      ops.rmsprop_update(self._flat_var, self._rms, self._mom if self._momentum != 0.0 else None, self._flat_grad,
+      ops.rmsprop_update(self._flat_var, self._rms, self._mom if (self._momentum != 0.0 or self._keep_mom) else None, self._flat_grad,
                        self._sumsq, lr, self._decay, self._momentum, self._epsilon, self._clip_norm,
                        grad_scale=1.0, grad_norm=self._norm)
       return self._norm
@@ -179,7 +184,7 @@ class RMSPropApplier(object):
     ops.grad_sumsq(self._grad_shard, self._sumsq)
     dist.all_reduce(self._sumsq, op=dist.ReduceOp.SUM, group=self._group)      # 8 bytes
     var_shard = self._flat_var[self._lo:self._lo + self._shard]
-    ops.rmsprop_update(var_shard, self._rms, self._mom if self._momentum != 0.0 else None, self._grad_shard,
+    ops.rmsprop_update(var_shard, self._rms, self._mom if (self._momentum != 0.0 or self._keep_mom) else None, self._grad_shard,
                      self._sumsq, lr, self._decay, self._momentum, self._epsilon, self._clip_norm,
                      grad_scale=(1.0 / world) if self._average else 1.0, grad_norm=self._norm)
     dist.all_gather_into_tensor(self._flat_var, var_shard, group=self._group)
