@@ -51,7 +51,7 @@ def parse():
   p.add_argument("--envs-per-gpu", type=int, default=ENVS_PER_GPU)
   p.add_argument("--window-kernel", default="auto", choices=["auto", "on", "off"],
                  help="K1 as ONE launch over the T steps of a pass (the T actions are inputs) instead of T launches; "
-                      "auto: on for u8 frames, off for f32")
+                      "auto = on")
   p.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
   p.add_argument("--no-cpu-baseline", action="store_true")
   p.add_argument("--no-agent", action="store_true", help="skip the full-agent (configs[2]) side measurement")
@@ -68,7 +68,7 @@ def workload_config(args):
       "workload": "configs[1]: %d batched maze envs per GPU, fused step/render/pixel-change (K1) x %d + "
                   "20-step n-step returns/advantages (K3) + PC Q-targets (K4)" % (args.envs_per_gpu, ROLLOUT),
       "envs_per_gpu": args.envs_per_gpu, "rollout_len": ROLLOUT, "obs_dtype": args.obs_dtype,
-      "k1_launches_per_pass": "1 (window kernel)" if (args.window_kernel == "on" or (args.window_kernel == "auto" and args.obs_dtype == "u8")) else str(ROLLOUT),
+      "k1_launches_per_pass": "1 (window kernel)" if args.window_kernel != "off" else str(ROLLOUT),
       "gamma": 0.99, "gamma_pc": 0.9,
       "l2": "every pass writes a %.1f GB rollout buffer (obs+pc+targets), far larger than the 126 MB L2" % (
           args.envs_per_gpu * ROLLOUT * (K1_BYTES[args.obs_dtype] + 1600) / 1e9),

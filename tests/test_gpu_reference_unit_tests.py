@@ -182,7 +182,10 @@ def test_rmsprop_apply():
   np.testing.assert_allclose(np.array([x, y]), var.cpu().numpy(), rtol=1e-6)
   np.testing.assert_allclose(float(norm), math.sqrt(dx * dx + dy * dy), rtol=1e-6)
   np.testing.assert_allclose(opt.get_slot(var, "rms").cpu().numpy(), [ms_x, ms_y], rtol=1e-6)      # :38-43 rms0 = 1
-  assert torch.equal(opt.get_slot(var, "momentum"), torch.zeros(2, device=dev))                    # momentum0 = 0
+  # the `momentum` slot starts at 0 (:38-43) and, as in TF's ApplyRMSProp, holds the step just taken even with
+  # momentum = 0:  mom = momentum * mom + lr * g / sqrt(ms + eps);  var -= mom
+  np.testing.assert_allclose(opt.get_slot(var, "momentum").cpu().numpy(),
+                             [2.0 * dx / math.sqrt(ms_x + 1.0), 2.0 * dy / math.sqrt(ms_y + 1.0)], rtol=1e-6)
 
   # apply grad1
   opt._apply_gradients([var], [grad1])

@@ -460,6 +460,69 @@ __global__ void __launch_bounds__(kWarps * 32) maze_window_warp_kernel(WindowArg
   }
 }
 
+// Window form, one WARP per env walking its T steps in order (no re-simulation): the warp keeps the env's cursor, its
+// two chunk columns' wall patterns of all 7 bands in registers (they do not depend on the env or the step), and per
+// step only builds the agent band's two words, writes the 20x20 map and streams the frame out -- ~300 integer
+// instructions per 21 KB u8 frame instead of ~1000 (ncu of maze_window_warp_kernel<u8>: ALU pipe 75 % busy at 49 % of
+// DRAM: instruction-bound).  Lane 0 writes the small outputs and, after the last step, the env's state.
+template <typename T, int kWarps>
+__global__ void __launch_bounds__(kWarps * 32) maze_window_env_kernel(WindowArgs a, int32_t* pos_out, int32_t* la_out,
+                                                                      float* lr_out) {
+  const int lane = threadIdx.x & 31;
+  const int e = blockIdx.x * kWarps + (threadIdx.x >> 5);
+  if (e >= a.n) return;
+  constexpr int G = Chunk<T>::kGroupsPerBand;
+  constexpr int kChunksPerGroup = 63;
+  const ChunkMasks m0 = make_masks<T>(lane);
+  const ChunkMasks m1 = make_masks<T>(lane + 32);
+  const bool has1 = lane + 32 < kChunksPerGroup;
+  uint4 w0[UNREAL_MAZE_GRID], w1[UNREAL_MAZE_GRID];
+#pragma unroll
+  for (int cy = 0; cy < UNREAL_MAZE_GRID; ++cy) {
+    w0[cy] = band_value(m0, c_maze.wall_rows[cy], false, 0);
+    w1[cy] = band_value(m1, c_maze.wall_rows[cy], false, 0);
+  }
+  const int mine = (lane < a.t) ? a.action[(size_t)lane * a.n + e] : 0;
+  MazeCursor c{a.pos[2 * e], a.pos[2 * e + 1], a.last_action[e], a.last_reward[e]};
+  for (int t = 0; t < a.t; ++t) {
+    const int act = __shfl_sync(0xffffffffu, mine, t);
+    const MazeStep st = maze_step_core(c_maze, c.x, c.y, act);
+    const size_t b = (size_t)t * a.n + e;
+    if (lane == 0) {
+      if (a.rec) a.rec[b] = frame_pack(c.x, c.y, st.x1, st.y1, act, st.reward, st.terminal, c.la, (int)c.lr);
+      a.reward[b] = (float)st.reward;
+      a.terminal[b] = (uint8_t)st.terminal;
+    }
+    EnvInfo f;
+    f.x0 = c.x; f.y0 = c.y; f.x1 = st.x1; f.y1 = st.y1; f.live = 1;
+    cursor_advance(c, st, act, a.auto_reset);
+    f.rx = c.x; f.ry = c.y;                                  // the frame shows the cell the env is in after the step
+    if (a.pc != nullptr) {
+      float* pc = a.pc + b * kPcElems;
+#pragma unroll
+      for (int q = lane; q < kPcElems / 4; q += 32) write_pc(pc, f, q);
+    }
+    if (a.obs == nullptr) continue;
+    uint4* out = reinterpret_cast<uint4*>(reinterpret_cast<T*>(a.obs) + b * kFrameElems) + lane;
+    const uint4 ag0 = band_value(m0, 0u, true, f.rx), ag1 = band_value(m1, 0u, true, f.rx);   // agent words only
+#pragma unroll
+    for (int cy = 0; cy < UNREAL_MAZE_GRID; ++cy) {
+      uint4 v0 = w0[cy], v1 = w1[cy];
+      if (cy == f.ry) {
+        v0.x |= ag0.x; v0.y |= ag0.y; v0.z |= ag0.z; v0.w |= ag0.w;
+        v1.x |= ag1.x; v1.y |= ag1.y; v1.z |= ag1.z; v1.w |= ag1.w;
+      }
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        uint4* p = out + (size_t)(cy * G + g) * kChunksPerGroup;
+        __stcs(p, v0);
+        if (has1) __stcs(p + 32, v1);
+      }
+    }
+  }
+  if (lane == 0) { pos_out[2 * e] = c.x; pos_out[2 * e + 1] = c.y; la_out[e] = c.la; lr_out[e] = c.lr; }
+}
+
 // ------------------------------------------------------------------------------------
 // x'' render: the frame directly in the conv1 kernels' input layout (csrc/conv_tcgen05.cu):
 // bf16 planes [6][441][8], x''[q][Y*21+X][e] = frame[4Y+dy, 4X+dx, c] with dy*12+dx*3+c = 8q+e.
@@ -717,7 +780,18 @@ extern "C" int unreal_maze_window(int32_t* pos, const int32_t* action, float* re
   WindowArgs a{pos, last_action, last_reward, action, reward, terminal, obs, pc, frame_rec, n, t, auto_reset};
   const long long items = (long long)n * t;
   int variant = get_tunable("maze_render_variant", -1);
-  if (variant < 0 || variant == 1) variant = (obs == nullptr || obs_dtype == UNREAL_U8) ? 2 : 0;
+  // u8 frames: one warp per env walking its T steps (variant 3); f32 frames: one CTA per (step, env) item (variant 0)
+  if (variant < 0 || variant == 1) variant = (obs == nullptr || obs_dtype == UNREAL_U8) ? 3 : 0;
+  if (variant == 3) {
+    const int warps = get_tunable("maze_warps_per_cta", 4);
+    if (obs_dtype == UNREAL_F32) maze_window_env_kernel<float, 4><<<(n + 3) / 4, 128, 0, st>>>(a, pos, last_action, last_reward);
+    else if (warps == 8) maze_window_env_kernel<uint8_t, 8><<<(n + 7) / 8, 256, 0, st>>>(a, pos, last_action, last_reward);
+    else if (warps == 2) maze_window_env_kernel<uint8_t, 2><<<(n + 1) / 2, 64, 0, st>>>(a, pos, last_action, last_reward);
+    else if (warps == 1) maze_window_env_kernel<uint8_t, 1><<<n, 32, 0, st>>>(a, pos, last_action, last_reward);
+    else maze_window_env_kernel<uint8_t, 4><<<(n + 3) / 4, 128, 0, st>>>(a, pos, last_action, last_reward);
+    UNREAL_LAUNCH_CHECK("maze_window_env_kernel");
+    return UNREAL_OK;                       // the env kernel advances the state itself
+  }
   if (variant == 2) {
     if (obs_dtype == UNREAL_F32) maze_window_warp_kernel<float, 4><<<(unsigned)((items + 3) / 4), 128, 0, st>>>(a);
     else if (get_tunable("maze_warps_per_cta", 4) == 8) maze_window_warp_kernel<uint8_t, 8><<<(unsigned)((items + 7) / 8), 256, 0, st>>>(a);

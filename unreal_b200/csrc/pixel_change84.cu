@@ -47,6 +47,8 @@ struct Pc84Args {
   const uint8_t* p1; int64_t stride1;   // frame f >= 1:            p1 + s*stride1 + (f-1)*frame_bytes
   float* pc;
   int sequences, l;
+  uint32_t magic;   // 0x4B000000, passed as a kernel parameter so that it stays an OPERAND (constant bank) of the u8
+                    // kernel's PRMTs and their selectors can be immediates
 };
 
 __device__ __forceinline__ float pc84_pixel(float a0, float a1, float a2, float b0, float b1, float b2) {
@@ -196,30 +198,73 @@ struct Pc84U8 {
   static constexpr int kFrameBytes = 84 * 84 * 3;
 };
 
-// one frame of one cell: 4 x 4 word loads, 48 conversions into cur[], the 16 pixel means against prev[]
-__device__ __forceinline__ float pc84_u8_cell(const uint8_t* cellp, float (&cur)[48], const float (&prev)[48]) {
-  float rows[4];
-#pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    const uint32_t* wp = reinterpret_cast<const uint32_t*>(cellp + r * Pc84U8::kRowBytes);
-    const uint32_t w[4] = {wp[0], wp[1], wp[2], wp[3]};
-#pragma unroll
-    for (int e = 0; e < 12; ++e) cur[r * 12 + e] = u8_over_255(w[(e + 2) >> 2], (e + 2) & 3);
-    const float* a = cur + r * 12;
-    const float* p = prev + r * 12;
-    const float m0 = pc84_pixel2(a[0], a[1], a[2], p[0], p[1], p[2]);
-    const float m1 = pc84_pixel2(a[3], a[4], a[5], p[3], p[4], p[5]);
-    const float m2 = pc84_pixel2(a[6], a[7], a[8], p[6], p[7], p[8]);
-    const float m3 = pc84_pixel2(a[9], a[10], a[11], p[9], p[10], p[11]);
-    rows[r] = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(m0, m1), m2), m3), 0.25f);
+// ---- packed fp32x2 arithmetic (Blackwell FADD2 / FMUL2 / FFMA2: two IEEE-rounded fp32 operations per issue slot; the
+// kernel is issue-bound, not lane-bound).  A pair holds the SAME byte position of two consecutive pixel rows.
+__device__ __forceinline__ float2 f2(float v) { return make_float2(v, v); }
+__device__ __forceinline__ float2 neg2(float2 a) { return make_float2(-a.x, -a.y); }       // folds into the -R operand modifier
+__device__ __forceinline__ float2 abs2(float2 a) { return make_float2(fabsf(a.x), fabsf(a.y)); }   // |R| operand modifier
+
+// byte `byte` of the two rows' words -> (v0 / 255, v1 / 255), each correctly rounded: PRMT drops the byte into the
+// mantissa of 2^23 (0x4B000000 | v), one FADD2 removes the 2^23 from both, then fma(v, hi, RN(v * lo)) with
+// hi = RN(1/255), lo = RN(1/255 - hi): 2 + 3 issue slots for two bytes.  kXu: convert through I2F.U8 instead (one slot
+// per byte, but on the 16-lane conversion pipe) -- used for a few byte positions to balance the pipes.
+// `magic` = 0x4B000000 arrives as a kernel parameter (PRMT takes a single immediate: with the constant folded into it
+// the compiler re-materialises a selector register per PRMT -- 40 extra MOVs per frame)
+
+template <bool kXu>
+__device__ __forceinline__ float2 u8pair_over_255(uint32_t w0, uint32_t w1, int byte, uint32_t magic) {
+  float2 v;
+  if (kXu) {
+    v.x = (float)((w0 >> (8 * byte)) & 0xffu);
+    v.y = (float)((w1 >> (8 * byte)) & 0xffu);
+  } else {
+    float2 m;
+    m.x = __uint_as_float(__byte_perm(w0, magic, 0x7540u | (uint32_t)byte));
+    m.y = __uint_as_float(__byte_perm(w1, magic, 0x7540u | (uint32_t)byte));
+    v = __fadd2_rn(m, f2(-8388608.0f));
   }
-  return __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(rows[0], rows[1]), rows[2]), rows[3]), 0.25f);
+  return __ffma2_rn(v, f2(0x1.010102p-8f), __fmul2_rn(v, f2(-0x1.fdfdfep-33f)));
+}
+
+// ((|a0-b0| + |a1-b1|) + |a2-b2|) / 3 for two pixels at once
+__device__ __forceinline__ float2 pc84_pixel_pair(float2 a0, float2 a1, float2 a2, float2 b0, float2 b1, float2 b2) {
+  const float2 d0 = __fadd2_rn(a0, neg2(b0)), d1 = __fadd2_rn(a1, neg2(b1)), d2 = __fadd2_rn(a2, neg2(b2));
+  float2 s = __fadd2_rn(abs2(d0), abs2(d1));
+  s = __fadd2_rn(s, abs2(d2));
+  return __ffma2_rn(s, f2(0x1.555556p-2f), __fmul2_rn(s, f2(-0x1.555556p-27f)));       // div3_exact, both lanes
+}
+
+// one frame of one cell: 4 x 4 word loads, 48 conversions into cur[] (pairs of rows), the 16 pixel means against prev[]
+template <int kXuBytes>
+__device__ __forceinline__ float pc84_u8_cell(const uint8_t* cellp, float2 (&cur)[24], const float2 (&prev)[24], uint32_t magic) {
+  float2 rows[2];
+#pragma unroll
+  for (int rp = 0; rp < 2; ++rp) {
+    const uint32_t* wa = reinterpret_cast<const uint32_t*>(cellp + (2 * rp) * Pc84U8::kRowBytes);
+    const uint32_t* wb = reinterpret_cast<const uint32_t*>(cellp + (2 * rp + 1) * Pc84U8::kRowBytes);
+    const uint32_t a4[4] = {wa[0], wa[1], wa[2], wa[3]};
+    const uint32_t b4[4] = {wb[0], wb[1], wb[2], wb[3]};
+    float2* a = cur + rp * 12;
+    const float2* p = prev + rp * 12;
+#pragma unroll
+    for (int e = 0; e < 12; ++e) {
+      if (e < kXuBytes) a[e] = u8pair_over_255<true>(a4[(e + 2) >> 2], b4[(e + 2) >> 2], (e + 2) & 3, magic);
+      else a[e] = u8pair_over_255<false>(a4[(e + 2) >> 2], b4[(e + 2) >> 2], (e + 2) & 3, magic);
+    }
+    const float2 m0 = pc84_pixel_pair(a[0], a[1], a[2], p[0], p[1], p[2]);
+    const float2 m1 = pc84_pixel_pair(a[3], a[4], a[5], p[3], p[4], p[5]);
+    const float2 m2 = pc84_pixel_pair(a[6], a[7], a[8], p[6], p[7], p[8]);
+    const float2 m3 = pc84_pixel_pair(a[9], a[10], a[11], p[9], p[10], p[11]);
+    rows[rp] = __fmul2_rn(__fadd2_rn(__fadd2_rn(__fadd2_rn(m0, m1), m2), m3), f2(0.25f));    // mean over the 4 columns
+  }
+  return __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(rows[0].x, rows[0].y), rows[1].x), rows[1].y), 0.25f);   // then the 4 rows
 }
 
 // Warp-specialised: warp 13 is the TMA producer (one bulk copy per frame into a 4-deep ring, gated by per-buffer `empty`
 // barriers), warps 0..12 own one cell per thread and run free of each other -- a warp waits on `full[b]`, reduces its
 // cells and arrives on `empty[b]`; there is no CTA-wide barrier in the loop.  The previous frame's 48 values ping-pong
 // between two register arrays (frame k in A against B, frame k+1 in B against A: no copies).
+template <int kXuBytes>
 __global__ void __launch_bounds__(Pc84U8::kThreads, 1) pixel_change84_u8_kernel(const Pc84Args g) {
   using P = Pc84U8;
   extern __shared__ uint8_t smem_raw[];
@@ -262,13 +307,14 @@ __global__ void __launch_bounds__(Pc84U8::kThreads, 1) pixel_change84_u8_kernel(
   const int ci = cell / 20, cj = cell - ci * 20;
   // byte offset of the word holding the cell's first byte (the cell starts 2 bytes into it: (6 + 12 cj) % 4 == 2)
   const int off0 = P::kLead + 4 * ci * P::kRowBytes + (6 + 12 * cj) - 2;
-  float A[48], B[48];
+  const uint32_t magic = g.magic;
+  float2 A[24], B[24];
 #pragma unroll
-  for (int e = 0; e < 48; ++e) A[e] = B[e] = 0.f;
-  auto step = [&](int k, float (&cur)[48], const float (&prev)[48]) {
+  for (int e = 0; e < 24; ++e) A[e] = B[e] = make_float2(0.f, 0.f);
+  auto step = [&](int k, float2 (&cur)[24], const float2 (&prev)[24]) {
     const int b = k % P::kBufs;
     mbar_wait(full0 + 8u * b, (uint32_t)(k / P::kBufs) & 1u);
-    const float v = pc84_u8_cell(gen + b * P::kBufBytes + off0, cur, prev);
+    const float v = pc84_u8_cell<kXuBytes>(gen + b * P::kBufBytes + off0, cur, prev, magic);
     __syncwarp();
     if (lane == 0) mbar_arrive(empty0 + 8u * b);       // this warp is done with buffer b
     const int itn = k / per, f = k - itn * per;
@@ -283,23 +329,25 @@ __global__ void __launch_bounds__(Pc84U8::kThreads, 1) pixel_change84_u8_kernel(
   }
 }
 
+template <int kXuBytes>
 static int launch84_u8(const Pc84Args& g, cudaStream_t st) {
   using P = Pc84U8;
   static bool configured = false;
+  auto kern = pixel_change84_u8_kernel<kXuBytes>;
   if (!configured) {
-    UNREAL_CUDA(cudaFuncSetAttribute(pixel_change84_u8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P::kSmem));
+    UNREAL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, P::kSmem));
     configured = true;
   }
   const int sms = sm_count();
   if (sms <= 0) return UNREAL_ECUDA;
   const int grid = g.sequences < sms ? g.sequences : sms;
-  pixel_change84_u8_kernel<<<grid, P::kThreads, P::kSmem, st>>>(g);
+  kern<<<grid, P::kThreads, P::kSmem, st>>>(g);
   UNREAL_LAUNCH_CHECK("pixel_change84_u8_kernel");
   return UNREAL_OK;
 }
 
 // Exhaustive device check of the two division-free roundings above against __fdiv_rn.
-__global__ void selfcheck_arith_kernel(unsigned long long* out) {
+__global__ void selfcheck_arith_kernel(unsigned long long* out, uint32_t mg) {
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   const uint64_t id = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   unsigned long long bad3 = 0, bad255 = 0;
@@ -312,14 +360,21 @@ __global__ void selfcheck_arith_kernel(unsigned long long* out) {
   if (id < 256 * 4) {                                   // every byte value in every byte lane of a word
     const uint32_t v = (uint32_t)(id >> 2), lane_b = (uint32_t)(id & 3);
     const uint32_t word = (v << (8 * lane_b)) | (0xA5A5A5A5u & ~(0xffu << (8 * lane_b)));
-    float got;
+    float2 g0, g1;                                      // both conversion paths, both lanes of the packed pair
     switch (lane_b) {
-      case 0: got = u8_over_255(word, 0); break;
-      case 1: got = u8_over_255(word, 1); break;
-      case 2: got = u8_over_255(word, 2); break;
-      default: got = u8_over_255(word, 3); break;
+      case 0: g0 = u8pair_over_255<false>(word, ~word, 0, mg); g1 = u8pair_over_255<true>(~word, word, 0, mg); break;
+      case 1: g0 = u8pair_over_255<false>(word, ~word, 1, mg); g1 = u8pair_over_255<true>(~word, word, 1, mg); break;
+      case 2: g0 = u8pair_over_255<false>(word, ~word, 2, mg); g1 = u8pair_over_255<true>(~word, word, 2, mg); break;
+      default: g0 = u8pair_over_255<false>(word, ~word, 3, mg); g1 = u8pair_over_255<true>(~word, word, 3, mg); break;
     }
-    if (__float_as_uint(got) != __float_as_uint(__fdiv_rn((float)v, 255.0f))) ++bad255;
+    const uint32_t want = __float_as_uint(__fdiv_rn((float)v, 255.0f));
+    const uint32_t wantn = __float_as_uint(__fdiv_rn((float)(255u - v), 255.0f));
+    if (__float_as_uint(g0.x) != want || __float_as_uint(g0.y) != wantn) ++bad255;
+    if (__float_as_uint(g1.x) != wantn || __float_as_uint(g1.y) != want) ++bad255;
+    if (__float_as_uint(u8_over_255(word, (int)lane_b)) != want) ++bad255;
+    const float2 t3 = pc84_pixel_pair(f2(0.f), f2(0.f), f2(0.f), make_float2((float)v, 0.f), f2(0.f), make_float2(0.f, (float)v * 0.5f));
+    if (__float_as_uint(t3.x) != __float_as_uint(__fdiv_rn((float)v, 3.0f)) ||
+        __float_as_uint(t3.y) != __float_as_uint(__fdiv_rn((float)v * 0.5f, 3.0f))) ++bad255;
   }
   if (bad3) atomicAdd(out, bad3);
   if (bad255) atomicAdd(out + 1, bad255);
@@ -350,10 +405,14 @@ int pixel_change84(const void* p0, int64_t stride0, const void* p1, int64_t stri
                    int sequences, int l, cudaStream_t st) {
   if (!aligned16(p0) || !aligned16(p1)) return -100;
   Pc84Args g{reinterpret_cast<const uint8_t*>(p0), stride0, reinterpret_cast<const uint8_t*>(p1), stride1, pc,
-             sequences, l};
+             sequences, l, 0x4B000000u};
   if (dtype == UNREAL_U8) {
     if (get_tunable("pc84_u8_lut", 0) != 0) return launch84<uint8_t, 20>(g, st);   // round-1 table kernel (A/B)
-    return launch84_u8(g, st);
+    switch (get_tunable("pc84_u8_xu_bytes", 0)) {     // byte positions (of 12 per row) converted on the I2F pipe
+      case 2: return launch84_u8<2>(g, st);
+      case 4: return launch84_u8<4>(g, st);
+      default: return launch84_u8<0>(g, st);
+    }
   }
   return launch84<float, 10>(g, st);
 }
@@ -366,7 +425,7 @@ extern "C" int unreal_selfcheck_arith(unsigned long long* mismatches, void* stre
   UNREAL_REQUIRE(mismatches != nullptr, "unreal_selfcheck_arith: null output");
   cudaStream_t st = unreal::as_stream(stream);
   UNREAL_CUDA(cudaMemsetAsync(mismatches, 0, 2 * sizeof(unsigned long long), st));
-  unreal::selfcheck_arith_kernel<<<148 * 8, 256, 0, st>>>(mismatches);
+  unreal::selfcheck_arith_kernel<<<148 * 8, 256, 0, st>>>(mismatches, 0x4B000000u);
   UNREAL_LAUNCH_CHECK("selfcheck_arith_kernel");
   return UNREAL_OK;
 }

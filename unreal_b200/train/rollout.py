@@ -29,10 +29,11 @@ class RolloutTargets(object):
     self.device = torch.device(device)
     self.auto_reset = auto_reset
     self.use_graphs = use_graphs
-    # the T actions of a pass are inputs, so all T steps can go out as ONE launch (unreal_maze_window) instead of T
-    # K1 launches; default: on for u8 frames (the per-step launch ramp is a third of a 14 us transfer), off for f32
-    # (per-step launches already run at 0.99 of HBM).  Same results either way (tests/test_gpu_rollout_bench_config.py).
-    self.window_kernel = (obs_dtype == torch.uint8) if window_kernel is None else bool(window_kernel)
+    # the T actions of a pass are inputs, so all T steps go out as ONE launch (unreal_maze_window) instead of T K1
+    # launches: no launch ramps / drains between the steps (f32: 7.1 TB/s instead of 6.45; u8: the ramp was a third of
+    # a 14 us transfer).  Same results either way (tests/test_gpu_rollout_bench_config.py); False = one launch per step,
+    # which is what a rollout whose actions depend on the observations (Trainer) has to do.
+    self.window_kernel = (self.t <= 32) if window_kernel is None else bool(window_kernel)
     if self.window_kernel and self.t > 32:
       raise _lib.UnrealError("the window kernel covers at most 32 rollout steps")
     d, n, t = self.device, self.n, self.t
@@ -61,7 +62,8 @@ class RolloutTargets(object):
   # launches per pass, by kernel
   @property
   def launches_per_pass(self):
-    return (2 if self.window_kernel else self.t) + 2
+    # window form: u8 = one warp-per-env kernel; f32 = one CTA-per-item kernel + the state kernel
+    return ((1 if self.obs.dtype == torch.uint8 else 2) if self.window_kernel else self.t) + 2
 
   # ---- the three phases, eager --------------------------------------------------------
   def _steps(self):
