@@ -44,6 +44,35 @@ def _worker(rank, world, port, q):
     res["before"] = m.flat.detach().cpu().numpy().copy()
     m.update(feed, 7e-4, ap2)
     res["after"] = m.flat.detach().cpu().numpy().copy()
+    # (3) the whole agent under NCCL: CUDA-graph replay of the update (graph A fwd+bwd, eager exchange + K6, graph B shadow
+    # refresh -- Trainer._update) against eager launches, same seeds, a few iterations
+    from unreal_b200.train.trainer import Trainer
+    from unreal_b200.environment.environment import Environment
+    from unreal_b200.train.sharding import env_seeds, env_shard
+    params = []
+    for graphs in (False, True):
+      Environment.action_size = -1
+      n_env = 4
+      lo, hi = env_shard(n_env * world, world, rank)
+      net = UnrealModel(4, 0, -1, True, True, True, True, 0.05, 0.001, dev, {'segnet_mode': 0}, (84, 84), True, 0, 0.0,
+                        0.0, num_envs=n_env, seed=3)
+      ap3 = RMSPropApplier(7e-4, decay=0.99, momentum=0.0, epsilon=0.1, clip_norm=40.0)
+      tr = Trainer(rank, net, 7e-4, None, ap3, 'maze', '', True, True, True, True, 0.05, 0.001, 20, 20, 0.99, 0.9, 40,
+                   10 ** 9, str(dev), {'segnet_mode': 0}, (84, 84), True, 0, np.random.RandomState(1), 50.0, 0.0, 0.0,
+                   num_envs=n_env, seeds=env_seeds(0xA3C, lo, hi), use_graphs=graphs, obs_cells=True)
+      tr.prepare()
+      while not tr.experience.is_full():
+        tr.process(None, 0)
+      steps = 0
+      for it in range(5):
+        d, _ = tr.process(None, it * 1000000)
+        steps += d
+      torch.cuda.synchronize()
+      params.append(net.flat.detach().cpu().numpy().copy())
+      res["agent_graph_%d" % int(graphs)] = dict(steps=steps, ugraph=tr._ugraph is not None, split=tr._ugraph_b is not None,
+                                                  norm=float(tr.last_losses["grad_norm"]))
+      tr.stop()
+    res["agent_params"] = params
     torch.cuda.synchronize()
     q.put(res)
   finally:
@@ -86,3 +115,10 @@ def test_two_gpu_learner_exchange():
   ms = 1.0 + (gc * gc - 1.0) * 0.01
   want2 = results[0]["before"] - 7e-4 * gc / np.sqrt(ms + 0.1)
   assert np.allclose(results[0]["after"], want2, rtol=1e-5, atol=1e-7)
+  # (3) graph-replayed learner == eager learner on every rank, identical parameters across ranks
+  for r in results:
+    assert r["agent_graph_1"]["ugraph"] and r["agent_graph_1"]["split"] and not r["agent_graph_0"]["ugraph"]
+    assert r["agent_graph_0"]["steps"] == r["agent_graph_1"]["steps"]
+    eager, graphed = r["agent_params"]
+    assert np.allclose(eager, graphed, rtol=1e-3, atol=1e-5)
+  assert np.array_equal(results[0]["agent_params"][1], results[1]["agent_params"][1])

@@ -460,28 +460,31 @@ __global__ void __launch_bounds__(kWarps * 32) maze_window_warp_kernel(WindowArg
   }
 }
 
-// Window form, one WARP per env walking its T steps in order (no re-simulation): the warp keeps the env's cursor, its
-// two chunk columns' wall patterns of all 7 bands in registers (they do not depend on the env or the step), and per
-// step only builds the agent band's two words, writes the 20x20 map and streams the frame out -- ~300 integer
+// Window form, one WARP per env walking its T steps in order (no re-simulation): the warp keeps the env's cursor; the
+// wall patterns of all (band, chunk column) pairs do not depend on the env or the step and sit in a 7 KB shared-memory
+// table built once per CTA; per step a lane only builds the agent band's two words, writes the 20x20 map and streams
+// the frame out -- ~300 integer
 // instructions per 21 KB u8 frame instead of ~1000 (ncu of maze_window_warp_kernel<u8>: ALU pipe 75 % busy at 49 % of
 // DRAM: instruction-bound).  Lane 0 writes the small outputs and, after the last step, the env's state.
 template <typename T, int kWarps>
 __global__ void __launch_bounds__(kWarps * 32) maze_window_env_kernel(WindowArgs a, int32_t* pos_out, int32_t* la_out,
                                                                       float* lr_out) {
+  constexpr int G = Chunk<T>::kGroupsPerBand;
+  constexpr int kChunksPerGroup = 63;
+  // the wall words of (band, chunk column): the same for every env and step -> built once per CTA
+  __shared__ uint4 s_wall[UNREAL_MAZE_GRID][64];
+  for (int c = threadIdx.x; c < 64; c += kWarps * 32) {
+    const ChunkMasks mc = make_masks<T>(c < kChunksPerGroup ? c : 0);
+#pragma unroll
+    for (int cy = 0; cy < UNREAL_MAZE_GRID; ++cy) s_wall[cy][c] = band_value(mc, c_maze.wall_rows[cy], false, 0);
+  }
+  __syncthreads();
   const int lane = threadIdx.x & 31;
   const int e = blockIdx.x * kWarps + (threadIdx.x >> 5);
   if (e >= a.n) return;
-  constexpr int G = Chunk<T>::kGroupsPerBand;
-  constexpr int kChunksPerGroup = 63;
   const ChunkMasks m0 = make_masks<T>(lane);
-  const ChunkMasks m1 = make_masks<T>(lane + 32);
+  const ChunkMasks m1 = make_masks<T>(lane + 32 < kChunksPerGroup ? lane + 32 : 0);
   const bool has1 = lane + 32 < kChunksPerGroup;
-  uint4 w0[UNREAL_MAZE_GRID], w1[UNREAL_MAZE_GRID];
-#pragma unroll
-  for (int cy = 0; cy < UNREAL_MAZE_GRID; ++cy) {
-    w0[cy] = band_value(m0, c_maze.wall_rows[cy], false, 0);
-    w1[cy] = band_value(m1, c_maze.wall_rows[cy], false, 0);
-  }
   const int mine = (lane < a.t) ? a.action[(size_t)lane * a.n + e] : 0;
   MazeCursor c{a.pos[2 * e], a.pos[2 * e + 1], a.last_action[e], a.last_reward[e]};
   for (int t = 0; t < a.t; ++t) {
@@ -507,7 +510,7 @@ __global__ void __launch_bounds__(kWarps * 32) maze_window_env_kernel(WindowArgs
     const uint4 ag0 = band_value(m0, 0u, true, f.rx), ag1 = band_value(m1, 0u, true, f.rx);   // agent words only
 #pragma unroll
     for (int cy = 0; cy < UNREAL_MAZE_GRID; ++cy) {
-      uint4 v0 = w0[cy], v1 = w1[cy];
+      uint4 v0 = s_wall[cy][lane], v1 = s_wall[cy][lane + 32];
       if (cy == f.ry) {
         v0.x |= ag0.x; v0.y |= ag0.y; v0.z |= ag0.z; v0.w |= ag0.w;
         v1.x |= ag1.x; v1.y |= ag1.y; v1.z |= ag1.z; v1.w |= ag1.w;
@@ -783,12 +786,12 @@ extern "C" int unreal_maze_window(int32_t* pos, const int32_t* action, float* re
   // u8 frames: one warp per env walking its T steps (variant 3); f32 frames: one CTA per (step, env) item (variant 0)
   if (variant < 0 || variant == 1) variant = (obs == nullptr || obs_dtype == UNREAL_U8) ? 3 : 0;
   if (variant == 3) {
-    const int warps = get_tunable("maze_warps_per_cta", 4);
+    const int warps = get_tunable("maze_warps_per_cta", 8);
     if (obs_dtype == UNREAL_F32) maze_window_env_kernel<float, 4><<<(n + 3) / 4, 128, 0, st>>>(a, pos, last_action, last_reward);
-    else if (warps == 8) maze_window_env_kernel<uint8_t, 8><<<(n + 7) / 8, 256, 0, st>>>(a, pos, last_action, last_reward);
+    else if (warps == 4) maze_window_env_kernel<uint8_t, 4><<<(n + 3) / 4, 128, 0, st>>>(a, pos, last_action, last_reward);
     else if (warps == 2) maze_window_env_kernel<uint8_t, 2><<<(n + 1) / 2, 64, 0, st>>>(a, pos, last_action, last_reward);
     else if (warps == 1) maze_window_env_kernel<uint8_t, 1><<<n, 32, 0, st>>>(a, pos, last_action, last_reward);
-    else maze_window_env_kernel<uint8_t, 4><<<(n + 3) / 4, 128, 0, st>>>(a, pos, last_action, last_reward);
+    else maze_window_env_kernel<uint8_t, 8><<<(n + 7) / 8, 256, 0, st>>>(a, pos, last_action, last_reward);
     UNREAL_LAUNCH_CHECK("maze_window_env_kernel");
     return UNREAL_OK;                       // the env kernel advances the state itself
   }
