@@ -677,7 +677,7 @@ def run_b200(args):
     if os.path.exists(traffic_file):
       try:
         with open(traffic_file) as f:
-          line["roofline"]["traffic"] = json.load(f).get(args.obs_dtype)
+          line["roofline"]["traffic"] = json.load(f).get(args.obs_dtype if window else args.obs_dtype + "_per_step")
       except Exception:
         pass
     if agent is not None:
