@@ -361,6 +361,14 @@ int unreal_a3c_head_loss(const float* h, const float* wp, const float* bp, const
 int unreal_a3c_head_bwd(const float* h, const float* wp, const float* wv, const float* dz, const float* dv,
                         const float* go2, int64_t m, int a, float* dh, float* dwp, float* dbp, float* dwv, float* dbv,
                         void* stream);
+/* Maze-cell de-duplication of the encoder: a maze frame is a pure function of the agent cell (maze_environment.py:93-96),
+ * so conv1 -> conv2 -> fc1 (model.py:281-289, :332-340) over all samples of an update is a lookup in a 49-row table
+ * (cell index y*7+x) and its backward pass a segment sum by cell.  pos [S,2] i32 = the samples' agent cells (x, y).
+ *   gather:       out[s, 0:d] = table[cell(s), 0:d]                 bf16; out rows are ld_out elements apart
+ *   segment_sum:  out[cell, 0:256] += sum_{s: cell(s)=cell} dy[s]   dy f32 / bf16 [S,256], out f32 [49,256] (caller-zeroed) */
+int unreal_cell_gather(const void* table_bf16, const int32_t* pos, void* out_bf16, int64_t ld_out, int64_t s, int d,
+                       void* stream);
+int unreal_cell_segment_sum(const void* dy, int dy_dtype, const int32_t* pos, float* out, int64_t s, int d, void* stream);
 /* Reward-prediction head after its fc GEMM (model.py:482-488 softmax, :571-575 loss).  logits8 [N,8] f32: columns 0..2 =
  * features . W_rp (the bf16 tcgen05 GEMM on the weight shadow padded to 8 columns), bias [3] added here.
  *   p_out (nullable) [N,3] = softmax(logits + bias)                                  (run_rp_c, model.py:723-728)

@@ -459,3 +459,64 @@ def test_rp_head_on_the_device_path_matches_torch():
     pr = K.rp_loss(logits8, b32.detach().contiguous(), want_p=True)["p"]
     assert torch.allclose(pr, p.detach(), rtol=1e-4, atol=1e-6)
     assert torch.allclose(logits8[:, 3:], torch.zeros_like(logits8[:, 3:]))
+
+
+def test_cell_gather_and_segment_sum_match_torch():
+  """unreal_cell_gather / unreal_cell_segment_sum (the two kernels of the maze-cell de-duplication) against torch
+  index_select / index_add_: gather bit-exact, also into a column slice of a wider buffer; sums to fp32 order."""
+  from unreal_b200 import kernels as K
+  dev = torch.device("cuda", 0)
+  g = torch.Generator(device=dev).manual_seed(3)
+  for S in (1, 77, 4099, 200000):
+    pos = torch.stack((torch.randint(0, 7, (S,), device=dev, generator=g), torch.randint(0, 7, (S,), device=dev, generator=g)),
+                      dim=1).to(torch.int32).contiguous()
+    idx = (pos[:, 1] * 7 + pos[:, 0]).long()
+    table = torch.randn(49, 256, device=dev, generator=g).to(torch.bfloat16)
+    assert torch.equal(K.cell_gather(table, pos), table[idx])
+    wide = torch.zeros(S, 520, dtype=torch.bfloat16, device=dev)
+    K.cell_gather(table, pos, out=wide[:, :256])
+    assert torch.equal(wide[:, :256], table[idx]) and not wide[:, 256:].any()
+    for dt in (torch.float32, torch.bfloat16):
+      dy = torch.randn(S, 256, device=dev, generator=g).to(dt)
+      want = torch.zeros(49, 256, device=dev, dtype=torch.float64).index_add_(0, idx, dy.double())
+      got = K.cell_segment_sum(dy, pos)
+      assert torch.allclose(got.double(), want, rtol=1e-5, atol=1e-4 * max(1.0, S ** 0.5) * 1e-1)
+
+
+def test_cell_table_encoder_equals_dense_encoder():
+  """UnrealModel.dedup_cells: conv1 -> conv2 -> fc1 of every sample as a row of the 49-cell table.  On the same feed of
+  maze CELLS the losses must equal the dense (render-fused) encoder's -- the forward values are the same numbers -- and
+  every variable's gradient must agree to the bf16 rounding of the per-cell gradient sums."""
+  dev = torch.device("cuda", 0)
+  m = _model(dev, seed=5, n=6)
+  T, N, L = 5, 6, 4
+  rs = np.random.RandomState(9)
+  from oracle import unreal_oracle as O
+  cells = np.array([(x, y) for y in range(7) for x in range(7) if not O.WALLS[y, x]], np.int32)
+  feed = _to(_feed(T, N, L, seed=31, maze_frames=True), dev)
+  pick = lambda *lead: torch.from_numpy(cells[rs.randint(0, len(cells), size=lead)]).to(dev)   # noqa: E731
+  feed["base"]["images"] = pick(T, N); feed["pc"]["images"] = pick(L, N); feed["vr"]["images"] = pick(L, N)
+  feed["rp"]["images"] = pick(N, 3)
+  out = {}
+  for dedup in (False, True):
+    m.dedup_cells = dedup
+    m.refresh_shadow()
+    total, parts, grad = m.loss_and_grads(feed)
+    out[dedup] = (float(total), {k: float(v) for k, v in parts.items()}, {k: v.clone() for k, v in m._views(grad).items()})
+  for k in out[False][1]:
+    a, b = out[False][1][k], out[True][1][k]
+    assert abs(a - b) <= 1e-5 * max(1.0, abs(a)), (k, a, b)
+  for k, ref in out[False][2].items():
+    got = out[True][2][k]
+    assert float((got - ref).abs().max()) <= 1e-2 * float(ref.abs().max()) + 1e-7, k
+  # acting helpers read the no-grad table: same policy / value as the dense path
+  lar = feed["base"]["lar"][0]
+  res = {}
+  for dedup in (False, True):
+    m.dedup_cells = dedup
+    m.refresh_shadow(); m.reset_state()
+    pi, v, _ = m.run_base_policy_and_value(None, {'image': feed["base"]["images"][0]}, lar)
+    q = m.run_pc_q_max(None, {'image': feed["base"]["images"][1]}, lar)
+    res[dedup] = (pi.clone(), v.clone(), q.clone())
+  for a, b in zip(res[False], res[True]):
+    assert torch.allclose(a, b, rtol=1e-4, atol=1e-5)

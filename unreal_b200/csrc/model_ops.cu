@@ -652,6 +652,60 @@ __global__ void __launch_bounds__(256) rp_loss_kernel(const float* __restrict__ 
   }
 }
 
+// ---- maze-cell de-duplication of the encoder (UnrealModel.dedup_cells) -------------------------------------------------
+// A maze frame is a pure function of the agent cell, so conv1 -> conv2 -> fc1 (model.py:281-289, :332-340) of ALL samples
+// of an update is a lookup in a 49-row table evaluated once, and its backward pass is a segment sum of the per-sample
+// gradient by cell followed by a 49-sample encoder backward.  Same values as the dense path up to summation order.
+//
+// gather: out[s, :] = table[cell(s), :]   (bf16, D columns; out rows ld_out elements apart: e.g. the LSTM step operand)
+__global__ void __launch_bounds__(256) cell_gather_kernel(const __nv_bfloat16* __restrict__ table, const int32_t* __restrict__ pos,
+                                                          __nv_bfloat16* __restrict__ out, int64_t ld_out, int64_t s, int d8) {
+  const int64_t total = s * d8;     // one thread per 16-byte chunk
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / d8;
+    const int c = (int)(i - r * d8);
+    int x = pos[2 * r], y = pos[2 * r + 1];
+    x = x < 0 ? 0 : (x > 6 ? 6 : x); y = y < 0 ? 0 : (y > 6 ? 6 : y);
+    const uint4 v = reinterpret_cast<const uint4*>(table + (size_t)(y * 7 + x) * d8 * 8)[c];
+    reinterpret_cast<uint4*>(out + r * ld_out)[c] = v;
+  }
+}
+
+// segment sum: out[cell, :] += sum over the samples s with cell(s) == cell of dy[s, :]   (D = 256; out [49,256] f32).
+// One thread per column: a thread owns column j of all 49 bins in shared memory, so rows are accumulated without atomics;
+// the CTA's bins go to global memory with one atomicAdd per non-zero bin element at the end.
+template <typename TD>
+__global__ void __launch_bounds__(256) cell_segment_sum_kernel(const TD* __restrict__ dy, const int32_t* __restrict__ pos,
+                                                               float* __restrict__ out, int64_t s, int64_t rows_per_cta) {
+  extern __shared__ float s_bins[];      // [49][256]
+  const int j = threadIdx.x;
+  for (int b = 0; b < 49; ++b) s_bins[b * 256 + j] = 0.f;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta;
+  const int64_t r1 = r0 + rows_per_cta < s ? r0 + rows_per_cta : s;
+  int64_t r = r0;
+  for (; r + 4 <= r1; r += 4) {
+    float v[4]; int c[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      v[u] = In<TD>::ld(dy + (r + u) * 256 + j);
+      int x = pos[2 * (r + u)], y = pos[2 * (r + u) + 1];
+      x = x < 0 ? 0 : (x > 6 ? 6 : x); y = y < 0 ? 0 : (y > 6 ? 6 : y);
+      c[u] = y * 7 + x;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) s_bins[c[u] * 256 + j] += v[u];
+  }
+  for (; r < r1; ++r) {
+    int x = pos[2 * r], y = pos[2 * r + 1];
+    x = x < 0 ? 0 : (x > 6 ? 6 : x); y = y < 0 ? 0 : (y > 6 ? 6 : y);
+    s_bins[(y * 7 + x) * 256 + j] += In<TD>::ld(dy + r * 256 + j);
+  }
+  for (int b = 0; b < 49; ++b) {
+    const float v = s_bins[b * 256 + j];
+    if (v != 0.f) atomicAdd(out + b * 256 + j, v);
+  }
+}
+
 }  // namespace unreal
 
 using namespace unreal;
@@ -886,5 +940,49 @@ extern "C" int unreal_rp_loss(const float* logits8, const float* bias, const flo
   rp_loss_kernel<<<grid, 256, 0, as_stream(stream)>>>(logits8, bias, c, n, p_out, loss, reinterpret_cast<__nv_bfloat16*>(dz16),
                                                      db, go);
   UNREAL_LAUNCH_CHECK("rp_loss_kernel");
+  return UNREAL_OK;
+}
+
+extern "C" int unreal_cell_gather(const void* table_bf16, const int32_t* pos, void* out_bf16, int64_t ld_out, int64_t s, int d,
+                                  void* stream) {
+  UNREAL_REQUIRE(table_bf16 && pos && out_bf16 && s >= 0, "unreal_cell_gather: null buffer or s < 0");
+  UNREAL_REQUIRE(d > 0 && d % 8 == 0 && ld_out >= d && ld_out % 8 == 0, "unreal_cell_gather: d and ld_out must be multiples of 8");
+  UNREAL_REQUIRE(aligned16(table_bf16) && aligned16(out_bf16), "unreal_cell_gather: buffers must be 16-byte aligned");
+  if (s == 0) return UNREAL_OK;
+  const int64_t total = s * (d / 8);
+  const int sms = sm_count();
+  if (sms <= 0) return UNREAL_ECUDA;
+  int64_t want = (total + 255) / 256;
+  const int grid = (int)(want < (int64_t)sms * 16 ? want : (int64_t)sms * 16);
+  cell_gather_kernel<<<grid, 256, 0, as_stream(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(table_bf16), pos,
+                                                         reinterpret_cast<__nv_bfloat16*>(out_bf16), ld_out, s, d / 8);
+  UNREAL_LAUNCH_CHECK("cell_gather_kernel");
+  return UNREAL_OK;
+}
+
+extern "C" int unreal_cell_segment_sum(const void* dy, int dy_dtype, const int32_t* pos, float* out, int64_t s, int d,
+                                       void* stream) {
+  UNREAL_REQUIRE(dy && pos && out && s >= 0, "unreal_cell_segment_sum: null buffer or s < 0");
+  UNREAL_REQUIRE(d == 256, "unreal_cell_segment_sum: rows of 256 columns (fc1's width), got %d", d);
+  UNREAL_REQUIRE(dy_dtype == UNREAL_F32 || dy_dtype == UNREAL_BF16, "unreal_cell_segment_sum: dy must be f32 or bf16");
+  if (s == 0) return UNREAL_OK;
+  const int sms = sm_count();
+  if (sms <= 0) return UNREAL_ECUDA;
+  constexpr int kSmem = 49 * 256 * 4;
+  static bool configured = false;
+  if (!configured) {
+    UNREAL_CUDA(cudaFuncSetAttribute(cell_segment_sum_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+    UNREAL_CUDA(cudaFuncSetAttribute(cell_segment_sum_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+    configured = true;
+  }
+  int64_t ctas = (int64_t)sms * 4;
+  if (ctas > (s + 63) / 64) ctas = (s + 63) / 64;
+  const int64_t rows_per_cta = (s + ctas - 1) / ctas;
+  ctas = (s + rows_per_cta - 1) / rows_per_cta;
+  if (dy_dtype == UNREAL_F32)
+    cell_segment_sum_kernel<float><<<(unsigned)ctas, 256, kSmem, as_stream(stream)>>>(reinterpret_cast<const float*>(dy), pos, out, s, rows_per_cta);
+  else
+    cell_segment_sum_kernel<__nv_bfloat16><<<(unsigned)ctas, 256, kSmem, as_stream(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(dy), pos, out, s, rows_per_cta);
+  UNREAL_LAUNCH_CHECK("cell_segment_sum_kernel");
   return UNREAL_OK;
 }

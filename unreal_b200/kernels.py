@@ -734,6 +734,30 @@ def a3c_head_bwd(h, wp, wv, dz, dv, go2):
   return dh, dwp, dbp, dwv, dbv
 
 
+def cell_gather(table16, pos, out=None):
+  """table16 bf16 [49, D], pos i32 [S,2] (agent cells) -> out bf16 [S, D] = table rows of the cells.  `out` may be a
+  column slice of a wider row-major buffer (rows out.stride(0) elements apart)."""
+  s = pos.shape[0]
+  d = table16.shape[1]
+  if out is None:
+    out = torch.empty(s, d, dtype=torch.bfloat16, device=table16.device)
+  if out.dim() != 2 or out.shape[0] != s or out.shape[1] != d or out.stride(1) != 1 or out.dtype != torch.bfloat16:
+    raise _lib.UnrealError("cell_gather: out must be bf16 [S, D] with contiguous rows")
+  call("unreal_cell_gather", ptr(table16, torch.bfloat16, "table"), ptr(pos, torch.int32, "pos"), out.data_ptr(),
+       int(out.stride(0)), s, d, stream_ptr())
+  return out
+
+
+def cell_segment_sum(dy, pos, out=None):
+  """dy f32 / bf16 [S,256], pos i32 [S,2] -> f32 [49,256]: rows summed by agent cell (accumulated into `out`)."""
+  s = dy.shape[0]
+  if out is None:
+    out = torch.zeros(49, 256, dtype=torch.float32, device=dy.device)
+  call("unreal_cell_segment_sum", ptr(dy, None, "dy"), _lib.dtype_tag(dy), ptr(pos, torch.int32, "pos"),
+       ptr(out, torch.float32, "out"), s, dy.shape[1], stream_ptr())
+  return out
+
+
 def rp_loss(logits8, bias, c=None, want_p=False, want_loss=False, want_grad=False, go=None):
   """Reward-prediction softmax / cross-entropy on logits8 [N,8] f32 (columns 0..2; bias [3] added inside):
   -> dict(p [N,3], loss f64 [1], dz16 bf16 [N,8], db [3]) with the requested entries."""

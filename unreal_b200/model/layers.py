@@ -348,3 +348,48 @@ class RpHeadLossFn(torch.autograd.Function):
     dh2 = K.gemm_bf16(dz16, w8, out_dtype=torch.bfloat16) if ctx.needs_input_grad[0] else None     # [N,8] . [7776,8]^T
     dw = _wgrad(h2_16, dz16)[:, :3].contiguous()
     return dh2, None, dw, out["db"], None
+
+
+class CellGatherFn(torch.autograd.Function):
+  """Maze-cell de-duplication (UnrealModel.dedup_cells): out[s] = table[cell(s)] for the samples' agent cells
+  `pos` [S,2]; the backward pass is the segment sum of the per-sample gradient by cell (`unreal_cell_segment_sum`), in
+  fp32 -- the table is handed over as fp32 so that autograd adds the towers' gradients in fp32 as well."""
+
+  @staticmethod
+  def forward(ctx, table32, pos):
+    ctx.save_for_backward(pos)
+    return K.cell_gather(table32.to(torch.bfloat16), pos)      # exact: the table holds bf16 values
+
+  @staticmethod
+  def backward(ctx, dout):
+    (pos,) = ctx.saved_tensors
+    return K.cell_segment_sum(dout.contiguous(), pos), None
+
+
+class RpCellLossFn(torch.autograd.Function):
+  """Reward prediction on maze cells (model.py:475-488, :571-575) without materialising the 7776 features of every
+  sample: with G[c, f, :] = h2_table[c] . W_rp[f-th 2592-row block] (one 49-row tcgen05 GEMM against the [2592, 24]
+  shadow `w24`), a sample's logits are G[cell of frame 0, 0] + G[cell of frame 1, 1] + G[cell of frame 2, 2].  Backward:
+  d logits scattered into dG by (cell, frame), then two 49-row GEMMs give dh2_table and dW_rp."""
+
+  @staticmethod
+  def forward(ctx, h2t16, w24, w32, b32, idx3, c):
+    g = K.gemm_bf16(h2t16, w24, b_mn_major=True).view(49, 3, 8)                     # f32
+    logits8 = (g[idx3[:, 0], 0] + g[idx3[:, 1], 1] + g[idx3[:, 2], 2]).contiguous()
+    out = K.rp_loss(logits8, b32, c, want_loss=True)
+    ctx.save_for_backward(h2t16, w24, logits8, b32, idx3, c)
+    return out["loss"][0].to(torch.float32)
+
+  @staticmethod
+  def backward(ctx, go):
+    h2t16, w24, logits8, b32, idx3, c = ctx.saved_tensors
+    out = K.rp_loss(logits8, b32, c, want_grad=True, go=go.to(torch.float32).reshape(1).contiguous())
+    dz = out["dz16"].float()
+    dg = torch.zeros(49, 3, 8, dtype=torch.float32, device=dz.device)
+    for f in range(3):
+      dg[:, f].index_add_(0, idx3[:, f], dz)
+    dg16 = dg.view(49, 24).to(torch.bfloat16)
+    dh = K.gemm_bf16(dg16, w24, out_dtype=torch.bfloat16)                            # [49,24] . [2592,24]^T
+    dw24 = _wgrad(h2t16, dg16)                                                       # [2592, 24]
+    dw = dw24.view(2592, 3, 8)[:, :, :3].permute(1, 0, 2).reshape(7776, 3)
+    return dh, None, dw, out["db"], None, None

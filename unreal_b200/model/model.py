@@ -26,7 +26,8 @@ import torch
 
 from .. import _lib
 from .. import kernels as K
-from .layers import A3CHeadLossFn, ConvFn, Deconv8Fn, EncoderFn, LinearFn, LstmFn, PcHeadLossFn, PcLossFn, RpHeadLossFn, split_k_for
+from .layers import (A3CHeadLossFn, CellGatherFn, ConvFn, Deconv8Fn, EncoderFn, LinearFn, LstmFn, PcHeadLossFn, PcLossFn, RpCellLossFn,
+                     RpHeadLossFn, split_k_for)
 
 
 def _variable_specs(A, G, use_pc, use_rp):
@@ -80,6 +81,12 @@ class UnrealModel(object):
     self.fused_conv = True    # False: convolutions as explicit im2col + GEMM (A/B switch for benchmarks)
     self.fused_encoder = True # False: conv1 / conv2 as separate autograd nodes (dense gradient + relu_grad pass between them)
     self.fused_heads = True   # False: policy / value heads and their losses as torch ops
+    # maze CELL observations (int32 [.,2]): a frame is a pure function of the agent cell, so conv1 -> conv2 -> fc1 of every
+    # sample is a row of a 49-entry table computed once per update (and once per rollout for acting), and the encoder's
+    # backward pass is a segment sum by cell + a 49-sample backward.  False: the dense render-fused encoder on all samples.
+    self.dedup_cells = True
+    self._cells49 = torch.tensor([[x, y] for y in range(7) for x in range(7)], dtype=torch.int32, device=self._device)
+    self._fc_tab_act = torch.zeros(49, 256, dtype=torch.bfloat16, device=self._device)
     self._act_xh = {}         # acting-step [x, h] GEMM operands by batch size (persistent: padding columns stay zero)
     self._build_variables(seed)
     self.reset_state()
@@ -141,7 +148,18 @@ class UnrealModel(object):
       # W_rp [7776,3] as a bf16 [7776,8] shadow (zero columns 3..7): the B operand of the head's tcgen05 GEMM
       if getattr(self, "rp_w8", None) is None:
         self.rp_w8 = torch.zeros(7776, 8, dtype=torch.bfloat16, device=self._device)
+        self.rp_w24 = torch.zeros(2592, 24, dtype=torch.bfloat16, device=self._device)
       self.rp_w8[:, :3].copy_(self.v16["W_rp_fc1"])
+      # the same filter by frame for the cell-table path: w24[r, f*8 + k] = W_rp[f*2592 + r, k]
+      self.rp_w24.view(2592, 3, 8)[:, :, :3].copy_(self.v16["W_rp_fc1"].view(3, 2592, 3).permute(1, 0, 2))
+    if self.fused_conv and self.fused_encoder and getattr(self, "dedup_cells", False):
+      # acting-side table fc1(conv2(conv1(frame of cell))) for all 49 cells, refreshed IN PLACE with the parameters
+      with torch.no_grad():
+        p32 = self._views(self.flat)
+        h2 = EncoderFn.apply(self._cells49, p32["W_base_conv1"], p32["b_base_conv1"], p32["W_base_conv2"], p32["b_base_conv2"],
+                             self.taps1, self.taps2)
+        K.gemm_bf16(h2.view(49, 2592), self.v16["W_base_fc1"], out=self._fc_tab_act, b_mn_major=True, bias=p32["b_base_fc1"],
+                    relu=True)
     if self._use_pixel_change:
       # merged 8-channel shadow of the two pixel-control deconv filters: channel 0 = value, 1..A = advantages
       A = self._action_size
@@ -204,9 +222,24 @@ class UnrealModel(object):
     fc = LinearFn.apply(h2.view(t * n, 2592), self.v16["W_base_fc1"], p32["W_base_fc1"], p32["b_base_fc1"], True, True)
     return fc.view(t, n, 256)
 
-  def _tower(self, p32, images, lar, c0, h0):
+  def _use_tables(self, images):
+    return self.dedup_cells and images.dtype == torch.int32 and self.fused_conv and self.fused_encoder
+
+  def _cell_tables(self, p32):
+    """(h2 table bf16 [49,2592], fc1 table f32 [49,256]) of the 49 maze cells, inside the autograd graph: every tower of
+    the update gathers its rows from them, and their gradients arrive as per-cell sums."""
+    h2t = EncoderFn.apply(self._cells49, p32["W_base_conv1"], p32["b_base_conv1"], p32["W_base_conv2"], p32["b_base_conv2"],
+                          self.taps1, self.taps2).view(49, 2592)
+    fct = LinearFn.apply(h2t, self.v16["W_base_fc1"], p32["W_base_fc1"], p32["b_base_fc1"], True, True)
+    return h2t, fct.float()
+
+  def _tower(self, p32, images, lar, c0, h0, tables=None):
     """encoder + fc1 + LSTM unroll.  images [T,N,84,84,3], lar [T,N,A+1+G] -> h [T,N,256] f32."""
     t, n = images.shape[:2]
+    if tables is not None and self._use_tables(images):
+      fc = CellGatherFn.apply(tables[1], images.reshape(t * n, 2)).view(t, n, 256)
+      return LstmFn.apply(fc, lar.to(torch.float32), self.wcat16, p32["lstm_kernel"], p32["lstm_bias"], c0, h0, self.lstm_in,
+                          self.kx), None
     h2 = self._encoder(p32, images.reshape(t * n, *images.shape[2:]))
     fc = self._lstm_input(p32, h2, t, n)
     return LstmFn.apply(fc, lar.to(torch.float32), self.wcat16, p32["lstm_kernel"], p32["lstm_bias"], c0, h0, self.lstm_in,
@@ -303,12 +336,15 @@ class UnrealModel(object):
     into the [x, h] operand of the step GEMM (`_act_xh`, persistent, padding columns stay zero), the last action /
     reward vector and h are cast into their columns, one GEMM gives the gates [N,1024] f32."""
     n = images.shape[0]
-    h2 = EncoderFn.apply(images, p32["W_base_conv1"], p32["b_base_conv1"], p32["W_base_conv2"], p32["b_base_conv2"],
-                         self.taps1, self.taps2)
     xh = self._act_xh.get(n)
     if xh is None:
       xh = self._act_xh[n] = torch.zeros(n, self.kx + 256, dtype=torch.bfloat16, device=self._device)
-    K.gemm_bf16(h2.view(n, 2592), self.v16["W_base_fc1"], out=xh[:, :256], b_mn_major=True, bias=p32["b_base_fc1"], relu=True)
+    if self._use_tables(images):      # maze cells: fc1's output is a row of the 49-entry table (refresh_shadow)
+      K.cell_gather(self._fc_tab_act, images.reshape(n, 2), out=xh[:, :256])
+    else:
+      h2 = EncoderFn.apply(images, p32["W_base_conv1"], p32["b_base_conv1"], p32["W_base_conv2"], p32["b_base_conv2"],
+                           self.taps1, self.taps2)
+      K.gemm_bf16(h2.view(n, 2592), self.v16["W_base_fc1"], out=xh[:, :256], b_mn_major=True, bias=p32["b_base_fc1"], relu=True)
     xh[:, 256:self.lstm_in].copy_(lar)
     xh[:, self.kx:].copy_(h_prev)
     return K.gemm_bf16(xh, self.wcat16, b_mn_major=True, bias=p32["lstm_bias"])
@@ -383,7 +419,8 @@ class UnrealModel(object):
     p32 = self._views(self.flat)
     parts = OrderedDict()
     b = feed["base"]
-    (h, _, _), _ = self._tower(p32, b["images"], b["lar"], b["c0"], b["h0"])
+    tables = self._cell_tables(p32) if self._use_tables(b["images"]) else None
+    (h, _, _), _ = self._tower(p32, b["images"], b["lar"], b["c0"], b["h0"], tables)
     mask = b["mask"].to(torch.float32)
     if self.fused_heads and self._action_size <= 7:
       t_, n_ = h.shape[:2]
@@ -403,7 +440,7 @@ class UnrealModel(object):
     if self._use_pixel_change and "pc" in feed:
       f = feed["pc"]
       L, n = f["images"].shape[:2]
-      (h, _, _), _ = self._tower(p32, f["images"], f["lar"], *self._zeros_state(n))
+      (h, _, _), _ = self._tower(p32, f["images"], f["lar"], *self._zeros_state(n), tables)
       act = f["a"].reshape(L * n, -1).argmax(-1).to(torch.int32)
       tgt = f["R"].reshape(L * n, 400).contiguous()
       msk = f["mask"].reshape(L * n).to(torch.float32).contiguous()
@@ -420,7 +457,7 @@ class UnrealModel(object):
     if self._use_value_replay and "vr" in feed:
       f = feed["vr"]
       n = f["images"].shape[1]
-      (h, _, _), _ = self._tower(p32, f["images"], f["lar"], *self._zeros_state(n))
+      (h, _, _), _ = self._tower(p32, f["images"], f["lar"], *self._zeros_state(n), tables)
       if self.fused_heads:
         l_, n_ = h.shape[:2]
         _, parts["vr"], _ = A3CHeadLossFn.apply(
@@ -431,8 +468,13 @@ class UnrealModel(object):
       total = total + parts["vr"]
     if self._use_reward_prediction and "rp" in feed:
       f = feed["rp"]
-      parts["rp"] = RpHeadLossFn.apply(self._rp_features(p32, f["images"]), self.rp_w8, p32["W_rp_fc1"], p32["b_rp_fc1"],
-                                       f["c"].to(torch.float32).contiguous())
+      if tables is not None and self._use_tables(f["images"]):
+        cells = f["images"].reshape(-1, 3, 2).to(torch.int64).clamp_(0, 6)
+        parts["rp"] = RpCellLossFn.apply(tables[0], self.rp_w24, p32["W_rp_fc1"], p32["b_rp_fc1"],
+                                         (cells[..., 1] * 7 + cells[..., 0]).contiguous(), f["c"].to(torch.float32).contiguous())
+      else:
+        parts["rp"] = RpHeadLossFn.apply(self._rp_features(p32, f["images"]), self.rp_w8, p32["W_rp_fc1"], p32["b_rp_fc1"],
+                                         f["c"].to(torch.float32).contiguous())
       total = total + parts["rp"]
     return total, parts
 
