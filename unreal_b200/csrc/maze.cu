@@ -460,31 +460,30 @@ __global__ void __launch_bounds__(kWarps * 32) maze_window_warp_kernel(WindowArg
   }
 }
 
-// Window form, one WARP per env walking its T steps in order (no re-simulation): the warp keeps the env's cursor; the
-// wall patterns of all (band, chunk column) pairs do not depend on the env or the step and sit in a 7 KB shared-memory
-// table built once per CTA; per step a lane only builds the agent band's two words, writes the 20x20 map and streams
-// the frame out -- ~300 integer
+// Window form, one WARP per env walking its T steps in order (no re-simulation): the warp keeps the env's cursor, its
+// two chunk columns' wall patterns of all 7 bands in registers (they do not depend on the env or the step), and per
+// step only builds the agent band's two words, writes the 20x20 map and streams the frame out -- ~300 integer
 // instructions per 21 KB u8 frame instead of ~1000 (ncu of maze_window_warp_kernel<u8>: ALU pipe 75 % busy at 49 % of
 // DRAM: instruction-bound).  Lane 0 writes the small outputs and, after the last step, the env's state.
+// (Measured alternative: the wall words in a 7 KB shared-memory table -- 80 registers instead of 128, twice the resident
+// warps -- is SLOWER, 0.83 vs 0.89 of HBM: the 14 LDS.128 per frame sit in front of the stores.)
 template <typename T, int kWarps>
 __global__ void __launch_bounds__(kWarps * 32) maze_window_env_kernel(WindowArgs a, int32_t* pos_out, int32_t* la_out,
                                                                       float* lr_out) {
-  constexpr int G = Chunk<T>::kGroupsPerBand;
-  constexpr int kChunksPerGroup = 63;
-  // the wall words of (band, chunk column): the same for every env and step -> built once per CTA
-  __shared__ uint4 s_wall[UNREAL_MAZE_GRID][64];
-  for (int c = threadIdx.x; c < 64; c += kWarps * 32) {
-    const ChunkMasks mc = make_masks<T>(c < kChunksPerGroup ? c : 0);
-#pragma unroll
-    for (int cy = 0; cy < UNREAL_MAZE_GRID; ++cy) s_wall[cy][c] = band_value(mc, c_maze.wall_rows[cy], false, 0);
-  }
-  __syncthreads();
   const int lane = threadIdx.x & 31;
   const int e = blockIdx.x * kWarps + (threadIdx.x >> 5);
   if (e >= a.n) return;
+  constexpr int G = Chunk<T>::kGroupsPerBand;
+  constexpr int kChunksPerGroup = 63;
   const ChunkMasks m0 = make_masks<T>(lane);
-  const ChunkMasks m1 = make_masks<T>(lane + 32 < kChunksPerGroup ? lane + 32 : 0);
+  const ChunkMasks m1 = make_masks<T>(lane + 32);
   const bool has1 = lane + 32 < kChunksPerGroup;
+  uint4 w0[UNREAL_MAZE_GRID], w1[UNREAL_MAZE_GRID];
+#pragma unroll
+  for (int cy = 0; cy < UNREAL_MAZE_GRID; ++cy) {
+    w0[cy] = band_value(m0, c_maze.wall_rows[cy], false, 0);
+    w1[cy] = band_value(m1, c_maze.wall_rows[cy], false, 0);
+  }
   const int mine = (lane < a.t) ? a.action[(size_t)lane * a.n + e] : 0;
   MazeCursor c{a.pos[2 * e], a.pos[2 * e + 1], a.last_action[e], a.last_reward[e]};
   for (int t = 0; t < a.t; ++t) {
@@ -510,7 +509,7 @@ __global__ void __launch_bounds__(kWarps * 32) maze_window_env_kernel(WindowArgs
     const uint4 ag0 = band_value(m0, 0u, true, f.rx), ag1 = band_value(m1, 0u, true, f.rx);   // agent words only
 #pragma unroll
     for (int cy = 0; cy < UNREAL_MAZE_GRID; ++cy) {
-      uint4 v0 = s_wall[cy][lane], v1 = s_wall[cy][lane + 32];
+      uint4 v0 = w0[cy], v1 = w1[cy];
       if (cy == f.ry) {
         v0.x |= ag0.x; v0.y |= ag0.y; v0.z |= ag0.z; v0.w |= ag0.w;
         v1.x |= ag1.x; v1.y |= ag1.y; v1.z |= ag1.z; v1.w |= ag1.w;
