@@ -29,6 +29,8 @@ def run(args, seed, out):
   Environment.action_size = -1
   net = UnrealModel(4, 0, -1, True, True, True, True, 0.05, args.entropy_beta, dev, {'segnet_mode': 0}, (84, 84), True, 0, 0.0,
                     0.0, num_envs=n, seed=seed)
+  if args.grad_sum:
+    net.grad_scale = 1.0
   applier = RMSPropApplier(args.lr, decay=0.99, momentum=0.0, epsilon=0.1, clip_norm=args.clip)
   # the Trainer anneals lr0 * (max_t - global_t) / max_t (trainer.py:140-144): a warm-up is the same formula run
   # backwards, so it is expressed through the global_t handed to process()
@@ -48,7 +50,7 @@ def run(args, seed, out):
     frac = min(1.0, (0.1 + 0.9 * u / args.warmup)) if args.warmup > 0 else 1.0      # lr = frac * lr0
     d, _ = tr.process(None, int((1.0 - frac) * max_t))
     env_steps += d
-    if u % 100 == 0:
+    if u % args.log_every == 0:
       cur = tr.episode_stats.clone()
       ep, sc = (cur - prev).tolist()
       prev = cur
@@ -74,7 +76,11 @@ def main():
   p.add_argument("--warmup", type=int, default=0, help="updates over which lr ramps linearly from lr/10 to lr")
   p.add_argument("--entropy-beta", type=float, default=0.001)
   p.add_argument("--clip", type=float, default=40.0)
+  p.add_argument("--grad-sum", action="store_true",
+                 help="apply the SUM of the envs' gradients (N reference workers each applying its own, to first order) instead "
+                      "of their mean; give --clip per update, e.g. 40 * envs")
   p.add_argument("--history", type=int, default=2000)
+  p.add_argument("--log-every", type=int, default=100)
   p.add_argument("--seeds", default="0")
   p.add_argument("--obs", default="cells", choices=["cells", "s2d", "f32"])
   p.add_argument("--out", default="-")
@@ -88,9 +94,10 @@ def main():
     torch.cuda.empty_cache()
   out.write(json.dumps({"learning_check": {
       "seeds": seeds, "solved": sum(1 for _, ok, _ in results if ok),
-      "criterion": "mean episode score >= 0.9 at <= 25 steps per episode (optimum: +1 in 20 moves) in the last 100 updates",
+      "criterion": "mean episode score >= 0.9 at <= 25 steps per episode (optimum: +1 in 20 moves) in the last logging window",
       "config": {"envs": args.envs, "max_updates": args.updates, "lr": args.lr, "warmup_updates": args.warmup,
-                 "entropy_beta": args.entropy_beta, "clip": args.clip, "obs": args.obs},
+                 "entropy_beta": args.entropy_beta, "clip": args.clip, "gradient": "sum over envs" if args.grad_sum else "mean over envs",
+                 "obs": args.obs},
       "per_seed": [{"seed": s, "solved": ok, "updates": (f or {}).get("updates"), "mean_score": (f or {}).get("mean_score"),
                     "steps_per_episode": (f or {}).get("steps_per_episode")} for s, ok, f in results]}}) + "\n")
   out.flush()

@@ -85,6 +85,10 @@ class UnrealModel(object):
     # sample is a row of a 49-entry table computed once per update (and once per rollout for acting), and the encoder's
     # backward pass is a segment sum by cell + a 49-sample backward.  False: the dense render-fused encoder on all samples.
     self.dedup_cells = True
+    # update(): the total loss is the SUM over envs (each env is one reference worker); its gradient is scaled by
+    # grad_scale before the clip -- None = 1/N, the synchronous mean of N workers; 1.0 = the sum, i.e. N workers each
+    # applying its own gradient (the reference's Hogwild, to first order in the step size)
+    self.grad_scale = None
     self._cells49 = torch.tensor([[x, y] for y in range(7) for x in range(7)], dtype=torch.int32, device=self._device)
     self._fc_tab_act = torch.zeros(49, 256, dtype=torch.bfloat16, device=self._device)
     self._act_xh = {}         # acting-step [x, h] GEMM operands by batch size (persistent: padding columns stay zero)
@@ -534,6 +538,8 @@ class UnrealModel(object):
     if 'si' in feed["base"]:
       feed = self.feed_from_trainer(feed)
     n = feed["base"]["images"].shape[1]
+    if grad_scale is None:
+      grad_scale = self.grad_scale
     scale = (1.0 / n) if grad_scale is None else grad_scale
     return self.loss_and_grads(feed, scale)
 
@@ -542,6 +548,8 @@ class UnrealModel(object):
     if 'si' in feed["base"]:
       feed = self.feed_from_trainer(feed)
     n = feed["base"]["images"].shape[1]
+    if grad_scale is None:
+      grad_scale = self.grad_scale
     scale = (1.0 / n) if grad_scale is None else grad_scale
     total, parts, grad = self.loss_and_grads(feed, scale)
     norm = grad_applier.apply_flat_to(self.flat, grad, learning_rate)
