@@ -109,24 +109,31 @@ __global__ void __launch_bounds__(128) replay_sample_rp_kernel(unreal_replay R, 
   const int64_t hi = top + *r.count - 1;
   int64_t end = -1;
   constexpr int kBatch = 8;
-  for (int64_t base = lo; base <= hi && end < 0; base += 32 * kBatch) {
+  // slot(abs) = abs % H with ONE 64-bit modulo per env: the eligible range is shorter than H, so a running slot
+  // needs a single conditional subtraction (a 64-bit `%` per record was most of this kernel's time)
+  const int H = r.H;
+  const int slot0 = (int)(lo % H);
+  const int span = (int)(hi - lo + 1);                     // <= H - 3
+  for (int off0 = 0; off0 < span && end < 0; off0 += 32 * kBatch) {
     uint64_t v[kBatch];
 #pragma unroll
     for (int j = 0; j < kBatch; ++j) {
-      const int64_t a = base + 32 * j + lane;
-      v[j] = (a <= hi) ? ring_at_abs(r, a) : 0ull;
+      const int off = off0 + 32 * j + lane;
+      int slot = slot0 + off;
+      if (slot >= H) slot -= H;
+      v[j] = (off < span) ? r.rec[slot] : 0ull;
     }
 #pragma unroll
     for (int j = 0; j < kBatch; ++j) {
-      const int64_t a = base + 32 * j + lane;
-      const bool match = (a <= hi) && (((frame_reward(v[j]) > 0) ? 1 : 0) != from_neg);
+      const int off = off0 + 32 * j + lane;
+      const bool match = (off < span) && (((frame_reward(v[j]) > 0) ? 1 : 0) != from_neg);
       const unsigned b = __ballot_sync(0xffffffffu, match);
       const int c = __popc(b);
       if (end < 0) {
         if (k < c) {
           unsigned bits = b;
           for (int i = 0; i < k; ++i) bits &= bits - 1;     // drop the k lowest set bits
-          end = base + 32 * j + (__ffs(bits) - 1);
+          end = lo + off0 + 32 * j + (__ffs(bits) - 1);
         } else {
           k -= c;
         }
