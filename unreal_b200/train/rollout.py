@@ -58,6 +58,8 @@ class RolloutTargets(object):
     self._h_in = None
     self._h_out = None
     self._copy_stream = None
+    self.host_graph = True       # run_host(): the copies + phases as one CUDA graph (False: ~15 stream calls per pass)
+    self._host_graph = None
 
   # launches per pass, by kernel
   @property
@@ -164,33 +166,51 @@ class RolloutTargets(object):
         self._copy_stream = torch.cuda.Stream(self.device)
         self._ev = [torch.cuda.Event() for _ in range(5)]
       main = torch.cuda.current_stream()
-      side = self._copy_stream
-      ev_start, ev_in, ev_k1, ev_k3, ev_out = self._ev
-      phases = ([g.replay for g in self._graphs] if self.use_graphs
-                else [self._steps, self._returns, self._pc_targets])
-      ev_start.record(main)
-      self.actions.copy_(hi["actions"], non_blocking=True)
-      side.wait_event(ev_start)                      # previous pass has finished with the inputs
-      with torch.cuda.stream(side):
-        self.values.copy_(hi["values"], non_blocking=True)
-        self.boot_value.copy_(hi["boot_value"], non_blocking=True)
-        self.boot_q.copy_(hi["boot_q"], non_blocking=True)
-        ev_in.record(side)
-      phases[0]()                                    # T x K1
-      ev_k1.record(main)
-      with torch.cuda.stream(side):
-        side.wait_event(ev_k1)
-        ho["reward"].copy_(self.reward, non_blocking=True)
-        ho["terminal"].copy_(self.terminal, non_blocking=True)
-      main.wait_event(ev_in)
-      phases[1]()                                    # K3
-      ev_k3.record(main)
-      with torch.cuda.stream(side):
-        side.wait_event(ev_k3)
-        ho["R"].copy_(self.R, non_blocking=True)
-        ho["adv"].copy_(self.adv, non_blocking=True)
-        ev_out.record(side)
-      phases[2]()                                    # K4
-      main.wait_event(ev_out)
+      if self.use_graphs and self.host_graph:
+        # the whole pass -- the H2D copies, the three phases and the D2H copies with their cross-stream overlap -- as ONE
+        # CUDA graph over the pinned staging buffers: one launch and one synchronisation per call instead of ~15 API calls
+        if self._host_graph is None:
+          self._pipeline(main)                                # THIS call's pass, eagerly (creates every lazy resource)
+          main.synchronize()
+          g = torch.cuda.CUDAGraph()
+          with _lib.graph_capture(g):                         # recorded for the following calls, not executed
+            self._pipeline(torch.cuda.current_stream(), replay_graphs=False)
+          self._host_graph = g
+        else:
+          self._host_graph.replay()
+      else:
+        self._pipeline(main)
       main.synchronize()
-    return {k: v.numpy() for k, v in ho.items()}
+    return {k: v.numpy() for k, v in self._h_out.items()}
+
+  def _pipeline(self, main, replay_graphs=True):
+    """The copies and phases of one host-buffer pass on `main` + the copy stream (see run_host)."""
+    hi, ho = self._h_in, self._h_out
+    side = self._copy_stream
+    ev_start, ev_in, ev_k1, ev_k3, ev_out = self._ev
+    phases = ([g.replay for g in self._graphs] if (self.use_graphs and replay_graphs)
+              else [self._steps, self._returns, self._pc_targets])
+    ev_start.record(main)
+    self.actions.copy_(hi["actions"], non_blocking=True)
+    side.wait_event(ev_start)                      # previous pass has finished with the inputs
+    with torch.cuda.stream(side):
+      self.values.copy_(hi["values"], non_blocking=True)
+      self.boot_value.copy_(hi["boot_value"], non_blocking=True)
+      self.boot_q.copy_(hi["boot_q"], non_blocking=True)
+      ev_in.record(side)
+    phases[0]()                                    # K1 (window kernel, or T launches)
+    ev_k1.record(main)
+    with torch.cuda.stream(side):
+      side.wait_event(ev_k1)
+      ho["reward"].copy_(self.reward, non_blocking=True)
+      ho["terminal"].copy_(self.terminal, non_blocking=True)
+    main.wait_event(ev_in)
+    phases[1]()                                    # K3
+    ev_k3.record(main)
+    with torch.cuda.stream(side):
+      side.wait_event(ev_k3)
+      ho["R"].copy_(self.R, non_blocking=True)
+      ho["adv"].copy_(self.adv, non_blocking=True)
+      ev_out.record(side)
+    phases[2]()                                    # K4
+    main.wait_event(ev_out)
