@@ -254,9 +254,24 @@ conv_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_
 // space-to-depth + bf16 conversion of frames: in [S,84,84,3] f32 / u8 (/255) -> x'' [S,6,441,8]
 // (pixel (Y,X) = Y*21+X, channel dy*12 + dx*3 + c split into six 8-channel planes).  One thread per
 // x' pixel: four 48-byte (f32) row pieces in, six coalesced 16-byte plane rows out.
+// u8 frames: two adjacent bytes of a word -> (v0/255, v1/255) as correctly rounded float32 without a divide, like the u8
+// pixel-change kernel (csrc/pixel_change84.cu: PRMT into the mantissa of 2^23, one FADD2, fma(v, hi, RN(v * lo)) on the
+// packed fp32x2 pipe; exhaustively checked by unreal_selfcheck_arith) -- the kernel was instruction-bound on 48
+// __fdiv_rn per thread (0.39 of HBM).  `magic` = 0x4B000000 arrives as a kernel parameter so the PRMT selectors stay immediates.
+__device__ __forceinline__ uint32_t u8pair_to_bf16x2(uint32_t word, int byte0, uint32_t magic) {
+  float2 m;
+  m.x = __uint_as_float(__byte_perm(word, magic, 0x7540u | (uint32_t)byte0));
+  m.y = __uint_as_float(__byte_perm(word, magic, 0x7540u | (uint32_t)(byte0 + 1)));
+  const float2 v = __fadd2_rn(m, make_float2(-8388608.0f, -8388608.0f));
+  const float2 q = __ffma2_rn(v, make_float2(0x1.010102p-8f, 0x1.010102p-8f),
+                              __fmul2_rn(v, make_float2(-0x1.fdfdfep-33f, -0x1.fdfdfep-33f)));
+  __nv_bfloat162 p2 = __floats2bfloat162_rn(q.x, q.y);
+  return *reinterpret_cast<uint32_t*>(&p2);
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) s2d_frames_kernel(const T* __restrict__ in, __nv_bfloat16* __restrict__ out,
-                                                         int64_t total) {
+                                                         int64_t total, uint32_t magic) {
   for (int64_t id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; id < total; id += (int64_t)gridDim.x * blockDim.x) {
     const int X = (int)(id % 21);
     const int Y = (int)((id / 21) % 21);
@@ -266,6 +281,16 @@ __global__ void __launch_bounds__(256) s2d_frames_kernel(const T* __restrict__ i
 #pragma unroll
     for (int dy = 0; dy < 4; ++dy) {
       float v[12];
+      if (sizeof(T) == 1) {
+        const uint32_t* p = reinterpret_cast<const uint32_t*>(src + dy * 252);   // 12 bytes, 4-byte aligned
+#pragma unroll
+        for (int w = 0; w < 3; ++w) {
+          const uint32_t u = __ldcs(p + w);
+          pk[dy * 6 + 2 * w] = u8pair_to_bf16x2(u, 0, magic);
+          pk[dy * 6 + 2 * w + 1] = u8pair_to_bf16x2(u, 2, magic);
+        }
+        continue;
+      }
       if (sizeof(T) == 4) {
         const float4* p = reinterpret_cast<const float4*>(src + dy * 252);
         const float4 a = __ldcs(p), b = __ldcs(p + 1), c = __ldcs(p + 2);
@@ -1030,10 +1055,10 @@ extern "C" int unreal_s2d_frames(const void* frames, int dtype, void* out_bf16, 
   const int grid = (int)(want < (int64_t)sms * 16 ? want : (int64_t)sms * 16);
   if (dtype == UNREAL_F32)
     s2d_frames_kernel<float><<<grid, 256, 0, as_stream(stream)>>>(reinterpret_cast<const float*>(frames),
-                                                                 reinterpret_cast<__nv_bfloat16*>(out_bf16), total);
+                                                                 reinterpret_cast<__nv_bfloat16*>(out_bf16), total, 0x4B000000u);
   else
     s2d_frames_kernel<uint8_t><<<grid, 256, 0, as_stream(stream)>>>(reinterpret_cast<const uint8_t*>(frames),
-                                                                   reinterpret_cast<__nv_bfloat16*>(out_bf16), total);
+                                                                   reinterpret_cast<__nv_bfloat16*>(out_bf16), total, 0x4B000000u);
   UNREAL_LAUNCH_CHECK("s2d_frames_kernel");
   return UNREAL_OK;
 }
