@@ -196,3 +196,61 @@ def test_cell_observation_agent_equals_frame_agent(dedup):
   assert tr_b.last_feed['base']['si'].dtype == torch.int32
   assert torch.allclose(net_a.flat, net_b.flat, rtol=1e-3, atol=3e-5 if dedup else 1e-5)
   tr_a.stop(); tr_b.stop()
+
+
+def test_rejected_checkpoint_leaves_the_agent_untouched(tmp_path):
+  """checkpoint.load validates keys, dtypes and shapes BEFORE it modifies anything (and reads with weights_only=True):
+  a checkpoint for another ring size, one with a tampered RMSProp shard, one with an unknown key and one carrying a
+  non-tensor object are all refused with the trainer exactly as it was."""
+  from unreal_b200 import _lib
+  from unreal_b200.train import checkpoint
+  n = 4
+  tr, net, ap = _agent(n, H=40, seed=3)
+  while not tr.experience.is_full():
+    tr.process(None, 0)
+  tr.process(None, 0)
+  good = checkpoint.state_dict(tr, global_t=5)
+  tr2, net2, ap2 = _agent(n, H=40, seed=99)
+  while not tr2.experience.is_full():
+    tr2.process(None, 0)
+  tr2.process(None, 0)
+  before = (net2.flat.detach().clone(), tr2.streams.mt.clone(), tr2.experience.ring.export_state()["rec"].clone(),
+            ap2._rms.clone(), tr2.local_t)
+
+  def untouched():
+    return (torch.equal(net2.flat.detach(), before[0]) and torch.equal(tr2.streams.mt, before[1]) and
+            torch.equal(tr2.experience.ring.export_state()["rec"], before[2]) and torch.equal(ap2._rms, before[3]) and
+            tr2.local_t == before[4])
+
+  bad = []
+  d = dict(good); d["rmsprop"] = dict(good["rmsprop"]); d["rmsprop"]["shard_lo"] = 128
+  bad.append(d)                                                   # another rank's RMSProp slice
+  d = dict(good); d["history"] = 41
+  bad.append(d)
+  d = dict(good); d["surprise"] = torch.zeros(1)
+  bad.append(d)                                                   # unknown key
+  d = dict(good); d["rng"] = dict(good["rng"]); d["rng"]["mt"] = good["rng"]["mt"][:, :2].clone()
+  bad.append(d)
+  d = dict(good); d["flat"] = good["flat"].to(torch.float16)
+  bad.append(d)                                                   # unexpected dtype
+  d = dict(good); d["rank"] = 1; d["world"] = 2
+  bad.append(d)                                                   # written by rank 1 of 2
+  for i, d in enumerate(bad):
+    with pytest.raises(_lib.UnrealError):
+      checkpoint.load_state_dict(tr2, d)
+    assert untouched(), i
+  path = str(tmp_path / "agent.pt")
+  checkpoint.save(path, tr, global_t=5)
+  assert checkpoint.rank_path(path, 1, 0) == path and checkpoint.rank_path(path, 8, 3) == path + ".rank3of8"
+  assert checkpoint.load(path, tr2) == 5 and not untouched()
+  import pickle
+
+  class Evil(object):
+    def __reduce__(self):
+      return (print, ("code ran on load",))
+
+  evil = str(tmp_path / "evil.pt")
+  torch.save({"format": checkpoint.FORMAT, "payload": Evil()}, evil)
+  with pytest.raises((pickle.UnpicklingError, RuntimeError, _lib.UnrealError)):
+    checkpoint.load(evil, tr2)
+  tr.stop(); tr2.stop()

@@ -235,3 +235,42 @@ def test_observation_modes_agree_through_resets_and_masks():
     assert torch.equal(outs["cells"][0]['image'][am], pos[am]), step
     terms += int((outs["f32"][2] & active).sum())
   assert terms > 100
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.uint8], ids=["f32", "u8"])
+@pytest.mark.parametrize("auto_reset", [False, True], ids=["no-reset", "auto-reset"])
+def test_window_kernel_equals_step_by_step(K, dtype, auto_reset):
+  """unreal_maze_window (T process() calls per env in one launch: per-item re-simulation for f32, one warp per env for
+  u8) against T unreal_maze_step calls, bit for bit on every output and on the carried state -- env counts off the
+  CTA / warp granularity, window lengths 1 .. 32 (the maximum), frames / maps optional, two windows in a row."""
+  dev = "cuda:0"
+  rs = np.random.RandomState(7)
+  for n, t in ((1, 1), (5, 7), (130, 20), (67, 32)):
+    a_st, b_st = K.MazeState(n, dev), K.MazeState(n, dev)
+    for rep in range(2):
+      acts = torch.from_numpy(rs.randint(0, 4, size=(t, n)).astype(np.int32)).to(dev)
+      if rep == 1 and n > 3:
+        acts[:, 0] = 9                      # an out-of-range action is a no-op move with reward 0 (maze_environment.py:99-108)
+      want = dict(obs=torch.empty(t, n, 84, 84, 3, dtype=dtype, device=dev), pc=torch.empty(t, n, 20, 20, device=dev),
+                  reward=torch.empty(t, n, device=dev), terminal=torch.empty(t, n, dtype=torch.uint8, device=dev),
+                  rec=torch.empty(t, n, dtype=torch.int64, device=dev))
+      for i in range(t):
+        K.maze_step(a_st, acts[i], obs=want["obs"][i], pc=want["pc"][i], reward=want["reward"][i],
+                    terminal=want["terminal"][i], frame_rec=want["rec"][i], auto_reset=auto_reset)
+      got = {k: torch.full_like(v, 3) for k, v in want.items()}
+      K.maze_window(b_st, acts, obs=got["obs"], pc=got["pc"], reward=got["reward"], terminal=got["terminal"],
+                    frame_rec=got["rec"], auto_reset=auto_reset)
+      for k in want:
+        assert torch.equal(got[k], want[k]), (n, t, rep, k)
+      for f in ("pos", "last_action", "last_reward"):
+        assert torch.equal(getattr(a_st, f), getattr(b_st, f)), (n, t, rep, f)
+  # outputs are optional: no frames / no maps, state still advances identically
+  a_st, b_st = K.MazeState(33, dev), K.MazeState(33, dev)
+  acts = torch.from_numpy(rs.randint(0, 4, size=(20, 33)).astype(np.int32)).to(dev)
+  r1, t1 = K.maze_window(a_st, acts, auto_reset=auto_reset)
+  obs = torch.empty(20, 33, 84, 84, 3, dtype=dtype, device=dev)
+  r2, t2 = K.maze_window(b_st, acts, obs=obs, auto_reset=auto_reset)
+  assert torch.equal(r1, r2) and torch.equal(t1, t2) and torch.equal(a_st.pos, b_st.pos)
+  from unreal_b200 import _lib
+  with pytest.raises(_lib.UnrealError):
+    K.maze_window(K.MazeState(4, dev), torch.zeros(33, 4, dtype=torch.int32, device=dev))
