@@ -611,6 +611,15 @@ extern "C" int unreal_gemm_bf16(const void* a, int64_t lda, int a_mn_major, cons
   UNREAL_REQUIRE(!(relu && (accumulate || split_k > 1)), "unreal_gemm_bf16: ReLU cannot be fused with accumulation");
   // tile width: wide tiles for wide outputs; MN-major B needs whole 64-column boxes
   int bn = (n > 128) ? 256 : ((n > 64) ? 128 : (n > 32 ? 64 : 32));
+  // small-M problems (the LSTM step at 1024-2048 envs, acting-side layers): a wide tile leaves most SMs idle and the
+  // launch is one pipeline fill long whatever the tile does -- narrow the tile until the grid is about one wave
+  // (measured, profiles/r2_gemm_small_tiles.jsonl: [1024,520]x[520,1024] 11.1 us at BN 256, 7.2 us at BN 64;
+  // [2048,...] 11.4 -> 8.6 us at BN 128; at 8192 rows BN 256 stays best)
+  {
+    const int64_t m_tiles = (m + kBM - 1) / kBM;
+    const int64_t want = (int64_t)sm_count() * 4 / 5;
+    while (bn > 64 && m_tiles * ((n + bn - 1) / bn) * split_k < want) bn /= 2;
+  }
   { int forced = get_tunable("gemm_bn", 0); if (forced == 32 || forced == 64 || forced == 128 || forced == 256) bn = forced; }
   if (b_mn_major && bn < 64) bn = 64;
   // CTA-pair kernel (256 x 256 tiles) once there is at least one full wave of pairs
