@@ -196,6 +196,12 @@ int unreal_replay_add_slots(unreal_replay_t* r, const uint64_t* frame_rec, int32
  * multiple of 4; 128-bit accesses when it is a multiple of 16 and both pointers are 16-byte aligned. */
 int unreal_ring_store(void* payload, const void* src, const int32_t* slot, int n_envs, int history_size,
                       long long item_bytes, void* stream);
+/* Frame-producer helper of the generic-frame env adapter (environment/frame_environment.py): the new frames of the envs
+ * that stepped.  out[e, :] <- src[idx ? idx[e] : e, :] for every env with mask[e] != 0 (mask NULL: all envs, idx NULL:
+ * row e); rows of item_bytes bytes (a multiple of 4).  What `image = frames[k]` / the masked upload of a simulator's
+ * frame does per env in the reference's env classes (lab_environment.py:99-102, indoor_environment.py:102-103). */
+int unreal_rows_select(void* out, const void* src, const int64_t* idx, const uint8_t* mask, int n, long long item_bytes,
+                       void* stream);
 /* The payloads of a sampled sequence (sample_sequence :109-117 / sample_rp_sequence :146-151 collecting
  * self._frames[start+i]): out item (e,t) <- payload[e, (top[e]+start[e]+t) % H] for t < len[e] (len NULL:
  * all seq_len), zeros beyond and for start[e] < 0.  out is [L,N,item] when time_major else [N,L,item]. */

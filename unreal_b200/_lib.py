@@ -67,6 +67,7 @@ SIGNATURES = {
     "unreal_frame_pack": (c_int, [P, P, P, P, P, P, P, c_int, P]),
     "unreal_replay_add_slots": (c_int, [c_void_p, P, P, P]),
     "unreal_ring_store": (c_int, [P, P, P, c_int, c_int, c_int64, P]),
+    "unreal_rows_select": (c_int, [P, P, P, P, c_int, c_int64, P]),
     "unreal_replay_gather": (c_int, [c_void_p, P, c_int64, P, P, c_int, c_int, P, P]),
     "unreal_rollout_lar": (c_int, [P, P, P, c_int, c_int, c_int, P, P]),
     "unreal_rollout_post": (c_int, [P, P, P, c_int, P, P, P, P, P, P, P, P]),

@@ -199,6 +199,18 @@ __global__ void __launch_bounds__(256) ring_store_kernel(W* __restrict__ payload
   for (int w = threadIdx.x; w < words; w += blockDim.x) dst[w] = from[w];
 }
 
+// out[e, :] <- src[idx ? idx[e] : e, :] for the envs with mask[e] != 0 (mask NULL: all); one CTA per env
+template <typename W>
+__global__ void __launch_bounds__(256) rows_select_kernel(W* __restrict__ out, const W* __restrict__ src,
+                                                          const int64_t* __restrict__ idx, const uint8_t* __restrict__ mask,
+                                                          int words) {
+  const int e = blockIdx.x;
+  if (mask != nullptr && mask[e] == 0) return;
+  const W* from = src + (size_t)(idx ? idx[e] : e) * words;
+  W* dst = out + (size_t)e * words;
+  for (int w = threadIdx.x; w < words; w += blockDim.x) dst[w] = from[w];
+}
+
 // small items (a reward, an objective vector): one thread per word
 template <typename W>
 __global__ void ring_store_flat_kernel(W* __restrict__ payload, const W* __restrict__ src,
@@ -401,6 +413,20 @@ extern "C" int unreal_ring_store(void* payload, const void* src, const int32_t* 
     else ring_store_flat_kernel<uint32_t><<<grid, 256, 0, st>>>((uint32_t*)payload, (const uint32_t*)src, slot, n_envs, history_size, words);
   }
   UNREAL_LAUNCH_CHECK("ring_store_kernel");
+  return UNREAL_OK;
+}
+
+extern "C" int unreal_rows_select(void* out, const void* src, const int64_t* idx, const uint8_t* mask, int n,
+                                  long long item_bytes, void* stream) {
+  UNREAL_REQUIRE(out && src && n >= 0, "unreal_rows_select: null argument or n < 0");
+  UNREAL_REQUIRE(item_bytes >= 4 && item_bytes % 4 == 0 && item_bytes < (1ll << 31),
+                 "unreal_rows_select: item_bytes %lld must be a positive multiple of 4", item_bytes);
+  if (n == 0) return UNREAL_OK;
+  const bool v16 = item_bytes % 16 == 0 && aligned16(out) && aligned16(src);
+  const int words = (int)(item_bytes / (v16 ? 16 : 4));
+  if (v16) rows_select_kernel<uint4><<<n, 256, 0, as_stream(stream)>>>((uint4*)out, (const uint4*)src, idx, mask, words);
+  else rows_select_kernel<uint32_t><<<n, 256, 0, as_stream(stream)>>>((uint32_t*)out, (const uint32_t*)src, idx, mask, words);
+  UNREAL_LAUNCH_CHECK("rows_select_kernel");
   return UNREAL_OK;
 }
 

@@ -81,13 +81,13 @@ class TableFrameProducer(FrameProducer):
     m = torch.ones(self.num_envs, dtype=torch.bool, device=self.device) if mask is None else mask.to(torch.bool)
     self.counter.add_(m.to(torch.int64))
     h = self._hash(torch.zeros_like(self.counter))
-    out.copy_(torch.where(_rows(m, out), self.table.index_select(0, h % self.K_FRAMES), out))
+    K.rows_select(out, self.table, (h % self.K_FRAMES).contiguous(), m)
 
   def step(self, action, active, out, reward, terminal, objective=None):
     m = torch.ones(self.num_envs, dtype=torch.bool, device=self.device) if active is None else active.to(torch.bool)
     self.counter.add_(m.to(torch.int64))
     h = self._hash(action.to(torch.int64) + 1)
-    out.copy_(torch.where(_rows(m, out), self.table.index_select(0, h % self.K_FRAMES), out))
+    K.rows_select(out, self.table, (h % self.K_FRAMES).contiguous(), m)
     q = h // self.K_FRAMES
     r = torch.where(h % 3 == 0, ((q % 5) - 2).to(torch.float32) * 0.5, torch.zeros((), device=self.device))
     reward.copy_(torch.where(m, r, torch.zeros_like(r)))
@@ -118,10 +118,7 @@ class RandomFrameProducer(FrameProducer):
 
   def _draw(self, mask, out):
     fresh = torch.randint(0, 256, out.shape, dtype=torch.uint8, device=self.device, generator=self.gen)
-    if mask is None:
-      out.copy_(fresh)
-    else:
-      out.copy_(torch.where(_rows(mask, out), fresh, out))
+    K.rows_select(out, fresh, None, mask)
 
   def reset(self, mask, out, objective=None):
     self._draw(mask, out)
@@ -175,7 +172,7 @@ class HostEnvProducer(FrameProducer):
 
   def _upload(self, mask_host, out, objective):
     m = torch.from_numpy(mask_host).to(self.device)
-    out.copy_(torch.where(_rows(m, out), self._stage.to(self.device, non_blocking=True), out))
+    K.rows_select(out, self._stage.to(self.device, non_blocking=True), None, m)
     if objective is not None and self.objective_size:
       fresh = self._obj[:, :self.objective_size].to(self.device, non_blocking=True)
       objective.copy_(torch.where(_rows(m, objective), fresh, objective))

@@ -367,6 +367,21 @@ class ReplayRing(object):
     return start, rec
 
 
+def rows_select(out, src, idx=None, mask=None):
+  """out[e] <- src[idx[e]] (idx None: src[e]) for the envs with mask[e] != 0 (None: all); rows = everything after dim 0."""
+  n = out.shape[0]
+  if out.dtype != src.dtype or tuple(out.shape[1:]) != tuple(src.shape[1:]):
+    raise _lib.UnrealError("rows_select: out %s %s and src %s %s rows differ" % (tuple(out.shape), out.dtype, tuple(src.shape), src.dtype))
+  if idx is None and src.shape[0] != n:
+    raise _lib.UnrealError("rows_select: without idx, src must hold one row per env")
+  item = out[0].numel() * out.element_size()
+  if mask is not None and mask.dtype == torch.bool:
+    mask = mask.to(torch.uint8)
+  call("unreal_rows_select", ptr(out, name="out"), ptr(src, name="src"), ptr(idx, torch.int64, "idx"),
+       ptr(mask, torch.uint8, "mask"), n, item, stream_ptr())
+  return out
+
+
 def frame_unpack(rec, fields=("pos0", "pos1", "action", "reward", "terminal", "last_action", "last_reward", "valid")):
   """Packed records (any shape) -> dict of SoA tensors with that shape (+[2] for positions)."""
   m = rec.numel()
