@@ -282,6 +282,15 @@ int unreal_lstm_cell_fwd_ld(float* gates, const float* c_prev, float* c_out, flo
  * state's h afterwards (unchanged for inactive envs). */
 int unreal_lstm_cell_act(const float* gates, float* c_state, float* h_state, float* h_out, const uint8_t* active, int n,
                          void* stream);
+/* The same cell steps with the gates stored as bf16 [N,1024] (the step GEMM writes the pre-activations as bf16, the
+ * activations kept for the backward pass are bf16): fwd = unreal_lstm_cell_fwd_ld, act = unreal_lstm_cell_act,
+ * bwd = unreal_lstm_cell_bwd2 (dh_rec nullable).  The cell kernels are HBM-bound on that buffer. */
+int unreal_lstm_cell_fwd_g16(void* gates_bf16, const float* c_prev, float* c_out, float* h_out, void* h16_out, int h16_ld,
+                             int n, void* stream);
+int unreal_lstm_cell_act_g16(const void* gates_bf16, float* c_state, float* h_state, float* h_out, const uint8_t* active,
+                             int n, void* stream);
+int unreal_lstm_cell_bwd_g16(const void* gates_act_bf16, const float* c_prev, const float* c, const float* dh,
+                             const float* dh_rec, float* dc, void* dgates_bf16, int n, void* stream);
 /* backward of the above: dh [N,256] total gradient wrt h_t; dc [N,256] in: wrt c_t, out: wrt
  * c_{t-1}; dgates bf16 [N,1024] wrt the pre-activations. */
 int unreal_lstm_cell_bwd(const float* gates_act, const float* c_prev, const float* c, const float* dh, float* dc,

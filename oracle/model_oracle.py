@@ -123,7 +123,7 @@ class ModelOracle(object):
     c, h = c0, h0
     outs = []
     for t in range(T):
-      z = torch.cat([x[t], _bf16(h, self.q)], dim=1) @ kernel + bias
+      z = _bf16(torch.cat([x[t], _bf16(h, self.q)], dim=1) @ kernel + bias, self.q)   # the CUDA path stores the gates as bf16
       i, j, f, o = z.split(256, dim=1)
       c = c * torch.sigmoid(f + 1.0) + torch.sigmoid(i) * torch.tanh(j)
       h = torch.tanh(c) * torch.sigmoid(o)

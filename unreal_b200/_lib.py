@@ -83,6 +83,9 @@ SIGNATURES = {
     "unreal_lstm_cell_fwd": (c_int, [P, P, P, P, P, c_int, P]),
     "unreal_lstm_cell_fwd_ld": (c_int, [P, P, P, P, P, c_int, c_int, P]),
     "unreal_lstm_cell_act": (c_int, [P, P, P, P, P, c_int, P]),
+    "unreal_lstm_cell_fwd_g16": (c_int, [P, P, P, P, P, c_int, c_int, P]),
+    "unreal_lstm_cell_act_g16": (c_int, [P, P, P, P, P, c_int, P]),
+    "unreal_lstm_cell_bwd_g16": (c_int, [P, P, P, P, P, P, P, c_int, P]),
     "unreal_lstm_cell_bwd": (c_int, [P, P, P, P, P, P, c_int, P]),
     "unreal_lstm_cell_bwd2": (c_int, [P, P, P, P, P, P, P, c_int, P]),
     "unreal_s2d_frames": (c_int, [P, c_int, P, c_int, P]),

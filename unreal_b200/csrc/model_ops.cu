@@ -153,21 +153,35 @@ __global__ void __launch_bounds__(256) col2im_vec8_kernel(const __nv_bfloat16* _
 // ---- BasicLSTMCell pointwise -----------------------------------------------------------
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
 
+// Gate storage type: float, or bf16 (UnrealModel.lstm_gates_bf16: the step GEMM writes the pre-activations as bf16 and
+// the activations kept for the backward pass are bf16 as well -- the cell kernels are HBM-bound on exactly that buffer:
+// 95 MB per step at 8192 envs in f32, 61 MB in bf16; the rounding is that of every other activation between layers).
+template <typename TG> struct Gate;
+template <> struct Gate<float> {
+  static __device__ __forceinline__ float ld(const float* p) { return *p; }
+  static __device__ __forceinline__ void st(float* p, float v) { *p = v; }
+};
+template <> struct Gate<__nv_bfloat16> {
+  static __device__ __forceinline__ float ld(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+  static __device__ __forceinline__ void st(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+};
+
 // gates [N,1024] pre-activations (i | j | f | o blocks of 256) are replaced by their activations
-__global__ void __launch_bounds__(256) lstm_cell_fwd_kernel(float* __restrict__ gates, const float* __restrict__ c_prev,
+template <typename TG>
+__global__ void __launch_bounds__(256) lstm_cell_fwd_kernel(TG* __restrict__ gates, const float* __restrict__ c_prev,
                                                             float* __restrict__ c_out, float* __restrict__ h_out,
                                                             __nv_bfloat16* __restrict__ h16_out, int n, int h16_ld) {
   const int id = blockIdx.x * blockDim.x + threadIdx.x;
   if (id >= n * 256) return;
   const int e = id >> 8, u = id & 255;
-  float* gr = gates + (size_t)e * 1024;
-  const float i = sigmoidf_(gr[u]);
-  const float j = tanhf(gr[256 + u]);
-  const float f = sigmoidf_(gr[512 + u] + 1.0f);   // forget_bias = 1.0
-  const float o = sigmoidf_(gr[768 + u]);
+  TG* gr = gates + (size_t)e * 1024;
+  const float i = sigmoidf_(Gate<TG>::ld(gr + u));
+  const float j = tanhf(Gate<TG>::ld(gr + 256 + u));
+  const float f = sigmoidf_(Gate<TG>::ld(gr + 512 + u) + 1.0f);   // forget_bias = 1.0
+  const float o = sigmoidf_(Gate<TG>::ld(gr + 768 + u));
   const float c = c_prev[id] * f + i * j;
   const float h = tanhf(c) * o;
-  gr[u] = i; gr[256 + u] = j; gr[512 + u] = f; gr[768 + u] = o;
+  Gate<TG>::st(gr + u, i); Gate<TG>::st(gr + 256 + u, j); Gate<TG>::st(gr + 512 + u, f); Gate<TG>::st(gr + 768 + u, o);
   c_out[id] = c;
   h_out[id] = h;
   h16_out[(size_t)e * h16_ld + u] = __float2bfloat16_rn(h);     // h16_ld > 256: straight into the next step's [x, h] GEMM operand
@@ -175,7 +189,8 @@ __global__ void __launch_bounds__(256) lstm_cell_fwd_kernel(float* __restrict__ 
 
 // Acting step: the cell applied IN PLACE to the persistent state of the envs with active[e] != 0 (the others keep
 // their state and report their old h): replaces cell + two masked selects + two copies per env step.
-__global__ void __launch_bounds__(256) lstm_cell_act_kernel(const float* __restrict__ gates, float* __restrict__ c_state,
+template <typename TG>
+__global__ void __launch_bounds__(256) lstm_cell_act_kernel(const TG* __restrict__ gates, float* __restrict__ c_state,
                                                             float* __restrict__ h_state, float* __restrict__ h_out,
                                                             const uint8_t* __restrict__ active, int n) {
   const int id = blockIdx.x * blockDim.x + threadIdx.x;
@@ -185,11 +200,11 @@ __global__ void __launch_bounds__(256) lstm_cell_act_kernel(const float* __restr
     if (h_out != nullptr) h_out[id] = h_state[id];
     return;
   }
-  const float* gr = gates + (size_t)e * 1024;
-  const float i = sigmoidf_(gr[u]);
-  const float j = tanhf(gr[256 + u]);
-  const float f = sigmoidf_(gr[512 + u] + 1.0f);   // forget_bias = 1.0
-  const float o = sigmoidf_(gr[768 + u]);
+  const TG* gr = gates + (size_t)e * 1024;
+  const float i = sigmoidf_(Gate<TG>::ld(gr + u));
+  const float j = tanhf(Gate<TG>::ld(gr + 256 + u));
+  const float f = sigmoidf_(Gate<TG>::ld(gr + 512 + u) + 1.0f);   // forget_bias = 1.0
+  const float o = sigmoidf_(Gate<TG>::ld(gr + 768 + u));
   const float c = c_state[id] * f + i * j;
   const float h = tanhf(c) * o;
   c_state[id] = c;
@@ -200,7 +215,8 @@ __global__ void __launch_bounds__(256) lstm_cell_act_kernel(const float* __restr
 // dh: total gradient wrt h_t (heads + recurrent); dc: in = gradient wrt c_t from step t+1,
 // out = gradient wrt c_{t-1}.  dgates are the gradients wrt the PRE-activations, as bf16 (the
 // operand dtype of the dgrad / wgrad GEMMs that consume them).
-__global__ void __launch_bounds__(256) lstm_cell_bwd_kernel(const float* __restrict__ gates_act,
+template <typename TG>
+__global__ void __launch_bounds__(256) lstm_cell_bwd_kernel(const TG* __restrict__ gates_act,
                                                             const float* __restrict__ c_prev, const float* __restrict__ c,
                                                             const float* __restrict__ dh, float* __restrict__ dc,
                                                             __nv_bfloat16* __restrict__ dgates, int n,
@@ -208,8 +224,8 @@ __global__ void __launch_bounds__(256) lstm_cell_bwd_kernel(const float* __restr
   const int id = blockIdx.x * blockDim.x + threadIdx.x;
   if (id >= n * 256) return;
   const int e = id >> 8, u = id & 255;
-  const float* gr = gates_act + (size_t)e * 1024;
-  const float i = gr[u], j = gr[256 + u], f = gr[512 + u], o = gr[768 + u];
+  const TG* gr = gates_act + (size_t)e * 1024;
+  const float i = Gate<TG>::ld(gr + u), j = Gate<TG>::ld(gr + 256 + u), f = Gate<TG>::ld(gr + 512 + u), o = Gate<TG>::ld(gr + 768 + u);
   const float tc = tanhf(c[id]);
   const float dhv = dh[id] + (dh2 ? dh2[id] : 0.f);     // heads' gradient (+ the recurrent one from step t+1)
   const float d_o = dhv * tc;
@@ -784,7 +800,7 @@ extern "C" int unreal_col2im(const void* cols, int cols_dtype, void* out, int ou
 extern "C" int unreal_lstm_cell_fwd(float* gates, const float* c_prev, float* c_out, float* h_out, void* h16_out,
                                     int n, void* stream) {
   UNREAL_REQUIRE(gates && c_prev && c_out && h_out && h16_out && n > 0, "unreal_lstm_cell_fwd: null buffer or n <= 0");
-  lstm_cell_fwd_kernel<<<(n * 256 + 255) / 256, 256, 0, as_stream(stream)>>>(
+  lstm_cell_fwd_kernel<float><<<(n * 256 + 255) / 256, 256, 0, as_stream(stream)>>>(
       gates, c_prev, c_out, h_out, reinterpret_cast<__nv_bfloat16*>(h16_out), n, 256);
   UNREAL_LAUNCH_CHECK("lstm_cell_fwd_kernel");
   return UNREAL_OK;
@@ -794,7 +810,7 @@ extern "C" int unreal_lstm_cell_fwd_ld(float* gates, const float* c_prev, float*
                                        int h16_ld, int n, void* stream) {
   UNREAL_REQUIRE(gates && c_prev && c_out && h_out && h16_out && n > 0, "unreal_lstm_cell_fwd_ld: null buffer or n <= 0");
   UNREAL_REQUIRE(h16_ld >= 256, "unreal_lstm_cell_fwd_ld: h16_ld %d < 256", h16_ld);
-  lstm_cell_fwd_kernel<<<(n * 256 + 255) / 256, 256, 0, as_stream(stream)>>>(
+  lstm_cell_fwd_kernel<float><<<(n * 256 + 255) / 256, 256, 0, as_stream(stream)>>>(
       gates, c_prev, c_out, h_out, reinterpret_cast<__nv_bfloat16*>(h16_out), n, h16_ld);
   UNREAL_LAUNCH_CHECK("lstm_cell_fwd_kernel");
   return UNREAL_OK;
@@ -803,7 +819,7 @@ extern "C" int unreal_lstm_cell_fwd_ld(float* gates, const float* c_prev, float*
 extern "C" int unreal_lstm_cell_act(const float* gates, float* c_state, float* h_state, float* h_out, const uint8_t* active,
                                     int n, void* stream) {
   UNREAL_REQUIRE(gates && c_state && h_state && n > 0, "unreal_lstm_cell_act: null buffer or n <= 0");
-  lstm_cell_act_kernel<<<(n * 256 + 255) / 256, 256, 0, as_stream(stream)>>>(gates, c_state, h_state, h_out, active, n);
+  lstm_cell_act_kernel<float><<<(n * 256 + 255) / 256, 256, 0, as_stream(stream)>>>(gates, c_state, h_state, h_out, active, n);
   UNREAL_LAUNCH_CHECK("lstm_cell_act_kernel");
   return UNREAL_OK;
 }
@@ -812,7 +828,7 @@ extern "C" int unreal_lstm_cell_bwd(const float* gates_act, const float* c_prev,
                                     float* dc, void* dgates_bf16, int n, void* stream) {
   UNREAL_REQUIRE(gates_act && c_prev && c && dh && dc && dgates_bf16 && n > 0,
                  "unreal_lstm_cell_bwd: null buffer or n <= 0");
-  lstm_cell_bwd_kernel<<<(n * 256 + 255) / 256, 256, 0, as_stream(stream)>>>(
+  lstm_cell_bwd_kernel<float><<<(n * 256 + 255) / 256, 256, 0, as_stream(stream)>>>(
       gates_act, c_prev, c, dh, dc, reinterpret_cast<__nv_bfloat16*>(dgates_bf16), n, nullptr);
   UNREAL_LAUNCH_CHECK("lstm_cell_bwd_kernel");
   return UNREAL_OK;
@@ -822,7 +838,7 @@ extern "C" int unreal_lstm_cell_bwd2(const float* gates_act, const float* c_prev
                                      const float* dh_rec, float* dc, void* dgates_bf16, int n, void* stream) {
   UNREAL_REQUIRE(gates_act && c_prev && c && dh && dc && dgates_bf16 && n > 0,
                  "unreal_lstm_cell_bwd2: null buffer or n <= 0");
-  lstm_cell_bwd_kernel<<<(n * 256 + 255) / 256, 256, 0, as_stream(stream)>>>(
+  lstm_cell_bwd_kernel<float><<<(n * 256 + 255) / 256, 256, 0, as_stream(stream)>>>(
       gates_act, c_prev, c, dh, dc, reinterpret_cast<__nv_bfloat16*>(dgates_bf16), n, dh_rec);
   UNREAL_LAUNCH_CHECK("lstm_cell_bwd_kernel");
   return UNREAL_OK;
@@ -984,5 +1000,36 @@ extern "C" int unreal_cell_segment_sum(const void* dy, int dy_dtype, const int32
   else
     cell_segment_sum_kernel<__nv_bfloat16><<<(unsigned)ctas, 256, kSmem, as_stream(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(dy), pos, out, s, rows_per_cta);
   UNREAL_LAUNCH_CHECK("cell_segment_sum_kernel");
+  return UNREAL_OK;
+}
+
+// ---- the same three cell entry points with bf16 gate storage (gates / gates_act are bf16 [N,1024]) ------------------------
+extern "C" int unreal_lstm_cell_fwd_g16(void* gates_bf16, const float* c_prev, float* c_out, float* h_out, void* h16_out,
+                                        int h16_ld, int n, void* stream) {
+  UNREAL_REQUIRE(gates_bf16 && c_prev && c_out && h_out && h16_out && n > 0, "unreal_lstm_cell_fwd_g16: null buffer or n <= 0");
+  UNREAL_REQUIRE(h16_ld >= 256, "unreal_lstm_cell_fwd_g16: h16_ld %d < 256", h16_ld);
+  lstm_cell_fwd_kernel<__nv_bfloat16><<<(n * 256 + 255) / 256, 256, 0, as_stream(stream)>>>(
+      reinterpret_cast<__nv_bfloat16*>(gates_bf16), c_prev, c_out, h_out, reinterpret_cast<__nv_bfloat16*>(h16_out), n, h16_ld);
+  UNREAL_LAUNCH_CHECK("lstm_cell_fwd_kernel<bf16>");
+  return UNREAL_OK;
+}
+
+extern "C" int unreal_lstm_cell_act_g16(const void* gates_bf16, float* c_state, float* h_state, float* h_out,
+                                        const uint8_t* active, int n, void* stream) {
+  UNREAL_REQUIRE(gates_bf16 && c_state && h_state && n > 0, "unreal_lstm_cell_act_g16: null buffer or n <= 0");
+  lstm_cell_act_kernel<__nv_bfloat16><<<(n * 256 + 255) / 256, 256, 0, as_stream(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(gates_bf16), c_state, h_state, h_out, active, n);
+  UNREAL_LAUNCH_CHECK("lstm_cell_act_kernel<bf16>");
+  return UNREAL_OK;
+}
+
+extern "C" int unreal_lstm_cell_bwd_g16(const void* gates_act_bf16, const float* c_prev, const float* c, const float* dh,
+                                        const float* dh_rec, float* dc, void* dgates_bf16, int n, void* stream) {
+  UNREAL_REQUIRE(gates_act_bf16 && c_prev && c && dh && dc && dgates_bf16 && n > 0,
+                 "unreal_lstm_cell_bwd_g16: null buffer or n <= 0");
+  lstm_cell_bwd_kernel<__nv_bfloat16><<<(n * 256 + 255) / 256, 256, 0, as_stream(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(gates_act_bf16), c_prev, c, dh, dc, reinterpret_cast<__nv_bfloat16*>(dgates_bf16), n,
+      dh_rec);
+  UNREAL_LAUNCH_CHECK("lstm_cell_bwd_kernel<bf16>");
   return UNREAL_OK;
 }

@@ -498,6 +498,13 @@ def col2im(cols, s, h, w, c, kh, kw, stride, bias=None, relu=False, out_dtype=to
 def lstm_cell_fwd(gates, c_prev, c_out, h_out, h16_out):
   """h16_out [n,256] bf16; a column slice of a wider row-major buffer is accepted (rows stride(0) apart)."""
   n = gates.shape[0]
+  if gates.dtype == torch.bfloat16:       # bf16 gate storage
+    if h16_out.dim() != 2 or h16_out.shape[1] != 256 or h16_out.stride(1) != 1 or h16_out.dtype != torch.bfloat16:
+      raise _lib.UnrealError("h16_out must be bf16 [n,256] with contiguous rows")
+    call("unreal_lstm_cell_fwd_g16", ptr(gates, torch.bfloat16, "gates"), ptr(c_prev, torch.float32, "c_prev"),
+         ptr(c_out, torch.float32, "c_out"), ptr(h_out, torch.float32, "h_out"), h16_out.data_ptr(), int(h16_out.stride(0)),
+         n, stream_ptr())
+    return
   if h16_out.is_contiguous():
     call("unreal_lstm_cell_fwd", ptr(gates, torch.float32, "gates"), ptr(c_prev, torch.float32, "c_prev"),
          ptr(c_out, torch.float32, "c_out"), ptr(h_out, torch.float32, "h_out"), ptr(h16_out, torch.bfloat16, "h16_out"),
@@ -513,6 +520,11 @@ def lstm_cell_fwd(gates, c_prev, c_out, h_out, h16_out):
 def lstm_cell_bwd(gates_act, c_prev, c, dh, dc, dgates16, dh_rec=None):
   """dh (+ dh_rec): gradient w.r.t. h_t; dc in / out; dgates16 [n,1024] bf16 out."""
   n = gates_act.shape[0]
+  if gates_act.dtype == torch.bfloat16:
+    call("unreal_lstm_cell_bwd_g16", ptr(gates_act, torch.bfloat16, "gates_act"), ptr(c_prev, torch.float32, "c_prev"),
+         ptr(c, torch.float32, "c"), ptr(dh, torch.float32, "dh"), ptr(dh_rec, torch.float32, "dh_rec"),
+         ptr(dc, torch.float32, "dc"), ptr(dgates16, torch.bfloat16, "dgates16"), n, stream_ptr())
+    return
   call("unreal_lstm_cell_bwd2", ptr(gates_act, torch.float32, "gates_act"), ptr(c_prev, torch.float32, "c_prev"),
        ptr(c, torch.float32, "c"), ptr(dh, torch.float32, "dh"), ptr(dh_rec, torch.float32, "dh_rec"),
        ptr(dc, torch.float32, "dc"), ptr(dgates16, torch.bfloat16, "dgates16"), n, stream_ptr())
@@ -815,6 +827,11 @@ def rollout_post(reward, terminal, frame_rec, active, ended, last_rec, episode_r
 def lstm_cell_act(gates, c_state, h_state, h_out=None, active=None):
   """Acting step of the cell, in place on the persistent state of the active envs; h_out receives the state's h."""
   n = gates.shape[0]
+  if gates.dtype == torch.bfloat16:
+    call("unreal_lstm_cell_act_g16", ptr(gates, torch.bfloat16, "gates"), ptr(c_state, torch.float32, "c_state"),
+         ptr(h_state, torch.float32, "h_state"), ptr(h_out, torch.float32, "h_out"), ptr(active, torch.uint8, "active"), n,
+         stream_ptr())
+    return h_out
   call("unreal_lstm_cell_act", ptr(gates, torch.float32, "gates"), ptr(c_state, torch.float32, "c_state"),
        ptr(h_state, torch.float32, "h_state"), ptr(h_out, torch.float32, "h_out"), ptr(active, torch.uint8, "active"), n,
        stream_ptr())

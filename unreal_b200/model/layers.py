@@ -164,8 +164,10 @@ class LstmFn(torch.autograd.Function):
   """
 
   @staticmethod
-  def forward(ctx, fc16, lar, wcat16, w32, b32, c0, h0, lstm_in, kx):
-    """fc16 [T,N,256] bf16 (fc1 output), lar [T,N,lstm_in-256] f32: packed straight into the step operands."""
+  def forward(ctx, fc16, lar, wcat16, w32, b32, c0, h0, lstm_in, kx, gates_dtype=torch.float32):
+    """fc16 [T,N,256] bf16 (fc1 output), lar [T,N,lstm_in-256] f32: packed straight into the step operands.
+    gates_dtype bf16: the step GEMM writes the gate pre-activations as bf16 and the cell keeps their activations for the
+    backward pass as bf16 (half the traffic of the HBM-bound cell kernels)."""
     t, n = fc16.shape[:2]
     kc = kx + 256
     dev = fc16.device
@@ -175,7 +177,7 @@ class LstmFn(torch.autograd.Function):
     if kx > lstm_in:
       xh[:, :, lstm_in:kx].zero_()
     xh[0, :, kx:].copy_(h0)
-    gates = torch.empty(t, n, 1024, device=dev)
+    gates = torch.empty(t, n, 1024, device=dev, dtype=gates_dtype)
     c_all = torch.empty(t + 1, n, 256, device=dev)
     h_all = torch.empty(t, n, 256, device=dev)
     h16_last = torch.empty(n, 256, device=dev, dtype=torch.bfloat16)
@@ -211,7 +213,7 @@ class LstmFn(torch.autograd.Function):
     _, db = K.relu_grad(dg2, None, want_out=False)
     # only the 256 fc1 columns carry a gradient (last_action_reward is an input)
     dfc = K.gemm_bf16(dg2, wcat16[:256], out_dtype=torch.bfloat16).view(t, n, 256)
-    return dfc, None, None, dw, db, None, None, None, None
+    return dfc, None, None, dw, db, None, None, None, None, None
 
 
 class Deconv8Fn(torch.autograd.Function):

@@ -89,6 +89,8 @@ class UnrealModel(object):
     # grad_scale before the clip -- None = 1/N, the synchronous mean of N workers; 1.0 = the sum, i.e. N workers each
     # applying its own gradient (the reference's Hogwild, to first order in the step size)
     self.grad_scale = None
+    # LSTM gate pre-activations / saved activations as bf16 (False: f32).  The cell kernels are HBM-bound on that buffer.
+    self.lstm_gates_bf16 = True
     self._cells49 = torch.tensor([[x, y] for y in range(7) for x in range(7)], dtype=torch.int32, device=self._device)
     self._fc_tab_act = torch.zeros(49, 256, dtype=torch.bfloat16, device=self._device)
     self._act_xh = {}         # acting-step [x, h] GEMM operands by batch size (persistent: padding columns stay zero)
@@ -226,6 +228,9 @@ class UnrealModel(object):
     fc = LinearFn.apply(h2.view(t * n, 2592), self.v16["W_base_fc1"], p32["W_base_fc1"], p32["b_base_fc1"], True, True)
     return fc.view(t, n, 256)
 
+  def _gates_dtype(self):
+    return torch.bfloat16 if self.lstm_gates_bf16 else torch.float32
+
   def _use_tables(self, images):
     return self.dedup_cells and images.dtype == torch.int32 and self.fused_conv and self.fused_encoder
 
@@ -243,11 +248,11 @@ class UnrealModel(object):
     if tables is not None and self._use_tables(images):
       fc = CellGatherFn.apply(tables[1], images.reshape(t * n, 2)).view(t, n, 256)
       return LstmFn.apply(fc, lar.to(torch.float32), self.wcat16, p32["lstm_kernel"], p32["lstm_bias"], c0, h0, self.lstm_in,
-                          self.kx), None
+                          self.kx, self._gates_dtype()), None
     h2 = self._encoder(p32, images.reshape(t * n, *images.shape[2:]))
     fc = self._lstm_input(p32, h2, t, n)
     return LstmFn.apply(fc, lar.to(torch.float32), self.wcat16, p32["lstm_kernel"], p32["lstm_bias"], c0, h0, self.lstm_in,
-                        self.kx), h2
+                        self.kx, self._gates_dtype()), h2
 
   def _policy_value(self, p32, h):
     """model.py:358-377 (tiny [.,256]x[256,A+1] products, fp32).  Without autograd (acting, bootstraps): one fused
@@ -351,7 +356,7 @@ class UnrealModel(object):
       K.gemm_bf16(h2.view(n, 2592), self.v16["W_base_fc1"], out=xh[:, :256], b_mn_major=True, bias=p32["b_base_fc1"], relu=True)
     xh[:, 256:self.lstm_in].copy_(lar)
     xh[:, self.kx:].copy_(h_prev)
-    return K.gemm_bf16(xh, self.wcat16, b_mn_major=True, bias=p32["lstm_bias"])
+    return K.gemm_bf16(xh, self.wcat16, b_mn_major=True, bias=p32["lstm_bias"], out_dtype=self._gates_dtype())
 
   def run_base_policy_and_value(self, sess, s_t, last_action_reward, active=None, mode=""):
     """model.py:630-660: one acting step; advances the LSTM state of the active envs."""
