@@ -194,7 +194,9 @@ def test_cell_observation_agent_equals_frame_agent(dedup):
       a, b = float(tr_a.last_losses[k]), float(tr_b.last_losses[k])
       assert abs(a - b) <= 1e-3 * max(1.0, abs(a)), (it, k, a, b)
   assert tr_b.last_feed['base']['si'].dtype == torch.int32
-  assert torch.allclose(net_a.flat, net_b.flat, rtol=1e-3, atol=3e-5 if dedup else 1e-5)
+  # cell-table: a parameter moves by <= lr * |g| / sqrt(rms + eps) ~ 7e-4 * 5 per update and the two gradients differ by
+  # the bf16 rounding of a per-cell sum (2^-8 relative): 4 updates * 3.5e-3 * 4e-3 ~ 6e-5 absolute
+  assert torch.allclose(net_a.flat, net_b.flat, rtol=1e-3, atol=1e-4 if dedup else 1e-5)
   tr_a.stop(); tr_b.stop()
 
 
