@@ -601,6 +601,24 @@ def run_b200(args):
   e2e_ms = e0.elapsed_time(e1)
   checksum = float(out["R"].sum())
   parity, parity_what = parity_check(torch, eng) if rank == 0 else ("", "")
+  # context for a K1 fraction above 1.0: K1 only WRITES, the roofline denominator (MEASURED_PEAKS.json) is a COPY.  A plain
+  # device fill of the same buffer, timed here the same way, is the write-only bandwidth of this GPU.
+  fill_gbs = None
+  if rank == 0:
+    try:
+      buf = eng.obs.view(-1)
+      for _ in range(2):
+        buf.zero_()
+      f0 = torch.cuda.Event(enable_timing=True); f1 = torch.cuda.Event(enable_timing=True)
+      torch.cuda.synchronize(dev)
+      f0.record()
+      for _ in range(3):
+        buf.zero_()
+      f1.record()
+      torch.cuda.synchronize(dev)
+      fill_gbs = 3 * buf.numel() * buf.element_size() / (f0.elapsed_time(f1) * 1e-3) / 1e9
+    except Exception:
+      fill_gbs = None
 
   h2d_bytes, d2h_bytes, launches_per_pass = eng.h2d_bytes_per_pass, eng.d2h_bytes_per_pass, eng.launches_per_pass
   agent = None
@@ -671,7 +689,11 @@ def run_b200(args):
                      "whole_pass_gbs": path_bytes / (total_ms / K * 1e-3) / 1e9,
                      "whole_pass_frac": path_bytes / (total_ms / K * 1e-3) / 1e9 / peak,
                      "k3_us": k3_ms * 1e3, "k4_us": k4_ms * 1e3,
-                     "k4_gbs": n * 65600 / (k4_ms * 1e-3) / 1e9},
+                     "k4_gbs": n * 65600 / (k4_ms * 1e-3) / 1e9,
+                     "write_only_fill_gbs": fill_gbs,
+                     "note": "K1 is a pure writer; `peak` is the measured COPY bandwidth (read + write), which a write-only "
+                             "stream can exceed: `write_only_fill_gbs` is torch's zero_() over the same obs buffer, timed in "
+                             "this run"},
     }
     traffic_file = os.path.join(ROOT, "profiles", "k1_traffic.json")
     if os.path.exists(traffic_file):
