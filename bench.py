@@ -607,6 +607,8 @@ def run_b200(args):
   if rank == 0:
     try:
       buf = eng.obs.view(-1)
+      if buf.dtype == torch.uint8 and buf.numel() % 4 == 0:
+        buf = buf.view(torch.float32)          # torch's byte fill is not a bandwidth test; same bytes as 4-byte words
       for _ in range(2):
         buf.zero_()
       f0 = torch.cuda.Event(enable_timing=True); f1 = torch.cuda.Event(enable_timing=True)
