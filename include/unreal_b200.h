@@ -384,6 +384,17 @@ int unreal_a3c_head_bwd(const float* h, const float* wp, const float* wv, const 
 int unreal_cell_gather(const void* table_bf16, const int32_t* pos, void* out_bf16, int64_t ld_out, int64_t s, int d,
                        void* stream);
 int unreal_cell_segment_sum(const void* dy, int dy_dtype, const int32_t* pos, float* out, int64_t s, int d, void* stream);
+/* Pixel-control head with its loss fused into the deconv (unreal_pc_deconv_fwd + unreal_pc_loss + unreal_pc_loss_grad16 in
+ * one kernel; model.py:418-441, :531-546): h bf16 [S,9,9,32] -> loss (double, accumulated) and d loss / d (pre-ReLU deconv
+ * output) as conv2-geometry input dy16 bf16 [S,400,16] (channels 8..15 zero), NOT yet multiplied by the upstream
+ * gradient, plus the deconv bias gradient db8 [8] (caller-zeroed, nullable).  The f32 head output is never materialised.
+ * unreal_conv2_fwd_linear_scaled = unreal_conv2_fwd_linear with the accumulators multiplied by *scale (device scalar):
+ * the backward convolution applying that upstream gradient. */
+int unreal_pc_deconv_loss(const void* h_bf16, const void* w_dtaps_bf16, const float* bias8, const int32_t* act,
+                          const float* target, const float* mask, int a, float lam, int s, double* loss, void* dy16_bf16,
+                          float* db8, void* stream);
+int unreal_conv2_fwd_linear_scaled(const void* in_bf16, const void* w_taps_bf16, const float* scale, void* out_bf16, int s,
+                                   void* stream);
 /* Reward-prediction head after its fc GEMM (model.py:482-488 softmax, :571-575 loss).  logits8 [N,8] f32: columns 0..2 =
  * features . W_rp (the bf16 tcgen05 GEMM on the weight shadow padded to 8 columns), bias [3] added here.
  *   p_out (nullable) [N,3] = softmax(logits + bias)                                  (run_rp_c, model.py:723-728)

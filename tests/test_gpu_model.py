@@ -520,3 +520,31 @@ def test_cell_table_encoder_equals_dense_encoder():
     res[dedup] = (pi.clone(), v.clone(), q.clone())
   for a, b in zip(res[False], res[True]):
     assert torch.allclose(a, b, rtol=1e-4, atol=1e-5)
+
+
+def test_fused_pc_deconv_loss_equals_the_three_kernel_path():
+  """unreal_pc_deconv_loss (pixel-control deconv forward + dueling / gather / L2 loss + its gradient in ONE kernel, the
+  f32 head output never materialised) against PcHeadLossFn (deconv -> y8 f32 -> unreal_pc_loss -> unreal_pc_loss_grad16):
+  same loss, same gradients for the input, both deconv filters and biases, including an upstream gradient != 1."""
+  from unreal_b200.model.layers import PcFusedHeadLossFn, PcHeadLossFn
+  dev = torch.device("cuda", 0)
+  m = _model(dev, seed=9, n=2)
+  p32 = m._views(m.flat)
+  g = torch.Generator(device=dev).manual_seed(4)
+  for s in (3, 129, 700):
+    hp = torch.relu(torch.randn(s, 2592, device=dev, generator=g)).to(torch.bfloat16)
+    act = torch.randint(0, A, (s,), device=dev, generator=g, dtype=torch.int32)
+    tgt = torch.rand(s, 400, device=dev, generator=g)
+    msk = (torch.rand(s, device=dev, generator=g) < 0.8).float()
+    res = []
+    for fn in (PcHeadLossFn, PcFusedHeadLossFn):
+      x = hp.clone().requires_grad_(True)
+      leaves = [p32[k].detach().clone().requires_grad_(True) for k in ("W_pc_deconv_v", "b_pc_deconv_v", "W_pc_deconv_a", "b_pc_deconv_a")]
+      loss = fn.apply(x, m.pc_taps, m.pc_b8, m.pc_lin_taps, leaves[0], leaves[1], leaves[2], leaves[3], act, tgt, msk, A, 0.05)
+      (loss * 0.37).backward()
+      res.append((loss.detach(), x.grad.float(), [l.grad for l in leaves]))
+    (l0, dx0, g0), (l1, dx1, g1) = res
+    assert abs(float(l0) - float(l1)) <= 1e-5 * max(1.0, abs(float(l0))), s
+    assert float((dx0 - dx1).abs().max()) <= 2.0 ** -7 * float(dx0.abs().max()) + 1e-9, s      # both round dh to bf16
+    for a_, b_, name in zip(g0, g1, ("Wv", "bv", "Wa", "ba")):
+      assert torch.allclose(a_, b_, rtol=1e-3, atol=1e-4 * float(a_.abs().max()) + 1e-9), (s, name)

@@ -89,6 +89,7 @@ struct ConvArgs {
   int box_bytes;      // bytes one A box delivers
   int mode;           // 2: conv2 over h1
   int relu;           // apply max(., 0) in the epilogue
+  const float* scale; // nullable device scalar multiplied into the accumulators (the upstream gradient of a backward conv)
 };
 
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2, int c3) {
@@ -201,6 +202,7 @@ conv_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_
     float b[N];
 #pragma unroll
     for (int j = 0; j < N; ++j) b[j] = g.bias ? __ldg(g.bias + j) : 0.f;
+    const float sc = g.scale ? __ldg(g.scale) : 1.f;
     for (int it = blockIdx.x; it < g.items; it += gridDim.x) {
       mbar_wait(tfull_bar(acc), acc_phase);
       fence_after_sync();
@@ -218,8 +220,8 @@ conv_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_
           uint32_t pk[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            float v0 = __uint_as_float(r[8 * q + 2 * j]) + b[8 * q + 2 * j];
-            float v1 = __uint_as_float(r[8 * q + 2 * j + 1]) + b[8 * q + 2 * j + 1];
+            float v0 = __uint_as_float(r[8 * q + 2 * j]) * sc + b[8 * q + 2 * j];
+            float v1 = __uint_as_float(r[8 * q + 2 * j + 1]) * sc + b[8 * q + 2 * j + 1];
             if (g.relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
             __nv_bfloat162 p = __floats2bfloat162_rn(v0, v1);
             pk[j] = *reinterpret_cast<uint32_t*>(&p);
@@ -809,11 +811,26 @@ constexpr int kDgSmem = kDgWBytes + kDgStages * kDgABytes + 1024 + 1024;
 // (model.py:418-430: the same 4x4 stride-2 VALID transposed convolution [S,9,9,32] -> [S,20,20,8], filter
 // [kh,kw,out,in] = conv2's HWIO with c = out): N = 32 accumulator columns, epilogue adds the bias, applies
 // ReLU and writes f32 -- replaces a GEMM into 41 KB/sample of f32 columns + col2im.
+// CO = 8 with `pl.target` set: the pixel-control head's loss FUSED into the deconv's epilogue (model.py:431-441 dueling
+// combine + Q(a) gather, :531-546 lambda * 0.5 * sum (R - Q_a)^2).  A thread holds all 8 channels of its 2x2 pixels, so
+// it finishes the loss and writes d loss / d (pre-ReLU output) straight as conv2-geometry input [S,400,16] bf16
+// (channels 8..15 zero; un-scaled by the upstream gradient, which the backward convolutions apply) plus the bias
+// gradient -- the f32 head output [S,20,20,8] (2.1 GB at 8192 envs x 20) is never written, nor read back twice.
+struct PcLossArgs {
+  const int32_t* act;     // [S]
+  const float* target;    // [S,20,20]
+  const float* mask;      // [S]
+  double* loss;           // += lam * 0.5 * sum mask (target - Q[act])^2
+  int a;                  // number of actions
+  float lam;
+};
+
 template <int CO>
 __global__ void __launch_bounds__(kConvThreads, 2)
 conv2_dgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_w,
                            void* __restrict__ out_raw, const float* __restrict__ bias, int samples,
-                           const __nv_bfloat16* __restrict__ mask_y, float* __restrict__ db, int pitch21) {
+                           const __nv_bfloat16* __restrict__ mask_y, float* __restrict__ db, int pitch21,
+                           const PcLossArgs pl) {
   constexpr int kN = 4 * CO;                         // (dy, dx, c) accumulator columns
   constexpr int kTapBytes = kN * 64;                 // one resident tap filter [kN rows x 64 B]
   extern __shared__ uint8_t smem_raw[];
@@ -900,6 +917,7 @@ conv2_dgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __gr
     float dbacc[16];
 #pragma unroll
     for (int c = 0; c < 16; ++c) dbacc[c] = 0.f;
+    float loss_part = 0.f;
     for (int it = blockIdx.x; it < samples; it += gridDim.x) {
       mbar_wait(tfull_bar(acc), acc_phase);
       fence_after_sync();
@@ -912,6 +930,51 @@ conv2_dgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __gr
         fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty_bar(acc));
+        if (pl.target != nullptr) {
+          if (r < 100) {
+            const float m = __ldg(pl.mask + it);
+            const int a = __ldg(pl.act + it);
+            const float inv_a = 1.0f / (float)pl.a;
+            __nv_bfloat16* out16 = reinterpret_cast<__nv_bfloat16*>(out_raw);
+#pragma unroll
+            for (int dy = 0; dy < 2; ++dy) {
+              const int64_t pix = ((int64_t)it * 20 + 2 * Y + dy) * 20 + 2 * X;
+              const float2 tg = __ldcs(reinterpret_cast<const float2*>(pl.target + pix));
+              uint4* dst = reinterpret_cast<uint4*>(out16 + pix * 16);
+#pragma unroll
+              for (int dx = 0; dx < 2; ++dx) {
+                float y[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) y[c] = fmaxf(__uint_as_float(v[dy * 16 + dx * 8 + c]) + b8[c], 0.f);
+                float sum = 0.f, qa = 0.f;
+#pragma unroll
+                for (int k = 0; k < 7; ++k) {
+                  if (k < pl.a) { sum += y[1 + k]; if (k == a) qa = y[1 + k]; }
+                }
+                qa = y[0] + qa - sum * inv_a;
+                const float diff = qa - (dx ? tg.y : tg.x);
+                loss_part += m * diff * diff;
+                const float g = pl.lam * m * diff;
+                float d[8];
+                d[0] = y[0] > 0.f ? g : 0.f;
+#pragma unroll
+                for (int k = 0; k < 7; ++k) d[1 + k] = (k < pl.a && y[1 + k] > 0.f) ? g * ((k == a ? 1.f : 0.f) - inv_a) : 0.f;
+                uint32_t pk[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  __nv_bfloat162 p = __floats2bfloat162_rn(d[2 * j], d[2 * j + 1]);
+                  pk[j] = *reinterpret_cast<uint32_t*>(&p);
+                  const float2 f = __bfloat1622float2(p);      // the bias gradient sums the ROUNDED values
+                  dbacc[2 * j] += f.x; dbacc[2 * j + 1] += f.y;
+                }
+                __stcs(dst + 2 * dx, make_uint4(pk[0], pk[1], pk[2], pk[3]));
+                __stcs(dst + 2 * dx + 1, make_uint4(0u, 0u, 0u, 0u));
+              }
+            }
+          }
+          if (++acc == kDgAcc) { acc = 0; acc_phase ^= 1u; }
+          continue;
+        }
         if (r < 100) {
           float* base = reinterpret_cast<float*>(out_raw) + (((int64_t)it * 20 + 2 * Y) * 20 + 2 * X) * 8;
 #pragma unroll
@@ -1009,6 +1072,22 @@ conv2_dgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __gr
         if (lane == 0) atomicAdd(db + c, x);
       }
     }
+    if (CO == 8 && pl.target != nullptr) {
+      if (db != nullptr) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          float x = dbacc[c];
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+          if (lane == 0) atomicAdd(db + c, x);
+        }
+      }
+      if (pl.loss != nullptr) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) loss_part += __shfl_xor_sync(0xffffffffu, loss_part, o);
+        if (lane == 0) atomicAdd(pl.loss, 0.5 * (double)pl.lam * (double)loss_part);
+      }
+    }
   }
   __syncwarp();
   fence_before_sync();
@@ -1088,7 +1167,7 @@ extern "C" int unreal_conv1_fwd_maze(const int32_t* pos, const void* w_taps_bf16
 }
 
 static int conv_fwd_impl(const void* in_bf16, int layer, const void* w_taps_bf16, const float* bias, void* out_bf16, int s,
-                         int relu, void* stream) {
+                         int relu, void* stream, const float* scale = nullptr) {
   UNREAL_REQUIRE(in_bf16 && w_taps_bf16 && out_bf16 && s > 0, "unreal_conv_fwd: null buffer or s <= 0");
   UNREAL_REQUIRE(layer == 1 || layer == 2, "unreal_conv_fwd: layer must be 1 (conv1 over x') or 2 (conv2 over h1)");
   UNREAL_REQUIRE(aligned16(in_bf16) && aligned16(w_taps_bf16) && aligned16(out_bf16),
@@ -1098,6 +1177,7 @@ static int conv_fwd_impl(const void* in_bf16, int layer, const void* w_taps_bf16
   g.bias = bias;
   g.mode = layer;
   g.relu = relu;
+  g.scale = scale;
   int rc;
   const int n = layer == 1 ? 16 : 32;
   if (layer == 1) {
@@ -1153,6 +1233,11 @@ extern "C" int unreal_conv_fwd(const void* in_bf16, int layer, const void* w_tap
 
 extern "C" int unreal_conv2_fwd_linear(const void* in_bf16, const void* w_taps_bf16, void* out_bf16, int s, void* stream) {
   return conv_fwd_impl(in_bf16, 2, w_taps_bf16, nullptr, out_bf16, s, 0, stream);
+}
+
+extern "C" int unreal_conv2_fwd_linear_scaled(const void* in_bf16, const void* w_taps_bf16, const float* scale, void* out_bf16,
+                                              int s, void* stream) {
+  return conv_fwd_impl(in_bf16, 2, w_taps_bf16, nullptr, out_bf16, s, 0, stream, scale);
 }
 
 static int conv1_wgrad_launch(const void* xpp_bf16, const void* dy_planes_bf16, float* dw_taps, int s, int pitch21,
@@ -1229,7 +1314,8 @@ extern "C" int unreal_conv2_wgrad(const void* h1_bf16, const void* dy_bf16, floa
 
 template <int CO>
 static int launch_deconv(const void* dy_bf16, const void* w_dtaps_bf16, void* out, const float* bias, int s, void* stream,
-                         const void* mask_y = nullptr, float* db = nullptr, int pitch21 = 0) {
+                         const void* mask_y = nullptr, float* db = nullptr, int pitch21 = 0,
+                         PcLossArgs pl = PcLossArgs{nullptr, nullptr, nullptr, nullptr, 0, 0.f}) {
   CUtensorMap ta, tw;
   {
     const uint64_t dims[4] = {32, 9, 9, (uint64_t)s};           // dY2 [S][9 Y][9 X][32 o]
@@ -1253,7 +1339,7 @@ static int launch_deconv(const void* dy_bf16, const void* w_dtaps_bf16, void* ou
   const int sms = sm_count();
   if (sms <= 0) return UNREAL_ECUDA;
   conv2_dgrad_tcgen05_kernel<CO><<<s < 2 * sms ? s : 2 * sms, kConvThreads, kDgSmem, as_stream(stream)>>>(
-      ta, tw, out, bias, s, reinterpret_cast<const __nv_bfloat16*>(mask_y), db, pitch21);
+      ta, tw, out, bias, s, reinterpret_cast<const __nv_bfloat16*>(mask_y), db, pitch21, pl);
   UNREAL_LAUNCH_CHECK("conv2_dgrad_tcgen05_kernel");
   return UNREAL_OK;
 }
@@ -1277,4 +1363,16 @@ extern "C" int unreal_pc_deconv_fwd(const void* h_bf16, const void* w_dtaps_bf16
   UNREAL_REQUIRE(h_bf16 && w_dtaps_bf16 && y8 && s > 0, "unreal_pc_deconv_fwd: null buffer or s <= 0");
   UNREAL_REQUIRE(aligned16(h_bf16) && aligned16(w_dtaps_bf16) && aligned16(y8), "unreal_pc_deconv_fwd: 16-byte alignment");
   return launch_deconv<8>(h_bf16, w_dtaps_bf16, y8, bias8, s, stream);
+}
+
+extern "C" int unreal_pc_deconv_loss(const void* h_bf16, const void* w_dtaps_bf16, const float* bias8, const int32_t* act,
+                                     const float* target, const float* mask, int a, float lam, int s, double* loss,
+                                     void* dy16_bf16, float* db8, void* stream) {
+  UNREAL_REQUIRE(h_bf16 && w_dtaps_bf16 && act && target && mask && dy16_bf16 && s > 0,
+                 "unreal_pc_deconv_loss: null buffer or s <= 0");
+  UNREAL_REQUIRE(a >= 1 && a <= 7, "unreal_pc_deconv_loss: action count %d not in 1..7 (8-channel padded head)", a);
+  UNREAL_REQUIRE(aligned16(h_bf16) && aligned16(w_dtaps_bf16) && aligned16(dy16_bf16) && aligned16(target),
+                 "unreal_pc_deconv_loss: 16-byte alignment");
+  return launch_deconv<8>(h_bf16, w_dtaps_bf16, dy16_bf16, bias8, s, stream, nullptr, db8, 0,
+                          PcLossArgs{act, target, mask, loss, a, lam});
 }

@@ -708,14 +708,32 @@ def pc_loss_grad16(y8, act, target, mask, num_actions, lam, go):
   return dy16, db8
 
 
-def conv2_fwd_linear(x, w_taps, out=None):
-  """conv2's geometry without bias / ReLU: x bf16 [S,20,20,16], w_taps = conv_taps(W [4,4,16,32], 2) -> bf16 [S,9,9,32]."""
+def conv2_fwd_linear(x, w_taps, out=None, scale=None):
+  """conv2's geometry without bias / ReLU: x bf16 [S,20,20,16], w_taps = conv_taps(W [4,4,16,32], 2) -> bf16 [S,9,9,32];
+  `scale`: device scalar (f32 [1]) multiplied into the result before rounding."""
   s = x.shape[0]
   if out is None:
     out = torch.empty(s, 9, 9, 32, dtype=torch.bfloat16, device=x.device)
+  if scale is not None:
+    call("unreal_conv2_fwd_linear_scaled", ptr(x, torch.bfloat16, "x"), ptr(w_taps, torch.bfloat16, "w_taps"),
+         ptr(scale, torch.float32, "scale"), ptr(out, torch.bfloat16, "out"), s, stream_ptr())
+    return out
   call("unreal_conv2_fwd_linear", ptr(x, torch.bfloat16, "x"), ptr(w_taps, torch.bfloat16, "w_taps"),
        ptr(out, torch.bfloat16, "out"), s, stream_ptr())
   return out
+
+
+def pc_deconv_loss(h16, w_dtaps, bias8, act, target, mask, num_actions, lam):
+  """Pixel-control head + loss in one kernel: h16 bf16 [S,9,9,32] (any view of S*2592) -> (loss f64 [1],
+  dy16 bf16 [S,400,16] = d loss / d pre-ReLU output, un-scaled by the upstream gradient, db8 [8])."""
+  s = h16.numel() // 2592
+  loss = torch.zeros(1, dtype=torch.float64, device=h16.device)
+  dy16 = torch.empty(s, 400, 16, dtype=torch.bfloat16, device=h16.device)
+  db8 = torch.zeros(8, dtype=torch.float32, device=h16.device)
+  call("unreal_pc_deconv_loss", ptr(h16, torch.bfloat16, "h16"), ptr(w_dtaps, torch.bfloat16, "w_dtaps"),
+       ptr(bias8, torch.float32, "bias8"), ptr(act, torch.int32, "act"), ptr(target, torch.float32, "target"),
+       ptr(mask, torch.float32, "mask"), int(num_actions), float(lam), s, ptr(loss), ptr(dy16), ptr(db8), stream_ptr())
+  return loss, dy16, db8
 
 
 def a3c_head(h, wp, bp, wv, bv, act=None, adv=None, ret=None, mask=None, entropy_beta=0.0, value_coef=0.25,

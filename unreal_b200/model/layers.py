@@ -302,6 +302,35 @@ class PcHeadLossFn(torch.autograd.Function):
             db8[1:1 + a].clone(), None, None, None, None, None)
 
 
+class PcFusedHeadLossFn(torch.autograd.Function):
+  """PcHeadLossFn with the loss fused INTO the deconv kernel (`unreal_pc_deconv_loss`): the f32 head output [S,20,20,8]
+  (2.1 GB per update at 8192 envs) is never written -- the epilogue that holds a pixel's 8 channels finishes the dueling /
+  gather / L2 loss and writes its gradient as the conv2-geometry bf16 operand of the backward pass directly.  The upstream
+  gradient (a device scalar) is applied by the backward convolutions (`unreal_conv2_fwd_linear_scaled`) and to the two
+  small filter / bias gradients."""
+
+  @staticmethod
+  def forward(ctx, h16, taps, b8, lin_taps, wv32, bv32, wa32, ba32, act, target, mask, num_actions, lam):
+    loss, dy16, db8 = K.pc_deconv_loss(h16, taps, b8, act, target, mask, num_actions, lam)
+    ctx.num_actions = num_actions
+    ctx.lin_taps = lin_taps
+    ctx.save_for_backward(h16, dy16, db8)
+    return loss[0].to(torch.float32)
+
+  @staticmethod
+  def backward(ctx, go):
+    h16, dy16, db8 = ctx.saved_tensors
+    a = ctx.num_actions
+    s = h16.shape[0]
+    go32 = go.to(torch.float32).reshape(1).contiguous()
+    dy16 = dy16.view(s, 20, 20, 16)
+    dh = K.conv2_fwd_linear(dy16, ctx.lin_taps, scale=go32).view(s, 2592)
+    dw16 = K.conv2_wgrad(dy16, h16.reshape(s * 81, 32)) * go32           # [4,4,16,32]: channels 8..15 are padding
+    db8 = db8 * go32
+    return (dh, None, None, None, dw16[:, :, 0:1].contiguous(), db8[0:1].clone(), dw16[:, :, 1:1 + a].contiguous(),
+            db8[1:1 + a].clone(), None, None, None, None, None)
+
+
 class A3CHeadLossFn(torch.autograd.Function):
   """Policy / value heads and their losses as ONE autograd node over two kernels (model.py:358-377, :499-527, :556-565):
   the forward pass computes logits, softmax, value, the policy / value / entropy sums and the gradients w.r.t. logits

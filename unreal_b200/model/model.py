@@ -26,7 +26,7 @@ import torch
 
 from .. import _lib
 from .. import kernels as K
-from .layers import (A3CHeadLossFn, CellGatherFn, ConvFn, Deconv8Fn, EncoderFn, LinearFn, LstmFn, PcHeadLossFn, PcLossFn, RpCellLossFn,
+from .layers import (A3CHeadLossFn, CellGatherFn, ConvFn, Deconv8Fn, EncoderFn, LinearFn, LstmFn, PcFusedHeadLossFn, PcHeadLossFn, PcLossFn, RpCellLossFn,
                      RpHeadLossFn, split_k_for)
 
 
@@ -91,6 +91,8 @@ class UnrealModel(object):
     self.grad_scale = None
     # LSTM gate pre-activations / saved activations as bf16 (False: f32).  The cell kernels are HBM-bound on that buffer.
     self.lstm_gates_bf16 = True
+    # pixel-control loss inside the deconv kernel's epilogue (False: deconv -> f32 head output -> separate loss / gradient passes)
+    self.fused_pc_loss = True
     self._cells49 = torch.tensor([[x, y] for y in range(7) for x in range(7)], dtype=torch.int32, device=self._device)
     self._fc_tab_act = torch.zeros(49, 256, dtype=torch.bfloat16, device=self._device)
     self._act_xh = {}         # acting-step [x, h] GEMM operands by batch size (persistent: padding columns stay zero)
@@ -456,7 +458,7 @@ class UnrealModel(object):
       if self.fused_conv and self.fused_encoder:
         hp = LinearFn.apply(h.reshape(L * n, 256).to(torch.bfloat16), self.v16["W_pc_fc1"], p32["W_pc_fc1"], p32["b_pc_fc1"],
                             True, True)
-        parts["pc"] = PcHeadLossFn.apply(hp, self.pc_taps, self.pc_b8, self.pc_lin_taps, p32["W_pc_deconv_v"],
+        parts["pc"] = (PcFusedHeadLossFn if self.fused_pc_loss else PcHeadLossFn).apply(hp, self.pc_taps, self.pc_b8, self.pc_lin_taps, p32["W_pc_deconv_v"],
                                          p32["b_pc_deconv_v"], p32["W_pc_deconv_a"], p32["b_pc_deconv_a"], act, tgt, msk,
                                          self._action_size, self._pixel_change_lambda)
       else:
