@@ -546,5 +546,7 @@ def test_fused_pc_deconv_loss_equals_the_three_kernel_path():
     (l0, dx0, g0), (l1, dx1, g1) = res
     assert abs(float(l0) - float(l1)) <= 1e-5 * max(1.0, abs(float(l0))), s
     assert float((dx0 - dx1).abs().max()) <= 2.0 ** -7 * float(dx0.abs().max()) + 1e-9, s      # both round dh to bf16
+    # the two paths round d loss / d y to bf16 at different points (before / after the upstream gradient is applied):
+    # filter and bias gradients agree to the bf16 operand rounding, 2^-8 of the largest element
     for a_, b_, name in zip(g0, g1, ("Wv", "bv", "Wa", "ba")):
-      assert torch.allclose(a_, b_, rtol=1e-3, atol=1e-4 * float(a_.abs().max()) + 1e-9), (s, name)
+      assert float((a_ - b_).abs().max()) <= 2.0 ** -8 * float(a_.abs().max()) + 1e-9, (s, name)
