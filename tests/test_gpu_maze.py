@@ -239,7 +239,8 @@ def test_observation_modes_agree_through_resets_and_masks():
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.uint8], ids=["f32", "u8"])
 @pytest.mark.parametrize("auto_reset", [False, True], ids=["no-reset", "auto-reset"])
-def test_window_kernel_equals_step_by_step(K, dtype, auto_reset):
+@pytest.mark.parametrize("wvariant", [-1, 0, 2, 3], ids=["default", "cta-per-item", "warp-per-item", "warp-per-env"])
+def test_window_kernel_equals_step_by_step(K, dtype, auto_reset, wvariant):
   """unreal_maze_window (T process() calls per env in one launch: per-item re-simulation for f32, one warp per env for
   u8) against T unreal_maze_step calls, bit for bit on every output and on the carried state -- env counts off the
   CTA / warp granularity, window lengths 1 .. 32 (the maximum), frames / maps optional, two windows in a row."""
@@ -258,8 +259,13 @@ def test_window_kernel_equals_step_by_step(K, dtype, auto_reset):
         K.maze_step(a_st, acts[i], obs=want["obs"][i], pc=want["pc"][i], reward=want["reward"][i],
                     terminal=want["terminal"][i], frame_rec=want["rec"][i], auto_reset=auto_reset)
       got = {k: torch.full_like(v, 3) for k, v in want.items()}
-      K.maze_window(b_st, acts, obs=got["obs"], pc=got["pc"], reward=got["reward"], terminal=got["terminal"],
-                    frame_rec=got["rec"], auto_reset=auto_reset)
+      from unreal_b200 import _lib as L
+      L.set_tunable("maze_render_variant", wvariant)         # all three window kernels, whatever the default for the dtype is
+      try:
+        K.maze_window(b_st, acts, obs=got["obs"], pc=got["pc"], reward=got["reward"], terminal=got["terminal"],
+                      frame_rec=got["rec"], auto_reset=auto_reset)
+      finally:
+        L.set_tunable("maze_render_variant", -1)
       for k in want:
         assert torch.equal(got[k], want[k]), (n, t, rep, k)
       for f in ("pos", "last_action", "last_reward"):
