@@ -416,23 +416,12 @@ __global__ void __launch_bounds__(kThreads) maze_window_cta_kernel(WindowArgs a)
   if (a.pc != nullptr && tid >= kThreads - kPcElems / 4) write_pc(a.pc + b * kPcElems, f, tid - (kThreads - kPcElems / 4));
   if (a.obs == nullptr || gsub >= R) return;
   uint4* out = reinterpret_cast<uint4*>(reinterpret_cast<T*>(a.obs) + b * kFrameElems) + c;
-  if constexpr (G % R == 0) {
-    // band-major: the 128-bit word of a (band, chunk column) is built once and stored to the band's G / R groups of this
-    // thread (f32: 7 words for 21 stores; the group-major loop rebuilt it per store and kept the ALU pipe 66 % busy)
 #pragma unroll
-    for (int cy = 0; cy < UNREAL_MAZE_GRID; ++cy) {
-      const uint4 v = band_value(m, c_maze.wall_rows[cy], cy == f.ry, f.rx);
-#pragma unroll
-      for (int k = 0; k < G / R; ++k) __stcs(out + (size_t)(cy * G + gsub + R * k) * kChunksPerGroup, v);
-    }
-  } else {
-#pragma unroll
-    for (int j = 0; j < (kGroups + R - 1) / R; ++j) {
-      const int g = gsub + R * j;
-      if (g < kGroups) {
-        const int cy = g / G;
-        __stcs(out + (size_t)g * kChunksPerGroup, band_value(m, c_maze.wall_rows[cy], cy == f.ry, f.rx));
-      }
+  for (int j = 0; j < (kGroups + R - 1) / R; ++j) {
+    const int g = gsub + R * j;
+    if (g < kGroups) {
+      const int cy = g / G;
+      __stcs(out + (size_t)g * kChunksPerGroup, band_value(m, c_maze.wall_rows[cy], cy == f.ry, f.rx));
     }
   }
 }
