@@ -395,6 +395,10 @@ int unreal_pc_deconv_loss(const void* h_bf16, const void* w_dtaps_bf16, const fl
                           float* db8, void* stream);
 int unreal_conv2_fwd_linear_scaled(const void* in_bf16, const void* w_taps_bf16, const float* scale, void* out_bf16, int s,
                                    void* stream);
+/* The bootstrap of Trainer._process_pc (run_pc_q_max, model.py:707-712; :431-441): the same deconv with the dueling combine
+ * and the max over actions in its epilogue -> qmax f32 [S,20,20]; the head output itself is not written. */
+int unreal_pc_deconv_qmax(const void* h_bf16, const void* w_dtaps_bf16, const float* bias8, int a, int s, float* qmax,
+                          void* stream);
 /* Reward-prediction head after its fc GEMM (model.py:482-488 softmax, :571-575 loss).  logits8 [N,8] f32: columns 0..2 =
  * features . W_rp (the bf16 tcgen05 GEMM on the weight shadow padded to 8 columns), bias [3] added here.
  *   p_out (nullable) [N,3] = softmax(logits + bias)                                  (run_rp_c, model.py:723-728)

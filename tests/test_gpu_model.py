@@ -550,3 +550,19 @@ def test_fused_pc_deconv_loss_equals_the_three_kernel_path():
     # filter and bias gradients agree to the bf16 operand rounding, 2^-8 of the largest element
     for a_, b_, name in zip(g0, g1, ("Wv", "bv", "Wa", "ba")):
       assert float((a_ - b_).abs().max()) <= 2.0 ** -8 * float(a_.abs().max()) + 1e-9, (s, name)
+
+
+def test_pc_q_max_epilogue_equals_the_materialised_head():
+  """run_pc_q_max with the dueling combine + max over actions inside the deconv's epilogue (unreal_pc_deconv_qmax) against
+  the path that materialises the [N,20,20,8] head output and reduces it with torch ops: same maps (fp32 order only)."""
+  dev = torch.device("cuda", 0)
+  m = _model(dev, seed=12, n=5)
+  g = torch.Generator(device=dev).manual_seed(6)
+  frames = torch.rand(5, 84, 84, 3, device=dev, generator=g)
+  lar = torch.zeros(5, A + 1, device=dev); lar[:, 1] = 1.0; lar[:, A] = -1.0
+  out = {}
+  for fused in (False, True):
+    m.fused_pc_loss = fused
+    out[fused] = m.run_pc_q_max(None, {'image': frames}, lar).clone()
+  assert tuple(out[True].shape) == (5, 20, 20)
+  assert torch.allclose(out[True], out[False], rtol=1e-5, atol=1e-6)

@@ -823,6 +823,7 @@ struct PcLossArgs {
   double* loss;           // += lam * 0.5 * sum mask (target - Q[act])^2
   int a;                  // number of actions
   float lam;
+  float* qmax;            // set (with target == NULL): write only max_a Q [S,20,20] (run_pc_q_max, model.py:707-712)
 };
 
 template <int CO>
@@ -930,6 +931,31 @@ conv2_dgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __gr
         fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty_bar(acc));
+        if (pl.qmax != nullptr) {
+          // bootstrap path: the dueling combine and max over actions in the epilogue, 1.6 KB out per sample instead of 12.8
+          if (r < 100) {
+            const float inv_a = 1.0f / (float)pl.a;
+#pragma unroll
+            for (int dy = 0; dy < 2; ++dy) {
+              float q2[2];
+#pragma unroll
+              for (int dx = 0; dx < 2; ++dx) {
+                float y[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) y[c] = fmaxf(__uint_as_float(v[dy * 16 + dx * 8 + c]) + b8[c], 0.f);
+                float sum = 0.f, best = -3.4e38f;
+#pragma unroll
+                for (int k = 0; k < 7; ++k) {
+                  if (k < pl.a) { sum += y[1 + k]; best = fmaxf(best, y[1 + k]); }
+                }
+                q2[dx] = y[0] + best - sum * inv_a;          // max_a (V + A_a - mean A) = V + max_a A_a - mean A
+              }
+              *reinterpret_cast<float2*>(pl.qmax + ((int64_t)it * 20 + 2 * Y + dy) * 20 + 2 * X) = make_float2(q2[0], q2[1]);
+            }
+          }
+          if (++acc == kDgAcc) { acc = 0; acc_phase ^= 1u; }
+          continue;
+        }
         if (pl.target != nullptr) {
           if (r < 100) {
             const float m = __ldg(pl.mask + it);
@@ -1315,7 +1341,7 @@ extern "C" int unreal_conv2_wgrad(const void* h1_bf16, const void* dy_bf16, floa
 template <int CO>
 static int launch_deconv(const void* dy_bf16, const void* w_dtaps_bf16, void* out, const float* bias, int s, void* stream,
                          const void* mask_y = nullptr, float* db = nullptr, int pitch21 = 0,
-                         PcLossArgs pl = PcLossArgs{nullptr, nullptr, nullptr, nullptr, 0, 0.f}) {
+                         PcLossArgs pl = PcLossArgs{nullptr, nullptr, nullptr, nullptr, 0, 0.f, nullptr}) {
   CUtensorMap ta, tw;
   {
     const uint64_t dims[4] = {32, 9, 9, (uint64_t)s};           // dY2 [S][9 Y][9 X][32 o]
@@ -1374,5 +1400,14 @@ extern "C" int unreal_pc_deconv_loss(const void* h_bf16, const void* w_dtaps_bf1
   UNREAL_REQUIRE(aligned16(h_bf16) && aligned16(w_dtaps_bf16) && aligned16(dy16_bf16) && aligned16(target),
                  "unreal_pc_deconv_loss: 16-byte alignment");
   return launch_deconv<8>(h_bf16, w_dtaps_bf16, dy16_bf16, bias8, s, stream, nullptr, db8, 0,
-                          PcLossArgs{act, target, mask, loss, a, lam});
+                          PcLossArgs{act, target, mask, loss, a, lam, nullptr});
+}
+
+extern "C" int unreal_pc_deconv_qmax(const void* h_bf16, const void* w_dtaps_bf16, const float* bias8, int a, int s, float* qmax,
+                                     void* stream) {
+  UNREAL_REQUIRE(h_bf16 && w_dtaps_bf16 && qmax && s > 0, "unreal_pc_deconv_qmax: null buffer or s <= 0");
+  UNREAL_REQUIRE(a >= 1 && a <= 7, "unreal_pc_deconv_qmax: action count %d not in 1..7 (8-channel padded head)", a);
+  UNREAL_REQUIRE(aligned16(h_bf16) && aligned16(w_dtaps_bf16) && aligned16(qmax), "unreal_pc_deconv_qmax: 16-byte alignment");
+  return launch_deconv<8>(h_bf16, w_dtaps_bf16, qmax, bias8, s, stream, nullptr, nullptr, 0,
+                          PcLossArgs{nullptr, nullptr, nullptr, nullptr, a, 0.f, qmax});
 }

@@ -723,6 +723,16 @@ def conv2_fwd_linear(x, w_taps, out=None, scale=None):
   return out
 
 
+def pc_deconv_qmax(h16, w_dtaps, bias8, num_actions, out=None):
+  """max over actions of the pixel-control Q map, straight from the deconv's epilogue: h16 bf16 [S,9,9,32] -> f32 [S,20,20]."""
+  s = h16.numel() // 2592
+  if out is None:
+    out = torch.empty(s, 20, 20, dtype=torch.float32, device=h16.device)
+  call("unreal_pc_deconv_qmax", ptr(h16, torch.bfloat16, "h16"), ptr(w_dtaps, torch.bfloat16, "w_dtaps"),
+       ptr(bias8, torch.float32, "bias8"), int(num_actions), s, ptr(out, torch.float32, "qmax"), stream_ptr())
+  return out
+
+
 def pc_deconv_loss(h16, w_dtaps, bias8, act, target, mask, num_actions, lam):
   """Pixel-control head + loss in one kernel: h16 bf16 [S,9,9,32] (any view of S*2592) -> (loss f64 [1],
   dy16 bf16 [S,400,16] = d loss / d pre-ReLU output, un-scaled by the upstream gradient, db8 [8])."""

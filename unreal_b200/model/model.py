@@ -394,6 +394,11 @@ class UnrealModel(object):
     img = self._images(s_t)
     p32, h, _ = self._step(s_t, last_action_reward, self._zeros_state(img.shape[1]))
     with torch.no_grad():
+      if self.fused_conv and self.fused_pc_loss and self._action_size <= 7:
+        # pc_fc1 GEMM, then the deconv with the dueling combine + max over actions in its epilogue (no [N,20,20,8] output)
+        hp = K.gemm_bf16(h.to(torch.bfloat16), self.v16["W_pc_fc1"], b_mn_major=True, bias=p32["b_pc_fc1"], relu=True,
+                         out_dtype=torch.bfloat16)
+        return K.pc_deconv_qmax(hp, self.pc_taps, self.pc_b8, self._action_size)
       return self._pc_q(p32, h)[1]
 
   def run_vr_value(self, sess, s_t, last_action_reward):
