@@ -8,7 +8,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from unreal_b200 import kernels as K
 dev = torch.device("cuda", 0)
-S = 4096
+S = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 g = torch.Generator(device=dev).manual_seed(0)
 w1 = (torch.randn(8, 8, 3, 16, device=dev, generator=g) * 0.05).to(torch.bfloat16); b1 = torch.zeros(16, device=dev)
 w2 = (torch.randn(4, 4, 16, 32, device=dev, generator=g) * 0.05).to(torch.bfloat16); b2 = torch.zeros(32, device=dev)
@@ -21,6 +21,8 @@ ring = K.ReplayRing(256, 64, dev)
 payload = torch.randint(0, 256, (256, 64, 84, 84, 3), dtype=torch.uint8, device=dev, generator=g)
 start = torch.randint(0, 40, (256,), dtype=torch.int32, device=dev, generator=g)
 length = torch.full((256,), 21, dtype=torch.int32, device=dev)
+act_pc = torch.randint(0, 4, (S,), device=dev, dtype=torch.int32, generator=g)
+tgt_pc = torch.rand(S, 400, device=dev, generator=g)
 for _ in range(2):
   h1 = K.conv_fwd(xpp, 1, t1, b1)
   h1m = K.conv1_fwd_maze(pos, t1, b1)
@@ -30,6 +32,8 @@ for _ in range(2):
   dw1 = K.conv1_wgrad(xpp, planes)
   dw1m = K.conv1_wgrad_maze(pos, planes)
   y8 = K.pc_deconv_fwd(h2, t8, b8)
+  pl = K.pc_deconv_loss(h2, t8, b8, act_pc, tgt_pc, torch.ones(S, device=dev), 4, 0.05)
+  qm = K.pc_deconv_qmax(h2, t8, b8, 4)
   fr = ring.gather(payload, start, length, 21)
 torch.cuda.synchronize()
 assert torch.equal(h1, h1m)
