@@ -776,8 +776,12 @@ conv2_wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __gr
       tmem_ld_wait();
       float* o = dw + (st * 64 + m) * 32;
       if (lane < 16) {
+        // 128-bit reductions: 296 CTAs add their 32 KB of partial filters to the same 8192 addresses, and 32 scalar atomics per
+        // thread kept the LSU queue full (ncu: lg_throttle 5.7 stalled warps per issue at the end of the kernel)
 #pragma unroll
-        for (int j = 0; j < 32; ++j) atomicAdd(o + j, __uint_as_float(v[j]));
+        for (int j = 0; j < 32; j += 4)
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + j), "f"(__uint_as_float(v[j])),
+                       "f"(__uint_as_float(v[j + 1])), "f"(__uint_as_float(v[j + 2])), "f"(__uint_as_float(v[j + 3])) : "memory");
       }
     }
   }
