@@ -291,6 +291,30 @@ int unreal_lstm_cell_act_g16(const void* gates_bf16, float* c_state, float* h_st
                              int n, void* stream);
 int unreal_lstm_cell_bwd_g16(const void* gates_act_bf16, const float* c_prev, const float* c, const float* dh,
                              const float* dh_rec, float* dc, void* dgates_bf16, int n, void* stream);
+/* One LSTM step as ONE launch: the step GEMM over [x_t, h_{t-1}] with the BasicLSTMCell arithmetic in its epilogue
+ * (model/model.py:110, :343-351; a tile holds all four gates of 64 units, the pre-activations never reach HBM).
+ *   xh [N, k] bf16, rows ld_xh apart (k = lstm input + padding + 256); w [k,1024] bf16 (i | j | f | o columns); bias [1024]
+ *   c_prev -> c_out [N,256] f32 (may alias: the acting step updates the persistent state in place); h_out [N,256] f32
+ *   (nullable); h16_out bf16 rows h16_ld apart (nullable: the next step's operand columns); acts [N,1024] bf16
+ *   (nullable: the gate activations the backward pass reads); active [N] (nullable): rows with 0 keep c / h, and
+ *   h_copy [N,256] (nullable, needs h_out) receives every row's h -- the new one, or what h_out held.
+ *   tiled != 0: c_prev, c_out and acts are in the 32-row tiled layout the epilogue accesses contiguously (rows padded
+ *   to a multiple of 32; 16-byte chunk ch of row r at 16 * ((r / 32 * chunks_per_row + ch) * 32 + r % 32)); these are
+ *   buffers only this kernel and unreal_lstm_step_bwd touch.
+ * Replaces unreal_gemm_bf16 + unreal_lstm_cell_fwd_g16 / unreal_lstm_cell_act_g16. */
+int unreal_lstm_step_fwd(const void* xh, int64_t ld_xh, const void* w, const float* bias, const float* c_prev, float* c_out,
+                         float* h_out, float* h_copy, void* h16_out, int h16_ld, void* acts, const uint8_t* active, int tiled,
+                         int n, int k, void* stream);
+/* One backward LSTM step as ONE launch: dh_rec = dgates_next [N,1024] bf16 x wh [256,1024]^T bf16 (the h rows of the
+ * cell's kernel, rows ld_wh apart) on the tensor cores, and in its epilogue the cell's backward pass of step t on
+ * dh [N,256] + dh_rec (the gradient of tf.nn.dynamic_rnn's unroll, model.py:343-351): acts [N,1024] bf16 step t's gate
+ * activations, c_prev / c [N,256]; dc [N,256] in: wrt c_t, out: wrt c_{t-1}; dgates [N,1024] bf16 out (row-major).
+ * dgates_next NULL = the unroll's last step: no product, dh2 [N,256] (nullable) is added to dh instead.
+ * tiled != 0: acts, c_prev, c and dc are in unreal_lstm_step_fwd's tiled layout.
+ * Replaces unreal_gemm_bf16 + unreal_lstm_cell_bwd_g16. */
+int unreal_lstm_step_bwd(const void* dgates_next, const void* wh, int64_t ld_wh, const void* acts, const float* c_prev,
+                         const float* c, const float* dh, const float* dh2, float* dc, void* dgates, int tiled, int n,
+                         void* stream);
 /* backward of the above: dh [N,256] total gradient wrt h_t; dc [N,256] in: wrt c_t, out: wrt
  * c_{t-1}; dgates bf16 [N,1024] wrt the pre-activations. */
 int unreal_lstm_cell_bwd(const float* gates_act, const float* c_prev, const float* c, const float* dh, float* dc,

@@ -88,13 +88,16 @@ class ModelOracle(object):
   so that the tight-tolerance tests compare accumulation order only."""
 
   def __init__(self, params, action_size, objective_size=0, pixel_change_lambda=0.05, entropy_beta=0.001,
-               emulate_bf16=False):
+               emulate_bf16=False, round_gates=True):
     self.p = params
     self.A = action_size
     self.G = objective_size
     self.pc_lambda = pixel_change_lambda
     self.entropy_beta = entropy_beta
     self.q = emulate_bf16
+    # the LSTM gate pre-activations as bf16 too: the CUDA path's GEMM + cell kernel steps store them (small batches, the
+    # acting step); its one-launch steps (UnrealModel.fused_lstm_step, large batches) take them from the fp32 accumulator
+    self.qz = emulate_bf16 and round_gates
     # float32 like the reference's placeholders (model.py:141 "float"); float64 parameters switch every tensor to
     # double, which is what the finite-difference gradient check of tests/test_model_oracle.py runs in
     self.dtype = next(iter(params.values())).dtype
@@ -123,7 +126,7 @@ class ModelOracle(object):
     c, h = c0, h0
     outs = []
     for t in range(T):
-      z = _bf16(torch.cat([x[t], _bf16(h, self.q)], dim=1) @ kernel + bias, self.q)   # the CUDA path stores the gates as bf16
+      z = _bf16(torch.cat([x[t], _bf16(h, self.q)], dim=1) @ kernel + bias, self.qz)
       i, j, f, o = z.split(256, dim=1)
       c = c * torch.sigmoid(f + 1.0) + torch.sigmoid(i) * torch.tanh(j)
       h = torch.tanh(c) * torch.sigmoid(o)

@@ -1,6 +1,6 @@
 """Small single-kernel workloads for `ncu --set full` captures (one GPU, a handful of launches).
 
-    python scripts/ncu_targets.py k2u8 | k2f32 | k1u8w | k1f32w | k1u8 | k4 | rp | conv2bwd | gemm2sm
+    python scripts/ncu_targets.py k2u8 | k2f32 | k1u8w | k1f32w | k1u8 | k4 | rp | conv2bwd | gemm2sm | lstm [envs] | lstmfused [envs]
 
 Each target runs its kernel three times on the benchmark's shapes; select the kernel with `-k regex:...`.
 """
@@ -49,6 +49,41 @@ elif which == "gemm2sm":
   dy = torch.randn(81920, 256, device=dev, generator=g).to(torch.bfloat16)
   for _ in range(3):
     K.gemm_bf16(x, dy, a_mn_major=True, b_mn_major=True, split_k=16)
+elif which == "lstm":
+  # one forward and one backward LSTM step of the learner at `envs` rows: step GEMM over [x, h], cell, recurrent dh GEMM, cell backward
+  n = int(sys.argv[2]) if len(sys.argv) > 2 else 8192
+  xh = torch.randn(n, 520, device=dev, generator=g).to(torch.bfloat16)
+  w = (torch.randn(520, 1024, device=dev, generator=g) * 0.05).to(torch.bfloat16)
+  b = torch.zeros(1024, device=dev)
+  c0 = torch.randn(n, 256, device=dev, generator=g)
+  dh = torch.randn(n, 256, device=dev, generator=g)
+  for _ in range(2):
+    gates = torch.empty(n, 1024, device=dev, dtype=torch.bfloat16)
+    c1 = torch.empty(n, 256, device=dev); h = torch.empty(n, 256, device=dev)
+    h16 = torch.empty(n, 256, device=dev, dtype=torch.bfloat16)
+    K.gemm_bf16(xh, w, out=gates, b_mn_major=True, bias=b)
+    K.lstm_cell_fwd(gates, c0, c1, h, h16)
+    dc = torch.zeros(n, 256, device=dev)
+    dg = torch.empty(n, 1024, device=dev, dtype=torch.bfloat16)
+    K.lstm_cell_bwd(gates, c0, c1, dh, dc, dg, None)
+    K.gemm_bf16(dg, w[264:])
+elif which == "lstmfused":
+  # the fused step kernels (csrc/lstm_tcgen05.cu) in the unroll's tiled mode: two forward and two backward steps
+  n = int(sys.argv[2]) if len(sys.argv) > 2 else 8192
+  xh = torch.randn(3, n, 520, device=dev, generator=g).to(torch.bfloat16)
+  w = (torch.randn(520, 1024, device=dev, generator=g) * 0.05).to(torch.bfloat16)
+  b = torch.zeros(1024, device=dev)
+  c_all = torch.zeros(3, n, 256, device=dev)
+  h_all = torch.empty(2, n, 256, device=dev)
+  gates = torch.empty(2, n, 1024, device=dev, dtype=torch.bfloat16)
+  dh = torch.randn(2, n, 256, device=dev, generator=g) * 0.1
+  dc = torch.zeros(n, 256, device=dev)
+  dg = torch.empty(2, n, 1024, device=dev, dtype=torch.bfloat16)
+  for _ in range(2):
+    for i in range(2):
+      K.lstm_step_fwd(xh[i], w, b, c_all[i], c_all[i + 1], h_out=h_all[i], h16_out=xh[i + 1, :, 264:], acts=gates[i], tiled=True)
+    K.lstm_step_bwd(None, w[264:], gates[1], c_all[1], c_all[2], dh[1], dc, dg[1], tiled=True)
+    K.lstm_step_bwd(dg[1], w[264:], gates[0], c_all[0], c_all[1], dh[0], dc, dg[0], tiled=True)
 else:
   raise SystemExit("unknown target " + which)
 torch.cuda.synchronize()

@@ -566,3 +566,158 @@ def test_pc_q_max_epilogue_equals_the_materialised_head():
     out[fused] = m.run_pc_q_max(None, {'image': frames}, lar).clone()
   assert tuple(out[True].shape) == (5, 20, 20)
   assert torch.allclose(out[True], out[False], rtol=1e-5, atol=1e-6)
+
+
+def _bf16_close(got, want, ulps=1.0):
+  """bf16 storage of a value computed in fp32: within `ulps` bf16 roundings (2^-8 relative each) of the fp32 reference."""
+  return torch.allclose(got.float(), want, rtol=ulps * 2.0 ** -8, atol=1e-6)
+
+
+def test_tile32_round_trip():
+  from unreal_b200 import kernels as K
+  dev = torch.device("cuda", 0)
+  for n, c, dt in ((1, 256, torch.float32), (77, 256, torch.float32), (64, 1024, torch.bfloat16), (100, 1024, torch.bfloat16)):
+    x = torch.randn(n, c, device=dev).to(dt)
+    xt = K.tile32(x)
+    assert xt.shape == ((n + 31) // 32 * 32, c) and torch.equal(K.untile32(xt, n), x)
+    e = 16 // x.element_size()
+    r, ch = n - 1, 3                      # chunk ch of row r sits at chunk index (r // 32 * chunks + ch) * 32 + r % 32
+    at = ((r // 32) * (c // e) + ch) * 32 + r % 32
+    assert torch.equal(xt.reshape(-1)[at * e:(at + 1) * e], x[r, ch * e:(ch + 1) * e])
+
+
+@pytest.mark.parametrize("tiled", [False, True], ids=["row-major", "tiled"])
+@pytest.mark.parametrize("n", [1, 100, 128, 1161, 4096])
+def test_lstm_step_fwd_equals_gemm_plus_cell(n, tiled):
+  """unreal_lstm_step_fwd (the BasicLSTMCell in the step GEMM's epilogue, model.py:110, :343-351) against an fp32 torch
+  evaluation of the same step on the same bf16 operands, and against the two-kernel path it replaces; ragged row counts,
+  the row-slice operand of the unroll, c / activations row-major and in the kernels' tiled layout, the acting variant
+  (state in place, inactive rows untouched)."""
+  from unreal_b200 import kernels as K
+  dev = torch.device("cuda", 0)
+  g = torch.Generator(device=dev).manual_seed(n)
+  kx, kc = 264, 520
+  xh3 = (torch.randn(2, n + 3, kc, device=dev, generator=g)).to(torch.bfloat16)      # [t, rows, kc]: step 0 feeds step 1
+  xh3[:, :, 261:kx] = 0
+  w = (torch.randn(kc, 1024, device=dev, generator=g) * 0.06).to(torch.bfloat16)
+  bias = torch.randn(1024, device=dev, generator=g) * 0.1
+  c0 = torch.randn(n, 256, device=dev, generator=g)
+  xh = xh3[0, :n]
+  z = xh.float() @ w.float() + bias
+  i, j, f, o = z.split(256, dim=1)
+  i, j, f, o = torch.sigmoid(i), torch.tanh(j), torch.sigmoid(f + 1.0), torch.sigmoid(o)
+  c_ref = c0 * f + i * j
+  h_ref = torch.tanh(c_ref) * o
+  sentinel = 7.25
+  nt = (n + 31) // 32 * 32 if tiled else n
+  pad = 0 if tiled else 2
+  c1b = torch.full((nt + pad, 256), sentinel, device=dev); h1 = torch.full((n + 2, 256), sentinel, device=dev)
+  actsb = torch.full((nt + pad, 1024), sentinel, device=dev).to(torch.bfloat16)
+  before = xh3[1].clone()
+  K.lstm_step_fwd(xh, w, bias, K.tile32(c0) if tiled else c0, c1b[:nt], h_out=h1[:n], h16_out=xh3[1, :n, kx:], acts=actsb[:nt],
+                  tiled=tiled)
+  torch.cuda.synchronize()
+  c1 = K.untile32(c1b, nt) if tiled else c1b
+  acts = K.untile32(actsb, nt) if tiled else actsb
+  assert torch.allclose(c1[:n], c_ref, rtol=1e-5, atol=2e-5), float((c1[:n] - c_ref).abs().max())
+  assert torch.allclose(h1[:n], h_ref, rtol=1e-5, atol=2e-5)
+  assert _bf16_close(acts[:n], torch.cat([i, j, f, o], dim=1))
+  assert torch.equal(xh3[1, :n, kx:], h1[:n].to(torch.bfloat16)), "h' as bf16 in the next step's operand columns"
+  # nothing outside the addressed rows / columns (tiled: the padding rows of the last 32-row block)
+  assert (c1[n:] == sentinel).all() and (h1[n:] == sentinel).all() and (acts[n:].float() == sentinel).all()
+  assert torch.equal(xh3[1, :, :kx], before[:, :kx]) and torch.equal(xh3[1, n:], before[n:])
+  # the two-kernel path on f32 gates
+  gates = K.gemm_bf16(xh, w, b_mn_major=True, bias=bias)
+  c2 = torch.empty(n, 256, device=dev); h2 = torch.empty(n, 256, device=dev)
+  h16 = torch.empty(n, 256, device=dev, dtype=torch.bfloat16)
+  K.lstm_cell_fwd(gates, c0, c2, h2, h16)
+  assert torch.allclose(c1[:n], c2, rtol=1e-5, atol=1e-5) and torch.allclose(h1[:n], h2, rtol=1e-5, atol=1e-5)
+  if tiled:
+    return
+  # acting: persistent state in place, rows with active == 0 keep c / h and report their old h
+  active = (torch.rand(n, device=dev, generator=g) < 0.6).to(torch.uint8)
+  c_state = c0.clone(); h_state = torch.randn(n, 256, device=dev, generator=g); h_old = h_state.clone()
+  h_rep = torch.full((n, 256), sentinel, device=dev)
+  K.lstm_step_fwd(xh, w, bias, c_state, c_state, h_out=h_state, active=active, h_copy=h_rep)
+  on = active.bool()[:, None]
+  assert torch.equal(c_state, torch.where(on, c1[:n], c0)) and torch.equal(h_state, torch.where(on, h1[:n], h_old))
+  assert torch.equal(h_rep, h_state)
+
+
+@pytest.mark.parametrize("tiled", [False, True], ids=["row-major", "tiled"])
+@pytest.mark.parametrize("last", [False, True], ids=["recurrent", "last-step"])
+@pytest.mark.parametrize("n", [1, 100, 1161, 8192])
+def test_lstm_step_bwd_equals_gemm_plus_cell_bwd(n, last, tiled):
+  """unreal_lstm_step_bwd (recurrent dh GEMM with the cell's backward pass in its epilogue) against the two kernels it
+  replaces (unreal_gemm_bf16 + unreal_lstm_cell_bwd_g16, themselves checked against autograd through the oracle tests) and
+  against torch autograd of the cell on the same bf16 activations.  `last`: the unroll's last step (no product; dh2)."""
+  from unreal_b200 import kernels as K
+  dev = torch.device("cuda", 0)
+  g = torch.Generator(device=dev).manual_seed(100 + n)
+  w = (torch.randn(520, 1024, device=dev, generator=g) * 0.06).to(torch.bfloat16)
+  wh = w[264:]
+  dg_next = (torch.randn(n, 1024, device=dev, generator=g) * 0.1).to(torch.bfloat16)
+  dh2 = torch.randn(n, 256, device=dev, generator=g) * 0.1
+  z = torch.randn(n, 1024, device=dev, generator=g)
+  acts = torch.cat([torch.sigmoid(z[:, :256]), torch.tanh(z[:, 256:512]), torch.sigmoid(z[:, 512:])], dim=1).to(torch.bfloat16)
+  c_prev = torch.randn(n, 256, device=dev, generator=g)
+  a = acts.float()
+  c = c_prev * a[:, 512:768] + a[:, :256] * a[:, 256:512]
+  dh = torch.randn(n, 256, device=dev, generator=g) * 0.1
+  dc0 = torch.randn(n, 256, device=dev, generator=g) * 0.1
+  sentinel = 3.5
+  nt = (n + 31) // 32 * 32 if tiled else n
+  T_ = (lambda x: K.tile32(x)) if tiled else (lambda x: x)
+  dcb = torch.full((nt + 2, 256), sentinel, device=dev)
+  dcb[:nt] = T_(dc0) if not tiled else torch.where(K.tile32(torch.ones(n, 256, device=dev)) > 0, K.tile32(dc0), dcb[:nt])
+  dgates = torch.full((n + 2, 1024), sentinel, device=dev).to(torch.bfloat16)
+  K.lstm_step_bwd(None if last else dg_next, wh, T_(acts), T_(c_prev), T_(c), dh, dcb[:nt], dgates[:n], dh2=dh2 if last else None,
+                  tiled=tiled)
+  torch.cuda.synchronize()
+  dc = K.untile32(dcb[:nt], nt) if tiled else dcb
+  assert (dc[n:nt] == sentinel).all() and (dcb[nt:] == sentinel).all() and (dgates[n:].float() == sentinel).all()
+  # the kernels it replaces
+  dh_rec = dh2 if last else K.gemm_bf16(dg_next, wh)
+  dc_b = dc0.clone(); dg_b = torch.empty(n, 1024, device=dev, dtype=torch.bfloat16)
+  K.lstm_cell_bwd(acts, c_prev, c, dh, dc_b, dg_b, dh_rec)
+  assert torch.allclose(dc[:n], dc_b, rtol=1e-4, atol=1e-6), float((dc[:n] - dc_b).abs().max())
+  assert _bf16_close(dgates[:n], dg_b.float(), ulps=2.0)
+  # autograd of the cell in fp32 at the same activations: d/d(pre-activation) through sigmoid' = s (1 - s), tanh' = 1 - t^2
+  dh_tot = dh + (dh2 if last else dg_next.float() @ wh.float().t())
+  i, j, f, o = a[:, :256], a[:, 256:512], a[:, 512:768], a[:, 768:]
+  tc = torch.tanh(c)
+  dct = dc0 + dh_tot * o * (1 - tc * tc)
+  want = torch.cat([dct * j * i * (1 - i), dct * i * (1 - j * j), dct * c_prev * f * (1 - f), dh_tot * tc * o * (1 - o)], dim=1)
+  assert torch.allclose(dgates[:n].float(), want, rtol=2.0 ** -7, atol=1e-4)
+  assert torch.allclose(dc[:n], dct * f, rtol=1e-4, atol=1e-5)
+
+
+def test_fused_lstm_steps_equal_the_two_kernel_unroll():
+  """UnrealModel.fused_lstm_step: the whole update (loss, gradient) with one launch per LSTM step against GEMM + cell
+  kernels per step.  The two differ in ONE rounding: the two-kernel path stores the gate pre-activations as bf16 before
+  the cell reads them (2^-9 relative on z), the fused path feeds the cell from the fp32 accumulator."""
+  dev = torch.device("cuda", 0)
+  feed = _to(_feed(6, 5, 4, seed=11), dev)
+  out = {}
+  for fused in (True, False):
+    m = _model(dev, seed=5, n=5)
+    m.fused_lstm_step = fused
+    m.fused_lstm_min_rows = 1          # the unroll's one-launch steps at any batch size
+    total, _, grad = m.loss_and_grads(feed)
+    out[fused] = (float(total), grad.clone())
+  assert abs(out[True][0] - out[False][0]) <= 2e-3 * abs(out[False][0])
+  ga, gb = out[True][1], out[False][1]
+  assert float((ga - gb).norm()) <= 2e-2 * float(gb.norm())
+  # and each against the oracle that rounds what that path rounds (same bounds as test_loss_and_gradients_match_oracle)
+  from oracle import model_oracle as M
+  cpu_feed = {k: {kk: vv.cpu() for kk, vv in v.items()} for k, v in feed.items()}
+  for fused in (True, False):
+    m = _model(dev, seed=5, n=5)
+    params = {k: v.detach().cpu().clone() for k, v in m.named_vars().items()}
+    o = M.ModelOracle(params, A, 0, 0.05, 0.001, emulate_bf16=True, round_gates=not fused)
+    rtotal, _, rgrads = o.loss_and_grads(cpu_feed)
+    assert abs(out[fused][0] - float(rtotal)) <= 2e-3 * max(1.0, abs(float(rtotal))), fused
+    got = {k: v.cpu() for k, v in m._views(out[fused][1]).items()}
+    for k, rg in rgrads.items():
+      err = float((got[k] - rg).abs().max())
+      assert err <= 3e-2 * float(rg.abs().max()) + 1e-6, (fused, k, err, float(rg.abs().max()))

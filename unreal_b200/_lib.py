@@ -86,6 +86,8 @@ SIGNATURES = {
     "unreal_lstm_cell_fwd_g16": (c_int, [P, P, P, P, P, c_int, c_int, P]),
     "unreal_lstm_cell_act_g16": (c_int, [P, P, P, P, P, c_int, P]),
     "unreal_lstm_cell_bwd_g16": (c_int, [P, P, P, P, P, P, P, c_int, P]),
+    "unreal_lstm_step_fwd": (c_int, [P, c_int64, P, P, P, P, P, P, P, c_int, P, P, c_int, c_int, c_int, P]),
+    "unreal_lstm_step_bwd": (c_int, [P, P, c_int64, P, P, P, P, P, P, P, c_int, c_int, P]),
     "unreal_lstm_cell_bwd": (c_int, [P, P, P, P, P, P, c_int, P]),
     "unreal_lstm_cell_bwd2": (c_int, [P, P, P, P, P, P, P, c_int, P]),
     "unreal_s2d_frames": (c_int, [P, c_int, P, c_int, P]),

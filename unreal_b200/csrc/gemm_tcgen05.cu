@@ -525,9 +525,10 @@ int make_tma_2d(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, 
 }
 
 
-// rank-N bf16 tensor map with the 128-byte swizzle (conv_tcgen05.cu: 4-D / 5-D im2col boxes)
-int make_tma_nd_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                     const uint32_t* box, int swizzle_bytes) {
+// rank-N tensor map, bf16 or f32 elements, swizzle 0 / 32 / 64 / 128 bytes (conv_tcgen05.cu: 4-D / 5-D im2col boxes;
+// lstm_tcgen05.cu: narrow staging boxes of the cell warps)
+int make_tma_nd(CUtensorMap* map, bool f32, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                const uint32_t* box, int swizzle_bytes) {
   EncodeTiledFn fn = encode_tiled();
   if (fn == nullptr) {
     set_error("cuTensorMapEncodeTiled is not available from the CUDA driver");
@@ -536,15 +537,22 @@ int make_tma_nd_bf16(CUtensorMap* map, const void* base, int rank, const uint64_
   cuuint64_t d[5]; cuuint64_t st[4]; cuuint32_t b[5]; cuuint32_t e[5];
   for (int i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; e[i] = 1; }
   for (int i = 0; i + 1 < rank; ++i) st[i] = strides_bytes[i];
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), d, st, b, e,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_bytes == 0 ? CU_TENSOR_MAP_SWIZZLE_NONE
-                  : (swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B),
-                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  const CUtensorMapSwizzle sw = swizzle_bytes == 0 ? CU_TENSOR_MAP_SWIZZLE_NONE
+                                : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
+  CUresult r = fn(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank,
+                  const_cast<void*>(base), d, st, b, e, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
-    set_error("cuTensorMapEncodeTiled failed (%d) for a rank-%d bf16 tensor", (int)r, rank);
+    set_error("cuTensorMapEncodeTiled failed (%d) for a rank-%d %s tensor", (int)r, rank, f32 ? "f32" : "bf16");
     return UNREAL_ECUDA;
   }
   return UNREAL_OK;
+}
+
+int make_tma_nd_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                     const uint32_t* box, int swizzle_bytes) {
+  return make_tma_nd(map, false, base, rank, dims, strides_bytes, box, swizzle_bytes);
 }
 
 template <int BN, bool A_MN, bool B_MN>

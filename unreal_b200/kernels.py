@@ -517,6 +517,71 @@ def lstm_cell_fwd(gates, c_prev, c_out, h_out, h16_out):
        n, stream_ptr())
 
 
+def _rows2d(t, cols, dtype, name):
+  """[n, cols] view with contiguous rows (a column slice of a wider row-major buffer is accepted) -> (pointer, row pitch)."""
+  if not isinstance(t, torch.Tensor) or not t.is_cuda or t.dtype != dtype or t.dim() != 2 or t.shape[1] != cols or t.stride(1) != 1:
+    raise _lib.UnrealError("%s must be a CUDA %s [n,%d] tensor with contiguous rows" % (name, dtype, cols))
+  return t.data_ptr(), int(t.stride(0))
+
+
+def tile32(x, rows=None):
+  """[n, C] row-major -> the 32-row tiled layout of unreal_lstm_step_fwd / _bwd, [rows, C] with rows = n rounded up to 32
+  (16-byte chunk ch of row r at chunk index (r // 32 * chunks_per_row + ch) * 32 + r % 32)."""
+  n, c = x.shape
+  e = 16 // x.element_size()
+  rows = (n + 31) // 32 * 32 if rows is None else rows
+  buf = x.new_zeros(rows, c)
+  buf[:n] = x
+  return buf.view(rows // 32, 32, c // e, e).permute(0, 2, 1, 3).contiguous().view(rows, c)
+
+
+def untile32(xt, n):
+  """inverse of tile32: the first n rows, row-major"""
+  rows, c = xt.shape
+  e = 16 // xt.element_size()
+  return xt.view(rows // 32, c // e, 32, e).permute(0, 2, 1, 3).reshape(rows, c)[:n]
+
+
+def lstm_step_fwd(xh, w, bias, c_prev, c_out, h_out=None, h16_out=None, acts=None, active=None, h_copy=None, tiled=False):
+  """One LSTM step in one launch (unreal_lstm_step_fwd): step GEMM over xh [n,k] bf16 (rows may be a slice) x w [k,1024]
+  with the cell in the epilogue.  c_out may be c_prev (acting: in place, only rows with active != 0).
+  tiled: c_prev, c_out, acts are `tile32` buffers [n rounded up to 32, .]."""
+  n, k = xh.shape
+  xp, ldx = _rows2d(xh, k, torch.bfloat16, "xh")
+  if w.shape != (k, 1024):
+    raise _lib.UnrealError("w must be [%d,1024], got %s" % (k, tuple(w.shape)))
+  hp, hld = (None, 0) if h16_out is None else _rows2d(h16_out, 256, torch.bfloat16, "h16_out")
+  nt = (n + 31) // 32 * 32 if tiled else n
+  for name, t, rows in (("c_prev", c_prev, nt), ("c_out", c_out, nt), ("h_out", h_out, n), ("h_copy", h_copy, n)):
+    if t is not None and tuple(t.shape) != (rows, 256):
+      raise _lib.UnrealError("%s must be [%d,256]" % (name, rows))
+  if acts is not None and tuple(acts.shape) != (nt, 1024):
+    raise _lib.UnrealError("acts must be [%d,1024]" % nt)
+  call("unreal_lstm_step_fwd", xp, ldx, ptr(w, torch.bfloat16, "w"), ptr(bias, torch.float32, "bias"),
+       ptr(c_prev, torch.float32, "c_prev"), ptr(c_out, torch.float32, "c_out"), ptr(h_out, torch.float32, "h_out"),
+       ptr(h_copy, torch.float32, "h_copy"), hp, hld, ptr(acts, torch.bfloat16, "acts"), ptr(active, torch.uint8, "active"),
+       1 if tiled else 0, n, k, stream_ptr())
+
+
+def lstm_step_bwd(dgates_next, wh, acts, c_prev, c, dh, dc, dgates, dh2=None, tiled=False):
+  """One backward LSTM step in one launch (unreal_lstm_step_bwd): dh_rec = dgates_next [n,1024] x wh [256,1024]^T, then the
+  cell's backward pass of this step on dh + dh_rec -> dgates [n,1024] bf16, dc [n,256] in place.  dgates_next None: the
+  unroll's last step (dh + dh2).  tiled: acts, c_prev, c, dc are `tile32` buffers."""
+  n = dgates.shape[0]
+  wp, ldw = _rows2d(wh, 1024, torch.bfloat16, "wh")
+  if wh.shape[0] != 256:
+    raise _lib.UnrealError("wh must be [256,1024]")
+  nt = (n + 31) // 32 * 32 if tiled else n
+  for name, t, rows, cols in (("dgates_next", dgates_next, n, 1024), ("acts", acts, nt, 1024), ("dgates", dgates, n, 1024),
+                              ("c_prev", c_prev, nt, 256), ("c", c, nt, 256), ("dh", dh, n, 256), ("dh2", dh2, n, 256),
+                              ("dc", dc, nt, 256)):
+    if t is not None and tuple(t.shape) != (rows, cols):
+      raise _lib.UnrealError("%s must be [%d,%d]" % (name, rows, cols))
+  call("unreal_lstm_step_bwd", ptr(dgates_next, torch.bfloat16, "dgates_next"), wp, ldw, ptr(acts, torch.bfloat16, "acts"),
+       ptr(c_prev, torch.float32, "c_prev"), ptr(c, torch.float32, "c"), ptr(dh, torch.float32, "dh"), ptr(dh2, torch.float32, "dh2"),
+       ptr(dc, torch.float32, "dc"), ptr(dgates, torch.bfloat16, "dgates"), 1 if tiled else 0, n, stream_ptr())
+
+
 def lstm_cell_bwd(gates_act, c_prev, c, dh, dc, dgates16, dh_rec=None):
   """dh (+ dh_rec): gradient w.r.t. h_t; dc in / out; dgates16 [n,1024] bf16 out."""
   n = gates_act.shape[0]

@@ -164,10 +164,13 @@ class LstmFn(torch.autograd.Function):
   """
 
   @staticmethod
-  def forward(ctx, fc16, lar, wcat16, w32, b32, c0, h0, lstm_in, kx, gates_dtype=torch.float32):
+  def forward(ctx, fc16, lar, wcat16, w32, b32, c0, h0, lstm_in, kx, gates_dtype=torch.float32, fused_step=False):
     """fc16 [T,N,256] bf16 (fc1 output), lar [T,N,lstm_in-256] f32: packed straight into the step operands.
     gates_dtype bf16: the step GEMM writes the gate pre-activations as bf16 and the cell keeps their activations for the
-    backward pass as bf16 (half the traffic of the HBM-bound cell kernels)."""
+    backward pass as bf16 (half the traffic of the HBM-bound cell kernels).
+    fused_step (needs bf16 gates): one launch per step in both directions -- the cell runs in the step GEMM's epilogue
+    (unreal_lstm_step_fwd: the pre-activations never reach HBM, only the bf16 activations the backward pass reads) and
+    the cell's backward pass in the epilogue of the recurrent dh GEMM (unreal_lstm_step_bwd)."""
     t, n = fc16.shape[:2]
     kc = kx + 256
     dev = fc16.device
@@ -177,18 +180,31 @@ class LstmFn(torch.autograd.Function):
     if kx > lstm_in:
       xh[:, :, lstm_in:kx].zero_()
     xh[0, :, kx:].copy_(h0)
-    gates = torch.empty(t, n, 1024, device=dev, dtype=gates_dtype)
-    c_all = torch.empty(t + 1, n, 256, device=dev)
+    fused_step = bool(fused_step) and gates_dtype == torch.bfloat16
+    # fused steps: c of every step and the gate activations are touched by the step kernels only and live in their tiled
+    # layout (kernels.tile32; rows padded to a multiple of 32)
+    nt = (n + 31) // 32 * 32 if fused_step else n
+    gates = torch.empty(t, nt, 1024, device=dev, dtype=gates_dtype)
+    c_all = torch.empty(t + 1, nt, 256, device=dev)
     h_all = torch.empty(t, n, 256, device=dev)
-    h16_last = torch.empty(n, 256, device=dev, dtype=torch.bfloat16)
-    c_all[0].copy_(c0)
-    for i in range(t):
-      K.gemm_bf16(xh[i], wcat16, out=gates[i], b_mn_major=True, bias=b32)
-      K.lstm_cell_fwd(gates[i], c_all[i], c_all[i + 1], h_all[i], xh[i + 1, :, kx:] if i + 1 < t else h16_last)
+    if fused_step:
+      c_all[0].copy_(K.tile32(c0))
+      for i in range(t):
+        K.lstm_step_fwd(xh[i], wcat16, b32, c_all[i], c_all[i + 1], h_out=h_all[i],
+                        h16_out=xh[i + 1, :, kx:] if i + 1 < t else None, acts=gates[i], tiled=True)
+      c_last = K.untile32(c_all[t], n).contiguous()
+    else:
+      h16_last = torch.empty(n, 256, device=dev, dtype=torch.bfloat16)
+      c_all[0].copy_(c0)
+      for i in range(t):
+        K.gemm_bf16(xh[i], wcat16, out=gates[i], b_mn_major=True, bias=b32)
+        K.lstm_cell_fwd(gates[i], c_all[i], c_all[i + 1], h_all[i], xh[i + 1, :, kx:] if i + 1 < t else h16_last)
+      c_last = c_all[t].clone()
+    ctx.fused_step = fused_step
     ctx.lstm_in = lstm_in
     ctx.kx = kx
     ctx.save_for_backward(xh, wcat16, gates, c_all)
-    return h_all, c_all[t].clone(), h_all[t - 1].clone()
+    return h_all, c_last, h_all[t - 1].clone()
 
   @staticmethod
   def backward(ctx, dh_all, dc_last, dh_last):
@@ -197,11 +213,18 @@ class LstmFn(torch.autograd.Function):
     t, n, kc = xh.shape
     dev = xh.device
     dh_all = dh_all.contiguous()
-    dc = torch.zeros(n, 256, device=dev) if dc_last is None else dc_last.clone().contiguous()
     dgates = torch.empty(t, n, 1024, device=dev, dtype=torch.bfloat16)
     wh = wcat16[kx:]                                     # [256, 1024]: K-major B for dh = dgates @ Wh^T
     dh_rec = None if dh_last is None else dh_last.contiguous()
+    if ctx.fused_step:
+      dc = torch.zeros(c_all.shape[1], 256, device=dev) if dc_last is None else K.tile32(dc_last)
+    else:
+      dc = torch.zeros(n, 256, device=dev) if dc_last is None else dc_last.clone().contiguous()
     for i in range(t - 1, -1, -1):
+      if ctx.fused_step:
+        K.lstm_step_bwd(dgates[i + 1] if i < t - 1 else None, wh, gates[i], c_all[i], c_all[i + 1], dh_all[i], dc, dgates[i],
+                        dh2=dh_rec if i == t - 1 else None, tiled=True)
+        continue
       K.lstm_cell_bwd(gates[i], c_all[i], c_all[i + 1], dh_all[i], dc, dgates[i], dh_rec)    # dh = dh_all[i] + dh_rec
       if i > 0:
         # small batches: this [N,1024] x [256,1024]^T product is one N tile wide -- split K over more CTAs (measured
@@ -213,7 +236,7 @@ class LstmFn(torch.autograd.Function):
     _, db = K.relu_grad(dg2, None, want_out=False)
     # only the 256 fc1 columns carry a gradient (last_action_reward is an input)
     dfc = K.gemm_bf16(dg2, wcat16[:256], out_dtype=torch.bfloat16).view(t, n, 256)
-    return dfc, None, None, dw, db, None, None, None, None, None
+    return dfc, None, None, dw, db, None, None, None, None, None, None
 
 
 class Deconv8Fn(torch.autograd.Function):

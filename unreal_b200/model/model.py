@@ -91,6 +91,13 @@ class UnrealModel(object):
     self.grad_scale = None
     # LSTM gate pre-activations / saved activations as bf16 (False: f32).  The cell kernels are HBM-bound on that buffer.
     self.lstm_gates_bf16 = True
+    # one launch per LSTM step of the unroll (needs lstm_gates_bf16): the cell in the step GEMM's epilogue, the cell's
+    # backward pass in the epilogue of the recurrent dh GEMM (csrc/lstm_tcgen05.cu), for batches of at least
+    # fused_lstm_min_rows env rows (measured per step, profiles/r2_lstm_step_bench.jsonl: forward 20.1 us against 31.0 us
+    # for GEMM + cell kernel at 8192 rows and 12.6 / 15.2 at 2048, but 12.4 / 11.6 at 1024 where one tile's latency is
+    # the whole launch).  The acting step keeps GEMM + cell kernel: its state is row-major and updated under a mask.
+    self.fused_lstm_step = True
+    self.fused_lstm_min_rows = 2048
     # pixel-control loss inside the deconv kernel's epilogue (False: deconv -> f32 head output -> separate loss / gradient passes)
     self.fused_pc_loss = True
     self._cells49 = torch.tensor([[x, y] for y in range(7) for x in range(7)], dtype=torch.int32, device=self._device)
@@ -233,6 +240,9 @@ class UnrealModel(object):
   def _gates_dtype(self):
     return torch.bfloat16 if self.lstm_gates_bf16 else torch.float32
 
+  def _fused_step(self, n):
+    return self.fused_lstm_step and self.lstm_gates_bf16 and n >= self.fused_lstm_min_rows
+
   def _use_tables(self, images):
     return self.dedup_cells and images.dtype == torch.int32 and self.fused_conv and self.fused_encoder
 
@@ -250,11 +260,11 @@ class UnrealModel(object):
     if tables is not None and self._use_tables(images):
       fc = CellGatherFn.apply(tables[1], images.reshape(t * n, 2)).view(t, n, 256)
       return LstmFn.apply(fc, lar.to(torch.float32), self.wcat16, p32["lstm_kernel"], p32["lstm_bias"], c0, h0, self.lstm_in,
-                          self.kx, self._gates_dtype()), None
+                          self.kx, self._gates_dtype(), self._fused_step(n)), None
     h2 = self._encoder(p32, images.reshape(t * n, *images.shape[2:]))
     fc = self._lstm_input(p32, h2, t, n)
     return LstmFn.apply(fc, lar.to(torch.float32), self.wcat16, p32["lstm_kernel"], p32["lstm_bias"], c0, h0, self.lstm_in,
-                        self.kx, self._gates_dtype()), h2
+                        self.kx, self._gates_dtype(), self._fused_step(n)), h2
 
   def _policy_value(self, p32, h):
     """model.py:358-377 (tiny [.,256]x[256,A+1] products, fp32).  Without autograd (acting, bootstraps): one fused
@@ -334,8 +344,8 @@ class UnrealModel(object):
       img = self._images(s_t)
       n = img.shape[1]
       if self.fused_conv and self.fused_encoder:
-        gates = self._step_gates(p32, img[0], self._lar(last_action_reward, n)[0], state[1])
         c1 = torch.empty(n, 256, device=self._device); h1 = torch.empty(n, 256, device=self._device)
+        gates = self._step_gates(p32, img[0], self._lar(last_action_reward, n)[0], state[1])
         h16 = torch.empty(n, 256, device=self._device, dtype=torch.bfloat16)
         K.lstm_cell_fwd(gates, state[0].contiguous(), c1, h1, h16)
         return p32, h1, (c1, h1)
