@@ -228,10 +228,13 @@ lstm_step_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __
           const uint32_t sa = smem_base + stage * kFwdStageBytes, sb = sa + kLsBM * kLsBK * 2;
           const uint32_t a_lo = (sa >> 4) | (1u << 16);
           const uint32_t b_lo = (sb >> 4) | (((uint32_t)(kLsBK * 128) >> 4) << 16);
+          // the last block of K = 520 holds 8 columns: one UMMA instead of four over zero fill
+          const int kk = min(kLsBK / 16, (g.k - kb * kLsBK + 15) >> 4);
 #pragma unroll
           for (int k = 0; k < kLsBK / 16; ++k)
-            mma_f16_lohi(tmem_d, a_lo + (uint32_t)k * 2u, kLsDescHi, b_lo + (uint32_t)k * 128u, kLsDescHi, idesc,
-                         (kb > 0 || k > 0) ? 1u : 0u);
+            if (k < kk)
+              mma_f16_lohi(tmem_d, a_lo + (uint32_t)k * 2u, kLsDescHi, b_lo + (uint32_t)k * 128u, kLsDescHi, idesc,
+                           (kb > 0 || k > 0) ? 1u : 0u);
           mma_commit(empty_bar(stage));
           if (++stage == kFwdStages) { stage = 0; phase ^= 1u; }
         }
