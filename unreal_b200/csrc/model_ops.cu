@@ -484,14 +484,24 @@ struct HeadW {
   float wv[8];
 };
 
+// [Wp | Wv] of the heads, transposed into shared memory once per CTA (s_w[j][k]; row kHeadMaxA = Wv), then each lane's
+// eight rows k = lane + 32 i into registers.  (Every warp used to fetch its 64 weights with scalar global loads of
+// stride A: at acting batch sizes -- one or two rows of work per warp -- that set-up WAS the kernel, 21 us for an
+// 8 MB read.)  Block size 256.
 __device__ __forceinline__ void head_load_w(HeadW& w, const float* __restrict__ Wp, const float* __restrict__ Wv, int A,
-                                            int lane) {
+                                            int lane, float* s_w) {
+  for (int i = threadIdx.x; i < 256 * A; i += blockDim.x) {
+    const int k = i / A, j = i - k * A;
+    s_w[j * 256 + k] = Wp[i];
+  }
+  for (int k = threadIdx.x; k < 256; k += blockDim.x) s_w[kHeadMaxA * 256 + k] = Wv ? Wv[k] : 0.f;
+  __syncthreads();
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int k = lane + 32 * i;
 #pragma unroll
-    for (int j = 0; j < kHeadMaxA; ++j) w.wp[i][j] = (j < A) ? Wp[k * A + j] : 0.f;
-    w.wv[i] = Wv ? Wv[k] : 0.f;
+    for (int j = 0; j < kHeadMaxA; ++j) w.wp[i][j] = (j < A) ? s_w[j * 256 + k] : 0.f;
+    w.wv[i] = s_w[kHeadMaxA * 256 + k];
   }
 }
 
@@ -499,6 +509,53 @@ __device__ __forceinline__ float warp_sum(float x) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
   return x;
+}
+
+// One row of the heads on one warp.  x[i] = h[r, lane + 32 i].  The eight dot products (7 policy logits + the value) are
+// reduced with a TRANSPOSING butterfly: at distance 16 a lane keeps four of its eight partial sums and trades the other
+// four, at distance 8 two of four, at distance 4 one of two, then two plain steps -- 9 shuffles instead of 40, and
+// lane L ends up holding output j = L >> 2.  Softmax, entropy and log-likelihood then run ACROSS the lanes (three
+// shuffles each at distances 4, 8, 16), each output's exp / log computed once.
+struct HeadRow {
+  float p, lp, H, v, z;      // this lane's (j = lane >> 2) probability and clamped log; entropy and value in every lane
+};
+__device__ __forceinline__ HeadRow head_row(const HeadW& w, const float (&x)[8], int lane, int A, float bias_j) {
+  float z[kHeadMaxA + 1];
+#pragma unroll
+  for (int j = 0; j <= kHeadMaxA; ++j) z[j] = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+#pragma unroll
+    for (int j = 0; j < kHeadMaxA; ++j) z[j] = fmaf(x[i], w.wp[i][j], z[j]);
+    z[kHeadMaxA] = fmaf(x[i], w.wv[i], z[kHeadMaxA]);
+  }
+  const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+  float u[4], t2[2];
+#pragma unroll
+  for (int t = 0; t < 4; ++t) u[t] = (b4 ? z[4 + t] : z[t]) + __shfl_xor_sync(0xffffffffu, b4 ? z[t] : z[4 + t], 16);
+#pragma unroll
+  for (int t = 0; t < 2; ++t) t2[t] = (b3 ? u[2 + t] : u[t]) + __shfl_xor_sync(0xffffffffu, b3 ? u[t] : u[2 + t], 8);
+  float s = (b2 ? t2[1] : t2[0]) + __shfl_xor_sync(0xffffffffu, b2 ? t2[0] : t2[1], 4);
+  s += __shfl_xor_sync(0xffffffffu, s, 2);
+  s += __shfl_xor_sync(0xffffffffu, s, 1);
+  const int j = lane >> 2;
+  HeadRow o;
+  o.z = s + bias_j;
+  o.v = __shfl_sync(0xffffffffu, o.z, 4 * kHeadMaxA);
+  float mx = (j < A) ? o.z : -3.0e38f;
+#pragma unroll
+  for (int d = 4; d <= 16; d <<= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+  const float e = (j < A) ? __expf(o.z - mx) : 0.f;
+  float den = e;
+#pragma unroll
+  for (int d = 4; d <= 16; d <<= 1) den += __shfl_xor_sync(0xffffffffu, den, d);
+  o.p = e * (1.0f / den);
+  o.lp = __logf(fminf(fmaxf(o.p, 1e-20f), 1.0f));
+  float H = (j < A) ? -o.p * o.lp : 0.f;
+#pragma unroll
+  for (int d = 4; d <= 16; d <<= 1) H += __shfl_xor_sync(0xffffffffu, H, d);
+  o.H = H;
+  return o;
 }
 
 __global__ void __launch_bounds__(256) a3c_head_loss_kernel(const float* __restrict__ h, const float* __restrict__ Wp,
@@ -512,62 +569,48 @@ __global__ void __launch_bounds__(256) a3c_head_loss_kernel(const float* __restr
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  __shared__ float s_w[(kHeadMaxA + 1) * 256];
   HeadW w;
-  head_load_w(w, Wp, Wv, A, lane);
-  float s_pol = 0.f, s_val = 0.f, s_ent = 0.f;
-  for (int64_t r = warp0; r < M; r += nwarps) {
-    float z[kHeadMaxA + 1];
+  head_load_w(w, Wp, Wv, A, lane, s_w);
+  const int j = lane >> 2;
+  const bool writer = (lane & 3) == 0;                 // one lane per output
+  const float bias_j = (j < A) ? bp[j] : ((j == kHeadMaxA && bv) ? bv[0] : 0.f);
+  float s_pol = 0.f, s_val = 0.f, s_ent = 0.f;         // lane 0 (policy, entropy) and lane 28 (value) accumulate
+  // two rows per iteration: both rows' loads are in flight before either row's arithmetic starts
+  for (int64_t r0 = 2 * warp0; r0 < M; r0 += 2 * nwarps) {
+    const int nrow = (r0 + 1 < M) ? 2 : 1;
+    float x[2][8];
 #pragma unroll
-    for (int j = 0; j <= kHeadMaxA; ++j) z[j] = 0.f;
+    for (int q = 0; q < 2; ++q)
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float x = h[r * 256 + lane + 32 * i];
+      for (int i = 0; i < 8; ++i) x[q][i] = (q < nrow) ? h[(r0 + q) * 256 + lane + 32 * i] : 0.f;
 #pragma unroll
-      for (int j = 0; j < kHeadMaxA; ++j) z[j] = fmaf(x, w.wp[i][j], z[j]);
-      z[kHeadMaxA] = fmaf(x, w.wv[i], z[kHeadMaxA]);
-    }
-#pragma unroll
-    for (int j = 0; j <= kHeadMaxA; ++j) z[j] = warp_sum(z[j]);
-    const float v = z[kHeadMaxA] + (bv ? bv[0] : 0.f);
-    float mx = -3.0e38f;
-#pragma unroll
-    for (int j = 0; j < kHeadMaxA; ++j) if (j < A) { z[j] += bp[j]; mx = fmaxf(mx, z[j]); }
-    float den = 0.f, p[kHeadMaxA];
-#pragma unroll
-    for (int j = 0; j < kHeadMaxA; ++j) { p[j] = (j < A) ? __expf(z[j] - mx) : 0.f; den += p[j]; }
-    const float inv = 1.0f / den;
-    float H = 0.f, lp[kHeadMaxA];
-#pragma unroll
-    for (int j = 0; j < kHeadMaxA; ++j) {
-      p[j] *= inv;
-      lp[j] = __logf(fminf(fmaxf(p[j], 1e-20f), 1.0f));
-      if (j < A) H -= p[j] * lp[j];
-    }
-    if (lane == 0) {
-      if (v_out) v_out[r] = v;
-      if (pi_out) for (int j = 0; j < A; ++j) pi_out[r * A + j] = p[j];
+    for (int q = 0; q < 2; ++q) {
+      if (q >= nrow) break;
+      const int64_t r = r0 + q;
+      const HeadRow o = head_row(w, x[q], lane, A, bias_j);
       const float m = mask ? mask[r] : 1.f;
+      if (writer && j < A && pi_out) pi_out[r * A + j] = o.p;
+      if (lane == 4 * kHeadMaxA && v_out) v_out[r] = o.v;
       if (act != nullptr) {
         const int a = act[r];
         const float ad = adv[r];
-        float lpa = 0.f;
-#pragma unroll
-        for (int j = 0; j < kHeadMaxA; ++j) if (j == a) lpa = lp[j];
-        s_pol -= m * (lpa * ad + beta * H);
-        s_ent += m * H;
-        if (dz) for (int j = 0; j < A; ++j) dz[r * A + j] = m * (-ad * ((j == a ? 1.f : 0.f) - p[j]) + beta * p[j] * (lp[j] + H));
+        const float lpa_any = __shfl_sync(0xffffffffu, o.lp, (4 * a) & 31);
+        const float lpa = (a >= 0 && a < A) ? lpa_any : 0.f;
+        if (lane == 0) { s_pol -= m * (lpa * ad + beta * o.H); s_ent += m * o.H; }
+        if (writer && j < A && dz) dz[r * A + j] = m * (-ad * ((j == a ? 1.f : 0.f) - o.p) + beta * o.p * (o.lp + o.H));
       }
-      if (R != nullptr) {
-        const float d = R[r] - v;
+      if (R != nullptr && lane == 4 * kHeadMaxA) {
+        const float d = R[r] - o.v;
         s_val += coef * m * d * d;
         if (dv) dv[r] = -2.f * coef * m * d;
       }
     }
   }
   if (sums == nullptr) return;
-  // lane 0 of every warp holds the partial sums
   __shared__ float sp[8][3];
-  if (lane == 0) { sp[threadIdx.x >> 5][0] = s_pol; sp[threadIdx.x >> 5][1] = s_val; sp[threadIdx.x >> 5][2] = s_ent; }
+  if (lane == 0) { sp[threadIdx.x >> 5][0] = s_pol; sp[threadIdx.x >> 5][2] = s_ent; }
+  if (lane == 4 * kHeadMaxA) sp[threadIdx.x >> 5][1] = s_val;
   __syncthreads();
   if (threadIdx.x < 3) {
     double t = 0.0;
@@ -577,67 +620,68 @@ __global__ void __launch_bounds__(256) a3c_head_loss_kernel(const float* __restr
 }
 
 // dh = go_p * dz Wp^T + go_v * dv Wv^T;  dWp += go_p * h^T dz;  dbp += go_p * sum dz;  dWv += go_v * h^T dv;  dbv += ...
+// One thread per COLUMN k of h (256 per CTA), CTAs stride over chunks of 32 rows whose upstream gradients
+// g[row][0..A) = go_p dz, g[row][7] = go_v dv are staged in shared memory: per row a thread reads h[r,k], writes dh[r,k]
+// (both coalesced) and does 16 FMAs against 8 broadcast values -- ~40 registers, so the SM holds 32+ warps and the
+// row-to-row load latency is hidden by other warps.  (The first form -- one warp per row, 64 weight + 64 accumulator
+// registers per lane, 16 warps per SM, each row's loads waited for in turn -- ran at 244 us for 163 840 rows: 1.4 TB/s.)
+constexpr int kHeadBwdRows = 32;
 __global__ void __launch_bounds__(256) a3c_head_bwd_kernel(const float* __restrict__ h, const float* __restrict__ Wp,
                                                            const float* __restrict__ Wv, const float* __restrict__ dz,
                                                            const float* __restrict__ dv, const float* __restrict__ go,
                                                            int64_t M, int A, float* __restrict__ dh, float* __restrict__ dWp,
                                                            float* __restrict__ dbp, float* __restrict__ dWv,
                                                            float* __restrict__ dbv) {
-  const int lane = threadIdx.x & 31;
-  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  __shared__ __align__(16) float s_g[2][kHeadBwdRows][kHeadMaxA + 1];
+  __shared__ float s_b[kHeadMaxA + 1];
+  const int k = threadIdx.x;
   const float gp = dz ? go[0] : 0.f, gv = dv ? go[1] : 0.f;
-  HeadW w;
-  head_load_w(w, Wp, Wv, A, lane);
-  float aw[8][kHeadMaxA + 1];      // this lane's rows k = lane + 32 i of [dWp | dWv]
+  float w[kHeadMaxA + 1], acc[kHeadMaxA + 1];
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
+  for (int j = 0; j < kHeadMaxA; ++j) { w[j] = (dz && j < A) ? Wp[k * A + j] : 0.f; acc[j] = 0.f; }
+  w[kHeadMaxA] = (dv && Wv) ? Wv[k] : 0.f;
+  acc[kHeadMaxA] = 0.f;
+  if (k <= kHeadMaxA) s_b[k] = 0.f;
+  // staging role of this thread: row k / 8 of a chunk, component k % 8
+  const int srow = k >> 3, sj = k & 7;
+  float bsum = 0.f;
+  const int64_t chunks = (M + kHeadBwdRows - 1) / kHeadBwdRows;
+  int buf = 0;
+  for (int64_t c = blockIdx.x; c < chunks; c += gridDim.x, buf ^= 1) {
+    const int64_t r0 = c * kHeadBwdRows;
+    {
+      const int64_t r = r0 + srow;
+      float g = 0.f;
+      if (r < M) {
+        if (sj < kHeadMaxA) { if (dz && sj < A) g = gp * dz[r * A + sj]; }
+        else if (dv) g = gv * dv[r];
+      }
+      s_g[buf][srow][sj] = g;
+      bsum += g;
+    }
+    __syncthreads();            // one barrier per chunk: the other buffer is rewritten only after the next one
+    const int rows = (int)((M - r0) < kHeadBwdRows ? (M - r0) : kHeadBwdRows);
+    const float* hp = h + r0 * 256 + k;
+    float* dp = dh + r0 * 256 + k;
+#pragma unroll 8
+    for (int i = 0; i < rows; ++i) {
+      const float x = hp[(int64_t)i * 256];
+      const float4 g0 = *reinterpret_cast<const float4*>(&s_g[buf][i][0]);
+      const float4 g1 = *reinterpret_cast<const float4*>(&s_g[buf][i][4]);
+      const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      float d = 0.f;
 #pragma unroll
-    for (int j = 0; j <= kHeadMaxA; ++j) aw[i][j] = 0.f;
-  float ab[kHeadMaxA + 1];
-#pragma unroll
-  for (int j = 0; j <= kHeadMaxA; ++j) ab[j] = 0.f;
-  for (int64_t r = warp0; r < M; r += nwarps) {
-    float g[kHeadMaxA + 1];
-#pragma unroll
-    for (int j = 0; j < kHeadMaxA; ++j) g[j] = (dz && j < A) ? gp * dz[r * A + j] : 0.f;
-    g[kHeadMaxA] = dv ? gv * dv[r] : 0.f;
-#pragma unroll
-    for (int j = 0; j <= kHeadMaxA; ++j) ab[j] += g[j];      // every lane holds the same sums; lane 0 reports them
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int k = lane + 32 * i;
-      const float x = h[r * 256 + k];
-      float d = g[kHeadMaxA] * w.wv[i];
-#pragma unroll
-      for (int j = 0; j < kHeadMaxA; ++j) { d = fmaf(g[j], w.wp[i][j], d); aw[i][j] = fmaf(x, g[j], aw[i][j]); }
-      aw[i][kHeadMaxA] = fmaf(x, g[kHeadMaxA], aw[i][kHeadMaxA]);
-      dh[r * 256 + k] = d;
+      for (int j = 0; j <= kHeadMaxA; ++j) { d = fmaf(g[j], w[j], d); acc[j] = fmaf(x, g[j], acc[j]); }
+      dp[(int64_t)i * 256] = d;
     }
   }
-  // reduce the 8 warps of the CTA in shared memory, then one atomic per element and CTA
-  __shared__ float sw[256][kHeadMaxA + 1];
-  for (int i = threadIdx.x; i < 256 * (kHeadMaxA + 1); i += blockDim.x) (&sw[0][0])[i] = 0.f;
+  atomicAdd(&s_b[sj], bsum);
   __syncthreads();
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
-#pragma unroll
-    for (int j = 0; j <= kHeadMaxA; ++j) atomicAdd(&sw[lane + 32 * i][j], aw[i][j]);
-  __shared__ float sb[kHeadMaxA + 1];
-  if (threadIdx.x <= kHeadMaxA) sb[threadIdx.x] = 0.f;
-  __syncthreads();
-  if (lane == 0)
-#pragma unroll
-    for (int j = 0; j <= kHeadMaxA; ++j) atomicAdd(&sb[j], ab[j]);
-  __syncthreads();
-  for (int i = threadIdx.x; i < 256 * (kHeadMaxA + 1); i += blockDim.x) {
-    const int k = i / (kHeadMaxA + 1), j = i - k * (kHeadMaxA + 1);
-    const float x = sw[k][j];
-    if (j < A) { if (dWp) atomicAdd(dWp + k * A + j, x); }
-    else if (j == kHeadMaxA) { if (dWv) atomicAdd(dWv + k, x); }
-  }
-  if (threadIdx.x < A && dbp) atomicAdd(dbp + threadIdx.x, sb[threadIdx.x]);
-  if (threadIdx.x == kHeadMaxA && dbv) atomicAdd(dbv, sb[kHeadMaxA]);
+  for (int j = 0; j < kHeadMaxA; ++j) if (j < A && dWp) atomicAdd(dWp + k * A + j, acc[j]);
+  if (dWv) atomicAdd(dWv + k, acc[kHeadMaxA]);
+  if (k < A && dbp) atomicAdd(dbp + k, s_b[k]);
+  if (k == kHeadMaxA && dbv) atomicAdd(dbv, s_b[kHeadMaxA]);
 }
 
 // col2im for f32 columns with C a multiple of 4 (the merged, padded deconv: C = 8): float4 per tap
@@ -1000,7 +1044,7 @@ extern "C" int unreal_a3c_head_loss(const float* h, const float* wp, const float
   UNREAL_REQUIRE(r == nullptr || wv != nullptr, "unreal_a3c_head_loss: returns need the value head");
   const int sms = sm_count();
   if (sms <= 0) return UNREAL_ECUDA;
-  int64_t want = (m + 7) / 8;
+  int64_t want = (m + 15) / 16;       // a warp takes two rows per iteration
   const int grid = (int)(want < (int64_t)sms * 4 ? want : (int64_t)sms * 4);
   a3c_head_loss_kernel<<<grid, 256, 0, as_stream(stream)>>>(h, wp, bp, wv, bv, act, adv, r, mask, m, a, entropy_beta, value_coef,
                                                            pi_out, v_out, sums, dz, dv);
@@ -1017,8 +1061,8 @@ extern "C" int unreal_a3c_head_bwd(const float* h, const float* wp, const float*
   UNREAL_REQUIRE(dv == nullptr || wv, "unreal_a3c_head_bwd: dv needs the value weights");
   const int sms = sm_count();
   if (sms <= 0) return UNREAL_ECUDA;
-  int64_t want = (m + 7) / 8;
-  const int grid = (int)(want < (int64_t)sms * 2 ? want : (int64_t)sms * 2);
+  int64_t want = (m + kHeadBwdRows - 1) / kHeadBwdRows;
+  const int grid = (int)(want < (int64_t)sms * 4 ? want : (int64_t)sms * 4);
   a3c_head_bwd_kernel<<<grid, 256, 0, as_stream(stream)>>>(h, wp, wv, dz, dv, go2, m, a, dh, dwp, dbp, dwv, dbv);
   UNREAL_LAUNCH_CHECK("a3c_head_bwd_kernel");
   return UNREAL_OK;

@@ -40,6 +40,11 @@ class LinearFn(torch.autograd.Function):
 
   @staticmethod
   def forward(ctx, x16, w16, w32, b32, relu, out_bf16):
+    # an fp32 input (the LSTM output feeding pc_fc1) is rounded to bf16 here, and its gradient leaves the dgrad GEMM as
+    # fp32 -- instead of a cast node whose backward pass is one more pass over the [S,256] gradient
+    ctx.x_f32 = x16.dtype == torch.float32
+    if ctx.x_f32:
+      x16 = x16.to(torch.bfloat16)
     y = K.gemm_bf16(x16, w16, b_mn_major=True, bias=b32, relu=relu,
                     out_dtype=torch.bfloat16 if out_bf16 else torch.float32)
     ctx.relu = relu
@@ -50,7 +55,9 @@ class LinearFn(torch.autograd.Function):
   def backward(ctx, dy):
     x16, w16, y = ctx.saved_tensors
     dy16, db = K.relu_grad(dy, y if ctx.relu else None)       # mask + bf16 + bias gradient in one pass
-    dx = K.gemm_bf16(dy16, w16, out_dtype=torch.bfloat16) if ctx.needs_input_grad[0] else None
+    dx = None
+    if ctx.needs_input_grad[0]:
+      dx = K.gemm_bf16(dy16, w16, out_dtype=torch.float32 if ctx.x_f32 else torch.bfloat16)
     dw = _wgrad(x16, dy16)
     return dx, None, dw, db, None, None
 
@@ -164,18 +171,24 @@ class LstmFn(torch.autograd.Function):
   """
 
   @staticmethod
-  def forward(ctx, fc16, lar, wcat16, w32, b32, c0, h0, lstm_in, kx, gates_dtype=torch.float32, fused_step=False):
+  def forward(ctx, fc16, lar, wcat16, w32, b32, c0, h0, lstm_in, kx, gates_dtype=torch.float32, fused_step=False, pos=None):
     """fc16 [T,N,256] bf16 (fc1 output), lar [T,N,lstm_in-256] f32: packed straight into the step operands.
+    pos int32 [T*N,2] (maze cells): fc16 is instead the 49-row fc1 TABLE [49,256] f32 (CellGatherFn's operand) and the
+    rows are gathered straight into the operands' fc1 columns -- no [T,N,256] intermediate and no strided copy of it
+    (84 MB each way per tower at 8192 envs) -- with the segment sum by cell as the table's gradient.
     gates_dtype bf16: the step GEMM writes the gate pre-activations as bf16 and the cell keeps their activations for the
     backward pass as bf16 (half the traffic of the HBM-bound cell kernels).
     fused_step (needs bf16 gates): one launch per step in both directions -- the cell runs in the step GEMM's epilogue
     (unreal_lstm_step_fwd: the pre-activations never reach HBM, only the bf16 activations the backward pass reads) and
     the cell's backward pass in the epilogue of the recurrent dh GEMM (unreal_lstm_step_bwd)."""
-    t, n = fc16.shape[:2]
+    t, n = lar.shape[:2]
     kc = kx + 256
     dev = fc16.device
     xh = torch.empty(t, n, kc, device=dev, dtype=torch.bfloat16)
-    xh[:, :, :256].copy_(fc16)
+    if pos is not None:
+      K.cell_gather(fc16.to(torch.bfloat16), pos, out=xh.view(t * n, kc)[:, :256])      # exact: the table holds bf16 values
+    else:
+      xh[:, :, :256].copy_(fc16)
     xh[:, :, 256:lstm_in].copy_(lar)
     if kx > lstm_in:
       xh[:, :, lstm_in:kx].zero_()
@@ -203,12 +216,12 @@ class LstmFn(torch.autograd.Function):
     ctx.fused_step = fused_step
     ctx.lstm_in = lstm_in
     ctx.kx = kx
-    ctx.save_for_backward(xh, wcat16, gates, c_all)
+    ctx.save_for_backward(xh, wcat16, gates, c_all, pos)
     return h_all, c_last, h_all[t - 1].clone()
 
   @staticmethod
   def backward(ctx, dh_all, dc_last, dh_last):
-    xh, wcat16, gates, c_all = ctx.saved_tensors
+    xh, wcat16, gates, c_all, pos = ctx.saved_tensors
     lstm_in, kx = ctx.lstm_in, ctx.kx
     t, n, kc = xh.shape
     dev = xh.device
@@ -235,8 +248,9 @@ class LstmFn(torch.autograd.Function):
     dw = torch.cat((dwcat[:lstm_in], dwcat[kx:]), dim=0)
     _, db = K.relu_grad(dg2, None, want_out=False)
     # only the 256 fc1 columns carry a gradient (last_action_reward is an input)
-    dfc = K.gemm_bf16(dg2, wcat16[:256], out_dtype=torch.bfloat16).view(t, n, 256)
-    return dfc, None, None, dw, db, None, None, None, None, None, None
+    dfc = K.gemm_bf16(dg2, wcat16[:256], out_dtype=torch.bfloat16)
+    dfc = dfc.view(t, n, 256) if pos is None else K.cell_segment_sum(dfc, pos)      # table mode: per-cell sums, fp32 [49,256]
+    return dfc, None, None, dw, db, None, None, None, None, None, None, None
 
 
 class Deconv8Fn(torch.autograd.Function):

@@ -258,9 +258,9 @@ class UnrealModel(object):
     """encoder + fc1 + LSTM unroll.  images [T,N,84,84,3], lar [T,N,A+1+G] -> h [T,N,256] f32."""
     t, n = images.shape[:2]
     if tables is not None and self._use_tables(images):
-      fc = CellGatherFn.apply(tables[1], images.reshape(t * n, 2)).view(t, n, 256)
-      return LstmFn.apply(fc, lar.to(torch.float32), self.wcat16, p32["lstm_kernel"], p32["lstm_bias"], c0, h0, self.lstm_in,
-                          self.kx, self._gates_dtype(), self._fused_step(n)), None
+      # the fc1 rows are gathered from the 49-cell table straight into the LSTM step operands
+      return LstmFn.apply(tables[1], lar.to(torch.float32), self.wcat16, p32["lstm_kernel"], p32["lstm_bias"], c0, h0,
+                          self.lstm_in, self.kx, self._gates_dtype(), self._fused_step(n), images.reshape(t * n, 2)), None
     h2 = self._encoder(p32, images.reshape(t * n, *images.shape[2:]))
     fc = self._lstm_input(p32, h2, t, n)
     return LstmFn.apply(fc, lar.to(torch.float32), self.wcat16, p32["lstm_kernel"], p32["lstm_bias"], c0, h0, self.lstm_in,
@@ -284,7 +284,7 @@ class UnrealModel(object):
     A = self._action_size
     if A > 7:
       raise _lib.UnrealError("the merged pixel-control head supports up to 7 actions")
-    hp = LinearFn.apply(h.to(torch.bfloat16), self.v16["W_pc_fc1"], p32["W_pc_fc1"], p32["b_pc_fc1"], True, True)
+    hp = LinearFn.apply(h, self.v16["W_pc_fc1"], p32["W_pc_fc1"], p32["b_pc_fc1"], True, True)
     return Deconv8Fn.apply(hp, self.pc_w8, self.pc_b8, p32["W_pc_deconv_v"], p32["b_pc_deconv_v"],
                            p32["W_pc_deconv_a"], p32["b_pc_deconv_a"], A, self.pc_taps if self.fused_conv else None)
 
@@ -471,7 +471,7 @@ class UnrealModel(object):
       tgt = f["R"].reshape(L * n, 400).contiguous()
       msk = f["mask"].reshape(L * n).to(torch.float32).contiguous()
       if self.fused_conv and self.fused_encoder:
-        hp = LinearFn.apply(h.reshape(L * n, 256).to(torch.bfloat16), self.v16["W_pc_fc1"], p32["W_pc_fc1"], p32["b_pc_fc1"],
+        hp = LinearFn.apply(h.reshape(L * n, 256), self.v16["W_pc_fc1"], p32["W_pc_fc1"], p32["b_pc_fc1"],
                             True, True)
         parts["pc"] = (PcFusedHeadLossFn if self.fused_pc_loss else PcHeadLossFn).apply(hp, self.pc_taps, self.pc_b8, self.pc_lin_taps, p32["W_pc_deconv_v"],
                                          p32["b_pc_deconv_v"], p32["W_pc_deconv_a"], p32["b_pc_deconv_a"], act, tgt, msk,
