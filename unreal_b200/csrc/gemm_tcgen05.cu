@@ -637,6 +637,18 @@ extern "C" int unreal_gemm_bf16(const void* a, int64_t lda, int a_mn_major, cons
   // ... and the problem is compute-bound (long K): short-K, output-dominated shapes are paced by the
   // epilogue, where independent CTAs measured faster (profiles/r1_gemm_bench_v4_2sm.jsonl)
   int use_2sm = (n > 128) && work2 >= sm_count() / 2 && kb_total >= 16;
+  if (split_k > 1) {
+    // split-K products (filter gradients) are a handful of tiles times the split the caller chose for ONE wave of single
+    // CTAs: as pairs that count must fill a wave of the 74 pairs about as well, or the second, nearly empty wave costs
+    // more than pairing saves (the LSTM's [520,S]x[S,1024] gradient at split 7: 140 single-CTA items = 0.95 of a wave,
+    // 181 us; 84 pair items = 1.14 waves, 285 us; pc_fc1's [256,S]x[S,2592] at split 6: 132 items / 66 pairs, 223 vs
+    // 199 us -- profiles/r2_wgrad_split_bench.jsonl)
+    const int sms = sm_count(), pairs = sms / 2;
+    const int64_t work1 = (int64_t)((m + kBM - 1) / kBM) * ((n + 255) / 256) * split_k;
+    const double eff1 = (double)work1 / (double)(((work1 + sms - 1) / sms) * sms);
+    const double eff2 = (double)work2 / (double)(((work2 + pairs - 1) / pairs) * pairs);
+    use_2sm = (n > 128) && kb_total / split_k >= 16 && eff2 >= eff1 - 0.05;
+  }
   { int forced = get_tunable("gemm_2sm", -1); if (forced == 0) use_2sm = 0; else if (forced == 1 && n > 128) use_2sm = 1; }
   if (use_2sm) {
     // 256 x 256 tiles.  256 x 128 tiles fill the last wave of the 74 CTA pairs better (fc1: 8.6 waves

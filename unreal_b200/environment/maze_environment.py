@@ -59,9 +59,11 @@ class BatchedMazeEnvironment(environment.Environment):
 
   def process(self, action, active=None, out_obs=None, out_pc=None, out_reward=None, out_terminal=None):
     """maze_environment.py:98-128 for all envs.  The returned tensors are owned by the env
-    and overwritten by the next call unless out_* buffers are supplied."""
+    and overwritten by the next call unless out_* buffers are supplied.  out_pc=False: no pixel-change map is
+    written (returned as None) -- the record ring re-derives it from the two cells when a frame is replayed, so the
+    batched Trainer has no reader for the 1.6 KB per env and step."""
     obs = self._obs if out_obs is None else out_obs
-    pc = self._pc if out_pc is None else out_pc
+    pc = None if out_pc is False else (self._pc if out_pc is None else out_pc)
     reward = self._reward if out_reward is None else out_reward
     terminal = self._terminal if out_terminal is None else out_terminal
     with torch.cuda.device(self.device):

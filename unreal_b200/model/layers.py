@@ -20,12 +20,15 @@ _SM = 148
 
 
 def split_k_for(m, n, k):
-  """Split the reduction so that a wgrad (few output tiles, K = samples) fills the 148 SMs."""
-  bn = 128 if n > 64 else 64
+  """Split the reduction so that a wgrad (few output tiles, K = samples) fills the 148 SMs in ONE wave: tiles as
+  unreal_gemm_bf16 cuts them (128 rows x 256 / 128 / 64 / 32 columns), and the largest split with tiles * split <= 148.
+  Measured (profiles/r2_wgrad_split_bench.jsonl): the LSTM's [520,S]x[S,1024] gradient at S = 163 840 takes 242 us at
+  split 4 (80 work items), 181 at 7 (140) and 263 at 8 (160: a second, nearly empty wave); fc1's [2592,S]x[S,256] at
+  S = 20 480 takes 54 us at 8 and 38 at 7."""
+  bn = 256 if n > 128 else (128 if n > 64 else (64 if n > 32 else 32))
   tiles = ((m + 127) // 128) * ((n + bn - 1) // bn)
   kb = (k + 63) // 64
-  want = (_SM + tiles - 1) // tiles
-  return max(1, min(want, max(1, kb // 4)))
+  return max(1, min(_SM // tiles if tiles <= _SM else 1, max(1, kb // 4)))
 
 
 def _wgrad(x16, dy16):

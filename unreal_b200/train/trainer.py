@@ -164,7 +164,6 @@ class Trainer(object):
     self._rew = torch.zeros(T, n, dtype=torch.float32, device=d)
     self._term = torch.zeros(T, n, dtype=torch.uint8, device=d)
     self._active = torch.zeros(T, n, dtype=torch.uint8, device=d)
-    self._pc = torch.zeros(T, n, 20, 20, dtype=torch.float32, device=d)
 
   def stop(self):
     if self.environment is not None:
@@ -261,7 +260,8 @@ class Trainer(object):
       action = self.choose_action(pi, active)
       self._val[t].copy_(v); self._act[t].copy_(action); self._active[t].copy_(active)
       # the new frame lands in obs[t+1]; envs whose rollout already ended are skipped by the kernel
-      env.process(action, active=active, out_obs=self._obs[t + 1], out_pc=self._pc[t],
+      # (no pixel-change map: replayed frames re-derive theirs from the record's two cells, _process_pc)
+      env.process(action, active=active, out_obs=self._obs[t + 1], out_pc=False,
                   out_reward=self._rew[t], out_terminal=self._term[t])
       self._pos[t + 1].copy_(env.state.pos)
       self.experience.add_frames(env.frame_rec)
