@@ -1,6 +1,6 @@
 """Small single-kernel workloads for `ncu --set full` captures (one GPU, a handful of launches).
 
-    python scripts/ncu_targets.py k2u8 | k2f32 | k1u8w | k1f32w | k1u8 | k4 | rp | conv2bwd | gemm2sm | lstm [envs] | lstmfused [envs]
+    python scripts/ncu_targets.py k2u8 | k2f32 | k1u8w | k1f32w | k1u8 | k4 | rp | conv2bwd | gemm2sm | lstm [envs] | lstmfused [envs] | pcfc1
 
 Each target runs its kernel three times on the benchmark's shapes; select the kernel with `-k regex:...`.
 """
@@ -84,6 +84,15 @@ elif which == "lstmfused":
       K.lstm_step_fwd(xh[i], w, b, c_all[i], c_all[i + 1], h_out=h_all[i], h16_out=xh[i + 1, :, 264:], acts=gates[i], tiled=True)
     K.lstm_step_bwd(None, w[264:], gates[1], c_all[1], c_all[2], dh[1], dc, dg[1], tiled=True)
     K.lstm_step_bwd(dg[1], w[264:], gates[0], c_all[0], c_all[1], dh[0], dc, dg[0], tiled=True)
+elif which == "pcfc1":
+  # pc_fc1 forward at the agent's batch: [163840,256] x [256,2592] + bias, ReLU, bf16 out (short K, 849 MB of output)
+  S = 163840
+  x = torch.randn(S, 256, device=dev, generator=g).to(torch.bfloat16)
+  w = (torch.randn(256, 2592, device=dev, generator=g) * 0.05).to(torch.bfloat16)
+  b = torch.zeros(2592, device=dev)
+  out = torch.empty(S, 2592, device=dev, dtype=torch.bfloat16)
+  for _ in range(3):
+    K.gemm_bf16(x, w, out=out, b_mn_major=True, bias=b, relu=True)
 else:
   raise SystemExit("unknown target " + which)
 torch.cuda.synchronize()

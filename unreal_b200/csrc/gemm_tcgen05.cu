@@ -54,14 +54,22 @@ struct GemmArgs {
   int tma_store;    // 1: epilogue stages tiles in shared memory and stores / reduces them with TMA
 };
 
-template <int BN>
+// DEEP: short-K, output-dominated products (pc_fc1 forward: K = 256, 849 MB out; the LSTM acting step).  Their tiles
+// spend ~1 us in the MMAs and then wait for the epilogue -- ncu of pc_fc1 forward (profiles/r2_pcfc1_fwd_ncu_summary.txt):
+// 342 us with the tensor pipe 35 % busy, DRAM 31 %, L2 43 %, the ONE epilogue warp per scheduler issuing 28 % of the
+// cycles and stalled on fixed-latency dependencies for most of the rest (~1800 dependent instructions per 32 x 256
+// accumulator slice).  The deep build runs EIGHT epilogue warps (two per TMEM lane quarter, half the columns each; 320
+// threads), paid for with a pipeline stage a 4-block K loop cannot use anyway.
+template <int BN, bool DEEP = false>
 struct GemmCfg {
   static constexpr int kABytes = kBM * kBK * 2;
   static constexpr int kBBytes = BN * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BN >= 256) ? 4 : (BN >= 128 ? 6 : 8);
+  static constexpr int kStages = DEEP ? ((BN >= 256) ? 3 : (BN >= 128 ? 5 : 6)) : ((BN >= 256) ? 4 : (BN >= 128 ? 6 : 8));
   static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
-  static constexpr int kEpiBytes = 4 * 2 * 4096;  // 4 epilogue warps x 2 buffers x [32 rows x 128 B]
+  static constexpr int kEpiWarps = DEEP ? 8 : 4;
+  static constexpr int kThreads = 32 * (2 + kEpiWarps);
+  static constexpr int kEpiBytes = kEpiWarps * 2 * 4096;  // epilogue warps x 2 buffers x [32 rows x 128 B]
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*barriers, tmem slot*/ + kEpiBytes + 1024 /*alignment slack*/;
 };
 
@@ -96,14 +104,14 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
 template <int BN>
 __device__ __forceinline__ void epilogue_tile(const GemmArgs& g, const CUtensorMap* tma_c, uint32_t tmem_row,
                                               uint32_t ebuf, uint32_t& ebuf_it, int lane, int warp_row0, int n_blk,
-                                              bool lead) {
+                                              bool lead, int c_begin = 0, int c_end = BN) {
   const bool atomic = g.accumulate || g.split_k > 1;
   const int row = warp_row0 + lane;
   const bool row_ok = row < g.m;
   if (g.tma_store) {
     const int group = g.c_bf16 ? 64 : 32;          // columns per 128-byte staged row
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += group) {
+    for (int c0 = c_begin; c0 < c_end; c0 += group) {
       const int gcol0 = n_blk * BN + c0;
       if (gcol0 >= g.n) break;                     // uniform: the rest of the tile is outside C
       const uint32_t buf = ebuf + (ebuf_it & 1u) * 4096u;
@@ -171,7 +179,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& g, const CUtensorM
     }
   } else {
 #pragma unroll 1
-  for (int c0 = 0; c0 < BN; c0 += 32) {
+  for (int c0 = c_begin; c0 < c_end; c0 += 32) {
     uint32_t r[32];
     tmem_ld32(tmem_row + (uint32_t)c0, r);
     tmem_ld_wait();
@@ -213,11 +221,11 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& g, const CUtensorM
   }
 }
 
-template <int BN, bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+template <int BN, bool A_MN, bool B_MN, bool DEEP = false>
+__global__ void __launch_bounds__(GemmCfg<BN, DEEP>::kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                     const __grid_constant__ CUtensorMap tma_c, const GemmArgs g) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, DEEP>;
   extern __shared__ uint8_t smem_raw[];
   // 128-byte swizzle atoms are 1024 bytes: every operand tile starts on a 1024-byte boundary
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -239,7 +247,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     prefetch_tensormap(&tma_b);
     if (g.tma_store) prefetch_tensormap(&tma_c);
     for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), Cfg::kEpiWarps); }
     fence_mbar_init();
   } else if (warp == 2) {
     tmem_alloc<Cfg::kTmemCols>(tmem_slot);
@@ -317,12 +325,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     int acc = 0; uint32_t acc_phase = 0;
     const uint32_t ebuf = smem_base + Cfg::kStages * Cfg::kStageBytes + 1024u + (uint32_t)(warp - 2) * 8192u;
     uint32_t ebuf_it = 0;
+    constexpr int kColsPerWarp = BN / (Cfg::kEpiWarps / 4);      // deep build: the two warps of a lane quarter split the columns
+    const int c_begin = ((warp - 2) >> 2) * kColsPerWarp;
     for (int w = blockIdx.x; w < work_total; w += gridDim.x) {
       const int n_blk = w % num_n, m_blk = (w / num_n) % num_m, sp = w / (num_n * num_m);
       mbar_wait(tfull_bar(acc), acc_phase);
       fence_after_sync();
       epilogue_tile<BN>(g, &tma_c, tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN), ebuf, ebuf_it,
-                        lane, m_blk * kBM + quarter * 32, n_blk, sp == 0);
+                        lane, m_blk * kBM + quarter * 32, n_blk, sp == 0, c_begin, c_begin + kColsPerWarp);
       fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
@@ -555,12 +565,12 @@ int make_tma_nd_bf16(CUtensorMap* map, const void* base, int rank, const uint64_
   return make_tma_nd(map, false, base, rank, dims, strides_bytes, box, swizzle_bytes);
 }
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, bool DEEP = false>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmArgs& g,
                        cudaStream_t st) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, DEEP>;
   static bool configured = false;
-  auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN>;
+  auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN, DEEP>;
   if (!configured) {
     UNREAL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     configured = true;
@@ -570,7 +580,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
   const int sms = sm_count();
   if (sms <= 0) return UNREAL_ECUDA;
   const int grid = (int)(work < sms ? work : sms);
-  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(ta, tb, tc, g);
+  kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(ta, tb, tc, g);
   UNREAL_LAUNCH_CHECK("gemm_tcgen05_kernel");
   return UNREAL_OK;
 }
@@ -685,6 +695,16 @@ extern "C" int unreal_gemm_bf16(const void* a, int64_t lda, int a_mn_major, cons
     UNREAL_GEMM2_CASE(128, false, false) UNREAL_GEMM2_CASE(128, false, true)
     UNREAL_GEMM2_CASE(128, true, false) UNREAL_GEMM2_CASE(128, true, true)
 #undef UNREAL_GEMM2_CASE
+  }
+  // short-K, output-dominated forward / dgrad products: the deep-epilogue build (GemmCfg<BN, true>)
+  int deep = split_k == 1 && !accumulate && !a_mn_major && kb_total <= 8 && tma_store && bn >= 128 &&
+             (int64_t)((m + kBM - 1) / kBM) * ((n + bn - 1) / bn) >= 2 * sm_count();
+  { int forced = get_tunable("gemm_deep_epilogue", -1); if (forced == 0) deep = 0; else if (forced == 1 && !a_mn_major && bn >= 128 && tma_store) deep = 1; }
+  if (deep) {
+    if (bn == 256 && b_mn_major) return launch_gemm<256, false, true, true>(ta, tb, tc, g, st);
+    if (bn == 256) return launch_gemm<256, false, false, true>(ta, tb, tc, g, st);
+    if (bn == 128 && b_mn_major) return launch_gemm<128, false, true, true>(ta, tb, tc, g, st);
+    if (bn == 128) return launch_gemm<128, false, false, true>(ta, tb, tc, g, st);
   }
 #define UNREAL_GEMM_CASE(BN_, AMN_, BMN_) \
   if (bn == BN_ && (a_mn_major != 0) == AMN_ && (b_mn_major != 0) == BMN_) return launch_gemm<BN_, AMN_, BMN_>(ta, tb, tc, g, st);
