@@ -419,6 +419,12 @@ int unreal_pc_deconv_loss(const void* h_bf16, const void* w_dtaps_bf16, const fl
                           float* db8, void* stream);
 int unreal_conv2_fwd_linear_scaled(const void* in_bf16, const void* w_taps_bf16, const float* scale, void* out_bf16, int s,
                                    void* stream);
+/* unreal_conv2_fwd_linear_scaled + the ReLU gradient of the layer its result flows into (pc_fc1, model.py:424, whose
+ * output [S,2592] is the deconv's input [S,9,9,32]): the epilogue zeroes the result where mask_y_bf16 [S,9,9,32] <= 0,
+ * rounds to bf16 and adds the rounded values summed over samples to db [2592] (pc_fc1's bias gradient; caller-zeroed,
+ * nullable) -- replaces unreal_relu_grad over the dense [S,2592] gradient.  scale nullable (1). */
+int unreal_conv2_fwd_linear_masked(const void* in_bf16, const void* w_taps_bf16, const float* scale, const void* mask_y_bf16,
+                                   void* out_bf16, float* db, int s, void* stream);
 /* The bootstrap of Trainer._process_pc (run_pc_q_max, model.py:707-712; :431-441): the same deconv with the dueling combine
  * and the max over actions in its epilogue -> qmax f32 [S,20,20]; the head output itself is not written. */
 int unreal_pc_deconv_qmax(const void* h_bf16, const void* w_dtaps_bf16, const float* bias8, int a, int s, float* qmax,

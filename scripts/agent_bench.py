@@ -54,10 +54,10 @@ def main():
     steps += d
   s1.record(); torch.cuda.synchronize(); wall = time.perf_counter() - w0
   dev_ms = s0.elapsed_time(s1)
-  upd_ms = sum(a.elapsed_time(b) for a, b in ev) / len(ev)
+  upd_ms = sum(a.elapsed_time(b) for a, b in ev) / len(ev) if ev else None     # graph replay never re-enters net.update
   print(json.dumps(dict(envs=n, history=H, iters=iters, fill_s=fill_s, wall_ms_per_update=wall / iters * 1e3,
                         device_ms_per_update=dev_ms / iters, model_update_ms=upd_ms,
-                        env_steps_per_s=n * 20 * iters / wall, losses={k: float(v) for k, v in tr.last_losses.items()},
+                        env_steps_per_s=steps / wall, losses={k: float(v) for k, v in tr.last_losses.items()},
                         mem_gb=torch.cuda.max_memory_allocated() / 1e9)))
 
 

@@ -552,6 +552,53 @@ def test_fused_pc_deconv_loss_equals_the_three_kernel_path():
       assert float((a_ - b_).abs().max()) <= 2.0 ** -8 * float(a_.abs().max()) + 1e-9, (s, name)
 
 
+def test_pc_tower_with_the_relu_gradient_in_the_backward_convolution_equals_two_nodes():
+  """PcTowerFusedFn (pc_fc1 + deconv + loss as one autograd node; pc_fc1's ReLU mask and bias gradient applied by
+  unreal_conv2_fwd_linear_masked's epilogue) against LinearFn -> PcFusedHeadLossFn with a unreal_relu_grad pass between
+  them: same loss; the masked bf16 gradient is the same tensor, so every gradient agrees to summation order.  Sample
+  counts below / at / above one wave of CTAs, an upstream gradient != 1."""
+  from unreal_b200 import kernels as K
+  from unreal_b200.model.layers import LinearFn, PcFusedHeadLossFn, PcTowerFusedFn
+  dev = torch.device("cuda", 0)
+  m = _model(dev, seed=10, n=2)
+  p32 = m._views(m.flat)
+  g = torch.Generator(device=dev).manual_seed(5)
+  names = ("W_pc_fc1", "b_pc_fc1", "W_pc_deconv_v", "b_pc_deconv_v", "W_pc_deconv_a", "b_pc_deconv_a")
+  for s in (1, 3, 296, 1000):
+    h = torch.randn(s, 256, device=dev, generator=g)
+    act = torch.randint(0, A, (s,), device=dev, generator=g, dtype=torch.int32)
+    tgt = torch.rand(s, 400, device=dev, generator=g)
+    msk = (torch.rand(s, device=dev, generator=g) < 0.8).float()
+    res = []
+    for fused in (False, True):
+      x = h.clone().requires_grad_(True)
+      lv = [p32[k].detach().clone().requires_grad_(True) for k in names]
+      if fused:
+        loss = PcTowerFusedFn.apply(x, m.v16["W_pc_fc1"], lv[0], lv[1], m.pc_taps, m.pc_b8, m.pc_lin_taps, lv[2], lv[3],
+                                    lv[4], lv[5], act, tgt, msk, A, 0.05)
+      else:
+        hp = LinearFn.apply(x, m.v16["W_pc_fc1"], lv[0], lv[1], True, True)
+        loss = PcFusedHeadLossFn.apply(hp, m.pc_taps, m.pc_b8, m.pc_lin_taps, lv[2], lv[3], lv[4], lv[5], act, tgt, msk, A, 0.05)
+      (loss * 0.37).backward()
+      res.append((loss.detach(), x.grad.float(), [l.grad for l in lv]))
+    (l0, dx0, g0), (l1, dx1, g1) = res
+    assert float(l0) == float(l1), s
+    assert float((dx0 - dx1).abs().max()) <= 1e-5 * float(dx0.abs().max()) + 1e-9, s
+    for a_, b_, name in zip(g0, g1, names):
+      assert float((a_ - b_).abs().max()) <= 1e-5 * float(a_.abs().max()) + 1e-9, (s, name)
+  # the kernel alone: masked result and bias gradient against torch on the un-masked kernel's output
+  s = 300
+  dy16 = (torch.randn(s, 20, 20, 16, device=dev, generator=g) * 0.1).to(torch.bfloat16)
+  y = torch.randn(s, 2592, device=dev, generator=g).to(torch.bfloat16)
+  sc = torch.tensor([0.61], device=dev)
+  dense = K.conv2_fwd_linear(dy16, m.pc_lin_taps, scale=sc).view(s, 2592)
+  got, db = K.conv2_fwd_linear(dy16, m.pc_lin_taps, scale=sc, mask_y=y)
+  want = torch.where(y > 0, dense, torch.zeros_like(dense))
+  assert torch.equal(got.view(s, 2592), want)
+  ref_db = want.float().sum(0)
+  assert float((db - ref_db).abs().max()) <= 1e-5 * float(ref_db.abs().max()) + 1e-6
+
+
 def test_pc_q_max_epilogue_equals_the_materialised_head():
   """run_pc_q_max with the dueling combine + max over actions inside the deconv's epilogue (unreal_pc_deconv_qmax) against
   the path that materialises the [N,20,20,8] head output and reduces it with torch ops: same maps (fp32 order only)."""

@@ -90,6 +90,8 @@ struct ConvArgs {
   int mode;           // 2: conv2 over h1
   int relu;           // apply max(., 0) in the epilogue
   const float* scale; // nullable device scalar multiplied into the accumulators (the upstream gradient of a backward conv)
+  const __nv_bfloat16* mask_y;   // MASKED build: [items][rows][N] activations of the layer the result is a gradient of
+  float* db;                     // MASKED build: [rows][N] += the masked, rounded result summed over items (its bias gradient)
 };
 
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2, int c3) {
@@ -103,7 +105,10 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, uint32_t src,
                ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 
-template <int N, int MODE>   // N output channels: 32 (conv2, MODE 2)
+// MASKED: the result is the gradient w.r.t. a ReLU layer's output `mask_y` (pc_fc1 seen as [S,9,9,32] behind the pixel-control
+// deconv): the epilogue zeroes it where mask_y <= 0 and sums the rounded values over items into db -- the ReLU-gradient /
+// bias-gradient pass over the [S,2592] gradient (2.5 GB of traffic per update at 8192 envs) disappears.
+template <int N, int MODE, bool MASKED = false>   // N output channels: 32 (conv2, MODE 2)
 __global__ void __launch_bounds__(kConvThreads, 2)
 conv_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_a2,
                         const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CUtensorMap tma_c,
@@ -199,11 +204,19 @@ conv_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_
     const uint32_t ebuf = ebuf_base + (uint32_t)(quarter < Cfg::kEpiWarps ? quarter : 0) * 8192u;
     uint32_t ebuf_it = 0;
     int acc = 0; uint32_t acc_phase = 0;
-    float b[N];
+    float b[N];       // MASKED: the bias-gradient partial sums of this thread's row instead (the masked build has no bias)
 #pragma unroll
-    for (int j = 0; j < N; ++j) b[j] = g.bias ? __ldg(g.bias + j) : 0.f;
+    for (int j = 0; j < N; ++j) b[j] = (!MASKED && g.bias) ? __ldg(g.bias + j) : 0.f;
     const float sc = g.scale ? __ldg(g.scale) : 1.f;
+    const int row = quarter * 32 + lane;
+    const bool row_ok = row < g.rows;
     for (int it = blockIdx.x; it < g.items; it += gridDim.x) {
+      uint4 yv[N / 8];
+      if constexpr (MASKED) {       // the mask row, requested before the accumulator wait
+        const uint4* ysrc = reinterpret_cast<const uint4*>(g.mask_y + ((int64_t)it * g.rows + (row_ok ? row : 0)) * N);
+#pragma unroll
+        for (int q = 0; q < N / 8; ++q) yv[q] = __ldg(ysrc + q);
+      }
       mbar_wait(tfull_bar(acc), acc_phase);
       fence_after_sync();
       if (quarter * 32 < g.rows) {
@@ -220,11 +233,24 @@ conv_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_
           uint32_t pk[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            float v0 = __uint_as_float(r[8 * q + 2 * j]) * sc + b[8 * q + 2 * j];
-            float v1 = __uint_as_float(r[8 * q + 2 * j + 1]) * sc + b[8 * q + 2 * j + 1];
-            if (g.relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
-            __nv_bfloat162 p = __floats2bfloat162_rn(v0, v1);
-            pk[j] = *reinterpret_cast<uint32_t*>(&p);
+            if constexpr (MASKED) {
+              const uint32_t yw = j == 0 ? yv[q].x : (j == 1 ? yv[q].y : (j == 2 ? yv[q].z : yv[q].w));
+              const float2 yf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&yw));
+              const float v0 = yf.x > 0.f ? __uint_as_float(r[8 * q + 2 * j]) * sc : 0.f;
+              const float v1 = yf.y > 0.f ? __uint_as_float(r[8 * q + 2 * j + 1]) * sc : 0.f;
+              __nv_bfloat162 p = __floats2bfloat162_rn(v0, v1);
+              pk[j] = *reinterpret_cast<uint32_t*>(&p);
+              if (row_ok) {                               // the bias gradient sums the ROUNDED values (as unreal_relu_grad does)
+                const float2 f = __bfloat1622float2(p);
+                b[8 * q + 2 * j] += f.x; b[8 * q + 2 * j + 1] += f.y;
+              }
+            } else {
+              float v0 = __uint_as_float(r[8 * q + 2 * j]) * sc + b[8 * q + 2 * j];
+              float v1 = __uint_as_float(r[8 * q + 2 * j + 1]) * sc + b[8 * q + 2 * j + 1];
+              if (g.relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
+              __nv_bfloat162 p = __floats2bfloat162_rn(v0, v1);
+              pk[j] = *reinterpret_cast<uint32_t*>(&p);
+            }
           }
           const uint32_t chunk = (uint32_t)q ^ (uint32_t)(lane & 7);
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowp + chunk * 16u), "r"(pk[0]), "r"(pk[1]),
@@ -241,6 +267,12 @@ conv_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
       if (++acc == kConvAcc) { acc = 0; acc_phase ^= 1u; }
+    }
+    if constexpr (MASKED) {
+      if (row_ok && g.db != nullptr) {
+#pragma unroll
+        for (int j = 0; j < N; ++j) atomicAdd(g.db + row * N + j, b[j]);
+      }
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
@@ -830,8 +862,12 @@ struct PcLossArgs {
   float* qmax;            // set (with target == NULL): write only max_a Q [S,20,20] (run_pc_q_max, model.py:707-712)
 };
 
-template <int CO>
-__global__ void __launch_bounds__(kConvThreads, 2)
+// EPI = 8 (CO = 8 only): two epilogue warps per TMEM lane quarter, one per output-row parity dy (16 accumulator columns
+// each).  The loss epilogue is a chain of dependent instructions per pixel on ONE warp per scheduler (ncu of the 4-warp
+// build, profiles/r2_conv2_bwd_20480samples_ncu_summary.txt: issue slots 39 % active, DRAM 29 %, tensor pipe 7 %, nothing
+// saturated); twice the warps hide twice the latency.
+template <int CO, int EPI = 4>
+__global__ void __launch_bounds__(64 + 32 * EPI, 2)
 conv2_dgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_w,
                            void* __restrict__ out_raw, const float* __restrict__ bias, int samples,
                            const __nv_bfloat16* __restrict__ mask_y, float* __restrict__ db, int pitch21,
@@ -853,7 +889,7 @@ conv2_dgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __gr
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&tma_a); prefetch_tensormap(&tma_w);
     for (int s = 0; s < kDgStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < kDgAcc; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    for (int a = 0; a < kDgAcc; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), EPI); }
     mbar_init(w_bar, 1);
     fence_mbar_init();
   } else if (warp == 2) {
@@ -928,9 +964,13 @@ conv2_dgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __gr
       fence_after_sync();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 64);
       if constexpr (CO == 8) {
-        // one load: column (dy, dx, c) = dy*16 + dx*8 + c; each dy is 16 contiguous floats (pixels 2X, 2X+1)
-        uint32_t v[32];
-        tmem_ld32(taddr, v);
+        // column (dy, dx, c) = dy*16 + dx*8 + c; each dy is 16 contiguous floats (pixels 2X, 2X+1).  EPI = 4: one load of
+        // both parities; EPI = 8: this warp's parity only
+        constexpr int kDy = EPI == 8 ? 1 : 2;
+        const int dy_base = EPI == 8 ? ((warp - 2) >> 2) : 0;
+        uint32_t v[16 * kDy];
+        if constexpr (EPI == 8) tmem_ld16(taddr + (uint32_t)(16 * dy_base), v);
+        else tmem_ld32(taddr, v);
         tmem_ld_wait();
         fence_before_sync();
         __syncwarp();
@@ -940,13 +980,14 @@ conv2_dgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __gr
           if (r < 100) {
             const float inv_a = 1.0f / (float)pl.a;
 #pragma unroll
-            for (int dy = 0; dy < 2; ++dy) {
+            for (int d = 0; d < kDy; ++d) {
+              const int dy = dy_base + d;
               float q2[2];
 #pragma unroll
               for (int dx = 0; dx < 2; ++dx) {
                 float y[8];
 #pragma unroll
-                for (int c = 0; c < 8; ++c) y[c] = fmaxf(__uint_as_float(v[dy * 16 + dx * 8 + c]) + b8[c], 0.f);
+                for (int c = 0; c < 8; ++c) y[c] = fmaxf(__uint_as_float(v[d * 16 + dx * 8 + c]) + b8[c], 0.f);
                 float sum = 0.f, best = -3.4e38f;
 #pragma unroll
                 for (int k = 0; k < 7; ++k) {
@@ -967,7 +1008,8 @@ conv2_dgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __gr
             const float inv_a = 1.0f / (float)pl.a;
             __nv_bfloat16* out16 = reinterpret_cast<__nv_bfloat16*>(out_raw);
 #pragma unroll
-            for (int dy = 0; dy < 2; ++dy) {
+            for (int d = 0; d < kDy; ++d) {
+              const int dy = dy_base + d;
               const int64_t pix = ((int64_t)it * 20 + 2 * Y + dy) * 20 + 2 * X;
               const float2 tg = __ldcs(reinterpret_cast<const float2*>(pl.target + pix));
               uint4* dst = reinterpret_cast<uint4*>(out16 + pix * 16);
@@ -975,7 +1017,7 @@ conv2_dgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __gr
               for (int dx = 0; dx < 2; ++dx) {
                 float y[8];
 #pragma unroll
-                for (int c = 0; c < 8; ++c) y[c] = fmaxf(__uint_as_float(v[dy * 16 + dx * 8 + c]) + b8[c], 0.f);
+                for (int c = 0; c < 8; ++c) y[c] = fmaxf(__uint_as_float(v[d * 16 + dx * 8 + c]) + b8[c], 0.f);
                 float sum = 0.f, qa = 0.f;
 #pragma unroll
                 for (int k = 0; k < 7; ++k) {
@@ -1008,15 +1050,16 @@ conv2_dgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __gr
         if (r < 100) {
           float* base = reinterpret_cast<float*>(out_raw) + (((int64_t)it * 20 + 2 * Y) * 20 + 2 * X) * 8;
 #pragma unroll
-          for (int dy = 0; dy < 2; ++dy) {
+          for (int d = 0; d < kDy; ++d) {
+            const int dy = dy_base + d;
             float4* dst = reinterpret_cast<float4*>(base + dy * 160);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               float4 o;
-              o.x = fmaxf(__uint_as_float(v[dy * 16 + 4 * q + 0]) + b8[(4 * q + 0) & 7], 0.f);
-              o.y = fmaxf(__uint_as_float(v[dy * 16 + 4 * q + 1]) + b8[(4 * q + 1) & 7], 0.f);
-              o.z = fmaxf(__uint_as_float(v[dy * 16 + 4 * q + 2]) + b8[(4 * q + 2) & 7], 0.f);
-              o.w = fmaxf(__uint_as_float(v[dy * 16 + 4 * q + 3]) + b8[(4 * q + 3) & 7], 0.f);
+              o.x = fmaxf(__uint_as_float(v[d * 16 + 4 * q + 0]) + b8[(4 * q + 0) & 7], 0.f);
+              o.y = fmaxf(__uint_as_float(v[d * 16 + 4 * q + 1]) + b8[(4 * q + 1) & 7], 0.f);
+              o.z = fmaxf(__uint_as_float(v[d * 16 + 4 * q + 2]) + b8[(4 * q + 2) & 7], 0.f);
+              o.w = fmaxf(__uint_as_float(v[d * 16 + 4 * q + 3]) + b8[(4 * q + 3) & 7], 0.f);
               dst[q] = o;
             }
           }
@@ -1128,7 +1171,7 @@ conv2_dgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __gr
   }
 }
 
-template <int N, int MODE>
+template <int N, int MODE, bool MASKED = false>
 static int launch_conv(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtensorMap& tw, const CUtensorMap& tc,
                        const ConvArgs& g, cudaStream_t st) {
   using Cfg = ConvCfg<MODE>;
@@ -1136,7 +1179,7 @@ static int launch_conv(const CUtensorMap& ta, const CUtensorMap& ta2, const CUte
   // + 5 KB: the last stage's 128-row UMMA read runs 40 rows past its 88-row stage into barriers / epilogue buffers
   constexpr int kSmem = kWBytes + Cfg::kStages * Cfg::kStageBytes + 1024 + Cfg::kEpiWarps * 2 * 4096 + 1024;
   static bool configured = false;
-  auto kern = conv_fwd_tcgen05_kernel<N, MODE>;
+  auto kern = conv_fwd_tcgen05_kernel<N, MODE, MASKED>;
   if (!configured) {
     UNREAL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
     configured = true;
@@ -1197,8 +1240,11 @@ extern "C" int unreal_conv1_fwd_maze(const int32_t* pos, const void* w_taps_bf16
 }
 
 static int conv_fwd_impl(const void* in_bf16, int layer, const void* w_taps_bf16, const float* bias, void* out_bf16, int s,
-                         int relu, void* stream, const float* scale = nullptr) {
+                         int relu, void* stream, const float* scale = nullptr, const void* mask_y = nullptr,
+                         float* db = nullptr) {
   UNREAL_REQUIRE(in_bf16 && w_taps_bf16 && out_bf16 && s > 0, "unreal_conv_fwd: null buffer or s <= 0");
+  UNREAL_REQUIRE(mask_y == nullptr || (layer == 2 && bias == nullptr && !relu && aligned16(mask_y)),
+                 "unreal_conv2_fwd_linear_masked: conv2 geometry, no bias / ReLU, 16-byte aligned mask");
   UNREAL_REQUIRE(layer == 1 || layer == 2, "unreal_conv_fwd: layer must be 1 (conv1 over x') or 2 (conv2 over h1)");
   UNREAL_REQUIRE(aligned16(in_bf16) && aligned16(w_taps_bf16) && aligned16(out_bf16),
                  "unreal_conv_fwd: buffers must be 16-byte aligned");
@@ -1208,6 +1254,8 @@ static int conv_fwd_impl(const void* in_bf16, int layer, const void* w_taps_bf16
   g.mode = layer;
   g.relu = relu;
   g.scale = scale;
+  g.mask_y = reinterpret_cast<const __nv_bfloat16*>(mask_y);
+  g.db = db;
   int rc;
   const int n = layer == 1 ? 16 : 32;
   if (layer == 1) {
@@ -1253,6 +1301,7 @@ static int conv_fwd_impl(const void* in_bf16, int layer, const void* w_taps_bf16
     rc = make_tma_nd_bf16(&tc, out_bf16, 3, dims, strides, box, 128);
     if (rc != UNREAL_OK) return rc;
   }
+  if (mask_y != nullptr) return launch_conv<32, 2, true>(ta, ta2, tw, tc, g, as_stream(stream));
   return launch_conv<32, 2>(ta, ta2, tw, tc, g, as_stream(stream));
 }
 
@@ -1268,6 +1317,12 @@ extern "C" int unreal_conv2_fwd_linear(const void* in_bf16, const void* w_taps_b
 extern "C" int unreal_conv2_fwd_linear_scaled(const void* in_bf16, const void* w_taps_bf16, const float* scale, void* out_bf16,
                                               int s, void* stream) {
   return conv_fwd_impl(in_bf16, 2, w_taps_bf16, nullptr, out_bf16, s, 0, stream, scale);
+}
+
+extern "C" int unreal_conv2_fwd_linear_masked(const void* in_bf16, const void* w_taps_bf16, const float* scale,
+                                              const void* mask_y_bf16, void* out_bf16, float* db, int s, void* stream) {
+  UNREAL_REQUIRE(mask_y_bf16 != nullptr, "unreal_conv2_fwd_linear_masked: null mask");
+  return conv_fwd_impl(in_bf16, 2, w_taps_bf16, nullptr, out_bf16, s, 0, stream, scale, mask_y_bf16, db);
 }
 
 static int conv1_wgrad_launch(const void* xpp_bf16, const void* dy_planes_bf16, float* dw_taps, int s, int pitch21,
@@ -1342,7 +1397,7 @@ extern "C" int unreal_conv2_wgrad(const void* h1_bf16, const void* dy_bf16, floa
   return UNREAL_OK;
 }
 
-template <int CO>
+template <int CO, int EPI = 4>
 static int launch_deconv(const void* dy_bf16, const void* w_dtaps_bf16, void* out, const float* bias, int s, void* stream,
                          const void* mask_y = nullptr, float* db = nullptr, int pitch21 = 0,
                          PcLossArgs pl = PcLossArgs{nullptr, nullptr, nullptr, nullptr, 0, 0.f, nullptr}) {
@@ -1363,12 +1418,12 @@ static int launch_deconv(const void* dy_bf16, const void* w_dtaps_bf16, void* ou
   }
   static bool configured = false;
   if (!configured) {
-    UNREAL_CUDA(cudaFuncSetAttribute(conv2_dgrad_tcgen05_kernel<CO>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDgSmem));
+    UNREAL_CUDA(cudaFuncSetAttribute(conv2_dgrad_tcgen05_kernel<CO, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDgSmem));
     configured = true;
   }
   const int sms = sm_count();
   if (sms <= 0) return UNREAL_ECUDA;
-  conv2_dgrad_tcgen05_kernel<CO><<<s < 2 * sms ? s : 2 * sms, kConvThreads, kDgSmem, as_stream(stream)>>>(
+  conv2_dgrad_tcgen05_kernel<CO, EPI><<<s < 2 * sms ? s : 2 * sms, 64 + 32 * EPI, kDgSmem, as_stream(stream)>>>(
       ta, tw, out, bias, s, reinterpret_cast<const __nv_bfloat16*>(mask_y), db, pitch21, pl);
   UNREAL_LAUNCH_CHECK("conv2_dgrad_tcgen05_kernel");
   return UNREAL_OK;
@@ -1403,8 +1458,10 @@ extern "C" int unreal_pc_deconv_loss(const void* h_bf16, const void* w_dtaps_bf1
   UNREAL_REQUIRE(a >= 1 && a <= 7, "unreal_pc_deconv_loss: action count %d not in 1..7 (8-channel padded head)", a);
   UNREAL_REQUIRE(aligned16(h_bf16) && aligned16(w_dtaps_bf16) && aligned16(dy16_bf16) && aligned16(target),
                  "unreal_pc_deconv_loss: 16-byte alignment");
-  return launch_deconv<8>(h_bf16, w_dtaps_bf16, dy16_bf16, bias8, s, stream, nullptr, db8, 0,
-                          PcLossArgs{act, target, mask, loss, a, lam, nullptr});
+  const PcLossArgs pl{act, target, mask, loss, a, lam, nullptr};
+  if (get_tunable("pc_loss_epi8", 1) != 0)     // eight epilogue warps (A/B switch for the benchmark scripts)
+    return launch_deconv<8, 8>(h_bf16, w_dtaps_bf16, dy16_bf16, bias8, s, stream, nullptr, db8, 0, pl);
+  return launch_deconv<8>(h_bf16, w_dtaps_bf16, dy16_bf16, bias8, s, stream, nullptr, db8, 0, pl);
 }
 
 extern "C" int unreal_pc_deconv_qmax(const void* h_bf16, const void* w_dtaps_bf16, const float* bias8, int a, int s, float* qmax,

@@ -773,12 +773,22 @@ def pc_loss_grad16(y8, act, target, mask, num_actions, lam, go):
   return dy16, db8
 
 
-def conv2_fwd_linear(x, w_taps, out=None, scale=None):
+def conv2_fwd_linear(x, w_taps, out=None, scale=None, mask_y=None, want_db=True):
   """conv2's geometry without bias / ReLU: x bf16 [S,20,20,16], w_taps = conv_taps(W [4,4,16,32], 2) -> bf16 [S,9,9,32];
-  `scale`: device scalar (f32 [1]) multiplied into the result before rounding."""
+  `scale`: device scalar (f32 [1]) multiplied into the result before rounding.  `mask_y` (bf16, S*2592 elements: the ReLU
+  output the result is a gradient of): the result is zeroed where mask_y <= 0 and (out, db f32 [2592] = its sum over
+  samples) is returned."""
   s = x.shape[0]
   if out is None:
     out = torch.empty(s, 9, 9, 32, dtype=torch.bfloat16, device=x.device)
+  if mask_y is not None:
+    if mask_y.numel() != s * 2592:
+      raise ValueError("conv2_fwd_linear: mask_y must hold S*2592 elements")
+    db = torch.zeros(2592, dtype=torch.float32, device=x.device) if want_db else None
+    call("unreal_conv2_fwd_linear_masked", ptr(x, torch.bfloat16, "x"), ptr(w_taps, torch.bfloat16, "w_taps"),
+         ptr(scale, torch.float32, "scale"), ptr(mask_y, torch.bfloat16, "mask_y"), ptr(out, torch.bfloat16, "out"),
+         ptr(db, torch.float32, "db"), s, stream_ptr())
+    return out, db
   if scale is not None:
     call("unreal_conv2_fwd_linear_scaled", ptr(x, torch.bfloat16, "x"), ptr(w_taps, torch.bfloat16, "w_taps"),
          ptr(scale, torch.float32, "scale"), ptr(out, torch.bfloat16, "out"), s, stream_ptr())

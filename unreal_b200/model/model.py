@@ -26,7 +26,7 @@ import torch
 
 from .. import _lib
 from .. import kernels as K
-from .layers import (A3CHeadLossFn, CellGatherFn, ConvFn, Deconv8Fn, EncoderFn, LinearFn, LstmFn, PcFusedHeadLossFn, PcHeadLossFn, PcLossFn, RpCellLossFn,
+from .layers import (A3CHeadLossFn, CellGatherFn, ConvFn, Deconv8Fn, EncoderFn, LinearFn, LstmFn, PcFusedHeadLossFn, PcHeadLossFn, PcLossFn, PcTowerFusedFn, RpCellLossFn,
                      RpHeadLossFn, split_k_for)
 
 
@@ -100,6 +100,9 @@ class UnrealModel(object):
     self.fused_lstm_min_rows = 2048
     # pixel-control loss inside the deconv kernel's epilogue (False: deconv -> f32 head output -> separate loss / gradient passes)
     self.fused_pc_loss = True
+    # pc_fc1's ReLU / bias gradient in the epilogue of the pixel-control head's backward convolution (PcTowerFusedFn; False:
+    # a unreal_relu_grad pass over the dense [S,2592] gradient between the two autograd nodes)
+    self.fused_pc_relu = True
     self._cells49 = torch.tensor([[x, y] for y in range(7) for x in range(7)], dtype=torch.int32, device=self._device)
     self._fc_tab_act = torch.zeros(49, 256, dtype=torch.bfloat16, device=self._device)
     self._act_xh = {}         # acting-step [x, h] GEMM operands by batch size (persistent: padding columns stay zero)
@@ -470,7 +473,13 @@ class UnrealModel(object):
       act = f["a"].reshape(L * n, -1).argmax(-1).to(torch.int32)
       tgt = f["R"].reshape(L * n, 400).contiguous()
       msk = f["mask"].reshape(L * n).to(torch.float32).contiguous()
-      if self.fused_conv and self.fused_encoder:
+      if self.fused_conv and self.fused_encoder and self.fused_pc_loss and self.fused_pc_relu:
+        # pc_fc1 + deconv + loss as one node: the ReLU / bias gradient of pc_fc1 leaves the backward convolution's epilogue
+        parts["pc"] = PcTowerFusedFn.apply(h.reshape(L * n, 256), self.v16["W_pc_fc1"], p32["W_pc_fc1"], p32["b_pc_fc1"],
+                                           self.pc_taps, self.pc_b8, self.pc_lin_taps, p32["W_pc_deconv_v"],
+                                           p32["b_pc_deconv_v"], p32["W_pc_deconv_a"], p32["b_pc_deconv_a"], act, tgt, msk,
+                                           self._action_size, self._pixel_change_lambda)
+      elif self.fused_conv and self.fused_encoder:
         hp = LinearFn.apply(h.reshape(L * n, 256), self.v16["W_pc_fc1"], p32["W_pc_fc1"], p32["b_pc_fc1"],
                             True, True)
         parts["pc"] = (PcFusedHeadLossFn if self.fused_pc_loss else PcHeadLossFn).apply(hp, self.pc_taps, self.pc_b8, self.pc_lin_taps, p32["W_pc_deconv_v"],
