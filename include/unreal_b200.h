@@ -423,8 +423,16 @@ int unreal_conv2_fwd_linear_scaled(const void* in_bf16, const void* w_taps_bf16,
  * output [S,2592] is the deconv's input [S,9,9,32]): the epilogue zeroes the result where mask_y_bf16 [S,9,9,32] <= 0,
  * rounds to bf16 and adds the rounded values summed over samples to db [2592] (pc_fc1's bias gradient; caller-zeroed,
  * nullable) -- replaces unreal_relu_grad over the dense [S,2592] gradient.  scale nullable (1). */
-int unreal_conv2_fwd_linear_masked(const void* in_bf16, const void* w_taps_bf16, const float* scale, const void* mask_y_bf16,
-                                   void* out_bf16, float* db, int s, void* stream);
+int unreal_conv2_fwd_linear_masked(const void* in_bf16, int c_in, const void* w_taps_bf16, const float* scale,
+                                   const void* mask_y_bf16, void* out_bf16, float* db, int s, void* stream);
+/* The same pixel-control backward pass on the loss gradient WITHOUT its 8 zero padding channels (half the bytes of the
+ * largest tensor of the update, written once and read twice): unreal_pc_deconv_loss_c8 writes dy8 bf16 [S,400,8];
+ * unreal_conv2_fwd_linear_masked takes it with c_in = 8 (in_bf16 [S,20,20,c_in], w_taps [32, 16*c_in]);
+ * unreal_conv2_wgrad_c8 = unreal_conv2_wgrad over an 8-channel activation x8 [S,20,20,8] -> dw [4,4,8,32] (accumulated). */
+int unreal_pc_deconv_loss_c8(const void* h_bf16, const void* w_dtaps_bf16, const float* bias8, const int32_t* act,
+                             const float* target, const float* mask, int a, float lam, int s, double* loss, void* dy8_bf16,
+                             float* db8, void* stream);
+int unreal_conv2_wgrad_c8(const void* x8_bf16, const void* dy_bf16, float* dw_taps, int s, void* stream);
 /* The bootstrap of Trainer._process_pc (run_pc_q_max, model.py:707-712; :431-441): the same deconv with the dueling combine
  * and the max over actions in its epilogue -> qmax f32 [S,20,20]; the head output itself is not written. */
 int unreal_pc_deconv_qmax(const void* h_bf16, const void* w_dtaps_bf16, const float* bias8, int a, int s, float* qmax,

@@ -29,6 +29,30 @@ def main():
   for _ in range(2):
     tr.process(None, 0)
   torch.cuda.synchronize()
+  if len(sys.argv) > 4 and sys.argv[4] == "phases":
+    # the data phase (rollout + sampling + targets) and the learner update profiled separately, kernels with launch counts
+    tables = []
+    for name, fn in (("data phase", lambda: tr._data_phase(None)), ("update", lambda: tr._update(tr.last_feed, 7e-4))):
+      with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], record_shapes=True) as prof:
+        tr._rng_in()
+        try:
+          feed = fn()
+        finally:
+          tr._rng_out()
+        if name == "data phase":
+          tr.last_feed = feed
+        torch.cuda.synchronize()
+      ka = [e for e in prof.key_averages(group_by_input_shape=True) if e.self_device_time_total > 0]
+      ka.sort(key=lambda e: -e.self_device_time_total)
+      tot = sum(e.self_device_time_total for e in ka)
+      lines = ["==== %s: %.1f us of device time, %d launches ====" % (name, tot, sum(e.count for e in ka))]
+      for e in ka[:70]:
+        lines.append("%9.1f us %5d x %7.2f  %-70s %s" % (e.self_device_time_total, e.count, e.self_device_time_total / e.count,
+                                                        e.key[:70], str(e.input_shapes)[:110]))
+      tables.append("\n".join(lines))
+    with open(out, "w") as f:
+      f.write("\n\n".join(tables) + "\n")
+    return
   with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], record_shapes=True) as prof:
     for _ in range(2):
       tr.process(None, 0)

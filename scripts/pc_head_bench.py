@@ -41,4 +41,13 @@ gb = lambda nbytes, us: round(nbytes / us / 1e3)
 res["deconv_loss_gbs"] = gb(S * (5184 + 1600 + 12800), res["deconv_loss_epi8"])
 res["bwd_conv_masked_gbs"] = gb(S * (12800 + 5184 + 5184), res["bwd_conv_masked"])
 res["wgrad_gbs"] = gb(S * (12800 + 5184), res["wgrad"])
+# the same three kernels on the 8-channel gradient
+loss, dy8, db8 = K.pc_deconv_loss(hp, m.pc_taps, b8, act, tgt, msk, A, 0.05, c8=True)
+res["deconv_loss_c8"] = round(timed(lambda: K.pc_deconv_loss(hp, m.pc_taps, b8, act, tgt, msk, A, 0.05, c8=True)), 1)
+dy8 = dy8.view(S, 20, 20, 8)
+res["bwd_conv_masked_c8"] = round(timed(lambda: K.conv2_fwd_linear(dy8, m.pc_lin_taps8, out=out, scale=sc, mask_y=hp)), 1)
+res["wgrad_c8"] = round(timed(lambda: K.conv2_wgrad(dy8, hp.view(S * 81, 32))), 1)
+res["deconv_loss_c8_gbs"] = gb(S * (5184 + 1600 + 6400), res["deconv_loss_c8"])
+res["bwd_conv_masked_c8_gbs"] = gb(S * (6400 + 5184 + 5184), res["bwd_conv_masked_c8"])
+res["wgrad_c8_gbs"] = gb(S * (6400 + 5184), res["wgrad_c8"])
 print(json.dumps(res), flush=True)

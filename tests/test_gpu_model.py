@@ -570,22 +570,27 @@ def test_pc_tower_with_the_relu_gradient_in_the_backward_convolution_equals_two_
     tgt = torch.rand(s, 400, device=dev, generator=g)
     msk = (torch.rand(s, device=dev, generator=g) < 0.8).float()
     res = []
-    for fused in (False, True):
+    for fused in (False, True, 8):
       x = h.clone().requires_grad_(True)
       lv = [p32[k].detach().clone().requires_grad_(True) for k in names]
       if fused:
-        loss = PcTowerFusedFn.apply(x, m.v16["W_pc_fc1"], lv[0], lv[1], m.pc_taps, m.pc_b8, m.pc_lin_taps, lv[2], lv[3],
+        loss = PcTowerFusedFn.apply(x, m.v16["W_pc_fc1"], lv[0], lv[1], m.pc_taps, m.pc_b8,
+                                    m.pc_lin_taps8 if fused == 8 else m.pc_lin_taps, lv[2], lv[3],
                                     lv[4], lv[5], act, tgt, msk, A, 0.05)
       else:
         hp = LinearFn.apply(x, m.v16["W_pc_fc1"], lv[0], lv[1], True, True)
         loss = PcFusedHeadLossFn.apply(hp, m.pc_taps, m.pc_b8, m.pc_lin_taps, lv[2], lv[3], lv[4], lv[5], act, tgt, msk, A, 0.05)
       (loss * 0.37).backward()
       res.append((loss.detach(), x.grad.float(), [l.grad for l in lv]))
-    (l0, dx0, g0), (l1, dx1, g1) = res
-    assert float(l0) == float(l1), s
+    (l0, dx0, g0), (l1, dx1, g1), (l2, dx2, g2) = res
+    assert float(l0) == float(l1) == float(l2), s
     assert float((dx0 - dx1).abs().max()) <= 1e-5 * float(dx0.abs().max()) + 1e-9, s
     for a_, b_, name in zip(g0, g1, names):
       assert float((a_ - b_).abs().max()) <= 1e-5 * float(a_.abs().max()) + 1e-9, (s, name)
+    # the 8-channel gradient: the UMMAs sum in another order, a bf16 rounding of d(pc_fc1 output) can move by one ulp
+    assert float((dx0 - dx2).abs().max()) <= 2.0 ** -7 * float(dx0.abs().max()) + 1e-9, s
+    for a_, b_, name in zip(g0, g2, names):
+      assert float((a_ - b_).abs().max()) <= 2.0 ** -7 * float(a_.abs().max()) + 1e-9, (s, name)
   # the kernel alone: masked result and bias gradient against torch on the un-masked kernel's output
   s = 300
   dy16 = (torch.randn(s, 20, 20, 16, device=dev, generator=g) * 0.1).to(torch.bfloat16)
@@ -597,6 +602,47 @@ def test_pc_tower_with_the_relu_gradient_in_the_backward_convolution_equals_two_
   assert torch.equal(got.view(s, 2592), want)
   ref_db = want.float().sum(0)
   assert float((db - ref_db).abs().max()) <= 1e-5 * float(ref_db.abs().max()) + 1e-6
+
+
+@pytest.mark.parametrize("s", [1, 5, 296, 297, 1500])
+def test_pc_backward_kernels_on_the_8_channel_gradient_equal_the_16_channel_ones(s):
+  """The pixel-control loss gradient without its 8 zero padding channels ([S,400,8] instead of conv2's [S,400,16]):
+  unreal_pc_deconv_loss_c8 writes the same values; unreal_conv2_fwd_linear_masked (c_in = 8: 64-byte box rows under the
+  64-byte swizzle) and unreal_conv2_wgrad_c8 give what the 16-channel kernels give on the zero-padded tensor -- the
+  padding contributes exact zeros, so only the fp32 summation order inside the UMMAs can differ."""
+  from unreal_b200 import kernels as K
+  dev = torch.device("cuda", 0)
+  m = _model(dev, seed=11, n=2)
+  g = torch.Generator(device=dev).manual_seed(s)
+  hp = torch.relu(torch.randn(s, 2592, device=dev, generator=g)).to(torch.bfloat16)
+  act = torch.randint(0, A, (s,), device=dev, generator=g, dtype=torch.int32)
+  tgt = torch.rand(s, 400, device=dev, generator=g)
+  msk = (torch.rand(s, device=dev, generator=g) < 0.8).float()
+  l16, dy16, db16 = K.pc_deconv_loss(hp, m.pc_taps, m.pc_b8, act, tgt, msk, A, 0.05)
+  l8, dy8, db8 = K.pc_deconv_loss(hp, m.pc_taps, m.pc_b8, act, tgt, msk, A, 0.05, c8=True)
+  assert tuple(dy8.shape) == (s, 400, 8) and torch.equal(dy8, dy16[:, :, :8]) and not bool(dy16[:, :, 8:].any())
+  assert abs(float(l8) - float(l16)) <= 1e-9 * max(1.0, abs(float(l16)))
+  assert float((db8 - db16).abs().max()) <= 1e-5 * float(db16.abs().max()) + 1e-9
+  # a random 8-channel gradient (the loss gradient itself is sparse in the action channels)
+  x8 = (torch.randn(s, 20, 20, 8, device=dev, generator=g) * 0.1).to(torch.bfloat16)
+  x16 = torch.zeros(s, 20, 20, 16, device=dev, dtype=torch.bfloat16); x16[..., :8] = x8
+  y = torch.randn(s, 2592, device=dev, generator=g).to(torch.bfloat16)
+  sc = torch.tensor([0.61], device=dev)
+  o16, b16 = K.conv2_fwd_linear(x16, m.pc_lin_taps, scale=sc, mask_y=y)
+  o8, b8 = K.conv2_fwd_linear(x8, m.pc_lin_taps8, scale=sc, mask_y=y)
+  ref = o16.float()
+  assert float((o8.float() - ref).abs().max()) <= 2.0 ** -7 * float(ref.abs().max()) + 1e-9      # one bf16 rounding of a reordered sum
+  assert float((b8 - b16).abs().max()) <= 2.0 ** -7 * float(b16.abs().max()) + 1e-6
+  # and against an fp32 torch convolution of the same bf16 operands
+  w8 = m.pc_w8.view(4, 4, 8, 32).float()                                    # HWIO
+  conv = torch.nn.functional.conv2d(x8.float().permute(0, 3, 1, 2), w8.permute(3, 2, 0, 1), stride=2).permute(0, 2, 3, 1) * 0.61
+  conv = torch.where(y.view(s, 9, 9, 32) > 0, conv, torch.zeros_like(conv))
+  assert float((o8.float() - conv).abs().max()) <= 2.0 ** -7 * float(conv.abs().max()) + 1e-6
+  dw16 = K.conv2_wgrad(x16, hp.view(s * 81, 32))
+  dw8 = K.conv2_wgrad(x8, hp.view(s * 81, 32))
+  assert tuple(dw8.shape) == (4, 4, 8, 32)
+  assert float((dw8 - dw16[:, :, :8]).abs().max()) <= 1e-5 * float(dw16.abs().max()) + 1e-6
+  assert not bool(dw16[:, :, 8:].any())
 
 
 def test_pc_q_max_epilogue_equals_the_materialised_head():

@@ -95,6 +95,7 @@ SIGNATURES = {
     "unreal_relu_grad": (c_int, [P, c_int, P, P, P, c_int64, c_int, c_int, P]),
     "unreal_conv1_wgrad": (c_int, [P, P, P, c_int, P]),
     "unreal_conv2_wgrad": (c_int, [P, P, P, c_int, P]),
+    "unreal_conv2_wgrad_c8": (c_int, [P, P, P, c_int, P]),
     "unreal_conv2_dgrad": (c_int, [P, P, P, c_int, P]),
     "unreal_pc_deconv_fwd": (c_int, [P, P, P, P, c_int, P]),
     "unreal_conv2_dgrad_relu": (c_int, [P, P, P, P, P, c_int, c_int, P]),
@@ -108,9 +109,10 @@ SIGNATURES = {
     "unreal_cell_gather": (c_int, [P, P, P, c_int64, c_int64, c_int, P]),
     "unreal_cell_segment_sum": (c_int, [P, c_int, P, P, c_int64, c_int, P]),
     "unreal_pc_deconv_loss": (c_int, [P, P, P, P, P, P, c_int, c_float, c_int, P, P, P, P]),
+    "unreal_pc_deconv_loss_c8": (c_int, [P, P, P, P, P, P, c_int, c_float, c_int, P, P, P, P]),
     "unreal_pc_deconv_qmax": (c_int, [P, P, P, c_int, c_int, P, P]),
     "unreal_conv2_fwd_linear_scaled": (c_int, [P, P, P, P, c_int, P]),
-    "unreal_conv2_fwd_linear_masked": (c_int, [P, P, P, P, P, P, c_int, P]),
+    "unreal_conv2_fwd_linear_masked": (c_int, [P, c_int, P, P, P, P, P, c_int, P]),
     "unreal_rp_loss": (c_int, [P, P, P, c_int64, P, P, P, P, P, P]),
     "unreal_conv2_fwd_linear": (c_int, [P, P, P, c_int, P]),
 }

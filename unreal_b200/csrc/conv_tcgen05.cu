@@ -70,16 +70,21 @@ __device__ __forceinline__ void maze_tile_to_smem(uint32_t dst, uint64_t walls49
 
 constexpr int kConvThreads = 192;
 constexpr int kConvAcc = 4;       // TMEM accumulator buffers of 32 columns
-template <int MODE> struct ConvCfg;   // MODE 2 = conv2 (conv1 has its own single-copy kernel below)
-template <> struct ConvCfg<2> {      // conv2: one step per filter row ky = 2by+dy; a box row is the 4 pixels
+template <int MODE, int C = 16> struct ConvCfg;   // MODE 2 = conv2 (conv1 has its own single-copy kernel below)
+template <int C> struct ConvCfg<2, C> {      // conv2: one step per filter row ky = 2by+dy; a box row is the 4 pixels
   // 2X..2X+3 of image row 2(Y+by)+dy = 64 (kx,c) K-columns = 128 bytes (rows of neighbouring X OVERLAP in
   // global memory: dim-1 stride 64 B under a 128-byte dim-0 extent; scripts/probes/tma_overlap_probe.cu), so a
   // sample is 4 boxes of 81 x 128 B instead of 8 of 81 x 64 B: half the TMA instructions, barrier round trips
   // and row requests.  A stage holds the 81 landed rows (88 = next multiple of the 8-row swizzle atom); the
   // 128-row UMMA reads on into the next stage, producing accumulator rows nobody stores.
-  static constexpr int kSteps = 4, kRowBytes = 128, kStageBytes = 88 * 128, kMmaPerStep = 4;
-  static constexpr int kStages = 6;  // 1.5 samples in flight per CTA, two CTAs per SM
+  // C = 8 input channels (the pixel-control loss gradient without its 8 padding channels): 64-byte rows under the
+  // 64-byte swizzle, two UMMAs per step, stages of 96 rows (a multiple of 1024 bytes) and twice as many of them.
+  static_assert(C == 16 || C == 8, "conv2 geometry with 16 or 8 input channels");
+  static constexpr int kSteps = 4, kRowBytes = 8 * C, kStageBytes = (C == 16 ? 88 : 96) * kRowBytes, kMmaPerStep = C / 4;
+  static constexpr int kStages = C == 16 ? 6 : 12;  // 1.5 (3) samples in flight per CTA, two CTAs per SM
   static constexpr int kEpiWarps = 3;   // 81 rows: quarters 0..2 store
+  // K-major UMMA descriptor high word: SBO (8 rows), version 1, swizzle mode (2: 128-byte, 4: 64-byte)
+  static constexpr uint32_t kDescHi = C == 16 ? ((1024u >> 4) | (1u << 14) | (2u << 29)) : ((512u >> 4) | (1u << 14) | (4u << 29));
 };
 
 struct ConvArgs {
@@ -108,12 +113,12 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, uint32_t src,
 // MASKED: the result is the gradient w.r.t. a ReLU layer's output `mask_y` (pc_fc1 seen as [S,9,9,32] behind the pixel-control
 // deconv): the epilogue zeroes it where mask_y <= 0 and sums the rounded values over items into db -- the ReLU-gradient /
 // bias-gradient pass over the [S,2592] gradient (2.5 GB of traffic per update at 8192 envs) disappears.
-template <int N, int MODE, bool MASKED = false>   // N output channels: 32 (conv2, MODE 2)
+template <int N, int MODE, bool MASKED = false, int C = 16>   // N output channels: 32 (conv2, MODE 2); C input channels
 __global__ void __launch_bounds__(kConvThreads, 2)
 conv_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_a2,
                         const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CUtensorMap tma_c,
                         const ConvArgs g) {
-  using Cfg = ConvCfg<MODE>;
+  using Cfg = ConvCfg<MODE, C>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   constexpr int kWTileBytes = N * Cfg::kRowBytes;          // one resident filter slice [N rows x kRowBytes]
@@ -172,7 +177,7 @@ conv_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_
     if (lane == 0) {
       // ===== MMA issuer: UMMA 128 x N x 16 over every step's K columns =====
       constexpr uint32_t idesc = idesc_bf16_f32(128, N, false, false);
-      constexpr uint32_t kDescHiSw64 = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO 1024 B, version 1, 128-byte swizzle
+      constexpr uint32_t kDescHiSw64 = Cfg::kDescHi;
       mbar_wait(w_bar, 0);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
@@ -702,16 +707,24 @@ conv1_wgrad_tcgen05_kernel(const __nv_bfloat16* __restrict__ xpp, const __nv_bfl
 // B operand.  Tile rows the boxes never write were zeroed once, so K rows 81..95 contribute exactly 0.
 // Four [64 x 32] accumulators live in TMEM across ALL samples of a CTA and are added to global
 // once.  Replaces unreal_im2col (41 KB per sample written and re-read) + the split-K GEMM.
-constexpr int kW2AStages = 6;     // 1.5 samples in flight per CTA, two CTAs per SM
-constexpr int kW2BStages = 3;
-constexpr int kW2ABytes = 96 * 128;               // 81 landed rows of 128 B (+ rows the zero dY rows cancel)
-constexpr int kW2BBytes = 8192;                   // 96 rows x 64 B used
-constexpr int kW2Tail = kW2ABytes;                // the ignored A rows 64..127 of the last stage read here
-constexpr int kW2Smem = kW2AStages * kW2ABytes + kW2BStages * kW2BBytes + kW2Tail + 1024 + 1024;
+// C = 8 (the pixel-control head's filter gradient, the loss gradient [S,400,8] in the activation's role): 64-byte A rows under
+// the 64-byte swizzle = 32 (kx,c) values; the 64-row UMMA's second 32-row chunk (LBO) reads the next stage and lands in
+// accumulator rows nobody stores.
+template <int C> struct W2Cfg {
+  static constexpr int kAStages = C == 16 ? 6 : 10;   // 1.5 (2.5) samples in flight per CTA, two CTAs per SM
+  static constexpr int kBStages = C == 16 ? 3 : 4;
+  static constexpr int kABytes = 96 * 8 * C;          // 81 landed rows of 128 (64) B (+ rows the zero dY rows cancel)
+  static constexpr int kBBytes = 8192;                // 96 rows x 64 B used
+  static constexpr int kTail = kABytes;               // the ignored A rows 64..127 of the last stage read here
+  static constexpr int kSmem = kAStages * kABytes + kBStages * kBBytes + kTail + 1024 + 1024;
+};
 
+template <int C>
 __global__ void __launch_bounds__(128, 2)
 conv2_wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_a2,
                            const __grid_constant__ CUtensorMap tma_dy, float* __restrict__ dw, int samples) {
+  constexpr int kW2AStages = W2Cfg<C>::kAStages, kW2BStages = W2Cfg<C>::kBStages, kW2ABytes = W2Cfg<C>::kABytes,
+                kW2BBytes = W2Cfg<C>::kBBytes, kW2Tail = W2Cfg<C>::kTail;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_smem = smem_base;
@@ -755,7 +768,7 @@ conv2_wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __gr
         for (int st = 0; st < 4; ++st) {          // st = filter row ky = 2by + dy
           const int by = st >> 1, dy = st & 1;
           mbar_wait(emptyA(sa), pa ^ 1u);
-          mbar_arrive_expect_tx(fullA(sa), 64 * 9 * 9 * 2);
+          mbar_arrive_expect_tx(fullA(sa), 4 * C * 9 * 9 * 2);
           tma_load_4d(a_smem + sa * kW2ABytes, dy ? &tma_a2 : &tma_a, fullA(sa), 0, 0, by, it);
           if (++sa == kW2AStages) { sa = 0; pa ^= 1u; }
         }
@@ -768,8 +781,9 @@ conv2_wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __gr
       // MN-major descriptors.  A (h1 box, 128-byte rows, SW128): lo = (addr >> 4) | LBO (stride of the next
       // 64-element M chunk; only the first chunk is real, the second reads the next stage / the tail),
       // hi = SBO 1024 B (next 8 pixel rows).  B (dY2, 64-byte rows, SW64): SBO 512 B.
-      constexpr uint32_t hi_a = (1024u >> 4) | (1u << 14) | (2u << 29);
       constexpr uint32_t hi = (512u >> 4) | (1u << 14) | (4u << 29);
+      constexpr uint32_t hi_a = C == 16 ? ((1024u >> 4) | (1u << 14) | (2u << 29)) : hi;
+      constexpr uint32_t kAStep = C == 16 ? 128u : 64u;     // 16 pixel rows of A in 16-byte units
       int sa = 0; uint32_t pa = 0; int sb = 0; uint32_t pb = 0;
       bool first = true;
       for (int it = blockIdx.x; it < samples; it += gridDim.x) {
@@ -782,7 +796,7 @@ conv2_wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __gr
           const uint32_t a_lo = ((a_smem + sa * kW2ABytes) >> 4) | (((uint32_t)kW2ABytes >> 4) << 16);
 #pragma unroll
           for (int ks = 0; ks < 6; ++ks)
-            mma_f16_lohi(tmem_base + (uint32_t)(st * 32), a_lo + (uint32_t)(ks * 128), hi_a, b_lo + (uint32_t)(ks * 64), hi, idesc,
+            mma_f16_lohi(tmem_base + (uint32_t)(st * 32), a_lo + (uint32_t)ks * kAStep, hi_a, b_lo + (uint32_t)(ks * 64), hi, idesc,
                          (first && ks == 0) ? 0u : 1u);
           mma_commit(emptyA(sa));
           if (++sa == kW2AStages) { sa = 0; pa ^= 1u; }
@@ -806,8 +820,8 @@ conv2_wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __gr
       uint32_t v[32];
       tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(st * 32), v);
       tmem_ld_wait();
-      float* o = dw + (st * 64 + m) * 32;
-      if (lane < 16) {
+      float* o = dw + (st * (4 * C) + m) * 32;
+      if (lane < 16 && m < 4 * C) {
         // 128-bit reductions: 296 CTAs add their 32 KB of partial filters to the same 8192 addresses, and 32 scalar atomics per
         // thread kept the LSU queue full (ncu: lg_throttle 5.7 stalled warps per issue at the end of the kernel)
 #pragma unroll
@@ -860,6 +874,7 @@ struct PcLossArgs {
   int a;                  // number of actions
   float lam;
   float* qmax;            // set (with target == NULL): write only max_a Q [S,20,20] (run_pc_q_max, model.py:707-712)
+  int c8;                 // loss gradient as [S,400,8] (the real channels only) instead of conv2's [S,400,16] with zero padding
 };
 
 // EPI = 8 (CO = 8 only): two epilogue warps per TMEM lane quarter, one per output-row parity dy (16 accumulator columns
@@ -1012,7 +1027,7 @@ conv2_dgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __gr
               const int dy = dy_base + d;
               const int64_t pix = ((int64_t)it * 20 + 2 * Y + dy) * 20 + 2 * X;
               const float2 tg = __ldcs(reinterpret_cast<const float2*>(pl.target + pix));
-              uint4* dst = reinterpret_cast<uint4*>(out16 + pix * 16);
+              uint4* dst = reinterpret_cast<uint4*>(out16 + pix * (pl.c8 ? 8 : 16));
 #pragma unroll
               for (int dx = 0; dx < 2; ++dx) {
                 float y[8];
@@ -1039,8 +1054,12 @@ conv2_dgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __gr
                   const float2 f = __bfloat1622float2(p);      // the bias gradient sums the ROUNDED values
                   dbacc[2 * j] += f.x; dbacc[2 * j + 1] += f.y;
                 }
-                __stcs(dst + 2 * dx, make_uint4(pk[0], pk[1], pk[2], pk[3]));
-                __stcs(dst + 2 * dx + 1, make_uint4(0u, 0u, 0u, 0u));
+                if (pl.c8) {
+                  __stcs(dst + dx, make_uint4(pk[0], pk[1], pk[2], pk[3]));
+                } else {
+                  __stcs(dst + 2 * dx, make_uint4(pk[0], pk[1], pk[2], pk[3]));
+                  __stcs(dst + 2 * dx + 1, make_uint4(0u, 0u, 0u, 0u));
+                }
               }
             }
           }
@@ -1171,15 +1190,15 @@ conv2_dgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __gr
   }
 }
 
-template <int N, int MODE, bool MASKED = false>
+template <int N, int MODE, bool MASKED = false, int C = 16>
 static int launch_conv(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtensorMap& tw, const CUtensorMap& tc,
                        const ConvArgs& g, cudaStream_t st) {
-  using Cfg = ConvCfg<MODE>;
+  using Cfg = ConvCfg<MODE, C>;
   constexpr int kWBytes = (Cfg::kSteps * N * Cfg::kRowBytes + 1023) / 1024 * 1024;
   // + 5 KB: the last stage's 128-row UMMA read runs 40 rows past its 88-row stage into barriers / epilogue buffers
   constexpr int kSmem = kWBytes + Cfg::kStages * Cfg::kStageBytes + 1024 + Cfg::kEpiWarps * 2 * 4096 + 1024;
   static bool configured = false;
-  auto kern = conv_fwd_tcgen05_kernel<N, MODE, MASKED>;
+  auto kern = conv_fwd_tcgen05_kernel<N, MODE, MASKED, C>;
   if (!configured) {
     UNREAL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
     configured = true;
@@ -1241,10 +1260,11 @@ extern "C" int unreal_conv1_fwd_maze(const int32_t* pos, const void* w_taps_bf16
 
 static int conv_fwd_impl(const void* in_bf16, int layer, const void* w_taps_bf16, const float* bias, void* out_bf16, int s,
                          int relu, void* stream, const float* scale = nullptr, const void* mask_y = nullptr,
-                         float* db = nullptr) {
+                         float* db = nullptr, int c_in = 16) {
   UNREAL_REQUIRE(in_bf16 && w_taps_bf16 && out_bf16 && s > 0, "unreal_conv_fwd: null buffer or s <= 0");
   UNREAL_REQUIRE(mask_y == nullptr || (layer == 2 && bias == nullptr && !relu && aligned16(mask_y)),
                  "unreal_conv2_fwd_linear_masked: conv2 geometry, no bias / ReLU, 16-byte aligned mask");
+  UNREAL_REQUIRE(c_in == 16 || (c_in == 8 && mask_y != nullptr), "unreal_conv_fwd: 8 input channels only in the masked conv2 build");
   UNREAL_REQUIRE(layer == 1 || layer == 2, "unreal_conv_fwd: layer must be 1 (conv1 over x') or 2 (conv2 over h1)");
   UNREAL_REQUIRE(aligned16(in_bf16) && aligned16(w_taps_bf16) && aligned16(out_bf16),
                  "unreal_conv_fwd: buffers must be 16-byte aligned");
@@ -1277,20 +1297,23 @@ static int conv_fwd_impl(const void* in_bf16, int layer, const void* w_taps_bf16
   } else {
     // h1 [S][20][20][16]: image rows y = 2Y' + dy as {64 (4 pixels x 16 c), 9 X (stride 2 pixels: rows overlap),
     // 10 Y', S}, one map per dy; the box at Y' = by is filter row ky = 2by+dy for all 81 outputs
-    const uint64_t dims[4] = {64, 9, 10, (uint64_t)s};
-    const uint64_t strides[3] = {64, 1280, 12800};
-    const uint32_t box[4] = {64, 9, 9, 1};
-    rc = make_tma_nd_bf16(&ta, in_bf16, 4, dims, strides, box, 128);
+    // (c_in = 8: the same boxes at half the widths -- 64-byte rows, 64-byte swizzle)
+    const uint64_t c4 = 4 * (uint64_t)c_in;                       // elements of a box row: 4 pixels x c_in channels
+    const uint64_t dims[4] = {c4, 9, 10, (uint64_t)s};
+    const uint64_t strides[3] = {c4, 20 * c4, 200 * c4};          // bytes: 2 pixels, 2 image rows, one sample
+    const uint32_t box[4] = {(uint32_t)c4, 9, 9, 1};
+    rc = make_tma_nd_bf16(&ta, in_bf16, 4, dims, strides, box, 2 * (int)c4);
     if (rc != UNREAL_OK) return rc;
-    rc = make_tma_nd_bf16(&ta2, reinterpret_cast<const uint8_t*>(in_bf16) + 640, 4, dims, strides, box, 128);
-    g.items = s; g.rows = 81; g.box_bytes = 64 * 9 * 9 * 2;
+    rc = make_tma_nd_bf16(&ta2, reinterpret_cast<const uint8_t*>(in_bf16) + 10 * c4, 4, dims, strides, box, 2 * (int)c4);
+    g.items = s; g.rows = 81; g.box_bytes = (int)c4 * 9 * 9 * 2;
   }
   if (rc != UNREAL_OK) return rc;
   {
-    const uint64_t dims[2] = {256, (uint64_t)n};                 // [o][(ky,kx,c)]: one 64-column slice per filter row
-    const uint64_t strides[1] = {512};
-    const uint32_t box[2] = {64u, (uint32_t)n};
-    rc = make_tma_nd_bf16(&tw, w_taps_bf16, 2, dims, strides, box, 128);
+    const uint64_t k_row = layer == 1 ? 64 : 4 * (uint64_t)c_in;  // [o][(ky,kx,c)]: one k_row-column slice per filter row
+    const uint64_t dims[2] = {4 * k_row, (uint64_t)n};
+    const uint64_t strides[1] = {8 * k_row};
+    const uint32_t box[2] = {(uint32_t)k_row, (uint32_t)n};
+    rc = make_tma_nd_bf16(&tw, w_taps_bf16, 2, dims, strides, box, 2 * (int)k_row);
     if (rc != UNREAL_OK) return rc;
   }
   {
@@ -1301,6 +1324,7 @@ static int conv_fwd_impl(const void* in_bf16, int layer, const void* w_taps_bf16
     rc = make_tma_nd_bf16(&tc, out_bf16, 3, dims, strides, box, 128);
     if (rc != UNREAL_OK) return rc;
   }
+  if (mask_y != nullptr && c_in == 8) return launch_conv<32, 2, true, 8>(ta, ta2, tw, tc, g, as_stream(stream));
   if (mask_y != nullptr) return launch_conv<32, 2, true>(ta, ta2, tw, tc, g, as_stream(stream));
   return launch_conv<32, 2>(ta, ta2, tw, tc, g, as_stream(stream));
 }
@@ -1319,10 +1343,11 @@ extern "C" int unreal_conv2_fwd_linear_scaled(const void* in_bf16, const void* w
   return conv_fwd_impl(in_bf16, 2, w_taps_bf16, nullptr, out_bf16, s, 0, stream, scale);
 }
 
-extern "C" int unreal_conv2_fwd_linear_masked(const void* in_bf16, const void* w_taps_bf16, const float* scale,
+extern "C" int unreal_conv2_fwd_linear_masked(const void* in_bf16, int c_in, const void* w_taps_bf16, const float* scale,
                                               const void* mask_y_bf16, void* out_bf16, float* db, int s, void* stream) {
   UNREAL_REQUIRE(mask_y_bf16 != nullptr, "unreal_conv2_fwd_linear_masked: null mask");
-  return conv_fwd_impl(in_bf16, 2, w_taps_bf16, nullptr, out_bf16, s, 0, stream, scale, mask_y_bf16, db);
+  UNREAL_REQUIRE(c_in == 16 || c_in == 8, "unreal_conv2_fwd_linear_masked: c_in must be 16 or 8");
+  return conv_fwd_impl(in_bf16, 2, w_taps_bf16, nullptr, out_bf16, s, 0, stream, scale, mask_y_bf16, db, c_in);
 }
 
 static int conv1_wgrad_launch(const void* xpp_bf16, const void* dy_planes_bf16, float* dw_taps, int s, int pitch21,
@@ -1365,17 +1390,19 @@ extern "C" int unreal_conv1_wgrad_p21(const void* xpp_bf16, const void* dy_plane
   return conv1_wgrad_launch(xpp_bf16, dy_planes21_bf16, dw_taps, s, 1, stream);
 }
 
-extern "C" int unreal_conv2_wgrad(const void* h1_bf16, const void* dy_bf16, float* dw_taps, int s, void* stream) {
+template <int C>
+static int conv2_wgrad_launch(const void* h1_bf16, const void* dy_bf16, float* dw_taps, int s, void* stream) {
   UNREAL_REQUIRE(h1_bf16 && dy_bf16 && dw_taps && s > 0, "unreal_conv2_wgrad: null buffer or s <= 0");
   UNREAL_REQUIRE(aligned16(h1_bf16) && aligned16(dy_bf16) && aligned16(dw_taps), "unreal_conv2_wgrad: 16-byte alignment");
   CUtensorMap ta, ta2, td;
   {
-    const uint64_t dims[4] = {64, 9, 10, (uint64_t)s};          // the forward's overlapping 128-byte rows
-    const uint64_t strides[3] = {64, 1280, 12800};
-    const uint32_t box[4] = {64, 9, 9, 1};
-    int rc = make_tma_nd_bf16(&ta, h1_bf16, 4, dims, strides, box, 128);
+    constexpr uint64_t c4 = 4 * C;                              // the forward's overlapping rows of 4 pixels x C channels
+    const uint64_t dims[4] = {c4, 9, 10, (uint64_t)s};
+    const uint64_t strides[3] = {c4, 20 * c4, 200 * c4};
+    const uint32_t box[4] = {(uint32_t)c4, 9, 9, 1};
+    int rc = make_tma_nd_bf16(&ta, h1_bf16, 4, dims, strides, box, 2 * (int)c4);
     if (rc != UNREAL_OK) return rc;
-    rc = make_tma_nd_bf16(&ta2, reinterpret_cast<const uint8_t*>(h1_bf16) + 640, 4, dims, strides, box, 128);
+    rc = make_tma_nd_bf16(&ta2, reinterpret_cast<const uint8_t*>(h1_bf16) + 10 * c4, 4, dims, strides, box, 2 * (int)c4);
     if (rc != UNREAL_OK) return rc;
   }
   {
@@ -1387,20 +1414,28 @@ extern "C" int unreal_conv2_wgrad(const void* h1_bf16, const void* dy_bf16, floa
   }
   static bool configured = false;
   if (!configured) {
-    UNREAL_CUDA(cudaFuncSetAttribute(conv2_wgrad_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kW2Smem));
+    UNREAL_CUDA(cudaFuncSetAttribute(conv2_wgrad_tcgen05_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, W2Cfg<C>::kSmem));
     configured = true;
   }
   const int sms = sm_count();
   if (sms <= 0) return UNREAL_ECUDA;
-  conv2_wgrad_tcgen05_kernel<<<s < 2 * sms ? s : 2 * sms, 128, kW2Smem, as_stream(stream)>>>(ta, ta2, td, dw_taps, s);
+  conv2_wgrad_tcgen05_kernel<C><<<s < 2 * sms ? s : 2 * sms, 128, W2Cfg<C>::kSmem, as_stream(stream)>>>(ta, ta2, td, dw_taps, s);
   UNREAL_LAUNCH_CHECK("conv2_wgrad_tcgen05_kernel");
   return UNREAL_OK;
+}
+
+extern "C" int unreal_conv2_wgrad(const void* h1_bf16, const void* dy_bf16, float* dw_taps, int s, void* stream) {
+  return conv2_wgrad_launch<16>(h1_bf16, dy_bf16, dw_taps, s, stream);
+}
+
+extern "C" int unreal_conv2_wgrad_c8(const void* x8_bf16, const void* dy_bf16, float* dw_taps, int s, void* stream) {
+  return conv2_wgrad_launch<8>(x8_bf16, dy_bf16, dw_taps, s, stream);
 }
 
 template <int CO, int EPI = 4>
 static int launch_deconv(const void* dy_bf16, const void* w_dtaps_bf16, void* out, const float* bias, int s, void* stream,
                          const void* mask_y = nullptr, float* db = nullptr, int pitch21 = 0,
-                         PcLossArgs pl = PcLossArgs{nullptr, nullptr, nullptr, nullptr, 0, 0.f, nullptr}) {
+                         PcLossArgs pl = PcLossArgs{nullptr, nullptr, nullptr, nullptr, 0, 0.f, nullptr, 0}) {
   CUtensorMap ta, tw;
   {
     const uint64_t dims[4] = {32, 9, 9, (uint64_t)s};           // dY2 [S][9 Y][9 X][32 o]
@@ -1450,18 +1485,30 @@ extern "C" int unreal_pc_deconv_fwd(const void* h_bf16, const void* w_dtaps_bf16
   return launch_deconv<8>(h_bf16, w_dtaps_bf16, y8, bias8, s, stream);
 }
 
+static int pc_deconv_loss_impl(const void* h_bf16, const void* w_dtaps_bf16, const float* bias8, const int32_t* act,
+                               const float* target, const float* mask, int a, float lam, int s, double* loss,
+                               void* dy_bf16, float* db8, int c8, void* stream) {
+  UNREAL_REQUIRE(h_bf16 && w_dtaps_bf16 && act && target && mask && dy_bf16 && s > 0,
+                 "unreal_pc_deconv_loss: null buffer or s <= 0");
+  UNREAL_REQUIRE(a >= 1 && a <= 7, "unreal_pc_deconv_loss: action count %d not in 1..7 (8-channel padded head)", a);
+  UNREAL_REQUIRE(aligned16(h_bf16) && aligned16(w_dtaps_bf16) && aligned16(dy_bf16) && aligned16(target),
+                 "unreal_pc_deconv_loss: 16-byte alignment");
+  const PcLossArgs pl{act, target, mask, loss, a, lam, nullptr, c8};
+  if (get_tunable("pc_loss_epi8", 1) != 0)     // eight epilogue warps (A/B switch for the benchmark scripts)
+    return launch_deconv<8, 8>(h_bf16, w_dtaps_bf16, dy_bf16, bias8, s, stream, nullptr, db8, 0, pl);
+  return launch_deconv<8>(h_bf16, w_dtaps_bf16, dy_bf16, bias8, s, stream, nullptr, db8, 0, pl);
+}
+
 extern "C" int unreal_pc_deconv_loss(const void* h_bf16, const void* w_dtaps_bf16, const float* bias8, const int32_t* act,
                                      const float* target, const float* mask, int a, float lam, int s, double* loss,
                                      void* dy16_bf16, float* db8, void* stream) {
-  UNREAL_REQUIRE(h_bf16 && w_dtaps_bf16 && act && target && mask && dy16_bf16 && s > 0,
-                 "unreal_pc_deconv_loss: null buffer or s <= 0");
-  UNREAL_REQUIRE(a >= 1 && a <= 7, "unreal_pc_deconv_loss: action count %d not in 1..7 (8-channel padded head)", a);
-  UNREAL_REQUIRE(aligned16(h_bf16) && aligned16(w_dtaps_bf16) && aligned16(dy16_bf16) && aligned16(target),
-                 "unreal_pc_deconv_loss: 16-byte alignment");
-  const PcLossArgs pl{act, target, mask, loss, a, lam, nullptr};
-  if (get_tunable("pc_loss_epi8", 1) != 0)     // eight epilogue warps (A/B switch for the benchmark scripts)
-    return launch_deconv<8, 8>(h_bf16, w_dtaps_bf16, dy16_bf16, bias8, s, stream, nullptr, db8, 0, pl);
-  return launch_deconv<8>(h_bf16, w_dtaps_bf16, dy16_bf16, bias8, s, stream, nullptr, db8, 0, pl);
+  return pc_deconv_loss_impl(h_bf16, w_dtaps_bf16, bias8, act, target, mask, a, lam, s, loss, dy16_bf16, db8, 0, stream);
+}
+
+extern "C" int unreal_pc_deconv_loss_c8(const void* h_bf16, const void* w_dtaps_bf16, const float* bias8, const int32_t* act,
+                                        const float* target, const float* mask, int a, float lam, int s, double* loss,
+                                        void* dy8_bf16, float* db8, void* stream) {
+  return pc_deconv_loss_impl(h_bf16, w_dtaps_bf16, bias8, act, target, mask, a, lam, s, loss, dy8_bf16, db8, 1, stream);
 }
 
 extern "C" int unreal_pc_deconv_qmax(const void* h_bf16, const void* w_dtaps_bf16, const float* bias8, int a, int s, float* qmax,
@@ -1470,5 +1517,5 @@ extern "C" int unreal_pc_deconv_qmax(const void* h_bf16, const void* w_dtaps_bf1
   UNREAL_REQUIRE(a >= 1 && a <= 7, "unreal_pc_deconv_qmax: action count %d not in 1..7 (8-channel padded head)", a);
   UNREAL_REQUIRE(aligned16(h_bf16) && aligned16(w_dtaps_bf16) && aligned16(qmax), "unreal_pc_deconv_qmax: 16-byte alignment");
   return launch_deconv<8>(h_bf16, w_dtaps_bf16, qmax, bias8, s, stream, nullptr, nullptr, 0,
-                          PcLossArgs{nullptr, nullptr, nullptr, nullptr, a, 0.f, qmax});
+                          PcLossArgs{nullptr, nullptr, nullptr, nullptr, a, 0.f, qmax, 0});
 }

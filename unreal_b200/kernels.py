@@ -630,8 +630,8 @@ def conv_taps(w16, stride):
   """conv2's HWIO filter [4,4,16,32] (bf16) -> the K-major matrix [O, 256] the fused kernel keeps resident:
   K = (ky, kx, c), i.e. one 64-column (128-byte) slice per filter row ky."""
   k, _, c, o = w16.shape
-  if (k, c, stride) != (4, 16, 2):
-    raise _lib.UnrealError("conv_taps: the fused forward kernel is conv2's geometry (4x4x16, stride 2)")
+  if (k, stride) != (4, 2) or c not in (16, 8):
+    raise _lib.UnrealError("conv_taps: the fused forward kernel is conv2's geometry (4x4x16 or 4x4x8, stride 2)")
   return w16.reshape(k * k * c, o).t().contiguous()
 
 
@@ -687,12 +687,14 @@ def pc_loss(y8, act, target, mask, num_actions, lam, want_loss=True, want_grad=F
 
 
 def conv2_wgrad(h1, dy16):
-  """h1 [S,20,20,16] bf16, dy16 [S*81, 32] bf16 (masked gradient of conv2's output) -> filter gradient
-  in HWIO layout [4,4,16,32] f32, the im2col done by TMA boxes."""
-  s = h1.shape[0]
-  acc = torch.zeros(4, 4, 16, 32, dtype=torch.float32, device=h1.device)     # the kernel accumulates in HWIO order
-  call("unreal_conv2_wgrad", ptr(h1, torch.bfloat16, "h1"), ptr(dy16, torch.bfloat16, "dy16"), ptr(acc, torch.float32), s,
-       stream_ptr())
+  """h1 [S,20,20,16] (or [S,20,20,8]) bf16, dy16 [S*81, 32] bf16 (masked gradient of conv2's output) -> filter gradient
+  in HWIO layout [4,4,16 (8),32] f32, the im2col done by TMA boxes."""
+  s, c = h1.shape[0], h1.shape[-1]
+  if c not in (16, 8):
+    raise ValueError("conv2_wgrad: 16 or 8 input channels")
+  acc = torch.zeros(4, 4, c, 32, dtype=torch.float32, device=h1.device)     # the kernel accumulates in HWIO order
+  call("unreal_conv2_wgrad" if c == 16 else "unreal_conv2_wgrad_c8", ptr(h1, torch.bfloat16, "h1"),
+       ptr(dy16, torch.bfloat16, "dy16"), ptr(acc, torch.float32), s, stream_ptr())
   return acc
 
 
@@ -785,7 +787,9 @@ def conv2_fwd_linear(x, w_taps, out=None, scale=None, mask_y=None, want_db=True)
     if mask_y.numel() != s * 2592:
       raise ValueError("conv2_fwd_linear: mask_y must hold S*2592 elements")
     db = torch.zeros(2592, dtype=torch.float32, device=x.device) if want_db else None
-    call("unreal_conv2_fwd_linear_masked", ptr(x, torch.bfloat16, "x"), ptr(w_taps, torch.bfloat16, "w_taps"),
+    if x.shape[-1] * 16 != w_taps.shape[1] or x.shape[-1] not in (16, 8):
+      raise ValueError("conv2_fwd_linear: x [S,20,20,C] needs w_taps [32, 16*C], C = 16 or 8")
+    call("unreal_conv2_fwd_linear_masked", ptr(x, torch.bfloat16, "x"), int(x.shape[-1]), ptr(w_taps, torch.bfloat16, "w_taps"),
          ptr(scale, torch.float32, "scale"), ptr(mask_y, torch.bfloat16, "mask_y"), ptr(out, torch.bfloat16, "out"),
          ptr(db, torch.float32, "db"), s, stream_ptr())
     return out, db
@@ -808,14 +812,15 @@ def pc_deconv_qmax(h16, w_dtaps, bias8, num_actions, out=None):
   return out
 
 
-def pc_deconv_loss(h16, w_dtaps, bias8, act, target, mask, num_actions, lam):
+def pc_deconv_loss(h16, w_dtaps, bias8, act, target, mask, num_actions, lam, c8=False):
   """Pixel-control head + loss in one kernel: h16 bf16 [S,9,9,32] (any view of S*2592) -> (loss f64 [1],
-  dy16 bf16 [S,400,16] = d loss / d pre-ReLU output, un-scaled by the upstream gradient, db8 [8])."""
+  dy16 bf16 [S,400,16] = d loss / d pre-ReLU output, un-scaled by the upstream gradient, db8 [8]).  `c8`: the gradient
+  without its 8 zero padding channels, [S,400,8]."""
   s = h16.numel() // 2592
   loss = torch.zeros(1, dtype=torch.float64, device=h16.device)
-  dy16 = torch.empty(s, 400, 16, dtype=torch.bfloat16, device=h16.device)
+  dy16 = torch.empty(s, 400, 8 if c8 else 16, dtype=torch.bfloat16, device=h16.device)
   db8 = torch.zeros(8, dtype=torch.float32, device=h16.device)
-  call("unreal_pc_deconv_loss", ptr(h16, torch.bfloat16, "h16"), ptr(w_dtaps, torch.bfloat16, "w_dtaps"),
+  call("unreal_pc_deconv_loss_c8" if c8 else "unreal_pc_deconv_loss", ptr(h16, torch.bfloat16, "h16"), ptr(w_dtaps, torch.bfloat16, "w_dtaps"),
        ptr(bias8, torch.float32, "bias8"), ptr(act, torch.int32, "act"), ptr(target, torch.float32, "target"),
        ptr(mask, torch.float32, "mask"), int(num_actions), float(lam), s, ptr(loss), ptr(dy16), ptr(db8), stream_ptr())
   return loss, dy16, db8
