@@ -433,6 +433,20 @@ int unreal_pc_deconv_loss_c8(const void* h_bf16, const void* w_dtaps_bf16, const
                              const float* target, const float* mask, int a, float lam, int s, double* loss, void* dy8_bf16,
                              float* db8, void* stream);
 int unreal_conv2_wgrad_c8(const void* x8_bf16, const void* dy_bf16, float* dw_taps, int s, void* stream);
+/* ... and on the PLANE-MAJOR loss gradient, the layout the agent runs: unreal_pc_deconv_loss_planes writes the gradient as
+ * four parity planes of the 10 x 10 space-to-depth grid, dy_planes bf16 [S][4 = (dy,dx)][100 = (Y,X)][8]: element
+ * (y, x, c) of the [20,20,8] gradient sits at plane (y&1, x&1), row (y>>1)*10 + (x>>1).  A sample is then ONE 6400-byte bulk
+ * copy for both backward kernels instead of four overlapping TMA boxes (which bound the kernels above by the TMA engine's
+ * row rate, not by HBM):
+ *   unreal_pc_planes_conv  = unreal_conv2_fwd_linear_masked (w_planes bf16 [4 taps (by,bx)][2 dy][2 dx][32 o][8 c] =
+ *                            W8[2by+dy][2bx+dx][c][o] of the merged deconv filter; scale nullable; db [2592] nullable);
+ *   unreal_pc_planes_wgrad = unreal_conv2_wgrad_c8 (hp bf16 [S,9,9,32] -> dw8 f32 [4,4,8,32] HWIO, accumulated). */
+int unreal_pc_deconv_loss_planes(const void* h_bf16, const void* w_dtaps_bf16, const float* bias8, const int32_t* act,
+                                 const float* target, const float* mask, int a, float lam, int s, double* loss,
+                                 void* dy_planes_bf16, float* db8, void* stream);
+int unreal_pc_planes_conv(const void* dy_planes_bf16, const void* w_planes_bf16, const float* scale, const void* mask_y_bf16,
+                          void* out_bf16, float* db, int s, void* stream);
+int unreal_pc_planes_wgrad(const void* dy_planes_bf16, const void* hp_bf16, float* dw8, int s, void* stream);
 /* The bootstrap of Trainer._process_pc (run_pc_q_max, model.py:707-712; :431-441): the same deconv with the dueling combine
  * and the max over actions in its epilogue -> qmax f32 [S,20,20]; the head output itself is not written. */
 int unreal_pc_deconv_qmax(const void* h_bf16, const void* w_dtaps_bf16, const float* bias8, int a, int s, float* qmax,

@@ -50,4 +50,12 @@ res["wgrad_c8"] = round(timed(lambda: K.conv2_wgrad(dy8, hp.view(S * 81, 32))), 
 res["deconv_loss_c8_gbs"] = gb(S * (5184 + 1600 + 6400), res["deconv_loss_c8"])
 res["bwd_conv_masked_c8_gbs"] = gb(S * (6400 + 5184 + 5184), res["bwd_conv_masked_c8"])
 res["wgrad_c8_gbs"] = gb(S * (6400 + 5184), res["wgrad_c8"])
+# ... and on the plane-major gradient (one bulk copy per sample)
+res["deconv_loss_planes"] = round(timed(lambda: K.pc_deconv_loss(hp, m.pc_taps, b8, act, tgt, msk, A, 0.05, planes=True)), 1)
+loss, dyp, db8 = K.pc_deconv_loss(hp, m.pc_taps, b8, act, tgt, msk, A, 0.05, planes=True)
+res["bwd_conv_planes"] = round(timed(lambda: K.pc_planes_conv(dyp, m.pc_w_planes, hp, scale=sc, out=out)), 1)
+res["wgrad_planes"] = round(timed(lambda: K.pc_planes_wgrad(dyp, hp)), 1)
+res["deconv_loss_planes_gbs"] = gb(S * (5184 + 1600 + 6400), res["deconv_loss_planes"])
+res["bwd_conv_planes_gbs"] = gb(S * (6400 + 5184 + 5184), res["bwd_conv_planes"])
+res["wgrad_planes_gbs"] = gb(S * (6400 + 5184), res["wgrad_planes"])
 print(json.dumps(res), flush=True)

@@ -570,20 +570,23 @@ def test_pc_tower_with_the_relu_gradient_in_the_backward_convolution_equals_two_
     tgt = torch.rand(s, 400, device=dev, generator=g)
     msk = (torch.rand(s, device=dev, generator=g) < 0.8).float()
     res = []
-    for fused in (False, True, 8):
+    for fused in (False, True, 8, "planes"):
       x = h.clone().requires_grad_(True)
       lv = [p32[k].detach().clone().requires_grad_(True) for k in names]
       if fused:
         loss = PcTowerFusedFn.apply(x, m.v16["W_pc_fc1"], lv[0], lv[1], m.pc_taps, m.pc_b8,
-                                    m.pc_lin_taps8 if fused == 8 else m.pc_lin_taps, lv[2], lv[3],
+                                    {8: m.pc_lin_taps8, "planes": m.pc_w_planes}.get(fused, m.pc_lin_taps), lv[2], lv[3],
                                     lv[4], lv[5], act, tgt, msk, A, 0.05)
       else:
         hp = LinearFn.apply(x, m.v16["W_pc_fc1"], lv[0], lv[1], True, True)
         loss = PcFusedHeadLossFn.apply(hp, m.pc_taps, m.pc_b8, m.pc_lin_taps, lv[2], lv[3], lv[4], lv[5], act, tgt, msk, A, 0.05)
       (loss * 0.37).backward()
       res.append((loss.detach(), x.grad.float(), [l.grad for l in lv]))
-    (l0, dx0, g0), (l1, dx1, g1), (l2, dx2, g2) = res
-    assert float(l0) == float(l1) == float(l2), s
+    (l0, dx0, g0), (l1, dx1, g1), (l2, dx2, g2), (l3, dx3, g3) = res
+    assert float(l0) == float(l1) == float(l2) == float(l3), s
+    assert float((dx0 - dx3).abs().max()) <= 2.0 ** -7 * float(dx0.abs().max()) + 1e-9, s
+    for a_, b_, name in zip(g0, g3, names):
+      assert float((a_ - b_).abs().max()) <= 2.0 ** -7 * float(a_.abs().max()) + 1e-9, (s, name, "planes")
     assert float((dx0 - dx1).abs().max()) <= 1e-5 * float(dx0.abs().max()) + 1e-9, s
     for a_, b_, name in zip(g0, g1, names):
       assert float((a_ - b_).abs().max()) <= 1e-5 * float(a_.abs().max()) + 1e-9, (s, name)
@@ -643,6 +646,17 @@ def test_pc_backward_kernels_on_the_8_channel_gradient_equal_the_16_channel_ones
   assert tuple(dw8.shape) == (4, 4, 8, 32)
   assert float((dw8 - dw16[:, :, :8]).abs().max()) <= 1e-5 * float(dw16.abs().max()) + 1e-6
   assert not bool(dw16[:, :, 8:].any())
+  # the plane-major layout (four parity planes of the 10 x 10 grid, one bulk copy per sample): same three results
+  lp, dyp, dbp = K.pc_deconv_loss(hp, m.pc_taps, m.pc_b8, act, tgt, msk, A, 0.05, planes=True)
+  assert tuple(dyp.shape) == (s, 4, 100, 8) and torch.equal(dyp, K.pc_planes_from_dense(dy8.view(s, 20, 20, 8)))
+  assert abs(float(lp) - float(l16)) <= 1e-9 * max(1.0, abs(float(l16)))
+  xp = K.pc_planes_from_dense(x8)
+  op, bp = K.pc_planes_conv(xp, m.pc_w_planes, y, scale=sc)
+  assert float((op.float() - conv).abs().max()) <= 2.0 ** -7 * float(conv.abs().max()) + 1e-6
+  assert float((op.float() - ref).abs().max()) <= 2.0 ** -7 * float(ref.abs().max()) + 1e-9
+  assert float((bp - b16).abs().max()) <= 2.0 ** -7 * float(b16.abs().max()) + 1e-6
+  dwp = K.pc_planes_wgrad(xp, hp)
+  assert float((dwp - dw16[:, :, :8]).abs().max()) <= 1e-5 * float(dw16.abs().max()) + 1e-6
 
 
 def test_pc_q_max_epilogue_equals_the_materialised_head():

@@ -110,6 +110,9 @@ SIGNATURES = {
     "unreal_cell_segment_sum": (c_int, [P, c_int, P, P, c_int64, c_int, P]),
     "unreal_pc_deconv_loss": (c_int, [P, P, P, P, P, P, c_int, c_float, c_int, P, P, P, P]),
     "unreal_pc_deconv_loss_c8": (c_int, [P, P, P, P, P, P, c_int, c_float, c_int, P, P, P, P]),
+    "unreal_pc_deconv_loss_planes": (c_int, [P, P, P, P, P, P, c_int, c_float, c_int, P, P, P, P]),
+    "unreal_pc_planes_conv": (c_int, [P, P, P, P, P, P, c_int, P]),
+    "unreal_pc_planes_wgrad": (c_int, [P, P, P, c_int, P]),
     "unreal_pc_deconv_qmax": (c_int, [P, P, P, c_int, c_int, P, P]),
     "unreal_conv2_fwd_linear_scaled": (c_int, [P, P, P, P, c_int, P]),
     "unreal_conv2_fwd_linear_masked": (c_int, [P, c_int, P, P, P, P, P, c_int, P]),

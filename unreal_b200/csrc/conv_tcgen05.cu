@@ -874,7 +874,8 @@ struct PcLossArgs {
   int a;                  // number of actions
   float lam;
   float* qmax;            // set (with target == NULL): write only max_a Q [S,20,20] (run_pc_q_max, model.py:707-712)
-  int c8;                 // loss gradient as [S,400,8] (the real channels only) instead of conv2's [S,400,16] with zero padding
+  int c8;                 // loss gradient as [S,400,8] (the real channels only) instead of conv2's [S,400,16] with zero padding;
+                          // 2: as four parity planes [S][4 (dy,dx)][100 (Y,X)][8] (pc_planes_*_tcgen05_kernel's tile)
 };
 
 // EPI = 8 (CO = 8 only): two epilogue warps per TMEM lane quarter, one per output-row parity dy (16 accumulator columns
@@ -974,6 +975,20 @@ conv2_dgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __gr
 #pragma unroll
     for (int c = 0; c < 16; ++c) dbacc[c] = 0.f;
     float loss_part = 0.f;
+    constexpr int kDyPre = (CO == 8 && EPI == 8) ? 1 : 2;
+    float2 tg_next[kDyPre];
+    float m_next = 0.f;
+    int a_next = 0;
+#pragma unroll
+    for (int d = 0; d < kDyPre; ++d) tg_next[d] = make_float2(0.f, 0.f);
+    if (CO == 8 && pl.target != nullptr && r < 100 && (int)blockIdx.x < samples) {
+      const int dyb = EPI == 8 ? ((warp - 2) >> 2) : 0;
+      m_next = __ldg(pl.mask + blockIdx.x);
+      a_next = __ldg(pl.act + blockIdx.x);
+#pragma unroll
+      for (int d = 0; d < kDyPre; ++d)
+        tg_next[d] = __ldcs(reinterpret_cast<const float2*>(pl.target + ((int64_t)blockIdx.x * 20 + 2 * Y + dyb + d) * 20 + 2 * X));
+    }
     for (int it = blockIdx.x; it < samples; it += gridDim.x) {
       mbar_wait(tfull_bar(acc), acc_phase);
       fence_after_sync();
@@ -1017,16 +1032,29 @@ conv2_dgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __gr
           continue;
         }
         if (pl.target != nullptr) {
+          // this sample's targets / mask / action were requested one sample ago (their HBM latency would otherwise be
+          // exposed once per sample and warp); request the next sample's now
+          float2 tgs[kDy];
+#pragma unroll
+          for (int d = 0; d < kDy; ++d) tgs[d] = tg_next[d];
+          const float m = m_next;
+          const int a = a_next;
+          if (r < 100 && it + (int)gridDim.x < samples) {
+            const int nx = it + (int)gridDim.x;
+            m_next = __ldg(pl.mask + nx);
+            a_next = __ldg(pl.act + nx);
+#pragma unroll
+            for (int d = 0; d < kDy; ++d)
+              tg_next[d] = __ldcs(reinterpret_cast<const float2*>(pl.target + ((int64_t)nx * 20 + 2 * Y + dy_base + d) * 20 + 2 * X));
+          }
           if (r < 100) {
-            const float m = __ldg(pl.mask + it);
-            const int a = __ldg(pl.act + it);
             const float inv_a = 1.0f / (float)pl.a;
             __nv_bfloat16* out16 = reinterpret_cast<__nv_bfloat16*>(out_raw);
 #pragma unroll
             for (int d = 0; d < kDy; ++d) {
               const int dy = dy_base + d;
               const int64_t pix = ((int64_t)it * 20 + 2 * Y + dy) * 20 + 2 * X;
-              const float2 tg = __ldcs(reinterpret_cast<const float2*>(pl.target + pix));
+              const float2 tg = tgs[d];
               uint4* dst = reinterpret_cast<uint4*>(out16 + pix * (pl.c8 ? 8 : 16));
 #pragma unroll
               for (int dx = 0; dx < 2; ++dx) {
@@ -1054,7 +1082,9 @@ conv2_dgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __gr
                   const float2 f = __bfloat1622float2(p);      // the bias gradient sums the ROUNDED values
                   dbacc[2 * j] += f.x; dbacc[2 * j + 1] += f.y;
                 }
-                if (pl.c8) {
+                if (pl.c8 == 2) {        // consecutive lanes = consecutive 16-byte rows of one plane
+                  __stcs(reinterpret_cast<uint4*>(out16) + ((int64_t)it * 4 + dy * 2 + dx) * 100 + r, make_uint4(pk[0], pk[1], pk[2], pk[3]));
+                } else if (pl.c8) {
                   __stcs(dst + dx, make_uint4(pk[0], pk[1], pk[2], pk[3]));
                 } else {
                   __stcs(dst + 2 * dx, make_uint4(pk[0], pk[1], pk[2], pk[3]));
@@ -1187,6 +1217,303 @@ conv2_dgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __gr
   if (warp == 2) {
     fence_after_sync();
     tmem_dealloc<kDgAcc * 64>(tmem_base);
+  }
+}
+
+
+// ---- pixel-control head: the backward pass on the PLANE-MAJOR loss gradient ----------------------------------------
+// The two kernels above spend their time in the TMA engine, not in HBM or the tensor core: a sample is four boxes of 81
+// rows (each filter row ky re-fetches the image rows it overlaps with, 3.2x the tensor's bytes), ~420 row requests, and
+// halving the row width (16 -> 8 channels) changed nothing (scripts/pc_head_bench.py: wgrad 796 us at 163 840 samples
+// either way).  conv1's remedy applies: the fused deconv + loss kernel owns the layout of its gradient, so it writes the
+// space-to-depth view directly -- four parity planes (dy,dx) of the 10 x 10 grid, [S][4][100][8 channels] bf16, 6400
+// contiguous bytes per sample = the un-swizzled UMMA layout with a 16-byte row pitch.  ONE bulk copy lands a sample;
+// tap (by,bx) of the 2x2 stride-1 convolution over that view is the same tile with the descriptor start address advanced
+// by (by*10 + bx) rows.  GEMM rows follow the 10-wide grid (m' = oy*10 + ox; ox = 9, oy = 9 and rows >= 100 are
+// accumulator rows nobody stores).
+constexpr int kPpPlaneBytes = 100 * 16;
+constexpr int kPpTileBytes = 4 * kPpPlaneBytes;          // 6400
+constexpr int kPpStages = 8;
+constexpr int kPpAcc = 4;                                // TMEM accumulators of 32 columns
+constexpr int kPpWBytes = 4 * 2 * 2 * 32 * 16;           // [tap][dy][dx][32 out rows][8 ch] bf16
+constexpr int kPpSmem = kPpWBytes + kPpStages * kPpTileBytes + 1024 /*tail reads*/ + 1024 /*barriers*/ + 1024 /*align*/;
+
+// d(pc_fc1 output) [S,9,9,32] = conv 4x4 stride 2 of the gradient with the merged deconv filter, times *scale, zeroed where
+// the pc_fc1 output mask_y <= 0, rounded to bf16; db [81*32] += the rounded values summed over samples.
+__global__ void __launch_bounds__(kConvThreads, 2)
+pc_planes_conv_tcgen05_kernel(const __nv_bfloat16* __restrict__ dyp, const __nv_bfloat16* __restrict__ w_planes,
+                              const float* __restrict__ scale, const __nv_bfloat16* __restrict__ mask_y,
+                              __nv_bfloat16* __restrict__ out, float* __restrict__ db, int samples) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t w_smem = smem_base;
+  const uint32_t a_smem = smem_base + kPpWBytes;
+  const uint32_t bar_base = a_smem + kPpStages * kPpTileBytes + 1024;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kPpStages + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kPpStages + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kPpStages + kPpAcc + a); };
+  const uint32_t w_bar = bar_base + 8u * (2 * kPpStages + 2 * kPpAcc);
+  const uint32_t tmem_slot = w_bar + 8u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < kPpStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < kPpAcc; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    mbar_init(w_bar, 1);
+    fence_mbar_init();
+  } else if (warp == 2) {
+    tmem_alloc<kPpAcc * 32>(tmem_slot);
+  }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== producer: resident filters (one bulk copy), then ONE 6400-byte bulk copy per sample =====
+      mbar_arrive_expect_tx(w_bar, kPpWBytes);
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(w_smem), "l"(w_planes), "r"(kPpWBytes), "r"(w_bar) : "memory");
+      int stage = 0; uint32_t phase = 0;
+      for (int it = blockIdx.x; it < samples; it += gridDim.x) {
+        mbar_wait(empty_bar(stage), phase ^ 1u);
+        mbar_arrive_expect_tx(full_bar(stage), kPpTileBytes);
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(a_smem + stage * kPpTileBytes), "l"(reinterpret_cast<const uint8_t*>(dyp) + (int64_t)it * kPpTileBytes),
+                       "r"(kPpTileBytes), "r"(full_bar(stage)) : "memory");
+        if (++stage == kPpStages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer: 4 taps x 2 UMMA (128 x 32 x 16: the two dx planes of one dy) on the one resident tile =====
+      constexpr uint32_t idesc = idesc_bf16_f32(128, 32, false, false);
+      constexpr uint32_t desc_hi = (128u >> 4) | (1u << 14);        // SBO = 128 B (8 rows), descriptor version 1, no swizzle
+      const uint32_t w_lo0 = (w_smem >> 4) | ((512u >> 4) << 16);   // filter tiles: LBO = 512 B (32 rows of one 8-channel chunk)
+      mbar_wait(w_bar, 0);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int it = blockIdx.x; it < samples; it += gridDim.x) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        mbar_wait(full_bar(stage), phase);
+        fence_after_sync();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * 32);
+        const uint32_t a_lo0 = ((a_smem + stage * kPpTileBytes) >> 4) | ((uint32_t)(kPpPlaneBytes >> 4) << 16);   // LBO = plane stride
+#pragma unroll
+        for (int tap = 0; tap < 4; ++tap) {
+          const uint32_t shift16 = (uint32_t)((tap >> 1) * 10 + (tap & 1));
+#pragma unroll
+          for (int j = 0; j < 2; ++j)
+            mma_f16_lohi(tmem_d, a_lo0 + (uint32_t)(2 * j * kPpPlaneBytes >> 4) + shift16, desc_hi,
+                         w_lo0 + (uint32_t)(((tap * 2 + j) * 1024) >> 4), desc_hi, idesc, (tap > 0 || j > 0) ? 1u : 0u);
+        }
+        mma_commit(empty_bar(stage));
+        mma_commit(tfull_bar(acc));
+        if (++stage == kPpStages) { stage = 0; phase ^= 1u; }
+        if (++acc == kPpAcc) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else {
+    // ===== epilogue: row m' = oy*10 + ox -> scale, pc_fc1's ReLU mask, bf16, bias-gradient partial sums =====
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const int oy = r / 10, ox = r - oy * 10;
+    const bool valid = oy < 9 && ox < 9;
+    const int orow = valid ? oy * 9 + ox : 0;
+    int acc = 0; uint32_t acc_phase = 0;
+    float dbacc[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) dbacc[j] = 0.f;
+    const float sc = scale ? __ldg(scale) : 1.f;
+    // the mask row of a sample is requested one sample ahead: with the accumulators ready long before the epilogue gets to
+    // them, a load issued in the same iteration would expose its whole HBM latency once per sample
+    uint4 yn[4];
+    if (blockIdx.x < samples) {
+      const uint4* ysrc = reinterpret_cast<const uint4*>(mask_y + ((int64_t)blockIdx.x * 81 + orow) * 32);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) yn[q] = __ldg(ysrc + q);
+    }
+    for (int it = blockIdx.x; it < samples; it += gridDim.x) {
+      const int64_t row0 = ((int64_t)it * 81 + orow) * 32;
+      uint4 yv[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) yv[q] = yn[q];
+      if (it + (int)gridDim.x < samples) {
+        const uint4* ysrc = reinterpret_cast<const uint4*>(mask_y + ((int64_t)(it + gridDim.x) * 81 + orow) * 32);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) yn[q] = __ldg(ysrc + q);
+      }
+      mbar_wait(tfull_bar(acc), acc_phase);
+      fence_after_sync();
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 32), v);
+      tmem_ld_wait();
+      fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (valid) {
+        uint4* dst = reinterpret_cast<uint4*>(out + row0);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t yw = j == 0 ? yv[q].x : (j == 1 ? yv[q].y : (j == 2 ? yv[q].z : yv[q].w));
+            const float2 yf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&yw));
+            const float v0 = yf.x > 0.f ? __uint_as_float(v[8 * q + 2 * j]) * sc : 0.f;
+            const float v1 = yf.y > 0.f ? __uint_as_float(v[8 * q + 2 * j + 1]) * sc : 0.f;
+            __nv_bfloat162 p2 = __floats2bfloat162_rn(v0, v1);
+            pk[j] = *reinterpret_cast<uint32_t*>(&p2);
+            const float2 f = __bfloat1622float2(p2);      // the bias gradient sums the ROUNDED values (as unreal_relu_grad does)
+            dbacc[8 * q + 2 * j] += f.x; dbacc[8 * q + 2 * j + 1] += f.y;
+          }
+          __stcs(dst + q, make_uint4(pk[0], pk[1], pk[2], pk[3]));
+        }
+      }
+      if (++acc == kPpAcc) { acc = 0; acc_phase ^= 1u; }
+    }
+    if (valid && db != nullptr) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) atomicAdd(db + orow * 32 + j, dbacc[j]);
+    }
+  }
+  __syncwarp();
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 2) {
+    fence_after_sync();
+    tmem_dealloc<kPpAcc * 32>(tmem_base);
+  }
+}
+
+// The merged deconv filter's gradient dW8[ky][kx][c][o] = sum over samples and (oy,ox) of dy[2oy+ky, 2ox+kx, c] . hp[oy,ox,o]:
+// the reduction runs over pixels, so both operands are MN-major -- the gradient planes as they lie (A: M = (dy,dx,c) = 4 real
+// 8-channel chunks of the 8 a 64-row UMMA reads, K = grid rows at a 16-byte pitch, tap = start address shift), the sample's
+// pc_fc1 output hp [9,9,32] through a 4-D box {32, 10, 10, 1} (column ox = 9 and row oy = 9 are out of bounds = TMA zero
+// fill) as a 64-byte-swizzled B tile on the same 10-wide grid.  K = 112 rows: rows 100..111 of the B tile are zero (zeroed
+// once, never written), so the finite gradient values A holds there contribute nothing.  Four [32 x 32] accumulators (one per
+// tap) live in TMEM across all samples of a CTA and are added to global once, in HWIO order.
+constexpr int kPwAStages = 8;
+constexpr int kPwBStages = 4;
+constexpr int kPwBBytes = 8192;                    // 100 landed rows x 64 B (+ 12 zero rows), 1024-aligned
+constexpr int kPwTail = 8192;                      // the four garbage chunks of the last A stage read here
+constexpr int kPwSmem = kPwBStages * kPwBBytes + kPwAStages * kPpTileBytes + kPwTail + 1024 + 1024;
+
+__global__ void __launch_bounds__(128, 2)
+pc_planes_wgrad_tcgen05_kernel(const __nv_bfloat16* __restrict__ dyp, const __grid_constant__ CUtensorMap tma_hp,
+                               float* __restrict__ dw, int samples) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t b_smem = smem_base;
+  const uint32_t a_smem = b_smem + kPwBStages * kPwBBytes;
+  const uint32_t bar_base = a_smem + kPwAStages * kPpTileBytes + kPwTail;
+  auto fullA = [&](int s) { return bar_base + 8u * s; };
+  auto emptyA = [&](int s) { return bar_base + 8u * (kPwAStages + s); };
+  auto fullB = [&](int s) { return bar_base + 8u * (2 * kPwAStages + s); };
+  auto emptyB = [&](int s) { return bar_base + 8u * (2 * kPwAStages + kPwBStages + s); };
+  const uint32_t done_bar = bar_base + 8u * (2 * kPwAStages + 2 * kPwBStages);
+  const uint32_t tmem_slot = done_bar + 8u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // zero every tile byte once: the never-written rows of the B tiles, and whatever A reads before its first copies land
+  for (uint32_t off = threadIdx.x * 16u; off < (uint32_t)(kPwBStages * kPwBBytes + kPwAStages * kPpTileBytes + kPwTail); off += 128u * 16u)
+    asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(smem_base + off), "r"(0u) : "memory");
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&tma_hp);
+    for (int s = 0; s < kPwAStages; ++s) { mbar_init(fullA(s), 1); mbar_init(emptyA(s), 1); }
+    for (int s = 0; s < kPwBStages; ++s) { mbar_init(fullB(s), 1); mbar_init(emptyB(s), 1); }
+    mbar_init(done_bar, 1);
+    fence_mbar_init();
+  } else if (warp == 2) {
+    tmem_alloc<128>(tmem_slot);
+  }
+  fence_proxy_async_smem();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int sa = 0; uint32_t pa = 0; int sb = 0; uint32_t pb = 0;
+      for (int it = blockIdx.x; it < samples; it += gridDim.x) {
+        mbar_wait(emptyB(sb), pb ^ 1u);
+        mbar_arrive_expect_tx(fullB(sb), 100 * 64);
+        tma_load_4d(b_smem + sb * kPwBBytes, &tma_hp, fullB(sb), 0, 0, 0, it);
+        if (++sb == kPwBStages) { sb = 0; pb ^= 1u; }
+        mbar_wait(emptyA(sa), pa ^ 1u);
+        mbar_arrive_expect_tx(fullA(sa), kPpTileBytes);
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(a_smem + sa * kPpTileBytes), "l"(reinterpret_cast<const uint8_t*>(dyp) + (int64_t)it * kPpTileBytes),
+                       "r"(kPpTileBytes), "r"(fullA(sa)) : "memory");
+        if (++sa == kPwAStages) { sa = 0; pa ^= 1u; }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = idesc_bf16_f32(64, 32, true, true);
+      // A: MN-major un-swizzled -- LBO = 128 B (next 8 grid rows), SBO = plane stride (next 8-channel chunk)
+      // B: MN-major, 64-byte rows, 64-byte swizzle -- SBO = 512 B (next 8 grid rows)
+      constexpr uint32_t a_hi = ((uint32_t)kPpPlaneBytes >> 4) | (1u << 14);
+      constexpr uint32_t b_hi = (512u >> 4) | (1u << 14) | (4u << 29);
+      int sa = 0; uint32_t pa = 0; int sb = 0; uint32_t pb = 0;
+      bool first = true;
+      for (int it = blockIdx.x; it < samples; it += gridDim.x) {
+        mbar_wait(fullB(sb), pb);
+        mbar_wait(fullA(sa), pa);
+        fence_after_sync();
+        const uint32_t a_lo0 = ((a_smem + sa * kPpTileBytes) >> 4) | ((128u >> 4) << 16);
+        const uint32_t b_lo0 = ((b_smem + sb * kPwBBytes) >> 4) | ((64u >> 4) << 16);
+#pragma unroll
+        for (int tap = 0; tap < 4; ++tap) {
+          const uint32_t shift16 = (uint32_t)((tap >> 1) * 10 + (tap & 1));
+#pragma unroll
+          for (int ks = 0; ks < 7; ++ks)
+            mma_f16_lohi(tmem_base + (uint32_t)(tap * 32), a_lo0 + shift16 + (uint32_t)(ks * 16), a_hi, b_lo0 + (uint32_t)(ks * 64), b_hi,
+                         idesc, (first && ks == 0) ? 0u : 1u);
+        }
+        first = false;
+        mma_commit(emptyA(sa));
+        mma_commit(emptyB(sb));
+        if (++sa == kPwAStages) { sa = 0; pa ^= 1u; }
+        if (++sb == kPwBStages) { sb = 0; pb ^= 1u; }
+      }
+      mma_commit(done_bar);
+    }
+    __syncwarp();
+  }
+  {
+    // ===== final epilogue: a 64-row accumulator keeps row m = (dy,dx,c) in lane 32*(m/16) + m%16 (warps 0, 1: the 32 real
+    // rows), accumulator `tap` in columns tap*32 + o -> dW8 in HWIO order [ky = 2by+dy][kx = 2bx+dx][c][o] =====
+    mbar_wait(done_bar, 0);
+    fence_after_sync();
+    const int m = warp * 16 + lane;
+    const int pdy = (m >> 4) & 1, pdx = (m >> 3) & 1, c = m & 7;
+#pragma unroll 1
+    for (int tap = 0; tap < 4; ++tap) {
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(tap * 32), v);
+      tmem_ld_wait();
+      const int ky = 2 * (tap >> 1) + pdy, kx = 2 * (tap & 1) + pdx;
+      float* o = dw + ((ky * 4 + kx) * 8 + c) * 32;
+      if (lane < 16 && m < 32) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + j), "f"(__uint_as_float(v[j])),
+                       "f"(__uint_as_float(v[j + 1])), "f"(__uint_as_float(v[j + 2])), "f"(__uint_as_float(v[j + 3])) : "memory");
+      }
+    }
+  }
+  __syncwarp();
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 2) {
+    fence_after_sync();
+    tmem_dealloc<128>(tmem_base);
   }
 }
 
@@ -1509,6 +1836,55 @@ extern "C" int unreal_pc_deconv_loss_c8(const void* h_bf16, const void* w_dtaps_
                                         const float* target, const float* mask, int a, float lam, int s, double* loss,
                                         void* dy8_bf16, float* db8, void* stream) {
   return pc_deconv_loss_impl(h_bf16, w_dtaps_bf16, bias8, act, target, mask, a, lam, s, loss, dy8_bf16, db8, 1, stream);
+}
+
+extern "C" int unreal_pc_deconv_loss_planes(const void* h_bf16, const void* w_dtaps_bf16, const float* bias8, const int32_t* act,
+                                            const float* target, const float* mask, int a, float lam, int s, double* loss,
+                                            void* dy_planes_bf16, float* db8, void* stream) {
+  return pc_deconv_loss_impl(h_bf16, w_dtaps_bf16, bias8, act, target, mask, a, lam, s, loss, dy_planes_bf16, db8, 2, stream);
+}
+
+extern "C" int unreal_pc_planes_conv(const void* dy_planes_bf16, const void* w_planes_bf16, const float* scale,
+                                     const void* mask_y_bf16, void* out_bf16, float* db, int s, void* stream) {
+  UNREAL_REQUIRE(dy_planes_bf16 && w_planes_bf16 && mask_y_bf16 && out_bf16 && s > 0, "unreal_pc_planes_conv: null buffer or s <= 0");
+  UNREAL_REQUIRE(aligned16(dy_planes_bf16) && aligned16(w_planes_bf16) && aligned16(mask_y_bf16) && aligned16(out_bf16),
+                 "unreal_pc_planes_conv: 16-byte alignment");
+  static bool configured = false;
+  if (!configured) {
+    UNREAL_CUDA(cudaFuncSetAttribute(pc_planes_conv_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPpSmem));
+    configured = true;
+  }
+  const int sms = sm_count();
+  if (sms <= 0) return UNREAL_ECUDA;
+  pc_planes_conv_tcgen05_kernel<<<s < 2 * sms ? s : 2 * sms, kConvThreads, kPpSmem, as_stream(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(dy_planes_bf16), reinterpret_cast<const __nv_bfloat16*>(w_planes_bf16), scale,
+      reinterpret_cast<const __nv_bfloat16*>(mask_y_bf16), reinterpret_cast<__nv_bfloat16*>(out_bf16), db, s);
+  UNREAL_LAUNCH_CHECK("pc_planes_conv_tcgen05_kernel");
+  return UNREAL_OK;
+}
+
+extern "C" int unreal_pc_planes_wgrad(const void* dy_planes_bf16, const void* hp_bf16, float* dw8, int s, void* stream) {
+  UNREAL_REQUIRE(dy_planes_bf16 && hp_bf16 && dw8 && s > 0, "unreal_pc_planes_wgrad: null buffer or s <= 0");
+  UNREAL_REQUIRE(aligned16(dy_planes_bf16) && aligned16(hp_bf16) && aligned16(dw8), "unreal_pc_planes_wgrad: 16-byte alignment");
+  CUtensorMap th;
+  {
+    const uint64_t dims[4] = {32, 9, 9, (uint64_t)s};           // hp [S][9 oy][9 ox][32 o]
+    const uint64_t strides[3] = {64, 64 * 9, 64 * 81};
+    const uint32_t box[4] = {32, 10, 10, 1};                   // one zero column / row: the gradient planes' 10-wide grid
+    int rc = make_tma_nd_bf16(&th, hp_bf16, 4, dims, strides, box, 64);
+    if (rc != UNREAL_OK) return rc;
+  }
+  static bool configured = false;
+  if (!configured) {
+    UNREAL_CUDA(cudaFuncSetAttribute(pc_planes_wgrad_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPwSmem));
+    configured = true;
+  }
+  const int sms = sm_count();
+  if (sms <= 0) return UNREAL_ECUDA;
+  pc_planes_wgrad_tcgen05_kernel<<<s < 2 * sms ? s : 2 * sms, 128, kPwSmem, as_stream(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(dy_planes_bf16), th, dw8, s);
+  UNREAL_LAUNCH_CHECK("pc_planes_wgrad_tcgen05_kernel");
+  return UNREAL_OK;
 }
 
 extern "C" int unreal_pc_deconv_qmax(const void* h_bf16, const void* w_dtaps_bf16, const float* bias8, int a, int s, float* qmax,

@@ -812,18 +812,60 @@ def pc_deconv_qmax(h16, w_dtaps, bias8, num_actions, out=None):
   return out
 
 
-def pc_deconv_loss(h16, w_dtaps, bias8, act, target, mask, num_actions, lam, c8=False):
+def pc_deconv_loss(h16, w_dtaps, bias8, act, target, mask, num_actions, lam, c8=False, planes=False):
   """Pixel-control head + loss in one kernel: h16 bf16 [S,9,9,32] (any view of S*2592) -> (loss f64 [1],
   dy16 bf16 [S,400,16] = d loss / d pre-ReLU output, un-scaled by the upstream gradient, db8 [8]).  `c8`: the gradient
-  without its 8 zero padding channels, [S,400,8]."""
+  without its 8 zero padding channels, [S,400,8]; `planes`: as four parity planes of the 10 x 10 space-to-depth grid,
+  [S,4,100,8] (pc_planes_conv / pc_planes_wgrad)."""
   s = h16.numel() // 2592
   loss = torch.zeros(1, dtype=torch.float64, device=h16.device)
-  dy16 = torch.empty(s, 400, 8 if c8 else 16, dtype=torch.bfloat16, device=h16.device)
+  if planes:
+    dy16 = torch.empty(s, 4, 100, 8, dtype=torch.bfloat16, device=h16.device)
+  else:
+    dy16 = torch.empty(s, 400, 8 if c8 else 16, dtype=torch.bfloat16, device=h16.device)
   db8 = torch.zeros(8, dtype=torch.float32, device=h16.device)
-  call("unreal_pc_deconv_loss_c8" if c8 else "unreal_pc_deconv_loss", ptr(h16, torch.bfloat16, "h16"), ptr(w_dtaps, torch.bfloat16, "w_dtaps"),
+  call("unreal_pc_deconv_loss_planes" if planes else "unreal_pc_deconv_loss_c8" if c8 else "unreal_pc_deconv_loss", ptr(h16, torch.bfloat16, "h16"), ptr(w_dtaps, torch.bfloat16, "w_dtaps"),
        ptr(bias8, torch.float32, "bias8"), ptr(act, torch.int32, "act"), ptr(target, torch.float32, "target"),
        ptr(mask, torch.float32, "mask"), int(num_actions), float(lam), s, ptr(loss), ptr(dy16), ptr(db8), stream_ptr())
   return loss, dy16, db8
+
+
+def pc_w_planes(w8):
+  """The merged deconv filter [4,4,8,32] bf16 (HWIO) -> the resident B tiles of pc_planes_conv: [4 taps (by,bx)][2 dy][2 dx]
+  [32 o][8 c] = W8[2by+dy, 2bx+dx, c, o]."""
+  return w8.reshape(2, 2, 2, 2, 8, 32).permute(0, 2, 1, 3, 5, 4).reshape(4, 2, 2, 32, 8).contiguous()
+
+
+def pc_planes_from_dense(dy8):
+  """[S,20,20,8] -> the plane-major layout [S,4,100,8] (tests / tools; the agent's gradient is written that way)."""
+  s = dy8.shape[0]
+  return dy8.reshape(s, 10, 2, 10, 2, 8).permute(0, 2, 4, 1, 3, 5).reshape(s, 4, 100, 8).contiguous()
+
+
+def pc_planes_conv(dyp, w_planes, mask_y, scale=None, out=None, want_db=True):
+  """The pixel-control head's backward convolution on the plane-major gradient: dyp bf16 [S,4,100,8] -> (d pc_fc1 output
+  bf16 [S,9,9,32], masked by mask_y > 0 and scaled by the device scalar `scale`; db f32 [2592])."""
+  s = dyp.shape[0]
+  if tuple(dyp.shape[1:]) != (4, 100, 8) or mask_y.numel() != s * 2592 or w_planes.numel() != 4096:
+    raise ValueError("pc_planes_conv: dyp [S,4,100,8], mask_y S*2592 elements, w_planes = pc_w_planes(W8)")
+  if out is None:
+    out = torch.empty(s, 9, 9, 32, dtype=torch.bfloat16, device=dyp.device)
+  db = torch.zeros(2592, dtype=torch.float32, device=dyp.device) if want_db else None
+  call("unreal_pc_planes_conv", ptr(dyp, torch.bfloat16, "dyp"), ptr(w_planes, torch.bfloat16, "w_planes"),
+       ptr(scale, torch.float32, "scale"), ptr(mask_y, torch.bfloat16, "mask_y"), ptr(out, torch.bfloat16, "out"),
+       ptr(db, torch.float32, "db"), s, stream_ptr())
+  return out, db
+
+
+def pc_planes_wgrad(dyp, hp):
+  """dyp bf16 [S,4,100,8], hp bf16 (S*2592 elements, pc_fc1's output) -> the merged deconv filter's gradient [4,4,8,32] f32."""
+  s = dyp.shape[0]
+  if tuple(dyp.shape[1:]) != (4, 100, 8) or hp.numel() != s * 2592:
+    raise ValueError("pc_planes_wgrad: dyp [S,4,100,8], hp S*2592 elements")
+  acc = torch.zeros(4, 4, 8, 32, dtype=torch.float32, device=dyp.device)
+  call("unreal_pc_planes_wgrad", ptr(dyp, torch.bfloat16, "dyp"), ptr(hp, torch.bfloat16, "hp"), ptr(acc, torch.float32), s,
+       stream_ptr())
+  return acc
 
 
 def a3c_head(h, wp, bp, wv, bv, act=None, adv=None, ret=None, mask=None, entropy_beta=0.0, value_coef=0.25,

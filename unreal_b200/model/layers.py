@@ -373,18 +373,22 @@ class PcFusedHeadLossFn(torch.autograd.Function):
 
 class PcTowerFusedFn(torch.autograd.Function):
   """pc_fc1 (model.py:424) + PcFusedHeadLossFn as ONE autograd node, so that pc_fc1's ReLU gradient and bias gradient come
-  out of the backward convolution's epilogue (`unreal_conv2_fwd_linear_masked`) instead of a `unreal_relu_grad` pass over
-  the dense [S,2592] gradient (read 2 x 849 MB + write 849 MB per update at 8192 envs x 20)."""
+  out of the backward convolution's epilogue instead of a `unreal_relu_grad` pass over the dense [S,2592] gradient (read
+  2 x 849 MB + write 849 MB per update at 8192 envs x 20).  `lin_taps` selects the layout the loss gradient travels in
+  between the fused deconv + loss kernel and the two backward kernels:
+    [32, 256]      conv2's geometry [S,400,16], channels 8..15 zero (`unreal_conv2_fwd_linear_masked`, `unreal_conv2_wgrad`);
+    [32, 128]      the 8 real channels [S,400,8] (the same kernels' 8-channel builds);
+    [4,2,2,32,8]   (`K.pc_w_planes`) four parity planes [S,4,100,8]: one bulk copy per sample (`unreal_pc_planes_conv`,
+                   `unreal_pc_planes_wgrad`) -- what the agent runs."""
 
   @staticmethod
   def forward(ctx, h, w16, w32, b32, taps, b8, lin_taps, wv32, bv32, wa32, ba32, act, target, mask, num_actions, lam):
     ctx.x_f32 = h.dtype == torch.float32
     x16 = h.to(torch.bfloat16) if ctx.x_f32 else h
     hp = K.gemm_bf16(x16, w16, b_mn_major=True, bias=b32, relu=True, out_dtype=torch.bfloat16)
-    # `lin_taps` [32, 128]: the 8-channel build -- the loss gradient travels as [S,400,8] (1.05 GB per update at 8192 envs
-    # instead of 2.1 GB with conv2's 16 channels, half of them zero padding; it is written once and read twice)
-    ctx.c = lin_taps.shape[1] // 16
-    loss, dy16, db8 = K.pc_deconv_loss(hp, taps, b8, act, target, mask, num_actions, lam, c8=ctx.c == 8)
+    ctx.planes = lin_taps.dim() == 5
+    ctx.c = 8 if ctx.planes else lin_taps.shape[1] // 16
+    loss, dy16, db8 = K.pc_deconv_loss(hp, taps, b8, act, target, mask, num_actions, lam, c8=ctx.c == 8, planes=ctx.planes)
     ctx.num_actions = num_actions
     ctx.lin_taps = lin_taps
     ctx.save_for_backward(x16, w16, hp, dy16, db8)
@@ -396,10 +400,15 @@ class PcTowerFusedFn(torch.autograd.Function):
     a = ctx.num_actions
     s = hp.shape[0]
     go32 = go.to(torch.float32).reshape(1).contiguous()
-    dy16 = dy16.view(s, 20, 20, ctx.c)
-    dhp, db = K.conv2_fwd_linear(dy16, ctx.lin_taps, scale=go32, mask_y=hp)        # masked by hp > 0, + pc_fc1's bias gradient
+    # d(pc_fc1 output), masked by hp > 0, + pc_fc1's bias gradient; the deconv filters' gradient ([4,4,16 (8),32])
+    if ctx.planes:
+      dhp, db = K.pc_planes_conv(dy16, ctx.lin_taps, hp, scale=go32)
+      dw16 = K.pc_planes_wgrad(dy16, hp) * go32
+    else:
+      dy16 = dy16.view(s, 20, 20, ctx.c)
+      dhp, db = K.conv2_fwd_linear(dy16, ctx.lin_taps, scale=go32, mask_y=hp)
+      dw16 = K.conv2_wgrad(dy16, hp.view(s * 81, 32)) * go32
     dhp = dhp.view(s, 2592)
-    dw16 = K.conv2_wgrad(dy16, hp.view(s * 81, 32)) * go32                          # [4,4,16 (8),32]: channels 8..15 are padding
     db8 = db8 * go32
     dx = None
     if ctx.needs_input_grad[0]:

@@ -103,8 +103,9 @@ class UnrealModel(object):
     # pc_fc1's ReLU / bias gradient in the epilogue of the pixel-control head's backward convolution (PcTowerFusedFn; False:
     # a unreal_relu_grad pass over the dense [S,2592] gradient between the two autograd nodes)
     self.fused_pc_relu = True
-    # ... and the loss gradient between the fused deconv + loss kernel and the two backward kernels in 8 channels instead of 16
-    self.pc_grad_c8 = True
+    # ... and the layout of the loss gradient between the fused deconv + loss kernel and the two backward kernels: "planes"
+    # (four parity planes of 8 channels, one bulk copy per sample), "c8" ([S,400,8]) or "c16" (conv2's geometry, zero padded)
+    self.pc_grad_layout = "planes"
     self._cells49 = torch.tensor([[x, y] for y in range(7) for x in range(7)], dtype=torch.int32, device=self._device)
     self._fc_tab_act = torch.zeros(49, 256, dtype=torch.bfloat16, device=self._device)
     self._act_xh = {}         # acting-step [x, h] GEMM operands by batch size (persistent: padding columns stay zero)
@@ -193,12 +194,14 @@ class UnrealModel(object):
       w16 = torch.zeros(4, 4, 16, 32, dtype=torch.bfloat16, device=self._device)
       w16[:, :, :8] = w8                  # the same filter in conv2's geometry: the deconv's input gradient is conv2's forward
       l8 = K.conv_taps(w16, 2)
-      l88 = K.conv_taps(w8, 2)            # ... and without the 8 padding channels [32, 128] (PcTowerFusedFn)
+      l88 = K.conv_taps(w8, 2)            # ... without the 8 padding channels [32, 128], and as the plane kernels' tap tiles
+      lpl = K.pc_w_planes(w8)
       if getattr(self, "pc_w8", None) is None:
         self.pc_w8, self.pc_b8, self.pc_taps, self.pc_lin_taps, self.pc_lin_taps8 = w8.view(128, 32), b8, t8, l8, l88
+        self.pc_w_planes = lpl
       else:
         self.pc_w8.copy_(w8.view(128, 32)); self.pc_b8.copy_(b8); self.pc_taps.copy_(t8); self.pc_lin_taps.copy_(l8)
-        self.pc_lin_taps8.copy_(l88)
+        self.pc_lin_taps8.copy_(l88); self.pc_w_planes.copy_(lpl)
 
   def get_vars(self):
     """The variables in creation order (views of the flat buffer), like model.py:729-730."""
@@ -480,7 +483,8 @@ class UnrealModel(object):
       if self.fused_conv and self.fused_encoder and self.fused_pc_loss and self.fused_pc_relu:
         # pc_fc1 + deconv + loss as one node: the ReLU / bias gradient of pc_fc1 leaves the backward convolution's epilogue
         parts["pc"] = PcTowerFusedFn.apply(h.reshape(L * n, 256), self.v16["W_pc_fc1"], p32["W_pc_fc1"], p32["b_pc_fc1"],
-                                           self.pc_taps, self.pc_b8, self.pc_lin_taps8 if self.pc_grad_c8 else self.pc_lin_taps,
+                                           self.pc_taps, self.pc_b8,
+                                           {"planes": self.pc_w_planes, "c8": self.pc_lin_taps8}.get(self.pc_grad_layout, self.pc_lin_taps),
                                            p32["W_pc_deconv_v"], p32["b_pc_deconv_v"], p32["W_pc_deconv_a"], p32["b_pc_deconv_a"], act, tgt, msk,
                                            self._action_size, self._pixel_change_lambda)
       elif self.fused_conv and self.fused_encoder:
