@@ -101,6 +101,11 @@ int unreal_maze_render(const int32_t* pos, void* obs, int obs_dtype, int m, void
 
 /* closed-form pixel change between two cells: pos0, pos1 [M,2] -> pc [M,20,20]. */
 int unreal_maze_pixel_change(const int32_t* pos0, const int32_t* pos1, float* pc, int m, void* stream);
+/* Trainer._process_pc on replayed MAZE frames (trainer.py:339-380) in one pass: unreal_maze_pixel_change + unreal_pc_targets
+ * without the [t,n,20,20] maps between them.  pos0 / pos1 int32 [t,n,2] time-major (the frame's cell and the next frame's),
+ * len int32 [n] nullable (valid steps per env; later rows of tgt are zero), boot f32 [n,20,20], tgt f32 [t,n,20,20]. */
+int unreal_maze_pc_targets(const int32_t* pos0, const int32_t* pos1, const int32_t* len, const float* boot, float gamma_pc,
+                           float* tgt, int t, int n, void* stream);
 
 /* ---- K2: Environment._calc_pixel_change + _subsample (environment.py:88-99) ------------
  * literal |cur-prev| over the 2-pixel-cropped frame, mean over channels, 4x4 mean.

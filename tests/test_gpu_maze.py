@@ -171,6 +171,20 @@ def test_render_and_pc_pairs(K):
     assert np.array_equal(got[k], lit)
 
 
+def test_pixel_change_of_every_pair_of_free_cells_is_bit_exact(K):
+  """Every value the closed form can take (k / 48 for the overlap sums k of any two cells, adjacent or not), computed on the
+  device without an IEEE division (one FMA-corrected Newton step), against the oracle's float32 division: bit for bit."""
+  dev = "cuda:0"
+  cells = [(x, y) for y in range(7) for x in range(7) if not O.WALLS[y, x]]
+  a = torch.tensor([c for c in cells for _ in cells], dtype=torch.int32, device=dev)
+  b = torch.tensor([c for _ in cells for c in cells], dtype=torch.int32, device=dev)
+  got = K.maze_pixel_change(a, b).cpu().numpy()
+  an, bn = a.cpu().numpy(), b.cpu().numpy()
+  for k in range(len(an)):
+    want = O.maze_pixel_change_closed_form(int(an[k, 0]), int(an[k, 1]), int(bn[k, 0]), int(bn[k, 1]))
+    assert np.array_equal(got[k], want), (an[k], bn[k])
+
+
 def test_bad_arguments_fail_loudly(K):
   from unreal_b200 import _lib
   st = K.MazeState(4, "cuda:0")

@@ -93,6 +93,35 @@ def test_pc_targets(K, T, N, use_len, use_term):
     assert (got[L:, n] == 0).all()
 
 
+@pytest.mark.parametrize("T,N", [(20, 512), (20, 1), (3, 37), (21, 300), (1, 5)])
+@pytest.mark.parametrize("use_len", [False, True])
+def test_maze_pc_targets_equals_pixel_change_then_targets(K, T, N, use_len):
+  """unreal_maze_pc_targets (the replayed frames' pixel-change maps evaluated in registers inside the Q-target scan,
+  trainer.py:339-380) against the two kernels it replaces -- bit for bit -- and against the oracle's closed-form maps +
+  float64 scan; stationary steps (no pixel change), lengths from 0 to T."""
+  rs = np.random.RandomState(7 * T + N)
+  dev = "cuda:0"
+  p0 = rs.randint(0, 7, size=(T, N, 2)).astype(np.int32)
+  step = rs.randint(-1, 2, size=(T, N, 2)).astype(np.int32)
+  step[rs.rand(T, N) < 0.5, 1] = 0                               # mostly axis moves, some stationary, a few diagonal
+  p1 = np.clip(p0 + step, 0, 6).astype(np.int32)
+  boot = rs.rand(N, 20, 20).astype(np.float32)
+  lens = rs.randint(0, T + 1, size=N).astype(np.int32) if use_len else None
+  t0, t1, tb = (torch.from_numpy(a).to(dev) for a in (p0, p1, boot))
+  tl = None if lens is None else torch.from_numpy(lens).to(dev)
+  got = K.maze_pc_targets(t0, t1, tl, tb, 0.9)
+  pc = K.maze_pixel_change(t0.view(-1, 2), t1.view(-1, 2)).view(T, N, 20, 20)
+  assert torch.equal(got, K.pc_targets(pc, None, tl, tb, 0.9))
+  got = got.cpu().numpy()
+  for n in range(0, N, max(1, N // 25)):
+    L = int(lens[n]) if use_len else T
+    maps = np.stack([O.maze_pixel_change_closed_form(int(p0[t, n, 0]), int(p0[t, n, 1]), int(p1[t, n, 0]), int(p1[t, n, 1]))
+                     for t in range(L)]) if L else np.zeros((0, 20, 20))
+    if L:
+      _close(got[:L, n], O.pc_targets(maps.astype(np.float64), boot[n].astype(np.float64), 0.9))
+    assert (got[L:, n] == 0).all()
+
+
 @pytest.mark.parametrize("L", [21, 20, 5, 32, 1])
 def test_sequence_returns_warp_scan(K, L):
   rs = np.random.RandomState(L)
@@ -116,3 +145,5 @@ def test_empty_inputs(K):
   assert R.shape == (0, 5)
   out = K.pc_targets(torch.empty(4, 0, 20, 20, device=dev), None, None, torch.empty(0, 20, 20, device=dev), 0.9)
   assert out.shape == (4, 0, 20, 20)
+  zi = torch.empty(4, 0, 2, dtype=torch.int32, device=dev)
+  assert K.maze_pc_targets(zi, zi, None, torch.empty(0, 20, 20, device=dev), 0.9).shape == (4, 0, 20, 20)

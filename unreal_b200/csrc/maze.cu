@@ -95,17 +95,25 @@ __device__ __forceinline__ EnvInfo env_logic(const StepArgs& a, int e) {
 
 // 100 threads write the 20x20 map of one env as float4: k/48 with
 // k = ov(i,y0)*ov(j,x0) + ov(i,y1)*ov(j,x1), 0 when the agent did not move.
-__device__ __forceinline__ void write_pc(float* pc, const EnvInfo& f, int q) {
+__device__ __forceinline__ float4 pc_value4(int x0, int y0, int x1, int y1, int q) {
   int i = q / 5, j0 = (q - i * 5) * 4;
-  bool moved = (f.x0 != f.x1) || (f.y0 != f.y1);
-  int wy0 = pc_overlap(i, f.y0), wy1 = pc_overlap(i, f.y1);
+  bool moved = (x0 != x1) || (y0 != y1);
+  int wy0 = pc_overlap(i, y0), wy1 = pc_overlap(i, y1);
+  if (!moved || (wy0 | wy1) == 0) return make_float4(0.f, 0.f, 0.f, 0.f);    // most rows of the map touch neither square
   float v[4];
 #pragma unroll
   for (int u = 0; u < 4; ++u) {
-    int k = moved ? wy0 * pc_overlap(j0 + u, f.x0) + wy1 * pc_overlap(j0 + u, f.x1) : 0;
-    v[u] = (float)k / 48.0f;  // IEEE division: equals float32 of the reference's float64 means
+    const float k = (float)(wy0 * pc_overlap(j0 + u, x0) + wy1 * pc_overlap(j0 + u, x1));      // an integer <= 32
+    // k / 48 correctly rounded (= float32 of the reference's float64 means) without the IEEE-division sequence: one
+    // Newton correction of k * RN(1/48) with exact FMA residuals; equal to k / 48.0f for every integer k < 200
+    // (checked exhaustively; tests/test_gpu_maze.py compares every cell pair with the literal reference computation)
+    const float q = k * 0x1.555556p-6f;
+    v[u] = __fmaf_rn(__fmaf_rn(-q, 48.0f, k), 0x1.555556p-6f, q);
   }
-  reinterpret_cast<float4*>(pc)[q] = make_float4(v[0], v[1], v[2], v[3]);
+  return make_float4(v[0], v[1], v[2], v[3]);
+}
+__device__ __forceinline__ void write_pc(float* pc, const EnvInfo& f, int q) {
+  reinterpret_cast<float4*>(pc)[q] = pc_value4(f.x0, f.y0, f.x1, f.y1, q);
 }
 
 template <typename T> struct One;
@@ -587,6 +595,33 @@ __global__ void __launch_bounds__(128) maze_pc_pairs_kernel(const int32_t* __res
   write_pc(pc + (size_t)e * kPcElems, f, q);
 }
 
+// Trainer._process_pc (trainer.py:339-380) on replayed maze cells in ONE pass: pc_R[t] = pixel_change(cell_t, cell_t+1) +
+// gamma_pc * pc_R[t+1] with the map's closed form evaluated in registers -- the [L,N,20,20] pixel-change maps
+// (maze_pc_pairs_kernel: 262 MB written, then read back by pc_targets_kernel at 8192 envs) never exist.  One thread per
+// (env, float4 of the map); the same arithmetic, in the same order, as the two kernels it replaces.
+__global__ void __launch_bounds__(128) maze_pc_targets_kernel(const int2* __restrict__ p0, const int2* __restrict__ p1,
+                                                              const int32_t* __restrict__ len, const float4* __restrict__ boot,
+                                                              float g, float4* __restrict__ tgt, int T, int N) {
+  const size_t per_t = (size_t)N * (kPcElems / 4);
+  const size_t idx = (size_t)blockIdx.x * 128 + threadIdx.x;
+  if (idx >= per_t) return;
+  const int n = (int)(idx / (kPcElems / 4)), q = (int)(idx - (size_t)n * (kPcElems / 4));
+  const int n_t = len ? max(0, min(len[n], T)) : T;
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 R = boot[idx];
+  for (int t = T - 1; t >= n_t; --t) __stcs(tgt + (size_t)t * per_t + idx, zero);
+#pragma unroll 4
+  for (int t = n_t - 1; t >= 0; --t) {
+    const int2 a = __ldg(p0 + (size_t)t * N + n), b = __ldg(p1 + (size_t)t * N + n);
+    const float4 pc = pc_value4(a.x, a.y, b.x, b.y, q);
+    R.x = __fadd_rn(pc.x, __fmul_rn(g, R.x));   // pc_R = pixel_change + gamma_pc * pc_R   (:361)
+    R.y = __fadd_rn(pc.y, __fmul_rn(g, R.y));
+    R.z = __fadd_rn(pc.z, __fmul_rn(g, R.z));
+    R.w = __fadd_rn(pc.w, __fmul_rn(g, R.w));
+    __stcs(tgt + (size_t)t * per_t + idx, R);
+  }
+}
+
 __global__ void maze_reset_kernel(int32_t* pos, int32_t* last_action, float* last_reward, const uint8_t* mask,
                                   int n) {
   int e = blockIdx.x * blockDim.x + threadIdx.x;
@@ -762,6 +797,21 @@ extern "C" int unreal_maze_pixel_change(const int32_t* pos0, const int32_t* pos1
   long long threads = (long long)m * (kPcElems / 4);
   maze_pc_pairs_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, as_stream(stream)>>>(pos0, pos1, pc, m);
   UNREAL_LAUNCH_CHECK("maze_pc_pairs_kernel");
+  return UNREAL_OK;
+}
+
+extern "C" int unreal_maze_pc_targets(const int32_t* pos0, const int32_t* pos1, const int32_t* len, const float* boot,
+                                      float gamma_pc, float* tgt, int t, int n, void* stream) {
+  UNREAL_REQUIRE(t >= 0 && n >= 0, "unreal_maze_pc_targets: negative size");
+  if (t == 0 || n == 0) return UNREAL_OK;
+  UNREAL_REQUIRE(pos0 && pos1 && boot && tgt, "unreal_maze_pc_targets: pos0, pos1, boot and tgt must be non-null");
+  UNREAL_REQUIRE(aligned16(boot) && aligned16(tgt) && (reinterpret_cast<uintptr_t>(pos0) & 7u) == 0 &&
+                 (reinterpret_cast<uintptr_t>(pos1) & 7u) == 0, "unreal_maze_pc_targets: alignment (16 bytes; cells 8)");
+  const long long cols = (long long)n * (kPcElems / 4);
+  maze_pc_targets_kernel<<<(unsigned)((cols + 127) / 128), 128, 0, as_stream(stream)>>>(
+      reinterpret_cast<const int2*>(pos0), reinterpret_cast<const int2*>(pos1), len, reinterpret_cast<const float4*>(boot),
+      gamma_pc, reinterpret_cast<float4*>(tgt), t, n);
+  UNREAL_LAUNCH_CHECK("maze_pc_targets_kernel");
   return UNREAL_OK;
 }
 

@@ -132,6 +132,17 @@ def maze_pixel_change(pos0, pos1, out=None):
   return out
 
 
+def maze_pc_targets(pos0, pos1, length, boot, gamma_pc, out=None):
+  """pos0, pos1 int32 [T,N,2] (time-major cells of the replayed frames and their successors), length int32 [N] or None,
+  boot f32 [N,20,20] -> pixel-control targets f32 [T,N,20,20] = maze_pixel_change + pc_targets in one pass."""
+  t, n = pos0.shape[0], pos0.shape[1]
+  if out is None:
+    out = torch.empty(t, n, PC, PC, dtype=torch.float32, device=pos0.device)
+  call("unreal_maze_pc_targets", ptr(pos0, torch.int32), ptr(pos1, torch.int32), ptr(length, torch.int32),
+       ptr(boot, torch.float32), float(gamma_pc), ptr(out, torch.float32), t, n, stream_ptr())
+  return out
+
+
 # ---------------------------------------------------------------------------- pixel change (generic)
 def pixel_change(cur, prev, out=None):
   """cur, prev [M,H,W,C] float32 or uint8 -> [M,(H-4)//4,(W-4)//4] float32."""

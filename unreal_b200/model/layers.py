@@ -38,6 +38,29 @@ def _wgrad(x16, dy16):
   return K.gemm_bf16(x16, dy16, a_mn_major=True, b_mn_major=True, split_k=split_k_for(kin, nout, s))
 
 
+class FlatViewsFn(torch.autograd.Function):
+  """The variables as views of the flat parameter buffer, as ONE autograd node: the backward pass zero-fills one flat
+  gradient and copies each variable's gradient into its slice.  Plain slicing makes autograd build a full-size zero
+  tensor per variable and add them up one by one (20 fills + 19 adds over 7.6 MB each per update)."""
+
+  @staticmethod
+  def forward(ctx, flat, offsets):
+    ctx.offsets = offsets
+    ctx.numel = flat.numel()
+    return tuple(flat[o:o + n].view(shape) for _, shape, o, n in offsets)
+
+  @staticmethod
+  def backward(ctx, *grads):
+    g = None
+    for (_, _, o, n), gi in zip(ctx.offsets, grads):
+      if gi is None:
+        continue
+      if g is None:
+        g = torch.zeros(ctx.numel, dtype=gi.dtype, device=gi.device)
+      g[o:o + n].copy_(gi.reshape(-1))
+    return g, None
+
+
 class LinearFn(torch.autograd.Function):
   """y = act(x @ W + b): tf.matmul layers (model.py:337-340 fc1, :424 pc_fc1)."""
 
@@ -194,7 +217,11 @@ class LstmFn(torch.autograd.Function):
       xh[:, :, :256].copy_(fc16)
     xh[:, :, 256:lstm_in].copy_(lar)
     if kx > lstm_in:
-      xh[:, :, lstm_in:kx].zero_()
+      # padding columns: zero, except a ONE in the last of them -- its row of the kernel shadow is zero, so the steps are
+      # unchanged, and its row of the wgrad GEMM's result is the column sum of the gate gradients = the bias gradient
+      # (instead of a separate pass over the [T*N, 1024] gradient)
+      pad = (torch.arange(lstm_in, kx, device=dev) == kx - 1).to(torch.bfloat16)      # device ops only: graph-capture safe
+      xh[:, :, lstm_in:kx].copy_(pad)
     xh[0, :, kx:].copy_(h0)
     fused_step = bool(fused_step) and gates_dtype == torch.bfloat16
     # fused steps: c of every step and the gate activations are touched by the step kernels only and live in their tiled
@@ -249,7 +276,10 @@ class LstmFn(torch.autograd.Function):
     dg2 = dgates.view(t * n, 1024)
     dwcat = _wgrad(xh.view(t * n, kc), dg2)              # one wgrad over [x, h]: rows of the x part, padding, h part
     dw = torch.cat((dwcat[:lstm_in], dwcat[kx:]), dim=0)
-    _, db = K.relu_grad(dg2, None, want_out=False)
+    if kx > lstm_in:
+      db = dwcat[kx - 1].clone()                         # the ones column of the operand (forward)
+    else:
+      _, db = K.relu_grad(dg2, None, want_out=False)
     # only the 256 fc1 columns carry a gradient (last_action_reward is an input)
     dfc = K.gemm_bf16(dg2, wcat16[:256], out_dtype=torch.bfloat16)
     dfc = dfc.view(t, n, 256) if pos is None else K.cell_segment_sum(dfc, pos)      # table mode: per-cell sums, fp32 [49,256]

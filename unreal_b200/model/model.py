@@ -26,7 +26,7 @@ import torch
 
 from .. import _lib
 from .. import kernels as K
-from .layers import (A3CHeadLossFn, CellGatherFn, ConvFn, Deconv8Fn, EncoderFn, LinearFn, LstmFn, PcFusedHeadLossFn, PcHeadLossFn, PcLossFn, PcTowerFusedFn, RpCellLossFn,
+from .layers import (A3CHeadLossFn, CellGatherFn, FlatViewsFn, ConvFn, Deconv8Fn, EncoderFn, LinearFn, LstmFn, PcFusedHeadLossFn, PcHeadLossFn, PcLossFn, PcTowerFusedFn, RpCellLossFn,
                      RpHeadLossFn, split_k_for)
 
 
@@ -141,6 +141,8 @@ class UnrealModel(object):
     self.refresh_shadow()
 
   def _views(self, flat):
+    if torch.is_grad_enabled() and flat.requires_grad:      # one autograd node for all variables (layers.FlatViewsFn)
+      return OrderedDict(zip((name for name, _, _, _ in self._offsets), FlatViewsFn.apply(flat, self._offsets)))
     return OrderedDict((name, flat[o:o + n].view(shape)) for name, shape, o, n in self._offsets)
 
   def refresh_shadow(self):

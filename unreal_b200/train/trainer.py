@@ -315,8 +315,8 @@ class Trainer(object):
     pc_boot = self.local_network.run_pc_q_max(sess, boot_state, boot_lar).contiguous()
     pos0 = f["pos0"][:, :L - 1].transpose(0, 1).contiguous()      # [L-1, N, 2] time-major
     pos1 = f["pos1"][:, :L - 1].transpose(0, 1).contiguous()
-    pc = K.maze_pixel_change(pos0.view(-1, 2), pos1.view(-1, 2)).view(L - 1, n, 20, 20)
-    pc_R = K.pc_targets(pc, None, n_batch, pc_boot, self.gamma_pc)
+    # maze_pixel_change + pc_targets in one pass: the [L-1,N,20,20] maps themselves are never written
+    pc_R = K.maze_pc_targets(pos0, pos1, n_batch, pc_boot, self.gamma_pc)
     a = torch.nn.functional.one_hot(f["action"][:, :L - 1].to(torch.int64), self.action_size).to(torch.float32)
     return dict(pos=f["pos0"][:, :L - 1], last_action_reward=lar[:, :L - 1], a=a, R=pc_R.transpose(0, 1),
                 length=n_batch, start=start)
