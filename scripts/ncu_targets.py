@@ -1,6 +1,6 @@
 """Small single-kernel workloads for `ncu --set full` captures (one GPU, a handful of launches).
 
-    python scripts/ncu_targets.py k2u8 | k2f32 | k1u8w | k1f32w | k1u8 | k4 | rp | conv2bwd | gemm2sm | lstm [envs] | lstmfused [envs] | pcfc1
+    python scripts/ncu_targets.py k2u8 | k2f32 | k1u8w | k1f32w | k1u8 | k4 | rp | conv2bwd | gemm2sm | lstm [envs] | lstmfused [envs] | pcfc1 | pcplanes
 
 Each target runs its kernel three times on the benchmark's shapes; select the kernel with `-k regex:...`.
 """
@@ -93,6 +93,21 @@ elif which == "pcfc1":
   out = torch.empty(S, 2592, device=dev, dtype=torch.bfloat16)
   for _ in range(3):
     K.gemm_bf16(x, w, out=out, b_mn_major=True, bias=b, relu=True)
+elif which == "pcplanes":
+  # the pixel-control tower behind pc_fc1 at half the agent's batch: fused deconv + loss (plane-major gradient out), the backward
+  # convolution with pc_fc1's ReLU / bias gradient, the deconv filters' gradient -- one launch each
+  from unreal_b200.model.model import UnrealModel
+  S, A = 81920, 4
+  m = UnrealModel(A, 0, -1, True, True, True, True, 0.05, 0.001, dev, {'segnet_mode': 0}, (84, 84), True, 0, 0.0, 0.0, num_envs=4, seed=0)
+  hp = torch.relu(torch.randn(S, 2592, device=dev, generator=g)).to(torch.bfloat16)
+  act = torch.randint(0, A, (S,), device=dev, generator=g, dtype=torch.int32)
+  tgt = torch.rand(S, 400, device=dev, generator=g)
+  msk = torch.ones(S, device=dev)
+  sc = torch.tensor([0.5], device=dev)
+  for _ in range(2):
+    loss, dyp, db8 = K.pc_deconv_loss(hp, m.pc_taps, m.pc_b8, act, tgt, msk, A, 0.05, planes=True)
+    K.pc_planes_conv(dyp, m.pc_w_planes, hp, scale=sc)
+    K.pc_planes_wgrad(dyp, hp)
 else:
   raise SystemExit("unknown target " + which)
 torch.cuda.synchronize()

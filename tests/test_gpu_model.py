@@ -659,6 +659,36 @@ def test_pc_backward_kernels_on_the_8_channel_gradient_equal_the_16_channel_ones
   assert float((dwp - dw16[:, :, :8]).abs().max()) <= 1e-5 * float(dw16.abs().max()) + 1e-6
 
 
+@pytest.mark.parametrize("na", [3, 4])
+def test_pc_loss_epilogue_with_a_static_action_count_equals_the_generic_one(na):
+  """unreal_pc_deconv_loss with the action count as a compile-time constant (3 and 4, the reference's two action spaces) against
+  the run-time loop over the 7 advantage channels: the same arithmetic in the same order -- identical gradient bits."""
+  from unreal_b200 import _lib, kernels as K
+  dev = torch.device("cuda", 0)
+  g = torch.Generator(device=dev).manual_seed(40 + na)
+  s = 777
+  hp = torch.relu(torch.randn(s, 2592, device=dev, generator=g)).to(torch.bfloat16)
+  w8 = torch.zeros(4, 4, 8, 32, device=dev, dtype=torch.bfloat16)
+  w8[:, :, :1 + na] = (torch.randn(4, 4, 1 + na, 32, device=dev, generator=g) * 0.05).to(torch.bfloat16)
+  b8 = torch.zeros(8, device=dev); b8[:1 + na] = torch.randn(1 + na, device=dev, generator=g) * 0.1
+  taps = K.pc_deconv_taps(w8)
+  act = torch.randint(0, na, (s,), device=dev, generator=g, dtype=torch.int32)
+  tgt = torch.rand(s, 400, device=dev, generator=g)
+  msk = (torch.rand(s, device=dev, generator=g) < 0.8).float()
+  res = {}
+  try:
+    for static in (0, 1):
+      _lib.set_tunable("pc_loss_static_a", static)
+      res[static] = [K.pc_deconv_loss(hp, taps, b8, act, tgt, msk, na, 0.05, planes=pl, c8=c8) for pl, c8 in ((False, False), (False, True), (True, False))]
+  finally:
+    _lib.set_tunable("pc_loss_static_a", 1)
+  for (l0, d0, b0), (l1, d1, b1) in zip(res[0], res[1]):
+    assert torch.equal(d0, d1)
+    assert abs(float(l0) - float(l1)) <= 1e-9 * max(1.0, abs(float(l0)))
+    assert float((b0 - b1).abs().max()) <= 1e-5 * float(b0.abs().max()) + 1e-9
+  assert not bool(res[1][0][1][:, :, 1 + na:].any())           # channels beyond 1 + A stay zero
+
+
 def test_pc_q_max_epilogue_equals_the_materialised_head():
   """run_pc_q_max with the dueling combine + max over actions inside the deconv's epilogue (unreal_pc_deconv_qmax) against
   the path that materialises the [N,20,20,8] head output and reduces it with torch ops: same maps (fp32 order only)."""

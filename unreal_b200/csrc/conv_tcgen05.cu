@@ -882,7 +882,7 @@ struct PcLossArgs {
 // each).  The loss epilogue is a chain of dependent instructions per pixel on ONE warp per scheduler (ncu of the 4-warp
 // build, profiles/r2_conv2_bwd_20480samples_ncu_summary.txt: issue slots 39 % active, DRAM 29 %, tensor pipe 7 %, nothing
 // saturated); twice the warps hide twice the latency.
-template <int CO, int EPI = 4>
+template <int CO, int EPI = 4, int NA = 0>       // NA: the pixel-control loss's action count when known at compile time (0: run time)
 __global__ void __launch_bounds__(64 + 32 * EPI, 2)
 conv2_dgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_w,
                            void* __restrict__ out_raw, const float* __restrict__ bias, int samples,
@@ -1048,7 +1048,13 @@ conv2_dgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __gr
               tg_next[d] = __ldcs(reinterpret_cast<const float2*>(pl.target + ((int64_t)nx * 20 + 2 * Y + dy_base + d) * 20 + 2 * X));
           }
           if (r < 100) {
+            // NA > 0: the action count as a compile-time constant (the epilogue was ALU-bound on the per-channel predicates:
+            // ncu 71 % of the ALU pipe, issue slots 66 % busy, profiles/r2_pc_planes_ncu_summary.txt)
+            constexpr int kA = NA > 0 ? NA : 7;
             const float inv_a = 1.0f / (float)pl.a;
+            float ck[kA];                                    // (k == a) - 1/A: d Q_a / d Adv_k
+#pragma unroll
+            for (int k = 0; k < kA; ++k) ck[k] = (k == a ? 1.f : 0.f) - inv_a;
             __nv_bfloat16* out16 = reinterpret_cast<__nv_bfloat16*>(out_raw);
 #pragma unroll
             for (int d = 0; d < kDy; ++d) {
@@ -1058,29 +1064,32 @@ conv2_dgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __gr
               uint4* dst = reinterpret_cast<uint4*>(out16 + pix * (pl.c8 ? 8 : 16));
 #pragma unroll
               for (int dx = 0; dx < 2; ++dx) {
-                float y[8];
+                float y[1 + kA];
 #pragma unroll
-                for (int c = 0; c < 8; ++c) y[c] = fmaxf(__uint_as_float(v[d * 16 + dx * 8 + c]) + b8[c], 0.f);
+                for (int c = 0; c <= kA; ++c) y[c] = fmaxf(__uint_as_float(v[d * 16 + dx * 8 + c]) + b8[c], 0.f);
                 float sum = 0.f, qa = 0.f;
 #pragma unroll
-                for (int k = 0; k < 7; ++k) {
-                  if (k < pl.a) { sum += y[1 + k]; if (k == a) qa = y[1 + k]; }
+                for (int k = 0; k < kA; ++k) {
+                  if (NA > 0 || k < pl.a) { sum += y[1 + k]; if (k == a) qa = y[1 + k]; }
                 }
                 qa = y[0] + qa - sum * inv_a;
                 const float diff = qa - (dx ? tg.y : tg.x);
                 loss_part += m * diff * diff;
                 const float g = pl.lam * m * diff;
-                float d[8];
-                d[0] = y[0] > 0.f ? g : 0.f;
+                float dd[8];
+                dd[0] = y[0] > 0.f ? g : 0.f;
 #pragma unroll
-                for (int k = 0; k < 7; ++k) d[1 + k] = (k < pl.a && y[1 + k] > 0.f) ? g * ((k == a ? 1.f : 0.f) - inv_a) : 0.f;
+                for (int k = 0; k < 7; ++k)
+                  dd[1 + k] = (k < kA && (NA > 0 || k < pl.a) && y[k < kA ? 1 + k : 0] > 0.f) ? g * ck[k < kA ? k : 0] : 0.f;
                 uint32_t pk[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                  __nv_bfloat162 p = __floats2bfloat162_rn(d[2 * j], d[2 * j + 1]);
+                  if (2 * j > kA) { pk[j] = 0u; continue; }       // channels beyond 1 + A: zero
+                  __nv_bfloat162 p = __floats2bfloat162_rn(dd[2 * j], dd[2 * j + 1]);
                   pk[j] = *reinterpret_cast<uint32_t*>(&p);
                   const float2 f = __bfloat1622float2(p);      // the bias gradient sums the ROUNDED values
-                  dbacc[2 * j] += f.x; dbacc[2 * j + 1] += f.y;
+                  dbacc[2 * j] += f.x;
+                  if (2 * j + 1 <= kA) dbacc[2 * j + 1] += f.y;
                 }
                 if (pl.c8 == 2) {        // consecutive lanes = consecutive 16-byte rows of one plane
                   __stcs(reinterpret_cast<uint4*>(out16) + ((int64_t)it * 4 + dy * 2 + dx) * 100 + r, make_uint4(pk[0], pk[1], pk[2], pk[3]));
@@ -1759,7 +1768,7 @@ extern "C" int unreal_conv2_wgrad_c8(const void* x8_bf16, const void* dy_bf16, f
   return conv2_wgrad_launch<8>(x8_bf16, dy_bf16, dw_taps, s, stream);
 }
 
-template <int CO, int EPI = 4>
+template <int CO, int EPI = 4, int NA = 0>
 static int launch_deconv(const void* dy_bf16, const void* w_dtaps_bf16, void* out, const float* bias, int s, void* stream,
                          const void* mask_y = nullptr, float* db = nullptr, int pitch21 = 0,
                          PcLossArgs pl = PcLossArgs{nullptr, nullptr, nullptr, nullptr, 0, 0.f, nullptr, 0}) {
@@ -1780,12 +1789,12 @@ static int launch_deconv(const void* dy_bf16, const void* w_dtaps_bf16, void* ou
   }
   static bool configured = false;
   if (!configured) {
-    UNREAL_CUDA(cudaFuncSetAttribute(conv2_dgrad_tcgen05_kernel<CO, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDgSmem));
+    UNREAL_CUDA(cudaFuncSetAttribute(conv2_dgrad_tcgen05_kernel<CO, EPI, NA>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDgSmem));
     configured = true;
   }
   const int sms = sm_count();
   if (sms <= 0) return UNREAL_ECUDA;
-  conv2_dgrad_tcgen05_kernel<CO, EPI><<<s < 2 * sms ? s : 2 * sms, 64 + 32 * EPI, kDgSmem, as_stream(stream)>>>(
+  conv2_dgrad_tcgen05_kernel<CO, EPI, NA><<<s < 2 * sms ? s : 2 * sms, 64 + 32 * EPI, kDgSmem, as_stream(stream)>>>(
       ta, tw, out, bias, s, reinterpret_cast<const __nv_bfloat16*>(mask_y), db, pitch21, pl);
   UNREAL_LAUNCH_CHECK("conv2_dgrad_tcgen05_kernel");
   return UNREAL_OK;
@@ -1821,8 +1830,12 @@ static int pc_deconv_loss_impl(const void* h_bf16, const void* w_dtaps_bf16, con
   UNREAL_REQUIRE(aligned16(h_bf16) && aligned16(w_dtaps_bf16) && aligned16(dy_bf16) && aligned16(target),
                  "unreal_pc_deconv_loss: 16-byte alignment");
   const PcLossArgs pl{act, target, mask, loss, a, lam, nullptr, c8};
-  if (get_tunable("pc_loss_epi8", 1) != 0)     // eight epilogue warps (A/B switch for the benchmark scripts)
+  if (get_tunable("pc_loss_epi8", 1) != 0) {   // eight epilogue warps (A/B switch for the benchmark scripts)
+    // the two action counts of the reference's environments (maze: 4; indoor pointgoal: 3) as compile-time constants
+    if (a == 4 && get_tunable("pc_loss_static_a", 1) != 0) return launch_deconv<8, 8, 4>(h_bf16, w_dtaps_bf16, dy_bf16, bias8, s, stream, nullptr, db8, 0, pl);
+    if (a == 3 && get_tunable("pc_loss_static_a", 1) != 0) return launch_deconv<8, 8, 3>(h_bf16, w_dtaps_bf16, dy_bf16, bias8, s, stream, nullptr, db8, 0, pl);
     return launch_deconv<8, 8>(h_bf16, w_dtaps_bf16, dy_bf16, bias8, s, stream, nullptr, db8, 0, pl);
+  }
   return launch_deconv<8>(h_bf16, w_dtaps_bf16, dy_bf16, bias8, s, stream, nullptr, db8, 0, pl);
 }
 
