@@ -1400,13 +1400,13 @@ pc_planes_conv_tcgen05_kernel(const __nv_bfloat16* __restrict__ dyp, const __nv_
 // The merged deconv filter's gradient dW8[ky][kx][c][o] = sum over samples and (oy,ox) of dy[2oy+ky, 2ox+kx, c] . hp[oy,ox,o]:
 // the reduction runs over pixels, so both operands are MN-major -- the gradient planes as they lie (A: M = (dy,dx,c) = 4 real
 // 8-channel chunks of the 8 a 64-row UMMA reads, K = grid rows at a 16-byte pitch, tap = start address shift), the sample's
-// pc_fc1 output hp [9,9,32] through a 4-D box {32, 10, 10, 1} (column ox = 9 and row oy = 9 are out of bounds = TMA zero
-// fill) as a 64-byte-swizzled B tile on the same 10-wide grid.  K = 112 rows: rows 100..111 of the B tile are zero (zeroed
-// once, never written), so the finite gradient values A holds there contribute nothing.  Four [32 x 32] accumulators (one per
+// pc_fc1 output hp [9,9,32] through a 4-D box {32, 10, 9, 1} (column ox = 9 is out of bounds = TMA zero fill) as a
+// 64-byte-swizzled B tile on the same 10-wide grid.  K = 96 rows: rows 90..95 of the B tile are zero (zeroed once, never
+// written), so the finite gradient values A holds there contribute nothing.  Four [32 x 32] accumulators (one per
 // tap) live in TMEM across all samples of a CTA and are added to global once, in HWIO order.
-constexpr int kPwAStages = 8;
-constexpr int kPwBStages = 4;
-constexpr int kPwBBytes = 8192;                    // 100 landed rows x 64 B (+ 12 zero rows), 1024-aligned
+constexpr int kPwAStages = 10;
+constexpr int kPwBStages = 6;
+constexpr int kPwBBytes = 6144;                    // 90 landed rows x 64 B (+ 6 zero rows), 1024-aligned
 constexpr int kPwTail = 8192;                      // the four garbage chunks of the last A stage read here
 constexpr int kPwSmem = kPwBStages * kPwBBytes + kPwAStages * kPpTileBytes + kPwTail + 1024 + 1024;
 
@@ -1450,7 +1450,7 @@ pc_planes_wgrad_tcgen05_kernel(const __nv_bfloat16* __restrict__ dyp, const __gr
       int sa = 0; uint32_t pa = 0; int sb = 0; uint32_t pb = 0;
       for (int it = blockIdx.x; it < samples; it += gridDim.x) {
         mbar_wait(emptyB(sb), pb ^ 1u);
-        mbar_arrive_expect_tx(fullB(sb), 100 * 64);
+        mbar_arrive_expect_tx(fullB(sb), 90 * 64);
         tma_load_4d(b_smem + sb * kPwBBytes, &tma_hp, fullB(sb), 0, 0, 0, it);
         if (++sb == kPwBStages) { sb = 0; pb ^= 1u; }
         mbar_wait(emptyA(sa), pa ^ 1u);
@@ -1481,7 +1481,7 @@ pc_planes_wgrad_tcgen05_kernel(const __nv_bfloat16* __restrict__ dyp, const __gr
         for (int tap = 0; tap < 4; ++tap) {
           const uint32_t shift16 = (uint32_t)((tap >> 1) * 10 + (tap & 1));
 #pragma unroll
-          for (int ks = 0; ks < 7; ++ks)
+          for (int ks = 0; ks < 6; ++ks)
             mma_f16_lohi(tmem_base + (uint32_t)(tap * 32), a_lo0 + shift16 + (uint32_t)(ks * 16), a_hi, b_lo0 + (uint32_t)(ks * 64), b_hi,
                          idesc, (first && ks == 0) ? 0u : 1u);
         }
@@ -1883,7 +1883,7 @@ extern "C" int unreal_pc_planes_wgrad(const void* dy_planes_bf16, const void* hp
   {
     const uint64_t dims[4] = {32, 9, 9, (uint64_t)s};           // hp [S][9 oy][9 ox][32 o]
     const uint64_t strides[3] = {64, 64 * 9, 64 * 81};
-    const uint32_t box[4] = {32, 10, 10, 1};                   // one zero column / row: the gradient planes' 10-wide grid
+    const uint32_t box[4] = {32, 10, 9, 1};                    // one zero column: the gradient planes' 10-wide grid
     int rc = make_tma_nd_bf16(&th, hp_bf16, 4, dims, strides, box, 64);
     if (rc != UNREAL_OK) return rc;
   }
