@@ -73,7 +73,8 @@ def maze_step(state, action, obs=None, pc=None, reward=None, terminal=None, fram
     if active is None:
       cell_obs.copy_(state.pos.view_as(cell_obs))
     else:                        # like the render kernels: rows of inactive envs are left alone
-      cell_obs.copy_(torch.where(active.view(n, 1).bool(), state.pos.view(n, 2), cell_obs.view(n, 2)).view_as(cell_obs))
+      co = cell_obs.view(n, 2)
+      torch.where(active.view(n, 1).bool(), state.pos.view(n, 2), co, out=co)
   return reward, terminal
 
 
@@ -880,7 +881,7 @@ def pc_planes_wgrad(dyp, hp):
 
 
 def a3c_head(h, wp, bp, wv, bv, act=None, adv=None, ret=None, mask=None, entropy_beta=0.0, value_coef=0.25,
-             want_pi=False, want_v=False, want_sums=False, want_grads=False):
+             want_pi=False, want_v=False, want_sums=False, want_grads=False, v_out=None):
   """Policy / value heads (+ A3C losses) over h [M,256] f32 in one pass.  Returns a dict with the requested
   pi [M,A], v [M], sums f64 [3] (policy, value, entropy), dz [M,A], dv [M]."""
   m = h.shape[0]
@@ -889,8 +890,8 @@ def a3c_head(h, wp, bp, wv, bv, act=None, adv=None, ret=None, mask=None, entropy
   out = {}
   if want_pi:
     out["pi"] = torch.empty(m, a, dtype=torch.float32, device=d)
-  if want_v:
-    out["v"] = torch.empty(m, dtype=torch.float32, device=d)
+  if want_v:     # v_out: a caller-owned [M] buffer (the rollout's value history row) instead of a fresh tensor + a copy
+    out["v"] = torch.empty(m, dtype=torch.float32, device=d) if v_out is None else v_out
   if want_sums:
     out["sums"] = torch.zeros(3, dtype=torch.float64, device=d)
   if want_grads:

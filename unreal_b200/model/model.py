@@ -278,16 +278,19 @@ class UnrealModel(object):
     return LstmFn.apply(fc, lar.to(torch.float32), self.wcat16, p32["lstm_kernel"], p32["lstm_bias"], c0, h0, self.lstm_in,
                         self.kx, self._gates_dtype(), self._fused_step(n)), h2
 
-  def _policy_value(self, p32, h):
+  def _policy_value(self, p32, h, v_out=None):
     """model.py:358-377 (tiny [.,256]x[256,A+1] products, fp32).  Without autograd (acting, bootstraps): one fused
     head kernel (logits + softmax + value); with autograd: plain torch ops (the losses use A3CHeadLossFn instead)."""
     if self.fused_heads and not torch.is_grad_enabled() and self._action_size <= 7:
       lead = h.shape[:-1]
       out = K.a3c_head(h.reshape(-1, 256).contiguous(), p32["W_base_fc_p"].contiguous(), p32["b_base_fc_p"],
-                       p32["W_base_fc_v"].reshape(256).contiguous(), p32["b_base_fc_v"], want_pi=True, want_v=True)
+                       p32["W_base_fc_v"].reshape(256).contiguous(), p32["b_base_fc_v"], want_pi=True, want_v=True,
+                       v_out=v_out)
       return out["pi"].view(*lead, self._action_size), out["v"].view(*lead)
     logits = h @ p32["W_base_fc_p"] + p32["b_base_fc_p"]
     v = (h @ p32["W_base_fc_v"] + p32["b_base_fc_v"]).squeeze(-1)
+    if v_out is not None:
+      v = v_out.copy_(v.reshape(v_out.shape))
     return torch.softmax(logits, dim=-1), v
 
   def _pc_head(self, p32, h):
@@ -382,8 +385,11 @@ class UnrealModel(object):
     xh[:, self.kx:].copy_(h_prev)
     return K.gemm_bf16(xh, self.wcat16, b_mn_major=True, bias=p32["lstm_bias"], out_dtype=self._gates_dtype())
 
-  def run_base_policy_and_value(self, sess, s_t, last_action_reward, active=None, mode=""):
-    """model.py:630-660: one acting step; advances the LSTM state of the active envs."""
+  def run_base_policy_and_value(self, sess, s_t, last_action_reward, active=None, mode="", v_out=None):
+    """model.py:630-660: one acting step; advances the LSTM state of the active envs.  `v_out` (f32 [N], contiguous): the
+    values are written there (the batched rollout's history row) and returned as that tensor."""
+    if v_out is not None and not (v_out.is_contiguous() and v_out.dtype == torch.float32):
+      raise _lib.UnrealError("v_out must be a contiguous float32 [N] tensor")
     if self.fused_conv and self.fused_encoder:
       with torch.no_grad():
         p32 = self._views(self.flat)
@@ -392,11 +398,11 @@ class UnrealModel(object):
         gates = self._step_gates(p32, img[0], self._lar(last_action_reward, n)[0], self._lstm_h)
         h = torch.empty(n, 256, device=self._device)
         K.lstm_cell_act(gates, self._lstm_c, self._lstm_h, h, active)      # in place on the state of the active envs
-        pi, v = self._policy_value(p32, h)
+        pi, v = self._policy_value(p32, h, v_out)
       return pi, v, None
     p32, h, new_state = self._step(s_t, last_action_reward, self.base_lstm_state_out)
     with torch.no_grad():
-      pi, v = self._policy_value(p32, h)
+      pi, v = self._policy_value(p32, h, v_out)
       if active is None:
         self._lstm_c.copy_(new_state[0]); self._lstm_h.copy_(new_state[1])
       else:

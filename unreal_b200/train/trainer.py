@@ -177,13 +177,14 @@ class Trainer(object):
       learning_rate = 0.0
     return learning_rate
 
-  def choose_action(self, pi_values, active=None):
+  def choose_action(self, pi_values, active=None, out=None):
     """trainer.py:147-148, per env on its own device RandomState stream.  A 1-D numpy/torch
-    vector is accepted for the scalar case and returns a python int."""
+    vector is accepted for the scalar case and returns a python int.  `out` (int32 [N]): rows of active envs are
+    written there, the others left as they are."""
     scalar = not isinstance(pi_values, torch.Tensor) or pi_values.dim() == 1
     pi = torch.as_tensor(np.asarray(pi_values, dtype=np.float32) if scalar else pi_values)
     pi = pi.to(self.device, torch.float32).reshape(-1, pi.shape[-1]).contiguous()
-    a = self.streams.choose_action(pi, active)
+    a = self.streams.choose_action(pi, active, out)
     return int(a[0]) if scalar else a
 
   def set_start_time(self, start_time):
@@ -249,16 +250,24 @@ class Trainer(object):
     stats0 = self.episode_stats.clone()       # [episodes finished, sum of their scores] before this window
     self._obs[0].copy_(env.last_state['image'])
     self._pos[0].copy_(env.state.pos)
-    self._active.zero_(); self._rew.zero_(); self._term.zero_()
+    self._active.zero_(); self._rew.zero_(); self._term.zero_(); self._act.zero_()
+    import inspect
+    if getattr(self, "_net_v_out", None) is None:     # networks that can write the values straight into the history row
+      self._net_v_out = "v_out" in inspect.signature(net.run_base_policy_and_value).parameters
     last_rec = torch.zeros(n, dtype=torch.int64, device=d)
     # networks with the persistent [N,256] LSTM state buffers (UnrealModel) get them zeroed by the bookkeeping kernel
     lstm_c, lstm_h = getattr(net, "_lstm_c", None), getattr(net, "_lstm_h", None)
     fused_state = isinstance(lstm_c, torch.Tensor) and isinstance(lstm_h, torch.Tensor)
     for t in range(T):
       lar = K.rollout_lar(env.last_action, env.last_reward, self.action_size, out=self._lar[t])   # straight into the feed
-      pi, v, _ = net.run_base_policy_and_value(sess, {'image': self._obs[t]}, lar, active)
-      action = self.choose_action(pi, active)
-      self._val[t].copy_(v); self._act[t].copy_(action); self._active[t].copy_(active)
+      if self._net_v_out:
+        pi, v, _ = net.run_base_policy_and_value(sess, {'image': self._obs[t]}, lar, active, v_out=self._val[t])
+      else:
+        pi, v, _ = net.run_base_policy_and_value(sess, {'image': self._obs[t]}, lar, active)
+        self._val[t].copy_(v)
+      # the history row is the kernel's output: finished rollouts draw nothing and keep the zero the row was reset to
+      action = self.choose_action(pi, active, out=self._act[t])
+      self._active[t].copy_(active)
       # the new frame lands in obs[t+1]; envs whose rollout already ended are skipped by the kernel
       # (no pixel-change map: replayed frames re-derive theirs from the record's two cells, _process_pc)
       env.process(action, active=active, out_obs=self._obs[t + 1], out_pc=False,
