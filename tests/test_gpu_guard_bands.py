@@ -123,3 +123,53 @@ def test_lstm_bf16_cells_and_fused_pc_head_writes_stay_inside(K):
     loss, dy16, db8 = K.pc_deconv_loss(hp, m.pc_taps, m.pc_b8, torch.randint(0, 4, (s,), device=DEV, dtype=torch.int32, generator=g),
                                        torch.rand(s, 400, device=DEV, generator=g), torch.ones(s, device=DEV), 4, 0.05)
     assert torch.isfinite(loss).all() and not dy16[:, :, 8:].any()      # the padding channels are written as zeros
+
+
+@pytest.mark.parametrize("s", [1, 5, 297, 601])
+def test_pixel_control_backward_kernels_write_inside_their_buffers(K, s):
+  """The last third of round 2: fused deconv + loss with its three gradient layouts (conv2's [S,400,16], [S,400,8], four
+  parity planes), the backward convolutions with pc_fc1's ReLU mask (16 / 8 channels, planes), the filter gradients, and
+  the one-pass maze Q-target scan -- through the C ABI with caller-owned, guarded outputs; sample counts below / off /
+  above the 2 x 148 CTAs the persistent kernels launch."""
+  from unreal_b200._lib import call, ptr, stream_ptr
+  A = 4
+  g = torch.Generator(device=DEV).manual_seed(100 + s)
+  hp = torch.relu(torch.randn(s, 2592, device=DEV, generator=g)).to(torch.bfloat16)
+  w8 = torch.zeros(4, 4, 8, 32, device=DEV, dtype=torch.bfloat16)
+  w8[:, :, :1 + A] = (torch.randn(4, 4, 1 + A, 32, device=DEV, generator=g) * 0.05).to(torch.bfloat16)
+  w16 = torch.zeros(4, 4, 16, 32, device=DEV, dtype=torch.bfloat16); w16[:, :, :8] = w8
+  b8 = torch.zeros(8, device=DEV)
+  taps = K.pc_deconv_taps(w8)
+  act = torch.randint(0, A, (s,), device=DEV, generator=g, dtype=torch.int32)
+  tgt = torch.rand(s, 400, device=DEV, generator=g)
+  msk = torch.ones(s, device=DEV)
+  sc = torch.tensor([0.7], device=DEV)
+  for fn, shape in (("unreal_pc_deconv_loss", (s, 400, 16)), ("unreal_pc_deconv_loss_c8", (s, 400, 8)),
+                    ("unreal_pc_deconv_loss_planes", (s, 4, 100, 8))):
+    dy, loss, db = Guarded(shape, torch.bfloat16), Guarded((1,), torch.float64), Guarded((8,), torch.float32)
+    loss.t.zero_(); db.t.zero_()
+    call(fn, ptr(hp), ptr(taps), ptr(b8), ptr(act), ptr(tgt), ptr(msk), A, 0.05, s, ptr(loss.t), ptr(dy.t), ptr(db.t), stream_ptr())
+    _check(dy, loss, db)
+    assert bool(torch.isfinite(dy.t.float()).all())
+    out, dbf = Guarded((s, 9, 9, 32), torch.bfloat16), Guarded((2592,), torch.float32)
+    dbf.t.zero_()
+    if shape[1] == 4:
+      dw = Guarded((4, 4, 8, 32), torch.float32); dw.t.zero_()
+      call("unreal_pc_planes_conv", ptr(dy.t), ptr(K.pc_w_planes(w8)), ptr(sc), ptr(hp), ptr(out.t), ptr(dbf.t), s, stream_ptr())
+      call("unreal_pc_planes_wgrad", ptr(dy.t), ptr(hp), ptr(dw.t), s, stream_ptr())
+    else:
+      c = shape[2]
+      dw = Guarded((4, 4, c, 32), torch.float32); dw.t.zero_()
+      call("unreal_conv2_fwd_linear_masked", ptr(dy.t), c, ptr(K.conv_taps(w16 if c == 16 else w8, 2)), ptr(sc), ptr(hp), ptr(out.t),
+           ptr(dbf.t), s, stream_ptr())
+      call("unreal_conv2_wgrad" if c == 16 else "unreal_conv2_wgrad_c8", ptr(dy.t), ptr(hp), ptr(dw.t), s, stream_ptr())
+    _check(out, dbf, dw)
+    assert bool(torch.isfinite(out.t.float()).all()) and bool(torch.isfinite(dw.t).all()) and bool(torch.isfinite(dbf.t).all())
+  t = 7
+  p0 = torch.randint(0, 7, (t, s, 2), device=DEV, generator=g, dtype=torch.int32)
+  p1 = torch.randint(0, 7, (t, s, 2), device=DEV, generator=g, dtype=torch.int32)
+  ln = torch.randint(0, t + 1, (s,), device=DEV, generator=g, dtype=torch.int32)
+  boot = torch.rand(s, 20, 20, device=DEV, generator=g)
+  tg = Guarded((t, s, 20, 20), torch.float32)
+  K.maze_pc_targets(p0, p1, ln, boot, 0.9, out=tg.t)
+  _check(tg)
