@@ -3,14 +3,20 @@
 TEST INFRASTRUCTURE (see ``oracle/__init__.py``): imported only by ``tests/``,
 ``__graft_entry__.smoke()`` and the CPU-baseline legs of ``bench.py``.
 
-**PARITY UNPINNED.**  The arithmetic of model.py lives in TensorFlow 1.x (unpinned; README says
-r1.0), which is neither under ``/root/reference`` nor installable here, and the reference's own
-``model/model_test.py`` pins only the variable COUNT (20 / 18 / 12 / 14), which
-``tests/test_model_oracle.py`` checks.  What anchors the restatement instead (same file): every op against a direct
-loop implementation of TF's documented definition; the LSTM unroll against ``torch.nn.LSTMCell`` fed the same
-weights with permuted gate columns; autograd against float64 central differences of the total loss in all 20
-variables; and every head's loss against numbers worked out by hand from model.py's formulas.  Everything below
-restates model.py line by line with the documented TF-1 semantics of the ops it calls:
+**Parity: pinned to the reference's own model.py, executed; TensorFlow's kernels themselves unpinned.**  The arithmetic of
+model.py lives in TensorFlow 1.x (un-vendored, unpinned; README says r1.0, ``BasicLSTMCell``'s ``kernel`` / ``bias`` names need
+>= 1.2), which is neither under ``/root/reference`` nor installable here.  ``tests/golden/make_model_golden.py`` therefore
+imports the reference's ``model/model.py`` UNMODIFIED over ``tests/golden/tf1_shim`` -- the ~30 TF-1 ops of the vanilla path
+restated from their published definitions on torch float64 -- and records what the reference's own graph-building code, loss
+formulas and ``run_*`` methods compute: ``tests/test_model_oracle.py::test_oracle_matches_the_references_model_py`` holds this
+restatement to those vectors at 1e-9 (variable creation order and names, three acting steps with the carried LSTM state,
+every ``run_*`` output, every loss term of a Trainer-shaped feed, the gradient of ``total_loss`` in all 20 variables).
+What that does NOT pin is TensorFlow's implementation of the ops (conv2d, conv2d_transpose, BasicLSTMCell): the shim and this
+file restate the same published semantics.  Those are anchored separately (same test file): every op against a direct loop
+implementation of TF's documented definition; the LSTM unroll against ``torch.nn.LSTMCell`` fed the same weights with
+permuted gate columns; autograd against float64 central differences of the total loss in all 20 variables; every head's loss
+against numbers worked out by hand from model.py's formulas; and ``model/model_test.py``'s variable counts (20 / 18 / 12 /
+14).  Everything below restates model.py line by line with the documented TF-1 semantics of the ops it calls:
 
   tf.nn.conv2d NHWC / HWIO / VALID                      model.py:283-289, :786-787
   tf.matmul + relu, flatten in NHWC order               model.py:332-340

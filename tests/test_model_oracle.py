@@ -1,9 +1,10 @@
 """CPU checks of oracle/model_oracle.py (the PyTorch restatement of model/model.py).
 
-The reference pins only the variable count (model/model_test.py:8-77: 20 / 18 / 12 / 14); the op
-semantics the restatement relies on (TF conv2d NHWC/HWIO, conv2d_transpose with a
-[kh,kw,out,in] filter, BasicLSTMCell gate order and forget bias) are checked here against
-direct loop implementations of TF's documented definitions.  Parity with TF itself is UNPINNED.
+Pinned to the reference: `test_oracle_matches_the_references_model_py` compares it with vectors produced by the reference's own
+model/model.py running over a TF-1 op shim (tests/golden/make_model_golden.py).  TensorFlow itself cannot run here, so the op
+semantics both rely on (TF conv2d NHWC/HWIO, conv2d_transpose with a [kh,kw,out,in] filter, BasicLSTMCell gate order and
+forget bias) are checked against direct loop implementations of TF's documented definitions, torch.nn.LSTMCell, float64
+finite differences and hand-computed heads; the reference's model_test.py pins the variable counts (20 / 18 / 12 / 14).
 """
 import numpy as np
 import torch
@@ -311,3 +312,65 @@ def test_every_head_against_a_hand_computed_answer():
   rp = -(z[2] - math.log(sum(math.exp(v) for v in z)))
   assert abs(float(parts["rp"]) - rp) <= 1e-12 * max(1.0, abs(rp))
   assert abs(float(total) - (pol + val + vr + pc + rp)) <= 1e-9 * max(1.0, abs(float(total)))
+
+
+def test_oracle_matches_the_references_model_py():
+  """tests/golden/model_reference_golden.npz was produced by the REFERENCE'S OWN model/model.py, imported unmodified and
+  executed over tests/golden/tf1_shim (TensorFlow cannot be installed: its ~30 ops on this path are restated from their
+  published definitions; the graph building, variable order and reuse, layer wiring, loss formulas and the run_* methods
+  are the reference's code).  The oracle must reproduce, in float64: the three acting steps of run_base_policy_and_value
+  with their carried LSTM state, run_base_value / run_pc_q_max / run_vr_value / run_rp_c, every loss term of a training
+  feed assembled like Trainer.process (trainer.py:500-541) and the gradient of total_loss in all 20 variables
+  (rmsprop_applier.py:109-116)."""
+  import os
+  g = np.load(os.path.join(os.path.dirname(__file__), "golden", "model_reference_golden.npz"))
+  A, G, seed, T, Lp, Lv = (int(x) for x in g["meta"])
+  p = M.init_params(A, G, seed=seed)
+  p = type(p)((k, v.to(torch.float64)) for k, v in p.items())
+  o = M.ModelOracle(p, A, G, 0.05, 0.001)
+  # the reference created the oracle's 20 variables, in the oracle's order
+  last = [str(n).split("/")[-1].split(":")[0] for n in g["variable_names"]]
+  want = [n.replace("lstm_kernel", "kernel").replace("lstm_bias", "bias") for n, _, _ in M.variable_specs(A, G)]
+  assert last == want
+  assert str(g["variable_names"][6]) == "net_0/base_lstm_layer/basic_lstm_cell/kernel:0"
+  f64 = lambda k: torch.from_numpy(np.asarray(g[k], dtype=np.float64))          # noqa: E731
+  img = lambda k: torch.from_numpy(g[k].astype(np.float64) / 255.0)             # noqa: E731
+  close = lambda a, b: np.testing.assert_allclose(np.asarray(a), np.asarray(b), rtol=1e-9, atol=1e-11)   # noqa: E731
+  with torch.no_grad():
+    # acting: step size 1, the state carried from call to call (model.py:617-660)
+    c = h = torch.zeros(1, 256, dtype=torch.float64)
+    for t in range(3):
+      pi, v, (c, h) = o.base_forward(img("act_frames")[t][None, None], f64("act_lar")[t][None, None], c, h)
+      close(pi[0, 0], g["act_pi"][t]); close(v[0, 0], g["act_v"][t])
+    close(c, g["act_state_c"]); close(h, g["act_state_h"])
+    # run_base_value reads the carried state and leaves it alone (model.py:687-704)
+    _, v, _ = o.base_forward(img("one_frame")[0][None, None], f64("one_lar")[0][None, None], c, h)
+    close(v[0, 0], g["base_value"])
+    _, qmax = o.pc_forward(img("one_frame")[0][None, None], f64("one_lar")[0][None, None])
+    close(qmax[0, 0], g["pc_q_max"])
+    close(o.vr_forward(img("one_frame")[0][None, None], f64("one_lar")[0][None, None])[0, 0], g["vr_value"])
+    close(o.rp_forward(img("rp_frames")[None])[0], g["rp_c"])
+  ones = lambda n: torch.ones(n, 1, dtype=torch.float64)                        # noqa: E731
+  feed = {"base": dict(images=img("base_frames")[:, None], lar=f64("base_lar")[:, None], a=f64("base_a")[:, None],
+                       adv=f64("base_adv")[:, None], R=f64("base_R")[:, None], mask=ones(T), c0=f64("base_c0"), h0=f64("base_h0")),
+          "pc": dict(images=img("pc_frames")[:, None], lar=f64("pc_lar")[:, None], a=f64("pc_a")[:, None], R=f64("pc_R")[:, None],
+                     mask=ones(Lp)),
+          "vr": dict(images=img("vr_frames")[:, None], lar=f64("vr_lar")[:, None], R=f64("vr_R")[:, None], mask=ones(Lv)),
+          "rp": dict(images=img("rp_train_frames")[None], c=f64("rp_c_target"))}
+  total, parts, grads = o.loss_and_grads(feed)
+  close(total, g["total_loss"])
+  for k, name in (("policy", "policy_loss"), ("value", "value_loss"), ("pc", "pc_loss"), ("vr", "vr_loss"), ("rp", "rp_loss")):
+    close(parts[k], g[name])
+  with torch.no_grad():
+    pi, v, _ = o.base_forward(feed["base"]["images"], feed["base"]["lar"], feed["base"]["c0"], feed["base"]["h0"])
+    close(pi[:, 0], g["base_pi"]); close(v[:, 0], g["base_v"])
+    close(-(pi * torch.log(pi.clamp(1e-20, 1.0))).sum(-1)[:, 0], g["entropy"])
+    close(o.pc_forward(feed["pc"]["images"], feed["pc"]["lar"])[0][:, 0], g["pc_q"])
+    close(o.vr_forward(feed["vr"]["images"], feed["vr"]["lar"])[:, 0], g["vr_v"])
+    close(o.rp_forward(feed["rp"]["images"]), g["train_rp_c"])
+  for name, _, _ in M.variable_specs(A, G):
+    gr = grads[name].reshape(-1).numpy()
+    scale = max(float(g["grad_norm_" + name]), 1e-30)
+    assert abs(gr.sum() - float(g["grad_sum_" + name])) <= 1e-9 * scale * np.sqrt(gr.size), name
+    assert abs(np.sqrt((gr * gr).sum()) - scale) <= 1e-9 * scale, name
+    np.testing.assert_allclose(gr[g["grad_idx_" + name]], g["grad_val_" + name], rtol=1e-8, atol=1e-9 * scale, err_msg=name)
