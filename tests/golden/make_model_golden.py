@@ -9,8 +9,11 @@ TensorFlow is the reference's un-vendored dependency and cannot be installed her
 ``tests/golden/tf1_shim`` -- ~30 TF-1 ops restated from their published definitions over torch float64 (see its docstring).
 Everything else is the reference, unmodified: ``UnrealModel.__init__`` builds its graph (placeholders, scopes, variable
 creation order and reuse across the four towers), ``prepare_loss()`` builds the losses, ``run_base_policy_and_value /
-run_base_value / run_pc_q_max / run_vr_value / run_rp_c`` run with their own feed dicts, and the gradient of
-``total_loss`` w.r.t. ``get_vars()`` is what ``RMSPropApplier.minimize_local`` asks TF for (rmsprop_applier.py:109-116).
+run_base_value / run_pc_q_max / run_vr_value / run_rp_c`` run with their own feed dicts, the gradient of
+``total_loss`` w.r.t. ``get_vars()`` is what ``RMSPropApplier.minimize_local`` asks TF for (rmsprop_applier.py:109-116), and
+the learner step itself is the reference's ``train/rmsprop_applier.py`` too: a global network, ``sync_from``, then
+``minimize_local`` (clip_by_global_norm + ApplyRMSProp on slots it creates) run twice with the learning rate fed through
+its placeholder -- the second time with a gradient above the clip norm.
 
 The variables are set from ``oracle.model_oracle.init_params`` (by creation ORDER, after checking that the reference created
 the same 20 shapes in the same order); the test (tests/test_model_oracle.py::test_oracle_matches_the_references_model_py)
@@ -33,6 +36,7 @@ sys.path.insert(0, os.path.join(HERE, "tf1_shim"))
 import tensorflow as tf  # noqa: E402  (the shim)
 import torch  # noqa: E402
 from model.model import UnrealModel  # noqa: E402  (reference, unmodified)
+from train.rmsprop_applier import RMSPropApplier  # noqa: E402  (reference, unmodified)
 from oracle import model_oracle as MO  # noqa: E402
 
 A, G, SEED = 4, 0, 7
@@ -127,6 +131,33 @@ def main():
     out["grad_norm_" + name] = np.sqrt((g * g).sum())
     out["grad_idx_" + name] = idx
     out["grad_val_" + name] = g[idx]
+  # ---- the learner step as main.py / trainer.py wire it (main.py:299-318, trainer.py:120-133): a GLOBAL network, the worker's
+  # local copy synced from it (sync_from), gradients of the LOCAL loss applied to the GLOBAL variables by the reference's
+  # RMSPropApplier.minimize_local (global-norm clip at 40 + shared RMSProp, slots rms = 1 / momentum = 0); two updates with
+  # the annealed learning rate fed through its placeholder
+  glob = UnrealModel(A, G, -1, True, True, True, True, 0.05, 0.001, "/cpu:0", {'segnet_mode': 0}, [84, 84], True, 0, 0.0, 0.0)
+  for v, (name, _, _) in zip(glob.get_vars(), specs):
+    v.value = params[name].to(torch.float64).clone()
+  lr_in = tf.placeholder("float")
+  applier = RMSPropApplier(learning_rate=lr_in, decay=0.99, momentum=0.0, epsilon=0.1, clip_norm=40.0, device="/cpu:0")
+  apply_op, grad_norm = applier.minimize_local(net.total_loss, glob.get_vars(), net.get_vars(), 0)
+  sync = net.sync_from(glob)
+  norms = []
+  for step, lr_now in enumerate((7e-4, 6.5e-4)):
+    sess.run(sync)
+    feed[lr_in] = lr_now
+    norms.append(float(sess.run([apply_op, grad_norm], feed_dict=feed)[1]))
+    feed[net.base_adv] = feed[net.base_adv] * 30.0        # the second update's gradient exceeds the clip norm
+  out["update_grad_norms"] = np.array(norms)
+  out["update_lrs"] = np.array([7e-4, 6.5e-4])
+  for (name, _, _), v in zip(specs, glob.get_vars()):
+    val = v.value.detach().numpy().reshape(-1)
+    idx = pick.randint(0, val.size, size=64)
+    out["upd_sum_" + name] = (val - params[name].to(torch.float64).numpy().reshape(-1)).sum()
+    out["upd_idx_" + name] = idx
+    out["upd_val_" + name] = val[idx]
+    rms = applier.get_slot(v, "rms").value.numpy().reshape(-1)
+    out["upd_rms_" + name] = rms[idx]
   out["meta"] = np.array([A, G, SEED, T_BASE, L_PC, L_VR])
   path = os.path.join(HERE, "model_reference_golden.npz")
   np.savez_compressed(path, **out)

@@ -111,11 +111,21 @@ class Placeholder(Node):
     self.dtype = dtype
 
 
+class _Op(object):
+  def __init__(self, name):
+    self.name = name
+
+
 class Variable(Node):
   def __init__(self, name, value):
     Node.__init__(self, None, [], list(value.shape), name + ":0")
     self.value = value
-    self.op = self
+    self.op = _Op(name)
+    self.dtype = float64
+    self.device = "/cpu:0"
+
+  def _ref(self):
+    return self
 
 
 def placeholder(dtype, shape=None, name=None):
@@ -128,14 +138,17 @@ def placeholder_with_default(default, shape, name=None):
   return p
 
 
-def constant(v, dtype=None, name=None):
-  t = _t(np.asarray(v))
+def constant(v, dtype=None, shape=None, name=None):
+  t = _t(np.asarray(v, dtype=np.float64 if isinstance(v, (float, list)) else None))
+  if shape is not None:
+    t = t.expand([int(d) for d in (shape.as_list() if isinstance(shape, TensorShape) else shape)]).clone()
   return Node(lambda: t, [], list(t.shape))
 
 
 # ---- scopes, variables, collections ---------------------------------------------------------------
 class GraphKeys(object):
   TRAINABLE_VARIABLES, GLOBAL_VARIABLES, LOCAL_VARIABLES = "trainable_variables", "variables", "local_variables"
+  UPDATE_OPS = "update_ops"
 
 
 class VariableScope(object):
@@ -206,7 +219,7 @@ def get_variable(name, shape=None, dtype=None, initializer=None, **_):
 
 
 def get_collection(key, scope=None):
-  if key == GraphKeys.LOCAL_VARIABLES:
+  if key in (GraphKeys.LOCAL_VARIABLES, GraphKeys.UPDATE_OPS):
     return []
   vs = list(_g.variables.values())
   return [v for v in vs if scope is None or v.name.startswith(scope)]
@@ -244,7 +257,7 @@ def assign(ref, value):
 
 
 def group(*ops, **_):
-  return Node(lambda *a: None, list(ops))
+  return Node(lambda *a: None, [o.op_node if isinstance(o, _Op) else o for o in ops])
 
 
 # ---- ops -------------------------------------------------------------------------------------------
@@ -326,9 +339,29 @@ def gather(params, indices, **_):
   return Node(lambda p, i: p[i.long()], [params, indices])
 
 
-def gradients(ys, xs):
+def gradients(ys, xs, **_):
   """d ys / d xs for Variables xs, evaluated with autograd inside Session.run (a node like any other)."""
   return [_Grad(ys, x) for x in xs]
+
+
+def convert_to_tensor(v, name=None, **_):
+  return v if isinstance(v, Node) else constant(v)
+
+
+@contextlib.contextmanager
+def control_dependencies(_):
+  yield
+
+
+def global_norm(t_list):
+  return Node(lambda ts: torch.sqrt(sum((_t(t) ** 2).sum() for t in ts)), [list(t_list)], [])
+
+
+def clip_by_global_norm(t_list, clip_norm, use_norm=None, name=None):
+  """t_list[i] * clip_norm / max(global_norm, clip_norm), global_norm = sqrt(sum_i l2norm(t_i)^2)  (TF's definition)."""
+  norm = global_norm(t_list)
+  return [Node(lambda t, n: _t(t) * clip_norm / torch.clamp(n, min=clip_norm), [t, norm], getattr(t, "_shape", None))
+          for t in t_list], norm
 
 
 class _Grad(Node):
@@ -435,9 +468,17 @@ class Session(object):
     feed = {k: v for k, v in (feed_dict or {}).items() if isinstance(k, Node)}
     cache = {}
     want_grad = []
-    def collect(f):
-      if isinstance(f, _Grad):
-        want_grad.append(f)
+    seen = set()
+    def collect(f):                      # every gradient node the fetches depend on, anywhere in the graph
+      if isinstance(f, Node):
+        if id(f) in seen:
+          return
+        seen.add(id(f))
+        if isinstance(f, _Grad):
+          want_grad.append(f)
+          collect(f.y)
+        for i in f.inputs:
+          collect(i)
       elif isinstance(f, (list, tuple)):
         for v in f:
           collect(v)

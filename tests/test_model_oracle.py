@@ -374,3 +374,25 @@ def test_oracle_matches_the_references_model_py():
     assert abs(gr.sum() - float(g["grad_sum_" + name])) <= 1e-9 * scale * np.sqrt(gr.size), name
     assert abs(np.sqrt((gr * gr).sum()) - scale) <= 1e-9 * scale, name
     np.testing.assert_allclose(gr[g["grad_idx_" + name]], g["grad_val_" + name], rtol=1e-8, atol=1e-9 * scale, err_msg=name)
+  # ---- the learner step: sync_from + RMSPropApplier.minimize_local, run by the reference's own classes (two updates, the
+  # second with a gradient above the clip norm) against oracle gradients + the oracle's clip / ApplyRMSProp restatement
+  from oracle import unreal_oracle as O
+  names = [n for n, _, _ in M.variable_specs(A, G)]
+  vars_ = [p[n].numpy().copy() for n in names]
+  start = [v.copy() for v in vars_]
+  rms = [np.ones_like(v) for v in vars_]
+  mom = [np.zeros_like(v) for v in vars_]
+  assert float(g["update_grad_norms"][0]) < 40.0 < float(g["update_grad_norms"][1])
+  for step in range(2):
+    cur = type(p)((n, torch.from_numpy(v.copy())) for n, v in zip(names, vars_))
+    _, _, grads = M.ModelOracle(cur, A, G, 0.05, 0.001).loss_and_grads(feed)
+    norm = O.rmsprop_step(vars_, rms, mom, [grads[n].numpy() for n in names], float(g["update_lrs"][step]), decay=0.99,
+                          momentum=0.0, epsilon=0.1, clip_norm=40.0, dtype=np.float64)
+    assert abs(float(norm) - float(g["update_grad_norms"][step])) <= 1e-9 * float(norm)
+    feed["base"]["adv"] = feed["base"]["adv"] * 30.0
+  for n, v, v0, r in zip(names, vars_, start, rms):
+    idx = g["upd_idx_" + n]
+    np.testing.assert_allclose(v.reshape(-1)[idx], g["upd_val_" + n], rtol=1e-10, atol=1e-13, err_msg=n)
+    np.testing.assert_allclose(r.reshape(-1)[idx], g["upd_rms_" + n], rtol=1e-10, atol=1e-13, err_msg=n)
+    step_sum = float((v - v0).sum())
+    assert abs(step_sum - float(g["upd_sum_" + n])) <= 1e-9 * (abs(float(g["upd_sum_" + n])) + 1e-12 * v.size), n
