@@ -453,6 +453,17 @@ class test(object):
   TestCase = object
 
 
+class RunOptions(object):
+  FULL_TRACE = 3
+
+  def __init__(self, *a, **k):
+    pass
+
+
+class RunMetadata(object):
+  step_stats = None
+
+
 # ---- session ---------------------------------------------------------------------------------------
 class Session(object):
   def __init__(self, *a, **k):
@@ -464,8 +475,14 @@ class Session(object):
   def __exit__(self, *a):
     return False
 
-  def run(self, fetches, feed_dict=None):
-    feed = {k: v for k, v in (feed_dict or {}).items() if isinstance(k, Node)}
+  def run(self, fetches, feed_dict=None, options=None, run_metadata=None):
+    feed = {}
+    for k, v in (feed_dict or {}).items():
+      if isinstance(k, Node):
+        feed[k] = v
+      elif isinstance(k, tuple) and all(isinstance(x, Node) for x in k):      # a nested key (LSTMStateTuple of placeholders)
+        for kk, vv in zip(k, v):
+          feed[kk] = vv
     cache = {}
     want_grad = []
     seen = set()
@@ -506,10 +523,11 @@ class Session(object):
       elif isinstance(n, Variable):
         r = n.value
       elif isinstance(n, _Grad):
-        y = ev(n.y)
-        grads = torch.autograd.grad(y, [v.value for v in gvars], retain_graph=True, allow_unused=True)
-        for v, gr in zip(gvars, grads):
-          cache[("grad", id(n.y), id(v))] = torch.zeros_like(v.value) if gr is None else gr
+        if ("grad", id(n.y), id(n.x)) not in cache:        # one backward pass per differentiated node, for all variables
+          y = ev(n.y)
+          grads = torch.autograd.grad(y, [v.value for v in gvars], retain_graph=True, allow_unused=True)
+          for v, gr in zip(gvars, grads):
+            cache[("grad", id(n.y), id(v))] = torch.zeros_like(v.value) if gr is None else gr.detach()
         r = cache[("grad", id(n.y), id(n.x))]
       else:
         r = n.fn(*[_val(i, ev) for i in n.inputs])

@@ -396,3 +396,108 @@ def test_oracle_matches_the_references_model_py():
     np.testing.assert_allclose(r.reshape(-1)[idx], g["upd_rms_" + n], rtol=1e-10, atol=1e-13, err_msg=n)
     step_sum = float((v - v0).sum())
     assert abs(step_sum - float(g["upd_sum_" + n])) <= 1e-9 * (abs(float(g["upd_sum_" + n])) + 1e-12 * v.size), n
+
+
+class _OracleNet(object):
+  """oracle.ModelOracle behind the call surface RolloutOracle expects of a network (model.py:617-728): the carried LSTM
+  state lives here like `base_lstm_state_out` lives in the reference's model."""
+
+  def __init__(self, oracle):
+    self.o = oracle
+    self.reset_state()
+
+  def reset_state(self):
+    self.c = torch.zeros(1, 256, dtype=torch.float64)
+    self.h = torch.zeros(1, 256, dtype=torch.float64)
+
+  @staticmethod
+  def _x(s_t, lar):
+    img = s_t['image'] if isinstance(s_t, dict) else s_t
+    return (torch.from_numpy(np.asarray(img, np.float64))[None, None], torch.from_numpy(np.asarray(lar, np.float64))[None, None])
+
+  def run_base_policy_and_value(self, sess, s_t, lar, mode=""):
+    with torch.no_grad():
+      pi, v, (self.c, self.h) = self.o.base_forward(*self._x(s_t, lar), self.c, self.h)
+    return pi[0, 0].numpy(), float(v[0, 0]), None
+
+  def run_base_value(self, sess, s_t, lar):
+    with torch.no_grad():
+      return float(self.o.base_forward(*self._x(s_t, lar), self.c, self.h)[1][0, 0])
+
+  def run_pc_q_max(self, sess, s_t, lar):
+    with torch.no_grad():
+      return self.o.pc_forward(*self._x(s_t, lar))[1][0, 0].numpy()
+
+  def run_vr_value(self, sess, s_t, lar):
+    with torch.no_grad():
+      return float(self.o.vr_forward(*self._x(s_t, lar))[0, 0])
+
+
+def test_oracle_agent_loop_matches_the_references_trainer():
+  """tests/golden/agent_reference_golden.npz: the reference's own Trainer.process -- _fill_experience until the buffer is
+  full, then four learner iterations (sync_from, _process_base / _pc / _vr / _rp, the feed dict, minimize_local's update) --
+  with the reference's own model, Experience, maze and RMSPropApplier, all over the TF-1 op shim
+  (tests/golden/make_agent_golden.py).  The oracle replays the loop from the same seeds: RolloutOracle for the host logic,
+  ModelOracle for the network, the oracle's clip + ApplyRMSProp for the update.  After the fill and after EVERY iteration
+  the step counter, the returned (steps, score), the agent's cell, the position of the worker's RandomState stream, the
+  carried LSTM state and sampled entries + sums of all 20 global variables must agree (1e-8: float64 both sides, four
+  chained updates).  This pins the glue between the separately pinned pieces -- feed order, start state, bootstrap, the
+  replay samplers' share of the random stream, the learning-rate anneal -- to the reference's code."""
+  import os
+  from oracle import unreal_oracle as O
+  g = np.load(os.path.join(os.path.dirname(__file__), "golden", "agent_reference_golden.npz"))
+  A, G, seed, net_seed, H, n_proc, max_t = (int(x) for x in g["meta"])
+  names = [n for n, _, _ in M.variable_specs(A, G)]
+  vars_ = [v.to(torch.float64).numpy().copy() for v in M.init_params(A, G, seed=net_seed).values()]
+  p = dict((n, torch.from_numpy(v)) for n, v in zip(names, vars_))         # views: the update below is seen by the network
+  rms = [np.ones_like(v) for v in vars_]
+  mom = [np.zeros_like(v) for v in vars_]
+  oracle = M.ModelOracle(p, A, G, 0.05, 0.001)
+  net = _OracleNet(oracle)
+  rs = np.random.RandomState(seed)
+  w = O.RolloutOracle(H, rs, net, n_step_TD=20)
+
+  def check(tag, ret):
+    assert int(g[tag + "_local_t"]) == w.local_t, tag
+    want_ret = g[tag + "_ret"]
+    assert ret[0] == int(want_ret[0]) and ((ret[1] is None) == bool(np.isnan(want_ret[1]))), (tag, ret, want_ret)
+    if ret[1] is not None:
+      assert ret[1] == want_ret[1]
+    assert (w.env.x, w.env.y) == tuple(int(v) for v in g[tag + "_pos"]), tag
+    probe = np.random.RandomState(); probe.set_state(rs.get_state())
+    assert int(probe.randint(0, 2 ** 31 - 1)) == int(g[tag + "_next_draw"]), tag + ": the RandomState streams have diverged"
+    np.testing.assert_allclose(net.c.numpy(), g[tag + "_lstm_c"], rtol=1e-8, atol=1e-10, err_msg=tag)
+    np.testing.assert_allclose(net.h.numpy(), g[tag + "_lstm_h"], rtol=1e-8, atol=1e-10, err_msg=tag)
+    for n, v in zip(names, vars_):
+      np.testing.assert_allclose(v.reshape(-1)[g["idx_" + n]], g[tag + "_val_" + n], rtol=1e-8, atol=1e-11, err_msg=tag + " " + n)
+      assert abs(v.sum() - float(g[tag + "_sum_" + n])) <= 1e-8 * max(1.0, np.abs(v).sum()), (tag, n)
+
+  n_fill = 0
+  while not w.ring.is_full():
+    w.fill_step()
+    n_fill += 1
+  assert n_fill == int(g["n_fill"])
+  check("fill", (0, None))
+  t64 = lambda x: torch.from_numpy(np.asarray(x, np.float64))                 # noqa: E731
+  imgs = lambda states: t64(np.stack([s['image'] for s in states]))           # noqa: E731
+  global_t = 0
+  for it in range(n_proc):
+    lr = O.anneal_learning_rate(float(g["initial_lr"]), global_t, max_t)
+    t0 = w.local_t
+    c0, h0 = net.c.clone(), net.h.clone()                                     # start_lstm_state (trainer.py:228)
+    b = w.process_base()
+    pc, vr, rp = w.process_pc(), w.process_vr(), w.process_rp()
+    ones = lambda n: torch.ones(n, 1, dtype=torch.float64)                    # noqa: E731
+    feed = {"base": dict(images=imgs(b["states"])[:, None], lar=t64(b["lar"])[:, None], a=t64(b["a"])[:, None],
+                         adv=t64(b["adv"])[:, None], R=t64(b["R"])[:, None], mask=ones(len(b["states"])), c0=c0, h0=h0),
+            "pc": dict(images=imgs(pc["states"])[:, None], lar=t64(pc["lar"])[:, None], a=t64(pc["a"])[:, None],
+                       R=t64(pc["R"])[:, None], mask=ones(len(pc["states"]))),
+            "vr": dict(images=imgs(vr["states"])[:, None], lar=t64(vr["lar"])[:, None], R=t64(vr["R"])[:, None],
+                       mask=ones(len(vr["states"]))),
+            "rp": dict(images=imgs(rp["states"])[None], c=t64(rp["c"])[None])}
+    _, _, grads = oracle.loss_and_grads(feed)
+    O.rmsprop_step(vars_, rms, mom, [grads[n].numpy() for n in names], lr, decay=0.99, momentum=0.0, epsilon=0.1,
+                   clip_norm=40.0, dtype=np.float64)
+    steps = w.local_t - t0
+    global_t += steps
+    check("it%d" % it, (steps, b["score"]))
