@@ -256,3 +256,62 @@ def test_rejected_checkpoint_leaves_the_agent_untouched(tmp_path):
   with pytest.raises((pickle.UnpicklingError, RuntimeError, _lib.UnrealError)):
     checkpoint.load(evil, tr2)
   tr.stop(); tr2.stop()
+
+
+def test_single_env_drop_in_agent_follows_the_references_own_trainer():
+  """The drop-in classes on the device (Trainer with num_envs = 1 sharing the caller's RandomState, UnrealModel on the tcgen05
+  path, RMSPropApplier) against tests/golden/agent_reference_golden.npz -- the reference's OWN Trainer.process loop (its
+  model, Experience, maze and RMSPropApplier, run over the TF-1 op shim of tests/golden/make_agent_golden.py): the fill and
+  four learner iterations from the same seeds and initial parameters.  Discrete things must be identical (number of fill
+  calls, steps taken, scores, the agent's cell, the position of the RandomState stream: the bf16 policy has to pick the same
+  action at every one of the 140 draws).  The parameter CHANGE of every variable since the start must agree with the
+  reference's within the bf16 gradient noise (relative L2 over the sampled entries <= 0.25; measured per variable for one
+  gradient in test_gpu_model.py: <= 3 % for 18 variables, 12-17 % for conv1)."""
+  import os
+  from oracle import model_oracle as M
+  from unreal_b200.environment.environment import Environment
+  from unreal_b200.model.model import UnrealModel
+  from unreal_b200.train.rmsprop_applier import RMSPropApplier
+  from unreal_b200.train.trainer import Trainer
+  g = np.load(os.path.join(os.path.dirname(__file__), "golden", "agent_reference_golden.npz"))
+  A, G, seed, net_seed, H, n_proc, max_t = (int(x) for x in g["meta"])
+  Environment.action_size = -1
+  dev = torch.device("cuda", 0)
+  net = UnrealModel(A, G, -1, True, True, True, True, 0.05, 0.001, dev, {'segnet_mode': 0}, (84, 84), True, 0, 0.0, 0.0,
+                    num_envs=1, seed=0)
+  init = {k: v.numpy() for k, v in M.init_params(A, G, seed=net_seed).items()}
+  net.load_vars(init)
+  applier = RMSPropApplier(float(g["initial_lr"]), decay=0.99, momentum=0.0, epsilon=0.1, clip_norm=40.0)
+  rs = np.random.RandomState(seed)
+  tr = Trainer(1, net, float(g["initial_lr"]), None, applier, 'maze', '', True, True, True, True, 0.05, 0.001, 20, 20, 0.99, 0.9,
+               H, max_t, "cuda:0", {'segnet_mode': 0}, (84, 84), True, 0, rs, 50.0, 0.0, 0.0, num_envs=1)
+  tr.prepare()
+
+  def check(tag, ret):
+    assert tr.local_t == int(g[tag + "_local_t"]), tag
+    want = g[tag + "_ret"]
+    assert ret[0] == int(want[0]) and ((ret[1] is None) == bool(np.isnan(want[1]))), (tag, ret, want)
+    assert tuple(int(v) for v in tr.environment.state.pos[0].cpu()) == tuple(int(v) for v in g[tag + "_pos"]), tag
+    probe = np.random.RandomState(); probe.set_state(rs.get_state())
+    assert int(probe.randint(0, 2 ** 31 - 1)) == int(g[tag + "_next_draw"]), tag + ": the RandomState streams have diverged"
+    if tag == "fill":
+      return
+    for name, v in net.named_vars().items():
+      idx = g["idx_" + name]
+      d_ref = g[tag + "_val_" + name] - init[name].reshape(-1)[idx].astype(np.float64)
+      d_got = v.detach().cpu().double().reshape(-1).numpy()[idx] - init[name].reshape(-1)[idx].astype(np.float64)
+      rel = np.linalg.norm(d_got - d_ref) / max(np.linalg.norm(d_ref), 1e-12)
+      assert rel <= 0.25, (tag, name, rel)
+
+  fills = 0
+  while not tr.experience.is_full():
+    assert tr.process(None, 0) == (0, None)
+    fills += 1
+  assert fills == int(g["n_fill"])
+  check("fill", (0, None))
+  global_t = 0
+  for it in range(n_proc):
+    ret = tr.process(None, global_t)
+    global_t += ret[0]
+    check("it%d" % it, ret)
+  tr.stop()
