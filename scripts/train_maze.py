@@ -56,8 +56,8 @@ def run(args, seed, out):
       prev = cur
       now = time.perf_counter()
       final = dict(seed=seed, updates=u, env_steps=env_steps, wall_s=now - t0, episodes=ep,
-                   mean_score=(sc / ep if ep else None), steps_per_episode=(100 * 20 * n / ep if ep else None),
-                   env_steps_per_s=100 * 20 * n / (now - last), lr=frac * args.lr,
+                   mean_score=(sc / ep if ep else None), steps_per_episode=(args.log_every * 20 * n / ep if ep else None),
+                   env_steps_per_s=args.log_every * 20 * n / (now - last), lr=frac * args.lr,
                    total_loss_per_env=float(tr.last_losses["total"]) / n, grad_norm=float(tr.last_losses["grad_norm"]))
       last = now
       out.write(json.dumps(final) + "\n"); out.flush()
