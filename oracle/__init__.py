@@ -14,5 +14,10 @@ container by ``tests/golden/make_golden.py``) stored as fixtures under
 ``model/model.py`` and ``training_ops.apply_rms_prop`` is a third-party
 dependency that is absent from the reference tree (``tensorflow``, version
 unpinned, README.unreal.md:33 says r1.0); for those the published algorithm is
-restated and the reference's own call sites and test vectors anchor it.
+restated and the reference's own call sites and test vectors anchor it: the
+reference's ``model/model.py``, ``train/rmsprop_applier.py`` and ``Trainer.process``
+run UNMODIFIED over ``tests/golden/tf1_shim`` (a TF-1 graph API on torch float64)
+in ``tests/golden/make_model_golden.py`` / ``make_agent_golden.py``, and
+``oracle/model_oracle.py`` + the RMSProp / rollout restatements here reproduce
+their outputs at 1e-9 / 1e-8 (``tests/test_model_oracle.py``).
 """
