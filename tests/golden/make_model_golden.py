@@ -39,7 +39,7 @@ from model.model import UnrealModel  # noqa: E402  (reference, unmodified)
 from train.rmsprop_applier import RMSPropApplier  # noqa: E402  (reference, unmodified)
 from oracle import model_oracle as MO  # noqa: E402
 
-A, G, SEED = 4, 0, 7
+A, G, SEED = 4, 0, 7            # rebound by main(): the maze's action space, then the indoor pointgoal one with its objective
 T_BASE, L_PC, L_VR = 5, 4, 3
 
 
@@ -53,6 +53,8 @@ def lar(rs, n):
   out = np.zeros((n, A + 1 + G), np.float64)
   out[np.arange(n), rs.randint(0, A, size=n)] = 1.0
   out[:, A] = rs.randint(-1, 2, size=n)
+  if G:
+    out[:, A + 1:] = rs.randn(n, G)           # the objective vector (indoor_environment.py: distance / direction to the goal)
   return out
 
 
@@ -62,7 +64,10 @@ def onehot(idx, k):
   return out
 
 
-def main():
+def main(a=4, g=0, seed=7, fname="model_reference_golden.npz"):
+  global A, G, SEED
+  A, G, SEED = a, g, seed
+  tf.reset_default_graph()
   rs = np.random.RandomState(SEED)
   net = UnrealModel(A, G, 0, True, True, True, True, 0.05, 0.001, "/cpu:0", {'segnet_mode': 0}, [84, 84], True, 0, 0.0, 0.0)
   net.prepare_loss()
@@ -159,11 +164,12 @@ def main():
     rms = applier.get_slot(v, "rms").value.numpy().reshape(-1)
     out["upd_rms_" + name] = rms[idx]
   out["meta"] = np.array([A, G, SEED, T_BASE, L_PC, L_VR])
-  path = os.path.join(HERE, "model_reference_golden.npz")
+  path = os.path.join(HERE, fname)
   np.savez_compressed(path, **out)
   print("wrote %s (%d bytes): total_loss %.9f" % (path, os.path.getsize(path), float(out["total_loss"])))
   print({k: float(out[k]) for k in ("policy_loss", "value_loss", "pc_loss", "vr_loss", "rp_loss")})
 
 
 if __name__ == "__main__":
-  main()
+  main()                                                           # the maze: 4 actions, no objective
+  main(3, 2, 8, "model_reference_golden_a3g2.npz")                 # indoor pointgoal: 3 actions + a 2-vector objective

@@ -161,7 +161,8 @@ def test_loss_and_gradients_match_oracle(maze):
         assert err <= gtol, (k, emulate, err)
 
 
-def test_cuda_model_against_vectors_from_the_references_own_model_py():
+@pytest.mark.parametrize("fixture", ["model_reference_golden.npz", "model_reference_golden_a3g2.npz"], ids=["maze-A4", "indoor-A3-G2"])
+def test_cuda_model_against_vectors_from_the_references_own_model_py(fixture):
   """The CUDA model against tests/golden/model_reference_golden.npz DIRECTLY -- vectors produced by the reference's own
   model/model.py (unmodified, over the TF-1 op shim of tests/golden/make_model_golden.py), float64: the acting outputs
   (three run_base_policy_and_value steps with the carried LSTM state, run_base_value, run_pc_q_max, run_vr_value, run_rp_c),
@@ -169,7 +170,7 @@ def test_cuda_model_against_vectors_from_the_references_own_model_py():
   the reference's RMSPropApplier reported.  Tolerances are the bf16 operand rounding of the tensor-core path: 3e-2 relative on
   values and loss terms; gradients: the variable's norm within 1e-1, its 64 sampled entries within 2e-1 (L2, relative)."""
   import os
-  g = np.load(os.path.join(os.path.dirname(__file__), "golden", "model_reference_golden.npz"))
+  g = np.load(os.path.join(os.path.dirname(__file__), "golden", fixture))
   A_, G_, seed, T, Lp, Lv = (int(x) for x in g["meta"])
   from oracle import model_oracle as M
   from unreal_b200.model.model import UnrealModel

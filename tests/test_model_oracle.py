@@ -314,7 +314,11 @@ def test_every_head_against_a_hand_computed_answer():
   assert abs(float(total) - (pol + val + vr + pc + rp)) <= 1e-9 * max(1.0, abs(float(total)))
 
 
-def test_oracle_matches_the_references_model_py():
+import pytest  # noqa: E402
+
+
+@pytest.mark.parametrize("fixture", ["model_reference_golden.npz", "model_reference_golden_a3g2.npz"], ids=["maze-A4", "indoor-A3-G2"])
+def test_oracle_matches_the_references_model_py(fixture):
   """tests/golden/model_reference_golden.npz was produced by the REFERENCE'S OWN model/model.py, imported unmodified and
   executed over tests/golden/tf1_shim (TensorFlow cannot be installed: its ~30 ops on this path are restated from their
   published definitions; the graph building, variable order and reuse, layer wiring, loss formulas and the run_* methods
@@ -323,7 +327,7 @@ def test_oracle_matches_the_references_model_py():
   feed assembled like Trainer.process (trainer.py:500-541) and the gradient of total_loss in all 20 variables
   (rmsprop_applier.py:109-116)."""
   import os
-  g = np.load(os.path.join(os.path.dirname(__file__), "golden", "model_reference_golden.npz"))
+  g = np.load(os.path.join(os.path.dirname(__file__), "golden", fixture))
   A, G, seed, T, Lp, Lv = (int(x) for x in g["meta"])
   p = M.init_params(A, G, seed=seed)
   p = type(p)((k, v.to(torch.float64)) for k, v in p.items())
