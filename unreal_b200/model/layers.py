@@ -249,6 +249,11 @@ class LstmFn(torch.autograd.Function):
     ctx.fused_step = fused_step
     ctx.lstm_in = lstm_in
     ctx.kx = kx
+    ctx.extra = ()
+    if pos is not None:       # the fc1 table as the (zero-padded) bf16 operand of the backward pass's 49-row products
+      table16 = torch.zeros(64, 256, device=dev, dtype=torch.bfloat16)
+      table16[:49].copy_(fc16)
+      ctx.extra = (table16,)
     ctx.save_for_backward(xh, wcat16, gates, c_all, pos)
     return h_all, c_last, h_all[t - 1].clone()
 
@@ -277,6 +282,25 @@ class LstmFn(torch.autograd.Function):
         # 10.3 -> 5.1 us at 1024 envs; at 8192 envs the output's zero fill costs what the split saves)
         dh_rec = K.gemm_bf16(dgates[i], wh, split_k=4 if n <= 2048 else 1)
     dg2 = dgates.view(t * n, 1024)
+    if pos is not None and SEGMENT_SUM_FIRST and kx > lstm_in:
+      # table mode (maze cells): sums over samples commute with the products, so the gate gradients are summed BY CELL first --
+      # as a tensor-core GEMM against the samples' one-hot cell indicator [S,64] (products by 1, fp32 accumulation: the exact
+      # segment sums, one pass over dgates at HBM speed) -- and everything that involves the fc1 columns of the operand is a
+      # 49-row product with those sums:
+      #   d(fc1 table) = gsum . W_x[:256]^T   instead of the [T*N,1024] x [1024,256] GEMM + the segment-sum pass over its result;
+      #   dW_x[:256]   = table^T . gsum       instead of the fc1 half of the [520,T*N] x [T*N,1024] filter-gradient GEMM,
+      # which now only covers the operand's other 264 columns (last action / reward, padding with the ones column, h).
+      (table16,) = ctx.extra
+      cell = (pos[:, 1].to(torch.int64) * 7 + pos[:, 0].to(torch.int64)).clamp_(0, 48)
+      onehot = torch.zeros(t * n, 64, device=dev, dtype=torch.bfloat16)
+      onehot.scatter_(1, cell.view(-1, 1), 1.0)
+      gsum16 = _wgrad(onehot, dg2).to(torch.bfloat16)                                # [64,1024]: rows 49..63 zero
+      dfc = K.gemm_bf16(gsum16, wcat16[:256])[:49].contiguous()                      # [49,256] f32
+      dw_fc = _wgrad(table16, gsum16)                                                # [256,1024] f32
+      drest = _wgrad(xh.view(t * n, kc)[:, 256:], dg2)                               # [kc-256,1024]: lar | padding | h rows
+      dw = torch.cat((dw_fc, drest[:lstm_in - 256], drest[kx - 256:]), dim=0)
+      db = drest[kx - 1 - 256].clone()                                               # the ones column of the operand (forward)
+      return dfc, None, None, dw, db, None, None, None, None, None, None, None
     dwcat = _wgrad(xh.view(t * n, kc), dg2)              # one wgrad over [x, h]: rows of the x part, padding, h part
     dw = torch.cat((dwcat[:lstm_in], dwcat[kx:]), dim=0)
     if kx > lstm_in:
@@ -284,19 +308,8 @@ class LstmFn(torch.autograd.Function):
     else:
       _, db = K.relu_grad(dg2, None, want_out=False)
     # only the 256 fc1 columns carry a gradient (last_action_reward is an input)
-    if pos is not None and SEGMENT_SUM_FIRST:
-      # table mode: the sum by cell commutes with the product, so sum the GATE gradients by cell first -- as a tensor-core
-      # GEMM against the samples' one-hot cell indicator [S,64] (products by 1, fp32 accumulation: the exact segment sums,
-      # one pass over dgates at HBM speed) -- and multiply 49 rows instead of T*N: replaces the [T*N,1024] x [1024,256] GEMM,
-      # its [T*N,256] bf16 result and the segment-sum kernel's pass over it
-      cell = (pos[:, 1].to(torch.int64) * 7 + pos[:, 0].to(torch.int64)).clamp_(0, 48)
-      onehot = torch.zeros(t * n, 64, device=dev, dtype=torch.bfloat16)
-      onehot.scatter_(1, cell.view(-1, 1), 1.0)
-      gsum = _wgrad(onehot, dg2)                                                     # [64,1024] f32
-      dfc = K.gemm_bf16(gsum.to(torch.bfloat16), wcat16[:256])[:49].contiguous()     # [49,256] f32
-    else:
-      dfc = K.gemm_bf16(dg2, wcat16[:256], out_dtype=torch.bfloat16)
-      dfc = dfc.view(t, n, 256) if pos is None else K.cell_segment_sum(dfc, pos)    # table mode: per-cell sums, fp32 [49,256]
+    dfc = K.gemm_bf16(dg2, wcat16[:256], out_dtype=torch.bfloat16)
+    dfc = dfc.view(t, n, 256) if pos is None else K.cell_segment_sum(dfc, pos)      # table mode: per-cell sums, fp32 [49,256]
     return dfc, None, None, dw, db, None, None, None, None, None, None, None
 
 
