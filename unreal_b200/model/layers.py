@@ -282,24 +282,30 @@ class LstmFn(torch.autograd.Function):
         # 10.3 -> 5.1 us at 1024 envs; at 8192 envs the output's zero fill costs what the split saves)
         dh_rec = K.gemm_bf16(dgates[i], wh, split_k=4 if n <= 2048 else 1)
     dg2 = dgates.view(t * n, 1024)
-    if pos is not None and SEGMENT_SUM_FIRST and kx > lstm_in:
+    if pos is not None and SEGMENT_SUM_FIRST and lstm_in - 256 <= 14:
       # table mode (maze cells): sums over samples commute with the products, so the gate gradients are summed BY CELL first --
-      # as a tensor-core GEMM against the samples' one-hot cell indicator [S,64] (products by 1, fp32 accumulation: the exact
-      # segment sums, one pass over dgates at HBM speed) -- and everything that involves the fc1 columns of the operand is a
-      # 49-row product with those sums:
-      #   d(fc1 table) = gsum . W_x[:256]^T   instead of the [T*N,1024] x [1024,256] GEMM + the segment-sum pass over its result;
-      #   dW_x[:256]   = table^T . gsum       instead of the fc1 half of the [520,T*N] x [T*N,1024] filter-gradient GEMM,
-      # which now only covers the operand's other 264 columns (last action / reward, padding with the ones column, h).
+      # as a tensor-core GEMM against an indicator matrix P [S,64] = [one-hot cell (49) | last action / reward columns of the
+      # operand | 1 | 0 ...] (products by 0 / 1 / the operand's own bf16 values, fp32 accumulation; one pass over dgates at
+      # HBM speed) -- and everything that involves the operand's x columns comes out of that one [64,1024] result R:
+      #   d(fc1 table) = R[:49] . W_x[:256]^T    instead of the [T*N,1024] x [1024,256] GEMM + the segment-sum pass over its result;
+      #   dW_x[:256]   = table^T . R[:49]        instead of the fc1 half of the [520,T*N] x [T*N,1024] filter-gradient GEMM;
+      #   dW_x[256:]   = R[49:49+nl],  db = R[49+nl]   (the last-action / reward rows and the bias);
+      # the big filter-gradient GEMM is left with the 256 h columns: exactly two 128-row tiles.
       (table16,) = ctx.extra
+      nl = lstm_in - 256
+      xh2 = xh.view(t * n, kc)
       cell = (pos[:, 1].to(torch.int64) * 7 + pos[:, 0].to(torch.int64)).clamp_(0, 48)
-      onehot = torch.zeros(t * n, 64, device=dev, dtype=torch.bfloat16)
-      onehot.scatter_(1, cell.view(-1, 1), 1.0)
-      gsum16 = _wgrad(onehot, dg2).to(torch.bfloat16)                                # [64,1024]: rows 49..63 zero
+      ind = torch.zeros(t * n, 64, device=dev, dtype=torch.bfloat16)
+      ind.scatter_(1, cell.view(-1, 1), 1.0)
+      ind[:, 49:49 + nl].copy_(xh2[:, 256:lstm_in])
+      ind[:, 49 + nl].fill_(1.0)
+      r = _wgrad(ind, dg2)                                                           # [64,1024] f32
+      gsum16 = r.to(torch.bfloat16)
       dfc = K.gemm_bf16(gsum16, wcat16[:256])[:49].contiguous()                      # [49,256] f32
-      dw_fc = _wgrad(table16, gsum16)                                                # [256,1024] f32
-      drest = _wgrad(xh.view(t * n, kc)[:, 256:], dg2)                               # [kc-256,1024]: lar | padding | h rows
-      dw = torch.cat((dw_fc, drest[:lstm_in - 256], drest[kx - 256:]), dim=0)
-      db = drest[kx - 1 - 256].clone()                                               # the ones column of the operand (forward)
+      dw_fc = _wgrad(table16, gsum16)                                                # [256,1024] f32 (table rows 49..63 are zero)
+      dw_h = _wgrad(xh2[:, kx:], dg2)                                                # [256,1024] f32
+      dw = torch.cat((dw_fc, r[49:49 + nl], dw_h), dim=0)
+      db = r[49 + nl].clone()
       return dfc, None, None, dw, db, None, None, None, None, None, None, None
     dwcat = _wgrad(xh.view(t * n, kc), dg2)              # one wgrad over [x, h]: rows of the x part, padding, h part
     dw = torch.cat((dwcat[:lstm_in], dwcat[kx:]), dim=0)
