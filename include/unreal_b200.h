@@ -294,6 +294,13 @@ int unreal_lstm_cell_fwd_g16(void* gates_bf16, const float* c_prev, float* c_out
                              int n, void* stream);
 int unreal_lstm_cell_act_g16(const void* gates_bf16, float* c_state, float* h_state, float* h_out, const uint8_t* active,
                              int n, void* stream);
+/* unreal_lstm_cell_act_g16 + the acting heads of unreal_a3c_head_loss (model.py:343-377 for one step, run_base_policy_and_value
+ * :630-660) in one launch: the warp that computes an env's row of h also reduces softmax(h . Wp + bp) -> pi_out [N,A] and
+ * h . Wv + bv -> v_out [N]; wp f32 [256,A], wv f32 [256], a in 1..7.  Inactive envs keep c / h and report the heads of
+ * the h they hold. */
+int unreal_lstm_cell_act_heads(const void* gates_bf16, float* c_state, float* h_state, const uint8_t* active, int n,
+                               const float* wp, const float* bp, const float* wv, const float* bv, int a, float* pi_out,
+                               float* v_out, void* stream);
 int unreal_lstm_cell_bwd_g16(const void* gates_act_bf16, const float* c_prev, const float* c, const float* dh,
                              const float* dh_rec, float* dc, void* dgates_bf16, int n, void* stream);
 /* One LSTM step as ONE launch: the step GEMM over [x_t, h_{t-1}] with the BasicLSTMCell arithmetic in its epilogue

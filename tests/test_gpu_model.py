@@ -140,6 +140,36 @@ def test_acting_helpers_match_oracle():
   assert float(m.base_lstm_state_out[0][0].abs().max()) == 0 and float(m.base_lstm_state_out[0][1].abs().max()) > 0
 
 
+@pytest.mark.parametrize("n,a", [(1, 4), (77, 3), (4099, 7)])
+def test_acting_cell_with_the_heads_inside_equals_cell_then_heads(n, a):
+  """unreal_lstm_cell_act_heads (the acting step's cell + policy / value heads in one launch) against unreal_lstm_cell_act_g16
+  followed by the head kernel: the same state update bit for bit (active rows advanced, inactive rows untouched), the same
+  pi / v to fp32 summation order, also for the inactive rows (heads of the h they hold)."""
+  from unreal_b200 import kernels as K
+  dev = torch.device("cuda", 0)
+  g = torch.Generator(device=dev).manual_seed(n + a)
+  gates = torch.randn(n, 1024, device=dev, generator=g).to(torch.bfloat16)
+  c0 = torch.randn(n, 256, device=dev, generator=g); h0 = torch.randn(n, 256, device=dev, generator=g) * 0.5
+  wp = torch.randn(256, a, device=dev, generator=g) * 0.1; bp = torch.randn(a, device=dev, generator=g) * 0.1
+  wv = torch.randn(256, device=dev, generator=g) * 0.1; bv = torch.randn(1, device=dev, generator=g)
+  act = (torch.rand(n, device=dev, generator=g) < 0.7).to(torch.uint8)
+  for active in (None, act):
+    c1, h1 = c0.clone(), h0.clone()
+    hout = torch.empty(n, 256, device=dev)
+    K.lstm_cell_act(gates, c1, h1, hout, active)
+    ref = K.a3c_head(hout, wp, bp, wv, bv, want_pi=True, want_v=True)
+    c2, h2 = c0.clone(), h0.clone()
+    vrow = torch.full((n,), -7.0, device=dev)
+    pi, v = K.lstm_cell_act_heads(gates, c2, h2, wp, bp, wv, bv, active, v_out=vrow)
+    assert v.data_ptr() == vrow.data_ptr()
+    assert torch.equal(c1, c2) and torch.equal(h1, h2)
+    if active is not None:
+      keep = act == 0
+      assert torch.equal(c2[keep], c0[keep]) and torch.equal(h2[keep], h0[keep])
+    assert torch.allclose(pi, ref["pi"], rtol=1e-5, atol=1e-6) and torch.allclose(v, ref["v"], rtol=1e-5, atol=1e-5)
+    assert torch.allclose(pi.sum(-1), torch.ones(n, device=dev), atol=1e-5)
+
+
 @pytest.mark.parametrize("maze", [False, True])
 def test_loss_and_gradients_match_oracle(maze):
   dev = torch.device("cuda", 0)

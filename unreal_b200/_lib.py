@@ -86,6 +86,7 @@ SIGNATURES = {
     "unreal_lstm_cell_act": (c_int, [P, P, P, P, P, c_int, P]),
     "unreal_lstm_cell_fwd_g16": (c_int, [P, P, P, P, P, c_int, c_int, P]),
     "unreal_lstm_cell_act_g16": (c_int, [P, P, P, P, P, c_int, P]),
+    "unreal_lstm_cell_act_heads": (c_int, [P, P, P, P, c_int, P, P, P, P, c_int, P, P, P]),
     "unreal_lstm_cell_bwd_g16": (c_int, [P, P, P, P, P, P, P, c_int, P]),
     "unreal_lstm_step_fwd": (c_int, [P, c_int64, P, P, P, P, P, P, P, c_int, P, P, c_int, c_int, c_int, P]),
     "unreal_lstm_step_bwd": (c_int, [P, P, c_int64, P, P, P, P, P, P, P, c_int, c_int, P]),

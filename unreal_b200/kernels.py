@@ -986,6 +986,19 @@ def rollout_post(reward, terminal, frame_rec, active, ended, last_rec, episode_r
        ptr(lstm_h, torch.float32, "lstm_h"), ptr(stats, torch.float64, "stats"), stream_ptr())
 
 
+def lstm_cell_act_heads(gates, c_state, h_state, wp, bp, wv, bv, active=None, v_out=None):
+  """Acting step of the cell + the policy / value heads in one launch: gates bf16 [N,1024], state f32 [N,256] in place for
+  the active envs; wp [256,A], bp [A], wv [256], bv [1] f32 -> (pi f32 [N,A], v f32 [N]; v_out: a caller-owned [N] row)."""
+  n, a = gates.shape[0], wp.shape[1]
+  pi = torch.empty(n, a, dtype=torch.float32, device=gates.device)
+  v = torch.empty(n, dtype=torch.float32, device=gates.device) if v_out is None else v_out
+  call("unreal_lstm_cell_act_heads", ptr(gates, torch.bfloat16, "gates"), ptr(c_state, torch.float32, "c_state"),
+       ptr(h_state, torch.float32, "h_state"), ptr(active, torch.uint8, "active"), n, ptr(wp, torch.float32, "wp"),
+       ptr(bp, torch.float32, "bp"), ptr(wv, torch.float32, "wv"), ptr(bv, torch.float32, "bv"), a, ptr(pi, torch.float32),
+       ptr(v, torch.float32, "v_out"), stream_ptr())
+  return pi, v
+
+
 def lstm_cell_act(gates, c_state, h_state, h_out=None, active=None):
   """Acting step of the cell, in place on the persistent state of the active envs; h_out receives the state's h."""
   n = gates.shape[0]

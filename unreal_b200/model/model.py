@@ -103,6 +103,10 @@ class UnrealModel(object):
     # pc_fc1's ReLU / bias gradient in the epilogue of the pixel-control head's backward convolution (PcTowerFusedFn; False:
     # a unreal_relu_grad pass over the dense [S,2592] gradient between the two autograd nodes)
     self.fused_pc_relu = True
+    # acting step: the policy / value heads inside the LSTM cell kernel (unreal_lstm_cell_act_heads) instead of a separate head
+    # kernel reading h back.  OFF: measured at 8192 envs the fused kernel takes 19.4 us against 12.8 (cell) + 8.7 (heads) inside
+    # the captured data phase -- no gain (scripts/act_heads_bench.py); kept as a tested option
+    self.fused_act_heads = False
     # ... and the layout of the loss gradient between the fused deconv + loss kernel and the two backward kernels: "planes"
     # (four parity planes of 8 channels, one bulk copy per sample), "c8" ([S,400,8]) or "c16" (conv2's geometry, zero padded)
     self.pc_grad_layout = "planes"
@@ -396,6 +400,11 @@ class UnrealModel(object):
         img = self._images(s_t)
         n = img.shape[1]
         gates = self._step_gates(p32, img[0], self._lar(last_action_reward, n)[0], self._lstm_h)
+        if self.fused_heads and self.fused_act_heads and gates.dtype == torch.bfloat16 and self._action_size <= 7:
+          # the cell and the heads in one launch: the warp that computes an env's h reduces its logits and value as well
+          pi, v = K.lstm_cell_act_heads(gates, self._lstm_c, self._lstm_h, p32["W_base_fc_p"].contiguous(), p32["b_base_fc_p"],
+                                        p32["W_base_fc_v"].reshape(256).contiguous(), p32["b_base_fc_v"], active, v_out)
+          return pi, v, None
         h = torch.empty(n, 256, device=self._device)
         K.lstm_cell_act(gates, self._lstm_c, self._lstm_h, h, active)      # in place on the state of the active envs
         pi, v = self._policy_value(p32, h, v_out)
