@@ -20,6 +20,15 @@ def timed(fn, reps=50):
   for _ in range(reps): fn()
   e.record(); torch.cuda.synchronize()
   return round(s.elapsed_time(e) * 1e3 / reps, 2)
-full = timed(lambda: K.lstm_step_fwd(xh[0], w, b, c0, c1, h_out=h, h16_out=xh[1, :, kx:], acts=acts, tiled=True))
-half = timed(lambda: K.lstm_step_fwd(xh[0, :, kx:], w[kx:], b, c0, c1, h_out=h, h16_out=xh[1, :, kx:], acts=acts, tiled=True))
-print(json.dumps({"envs": n, "k520_us": full, "k256_us": half}))
+f_full = lambda: K.lstm_step_fwd(xh[0], w, b, c0, c1, h_out=h, h16_out=xh[1, :, kx:], acts=acts, tiled=True)
+f_half = lambda: K.lstm_step_fwd(xh[0, :, kx:], w[kx:], b, c0, c1, h_out=h, h16_out=xh[1, :, kx:], acts=acts, tiled=True)
+hc = xh[0, :, kx:].contiguous(); wc = w[kx:].contiguous()
+f_half_c = lambda: K.lstm_step_fwd(hc, wc, b, c0, c1, h_out=h, h16_out=xh[1, :, kx:], acts=acts, tiled=True)
+res = {"envs": n}
+for name, fn in (("k520", f_full), ("k256_view", f_half), ("k256_contiguous", f_half_c), ("k520_again", f_full)):
+  res[name + "_eager_us"] = timed(fn)
+  gr = torch.cuda.CUDAGraph()
+  with torch.cuda.graph(gr):
+    for _ in range(20): fn()
+  res[name + "_graph_us"] = round(timed(gr.replay, reps=10) / 20, 2)
+print(json.dumps(res))
