@@ -1,6 +1,6 @@
 """Small single-kernel workloads for `ncu --set full` captures (one GPU, a handful of launches).
 
-    python scripts/ncu_targets.py k2u8 | k2f32 | k1u8w | k1f32w | k1u8 | k4 | rp | conv2bwd | gemm2sm | lstm [envs] | lstmfused [envs] | pcfc1 | pcplanes
+    python scripts/ncu_targets.py k2u8 | k2f32 | k1u8w | k1f32w | k1u8 | k4 | rp | conv2bwd | gemm2sm | lstm [envs] | lstmfused [envs] | pcfc1 | pcplanes | pctargets
 
 Each target runs its kernel three times on the benchmark's shapes; select the kernel with `-k regex:...`.
 """
@@ -108,6 +108,16 @@ elif which == "pcplanes":
     loss, dyp, db8 = K.pc_deconv_loss(hp, m.pc_taps, m.pc_b8, act, tgt, msk, A, 0.05, planes=True)
     K.pc_planes_conv(dyp, m.pc_w_planes, hp, scale=sc)
     K.pc_planes_wgrad(dyp, hp)
+elif which == "pctargets":
+  # Trainer._process_pc's one-pass target kernel at the agent's size (T = 20, N = 8192)
+  T, N = 20, 8192
+  p0 = torch.randint(0, 7, (T, N, 2), device=dev, generator=g, dtype=torch.int32)
+  p1 = (p0 + torch.randint(-1, 2, (T, N, 2), device=dev, generator=g, dtype=torch.int32)).clamp_(0, 6)
+  boot = torch.rand(N, 20, 20, device=dev, generator=g)
+  ln = torch.full((N,), T, device=dev, dtype=torch.int32)
+  out = torch.empty(T, N, 20, 20, device=dev)
+  for _ in range(3):
+    K.maze_pc_targets(p0, p1, ln, boot, 0.9, out=out)
 else:
   raise SystemExit("unknown target " + which)
 torch.cuda.synchronize()
